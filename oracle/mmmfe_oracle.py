@@ -1,0 +1,765 @@
+"""CPU oracle for the interface-GMRES hot path of MMMFE-ST-DD.
+
+TEST INFRASTRUCTURE ONLY.  This file is a NumPy/SciPy restatement of the reference
+algorithm (space-time multiscale mortar mixed FE domain decomposition for
+``c0 p_t + div u = f, u = -K grad p`` with RT0 x DGQ0 subdomains, backward Euler
+and a Legendre mortar space on the space-time interfaces).  It is the checker for
+the CUDA path; nothing in the product (``mmmfe-st-dd_b200/``) may import it.  Only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs do.
+
+Parity status: the reference itself cannot be built here (deal.II, MPI and UMFPACK
+are absent).  The oracle is pinned against the only golden numbers the reference
+publishes -- ``report.pdf`` Tables 2 and 4 (GMRES counts and four relative error
+columns, 4 significant digits; ``tests/golden/report_tables.json``) -- see
+``tests/test_oracle_golden.py``.  Beyond those 4 digits parity is unpinned.
+
+Third-party arithmetic the reference delegates to and that is restated here from
+its published definition (none of it is under /root/reference):
+  * deal.II (>= 8.4 requested by CMakeLists.txt:23, 9.5.2 named by README.md:42,
+    unpinned): FE_RaviartThomas(0)/FE_DGQ(0) on rectangles, QGauss, QIterated
+    (QTrapezoid), FEFieldFunction point evaluation, VectorTools::project,
+    integrate_difference.
+  * UMFPACK through SparseDirectUMFPACK (unpinned): replaced by SciPy's SuperLU.
+
+Every function cites the reference file:line it follows (paths relative to
+/root/reference).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+# side index convention of the reference: 0 bottom, 1 right, 2 top, 3 left
+# (boundary_id - 1, inc/utilities.h:329-375)
+BOTTOM, RIGHT, TOP, LEFT = 0, 1, 2, 3
+# outward normal sign relative to the positive coordinate direction
+# (get_normal_direction, inc/utilities.h:79-91)
+NORMAL_SIGN = (-1.0, 1.0, 1.0, -1.0)
+OPPOSITE = (TOP, LEFT, BOTTOM, RIGHT)
+
+
+# ----------------------------------------------------------------------------------------
+# problem data (inc/data.h)
+# ----------------------------------------------------------------------------------------
+class DataDefault:
+    """inc/data.h:28-231.  p = sin(8t) sin(11x) cos(11y - 3.1415/4), K = I.
+
+    The 4-digit pi is the reference's (inc/data.h:101,134,136,167-169,226).
+    """
+
+    PI4 = 3.1415 / 4
+
+    def k_inverse(self, x, y):
+        """inc/data.h:40-62: returns (k00, k01, k10, k11) arrays."""
+        one = np.ones_like(x)
+        zero = np.zeros_like(x)
+        return one, zero, zero, one
+
+    def rhs(self, x, y, t):
+        """RightHandSidePressure::value, inc/data.h:90-105 (c0, alpha unused there)."""
+        s = np.sin(11 * x) * np.cos(11 * y - self.PI4)
+        return 8 * math.cos(8 * t) * s + math.sin(8 * t) * 242 * s
+
+    def pressure_bc(self, x, y, t):
+        """PressureBoundaryValues<2>::value, inc/data.h:121-140 (t may be an array: dim==3 branch)."""
+        return np.sin(8 * t) * np.sin(11 * x) * np.cos(11 * y - self.PI4)
+
+    def exact(self, x, y, t):
+        """ExactSolution::vector_value, inc/data.h:154-172."""
+        u1 = -np.sin(8 * t) * 11 * np.cos(11 * x) * np.cos(11 * y - self.PI4)
+        u2 = np.sin(8 * t) * 11 * np.sin(11 * x) * np.sin(11 * y - self.PI4)
+        p = np.sin(8 * t) * np.sin(11 * x) * np.cos(11 * y - self.PI4)
+        return u1, u2, p
+
+    def initial_pressure(self, x, y):
+        """InitialCondition::vector_value, inc/data.h:213-231 (t = 0)."""
+        return math.sin(0.0) * np.sin(11 * x) * np.cos(11 * y - self.PI4)
+
+
+# ----------------------------------------------------------------------------------------
+# parameter.txt (inc/filecheck_utility.h:34-95)
+# ----------------------------------------------------------------------------------------
+@dataclass
+class Params:
+    c0: float = 1.0
+    alpha: float = 1.0
+    space_degree: int = 0
+    mortar_degree: int = 1
+    num_refinement: int = 2
+    final_time: float = 0.5
+    tolerance: float = 1e-6
+    max_iteration: int = 500
+    need_plot_each_step: bool = False
+    bc_type: List[str] = field(default_factory=lambda: ["D", "D", "D", "D"])  # left,bottom,right,top
+    bc_value: List[float] = field(default_factory=lambda: [0.0, 0.0, 0.0, 0.0])
+    is_manufact: bool = True
+    mesh: List[List[int]] = field(default_factory=list)  # n_subdomains+1 rows of (nx, ny, nt); last = mortar
+
+
+def count_subdomains(path: str) -> int:
+    """Number of ``mesh_pattern_sub_d*`` lines: replaces the MPI rank count (darcy_main.cc:53-56)."""
+    n = 0
+    with open(path) as fh:
+        for line in fh:
+            if line.strip().startswith("mesh_pattern_sub_d"):
+                n += 1
+    return n
+
+
+def parse_parameter_file(path: str, n_processes: Optional[int] = None) -> Params:
+    """Positional parse, key names ignored (inc/filecheck_utility.h:44-84)."""
+    if n_processes is None:
+        n_processes = count_subdomains(path)
+    with open(path) as fh:
+        lines = fh.read().split("\n")
+    toks: List[str] = []
+    for line in lines[4:]:
+        toks.extend(line.split())
+    it = iter(toks)
+
+    def nxt():
+        next(it)  # dummy key
+        return next(it)
+
+    p = Params()
+    p.c0 = float(nxt())
+    p.alpha = float(nxt())
+    p.space_degree = int(nxt())
+    p.mortar_degree = int(nxt())
+    p.num_refinement = int(nxt())
+    p.final_time = float(nxt())
+    p.tolerance = float(nxt())
+    p.max_iteration = int(nxt())
+    p.need_plot_each_step = bool(int(nxt()))
+    p.bc_type, p.bc_value = [], []
+    for _ in range(4):
+        p.bc_type.append(nxt())
+        p.bc_value.append(float(next(it)))
+    for b in p.bc_type:
+        if b not in ("D", "N"):
+            raise ValueError("incompatible boundary condition read from parameter file")
+    p.is_manufact = bool(int(nxt()))
+    p.mesh = []
+    for _ in range(n_processes + 1):
+        next(it)
+        p.mesh.append([int(next(it)), int(next(it)), int(next(it))])
+    return p
+
+
+# ----------------------------------------------------------------------------------------
+# topology (inc/utilities.h:93-306)
+# ----------------------------------------------------------------------------------------
+def find_divisors(n: int):
+    """find_2_divisors, inc/utilities.h:94-110."""
+    tmp = math.floor(math.sqrt(n))
+    while n % tmp != 0:
+        tmp -= 1
+    return n // tmp, tmp
+
+
+def find_neighbors(r: int, n0: int, n1: int):
+    """find_neighbors dim==2, inc/utilities.h:183-205, 297-305.  Order bottom,right,top,left."""
+    nb = [r - n0, r + 1, r + n0, r - 1]
+    if r % n0 == 0:
+        nb[3] = -1
+    if (r + 1) % n0 == 0:
+        nb[1] = -1
+    return [(-1 if (v < 0 or v >= n0 * n1) else v) for v in nb]
+
+
+def gauss01(n: int):
+    """QGauss<1>(n) on [0,1]."""
+    x, w = np.polynomial.legendre.leggauss(n)
+    return 0.5 * (x + 1.0), 0.5 * w
+
+
+def legendre01(k: int, xi):
+    """Orthonormal Legendre polynomials on [0,1] up to degree k (deal.II Polynomials::Legendre).
+
+    Returns array (k+1, len(xi)).
+    """
+    xi = np.asarray(xi, dtype=float)
+    out = np.empty((k + 1,) + xi.shape)
+    s = 2.0 * xi - 1.0
+    for a in range(k + 1):
+        c = np.zeros(a + 1)
+        c[a] = 1.0
+        out[a] = math.sqrt(2 * a + 1.0) * np.polynomial.legendre.legval(s, c)
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# one subdomain: mesh, dofs, matrix, right-hand sides
+# ----------------------------------------------------------------------------------------
+class Subdomain:
+    """One rank of the reference = one rectangular subdomain (src/darcy_vtdd.cc:2082-2103).
+
+    Canonical dof order (ours; every compared quantity is permutation invariant):
+    x-edges (i=0..nx, j=0..ny-1) at j*(nx+1)+i, then y-edges (i=0..nx-1, j=0..ny) at
+    nxe + j*nx + i, then cells at nf + j*nx + i.  A flux dof is the flux integral
+    through its edge in the positive coordinate direction (deal.II RT0 + Piola).
+    """
+
+    def __init__(self, r, n0, n1, nx, ny, nt, prm: Params, data):
+        self.r = r
+        self.ix, self.iy = r % n0, r // n0
+        self.Lx, self.Ly = 1.0 / n0, 1.0 / n1
+        # get_subdomain_coordinates, inc/utilities.h:152-157
+        self.x0, self.y0 = self.ix * self.Lx, self.Ly * math.floor(r / n0)
+        self.nx, self.ny, self.nt = nx, ny, nt
+        self.hx, self.hy = self.Lx / nx, self.Ly / ny
+        self.dt = prm.final_time / float(nt)  # src/darcy_vtdd.cc:2083
+        self.c0 = prm.c0
+        self.nxe, self.nye = (nx + 1) * ny, nx * (ny + 1)
+        self.nf, self.np = self.nxe + self.nye, nx * ny
+        self.n = self.nf + self.np
+        self.neighbors = find_neighbors(r, n0, n1)
+        self.data = data
+        i = np.arange(nx)
+        j = np.arange(ny)
+        self.side_edges = [
+            self.nxe + i,  # bottom: y-edges (i, 0)
+            j * (nx + 1) + nx,  # right: x-edges (nx, j)
+            self.nxe + ny * nx + i,  # top: y-edges (i, ny)
+            j * (nx + 1),  # left: x-edges (0, j)
+        ]
+        self.n_side = [nx, ny, nx, ny]
+        self.edge_len = [self.hx, self.hy, self.hx, self.hy]
+
+    # -- geometry helpers -------------------------------------------------------------
+    def cell_ij(self):
+        jj, ii = np.meshgrid(np.arange(self.ny), np.arange(self.nx), indexing="ij")
+        return ii.ravel(), jj.ravel()
+
+    def side_points(self, side, xi):
+        """Physical points on the edges of a side at local abscissae xi: arrays (n_side, nq)."""
+        m = np.arange(self.n_side[side])[:, None]
+        if side in (BOTTOM, TOP):
+            x = self.x0 + (m + xi[None, :]) * self.hx
+            y = np.full_like(x, self.y0 if side == BOTTOM else self.y0 + self.Ly)
+        else:
+            y = self.y0 + (m + xi[None, :]) * self.hy
+            x = np.full_like(y, self.x0 if side == LEFT else self.x0 + self.Lx)
+        return x, y
+
+    # -- matrix -----------------------------------------------------------------------
+    def assemble_matrix(self):
+        """assemble_system, src/darcy_vtdd.cc:401-484: [[A, -B^T], [dt B, c0 M]], 2x2 Gauss (QGauss(degree+2))."""
+        nx, ny, hx, hy = self.nx, self.ny, self.hx, self.hy
+        ii, jj = self.cell_ij()
+        xl = ii * (nx + 1) * 0 + jj * (nx + 1) + ii  # left x-edge
+        xr = xl + 1
+        yb = self.nxe + jj * nx + ii
+        yt = yb + nx
+        cell = self.nf + jj * nx + ii
+        loc = np.stack([xl, xr, yb, yt], axis=1)  # (ncell, 4)
+        g, w = gauss01(2)
+        gx, gy = np.meshgrid(g, g, indexing="ij")
+        wq = (w[:, None] * w[None, :]).ravel()
+        gx, gy = gx.ravel(), gy.ravel()
+        # basis values at quadrature points (vector field, flux-integral normalised)
+        # x-left: ((1-xi)/hy, 0); x-right: (xi/hy, 0); y-bottom: (0,(1-eta)/hx); y-top: (0, eta/hx)
+        phi = np.zeros((4, 2, gx.size))
+        phi[0, 0] = (1 - gx) / hy
+        phi[1, 0] = gx / hy
+        phi[2, 1] = (1 - gy) / hx
+        phi[3, 1] = gy / hx
+        xq = self.x0 + (ii[:, None] + gx[None, :]) * hx
+        yq = self.y0 + (jj[:, None] + gy[None, :]) * hy
+        k00, k01, k10, k11 = self.data.k_inverse(xq, yq)
+        kin = np.stack([np.stack([k00, k01], -1), np.stack([k10, k11], -1)], -2)  # (ncell,nq,2,2)
+        jxw = wq * hx * hy
+        # A_loc[c,a,b] = sum_q jxw phi_a . Kinv phi_b
+        a_loc = np.einsum("q,adq,cqde,beq->cab", jxw, phi, kin, phi)
+        rows = np.repeat(loc, 4, axis=1).ravel()
+        cols = np.tile(loc, (1, 4)).ravel()
+        vals = a_loc.reshape(-1)
+        div = np.array([-1.0, 1.0, -1.0, 1.0])  # integral of div phi over the cell
+        # flux row, pressure col: -phi_p * div_phi_u -> -div
+        rows = np.concatenate([rows, loc.ravel()])
+        cols = np.concatenate([cols, np.repeat(cell, 4)])
+        vals = np.concatenate([vals, np.tile(-div, cell.size)])
+        # pressure row, flux col: dt * div
+        rows = np.concatenate([rows, np.repeat(cell, 4)])
+        cols = np.concatenate([cols, loc.ravel()])
+        vals = np.concatenate([vals, np.tile(self.dt * div, cell.size)])
+        # pressure-pressure: c0 |c|
+        rows = np.concatenate([rows, cell])
+        cols = np.concatenate([cols, cell])
+        vals = np.concatenate([vals, np.full(cell.size, self.c0 * hx * hy)])
+        mat = sp.coo_matrix((vals, (rows, cols)), shape=(self.n, self.n)).tocsc()
+        mat.sum_duplicates()
+        return mat
+
+    def factorize(self):
+        """A_direct.initialize, src/darcy_vtdd.cc:483 (UMFPACK there, SuperLU here)."""
+        self.matrix = self.assemble_matrix()
+        self.lu = spla.splu(self.matrix)
+
+    # -- right-hand sides -----------------------------------------------------------------
+    def project_initial_condition(self):
+        """VectorTools::project(IC, QGauss(degree+5)), src/darcy_vtdd.cc:2172-2176: DGQ0 -> cell mean."""
+        g, w = gauss01(5)
+        gx, gy = np.meshgrid(g, g, indexing="ij")
+        wq = (w[:, None] * w[None, :]).ravel()
+        ii, jj = self.cell_ij()
+        xq = self.x0 + (ii[:, None] + gx.ravel()[None, :]) * self.hx
+        yq = self.y0 + (jj[:, None] + gy.ravel()[None, :]) * self.hy
+        return (self.data.initial_pressure(xq, yq) * wq[None, :]).sum(axis=1)
+
+    def rhs_bar(self, t, p_old, qdegree, prm: Params):
+        """assemble_rhs_bar, src/darcy_vtdd.cc:632-766 (manufactured: all outer sides Dirichlet, 210, 271-273)."""
+        rhs = np.zeros(self.n)
+        g, w = gauss01(2)
+        gx, gy = np.meshgrid(g, g, indexing="ij")
+        wq = (w[:, None] * w[None, :]).ravel()
+        ii, jj = self.cell_ij()
+        xq = self.x0 + (ii[:, None] + gx.ravel()[None, :]) * self.hx
+        yq = self.y0 + (jj[:, None] + gy.ravel()[None, :]) * self.hy
+        f = self.data.rhs(xq, yq, t)
+        area = self.hx * self.hy
+        rhs[self.nf:] = (self.dt * f + self.c0 * p_old[:, None]) @ (wq * area)  # :718-720
+        xg, wg = gauss01(qdegree)  # face_quadrature_formula(qdegree), :639
+        for side in range(4):
+            if self.neighbors[side] >= 0:
+                continue
+            x, y = self.side_points(side, xg)
+            if prm.is_manufact:
+                gval = self.data.pressure_bc(x, y, t)
+            else:
+                if prm.bc_type[_side_to_bc(side)] != "D":
+                    continue
+                gval = np.full_like(x, _dirichlet_constant(prm, side))
+            rhs[self.side_edges[side]] += -NORMAL_SIGN[side] * (gval @ wg)  # :748-751
+        return rhs
+
+    def rhs_star(self, lam_bar, p_old, first):
+        """assemble_rhs_star, src/darcy_vtdd.cc:769-855.  lam_bar[side] = (2-D interface dof)/|e|."""
+        rhs = np.zeros(self.n)
+        if not first:
+            rhs[self.nf:] = self.c0 * self.hx * self.hy * p_old  # :809-826
+        for side in range(4):
+            if self.neighbors[side] >= 0:
+                rhs[self.side_edges[side]] += -NORMAL_SIGN[side] * lam_bar[side]  # :840-844
+        return rhs
+
+
+def _side_to_bc(side):
+    # parameter.txt order is left, bottom, right, top (boundary ids 101..104, src/darcy_vtdd.cc:215)
+    return {LEFT: 0, BOTTOM: 1, RIGHT: 2, TOP: 3}[side]
+
+
+def _dirichlet_constant(prm: Params, side):
+    # the top constant wrongly reads entry [1] (src/darcy_vtdd.cc:673)
+    return {LEFT: prm.bc_value[0], BOTTOM: prm.bc_value[1], RIGHT: prm.bc_value[2], TOP: prm.bc_value[1]}[side]
+
+
+# ----------------------------------------------------------------------------------------
+# space-time mortar projector as two explicit sampling operators
+# ----------------------------------------------------------------------------------------
+# Tie rule for a Gauss point that lies exactly on a cell boundary of the sampled mesh, per
+# direction: "lower" = lower cell in space / earlier level in time.  FEFieldFunction
+# (inc/utilities.h:484) picks one adjacent cell; report.pdf Table 4 row 1 is reproduced only by
+# lower/lower (the other three choices give 6.92e-01...7.15e-01 instead of 6.810e-01).
+TIE_RULE = {"space": "lower", "time": "lower"}
+
+
+def _locate(u, rule="lower"):
+    """Cell index of coordinate u (in units of cells); ties resolved by ``rule``."""
+    r = np.rint(u)
+    tie = np.abs(u - r) < 1e-9
+    idx = np.where(tie, r - 1 if rule == "lower" else r, np.floor(u)).astype(np.int64)
+    return np.maximum(idx, 0)
+
+
+def projector_tables(sd: Subdomain, side: int, mortar, k: int):
+    """Tables of project_mortar (inc/utilities.h:471-505; inc/projector.h:150-207, 445-524) for one side.
+
+    Fine trace layout: U[level*n_side + m] (src/darcy_vtdd.cc:1015, 1030), values = 2-D flux dofs.
+    Mortar layout: ((ft*ms + fs)*(k+1) + b)*(k+1) + a with a the spatial, b the temporal degree.
+    Returns (F2C, C2F) as CSR; C2F yields lam_bar = (2-D interface dof)/|e| directly.
+    """
+    mnx, mny, mnt = mortar
+    ms = mnx if side in (BOTTOM, TOP) else mny
+    ns, nt = sd.n_side[side], sd.nt
+    nq = k + 1
+    xi, w = gauss01(nq)
+    leg = legendre01(k, xi)  # (k+1, nq)
+    nd = nq * nq
+    # ---- f2c: Gauss points of every mortar face sample the fine piecewise-constant flux
+    fs = np.arange(ms)
+    ft = np.arange(mnt)
+    m_of = _locate((fs[:, None] + xi[None, :]) / ms * ns, TIE_RULE["space"])  # (ms, nq)
+    m_of = np.minimum(m_of, ns - 1)
+    l_of = _locate((ft[:, None] + xi[None, :]) / mnt * nt, TIE_RULE["time"])  # (mnt, nq)
+    l_of = np.minimum(l_of, nt - 1)
+    big_h = (sd.Lx if side in (BOTTOM, TOP) else sd.Ly) / ms
+    big_t = (sd.nt * sd.dt) / mnt
+    e_len = sd.edge_len[side]
+    # c_ab(F) = |F_H| sum_qr w_q w_r L_a(xi_q) L_b(xi_r) U[l(r), m(q)] / |e|
+    rows, cols, vals = [], [], []
+    coef = big_h * big_t / e_len
+    FT, FS, B, A, R, Q = np.meshgrid(ft, fs, np.arange(nq), np.arange(nq), np.arange(nq), np.arange(nq), indexing="ij")
+    row = ((FT * ms + FS) * nq + B) * nq + A
+    col = l_of[FT, R] * ns + m_of[FS, Q]
+    val = coef * w[Q] * w[R] * leg[A, Q] * leg[B, R]
+    f2c = sp.coo_matrix((val.ravel(), (row.ravel(), col.ravel())), shape=(ms * mnt * nd, ns * nt)).tocsr()
+    f2c.sum_duplicates()
+    # ---- c2f: Gauss points of every fine st face sample the mortar polynomial
+    m = np.arange(ns)
+    lv = np.arange(nt)
+    us = (m[:, None] + xi[None, :]) / ns * ms  # mortar-cell coordinate
+    ut = (lv[:, None] + xi[None, :]) / nt * mnt
+    fs_of = np.minimum(_locate(us, TIE_RULE["space"]), ms - 1)
+    ft_of = np.minimum(_locate(ut, TIE_RULE["time"]), mnt - 1)
+    xs_loc = us - fs_of
+    xt_loc = ut - ft_of
+    leg_s = legendre01(k, xs_loc)  # (k+1, ns, nq)
+    leg_t = legendre01(k, xt_loc)  # (k+1, nt, nq)
+    LV, M, R, Q, B, A = np.meshgrid(lv, m, np.arange(nq), np.arange(nq), np.arange(nq), np.arange(nq), indexing="ij")
+    row = LV * ns + M
+    col = ((ft_of[LV, R] * ms + fs_of[M, Q]) * nq + B) * nq + A
+    val = w[Q] * w[R] * leg_s[A, M, Q] * leg_t[B, LV, R] / (big_h * big_t)
+    c2f = sp.coo_matrix((val.ravel(), (row.ravel(), col.ravel())), shape=(ns * nt, ms * mnt * nd)).tocsr()
+    c2f.sum_duplicates()
+    return f2c, c2f
+
+
+# ----------------------------------------------------------------------------------------
+# one refinement cycle: bar sweep, interface GMRES, final sweep, errors
+# ----------------------------------------------------------------------------------------
+@dataclass
+class CycleResult:
+    cycle: int
+    gmres_iterations: int
+    r_norm: float
+    residuals: List[float]
+    lam: np.ndarray  # concatenated interface vector (subdomain-major, side-major)
+    errors: dict
+    traces: Optional[list] = None
+    solution_p: Optional[list] = None
+    solution_u: Optional[list] = None
+
+
+class Problem:
+    """DarcyVTProblem<2> for one refinement cycle (inc/darcy_vtdd.h:90-276; run() src/darcy_vtdd.cc:2029-2204)."""
+
+    def __init__(self, prm: Params, n_sub: int, mesh, mortar, data=None, keep_solution=False):
+        self.prm = prm
+        self.data = data or DataDefault()
+        self.n0, self.n1 = find_divisors(n_sub)
+        self.k = prm.mortar_degree
+        self.qdegree = prm.mortar_degree + 1  # darcy_main.cc:88
+        self.mortar = list(mortar)
+        self.keep_solution = keep_solution
+        self.subs = [Subdomain(r, self.n0, self.n1, mesh[r][0], mesh[r][1], mesh[r][2], prm, self.data)
+                     for r in range(n_sub)]
+        # interface vector layout: for r, for side with neighbour: mortar dofs of that side
+        self.offsets = {}
+        off = 0
+        nd = (self.k + 1) ** 2
+        for sd in self.subs:
+            for side in range(4):
+                if sd.neighbors[side] >= 0:
+                    ms = self.mortar[0] if side in (BOTTOM, TOP) else self.mortar[1]
+                    ln = ms * self.mortar[2] * nd
+                    self.offsets[(sd.r, side)] = (off, ln)
+                    off += ln
+        self.n_iface = off
+        self.partner = np.empty(off, dtype=np.int64)
+        self.sign = np.empty(off)
+        for (r, side), (o, ln) in self.offsets.items():
+            po, pl = self.offsets[(self.subs[r].neighbors[side], OPPOSITE[side])]
+            assert pl == ln
+            self.partner[o:o + ln] = po + np.arange(ln)
+            self.sign[o:o + ln] = NORMAL_SIGN[side]
+
+    def setup(self):
+        for sd in self.subs:
+            sd.factorize()
+            sd.f2c, sd.c2f = {}, {}
+            for side in range(4):
+                if sd.neighbors[side] >= 0:
+                    sd.f2c[side], sd.c2f[side] = projector_tables(sd, side, self.mortar, self.k)
+
+    # -- sweeps ---------------------------------------------------------------------------
+    def bar_sweep(self):
+        """solve_darcy_vt bar loop, src/darcy_vtdd.cc:884-890, solve_timestep case 0 :902-920."""
+        for sd in self.subs:
+            p_old = sd.project_initial_condition()
+            t = 0.0
+            sd.bar_trace = {s: np.zeros(sd.nt * sd.n_side[s]) for s in range(4) if sd.neighbors[s] >= 0}
+            sd.bar_solution = np.zeros((sd.nt, sd.n))
+            for lvl in range(sd.nt):
+                t += sd.dt
+                x = sd.lu.solve(sd.rhs_bar(t, p_old, self.qdegree, self.prm))
+                sd.bar_solution[lvl] = x
+                p_old = x[sd.nf:]
+                for s in sd.bar_trace:
+                    sd.bar_trace[s][lvl * sd.n_side[s]:(lvl + 1) * sd.n_side[s]] = x[sd.side_edges[s]]
+
+    def star_sweep(self, sd: Subdomain, lam_sides, keep=False):
+        """project c2f + nt star steps (src/darcy_vtdd.cc:1328-1346, 922-935); returns traces per side."""
+        lam_bar = {s: sd.c2f[s] @ lam_sides[s] for s in lam_sides}
+        traces = {s: np.zeros(sd.nt * sd.n_side[s]) for s in lam_sides}
+        p_old = np.zeros(sd.np)
+        sols = np.zeros((sd.nt, sd.n)) if keep else None
+        for lvl in range(sd.nt):
+            lb = {s: lam_bar[s][lvl * sd.n_side[s]:(lvl + 1) * sd.n_side[s]] for s in lam_sides}
+            full = [lb.get(s) for s in range(4)]
+            x = sd.lu.solve(sd.rhs_star(full, p_old, first=(lvl == 0)))
+            p_old = x[sd.nf:]
+            if keep:
+                sols[lvl] = x
+            for s in traces:
+                traces[s][lvl * sd.n_side[s]:(lvl + 1) * sd.n_side[s]] = x[sd.side_edges[s]]
+        return traces, sols
+
+    def split(self, v, sd):
+        return {s: v[self.offsets[(sd.r, s)][0]:self.offsets[(sd.r, s)][0] + self.offsets[(sd.r, s)][1]]
+                for s in range(4) if sd.neighbors[s] >= 0}
+
+    def flux_to_mortar(self, trace_of):
+        """signed f2c of per-subdomain traces, concatenated (src/darcy_vtdd.cc:1203, 1227, 1366-1386)."""
+        out = np.zeros(self.n_iface)
+        for sd in self.subs:
+            for s, tr in trace_of[sd.r].items():
+                o, ln = self.offsets[(sd.r, s)]
+                out[o:o + ln] = NORMAL_SIGN[s] * (sd.f2c[s] @ tr)
+        return out
+
+    def apply_S(self, q):
+        """One GMRES operator application: Ap = -(send + recv), src/darcy_vtdd.cc:1316-1411."""
+        tr = {}
+        for sd in self.subs:
+            tr[sd.r], _ = self.star_sweep(sd, self.split(q, sd))
+        send = self.flux_to_mortar(tr)
+        return -(send + send[self.partner])
+
+    # -- GMRES ----------------------------------------------------------------------------
+    def local_gmres(self):
+        """local_gmres, src/darcy_vtdd.cc:1139-1563, literally (CGS, Givens, Q1 off-by-one, doubled dots)."""
+        prm = self.prm
+        maxiter, tol = prm.max_iteration, prm.tolerance
+        send = self.flux_to_mortar({sd.r: sd.bar_trace for sd in self.subs})
+        r = send + send[self.partner]  # :1236-1256
+        r_norm = math.sqrt(float(r @ r))  # :1265-1276 (every interface counted twice)
+        Q = [r / r_norm]
+        beta = [r_norm]
+        cs, sn, H = [], [], []
+        residuals = [1.0]
+        k_counter = 0
+        cg_iteration = 0
+        while k_counter < maxiter:
+            ap = self.apply_S(Q[k_counter])
+            cg_iteration += 1  # :1363
+            h = np.zeros(k_counter + 2)
+            for i in range(k_counter + 1):
+                h[i] = float(ap @ Q[i])  # classical GS on the unmodified Ap, :1416-1422
+            q = ap.copy()
+            for i in range(k_counter + 1):
+                q -= h[i] * Q[i]  # :1436-1441
+            h[k_counter + 1] = math.sqrt(float(q @ q))  # :1445-1455
+            Q.append(q / h[k_counter + 1])
+            # apply_givens_rotation, :1092-1118
+            for i in range(k_counter):
+                temp = cs[i] * h[i] + sn[i] * h[i + 1]
+                h[i + 1] = -sn[i] * h[i] + cs[i] * h[i + 1]
+                h[i] = temp
+            v1, v2 = h[k_counter], h[k_counter + 1]
+            if abs(v1) < 1e-15:  # givens_rotation, :1076-1087
+                c, s = 0.0, 1.0
+            else:
+                tt = math.sqrt(v1 * v1 + v2 * v2)
+                c = abs(v1) / tt
+                s = c * v2 / v1
+            h[k_counter] = c * h[k_counter] + s * h[k_counter + 1]
+            h[k_counter + 1] = 0.0
+            cs.append(c)
+            sn.append(s)
+            H.append(h)
+            beta.append(-sn[k_counter] * beta[k_counter])  # :1474
+            beta[k_counter] *= cs[k_counter]  # :1475
+            err = abs(beta[k_counter + 1]) / r_norm  # :1478
+            residuals.append(err)
+            if err < tol:  # :1488-1492: break WITHOUT incrementing k_counter (quirk Q1)
+                break
+            k_counter += 1
+        # back_solve with k_counter columns, :1121-1135, 1512-1514
+        k = k_counter
+        y = np.zeros(k + 1)
+        for i in range(k - 1, -1, -1):
+            y[i] = beta[i] / H[i][i]
+            for j in range(i + 1, k):
+                y[i] -= H[j][i] * y[j] / H[i][i]
+        lam = np.zeros(self.n_iface)
+        for j in range(k + 1):
+            lam += Q[j] * y[j]  # :1517-1521 (y[k] = 0)
+        return lam, cg_iteration, r_norm, residuals
+
+    # -- final sweep + errors -------------------------------------------------------------
+    def final_sweep_and_errors(self, lam):
+        """solve_timestep case 2 (:937-953) + compute_errors (:1657-1833) + lambda error (:1566-1616)."""
+        num = np.zeros(7)
+        den = np.zeros(7)
+        sols_p, sols_u, traces = [], [], []
+        for sd in self.subs:
+            tr, star = self.star_sweep(sd, self.split(lam, sd), keep=True)
+            sol = star + sd.bar_solution  # :943-945
+            traces.append(tr)
+            if self.keep_solution:
+                sols_p.append(sol[:, sd.nf:].copy())
+                sols_u.append(sol[:, :sd.nf].copy())
+            if self.prm.is_manufact:
+                n_, d_ = subdomain_errors(sd, sol, self.data)
+                num[[0, 2, 4]] += n_
+                den[[0, 2, 4]] += d_
+                ln, ld = lambda_error(sd, self.split(lam, sd), self.mortar, self.k, self.qdegree, self.data)
+                num[6] += ln
+                den[6] += ld
+        errors = {}
+        if self.prm.is_manufact:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                rel = np.sqrt(num) / np.sqrt(den)  # :1816-1819
+            errors = {"velocity_l2l2": rel[0], "pressure_dg": rel[4], "pressure_l2l2": rel[2], "lambda_l2": rel[6]}
+        return errors, traces, sols_p, sols_u
+
+    def run_cycle(self, cycle=0) -> CycleResult:
+        self.setup()
+        self.bar_sweep()
+        lam, its, r_norm, residuals = self.local_gmres()
+        errors, traces, sp_, su_ = self.final_sweep_and_errors(lam)
+        return CycleResult(cycle, its, r_norm, residuals, lam, errors, traces, sp_ or None, su_ or None)
+
+
+def subdomain_errors(sd: Subdomain, sol, data):
+    """compute_errors per rank, src/darcy_vtdd.cc:1657-1775.
+
+    Returns numerators/denominators for (velocity L2-L2, pressure L2-L2, pressure DG).
+    QIterated(QTrapezoid, degree+2): 3x3 composite trapezoid per cell (:1683-1684).
+    """
+    nx, ny, hx, hy = sd.nx, sd.ny, sd.hx, sd.hy
+    tq = np.array([0.0, 0.5, 1.0])
+    tw = np.array([0.25, 0.5, 0.25])
+    gx, gy = np.meshgrid(tq, tq, indexing="ij")
+    wq = (tw[:, None] * tw[None, :]).ravel() * hx * hy
+    gx, gy = gx.ravel(), gy.ravel()
+    ii, jj = sd.cell_ij()
+    xq = sd.x0 + (ii[:, None] + gx[None, :]) * hx
+    yq = sd.y0 + (jj[:, None] + gy[None, :]) * hy
+    xc = sd.x0 + (ii + 0.5) * hx
+    yc = sd.y0 + (jj + 0.5) * hy
+    xl = jj * (nx + 1) + ii
+    yb = sd.nxe + jj * nx + ii
+    num = np.zeros(3)
+    den = np.zeros(3)
+    t = 0.0
+    final_time = sd.dt * sd.nt
+    old_jump = None
+    old_proj = None
+    for lvl in range(sd.nt):
+        t += sd.dt  # :1553
+        x = sol[lvl]
+        p = x[sd.nf:]
+        u1e, u2e, pe = data.exact(xq, yq, t)
+        p_err2 = float((((p[:, None] - pe) ** 2) @ wq).sum())
+        p_nrm2 = float(((pe ** 2) @ wq).sum())
+        num[1] += sd.dt * p_err2  # :1714-1715
+        den[1] += sd.dt * p_nrm2
+        proj = data.pressure_bc(xc, yc, t + 0.5 * sd.dt)  # :1669-1670, 1722-1725
+        if lvl != 0:
+            jump = old_jump + proj - p - old_proj  # :1730-1732
+            num[2] += float((jump ** 2).sum() * hx * hy)  # :1733-1742
+        if abs(t - final_time) < 1e-12:  # :1744-1749
+            num[2] += p_err2
+            den[2] += p_nrm2
+        old_proj = proj
+        old_jump = p.copy()  # old_solution_for_jump = solution, :951
+        uxl, uxr = x[xl], x[xl + 1]
+        uyb, uyt = x[yb], x[yb + nx]
+        uhx = (uxl[:, None] * (1 - gx)[None, :] + uxr[:, None] * gx[None, :]) / hy
+        uhy = (uyb[:, None] * (1 - gy)[None, :] + uyt[:, None] * gy[None, :]) / hx
+        num[0] += float((((uhx - u1e) ** 2 + (uhy - u2e) ** 2) @ wq).sum())  # :1774-1775 (no dt weight)
+        den[0] += float(((u1e ** 2 + u2e ** 2) @ wq).sum())
+    return num, den
+
+
+def lambda_error(sd: Subdomain, lam_sides, mortar, k, qdegree, data):
+    """compute_interface_error_l2, src/darcy_vtdd.cc:1566-1616 (the dofs_per_cell factor cancels)."""
+    nq = qdegree
+    xi, w = gauss01(nq)
+    leg = legendre01(k, xi)
+    num = den = 0.0
+    mnt = mortar[2]
+    big_t = sd.dt * sd.nt / mnt
+    for side, c in lam_sides.items():
+        ms = mortar[0] if side in (BOTTOM, TOP) else mortar[1]
+        big_h = (sd.Lx if side in (BOTTOM, TOP) else sd.Ly) / ms
+        coef = c.reshape(mnt, ms, k + 1, k + 1)  # [ft, fs, b, a]
+        # value at (q, r) of every face: sum_ab c_ab L_a(xi_q) L_b(xi_r) / |F_H|
+        val = np.einsum("tsba,aq,br->tsqr", coef, leg, leg) / (big_h * big_t)
+        s_coord = (np.arange(ms)[:, None] + xi[None, :]) * big_h  # (ms, nq)
+        t_coord = (np.arange(mnt)[:, None] + xi[None, :]) * big_t  # (mnt, nq)
+        if side in (BOTTOM, TOP):
+            x = sd.x0 + s_coord
+            y = np.full_like(x, sd.y0 if side == BOTTOM else sd.y0 + sd.Ly)
+        else:
+            y = sd.y0 + s_coord
+            x = np.full_like(y, sd.x0 if side == LEFT else sd.x0 + sd.Lx)
+        pe = data.pressure_bc(x[None, :, :, None], y[None, :, :, None], t_coord[:, None, None, :])
+        jxw = (w[:, None] * w[None, :])[None, None] * big_h * big_t
+        num += float((((val - pe) ** 2) * jxw).sum())
+        den += float(((pe ** 2) * jxw).sum())
+    return num, den
+
+
+def refined_meshes(prm: Params, n_sub: int):
+    """Mesh patterns of every cycle, src/darcy_vtdd.cc:2079-2161 (quirk Q12 for the mortar)."""
+    mesh = [list(m) for m in prm.mesh[:n_sub + 1]]
+    out = []
+    for idx in range(prm.num_refinement):
+        if idx > 0:
+            for m in mesh[:-1]:
+                m[0] *= 2; m[1] *= 2; m[2] *= 2
+            if prm.mortar_degree == 1 or idx % 2 == 0:
+                m = mesh[-1]
+                m[0] *= 2; m[1] *= 2; m[2] *= 2
+        out.append([list(m) for m in mesh])
+    return out
+
+
+def run(prm: Params, n_sub: Optional[int] = None, data=None, cycles: Optional[Sequence[int]] = None,
+        keep_solution=False, log: Optional[Callable[[str], None]] = None) -> List[CycleResult]:
+    """DarcyVTProblem::run, src/darcy_vtdd.cc:2029-2204."""
+    n_sub = n_sub if n_sub is not None else len(prm.mesh) - 1
+    if n_sub <= 1:
+        raise ValueError("Mortar MFEM is impossible with 1 subdomain")  # :2066
+    if len(prm.mesh) < n_sub + 1:
+        raise ValueError("Some of the mesh parameters were not provided")  # :2067
+    results = []
+    for idx, mesh in enumerate(refined_meshes(prm, n_sub)):
+        if cycles is not None and idx not in cycles:
+            continue
+        prob = Problem(prm, n_sub, mesh[:-1], mesh[-1], data=data, keep_solution=keep_solution)
+        res = prob.run_cycle(idx)
+        if log:
+            log(f"cycle {idx}: gmres {res.gmres_iterations} r_norm {res.r_norm:.16g} errors {res.errors}")
+        results.append(res)
+    return results
+
+
+if __name__ == "__main__":
+    import sys
+    import time
+
+    path = sys.argv[1] if len(sys.argv) > 1 else "parameter.txt"
+    prm = parse_parameter_file(path)
+    if len(sys.argv) > 2:
+        prm.num_refinement = int(sys.argv[2])
+    t0 = time.time()
+    run(prm, log=lambda s: print(s, f"[{time.time() - t0:.1f}s]", flush=True))
