@@ -1,0 +1,169 @@
+/* mmmfe_b200.h -- C ABI of the B200 (sm_100a) interface-GMRES engine.
+ *
+ * This is the drop-in boundary for the hot path of MMMFE-ST-DD.  The reference has no
+ * FFI; the seams this library replaces are member functions of DarcyVTProblem<2>.  Every entry point names
+ * the reference site it stands for (paths relative to the reference repository).
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary; every call returns 0 on success or a negative MMMFE_E_* code,
+ *     mmmfe_last_error() returns the message of the last failure on that context;
+ *   - one context per process and per refinement cycle, bound to one CUDA device, used from one host thread;
+ *   - all pointer arguments are HOST buffers owned by the caller; inputs are copied during the call, outputs are
+ *     written before the call returns; device memory is owned by the library;
+ *   - "side" is the reference side index 0 bottom, 1 right, 2 top, 3 left (boundary_id - 1,
+ *     inc/utilities.h:329-375); outward normal signs {-1,+1,+1,-1} (inc/utilities.h:79-91);
+ *   - a flux dof is the flux integral through its edge in the positive coordinate direction (deal.II RT0);
+ *   - FP64 throughout.
+ */
+#ifndef MMMFE_B200_H
+#define MMMFE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMMFE_OK 0
+#define MMMFE_E_INVALID (-1)     /* bad argument / call order                                   */
+#define MMMFE_E_UNSUPPORTED (-2) /* structure outside the path (e.g. c0 == 0, non-diagonal M)   */
+#define MMMFE_E_CUDA (-3)        /* CUDA runtime failure (message has the CUDA error string)    */
+#define MMMFE_E_NUMERIC (-4)     /* non-positive pivot in a front                               */
+#define MMMFE_E_COMM (-5)        /* NCCL failure                                                */
+
+typedef struct mmmfe_ctx mmmfe_ctx;
+
+/* Sparse matrix in CSR, 0-based, host memory. */
+typedef struct {
+  int64_t n_rows, n_cols;
+  const int64_t *row_ptr; /* n_rows + 1 */
+  const int32_t *col;     /* nnz        */
+  const double *val;      /* nnz        */
+} mmmfe_csr;
+
+/* One rectangular subdomain = one MPI rank of the reference (src/darcy_vtdd.cc:2082-2103). */
+typedef struct {
+  int32_t global_id;       /* reference rank r; ix = r % n0, iy = r / n0 (inc/utilities.h:152-157)         */
+  int32_t nx, ny, nt;      /* cells in x, y and backward-Euler steps (mesh_pattern_sub_d<r>)               */
+  double dt;               /* final_time / nt (src/darcy_vtdd.cc:2083)                                     */
+  /* Saddle matrix [[A, -B^T], [dt B, c0 M]] exactly as assemble_system builds it
+   * (src/darcy_vtdd.cc:464-466); unknowns [fluxes ; pressures], n = n_flux + n_pressure.                  */
+  mmmfe_csr matrix;
+  int32_t n_flux, n_pressure;
+  /* canon_of_dof[d] = canonical index of user dof d, or NULL when the user numbering is canonical:
+   * x-edges (i=0..nx, j=0..ny-1) at j*(nx+1)+i, y-edges (i=0..nx-1, j=0..ny) at (nx+1)*ny + j*nx + i,
+   * cells at n_flux + j*nx + i.  Used only to build the nested-dissection tree.                           */
+  const int32_t *canon_of_dof;
+  /* Interface sides.  neighbor[s] = global id of the subdomain across side s, or -1
+   * (find_neighbors, inc/utilities.h:176-306).  side_dofs[s] = the n_side[s] 2-D interface flux dofs in the
+   * order of interface_dofs_subd[s] (src/darcy_vtdd.cc:559-584).                                          */
+  int32_t neighbor[4];
+  int32_t n_side[4];
+  const int32_t *side_dofs[4];
+  /* Projector tables of project_mortar (inc/utilities.h:471-505) for each interface side, as explicit
+   * sampling operators:
+   *   f2c[s] : (mortar_len[s]) x (n_side[s]*nt)  fine 2-D flux trace U[level*n_side+i] -> mortar coefficients
+   *   c2f[s] : (n_side[s]*nt) x (mortar_len[s])  mortar coefficients -> lam_bar = (2-D interface dof)/|e|
+   * mortar_len[s] = interface_dofs[s].size() (src/darcy_vtdd.cc:524-541).                                 */
+  int32_t mortar_len[4];
+  mmmfe_csr f2c[4];
+  mmmfe_csr c2f[4];
+} mmmfe_subdomain;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------------- */
+/* device < 0: use the current device. */
+int mmmfe_create(mmmfe_ctx **ctx, int device);
+int mmmfe_destroy(mmmfe_ctx *ctx);
+const char *mmmfe_last_error(const mmmfe_ctx *ctx);
+const char *mmmfe_version(void);
+
+/* Options (set before mmmfe_setup): "keep_history" (default 1: keep every bar level on the device so that the
+ * final sweep can return full solutions), "use_graphs" (default 1: replay each sweep as a CUDA graph),
+ * "leaf_cells" (default 4: nested-dissection leaf size).                                                       */
+int mmmfe_set_option(mmmfe_ctx *ctx, const char *key, double value);
+
+/* ---- multi-GPU: one process per GPU, subdomains sharded over ranks ------------------------------------------ */
+/* Size in bytes of the NCCL unique id blob; mmmfe_comm_unique_id fills one (call on rank 0, broadcast it by any
+ * out-of-band means, e.g. torch.distributed), mmmfe_comm_init joins.  Single-rank runs skip both.
+ * Replaces MPI_COMM_WORLD of the reference (src/darcy_vtdd.cc:89).                                            */
+int mmmfe_comm_unique_id_size(void);
+int mmmfe_comm_unique_id(void *id_out);
+int mmmfe_comm_init(mmmfe_ctx *ctx, int rank, int world, const void *id);
+/* owner_rank[g] = rank that holds global subdomain g (length n_global); required before mmmfe_setup when
+ * world > 1, optional (all zero) otherwise.                                                                   */
+int mmmfe_set_owners(mmmfe_ctx *ctx, int32_t n_global, const int32_t *owner_rank);
+
+/* ---- setup: once per refinement cycle ----------------------------------------------------------------------- */
+/* Registers a subdomain held by this rank; returns its local index. */
+int mmmfe_add_subdomain(mmmfe_ctx *ctx, const mmmfe_subdomain *sd, int32_t *local_index);
+/* Groups subdomains with identical matrices, builds the nested-dissection tree of each group and factorises it
+ * on the device (multifrontal, block-inverse fronts, FP64 DMMA); builds the interface layout and exchange plan.
+ * Replaces A_direct.initialize(system_matrix) (src/darcy_vtdd.cc:483) and the buffer set-up at the top of
+ * local_gmres (src/darcy_vtdd.cc:1149-1223).                                                                  */
+int mmmfe_setup(mmmfe_ctx *ctx);
+
+/* Sizes. The local interface vector is the concatenation, over local subdomains in registration order and sides
+ * 0..3 with a neighbour, of that side's mortar coefficients (every interface therefore appears on both of its
+ * subdomains, as in the reference).                                                                           */
+int64_t mmmfe_interface_length(const mmmfe_ctx *ctx);
+int64_t mmmfe_interface_offset(const mmmfe_ctx *ctx, int32_t local_index, int32_t side);
+int32_t mmmfe_num_factor_groups(const mmmfe_ctx *ctx);
+/* Stored factor values of all groups (doubles) and the bytes one star step of every local subdomain streams. */
+int64_t mmmfe_factor_values(const mmmfe_ctx *ctx);
+int64_t mmmfe_step_bytes(const mmmfe_ctx *ctx);
+double mmmfe_factor_flops(const mmmfe_ctx *ctx);
+double mmmfe_factor_seconds(const mmmfe_ctx *ctx);
+
+/* ---- bar sweep: solve_timestep(0, .) for every level (src/darcy_vtdd.cc:884-890, 902-920) -------------------- */
+/* Per local subdomain, the caller provides the data-dependent right-hand sides assemble_rhs_bar would build
+ * (src/darcy_vtdd.cc:632-766) WITHOUT the c0*(p_old, w) term, which the library adds:
+ *   p0        [n_pressure]            projected initial pressure (src/darcy_vtdd.cc:2172-2176); NULL = 0
+ *   src       [nt][n_pressure]        dt * (f(t_n), w) per cell (src/darcy_vtdd.cc:718)
+ *   fr_dofs   [n_fr]                  flux dofs that carry outer-boundary data (src/darcy_vtdd.cc:732-755)
+ *   fr_vals   [nt][n_fr]              their right-hand-side values per level
+ * The bar solution of every level is kept on the device for the final sweep; interface traces are projected to
+ * the mortar space and the initial residual r = sum over the two sides of s*f2c(bar trace) is formed
+ * (src/darcy_vtdd.cc:1203-1256).                                                                              */
+int mmmfe_bar_set_data(mmmfe_ctx *ctx, int32_t local_index, const double *p0, const double *src, int32_t n_fr,
+                       const int32_t *fr_dofs, const double *fr_vals);
+int mmmfe_bar_sweep(mmmfe_ctx *ctx);
+
+/* ---- interface operator and GMRES ------------------------------------------------------------------------------ */
+/* One operator application Ap = -(send + recv) with send = s * f2c(star trace(c2f(q)))
+ * (src/darcy_vtdd.cc:1316-1411): HOST in, HOST out, length mmmfe_interface_length.  Collective over ranks.     */
+int mmmfe_apply_interface_operator(mmmfe_ctx *ctx, const double *q, double *ap);
+/* Same, operating on the library's device-resident buffers; `repeat` applications back to back with q fixed.
+ * Used by benchmarks (inputs already in HBM); returns the device time per application in milliseconds.        */
+int mmmfe_apply_interface_operator_device(mmmfe_ctx *ctx, int32_t repeat, double *ms_per_apply);
+
+typedef struct {
+  int32_t iterations;     /* operator applications = "# GMRES" (cg_iteration, src/darcy_vtdd.cc:1363, 1821) */
+  int32_t converged;      /* stop test |Beta_{k+1}| / r_norm < tol hit (src/darcy_vtdd.cc:1478-1492)        */
+  double r_norm;          /* printed "r_norm" (every interface counted twice, src/darcy_vtdd.cc:1265-1276)  */
+  double final_residual;  /* last relative residual                                                           */
+  double seconds;         /* wall time of the loop                                                            */
+} mmmfe_gmres_info;
+
+/* local_gmres (src/darcy_vtdd.cc:1139-1521): classical Gram-Schmidt Arnoldi, Givens least squares, the reference's
+ * stop test and its back_solve over k_counter columns (y[k] = 0 on a converged exit).  Requires a bar sweep.
+ * residual_history may be NULL, else receives min(history_cap, iterations+1) relative residuals.
+ * lambda_out (HOST, interface length) may be NULL.  Collective over ranks.                                    */
+int mmmfe_gmres_solve(mmmfe_ctx *ctx, double tol, int32_t max_iter, mmmfe_gmres_info *info,
+                      double *residual_history, int32_t history_cap, double *lambda_out);
+
+/* ---- final sweep: solve_timestep(2, .) (src/darcy_vtdd.cc:937-953, 1551-1558) ---------------------------------- */
+/* Star solve with the converged lambda plus the stored bar solution.  solution[nt][n_flux + n_pressure] of the
+ * given local subdomain (user dof numbering) is written to HOST memory.                                        */
+int mmmfe_final_sweep(mmmfe_ctx *ctx);
+int mmmfe_get_solution(mmmfe_ctx *ctx, int32_t local_index, double *solution);
+/* Interface flux traces of the last star (or final) sweep of one side: [nt][n_side]. */
+int mmmfe_get_star_trace(mmmfe_ctx *ctx, int32_t local_index, int32_t side, double *trace);
+
+/* ---- single-subdomain kernels exposed for parity tests --------------------------------------------------------- */
+/* x = K^{-1} rhs for the saddle matrix of one local subdomain (A_direct.vmult, src/darcy_vtdd.cc:864, 877). */
+int mmmfe_solve_saddle(mmmfe_ctx *ctx, int32_t local_index, const double *rhs, double *x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMMFE_B200_H */

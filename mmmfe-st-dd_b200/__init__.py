@@ -1,0 +1,249 @@
+"""ctypes binding of the B200 interface-GMRES engine (include/mmmfe_b200.h) and of the C++ host front-end
+(include/mmmfe_host.h).  Python is plumbing only: tests, bench.py and launch scripts call the same C ABI the
+``DarcyVT`` executable uses.  There is no CPU fallback: a missing library or device raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ENGINE_PATH = os.path.join(HERE, "libmmmfe_b200.so")
+HOST_PATH = os.path.join(HERE, "libmmmfe_host.so")
+
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+c_f64p = ctypes.POINTER(ctypes.c_double)
+
+
+class MmmfeError(RuntimeError):
+    pass
+
+
+class Csr(ctypes.Structure):
+    _fields_ = [("n_rows", ctypes.c_int64), ("n_cols", ctypes.c_int64), ("row_ptr", c_i64p), ("col", c_i32p),
+                ("val", c_f64p)]
+
+
+class SubdomainDesc(ctypes.Structure):
+    _fields_ = [("global_id", ctypes.c_int32), ("nx", ctypes.c_int32), ("ny", ctypes.c_int32),
+                ("nt", ctypes.c_int32), ("dt", ctypes.c_double), ("matrix", Csr), ("n_flux", ctypes.c_int32),
+                ("n_pressure", ctypes.c_int32), ("canon_of_dof", c_i32p), ("neighbor", ctypes.c_int32 * 4),
+                ("n_side", ctypes.c_int32 * 4), ("side_dofs", c_i32p * 4), ("mortar_len", ctypes.c_int32 * 4),
+                ("f2c", Csr * 4), ("c2f", Csr * 4)]
+
+
+class GmresInfo(ctypes.Structure):
+    _fields_ = [("iterations", ctypes.c_int32), ("converged", ctypes.c_int32), ("r_norm", ctypes.c_double),
+                ("final_residual", ctypes.c_double), ("seconds", ctypes.c_double)]
+
+
+_engine = None
+
+
+def load_engine():
+    """dlopen libmmmfe_b200.so (built in-tree by build.py); raises when it is absent."""
+    global _engine
+    if _engine is not None:
+        return _engine
+    if not os.path.exists(ENGINE_PATH):
+        raise MmmfeError(f"{ENGINE_PATH} is missing: run `python mmmfe-st-dd_b200/build.py` (no CPU fallback exists)")
+    lib = ctypes.CDLL(ENGINE_PATH)
+    vp = ctypes.c_void_p
+    sig = {
+        "mmmfe_create": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int]),
+        "mmmfe_destroy": (ctypes.c_int, [vp]),
+        "mmmfe_last_error": (ctypes.c_char_p, [vp]),
+        "mmmfe_version": (ctypes.c_char_p, []),
+        "mmmfe_set_option": (ctypes.c_int, [vp, ctypes.c_char_p, ctypes.c_double]),
+        "mmmfe_comm_unique_id_size": (ctypes.c_int, []),
+        "mmmfe_comm_unique_id": (ctypes.c_int, [vp]),
+        "mmmfe_comm_init": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp]),
+        "mmmfe_set_owners": (ctypes.c_int, [vp, ctypes.c_int32, c_i32p]),
+        "mmmfe_add_subdomain": (ctypes.c_int, [vp, ctypes.POINTER(SubdomainDesc), c_i32p]),
+        "mmmfe_setup": (ctypes.c_int, [vp]),
+        "mmmfe_interface_length": (ctypes.c_int64, [vp]),
+        "mmmfe_interface_offset": (ctypes.c_int64, [vp, ctypes.c_int32, ctypes.c_int32]),
+        "mmmfe_num_factor_groups": (ctypes.c_int32, [vp]),
+        "mmmfe_factor_values": (ctypes.c_int64, [vp]),
+        "mmmfe_step_bytes": (ctypes.c_int64, [vp]),
+        "mmmfe_factor_flops": (ctypes.c_double, [vp]),
+        "mmmfe_factor_seconds": (ctypes.c_double, [vp]),
+        "mmmfe_bar_set_data": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p, c_f64p, ctypes.c_int32, c_i32p, c_f64p]),
+        "mmmfe_bar_sweep": (ctypes.c_int, [vp]),
+        "mmmfe_apply_interface_operator": (ctypes.c_int, [vp, c_f64p, c_f64p]),
+        "mmmfe_apply_interface_operator_device": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p]),
+        "mmmfe_gmres_solve": (ctypes.c_int, [vp, ctypes.c_double, ctypes.c_int32, ctypes.POINTER(GmresInfo), c_f64p,
+                                             ctypes.c_int32, c_f64p]),
+        "mmmfe_final_sweep": (ctypes.c_int, [vp]),
+        "mmmfe_get_solution": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p]),
+        "mmmfe_get_star_trace": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.c_int32, c_f64p]),
+        "mmmfe_solve_saddle": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p, c_f64p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    lib._signatures = sig
+    _engine = lib
+    return lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a, typ):
+    return a.ctypes.data_as(typ) if a is not None else None
+
+
+def _csr(mat, keep):
+    """scipy CSR -> Csr struct (arrays kept alive in `keep`)."""
+    mat = mat.tocsr()
+    rp = np.ascontiguousarray(mat.indptr, dtype=np.int64)
+    col = np.ascontiguousarray(mat.indices, dtype=np.int32)
+    val = _f64(mat.data)
+    keep.extend([rp, col, val])
+    return Csr(mat.shape[0], mat.shape[1], _ptr(rp, c_i64p), _ptr(col, c_i32p), _ptr(val, c_f64p))
+
+
+class Engine:
+    """Thin object wrapper over the C ABI; one per process and refinement cycle."""
+
+    def __init__(self, device=-1):
+        self.lib = load_engine()
+        self.h = ctypes.c_void_p()
+        rc = self.lib.mmmfe_create(ctypes.byref(self.h), device)
+        if rc != 0:
+            raise MmmfeError(f"mmmfe_create failed ({rc}): no usable CUDA device; this package has no CPU path")
+        self.subs = []
+
+    def close(self):
+        if self.h:
+            self.lib.mmmfe_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MmmfeError(f"mmmfe error {rc}: {self.lib.mmmfe_last_error(self.h).decode()}")
+
+    def set_option(self, key, value):
+        self._check(self.lib.mmmfe_set_option(self.h, key.encode(), float(value)))
+
+    def comm_init(self, rank, world, uid_bytes):
+        buf = ctypes.create_string_buffer(uid_bytes, len(uid_bytes))
+        self._check(self.lib.mmmfe_comm_init(self.h, rank, world, ctypes.cast(buf, ctypes.c_void_p)))
+
+    def unique_id(self):
+        n = self.lib.mmmfe_comm_unique_id_size()
+        buf = ctypes.create_string_buffer(n)
+        rc = self.lib.mmmfe_comm_unique_id(ctypes.cast(buf, ctypes.c_void_p))
+        if rc != 0:
+            raise MmmfeError("ncclGetUniqueId failed")
+        return buf.raw
+
+    def set_owners(self, owners):
+        o = np.ascontiguousarray(owners, dtype=np.int32)
+        self._check(self.lib.mmmfe_set_owners(self.h, len(o), _ptr(o, c_i32p)))
+
+    def add_subdomain(self, *, global_id, nx, ny, nt, dt, matrix, n_flux, n_pressure, neighbor, side_dofs, f2c, c2f,
+                      canon_of_dof=None):
+        keep = []
+        d = SubdomainDesc()
+        d.global_id, d.nx, d.ny, d.nt, d.dt = global_id, nx, ny, nt, dt
+        d.matrix = _csr(matrix, keep)
+        d.n_flux, d.n_pressure = n_flux, n_pressure
+        if canon_of_dof is not None:
+            cn = np.ascontiguousarray(canon_of_dof, dtype=np.int32)
+            keep.append(cn)
+            d.canon_of_dof = _ptr(cn, c_i32p)
+        for s in range(4):
+            d.neighbor[s] = neighbor[s]
+            if neighbor[s] >= 0:
+                sdofs = np.ascontiguousarray(side_dofs[s], dtype=np.int32)
+                keep.append(sdofs)
+                d.n_side[s] = len(sdofs)
+                d.side_dofs[s] = _ptr(sdofs, c_i32p)
+                d.mortar_len[s] = f2c[s].shape[0]
+                d.f2c[s] = _csr(f2c[s], keep)
+                d.c2f[s] = _csr(c2f[s], keep)
+        li = ctypes.c_int32(-1)
+        self._check(self.lib.mmmfe_add_subdomain(self.h, ctypes.byref(d), ctypes.byref(li)))
+        self.subs.append(dict(nt=nt, n=n_flux + n_pressure, n_side=[d.n_side[s] for s in range(4)]))
+        return li.value
+
+    def setup(self):
+        self._check(self.lib.mmmfe_setup(self.h))
+
+    @property
+    def interface_length(self):
+        return int(self.lib.mmmfe_interface_length(self.h))
+
+    def interface_offset(self, li, side):
+        return int(self.lib.mmmfe_interface_offset(self.h, li, side))
+
+    def stats(self):
+        return dict(factor_groups=int(self.lib.mmmfe_num_factor_groups(self.h)),
+                    factor_values=int(self.lib.mmmfe_factor_values(self.h)),
+                    step_bytes=int(self.lib.mmmfe_step_bytes(self.h)),
+                    factor_flops=float(self.lib.mmmfe_factor_flops(self.h)),
+                    factor_seconds=float(self.lib.mmmfe_factor_seconds(self.h)))
+
+    def bar_set_data(self, li, p0, src, fr_dofs, fr_vals):
+        p0 = _f64(p0) if p0 is not None else None
+        src = _f64(src)
+        fr_dofs = np.ascontiguousarray(fr_dofs, dtype=np.int32)
+        fr_vals = _f64(fr_vals)
+        self._check(self.lib.mmmfe_bar_set_data(self.h, li, _ptr(p0, c_f64p), _ptr(src, c_f64p), len(fr_dofs),
+                                                _ptr(fr_dofs, c_i32p), _ptr(fr_vals, c_f64p)))
+
+    def bar_sweep(self):
+        self._check(self.lib.mmmfe_bar_sweep(self.h))
+
+    def apply(self, q):
+        q = _f64(q)
+        out = np.empty_like(q)
+        self._check(self.lib.mmmfe_apply_interface_operator(self.h, _ptr(q, c_f64p), _ptr(out, c_f64p)))
+        return out
+
+    def apply_device(self, repeat=1):
+        ms = ctypes.c_double(0.0)
+        self._check(self.lib.mmmfe_apply_interface_operator_device(self.h, repeat, ctypes.byref(ms)))
+        return ms.value
+
+    def gmres(self, tol, max_iter):
+        info = GmresInfo()
+        hist = np.zeros(max_iter + 2)
+        lam = np.zeros(self.interface_length)
+        self._check(self.lib.mmmfe_gmres_solve(self.h, tol, max_iter, ctypes.byref(info), _ptr(hist, c_f64p),
+                                               len(hist), _ptr(lam, c_f64p)))
+        return dict(iterations=info.iterations, converged=bool(info.converged), r_norm=info.r_norm,
+                    final_residual=info.final_residual, seconds=info.seconds,
+                    residuals=hist[:info.iterations + 1].copy(), lam=lam)
+
+    def final_sweep(self):
+        self._check(self.lib.mmmfe_final_sweep(self.h))
+
+    def get_solution(self, li):
+        s = self.subs[li]
+        out = np.empty((s["nt"], s["n"]))
+        self._check(self.lib.mmmfe_get_solution(self.h, li, _ptr(out, c_f64p)))
+        return out
+
+    def get_star_trace(self, li, side):
+        s = self.subs[li]
+        out = np.empty((s["nt"], s["n_side"][side]))
+        self._check(self.lib.mmmfe_get_star_trace(self.h, li, side, _ptr(out, c_f64p)))
+        return out
+
+    def solve_saddle(self, li, rhs):
+        rhs = _f64(rhs)
+        out = np.empty_like(rhs)
+        self._check(self.lib.mmmfe_solve_saddle(self.h, li, _ptr(rhs, c_f64p), _ptr(out, c_f64p)))
+        return out

@@ -1,0 +1,1159 @@
+// Host driver of the B200 interface-GMRES engine: C ABI (include/mmmfe_b200.h), factor grouping, the device
+// multifrontal factorisation, time-step sweeps as CUDA graphs on per-group streams, interface operator, GMRES.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/mmmfe_b200.h"
+#include "kernels.cuh"
+#include "nd_tree.h"
+
+#ifdef MMMFE_WITH_NCCL
+#include <dlfcn.h>
+#include <nccl.h>
+#endif
+
+namespace mmmfe {
+
+#ifdef MMMFE_WITH_NCCL
+// NCCL is bound at run time (dlopen), never at link time: inside a Python process the copy torch has already
+// loaded is reused (same SONAME), a stand-alone DarcyVT picks up the system library.
+struct NcclApi {
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  bool ok = false;
+};
+
+static NcclApi &nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW);
+  if (!h) return api;
+#define MMMFE_NCCL_SYM(name) api.name = reinterpret_cast<decltype(api.name)>(dlsym(h, "nccl" #name))
+  MMMFE_NCCL_SYM(GetUniqueId); MMMFE_NCCL_SYM(CommInitRank); MMMFE_NCCL_SYM(CommDestroy); MMMFE_NCCL_SYM(Send);
+  MMMFE_NCCL_SYM(Recv); MMMFE_NCCL_SYM(GroupStart); MMMFE_NCCL_SYM(GroupEnd); MMMFE_NCCL_SYM(AllReduce);
+#undef MMMFE_NCCL_SYM
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.GroupStart &&
+           api.GroupEnd && api.AllReduce;
+  return api;
+}
+#endif
+
+static const double kNormalSign[4] = {-1.0, 1.0, 1.0, -1.0};  // inc/utilities.h:79-91
+static const int kOpposite[4] = {2, 3, 0, 1};
+
+struct Error {
+  int code;
+  std::string msg;
+};
+
+[[noreturn]] static void fail(int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw Error{code, buf};
+}
+
+#define CUDA_CHECK(x)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (x);                                                                          \
+    if (e_ != cudaSuccess) fail(MMMFE_E_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), \
+                                __FILE__, __LINE__);                                               \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf &operator=(DevBuf &&o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+  }
+  void zero(cudaStream_t st = 0) {
+    if (n) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), st));
+  }
+  void upload(const T *h, size_t count) {
+    alloc(count);
+    if (count) CUDA_CHECK(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  void upload(const std::vector<T> &v) { upload(v.data(), v.size()); }
+};
+
+struct HostCsr {
+  int64_t n_rows = 0, n_cols = 0;
+  std::vector<int64_t> rp;
+  std::vector<int32_t> col;
+  std::vector<double> val;
+  void from(const mmmfe_csr &c) {
+    n_rows = c.n_rows;
+    n_cols = c.n_cols;
+    rp.assign(c.row_ptr, c.row_ptr + c.n_rows + 1);
+    col.assign(c.col, c.col + rp.back());
+    val.assign(c.val, c.val + rp.back());
+  }
+};
+
+struct DevCsr {
+  int64_t n_rows = 0;
+  DevBuf<int64_t> rp;
+  DevBuf<int32_t> col;
+  DevBuf<double> val;
+  void upload(const HostCsr &h) {
+    n_rows = h.n_rows;
+    rp.upload(h.rp);
+    col.upload(h.col);
+    val.upload(h.val);
+  }
+};
+
+// ---- one registered subdomain ------------------------------------------------------------------------------------
+struct Sub {
+  int32_t gid, nx, ny, nt, nf, np;
+  double dt;
+  HostCsr matrix;
+  std::vector<int32_t> canon;  // empty = canonical
+  int32_t neighbor[4], n_side[4], mortar_len[4];
+  std::vector<int32_t> side_dofs[4];
+  HostCsr f2c[4], c2f[4];
+  int64_t iface_off[4] = {-1, -1, -1, -1};  // into the local interface vector
+  int64_t fine_off[4] = {-1, -1, -1, -1};   // into the fine trace space (nt * n_side each)
+  int32_t batch = -1, member = -1;
+  // bar data on the device
+  DevBuf<double> p0, src, fr_vals, hist;
+  DevBuf<int32_t> fr_dofs;
+  int32_t n_fr = 0;
+  bool has_bar_data = false;
+};
+
+// ---- one factor: nested-dissection tree + block-inverse fronts on the device -------------------------------------
+struct LevelWork {
+  DevBuf<int32_t> small_nodes;
+  DevBuf<WorkItem> fwd, bwd;
+  int32_t n_small = 0, n_fwd = 0, n_bwd = 0;
+};
+
+struct Factor {
+  int32_t nx, ny, nf, np;
+  NdTree tree;
+  DevBuf<FrontDesc> fronts;
+  DevBuf<double> R;
+  DevBuf<int32_t> idx_user, src;
+  std::vector<LevelWork> levels;
+  DevCsr kup, kpu;
+  DevBuf<double> minv;
+  int64_t solve_bytes = 0;  // factor + index bytes one forward+backward pass streams
+  double seconds = 0.0;
+};
+
+// ---- one batch: up to 4 subdomains solved as simultaneous right-hand sides of one factor ---------------------------
+struct Batch {
+  std::shared_ptr<Factor> factor;
+  std::vector<int32_t> members;  // local subdomain indices
+  int32_t M = 1, nt = 0;
+  DevBuf<double> x, z, ptil;
+  DevBuf<int32_t> tr_dof, tr_mem, tr_stride, iface_q;
+  DevBuf<int64_t> tr_base;
+  DevBuf<double> tr_sign;
+  int32_t n_tr = 0;
+  DevBuf<const double *> p0_ptr, src_ptr;
+  DevBuf<double *> hist_ptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  cudaGraphExec_t graph_star = nullptr;
+  StepArgs step{};
+};
+
+struct Arena {
+  DevBuf<double> buf;
+  size_t top = 0;
+  double *take(size_t n) {
+    if (top + n > buf.n) fail(MMMFE_E_INVALID, "factorisation arena exhausted (%zu + %zu > %zu)", top, n, buf.n);
+    double *p = buf.p + top;
+    top += n;
+    return p;
+  }
+};
+
+}  // namespace mmmfe
+
+using namespace mmmfe;
+
+struct mmmfe_ctx {
+  int device = 0;
+  std::string err;
+  bool keep_history = true, use_graphs = true;
+  int leaf_cells = 4;
+  bool is_setup = false, bar_done = false, final_done = false;
+  int rank = 0, world = 1;
+  std::vector<int32_t> owner;
+#ifdef MMMFE_WITH_NCCL
+  ncclComm_t comm = nullptr;
+#endif
+  std::vector<std::unique_ptr<Sub>> subs;
+  std::vector<std::shared_ptr<Factor>> factors;
+  std::vector<std::unique_ptr<Batch>> batches;
+  cudaStream_t stream = nullptr;  // interface-vector stream
+  cudaEvent_t ev_start = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  int64_t n_iface = 0, n_fine = 0;
+  DevCsr c2f_all, f2c_all;  // f2c_all carries the outward sign
+  DevBuf<int64_t> partner;
+  DevBuf<double> lam_bar, trace, send, ap, qin, lam, r0;
+  // remote exchange plan
+  struct Peer {
+    int rank;
+    int64_t send_off, recv_off, count;
+  };
+  std::vector<Peer> peers;
+  DevBuf<int64_t> send_index;
+  DevBuf<double> send_buf, recv_buf;
+  // GMRES workspace
+  DevBuf<double> Q, h_dev, norm_dev;
+  int64_t q_rows = 0;
+  double factor_seconds = 0.0;
+  // temporaries of the factorisation
+  DevBuf<GemmProb> d_gemm;
+  DevBuf<int32_t> d_tiles;
+  DevBuf<InvProb> d_inv;
+  DevBuf<TransProb> d_trans;
+  DevBuf<int32_t> d_fail;
+};
+
+namespace mmmfe {
+
+// =================================================================================================================
+// numeric factorisation
+// =================================================================================================================
+static void run_gemm_batch(mmmfe_ctx *c, const std::vector<GemmProb> &pr) {
+  if (pr.empty()) return;
+  std::vector<int32_t> ts(pr.size() + 1);
+  int64_t tiles = 0;
+  for (size_t i = 0; i < pr.size(); ++i) {
+    ts[i] = int32_t(tiles);
+    tiles += int64_t((pr[i].m + 63) / 64) * ((pr[i].n + 63) / 64);
+  }
+  ts[pr.size()] = int32_t(tiles);
+  if (tiles > 2000000000LL) fail(MMMFE_E_INVALID, "too many GEMM tiles");
+  if (c->d_gemm.n < pr.size()) c->d_gemm.alloc(pr.size() * 2);
+  if (c->d_tiles.n < ts.size()) c->d_tiles.alloc(ts.size() * 2);
+  CUDA_CHECK(cudaMemcpyAsync(c->d_gemm.p, pr.data(), pr.size() * sizeof(GemmProb), cudaMemcpyHostToDevice, c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(c->d_tiles.p, ts.data(), ts.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  launch_grouped_gemm(c->d_gemm.p, c->d_tiles.p, int32_t(pr.size()), int32_t(tiles), c->stream);
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));  // descriptor buffers are reused by the next batch
+}
+
+static void run_trans_batch(mmmfe_ctx *c, const std::vector<TransProb> &pr) {
+  if (pr.empty()) return;
+  if (c->d_trans.n < pr.size()) c->d_trans.alloc(pr.size() * 2);
+  CUDA_CHECK(cudaMemcpyAsync(c->d_trans.p, pr.data(), pr.size() * sizeof(TransProb), cudaMemcpyHostToDevice, c->stream));
+  launch_transpose(c->d_trans.p, int32_t(pr.size()), c->stream);
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+// In-place inverse of a batch of SPD blocks by recursive Schur complements: everything above the 32x32 base
+// blocks is GEMM (DMMA).  Blocks must be stored full (both triangles) and come back full.
+static void inverse_batch(mmmfe_ctx *c, const std::vector<InvProb> &probs, Arena &arena) {
+  std::vector<InvProb> small, big;
+  for (const auto &p : probs) (p.n <= 32 ? small : big).push_back(p);
+  if (!small.empty()) {
+    if (c->d_inv.n < small.size()) c->d_inv.alloc(small.size() * 2);
+    CUDA_CHECK(cudaMemcpyAsync(c->d_inv.p, small.data(), small.size() * sizeof(InvProb), cudaMemcpyHostToDevice, c->stream));
+    launch_small_inverse(c->d_inv.p, int32_t(small.size()), c->d_fail.p, c->stream);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  }
+  if (big.empty()) return;
+  const size_t mark = arena.top;
+  std::vector<InvProb> a11, a22;
+  std::vector<double *> T(big.size());
+  for (size_t i = 0; i < big.size(); ++i) {
+    const int n = big[i].n, h = n / 2, ld = big[i].ld;
+    a11.push_back({big[i].A, h, ld});
+    a22.push_back({big[i].A + int64_t(h) * ld + h, n - h, ld});
+  }
+  inverse_batch(c, a11, arena);
+  std::vector<GemmProb> g1, g2, g3, g4;
+  std::vector<TransProb> tr;
+  for (size_t i = 0; i < big.size(); ++i) {
+    const int n = big[i].n, h = n / 2, r = n - h, ld = big[i].ld;
+    double *A = big[i].A, *A21 = A + int64_t(h) * ld, *A22 = A21 + h;
+    T[i] = arena.take(size_t(r) * h);
+    // T = A21 * inv(A11)
+    g1.push_back({A21, A, T[i], r, h, h, h, ld, 1, ld, 1, 1.0, 0.0});
+    // S = A22 - T * A21^T
+    g2.push_back({T[i], A21, A22, r, r, h, ld, h, 1, 1, ld, -1.0, 1.0});
+  }
+  run_gemm_batch(c, g1);
+  run_gemm_batch(c, g2);
+  inverse_batch(c, a22, arena);
+  for (size_t i = 0; i < big.size(); ++i) {
+    const int n = big[i].n, h = n / 2, r = n - h, ld = big[i].ld;
+    double *A = big[i].A, *A21 = A + int64_t(h) * ld, *A22 = A21 + h;
+    // A21 = -inv(S) * T
+    g3.push_back({A22, T[i], A21, r, h, r, ld, ld, 1, h, 1, -1.0, 0.0});
+    // A11 = inv(A11) - T^T * A21new
+    g4.push_back({T[i], A21, A, h, h, r, ld, 1, h, ld, 1, -1.0, 1.0});
+    tr.push_back({A21, A + h, h, r, ld, ld, 1.0});
+  }
+  run_gemm_batch(c, g3);
+  run_gemm_batch(c, g4);
+  run_trans_batch(c, tr);
+  arena.top = mark;
+}
+
+// S = A - K_up diag(1/M) K_pu in user flux numbering; also extracts K_up, K_pu, 1/M.
+static void build_schur(const Sub &sd, HostCsr &S, HostCsr &kup, HostCsr &kpu, std::vector<double> &minv) {
+  const int32_t nf = sd.nf, np = sd.np;
+  const HostCsr &K = sd.matrix;
+  if (K.n_rows != nf + np || K.n_cols != nf + np) fail(MMMFE_E_INVALID, "matrix must be (n_flux+n_pressure)^2");
+  minv.assign(np, 0.0);
+  kpu.n_rows = np; kpu.n_cols = nf; kpu.rp.assign(1, 0);
+  for (int32_t c = 0; c < np; ++c) {
+    double d = 0.0;
+    for (int64_t e = K.rp[nf + c]; e < K.rp[nf + c + 1]; ++e) {
+      const int32_t col = K.col[e];
+      if (col < nf) {
+        if (K.val[e] != 0.0) { kpu.col.push_back(col); kpu.val.push_back(K.val[e]); }
+      } else if (col == nf + c) d += K.val[e];
+      else if (K.val[e] != 0.0) fail(MMMFE_E_UNSUPPORTED, "pressure block is not diagonal (only DGQ0 is on the path)");
+    }
+    if (!(d > 0.0)) fail(MMMFE_E_UNSUPPORTED, "c0 * |cell| must be positive (c0 = 0 is not on the accelerated path)");
+    minv[c] = 1.0 / d;
+    kpu.rp.push_back(int64_t(kpu.col.size()));
+  }
+  kup.n_rows = nf; kup.n_cols = np; kup.rp.assign(1, 0);
+  S.n_rows = S.n_cols = nf; S.rp.assign(1, 0);
+  std::vector<int32_t> rc;
+  std::vector<double> rv;
+  for (int32_t e = 0; e < nf; ++e) {
+    rc.clear(); rv.clear();
+    auto add = [&](int32_t col, double v) {
+      for (size_t t = 0; t < rc.size(); ++t) if (rc[t] == col) { rv[t] += v; return; }
+      rc.push_back(col); rv.push_back(v);
+    };
+    for (int64_t k = K.rp[e]; k < K.rp[e + 1]; ++k) {
+      const int32_t col = K.col[k];
+      if (col < nf) add(col, K.val[k]);
+      else if (K.val[k] != 0.0) {
+        const int32_t cell = col - nf;
+        kup.col.push_back(cell); kup.val.push_back(K.val[k]);
+        const double f = -K.val[k] * minv[cell];
+        for (int64_t t = kpu.rp[cell]; t < kpu.rp[cell + 1]; ++t) add(kpu.col[t], f * kpu.val[t]);
+      }
+    }
+    kup.rp.push_back(int64_t(kup.col.size()));
+    for (size_t t = 0; t < rc.size(); ++t) { S.col.push_back(rc[t]); S.val.push_back(rv[t]); }
+    S.rp.push_back(int64_t(S.col.size()));
+  }
+}
+
+static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd) {
+  const auto t0 = std::chrono::steady_clock::now();
+  auto F = std::make_shared<Factor>();
+  F->nx = sd.nx; F->ny = sd.ny; F->nf = sd.nf; F->np = sd.np;
+  HostCsr S, kup, kpu;
+  std::vector<double> minv;
+  build_schur(sd, S, kup, kpu, minv);
+  F->kup.upload(kup); F->kpu.upload(kpu); F->minv.upload(minv);
+  NdTree &tr = F->tree;
+  tr.build(sd.nx, sd.ny, c->leaf_cells);
+  if (tr.n_flux != sd.nf) fail(MMMFE_E_INVALID, "n_flux %d does not match an RT0 grid %dx%d", sd.nf, sd.nx, sd.ny);
+  const int32_t nn = int32_t(tr.nodes.size());
+  // user numbering of the front variables
+  std::vector<int32_t> dof_of_canon;
+  if (!sd.canon.empty()) {
+    dof_of_canon.assign(sd.nf, -1);
+    for (int32_t d = 0; d < sd.nf; ++d) {
+      const int32_t cidx = sd.canon[d];
+      if (cidx < 0 || cidx >= sd.nf || dof_of_canon[cidx] >= 0) fail(MMMFE_E_INVALID, "canon_of_dof is not a permutation");
+      dof_of_canon[cidx] = d;
+    }
+  }
+  std::vector<int32_t> idx_user(tr.idx.size());
+  for (size_t i = 0; i < tr.idx.size(); ++i) idx_user[i] = dof_of_canon.empty() ? tr.idx[i] : dof_of_canon[tr.idx[i]];
+  std::vector<FrontDesc> fd(nn);
+  std::vector<int64_t> f_off(nn);
+  for (int32_t i = 0; i < nn; ++i) {
+    const NdNode &n = tr.nodes[i];
+    fd[i] = {n.s, n.b, n.ldr, n.nsplit, n.child[0], n.child[1], n.r_off, n.idx_off, n.src_off, n.z_off};
+    f_off[i] = n.f_off;
+  }
+  F->fronts.upload(fd);
+  F->idx_user.upload(idx_user);
+  F->src.upload(tr.src);
+  F->R.alloc(size_t(tr.r_total));
+  F->R.zero(c->stream);
+
+  // ---- numeric phase ----
+  DevCsr dS;
+  dS.upload(S);
+  DevBuf<int32_t> d_canon, d_node_of, d_pos_of, d_idx_canon;
+  if (!sd.canon.empty()) d_canon.upload(sd.canon);
+  d_node_of.upload(tr.node_of);
+  d_pos_of.upload(tr.pos_of);
+  d_idx_canon.upload(tr.idx);
+  DevBuf<int64_t> d_foff;
+  d_foff.upload(f_off);
+  DevBuf<double> W;
+  W.alloc(size_t(tr.f_total));
+  W.zero(c->stream);
+  c->d_fail.alloc(1);
+  c->d_fail.zero(c->stream);
+  launch_assemble_original(sd.nf, dS.rp.p, dS.col.p, dS.val.p, d_canon.p, nullptr, d_node_of.p, d_pos_of.p,
+                           F->fronts.p, d_foff.p, d_idx_canon.p, W.p, c->stream);
+  Arena arena;
+  size_t arena_need = 0;
+  for (const auto &lvl : tr.by_height) {
+    size_t need = 0;
+    for (int32_t id : lvl) need += size_t(tr.nodes[id].s) * (tr.nodes[id].s + tr.nodes[id].b);
+    arena_need = std::max(arena_need, need);
+  }
+  arena.buf.alloc(arena_need + 16);
+  DevBuf<int32_t> d_lvl;
+  for (size_t h = 0; h < tr.by_height.size(); ++h) {
+    const auto &lvl = tr.by_height[h];
+    if (h > 0) {
+      d_lvl.upload(lvl);
+      launch_extend_add(d_lvl.p, int32_t(lvl.size()), F->fronts.p, d_foff.p, F->src.p, W.p, c->stream);
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    arena.top = 0;
+    std::vector<InvProb> inv;
+    for (int32_t id : lvl) {
+      const NdNode &n = tr.nodes[id];
+      inv.push_back({W.p + n.f_off, n.s, n.s + n.b});
+    }
+    inverse_batch(c, inv, arena);
+    std::vector<GemmProb> gG, gU;
+    std::vector<TransProb> t1, t2;
+    for (int32_t id : lvl) {
+      const NdNode &n = tr.nodes[id];
+      const int s = n.s, b = n.b, f = s + b;
+      double *Fp = W.p + n.f_off;
+      double *Rp = F->R.p + n.r_off;
+      t1.push_back({Fp, Rp, s, s, f, n.ldr, 1.0});
+      if (b == 0) continue;
+      double *G = arena.take(size_t(b) * s);
+      double *F21 = Fp + int64_t(s) * f, *F22 = F21 + s;
+      gG.push_back({F21, Fp, G, b, s, s, s, f, 1, f, 1, 1.0, 0.0});    // G = F21 * inv(F11)
+      gU.push_back({G, F21, F22, b, b, s, f, s, 1, 1, f, -1.0, 1.0});  // U = F22 - G * F21^T
+      t2.push_back({G, Rp + s, s, b, s, n.ldr, -1.0});                 // R[:, s:] = -G^T
+    }
+    run_gemm_batch(c, gG);
+    run_gemm_batch(c, gU);
+    run_trans_batch(c, t1);
+    run_trans_batch(c, t2);
+  }
+  int32_t failed = 0;
+  CUDA_CHECK(cudaMemcpy(&failed, c->d_fail.p, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (failed) fail(MMMFE_E_NUMERIC, "non-positive pivot in a front: the flux Schur complement is not SPD");
+
+  // ---- work lists of the solve ----
+  F->levels.resize(tr.by_height.size());
+  int64_t bytes = 0;
+  for (size_t h = 0; h < tr.by_height.size(); ++h) {
+    std::vector<int32_t> small;
+    std::vector<WorkItem> fwd, bwd;
+    for (int32_t id : tr.by_height[h]) {
+      const NdNode &n = tr.nodes[id];
+      const int64_t f = n.s + n.b;
+      bytes += 8 * (int64_t(n.s) * n.b + int64_t(n.s) * f) + 4 * (2 * f + 2 * f);
+      if (n.s <= 32 && n.b <= 64) { small.push_back(id); continue; }
+      const int rows_per = (n.s + n.nsplit - 1) / n.nsplit;
+      for (int sp = 0; sp < n.nsplit; ++sp) {
+        const int r0 = sp * rows_per, r1 = std::min(n.s, r0 + rows_per);
+        if (n.b == 0) fwd.push_back({id, r0, r1, 0, 0, sp});
+        for (int c0 = 0; c0 < n.b; c0 += 256) fwd.push_back({id, r0, r1, c0, std::min(n.b, c0 + 256), sp});
+      }
+      for (int r0 = 0; r0 < n.s; r0 += 32) bwd.push_back({id, r0, std::min(n.s, r0 + 32), 0, 0, 0});
+    }
+    LevelWork &lw = F->levels[h];
+    lw.n_small = int32_t(small.size()); lw.n_fwd = int32_t(fwd.size()); lw.n_bwd = int32_t(bwd.size());
+    lw.small_nodes.upload(small); lw.fwd.upload(fwd); lw.bwd.upload(bwd);
+  }
+  F->solve_bytes = bytes;
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  F->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return F;
+}
+
+static void run_solve(const Factor &F, int M, double *x, double *z, cudaStream_t st) {
+  SolveArgs a{F.fronts.p, F.R.p, F.idx_user.p, F.src.p, z, x};
+  const int H = int(F.levels.size());
+  for (int h = 0; h < H; ++h) {
+    const LevelWork &lw = F.levels[h];
+    launch_forward_small(M, a, lw.small_nodes.p, lw.n_small, st);
+    launch_forward_large(M, a, lw.fwd.p, lw.n_fwd, st);
+  }
+  for (int h = H - 1; h >= 0; --h) {
+    const LevelWork &lw = F.levels[h];
+    launch_backward_large(M, a, lw.bwd.p, lw.n_bwd, st);
+    launch_backward_small(M, a, lw.small_nodes.p, lw.n_small, st);
+  }
+}
+
+// =================================================================================================================
+// sweeps
+// =================================================================================================================
+enum SweepMode { SWEEP_BAR, SWEEP_STAR, SWEEP_FINAL };
+
+static void enqueue_sweep(mmmfe_ctx *c, Batch &b, SweepMode mode) {
+  const Factor &F = *b.factor;
+  cudaStream_t st = b.stream;
+  const bool bar = mode == SWEEP_BAR;
+  const bool with_hist = (bar && c->keep_history) || (mode == SWEEP_FINAL && c->keep_history);
+  launch_init_ptil(b.step, bar ? b.p0_ptr.p : nullptr, bar ? b.src_ptr.p : nullptr, st);
+  for (int lvl = 0; lvl < b.nt; ++lvl) {
+    launch_build_rhs(b.step, bar ? nullptr : c->lam_bar.p, lvl, st);
+    if (bar)
+      for (int j = 0; j < int(b.members.size()); ++j) {
+        const Sub &sd = *c->subs[b.members[j]];
+        launch_add_sparse(b.x.p, b.M, j, sd.fr_dofs.p, sd.fr_vals.p + int64_t(lvl) * sd.n_fr, sd.n_fr, st);
+      }
+    run_solve(F, b.M, b.x.p, b.z.p, st);
+    const bool has_next = bar && lvl + 1 < b.nt;
+    launch_update(b.step, c->trace.p, lvl, has_next ? b.src_ptr.p : nullptr, F.np, with_hist ? b.hist_ptr.p : nullptr,
+                  int64_t(F.nf) + F.np, mode == SWEEP_FINAL ? 1 : 0, st);
+  }
+}
+
+static void run_star_sweeps(mmmfe_ctx *c, SweepMode mode) {
+  CUDA_CHECK(cudaEventRecord(c->ev_start, c->stream));
+  for (auto &bp : c->batches) {
+    Batch &b = *bp;
+    CUDA_CHECK(cudaStreamWaitEvent(b.stream, c->ev_start, 0));
+    if (mode == SWEEP_STAR && c->use_graphs) {
+      if (!b.graph_star) {
+        cudaGraph_t g = nullptr;
+        CUDA_CHECK(cudaStreamBeginCapture(b.stream, cudaStreamCaptureModeThreadLocal));
+        enqueue_sweep(c, b, SWEEP_STAR);
+        CUDA_CHECK(cudaStreamEndCapture(b.stream, &g));
+        CUDA_CHECK(cudaGraphInstantiate(&b.graph_star, g, 0));
+        CUDA_CHECK(cudaGraphDestroy(g));
+      }
+      CUDA_CHECK(cudaGraphLaunch(b.graph_star, b.stream));
+    } else {
+      enqueue_sweep(c, b, mode);
+    }
+    CUDA_CHECK(cudaEventRecord(b.done, b.stream));
+    CUDA_CHECK(cudaStreamWaitEvent(c->stream, b.done, 0));
+  }
+}
+
+// send = s * f2c(trace); exchange with the neighbours; out = sign * (send + recv)
+static void exchange_and_combine(mmmfe_ctx *c, double sign, double *out) {
+  launch_spmv(c->n_iface, c->f2c_all.rp.p, c->f2c_all.col.p, c->f2c_all.val.p, c->trace.p, c->send.p, c->stream);
+#ifdef MMMFE_WITH_NCCL
+  if (!c->peers.empty()) {
+    launch_gather(int64_t(c->send_index.n), c->send.p, c->send_index.p, c->send_buf.p, c->stream);
+    nccl().GroupStart();
+    for (const auto &p : c->peers) {
+      nccl().Send(c->send_buf.p + p.send_off, size_t(p.count), ncclDouble, p.rank, c->comm, c->stream);
+      nccl().Recv(c->recv_buf.p + p.recv_off, size_t(p.count), ncclDouble, p.rank, c->comm, c->stream);
+    }
+    if (nccl().GroupEnd() != ncclSuccess) fail(MMMFE_E_COMM, "NCCL face exchange failed");
+  }
+#endif
+  launch_exchange_combine(c->n_iface, c->send.p, c->partner.p, c->recv_buf.p, sign, out, c->stream);
+}
+
+// Ap = S q for q resident in d_q (src/darcy_vtdd.cc:1316-1411)
+static void apply_operator(mmmfe_ctx *c, const double *d_q, double *d_ap) {
+  launch_spmv(c->n_fine, c->c2f_all.rp.p, c->c2f_all.col.p, c->c2f_all.val.p, d_q, c->lam_bar.p, c->stream);
+  run_star_sweeps(c, SWEEP_STAR);
+  exchange_and_combine(c, -1.0, d_ap);
+}
+
+static void allreduce_sum(mmmfe_ctx *c, double *d, size_t n) {
+#ifdef MMMFE_WITH_NCCL
+  if (c->world > 1) {
+    if (nccl().AllReduce(d, d, n, ncclDouble, ncclSum, c->comm, c->stream) != ncclSuccess)
+      fail(MMMFE_E_COMM, "NCCL allreduce failed");
+  }
+#else
+  (void)c; (void)d; (void)n;
+#endif
+}
+
+// =================================================================================================================
+// setup
+// =================================================================================================================
+static bool same_matrix(const Sub &a, const Sub &b) {
+  return a.nx == b.nx && a.ny == b.ny && a.nt == b.nt && a.nf == b.nf && a.np == b.np && a.dt == b.dt &&
+         a.canon == b.canon && a.matrix.rp == b.matrix.rp && a.matrix.col == b.matrix.col &&
+         a.matrix.val == b.matrix.val;
+}
+
+static void setup(mmmfe_ctx *c) {
+  if (c->is_setup) fail(MMMFE_E_INVALID, "mmmfe_setup called twice");
+  if (c->subs.empty()) fail(MMMFE_E_INVALID, "no subdomains registered");
+  CUDA_CHECK(cudaSetDevice(c->device));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventCreate(&c->ev_t0));
+  CUDA_CHECK(cudaEventCreate(&c->ev_t1));
+  const int ns = int(c->subs.size());
+  // ---- group identical matrices, factorise one representative each ----
+  std::vector<int> group_of(ns, -1);
+  std::vector<int> reps;
+  for (int i = 0; i < ns; ++i) {
+    for (size_t g = 0; g < reps.size(); ++g)
+      if (same_matrix(*c->subs[reps[g]], *c->subs[i])) { group_of[i] = int(g); break; }
+    if (group_of[i] < 0) { group_of[i] = int(reps.size()); reps.push_back(i); }
+  }
+  for (int rep : reps) {
+    c->factors.push_back(factorize(c, *c->subs[rep]));
+    c->factor_seconds += c->factors.back()->seconds;
+  }
+  // ---- interface and fine-trace layouts ----
+  int64_t io = 0, fo = 0;
+  std::map<std::pair<int, int>, int64_t> local_off;  // (gid, side) -> offset
+  for (auto &sp : c->subs)
+    for (int s = 0; s < 4; ++s)
+      if (sp->neighbor[s] >= 0) {
+        sp->iface_off[s] = io; io += sp->mortar_len[s];
+        sp->fine_off[s] = fo; fo += int64_t(sp->nt) * sp->n_side[s];
+        local_off[{sp->gid, s}] = sp->iface_off[s];
+      }
+  c->n_iface = io; c->n_fine = fo;
+  HostCsr c2f, f2c;
+  c2f.n_rows = fo; c2f.n_cols = io; c2f.rp.assign(1, 0);
+  f2c.n_rows = io; f2c.n_cols = fo; f2c.rp.assign(1, 0);
+  for (auto &sp : c->subs)
+    for (int s = 0; s < 4; ++s)
+      if (sp->neighbor[s] >= 0) {
+        const HostCsr &a = sp->c2f[s], &b = sp->f2c[s];
+        if (a.n_rows != int64_t(sp->nt) * sp->n_side[s] || a.n_cols != sp->mortar_len[s] ||
+            b.n_cols != a.n_rows || b.n_rows != a.n_cols)
+          fail(MMMFE_E_INVALID, "projector table shapes of subdomain %d side %d are inconsistent", sp->gid, s);
+        for (int64_t r = 0; r < a.n_rows; ++r) {
+          for (int64_t k = a.rp[r]; k < a.rp[r + 1]; ++k) {
+            c2f.col.push_back(int32_t(sp->iface_off[s] + a.col[k])); c2f.val.push_back(a.val[k]);
+          }
+          c2f.rp.push_back(int64_t(c2f.col.size()));
+        }
+        for (int64_t r = 0; r < b.n_rows; ++r) {
+          for (int64_t k = b.rp[r]; k < b.rp[r + 1]; ++k) {
+            f2c.col.push_back(int32_t(sp->fine_off[s] + b.col[k])); f2c.val.push_back(kNormalSign[s] * b.val[k]);
+          }
+          f2c.rp.push_back(int64_t(f2c.col.size()));
+        }
+      }
+  c->c2f_all.upload(c2f); c->f2c_all.upload(f2c);
+  // ---- exchange plan ----
+  std::vector<int64_t> partner(size_t(io), -1);
+  struct Seg { int peer; int key_gid, key_side; int64_t off, len; };
+  std::vector<Seg> send_segs, recv_segs;
+  for (auto &sp : c->subs)
+    for (int s = 0; s < 4; ++s)
+      if (sp->neighbor[s] >= 0) {
+        const int nb = sp->neighbor[s];
+        const int owner = (c->world > 1 && !c->owner.empty()) ? c->owner[nb] : c->rank;
+        if (owner == c->rank) {
+          auto it = local_off.find({nb, kOpposite[s]});
+          if (it == local_off.end()) fail(MMMFE_E_INVALID, "neighbour %d of subdomain %d is not registered", nb, sp->gid);
+          for (int64_t i = 0; i < sp->mortar_len[s]; ++i) partner[sp->iface_off[s] + i] = it->second + i;
+        } else {
+          send_segs.push_back({owner, sp->gid, s, sp->iface_off[s], sp->mortar_len[s]});
+          recv_segs.push_back({owner, nb, kOpposite[s], sp->iface_off[s], sp->mortar_len[s]});
+        }
+      }
+  auto by_key = [](const Seg &a, const Seg &b) {
+    if (a.peer != b.peer) return a.peer < b.peer;
+    if (a.key_gid != b.key_gid) return a.key_gid < b.key_gid;
+    return a.key_side < b.key_side;
+  };
+  std::sort(send_segs.begin(), send_segs.end(), by_key);
+  std::sort(recv_segs.begin(), recv_segs.end(), by_key);
+  std::vector<int64_t> send_index;
+  int64_t roff = 0;
+  for (size_t i = 0; i < send_segs.size(); ++i) {
+    const Seg &sg = send_segs[i], &rg = recv_segs[i];
+    if (c->peers.empty() || c->peers.back().rank != sg.peer) c->peers.push_back({sg.peer, int64_t(send_index.size()), roff, 0});
+    for (int64_t k = 0; k < sg.len; ++k) send_index.push_back(sg.off + k);
+    for (int64_t k = 0; k < rg.len; ++k) partner[rg.off + k] = -(roff + k) - 2;
+    roff += rg.len;
+    c->peers.back().count += sg.len;
+  }
+  for (int64_t v : partner) if (v == -1) fail(MMMFE_E_INVALID, "interface entry without a partner");
+  c->partner.upload(partner);
+  c->send_index.upload(send_index);
+  c->send_buf.alloc(send_index.size() + 1);
+  c->recv_buf.alloc(size_t(roff) + 1);
+  c->lam_bar.alloc(size_t(fo)); c->trace.alloc(size_t(fo));
+  c->send.alloc(size_t(io)); c->ap.alloc(size_t(io)); c->qin.alloc(size_t(io)); c->lam.alloc(size_t(io));
+  c->r0.alloc(size_t(io));
+  c->lam_bar.zero(); c->trace.zero(); c->qin.zero(); c->lam.zero();
+  // ---- batches ----
+  for (size_t g = 0; g < reps.size(); ++g) {
+    std::vector<int32_t> mem;
+    for (int i = 0; i < ns; ++i) if (group_of[i] == int(g)) mem.push_back(i);
+    for (size_t m0 = 0; m0 < mem.size(); m0 += 4) {
+      auto b = std::make_unique<Batch>();
+      b->factor = c->factors[g];
+      b->members.assign(mem.begin() + m0, mem.begin() + std::min(mem.size(), m0 + 4));
+      const int cnt = int(b->members.size());
+      b->M = cnt <= 1 ? 1 : (cnt == 2 ? 2 : 4);
+      b->nt = c->subs[b->members[0]]->nt;
+      const Factor &F = *b->factor;
+      b->x.alloc(size_t(F.nf) * b->M); b->x.zero();
+      b->z.alloc(size_t(F.tree.z_total) * b->M); b->z.zero();
+      b->ptil.alloc(size_t(F.np) * b->M); b->ptil.zero();
+      std::vector<int32_t> tr_dof, tr_mem, tr_stride, iface_q(size_t(F.nf) * b->M, -1);
+      std::vector<int64_t> tr_base;
+      std::vector<double> tr_sign;
+      for (int j = 0; j < cnt; ++j) {
+        Sub &sd = *c->subs[b->members[j]];
+        sd.batch = int32_t(c->batches.size()); sd.member = j;
+        for (int s = 0; s < 4; ++s)
+          if (sd.neighbor[s] >= 0)
+            for (int i = 0; i < sd.n_side[s]; ++i) {
+              const int32_t d = sd.side_dofs[s][i];
+              if (d < 0 || d >= sd.nf) fail(MMMFE_E_INVALID, "side_dofs out of range");
+              iface_q[size_t(d) * b->M + j] = int32_t(tr_dof.size());
+              tr_dof.push_back(d); tr_mem.push_back(j); tr_stride.push_back(sd.n_side[s]);
+              tr_base.push_back(sd.fine_off[s] + i); tr_sign.push_back(kNormalSign[s]);
+            }
+      }
+      b->n_tr = int32_t(tr_dof.size());
+      b->tr_dof.upload(tr_dof); b->tr_mem.upload(tr_mem); b->tr_stride.upload(tr_stride);
+      b->tr_base.upload(tr_base); b->tr_sign.upload(tr_sign); b->iface_q.upload(iface_q);
+      CUDA_CHECK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming));
+      b->step = StepArgs{b->M, F.nf, F.np, F.kup.rp.p, F.kup.col.p, F.kup.val.p, F.kpu.rp.p, F.kpu.col.p,
+                         F.kpu.val.p, F.minv.p, b->x.p, b->ptil.p, b->n_tr, b->tr_dof.p, b->tr_mem.p,
+                         b->tr_stride.p, b->tr_base.p, b->tr_sign.p, b->iface_q.p};
+      c->batches.push_back(std::move(b));
+    }
+  }
+  CUDA_CHECK(cudaDeviceSynchronize());
+  c->is_setup = true;
+}
+
+static void bar_sweep(mmmfe_ctx *c) {
+  if (!c->is_setup) fail(MMMFE_E_INVALID, "mmmfe_setup must precede the bar sweep");
+  for (auto &bp : c->batches) {
+    Batch &b = *bp;
+    std::vector<const double *> p0(b.M, nullptr), src(b.M, nullptr);
+    std::vector<double *> hist(b.M, nullptr);
+    for (size_t j = 0; j < b.members.size(); ++j) {
+      Sub &sd = *c->subs[b.members[j]];
+      if (!sd.has_bar_data) fail(MMMFE_E_INVALID, "subdomain %d has no bar data", sd.gid);
+      p0[j] = sd.p0.p; src[j] = sd.src.p;
+      if (c->keep_history) {
+        sd.hist.alloc(size_t(sd.nt) * (size_t(sd.nf) + sd.np));
+        hist[j] = sd.hist.p;
+      }
+    }
+    b.p0_ptr.upload(p0); b.src_ptr.upload(src); b.hist_ptr.upload(hist);
+  }
+  run_star_sweeps(c, SWEEP_BAR);
+  // initial residual r = send + recv of the signed bar traces in mortar space (src/darcy_vtdd.cc:1203-1256)
+  exchange_and_combine(c, 1.0, c->r0.p);
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  c->bar_done = true;
+  c->final_done = false;
+}
+
+// local_gmres, src/darcy_vtdd.cc:1139-1521
+static void gmres(mmmfe_ctx *c, double tol, int max_iter, mmmfe_gmres_info *info, double *hist, int hist_cap,
+                  double *lambda_out) {
+  if (!c->bar_done) fail(MMMFE_E_INVALID, "mmmfe_bar_sweep must precede mmmfe_gmres_solve");
+  const auto t_begin = std::chrono::steady_clock::now();
+  const int64_t len = c->n_iface;
+  const int64_t rows = int64_t(max_iter) + 2;
+  if (c->q_rows < rows) { c->Q.alloc(size_t(rows) * len); c->q_rows = rows; }
+  c->h_dev.alloc(size_t(max_iter) + 4);
+  c->norm_dev.alloc(1024);
+  cudaStream_t st = c->stream;
+  double *Q = c->Q.p;
+  // initial residual r was formed at the end of the bar sweep
+  launch_multi_dot(len, c->r0.p, c->r0.p, len, 1, c->h_dev.p, st);
+  allreduce_sum(c, c->h_dev.p, 1);
+  double rr = 0.0;
+  CUDA_CHECK(cudaMemcpyAsync(&rr, c->h_dev.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  const double r_norm = std::sqrt(rr);  // :1265-1276
+  launch_scale_store(len, c->r0.p, r_norm, Q, st);  // Q[0] = r / r_norm, :1280-1285
+  std::vector<double> cs, sn, beta{r_norm};
+  std::vector<std::vector<double>> H;
+  std::vector<double> res{1.0};
+  std::vector<double> hh(size_t(max_iter) + 4);
+  int k = 0, its = 0, converged = 0;
+  while (k < max_iter) {
+    apply_operator(c, Q + int64_t(k) * len, c->ap.p);
+    ++its;  // cg_iteration++, :1363
+    launch_multi_dot(len, c->ap.p, Q, len, k + 1, c->h_dev.p, st);  // :1416-1422
+    allreduce_sum(c, c->h_dev.p, size_t(k) + 1);                      // :1427-1432
+    launch_cgs_update(len, c->ap.p, Q, len, k + 1, c->h_dev.p, c->norm_dev.p, st);  // :1436-1441
+    allreduce_sum(c, c->norm_dev.p, 1);                                               // :1449-1454
+    CUDA_CHECK(cudaMemcpyAsync(hh.data(), c->h_dev.p, (size_t(k) + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    double n2 = 0.0;
+    CUDA_CHECK(cudaMemcpyAsync(&n2, c->norm_dev.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    std::vector<double> h(hh.begin(), hh.begin() + k + 1);
+    h.push_back(std::sqrt(n2));  // :1455
+    launch_scale_store(len, c->ap.p, h[k + 1], Q + int64_t(k + 1) * len, st);  // :1458-1463
+    // apply_givens_rotation, :1092-1118
+    for (int i = 0; i < k; ++i) {
+      const double temp = cs[i] * h[i] + sn[i] * h[i + 1];
+      h[i + 1] = -sn[i] * h[i] + cs[i] * h[i + 1];
+      h[i] = temp;
+    }
+    double cs_k, sn_k;
+    const double v1 = h[k], v2 = h[k + 1];
+    if (std::fabs(v1) < 1e-15) { cs_k = 0; sn_k = 1; }  // givens_rotation, :1076-1087
+    else { const double t = std::sqrt(v1 * v1 + v2 * v2); cs_k = std::fabs(v1) / t; sn_k = cs_k * v2 / v1; }
+    h[k] = cs_k * h[k] + sn_k * h[k + 1];
+    h[k + 1] = 0.0;
+    cs.push_back(cs_k); sn.push_back(sn_k);
+    H.push_back(h);
+    beta.push_back(-sn[k] * beta[k]);  // :1474
+    beta[k] *= cs[k];                  // :1475
+    const double err = std::fabs(beta[k + 1]) / r_norm;  // :1478
+    res.push_back(err);
+    if (err < tol) { converged = 1; break; }  // :1488-1492, k not incremented (quirk Q1)
+    ++k;
+  }
+  // back_solve over k columns, :1121-1135; y[k] stays 0
+  std::vector<double> y(size_t(k) + 1, 0.0);
+  for (int i = k - 1; i >= 0; --i) {
+    y[i] = beta[i] / H[i][i];
+    for (int j = i + 1; j <= k - 1; ++j) y[i] -= H[j][i] * y[j] / H[i][i];
+  }
+  CUDA_CHECK(cudaMemcpyAsync(c->h_dev.p, y.data(), y.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  launch_axpy_rows(len, Q, len, k + 1, c->h_dev.p, c->lam.p, st);  // :1517-1521
+  if (lambda_out) CUDA_CHECK(cudaMemcpyAsync(lambda_out, c->lam.p, size_t(len) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  if (info) {
+    info->iterations = its; info->converged = converged; info->r_norm = r_norm; info->final_residual = res.back();
+    info->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+  }
+  if (hist) for (int i = 0; i < hist_cap && i < int(res.size()); ++i) hist[i] = res[i];
+}
+
+}  // namespace mmmfe
+
+// =================================================================================================================
+// C ABI
+// =================================================================================================================
+#define MMMFE_TRY(ctx, ...)                        \
+  try {                                            \
+    __VA_ARGS__;                                   \
+    return MMMFE_OK;                               \
+  } catch (const mmmfe::Error &e) {                \
+    if (ctx) (ctx)->err = e.msg;                   \
+    return e.code;                                 \
+  } catch (const std::exception &e) {              \
+    if (ctx) (ctx)->err = e.what();                \
+    return MMMFE_E_INVALID;                        \
+  }
+
+extern "C" {
+
+const char *mmmfe_version(void) { return "mmmfe-b200 0.1 (sm_100a)"; }
+
+int mmmfe_create(mmmfe_ctx **out, int device) {
+  if (!out) return MMMFE_E_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return MMMFE_E_CUDA;
+  auto *c = new mmmfe_ctx();
+  if (device < 0) cudaGetDevice(&device);
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete c; return MMMFE_E_CUDA; }
+  *out = c;
+  return MMMFE_OK;
+}
+
+int mmmfe_destroy(mmmfe_ctx *c) {
+  if (!c) return MMMFE_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto &b : c->batches) {
+    if (b->graph_star) cudaGraphExecDestroy(b->graph_star);
+    if (b->done) cudaEventDestroy(b->done);
+    if (b->stream) cudaStreamDestroy(b->stream);
+  }
+#ifdef MMMFE_WITH_NCCL
+  if (c->comm) nccl().CommDestroy(c->comm);
+#endif
+  if (c->ev_start) cudaEventDestroy(c->ev_start);
+  if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+  if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return MMMFE_OK;
+}
+
+const char *mmmfe_last_error(const mmmfe_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
+  if (!c || !key) return MMMFE_E_INVALID;
+  const std::string k(key);
+  if (k == "keep_history") c->keep_history = value != 0;
+  else if (k == "use_graphs") c->use_graphs = value != 0;
+  else if (k == "leaf_cells") c->leaf_cells = std::max(1, int(value));
+  else { c->err = "unknown option " + k; return MMMFE_E_INVALID; }
+  return MMMFE_OK;
+}
+
+int mmmfe_comm_unique_id_size(void) {
+#ifdef MMMFE_WITH_NCCL
+  return int(sizeof(ncclUniqueId));
+#else
+  return 0;
+#endif
+}
+
+int mmmfe_comm_unique_id(void *id_out) {
+#ifdef MMMFE_WITH_NCCL
+  ncclUniqueId id;
+  if (!nccl().ok || nccl().GetUniqueId(&id) != ncclSuccess) return MMMFE_E_COMM;
+  std::memcpy(id_out, &id, sizeof id);
+  return MMMFE_OK;
+#else
+  (void)id_out;
+  return MMMFE_E_UNSUPPORTED;
+#endif
+}
+
+int mmmfe_comm_init(mmmfe_ctx *c, int rank, int world, const void *id) {
+  if (!c || world < 1 || rank < 0 || rank >= world) return MMMFE_E_INVALID;
+  c->rank = rank; c->world = world;
+  if (world == 1) return MMMFE_OK;
+#ifdef MMMFE_WITH_NCCL
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, sizeof uid);
+  cudaSetDevice(c->device);
+  if (!nccl().ok) { c->err = "libnccl.so.2 could not be loaded"; return MMMFE_E_COMM; }
+  if (nccl().CommInitRank(&c->comm, world, uid, rank) != ncclSuccess) { c->err = "ncclCommInitRank failed"; return MMMFE_E_COMM; }
+  return MMMFE_OK;
+#else
+  (void)id;
+  c->err = "built without NCCL";
+  return MMMFE_E_UNSUPPORTED;
+#endif
+}
+
+int mmmfe_set_owners(mmmfe_ctx *c, int32_t n_global, const int32_t *owner_rank) {
+  if (!c || n_global <= 0 || !owner_rank) return MMMFE_E_INVALID;
+  c->owner.assign(owner_rank, owner_rank + n_global);
+  return MMMFE_OK;
+}
+
+int mmmfe_add_subdomain(mmmfe_ctx *c, const mmmfe_subdomain *d, int32_t *local_index) {
+  if (!c || !d) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, {
+    if (c->is_setup) fail(MMMFE_E_INVALID, "subdomains must be added before mmmfe_setup");
+    if (d->nx < 1 || d->ny < 1 || d->nt < 1 || !(d->dt > 0)) fail(MMMFE_E_INVALID, "bad mesh pattern");
+    auto s = std::make_unique<Sub>();
+    s->gid = d->global_id; s->nx = d->nx; s->ny = d->ny; s->nt = d->nt; s->dt = d->dt;
+    s->nf = d->n_flux; s->np = d->n_pressure;
+    if (int64_t(s->np) != int64_t(d->nx) * d->ny) fail(MMMFE_E_UNSUPPORTED, "only DGQ0 pressures (one per cell) are on the path");
+    s->matrix.from(d->matrix);
+    if (d->canon_of_dof) s->canon.assign(d->canon_of_dof, d->canon_of_dof + d->n_flux);
+    for (int k = 0; k < 4; ++k) {
+      s->neighbor[k] = d->neighbor[k]; s->n_side[k] = d->n_side[k]; s->mortar_len[k] = d->mortar_len[k];
+      if (d->neighbor[k] >= 0) {
+        if (!d->side_dofs[k]) fail(MMMFE_E_INVALID, "side_dofs missing for side %d", k);
+        s->side_dofs[k].assign(d->side_dofs[k], d->side_dofs[k] + d->n_side[k]);
+        s->f2c[k].from(d->f2c[k]);
+        s->c2f[k].from(d->c2f[k]);
+      }
+    }
+    if (local_index) *local_index = int32_t(c->subs.size());
+    c->subs.push_back(std::move(s));
+  });
+}
+
+int mmmfe_setup(mmmfe_ctx *c) {
+  if (!c) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, setup(c));
+}
+
+int64_t mmmfe_interface_length(const mmmfe_ctx *c) { return c ? c->n_iface : -1; }
+
+int64_t mmmfe_interface_offset(const mmmfe_ctx *c, int32_t li, int32_t side) {
+  if (!c || li < 0 || li >= int32_t(c->subs.size()) || side < 0 || side > 3) return -1;
+  return c->subs[li]->iface_off[side];
+}
+
+int32_t mmmfe_num_factor_groups(const mmmfe_ctx *c) { return c ? int32_t(c->factors.size()) : -1; }
+
+int64_t mmmfe_factor_values(const mmmfe_ctx *c) {
+  int64_t v = 0;
+  if (c) for (auto &f : c->factors) v += f->tree.r_total;
+  return v;
+}
+
+int64_t mmmfe_step_bytes(const mmmfe_ctx *c) {
+  // one star step of every local subdomain: each batch streams its factor once (forward G, backward [F11^-1|G])
+  // plus 8 * (2 n + 2 sum n_side) bytes of vector traffic per member
+  int64_t v = 0;
+  if (!c) return 0;
+  for (auto &b : c->batches) {
+    v += b->factor->solve_bytes;
+    v += int64_t(b->members.size()) * 16 * (int64_t(b->factor->nf) + b->factor->np);
+    v += 16 * int64_t(b->n_tr);
+  }
+  return v;
+}
+
+double mmmfe_factor_flops(const mmmfe_ctx *c) {
+  double v = 0;
+  if (c) for (auto &f : c->factors) v += f->tree.factor_flops;
+  return v;
+}
+
+double mmmfe_factor_seconds(const mmmfe_ctx *c) { return c ? c->factor_seconds : 0.0; }
+
+int mmmfe_bar_set_data(mmmfe_ctx *c, int32_t li, const double *p0, const double *src, int32_t n_fr,
+                       const int32_t *fr_dofs, const double *fr_vals) {
+  if (!c || li < 0 || li >= int32_t(c->subs.size()) || !src) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, {
+    Sub &sd = *c->subs[li];
+    CUDA_CHECK(cudaSetDevice(c->device));
+    if (p0) sd.p0.upload(p0, size_t(sd.np)); else { sd.p0.alloc(size_t(sd.np)); sd.p0.zero(); }
+    sd.src.upload(src, size_t(sd.nt) * sd.np);
+    sd.n_fr = n_fr;
+    sd.fr_dofs.upload(fr_dofs, size_t(n_fr));
+    sd.fr_vals.upload(fr_vals, size_t(n_fr) * sd.nt);
+    sd.has_bar_data = true;
+  });
+}
+
+int mmmfe_bar_sweep(mmmfe_ctx *c) {
+  if (!c) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, bar_sweep(c));
+}
+
+int mmmfe_apply_interface_operator(mmmfe_ctx *c, const double *q, double *ap) {
+  if (!c || !q || !ap) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, {
+    if (!c->is_setup) fail(MMMFE_E_INVALID, "mmmfe_setup first");
+    const size_t bytes = size_t(c->n_iface) * sizeof(double);
+    CUDA_CHECK(cudaMemcpyAsync(c->qin.p, q, bytes, cudaMemcpyHostToDevice, c->stream));
+    apply_operator(c, c->qin.p, c->ap.p);
+    CUDA_CHECK(cudaMemcpyAsync(ap, c->ap.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int mmmfe_apply_interface_operator_device(mmmfe_ctx *c, int32_t repeat, double *ms) {
+  if (!c || repeat < 1) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, {
+    if (!c->is_setup) fail(MMMFE_E_INVALID, "mmmfe_setup first");
+    CUDA_CHECK(cudaEventRecord(c->ev_t0, c->stream));
+    for (int i = 0; i < repeat; ++i) apply_operator(c, c->qin.p, c->ap.p);
+    CUDA_CHECK(cudaEventRecord(c->ev_t1, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    float t = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&t, c->ev_t0, c->ev_t1));
+    if (ms) *ms = double(t) / repeat;
+  });
+}
+
+int mmmfe_gmres_solve(mmmfe_ctx *c, double tol, int32_t max_iter, mmmfe_gmres_info *info, double *hist,
+                      int32_t hist_cap, double *lambda_out) {
+  if (!c || max_iter < 1) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, gmres(c, tol, max_iter, info, hist, hist_cap, lambda_out));
+}
+
+int mmmfe_final_sweep(mmmfe_ctx *c) {
+  if (!c) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, {
+    if (!c->bar_done) fail(MMMFE_E_INVALID, "bar sweep first");
+    if (c->final_done) fail(MMMFE_E_INVALID, "final sweep already done for this bar sweep");
+    launch_spmv(c->n_fine, c->c2f_all.rp.p, c->c2f_all.col.p, c->c2f_all.val.p, c->lam.p, c->lam_bar.p, c->stream);
+    run_star_sweeps(c, SWEEP_FINAL);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->final_done = true;
+  });
+}
+
+int mmmfe_get_solution(mmmfe_ctx *c, int32_t li, double *solution) {
+  if (!c || li < 0 || li >= int32_t(c->subs.size()) || !solution) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, {
+    Sub &sd = *c->subs[li];
+    if (!sd.hist.p) fail(MMMFE_E_INVALID, "no stored solution (keep_history = 0 or no sweep yet)");
+    CUDA_CHECK(cudaMemcpy(solution, sd.hist.p, sd.hist.n * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
+int mmmfe_get_star_trace(mmmfe_ctx *c, int32_t li, int32_t side, double *trace) {
+  if (!c || li < 0 || li >= int32_t(c->subs.size()) || side < 0 || side > 3 || !trace) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, {
+    Sub &sd = *c->subs[li];
+    if (sd.fine_off[side] < 0) fail(MMMFE_E_INVALID, "side %d has no neighbour", side);
+    CUDA_CHECK(cudaMemcpy(trace, c->trace.p + sd.fine_off[side], size_t(sd.nt) * sd.n_side[side] * sizeof(double),
+                          cudaMemcpyDeviceToHost));
+  });
+}
+
+int mmmfe_solve_saddle(mmmfe_ctx *c, int32_t li, const double *rhs, double *x) {
+  if (!c || li < 0 || li >= int32_t(c->subs.size()) || !rhs || !x) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, {
+    if (!c->is_setup) fail(MMMFE_E_INVALID, "mmmfe_setup first");
+    Sub &sd = *c->subs[li];
+    const Factor &F = *c->batches[sd.batch]->factor;
+    cudaStream_t st = c->stream;
+    DevBuf<double> d_rhs, xv, z, pt, out;
+    d_rhs.upload(rhs, size_t(F.nf) + F.np);
+    xv.alloc(size_t(F.nf)); z.alloc(size_t(F.tree.z_total)); pt.alloc(size_t(F.np)); out.alloc(size_t(F.nf) + F.np);
+    DevBuf<int32_t> dofs;
+    std::vector<int32_t> all(F.nf);
+    for (int32_t i = 0; i < F.nf; ++i) all[i] = i;
+    dofs.upload(all);
+    std::vector<const double *> srcp{d_rhs.p + F.nf};
+    std::vector<double *> histp{out.p};
+    DevBuf<const double *> d_srcp;
+    DevBuf<double *> d_histp;
+    d_srcp.upload(srcp); d_histp.upload(histp);
+    StepArgs a{1, F.nf, F.np, F.kup.rp.p, F.kup.col.p, F.kup.val.p, F.kpu.rp.p, F.kpu.col.p, F.kpu.val.p,
+               F.minv.p, xv.p, pt.p, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    launch_init_ptil(a, nullptr, d_srcp.p, st);
+    launch_build_rhs(a, nullptr, 0, st);
+    launch_add_sparse(xv.p, 1, 0, dofs.p, d_rhs.p, F.nf, st);
+    run_solve(F, 1, xv.p, z.p, st);
+    launch_update(a, nullptr, 0, nullptr, F.np, d_histp.p, int64_t(F.nf) + F.np, 0, st);
+    CUDA_CHECK(cudaMemcpyAsync(x, out.p, out.n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+}  // extern "C"

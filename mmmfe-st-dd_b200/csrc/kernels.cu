@@ -1,0 +1,725 @@
+// CUDA kernels of the interface-GMRES engine, written for sm_100a (B200).
+//
+//  * factorisation: grouped FP64 GEMM on the tensor cores (DMMA, mma.sync.m8n8k4.f64 -- tcgen05 has no f64
+//    kind), warp-level Gauss-Jordan for the <=32x32 base blocks, front assembly / extend-add;
+//  * solve: level-scheduled block-inverse multifrontal sweeps (every front is one dense GEMV, no triangular
+//    solves), batched over the M subdomains that share a factor; HBM-bound, coalesced row streaming;
+//  * time stepping, projector SpMV, exchange/combine and the classical Gram-Schmidt kernels.
+#include "kernels.cuh"
+
+namespace mmmfe {
+
+// =================================================================================================================
+// grouped GEMM  C = alpha * A * B + beta * C   (FP64, DMMA)
+// =================================================================================================================
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+constexpr int GT = 64;  // C tile
+constexpr int GK = 16;  // k step
+
+__global__ void __launch_bounds__(256) k_grouped_gemm(const GemmProb *__restrict__ probs,
+                                                      const int32_t *__restrict__ tile_start, int32_t n_probs) {
+  __shared__ double As[GT][GK + 1];
+  __shared__ double Bs[GK][GT + 1];
+  // locate the problem of this tile
+  int lo = 0, hi = n_probs - 1;
+  const int tile = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tile_start[mid] <= tile) lo = mid; else hi = mid - 1;
+  }
+  const GemmProb pr = probs[lo];
+  const int local = tile - tile_start[lo];
+  const int tiles_n = (pr.n + GT - 1) / GT;
+  const int tm = local / tiles_n, tn = local % tiles_n;
+  const int row0 = tm * GT, col0 = tn * GT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;  // 4 x 2 warps, each 16 rows x 32 cols
+  double acc[2][4][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const bool a_rowmajor = (pr.acs == 1);
+  const bool b_rowmajor = (pr.bcs == 1);
+  for (int k0 = 0; k0 < pr.k; k0 += GK) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = tid + 256 * r;
+      int i, kk;
+      if (a_rowmajor) { i = e / GK; kk = e % GK; } else { i = e % GT; kk = e / GT; }
+      const int gi = row0 + i, gk = k0 + kk;
+      As[i][kk] = (gi < pr.m && gk < pr.k) ? pr.A[gi * pr.ars + gk * pr.acs] : 0.0;
+      int j;
+      if (b_rowmajor) { kk = e / GT; j = e % GT; } else { kk = e % GK; j = e / GK; }
+      const int gj = col0 + j;
+      const int gk2 = k0 + kk;
+      Bs[kk][j] = (gj < pr.n && gk2 < pr.k) ? pr.B[gk2 * pr.brs + gj * pr.bcs] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; kk += 4) {
+      double a[2], b[4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) a[i] = As[wm * 16 + i * 8 + (lane >> 2)][kk + (lane & 3)];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk + (lane & 3)][wn * 32 + j * 8 + (lane >> 2)];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gi = row0 + wm * 16 + i * 8 + (lane >> 2);
+      const int gj = col0 + wn * 32 + j * 8 + (lane & 3) * 2;
+      if (gi < pr.m) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+          if (gj + t < pr.n) {
+            double *c = pr.C + int64_t(gi) * pr.ldc + gj + t;
+            const double old = (pr.beta == 0.0) ? 0.0 : pr.beta * (*c);
+            *c = pr.alpha * acc[i][j][t] + old;
+          }
+      }
+    }
+}
+
+void launch_grouped_gemm(const GemmProb *d_probs, const int32_t *d_tile_start, int32_t n_probs, int32_t n_tiles,
+                         cudaStream_t st) {
+  if (n_tiles <= 0) return;
+  k_grouped_gemm<<<n_tiles, 256, 0, st>>>(d_probs, d_tile_start, n_probs);
+}
+
+// =================================================================================================================
+// in-place inverse of SPD blocks with n <= 32: one warp per block, Gauss-Jordan without pivoting
+// =================================================================================================================
+__global__ void __launch_bounds__(128) k_small_inverse(const InvProb *__restrict__ probs, int32_t n_probs,
+                                                       int32_t *fail) {
+  __shared__ double sm[4][32][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pi = blockIdx.x * 4 + warp;
+  if (pi >= n_probs) return;
+  const InvProb pr = probs[pi];
+  const int n = pr.n;
+  double(*a)[33] = sm[warp];
+  for (int i = 0; i < n; ++i)
+    if (lane < n) a[i][lane] = pr.A[int64_t(i) * pr.ld + lane];
+  __syncwarp();
+  for (int k = 0; k < n; ++k) {
+    const double d = a[k][k];
+    if (!(d > 0.0) && lane == 0) atomicExch(fail, 1);
+    __syncwarp();
+    const double inv = 1.0 / d;
+    if (lane < n) a[k][lane] = (lane == k) ? inv : a[k][lane] * inv;
+    __syncwarp();
+    for (int i = 0; i < n; ++i) {
+      if (i == k) continue;
+      const double f = a[i][k];
+      __syncwarp();
+      if (lane < n) a[i][lane] = (lane == k) ? -f * inv : a[i][lane] - f * a[k][lane];
+      __syncwarp();
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    if (lane < n) pr.A[int64_t(i) * pr.ld + lane] = a[i][lane];
+}
+
+void launch_small_inverse(const InvProb *d_probs, int32_t n_probs, int32_t *d_fail, cudaStream_t st) {
+  if (n_probs <= 0) return;
+  k_small_inverse<<<(n_probs + 3) / 4, 128, 0, st>>>(d_probs, n_probs, d_fail);
+}
+
+__global__ void __launch_bounds__(256) k_transpose(const TransProb *__restrict__ probs) {
+  const TransProb pr = probs[blockIdx.x];
+  for (int i = blockIdx.y; i < pr.rows; i += gridDim.y)
+    for (int j = threadIdx.x; j < pr.cols; j += blockDim.x)
+      pr.dst[int64_t(i) * pr.ld_dst + j] = pr.scale * pr.src[int64_t(j) * pr.ld_src + i];
+}
+
+void launch_transpose(const TransProb *d_probs, int32_t n_probs, cudaStream_t st) {
+  if (n_probs <= 0) return;
+  for (int32_t off = 0; off < n_probs; off += 32768) {
+    const int32_t cnt = n_probs - off < 32768 ? n_probs - off : 32768;
+    k_transpose<<<dim3(cnt, 16), 256, 0, st>>>(d_probs + off);
+  }
+}
+
+// =================================================================================================================
+// front assembly
+// =================================================================================================================
+__global__ void __launch_bounds__(256)
+k_assemble_original(int64_t n_flux, const int64_t *__restrict__ s_rp, const int32_t *__restrict__ s_col,
+                    const double *__restrict__ s_val, const int32_t *__restrict__ canon_of_dof,
+                    const int32_t *__restrict__ node_of, const int32_t *__restrict__ pos_of,
+                    const FrontDesc *__restrict__ fronts, const int64_t *__restrict__ f_off,
+                    const int32_t *__restrict__ idx_canon, double *F) {
+  const int64_t v = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (v >= n_flux) return;
+  const int32_t cv = canon_of_dof ? canon_of_dof[v] : int32_t(v);
+  const int32_t node = node_of[cv];
+  const int32_t p = pos_of[cv];
+  const FrontDesc fd = fronts[node];
+  const int64_t f = fd.s + fd.b;
+  double *Fp = F + f_off[node];
+  const int32_t *bnd = idx_canon + fd.idx_off + fd.s;
+  for (int64_t e = s_rp[v]; e < s_rp[v + 1]; ++e) {
+    const int32_t c = s_col[e];
+    const int32_t cc = canon_of_dof ? canon_of_dof[c] : c;
+    const double val = s_val[e];
+    if (node_of[cc] == node) {
+      Fp[p * f + pos_of[cc]] = val;
+    } else {
+      int lo = 0, hi = fd.b - 1, q = -1;
+      while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const int32_t t = bnd[mid];
+        if (t == cc) { q = mid; break; }
+        if (t < cc) lo = mid + 1; else hi = mid - 1;
+      }
+      if (q >= 0) {
+        Fp[p * f + fd.s + q] = val;
+        Fp[(fd.s + q) * f + p] = val;
+      }
+    }
+  }
+}
+
+void launch_assemble_original(int64_t n_flux, const int64_t *s_rp, const int32_t *s_col, const double *s_val,
+                              const int32_t *canon_of_dof, const int32_t *, const int32_t *node_of,
+                              const int32_t *pos_of, const FrontDesc *fronts, const int64_t *f_off,
+                              const int32_t *idx_canon, double *F, cudaStream_t st) {
+  k_assemble_original<<<unsigned((n_flux + 255) / 256), 256, 0, st>>>(n_flux, s_rp, s_col, s_val, canon_of_dof,
+                                                                      node_of, pos_of, fronts, f_off, idx_canon, F);
+}
+
+__global__ void __launch_bounds__(256)
+k_extend_add(const int32_t *__restrict__ nodes, const FrontDesc *__restrict__ fronts,
+             const int64_t *__restrict__ f_off, const int32_t *__restrict__ src, double *F) {
+  const int32_t node = nodes[blockIdx.x];
+  const FrontDesc fd = fronts[node];
+  const int32_t f = fd.s + fd.b;
+  double *Fp = F + f_off[node];
+  for (int c = 0; c < 2; ++c) {
+    const int32_t ch = c ? fd.child1 : fd.child0;
+    if (ch < 0) continue;
+    const FrontDesc cd = fronts[ch];
+    const int32_t fc = cd.s + cd.b;
+    const double *Fc = F + f_off[ch];
+    const int32_t *sm = src + fd.src_off + int64_t(c) * f;
+    for (int p1 = blockIdx.y; p1 < f; p1 += gridDim.y) {
+      const int32_t q1 = sm[p1];
+      if (q1 < 0) continue;
+      for (int p2 = threadIdx.x; p2 < f; p2 += blockDim.x) {
+        const int32_t q2 = sm[p2];
+        if (q2 >= 0) Fp[int64_t(p1) * f + p2] += Fc[int64_t(cd.s + q1) * fc + cd.s + q2];
+      }
+    }
+  }
+}
+
+void launch_extend_add(const int32_t *d_nodes, int32_t n_nodes, const FrontDesc *fronts, const int64_t *f_off,
+                       const int32_t *src, double *F, cudaStream_t st) {
+  for (int32_t off = 0; off < n_nodes; off += 32768) {
+    const int32_t cnt = n_nodes - off < 32768 ? n_nodes - off : 32768;
+    k_extend_add<<<dim3(cnt, 32), 256, 0, st>>>(d_nodes + off, fronts, f_off, src, F);
+  }
+}
+
+// =================================================================================================================
+// multifrontal solve
+// =================================================================================================================
+template <int M>
+__device__ __forceinline__ void gather_children(const SolveArgs &a, const FrontDesc &fd, int32_t f, int32_t p,
+                                                double (&val)[M]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int32_t ch = c ? fd.child1 : fd.child0;
+    if (ch < 0) continue;
+    const int32_t q = a.src[fd.src_off + int64_t(c) * f + p];
+    if (q < 0) continue;
+    const FrontDesc cd = a.fronts[ch];
+    const int64_t base = cd.z_off + cd.s + q;
+    for (int sp = 0; sp < cd.nsplit; ++sp)
+#pragma unroll
+      for (int j = 0; j < M; ++j) val[j] += a.z[(base + int64_t(sp) * cd.b) * M + j];
+  }
+}
+
+constexpr int FWD_ROWS = 128;  // rows of R per forward item (== NdNode::nsplit granularity)
+
+template <int M>
+__global__ void __launch_bounds__(256) k_forward_large(SolveArgs a, const WorkItem *__restrict__ items) {
+  __shared__ double vs[FWD_ROWS * M];
+  __shared__ double red[256 * M];
+  const WorkItem it = items[blockIdx.x];
+  const FrontDesc fd = a.fronts[it.node];
+  const int32_t s = fd.s, f = fd.s + fd.b;
+  const int tid = threadIdx.x;
+  const int nr = it.r1 - it.r0;
+  for (int t = tid; t < nr; t += 256) {
+    const int32_t p = it.r0 + t;
+    double val[M];
+    const int64_t d = a.idx[fd.idx_off + p];
+#pragma unroll
+    for (int j = 0; j < M; ++j) val[j] = a.x[d * M + j];
+    gather_children<M>(a, fd, f, p, val);
+#pragma unroll
+    for (int j = 0; j < M; ++j) vs[t * M + j] = val[j];
+    if (it.c0 == 0)
+#pragma unroll
+      for (int j = 0; j < M; ++j) a.z[(fd.z_off + p) * M + j] = val[j];
+  }
+  __syncthreads();
+  const int nc = it.c1 - it.c0;
+  if (nc <= 0) return;
+  int cw = 32;
+  while (cw < nc && cw < 256) cw <<= 1;
+  const int rg = 256 / cw;
+  const int cid = tid % cw, rgid = tid / cw;
+  double acc[M];
+#pragma unroll
+  for (int j = 0; j < M; ++j) acc[j] = 0.0;
+  if (cid < nc) {
+    const double *Rc = a.R + fd.r_off + int64_t(it.r0) * fd.ldr + s + it.c0 + cid;
+    for (int i = rgid; i < nr; i += rg) {
+      const double r = __ldg(Rc + int64_t(i) * fd.ldr);
+#pragma unroll
+      for (int j = 0; j < M; ++j) acc[j] += r * vs[i * M + j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < M; ++j) red[tid * M + j] = acc[j];
+  __syncthreads();
+  if (rgid == 0 && cid < nc) {
+    double tot[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) tot[j] = 0.0;
+    for (int g = 0; g < rg; ++g)
+#pragma unroll
+      for (int j = 0; j < M; ++j) tot[j] += red[(g * cw + cid) * M + j];
+    const int32_t q = it.c0 + cid;
+    if (it.split == 0) gather_children<M>(a, fd, f, s + q, tot);
+#pragma unroll
+    for (int j = 0; j < M; ++j) a.z[(fd.z_off + s + int64_t(it.split) * fd.b + q) * M + j] = tot[j];
+  }
+}
+
+// fronts with s <= 32 and b <= 64: one warp per front
+template <int M>
+__global__ void __launch_bounds__(256) k_forward_small(SolveArgs a, const int32_t *__restrict__ nodes,
+                                                       int32_t n_nodes) {
+  __shared__ double vs[8][32 * M];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * 8 + warp;
+  if (w >= n_nodes) return;
+  const FrontDesc fd = a.fronts[nodes[w]];
+  const int32_t s = fd.s, f = fd.s + fd.b;
+  if (lane < s) {
+    double val[M];
+    const int64_t d = a.idx[fd.idx_off + lane];
+#pragma unroll
+    for (int j = 0; j < M; ++j) val[j] = a.x[d * M + j];
+    gather_children<M>(a, fd, f, lane, val);
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      vs[warp][lane * M + j] = val[j];
+      a.z[(fd.z_off + lane) * M + j] = val[j];
+    }
+  }
+  __syncwarp();
+  for (int q = lane; q < fd.b; q += 32) {
+    double acc[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) acc[j] = 0.0;
+    gather_children<M>(a, fd, f, s + q, acc);
+    const double *Rc = a.R + fd.r_off + s + q;
+    for (int i = 0; i < s; ++i) {
+      const double r = __ldg(Rc + int64_t(i) * fd.ldr);
+#pragma unroll
+      for (int j = 0; j < M; ++j) acc[j] += r * vs[warp][i * M + j];
+    }
+#pragma unroll
+    for (int j = 0; j < M; ++j) a.z[(fd.z_off + s + q) * M + j] = acc[j];
+  }
+}
+
+constexpr int BWD_CHUNK = 512;
+
+template <int M>
+__global__ void __launch_bounds__(256) k_backward_large(SolveArgs a, const WorkItem *__restrict__ items) {
+  __shared__ double ws[BWD_CHUNK * M];
+  const WorkItem it = items[blockIdx.x];
+  const FrontDesc fd = a.fronts[it.node];
+  const int32_t s = fd.s, f = fd.s + fd.b;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rbase = it.r0 + warp * 4;
+  double acc[4][M];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int j = 0; j < M; ++j) acc[r][j] = 0.0;
+  const double *Rr = a.R + fd.r_off + int64_t(rbase) * fd.ldr;
+  for (int pc = 0; pc < f; pc += BWD_CHUNK) {
+    const int chunk = min(BWD_CHUNK, f - pc);
+    for (int t = tid; t < chunk; t += 256) {
+      const int32_t p = pc + t;
+      if (p < s) {
+#pragma unroll
+        for (int j = 0; j < M; ++j) ws[t * M + j] = a.z[(fd.z_off + p) * M + j];
+      } else {
+        const int64_t d = a.idx[fd.idx_off + p];
+#pragma unroll
+        for (int j = 0; j < M; ++j) ws[t * M + j] = a.x[d * M + j];
+      }
+    }
+    __syncthreads();
+    for (int t = lane; t < chunk; t += 32) {
+      double wv[M];
+#pragma unroll
+      for (int j = 0; j < M; ++j) wv[j] = ws[t * M + j];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (rbase + r < it.r1) {
+          const double rv = __ldg(Rr + int64_t(r) * fd.ldr + pc + t);
+#pragma unroll
+          for (int j = 0; j < M; ++j) acc[r][j] += rv * wv[j];
+        }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double v = acc[r][j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      acc[r][j] = v;
+    }
+  if (lane == 0)
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (rbase + r < it.r1) {
+        const int64_t d = a.idx[fd.idx_off + rbase + r];
+#pragma unroll
+        for (int j = 0; j < M; ++j) a.x[d * M + j] = acc[r][j];
+      }
+}
+
+template <int M>
+__global__ void __launch_bounds__(256) k_backward_small(SolveArgs a, const int32_t *__restrict__ nodes,
+                                                        int32_t n_nodes) {
+  __shared__ double ws[8][96 * M];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * 8 + warp;
+  if (w >= n_nodes) return;
+  const FrontDesc fd = a.fronts[nodes[w]];
+  const int32_t s = fd.s, f = fd.s + fd.b;
+  for (int p = lane; p < f; p += 32) {
+    if (p < s) {
+#pragma unroll
+      for (int j = 0; j < M; ++j) ws[warp][p * M + j] = a.z[(fd.z_off + p) * M + j];
+    } else {
+      const int64_t d = a.idx[fd.idx_off + p];
+#pragma unroll
+      for (int j = 0; j < M; ++j) ws[warp][p * M + j] = a.x[d * M + j];
+    }
+  }
+  __syncwarp();
+  for (int i = 0; i < s; ++i) {
+    double acc[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) acc[j] = 0.0;
+    const double *Rr = a.R + fd.r_off + int64_t(i) * fd.ldr;
+    for (int p = lane; p < f; p += 32) {
+      const double rv = __ldg(Rr + p);
+#pragma unroll
+      for (int j = 0; j < M; ++j) acc[j] += rv * ws[warp][p * M + j];
+    }
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double v = acc[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      acc[j] = v;
+    }
+    if (lane == 0) {
+      const int64_t d = a.idx[fd.idx_off + i];
+#pragma unroll
+      for (int j = 0; j < M; ++j) a.x[d * M + j] = acc[j];
+    }
+  }
+}
+
+#define MMMFE_DISPATCH_M(M, CALL) \
+  switch (M) {                    \
+    case 1: { constexpr int MM = 1; CALL; } break; \
+    case 2: { constexpr int MM = 2; CALL; } break; \
+    case 4: { constexpr int MM = 4; CALL; } break; \
+    default: break;               \
+  }
+
+void launch_forward_large(int M, const SolveArgs &a, const WorkItem *items, int32_t n_items, cudaStream_t st) {
+  if (n_items <= 0) return;
+  MMMFE_DISPATCH_M(M, (k_forward_large<MM><<<n_items, 256, 0, st>>>(a, items)));
+}
+void launch_forward_small(int M, const SolveArgs &a, const int32_t *nodes, int32_t n_nodes, cudaStream_t st) {
+  if (n_nodes <= 0) return;
+  MMMFE_DISPATCH_M(M, (k_forward_small<MM><<<(n_nodes + 7) / 8, 256, 0, st>>>(a, nodes, n_nodes)));
+}
+void launch_backward_large(int M, const SolveArgs &a, const WorkItem *items, int32_t n_items, cudaStream_t st) {
+  if (n_items <= 0) return;
+  MMMFE_DISPATCH_M(M, (k_backward_large<MM><<<n_items, 256, 0, st>>>(a, items)));
+}
+void launch_backward_small(int M, const SolveArgs &a, const int32_t *nodes, int32_t n_nodes, cudaStream_t st) {
+  if (n_nodes <= 0) return;
+  MMMFE_DISPATCH_M(M, (k_backward_small<MM><<<(n_nodes + 7) / 8, 256, 0, st>>>(a, nodes, n_nodes)));
+}
+
+// =================================================================================================================
+// time stepping
+// =================================================================================================================
+__global__ void __launch_bounds__(256) k_build_rhs(StepArgs a, const double *__restrict__ lam_bar, int32_t level) {
+  const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e >= a.n_flux) return;
+  const int64_t k0 = a.kup_rp[e], k1 = a.kup_rp[e + 1];
+  for (int j = 0; j < a.M; ++j) {
+    double acc = 0.0;
+    for (int64_t k = k0; k < k1; ++k) acc -= a.kup_val[k] * a.ptil[int64_t(a.kup_col[k]) * a.M + j];
+    if (lam_bar) {
+      const int32_t q = a.iface_q[e * a.M + j];
+      if (q >= 0) acc -= a.tr_sign[q] * lam_bar[a.tr_base[q] + int64_t(level) * a.tr_stride[q]];
+    }
+    a.x[e * a.M + j] = acc;
+  }
+}
+
+void launch_build_rhs(const StepArgs &a, const double *lam_bar, int32_t level, cudaStream_t st) {
+  k_build_rhs<<<unsigned((a.n_flux + 255) / 256), 256, 0, st>>>(a, lam_bar, level);
+}
+
+__global__ void __launch_bounds__(256) k_add_sparse(double *x, int32_t M, int32_t member,
+                                                    const int32_t *__restrict__ dofs,
+                                                    const double *__restrict__ vals, int32_t n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[int64_t(dofs[i]) * M + member] += vals[i];
+}
+
+void launch_add_sparse(double *x, int32_t M, int32_t member, const int32_t *dofs, const double *vals, int32_t n,
+                       cudaStream_t st) {
+  if (n <= 0) return;
+  k_add_sparse<<<(n + 255) / 256, 256, 0, st>>>(x, M, member, dofs, vals, n);
+}
+
+__global__ void __launch_bounds__(256)
+k_update(StepArgs a, double *__restrict__ trace, int32_t level, const double *const *__restrict__ src_next,
+         int64_t src_stride, double *const *__restrict__ hist, int64_t hist_level_stride, int add_hist) {
+  int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (t < a.n_pressure) {
+    const int64_t c = t;
+    const int64_t k0 = a.kpu_rp[c], k1 = a.kpu_rp[c + 1];
+    const double mi = a.minv[c];
+    for (int j = 0; j < a.M; ++j) {
+      double acc = 0.0;
+      for (int64_t k = k0; k < k1; ++k) acc += a.kpu_val[k] * a.x[int64_t(a.kpu_col[k]) * a.M + j];
+      const double p = a.ptil[c * a.M + j] - mi * acc;
+      if (hist && hist[j]) {
+        double *h = hist[j] + int64_t(level) * hist_level_stride + a.n_flux + c;
+        *h = add_hist ? *h + p : p;
+      }
+      double nxt = p;
+      if (src_next && src_next[j]) nxt += mi * src_next[j][int64_t(level + 1) * src_stride + c];
+      a.ptil[c * a.M + j] = nxt;
+    }
+    return;
+  }
+  t -= a.n_pressure;
+  if (t < a.n_tr) {
+    trace[a.tr_base[t] + int64_t(level) * a.tr_stride[t]] = a.x[int64_t(a.tr_dof[t]) * a.M + a.tr_mem[t]];
+    return;
+  }
+  t -= a.n_tr;
+  if (hist && t < a.n_flux) {
+    for (int j = 0; j < a.M; ++j)
+      if (hist[j]) {
+        double *h = hist[j] + int64_t(level) * hist_level_stride + t;
+        const double v = a.x[t * a.M + j];
+        *h = add_hist ? *h + v : v;
+      }
+  }
+}
+
+void launch_update(const StepArgs &a, double *trace, int32_t level, const double *const *src_next,
+                   int64_t src_stride, double *const *hist, int64_t hist_level_stride, int add_hist,
+                   cudaStream_t st) {
+  const int64_t n = a.n_pressure + a.n_tr + (hist ? a.n_flux : 0);
+  k_update<<<unsigned((n + 255) / 256), 256, 0, st>>>(a, trace, level, src_next, src_stride, hist,
+                                                      hist_level_stride, add_hist);
+}
+
+__global__ void __launch_bounds__(256) k_init_ptil(StepArgs a, const double *const *__restrict__ p0,
+                                                   const double *const *__restrict__ src0) {
+  const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (c >= a.n_pressure) return;
+  for (int j = 0; j < a.M; ++j) {
+    double v = 0.0;
+    if (p0 && p0[j]) v = p0[j][c];
+    if (src0 && src0[j]) v += a.minv[c] * src0[j][c];
+    a.ptil[c * a.M + j] = v;
+  }
+}
+
+void launch_init_ptil(const StepArgs &a, const double *const *p0, const double *const *src0, cudaStream_t st) {
+  k_init_ptil<<<unsigned((a.n_pressure + 255) / 256), 256, 0, st>>>(a, p0, src0);
+}
+
+// =================================================================================================================
+// interface vector kernels
+// =================================================================================================================
+__global__ void __launch_bounds__(256) k_spmv(int64_t n_rows, const int64_t *__restrict__ rp,
+                                              const int32_t *__restrict__ col, const double *__restrict__ val,
+                                              const double *__restrict__ x, double *__restrict__ y) {
+  const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (r >= n_rows) return;
+  double acc = 0.0;
+  for (int64_t k = rp[r]; k < rp[r + 1]; ++k) acc += val[k] * x[col[k]];
+  y[r] = acc;
+}
+
+void launch_spmv(int64_t n_rows, const int64_t *rp, const int32_t *col, const double *val, const double *x,
+                 double *y, cudaStream_t st) {
+  if (n_rows <= 0) return;
+  k_spmv<<<unsigned((n_rows + 255) / 256), 256, 0, st>>>(n_rows, rp, col, val, x, y);
+}
+
+__global__ void __launch_bounds__(256) k_exchange_combine(int64_t n, const double *__restrict__ send,
+                                                          const int64_t *__restrict__ partner,
+                                                          const double *__restrict__ recv, double sign,
+                                                          double *__restrict__ out) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int64_t p = partner[i];
+  const double other = (p >= 0) ? send[p] : recv[-p - 2];
+  out[i] = sign * (send[i] + other);
+}
+
+void launch_exchange_combine(int64_t n, const double *send, const int64_t *partner, const double *recv, double sign,
+                             double *out, cudaStream_t st) {
+  if (n <= 0) return;
+  k_exchange_combine<<<unsigned((n + 255) / 256), 256, 0, st>>>(n, send, partner, recv, sign, out);
+}
+
+__global__ void __launch_bounds__(256) k_gather(int64_t n, const double *__restrict__ srcv,
+                                                const int64_t *__restrict__ index, double *__restrict__ dst) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i < n) dst[i] = srcv[index[i]];
+}
+
+void launch_gather(int64_t n, const double *srcv, const int64_t *index, double *dst, cudaStream_t st) {
+  if (n <= 0) return;
+  k_gather<<<unsigned((n + 255) / 256), 256, 0, st>>>(n, srcv, index, dst);
+}
+
+__device__ __forceinline__ double block_sum_512(double v, double *sm) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (warp == 0) {
+    r = (lane < (blockDim.x >> 5)) ? sm[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  return r;  // valid in thread 0
+}
+
+__global__ void __launch_bounds__(512) k_multi_dot(int64_t len, const double *__restrict__ w,
+                                                   const double *__restrict__ Q, int64_t ldq,
+                                                   double *__restrict__ h) {
+  __shared__ double sm[16];
+  const double *q = Q + int64_t(blockIdx.x) * ldq;
+  double acc = 0.0;
+  for (int64_t j = threadIdx.x; j < len; j += blockDim.x) acc += w[j] * q[j];
+  const double r = block_sum_512(acc, sm);
+  if (threadIdx.x == 0) h[blockIdx.x] = r;
+}
+
+void launch_multi_dot(int64_t len, const double *w, const double *Q, int64_t ldq, int32_t k_plus_1, double *h,
+                      cudaStream_t st) {
+  k_multi_dot<<<k_plus_1, 512, 0, st>>>(len, w, Q, ldq, h);
+}
+
+constexpr int CGS_BLOCKS = 592;  // 4 per SM
+
+__global__ void __launch_bounds__(512) k_cgs_update(int64_t len, double *__restrict__ w,
+                                                    const double *__restrict__ Q, int64_t ldq, int32_t k_plus_1,
+                                                    const double *__restrict__ h, double *__restrict__ partial) {
+  __shared__ double sm[16];
+  double acc2 = 0.0;
+  for (int64_t j = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; j < len; j += int64_t(gridDim.x) * blockDim.x) {
+    double v = w[j];
+    for (int i = 0; i < k_plus_1; ++i) v -= h[i] * Q[int64_t(i) * ldq + j];
+    w[j] = v;
+    acc2 += v * v;
+  }
+  const double r = block_sum_512(acc2, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
+__global__ void __launch_bounds__(512) k_final_sum(const double *__restrict__ partial, int n, double *out) {
+  __shared__ double sm[16];
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) acc += partial[j];
+  const double r = block_sum_512(acc, sm);
+  if (threadIdx.x == 0) out[0] = r;
+}
+
+// norm2 must have room for 1 + CGS_BLOCKS doubles; result in norm2[0]
+void launch_cgs_update(int64_t len, double *w, const double *Q, int64_t ldq, int32_t k_plus_1, const double *h,
+                       double *norm2, cudaStream_t st) {
+  k_cgs_update<<<CGS_BLOCKS, 512, 0, st>>>(len, w, Q, ldq, k_plus_1, h, norm2 + 1);
+  k_final_sum<<<1, 512, 0, st>>>(norm2 + 1, CGS_BLOCKS, norm2);
+}
+
+__global__ void __launch_bounds__(256) k_scale_store(int64_t len, const double *__restrict__ w, double inv,
+                                                     double *__restrict__ dst) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i < len) dst[i] = w[i] / inv;
+}
+
+// dst = w / inv  (the reference divides: q[i] /= h[k+1], src/darcy_vtdd.cc:1461)
+void launch_scale_store(int64_t len, const double *w, double inv, double *dst, cudaStream_t st) {
+  if (len <= 0) return;
+  k_scale_store<<<unsigned((len + 255) / 256), 256, 0, st>>>(len, w, inv, dst);
+}
+
+__global__ void __launch_bounds__(256) k_axpy_rows(int64_t len, const double *__restrict__ Q, int64_t ldq,
+                                                   int32_t n_rows, const double *__restrict__ y,
+                                                   double *__restrict__ out) {
+  const int64_t j = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (j >= len) return;
+  double acc = 0.0;
+  for (int i = 0; i < n_rows; ++i) acc += Q[int64_t(i) * ldq + j] * y[i];
+  out[j] = acc;
+}
+
+// out = sum_i y[i] Q_i  (lambda reconstruction, src/darcy_vtdd.cc:1517-1521)
+void launch_axpy_rows(int64_t len, const double *Q, int64_t ldq, int32_t n_rows, const double *y, double *out,
+                      cudaStream_t st) {
+  if (len <= 0) return;
+  k_axpy_rows<<<unsigned((len + 255) / 256), 256, 0, st>>>(len, Q, ldq, n_rows, y, out);
+}
+
+}  // namespace mmmfe

@@ -1,0 +1,99 @@
+"""Glue used by the parity tests: feeds an oracle problem description to the CUDA engine through the C ABI."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import mmmfe_import  # noqa: E402
+import mmmfe_oracle as mo  # noqa: E402
+
+
+def pkg():
+    return mmmfe_import.load()
+
+
+def default_params(mortar_degree=1, cycles=1):
+    prm = mo.parse_parameter_file(os.path.join(ROOT, "parameter.txt"))
+    prm.mortar_degree = mortar_degree
+    prm.num_refinement = cycles
+    return prm
+
+
+def make_problem(prm, cycle=0, n_sub=None, mesh=None, mortar=None):
+    n_sub = n_sub or len(prm.mesh) - 1
+    if mesh is None:
+        m = mo.refined_meshes(prm, n_sub)[cycle]
+        mesh, mortar = m[:-1], m[-1]
+    prob = mo.Problem(prm, n_sub, mesh, mortar, keep_solution=True)
+    prob.setup()
+    return prob
+
+
+def bar_data(prob, sd):
+    """src[nt][np] = dt (f, w); flux data on outer Dirichlet edges; p0 (what assemble_rhs_bar adds besides c0 p_old)."""
+    zero = np.zeros(sd.np)
+    src = np.zeros((sd.nt, sd.np))
+    outer = [s for s in range(4) if sd.neighbors[s] < 0]
+    fr_dofs = np.concatenate([sd.side_edges[s] for s in outer]) if outer else np.zeros(0, dtype=np.int64)
+    fr_vals = np.zeros((sd.nt, len(fr_dofs)))
+    t = 0.0
+    for lvl in range(sd.nt):
+        t += sd.dt
+        rhs = sd.rhs_bar(t, zero, prob.qdegree, prob.prm)
+        src[lvl] = rhs[sd.nf:]
+        fr_vals[lvl] = rhs[fr_dofs]
+    return sd.project_initial_condition(), src, fr_dofs, fr_vals
+
+
+def engine_from_oracle(prob, perm_seed=None, options=None, local=None):
+    """Registers every (or the `local`) oracle subdomain with a fresh engine.  perm_seed: random user dof numbering."""
+    eng = pkg().Engine()
+    for k, v in (options or {}).items():
+        eng.set_option(k, v)
+    perms = {}
+    for sd in prob.subs:
+        if local is not None and sd.r not in local:
+            continue
+        mat = sd.matrix.tocsr()
+        side_dofs = [np.asarray(e) for e in sd.side_edges]
+        canon = None
+        if perm_seed is not None:
+            rng = np.random.default_rng(perm_seed + sd.r)
+            pf = rng.permutation(sd.nf)  # user flux dof d  <-> canonical pf[d]
+            pp = rng.permutation(sd.np)
+            full = np.concatenate([pf, sd.nf + pp])  # user -> canonical
+            inv = np.empty_like(full)
+            inv[full] = np.arange(sd.n)
+            mat = mat[full][:, full].tocsr()
+            side_dofs = [inv[e] for e in side_dofs]
+            canon = pf
+            perms[sd.r] = (full, inv)
+        eng.add_subdomain(global_id=sd.r, nx=sd.nx, ny=sd.ny, nt=sd.nt, dt=sd.dt, matrix=mat, n_flux=sd.nf,
+                          n_pressure=sd.np, neighbor=sd.neighbors, side_dofs=side_dofs, f2c=sd.f2c, c2f=sd.c2f,
+                          canon_of_dof=canon)
+    eng.perms = perms
+    return eng
+
+
+def set_bar_data(eng, prob, local=None):
+    li = 0
+    for sd in prob.subs:
+        if local is not None and sd.r not in local:
+            continue
+        p0, src, fr_dofs, fr_vals = bar_data(prob, sd)
+        if sd.r in eng.perms:
+            full, inv = eng.perms[sd.r]
+            fr_dofs = inv[fr_dofs]
+            pp = full[sd.nf:] - sd.nf
+            src = src[:, pp]
+            p0 = p0[pp]
+        eng.bar_set_data(li, p0, src, fr_dofs, fr_vals)
+        li += 1
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))

@@ -1,0 +1,141 @@
+"""Parity of the CUDA engine (through the C ABI) against the CPU oracle.  Needs a B200."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from helpers import default_params, engine_from_oracle, make_problem, mo, rel_l2, set_bar_data
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10  # north_star: 1e-10 relative L2 on mortar, pressure and velocity
+
+
+def _two_by_two(nxs, nts, mortar, k=1):
+    prm = default_params(k)
+    mesh = [[n, n, t] for n, t in zip(nxs, nts)]
+    return make_problem(prm, n_sub=4, mesh=mesh, mortar=mortar)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (2, 3), (3, 3), (5, 7), (16, 16), (33, 20), (64, 64), (96, 40), (150, 130)])
+def test_saddle_solve_matches_sparse_lu(shape):
+    """A_direct.vmult (src/darcy_vtdd.cc:877) == multifrontal block-inverse solve, incl. ragged grids."""
+    prm = default_params()
+    nx, ny = shape
+    prob = make_problem(prm, n_sub=2, mesh=[[nx, ny, 2], [nx, ny, 2]], mortar=[1, 1, 1])
+    eng = engine_from_oracle(prob)
+    eng.setup()
+    sd = prob.subs[0]
+    rng = np.random.default_rng(1)
+    rhs = rng.standard_normal(sd.n)
+    x = eng.solve_saddle(0, rhs)
+    ref = sd.lu.solve(rhs)
+    assert rel_l2(x, ref) < 1e-11
+    assert rel_l2(sd.matrix @ x, rhs) < 1e-11
+    eng.close()
+
+
+def test_saddle_solve_with_permuted_dofs():
+    prm = default_params()
+    prob = make_problem(prm, n_sub=2, mesh=[[12, 9, 2], [12, 9, 2]], mortar=[1, 1, 1])
+    eng = engine_from_oracle(prob, perm_seed=5)
+    eng.setup()
+    sd = prob.subs[1]
+    full, inv = eng.perms[1]
+    rhs = np.random.default_rng(2).standard_normal(sd.n)
+    x_user = eng.solve_saddle(1, rhs[full])
+    ref = sd.lu.solve(rhs)
+    assert rel_l2(x_user, ref[full]) < 1e-11
+    eng.close()
+
+
+@pytest.mark.parametrize("k,cycle", [(1, 0), (1, 1), (2, 0), (2, 2)])
+def test_interface_operator_matches_oracle(k, cycle):
+    prm = default_params(k, cycle + 1)
+    prob = make_problem(prm, cycle)
+    eng = engine_from_oracle(prob)
+    eng.setup()
+    assert eng.interface_length == prob.n_iface
+    rng = np.random.default_rng(3)
+    for _ in range(2):
+        q = rng.standard_normal(prob.n_iface)
+        assert rel_l2(eng.apply(q), prob.apply_S(q)) < TOL
+    # determinism: S applied twice to the same vector is bitwise identical
+    a, b = eng.apply(q), eng.apply(q)
+    assert np.array_equal(a, b)
+    # star traces of the last application
+    tr, _ = prob.star_sweep(prob.subs[2], prob.split(q, prob.subs[2]))
+    for side, t in tr.items():
+        assert rel_l2(eng.get_star_trace(2, side).ravel(), t) < TOL
+    eng.close()
+
+
+def test_factor_sharing_and_graph_equivalence():
+    prm = default_params(1, 2)
+    prob = make_problem(prm, 1)
+    q = np.random.default_rng(4).standard_normal(prob.n_iface)
+    outs = []
+    for graphs in (1, 0):
+        eng = engine_from_oracle(prob, options={"use_graphs": graphs})
+        eng.setup()
+        st = eng.stats()
+        assert st["factor_groups"] == 3  # subdomains 0 and 3 have identical matrices
+        outs.append(eng.apply(q))
+        eng.close()
+    assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("k,cycle,perm", [(1, 0, None), (1, 2, None), (2, 0, None), (1, 1, 11)])
+def test_full_solve_matches_oracle(k, cycle, perm):
+    """bar sweep + local_gmres + final sweep: r_norm, iteration count, residual history, lambda, p, u."""
+    prm = default_params(k, cycle + 1)
+    prob = make_problem(prm, cycle)
+    ref = prob.run_cycle(cycle)
+    eng = engine_from_oracle(prob, perm_seed=perm)
+    eng.setup()
+    set_bar_data(eng, prob)
+    eng.bar_sweep()
+    out = eng.gmres(prm.tolerance, prm.max_iteration)
+    assert out["iterations"] == ref.gmres_iterations
+    assert out["r_norm"] == pytest.approx(ref.r_norm, rel=1e-12)
+    np.testing.assert_allclose(out["residuals"], ref.residuals, rtol=1e-6, atol=1e-13)
+    assert rel_l2(out["lam"], ref.lam) < TOL
+    eng.final_sweep()
+    for li, sd in enumerate(prob.subs):
+        sol = eng.get_solution(li)
+        if perm is not None:
+            full, inv = eng.perms[sd.r]
+            sol = sol[:, inv]
+        assert rel_l2(sol[:, sd.nf:], ref.solution_p[li]) < TOL
+        assert rel_l2(sol[:, :sd.nf], ref.solution_u[li]) < TOL
+    eng.close()
+
+
+def test_checkerboard_4x4_nonmatching_space_time():
+    """4x4 subdomains, checkerboard fine/coarse in space and time (BASELINE config 3 scaled down)."""
+    prm = default_params(1)
+    mesh = []
+    for r in range(16):
+        fine = ((r % 4) + (r // 4)) % 2 == 0
+        mesh.append([16, 16, 8] if fine else [8, 8, 4])
+    prob = make_problem(prm, n_sub=16, mesh=mesh, mortar=[4, 4, 2])
+    eng = engine_from_oracle(prob)
+    eng.setup()
+    assert eng.stats()["factor_groups"] == 2
+    q = np.random.default_rng(6).standard_normal(prob.n_iface)
+    assert rel_l2(eng.apply(q), prob.apply_S(q)) < TOL
+    # linearity of the device operator
+    q2 = np.random.default_rng(7).standard_normal(prob.n_iface)
+    lhs = eng.apply(2 * q - 3 * q2)
+    rhs = 2 * eng.apply(q) - 3 * eng.apply(q2)
+    assert rel_l2(lhs, rhs) < 1e-11
+    eng.close()
+
+
+def test_errors_are_reported_not_swallowed():
+    prm = default_params()
+    prm.c0 = 0.0
+    prob = make_problem(prm, 0)
+    eng = engine_from_oracle(prob)
+    with pytest.raises(Exception, match="c0"):
+        eng.setup()
+    eng.close()
