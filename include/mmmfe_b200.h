@@ -163,6 +163,17 @@ int mmmfe_get_star_trace(mmmfe_ctx *ctx, int32_t local_index, int32_t side, doub
 /* x = K^{-1} rhs for the saddle matrix of one local subdomain (A_direct.vmult, src/darcy_vtdd.cc:864, 877). */
 int mmmfe_solve_saddle(mmmfe_ctx *ctx, int32_t local_index, const double *rhs, double *x);
 
+/* ---- diagnostics (host only, no device needed) ------------------------------------------------------------------- */
+/* The nested-dissection tree the engine builds for an nx x ny RT0 grid, in canonical flux numbering.
+ * sizes = {n_nodes, idx_len, src_len, r_total, z_total, n_heights}.
+ * node_table: n_nodes x 8 int32 = {s, b, child0, child1, height, nsplit, ldr, parent};
+ * offsets:    n_nodes x 4 int64 = {idx_off, src_off, r_off, z_off}.                                            */
+/* Copies the stored factor (R blocks, layout given by the nd-tree offsets/ldr) of a local subdomain's group. */
+int mmmfe_debug_get_factor(mmmfe_ctx *ctx, int32_t local_index, double *r_out, int64_t capacity);
+int mmmfe_nd_tree_sizes(int32_t nx, int32_t ny, int32_t leaf_cells, int64_t sizes[6]);
+int mmmfe_nd_tree_fill(int32_t nx, int32_t ny, int32_t leaf_cells, int32_t *node_table, int64_t *offsets,
+                       int32_t *idx, int32_t *src);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,10 @@ def load_engine():
         "mmmfe_get_solution": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p]),
         "mmmfe_get_star_trace": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.c_int32, c_f64p]),
         "mmmfe_solve_saddle": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p, c_f64p]),
+        "mmmfe_debug_get_factor": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p, ctypes.c_int64]),
+        "mmmfe_nd_tree_sizes": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_i64p]),
+        "mmmfe_nd_tree_fill": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_i32p, c_i64p, c_i32p,
+                                              c_i32p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -242,8 +246,29 @@ class Engine:
         self._check(self.lib.mmmfe_get_star_trace(self.h, li, side, _ptr(out, c_f64p)))
         return out
 
+    def debug_get_factor(self, li, r_total):
+        out = np.empty(r_total)
+        self._check(self.lib.mmmfe_debug_get_factor(self.h, li, _ptr(out, c_f64p), r_total))
+        return out
+
     def solve_saddle(self, li, rhs):
         rhs = _f64(rhs)
         out = np.empty_like(rhs)
         self._check(self.lib.mmmfe_solve_saddle(self.h, li, _ptr(rhs, c_f64p), _ptr(out, c_f64p)))
         return out
+
+
+def nd_tree(nx, ny, leaf_cells=4):
+    """The engine's nested-dissection tree as numpy arrays (host only)."""
+    lib = load_engine()
+    sizes = np.zeros(6, dtype=np.int64)
+    if lib.mmmfe_nd_tree_sizes(nx, ny, leaf_cells, _ptr(sizes, c_i64p)) != 0:
+        raise MmmfeError("bad grid")
+    nodes = np.zeros((sizes[0], 8), dtype=np.int32)
+    offs = np.zeros((sizes[0], 4), dtype=np.int64)
+    idx = np.zeros(sizes[1], dtype=np.int32)
+    src = np.zeros(sizes[2], dtype=np.int32)
+    lib.mmmfe_nd_tree_fill(nx, ny, leaf_cells, _ptr(nodes, c_i32p), _ptr(offs, c_i64p), _ptr(idx, c_i32p),
+                           _ptr(src, c_i32p))
+    return dict(nodes=nodes, offsets=offs, idx=idx, src=src, r_total=int(sizes[3]), z_total=int(sizes[4]),
+                n_heights=int(sizes[5]))

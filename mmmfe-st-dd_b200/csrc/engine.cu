@@ -285,9 +285,11 @@ static void run_trans_batch(mmmfe_ctx *c, const std::vector<TransProb> &pr) {
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 
-// In-place inverse of a batch of SPD blocks by recursive Schur complements: everything above the 32x32 base
-// blocks is GEMM (DMMA).  Blocks must be stored full (both triangles) and come back full.
-static void inverse_batch(mmmfe_ctx *c, const std::vector<InvProb> &probs, Arena &arena) {
+// In place: SPD block A (full storage) -> L^-1, the inverse of its Cholesky factor (lower triangle, exact zeros
+// above).  Recursive: everything above the 32x32 base blocks is GEMM on the FP64 tensor cores.
+//   A = [[A11, .], [A21, A22]] :  Li11 = rec(A11);  L21 = A21 Li11^T;  A22 -= L21 L21^T;  Li22 = rec(A22);
+//   L^-1 = [[Li11, 0], [-Li22 L21 Li11, Li22]]
+static void chol_inv_batch(mmmfe_ctx *c, const std::vector<InvProb> &probs, Arena &arena) {
   std::vector<InvProb> small, big;
   for (const auto &p : probs) (p.n <= 32 ? small : big).push_back(p);
   if (!small.empty()) {
@@ -299,39 +301,36 @@ static void inverse_batch(mmmfe_ctx *c, const std::vector<InvProb> &probs, Arena
   if (big.empty()) return;
   const size_t mark = arena.top;
   std::vector<InvProb> a11, a22;
-  std::vector<double *> T(big.size());
+  std::vector<double *> T(big.size()), T2(big.size());
   for (size_t i = 0; i < big.size(); ++i) {
     const int n = big[i].n, h = n / 2, ld = big[i].ld;
     a11.push_back({big[i].A, h, ld});
     a22.push_back({big[i].A + int64_t(h) * ld + h, n - h, ld});
   }
-  inverse_batch(c, a11, arena);
+  chol_inv_batch(c, a11, arena);
   std::vector<GemmProb> g1, g2, g3, g4;
-  std::vector<TransProb> tr;
+  std::vector<TransProb> zr;
   for (size_t i = 0; i < big.size(); ++i) {
     const int n = big[i].n, h = n / 2, r = n - h, ld = big[i].ld;
     double *A = big[i].A, *A21 = A + int64_t(h) * ld, *A22 = A21 + h;
     T[i] = arena.take(size_t(r) * h);
-    // T = A21 * inv(A11)
-    g1.push_back({A21, A, T[i], r, h, h, h, ld, 1, ld, 1, 1.0, 0.0});
-    // S = A22 - T * A21^T
-    g2.push_back({T[i], A21, A22, r, r, h, ld, h, 1, 1, ld, -1.0, 1.0});
+    g1.push_back({A21, A, T[i], r, h, h, h, ld, 1, 1, ld, 1.0, 0.0});       // L21 = A21 * Li11^T
+    g2.push_back({T[i], T[i], A22, r, r, h, ld, h, 1, 1, h, -1.0, 1.0});    // A22 -= L21 * L21^T
   }
   run_gemm_batch(c, g1);
   run_gemm_batch(c, g2);
-  inverse_batch(c, a22, arena);
+  chol_inv_batch(c, a22, arena);
   for (size_t i = 0; i < big.size(); ++i) {
     const int n = big[i].n, h = n / 2, r = n - h, ld = big[i].ld;
     double *A = big[i].A, *A21 = A + int64_t(h) * ld, *A22 = A21 + h;
-    // A21 = -inv(S) * T
-    g3.push_back({A22, T[i], A21, r, h, r, ld, ld, 1, h, 1, -1.0, 0.0});
-    // A11 = inv(A11) - T^T * A21new
-    g4.push_back({T[i], A21, A, h, h, r, ld, 1, h, ld, 1, -1.0, 1.0});
-    tr.push_back({A21, A + h, h, r, ld, ld, 1.0});
+    T2[i] = arena.take(size_t(r) * h);
+    g3.push_back({T[i], A, T2[i], r, h, h, h, h, 1, ld, 1, 1.0, 0.0});      // T2 = L21 * Li11
+    g4.push_back({A22, T2[i], A21, r, h, r, ld, ld, 1, h, 1, -1.0, 0.0});   // A21 = -Li22 * T2
+    zr.push_back({A21, A + h, h, r, ld, ld, 0.0});                          // upper-right block = 0
   }
   run_gemm_batch(c, g3);
   run_gemm_batch(c, g4);
-  run_trans_batch(c, tr);
+  run_trans_batch(c, zr);
   arena.top = mark;
 }
 
@@ -457,26 +456,25 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd) {
       const NdNode &n = tr.nodes[id];
       inv.push_back({W.p + n.f_off, n.s, n.s + n.b});
     }
-    inverse_batch(c, inv, arena);
-    std::vector<GemmProb> gG, gU;
-    std::vector<TransProb> t1, t2;
+    chol_inv_batch(c, inv, arena);  // F11 block now holds Li = L^-1
+    std::vector<GemmProb> gW, gU, gX, gG;
     for (int32_t id : lvl) {
       const NdNode &n = tr.nodes[id];
       const int s = n.s, b = n.b, f = s + b;
       double *Fp = W.p + n.f_off;
       double *Rp = F->R.p + n.r_off;
-      t1.push_back({Fp, Rp, s, s, f, n.ldr, 1.0});
+      gX.push_back({Fp, Fp, Rp, s, s, s, n.ldr, 1, f, f, 1, 1.0, 0.0});  // F11^-1 = Li^T Li -> R[:, :s]
       if (b == 0) continue;
-      double *G = arena.take(size_t(b) * s);
+      double *Wt = arena.take(size_t(b) * s);
       double *F21 = Fp + int64_t(s) * f, *F22 = F21 + s;
-      gG.push_back({F21, Fp, G, b, s, s, s, f, 1, f, 1, 1.0, 0.0});    // G = F21 * inv(F11)
-      gU.push_back({G, F21, F22, b, b, s, f, s, 1, 1, f, -1.0, 1.0});  // U = F22 - G * F21^T
-      t2.push_back({G, Rp + s, s, b, s, n.ldr, -1.0});                 // R[:, s:] = -G^T
+      gW.push_back({F21, Fp, Wt, b, s, s, s, f, 1, 1, f, 1.0, 0.0});          // Wt = F21 Li^T        (b x s)
+      gU.push_back({Wt, Wt, F22, b, b, s, f, s, 1, 1, s, -1.0, 1.0});         // U  = F22 - Wt Wt^T
+      gG.push_back({Fp, Wt, Rp + s, s, b, s, n.ldr, 1, f, 1, s, -1.0, 0.0});  // R[:, s:] = -(Wt Li)^T = -Li^T Wt^T
     }
-    run_gemm_batch(c, gG);
+    run_gemm_batch(c, gW);
     run_gemm_batch(c, gU);
-    run_trans_batch(c, t1);
-    run_trans_batch(c, t2);
+    run_gemm_batch(c, gX);
+    run_gemm_batch(c, gG);
   }
   int32_t failed = 0;
   CUDA_CHECK(cudaMemcpy(&failed, c->d_fail.p, sizeof(int32_t), cudaMemcpyDeviceToHost));
@@ -1153,6 +1151,16 @@ int mmmfe_solve_saddle(mmmfe_ctx *c, int32_t li, const double *rhs, double *x) {
     launch_update(a, nullptr, 0, nullptr, F.np, d_histp.p, int64_t(F.nf) + F.np, 0, st);
     CUDA_CHECK(cudaMemcpyAsync(x, out.p, out.n * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int mmmfe_debug_get_factor(mmmfe_ctx *c, int32_t li, double *r_out, int64_t capacity) {
+  if (!c || li < 0 || li >= int32_t(c->subs.size()) || !r_out) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, {
+    if (!c->is_setup) fail(MMMFE_E_INVALID, "mmmfe_setup first");
+    const Factor &F = *c->batches[c->subs[li]->batch]->factor;
+    if (capacity < int64_t(F.R.n)) fail(MMMFE_E_INVALID, "buffer too small (%lld needed)", (long long)F.R.n);
+    CUDA_CHECK(cudaMemcpy(r_out, F.R.p, F.R.n * sizeof(double), cudaMemcpyDeviceToHost));
   });
 }
 

@@ -101,42 +101,52 @@ void launch_grouped_gemm(const GemmProb *d_probs, const int32_t *d_tile_start, i
 }
 
 // =================================================================================================================
-// in-place inverse of SPD blocks with n <= 32: one warp per block, Gauss-Jordan without pivoting
+// base case of the factorisation: A (SPD, n <= 32) -> inverse Cholesky factor L^-1 (lower triangle, zeros above),
+// one warp per block.  Forming Schur complements through L^-1 (condition sqrt(cond A)) instead of A^-1 keeps the
+// factorisation as accurate as a Cholesky multifrontal method.
 // =================================================================================================================
-__global__ void __launch_bounds__(128) k_small_inverse(const InvProb *__restrict__ probs, int32_t n_probs,
+__global__ void __launch_bounds__(64) k_small_chol_inv(const InvProb *__restrict__ probs, int32_t n_probs,
                                                        int32_t *fail) {
-  __shared__ double sm[4][32][33];
+  __shared__ double sa[2][32][33];
+  __shared__ double sb[2][32][33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pi = blockIdx.x * 4 + warp;
+  const int pi = blockIdx.x * 2 + warp;
   if (pi >= n_probs) return;
   const InvProb pr = probs[pi];
   const int n = pr.n;
-  double(*a)[33] = sm[warp];
+  double(*a)[33] = sa[warp];
+  double(*li)[33] = sb[warp];
   for (int i = 0; i < n; ++i)
     if (lane < n) a[i][lane] = pr.A[int64_t(i) * pr.ld + lane];
   __syncwarp();
+  // right-looking Cholesky on the lower triangle; lane = row
   for (int k = 0; k < n; ++k) {
     const double d = a[k][k];
     if (!(d > 0.0) && lane == 0) atomicExch(fail, 1);
+    const double l = sqrt(d);
     __syncwarp();
-    const double inv = 1.0 / d;
-    if (lane < n) a[k][lane] = (lane == k) ? inv : a[k][lane] * inv;
+    if (lane == k) a[k][k] = l;
+    else if (lane > k && lane < n) a[lane][k] /= l;
     __syncwarp();
-    for (int i = 0; i < n; ++i) {
-      if (i == k) continue;
-      const double f = a[i][k];
-      __syncwarp();
-      if (lane < n) a[i][lane] = (lane == k) ? -f * inv : a[i][lane] - f * a[k][lane];
-      __syncwarp();
-    }
+    for (int j = k + 1; j < n; ++j)
+      if (lane >= j && lane < n) a[lane][j] -= a[lane][k] * a[j][k];
+    __syncwarp();
+  }
+  // L^-1 by forward substitution; lane = column
+  for (int i = 0; i < n; ++i) {
+    double v = (lane == i) ? 1.0 : 0.0;
+    for (int k = 0; k < i; ++k)
+      if (k >= lane) v -= a[i][k] * li[k][lane];
+    if (lane < n) li[i][lane] = (lane <= i) ? v / a[i][i] : 0.0;
+    __syncwarp();
   }
   for (int i = 0; i < n; ++i)
-    if (lane < n) pr.A[int64_t(i) * pr.ld + lane] = a[i][lane];
+    if (lane < n) pr.A[int64_t(i) * pr.ld + lane] = li[i][lane];
 }
 
 void launch_small_inverse(const InvProb *d_probs, int32_t n_probs, int32_t *d_fail, cudaStream_t st) {
   if (n_probs <= 0) return;
-  k_small_inverse<<<(n_probs + 3) / 4, 128, 0, st>>>(d_probs, n_probs, d_fail);
+  k_small_chol_inv<<<(n_probs + 1) / 2, 64, 0, st>>>(d_probs, n_probs, d_fail);
 }
 
 __global__ void __launch_bounds__(256) k_transpose(const TransProb *__restrict__ probs) {

@@ -114,3 +114,35 @@ void NdTree::build(int32_t nx_, int32_t ny_, int32_t leaf_cells) {
 }
 
 }  // namespace mmmfe
+
+// ---- diagnostics of include/mmmfe_b200.h ---------------------------------------------------------------------------
+extern "C" int mmmfe_nd_tree_sizes(int32_t nx, int32_t ny, int32_t leaf_cells, int64_t sizes[6]) {
+  if (nx < 1 || ny < 1 || !sizes) return -1;
+  mmmfe::NdTree t;
+  t.build(nx, ny, leaf_cells);
+  sizes[0] = int64_t(t.nodes.size());
+  sizes[1] = int64_t(t.idx.size());
+  sizes[2] = int64_t(t.src.size());
+  sizes[3] = t.r_total;
+  sizes[4] = t.z_total;
+  sizes[5] = int64_t(t.by_height.size());
+  return 0;
+}
+
+extern "C" int mmmfe_nd_tree_fill(int32_t nx, int32_t ny, int32_t leaf_cells, int32_t *node_table, int64_t *offsets,
+                                  int32_t *idx, int32_t *src) {
+  if (nx < 1 || ny < 1 || !node_table || !offsets || !idx || !src) return -1;
+  mmmfe::NdTree t;
+  t.build(nx, ny, leaf_cells);
+  for (size_t i = 0; i < t.nodes.size(); ++i) {
+    const mmmfe::NdNode &n = t.nodes[i];
+    int32_t *row = node_table + 8 * i;
+    row[0] = n.s; row[1] = n.b; row[2] = n.child[0]; row[3] = n.child[1];
+    row[4] = n.height; row[5] = n.nsplit; row[6] = n.ldr; row[7] = n.parent;
+    int64_t *o = offsets + 4 * i;
+    o[0] = n.idx_off; o[1] = n.src_off; o[2] = n.r_off; o[3] = n.z_off;
+  }
+  std::copy(t.idx.begin(), t.idx.end(), idx);
+  std::copy(t.src.begin(), t.src.end(), src);
+  return 0;
+}

@@ -1,0 +1,48 @@
+"""Quick device timing of one interface-operator application for a 2x2 checkerboard (no oracle LU)."""
+import sys
+import time
+
+import numpy as np
+
+from helpers import default_params, mo, pkg
+
+
+def build(nf, ntf, nc, ntc, mortar, k=1):
+    prm = default_params(k)
+    mesh = [[nf, nf, ntf], [nc, nc, ntc], [nc, nc, ntc], [nf, nf, ntf]]
+    prob = mo.Problem(prm, 4, mesh, mortar)
+    t0 = time.time()
+    for sd in prob.subs:
+        sd.matrix = sd.assemble_matrix()
+        sd.f2c, sd.c2f = {}, {}
+        for side in range(4):
+            if sd.neighbors[side] >= 0:
+                sd.f2c[side], sd.c2f[side] = mo.projector_tables(sd, side, prob.mortar, prob.k)
+    print(f"host assembly {time.time() - t0:.1f}s", flush=True)
+    return prob
+
+
+if __name__ == "__main__":
+    nf, ntf, nc, ntc, ms, mt = [int(a) for a in sys.argv[1:7]]
+    reps = int(sys.argv[7]) if len(sys.argv) > 7 else 3
+    prob = build(nf, ntf, nc, ntc, [ms, ms, mt])
+    eng = pkg().Engine()
+    for sd in prob.subs:
+        eng.add_subdomain(global_id=sd.r, nx=sd.nx, ny=sd.ny, nt=sd.nt, dt=sd.dt, matrix=sd.matrix.tocsr(),
+                          n_flux=sd.nf, n_pressure=sd.np, neighbor=sd.neighbors,
+                          side_dofs=[np.asarray(e) for e in sd.side_edges], f2c=sd.f2c, c2f=sd.c2f)
+    t0 = time.time()
+    eng.setup()
+    st = eng.stats()
+    print(f"setup {time.time() - t0:.2f}s  stats {st}", flush=True)
+    q = np.random.default_rng(0).standard_normal(prob.n_iface)
+    t0 = time.time()
+    ap = eng.apply(q)
+    print(f"first apply (graph capture) {time.time() - t0:.3f}s  |ap| {np.linalg.norm(ap):.6e}", flush=True)
+    ms_ = eng.apply_device(reps)
+    steps = sum(sd.nt for sd in prob.subs)
+    # bytes per apply: every batch streams its factor nt times
+    print(f"apply {ms_:.3f} ms  ({1e3 / ms_:.2f} applies/s)  step_bytes(all batches, 1 step) {st['step_bytes'] / 1e6:.1f} MB")
+    dofsteps = sum(sd.n * sd.nt for sd in prob.subs)
+    print(f"DOF*steps/s {dofsteps / (ms_ * 1e-3):.3e}")
+    eng.close()
