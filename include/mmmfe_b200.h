@@ -92,6 +92,9 @@ int mmmfe_comm_init(mmmfe_ctx *ctx, int rank, int world, const void *id);
 /* owner_rank[g] = rank that holds global subdomain g (length n_global); required before mmmfe_setup when
  * world > 1, optional (all zero) otherwise.                                                                   */
 int mmmfe_set_owners(mmmfe_ctx *ctx, int32_t n_global, const int32_t *owner_rank);
+/* In-place sum over ranks of n host doubles (error numerators/denominators: MPI_Reduce, src/darcy_vtdd.cc:1812-1813).
+ * A no-op on one rank.                                                                                        */
+int mmmfe_comm_allreduce_sum(mmmfe_ctx *ctx, double *inout, int32_t n);
 
 /* ---- setup: once per refinement cycle ----------------------------------------------------------------------- */
 /* Registers a subdomain held by this rank; returns its local index. */
@@ -113,6 +116,9 @@ int64_t mmmfe_factor_values(const mmmfe_ctx *ctx);
 int64_t mmmfe_step_bytes(const mmmfe_ctx *ctx);
 double mmmfe_factor_flops(const mmmfe_ctx *ctx);
 double mmmfe_factor_seconds(const mmmfe_ctx *ctx);
+/* Kernels this library has launched on the device since the context was created (graph replays count their
+ * kernel nodes).                                                                                              */
+int64_t mmmfe_kernel_launches(const mmmfe_ctx *ctx);
 
 /* ---- bar sweep: solve_timestep(0, .) for every level (src/darcy_vtdd.cc:884-890, 902-920) -------------------- */
 /* Per local subdomain, the caller provides the data-dependent right-hand sides assemble_rhs_bar would build
@@ -132,6 +138,11 @@ int mmmfe_bar_sweep(mmmfe_ctx *ctx);
 /* One operator application Ap = -(send + recv) with send = s * f2c(star trace(c2f(q)))
  * (src/darcy_vtdd.cc:1316-1411): HOST in, HOST out, length mmmfe_interface_length.  Collective over ranks.     */
 int mmmfe_apply_interface_operator(mmmfe_ctx *ctx, const double *q, double *ap);
+/* Initial residual r = sum over both sides of s * f2c(bar trace) (src/darcy_vtdd.cc:1212-1256), HOST out. */
+int mmmfe_get_initial_residual(mmmfe_ctx *ctx, double *r);
+/* Page-locked host buffers for callers that drive the operator from host memory. */
+void *mmmfe_alloc_pinned(int64_t bytes);
+void mmmfe_free_pinned(void *p);
 /* Same, operating on the library's device-resident buffers; `repeat` applications back to back with q fixed.
  * Used by benchmarks (inputs already in HBM); returns the device time per application in milliseconds.        */
 int mmmfe_apply_interface_operator_device(mmmfe_ctx *ctx, int32_t repeat, double *ms_per_apply);
@@ -142,6 +153,7 @@ typedef struct {
   double r_norm;          /* printed "r_norm" (every interface counted twice, src/darcy_vtdd.cc:1265-1276)  */
   double final_residual;  /* last relative residual                                                           */
   double seconds;         /* wall time of the loop                                                            */
+  double device_ms;       /* CUDA-event time of the iteration loop on the interface stream                    */
 } mmmfe_gmres_info;
 
 /* local_gmres (src/darcy_vtdd.cc:1139-1521): classical Gram-Schmidt Arnoldi, Givens least squares, the reference's
@@ -162,6 +174,15 @@ int mmmfe_get_star_trace(mmmfe_ctx *ctx, int32_t local_index, int32_t side, doub
 /* ---- single-subdomain kernels exposed for parity tests --------------------------------------------------------- */
 /* x = K^{-1} rhs for the saddle matrix of one local subdomain (A_direct.vmult, src/darcy_vtdd.cc:864, 877). */
 int mmmfe_solve_saddle(mmmfe_ctx *ctx, int32_t local_index, const double *rhs, double *x);
+
+/* ---- profiling ---------------------------------------------------------------------------------------------------- */
+/* Runs ONE star time step of every batch without graphs, with a CUDA event between kernel classes, and reports
+ * per class the device milliseconds, the algorithmic bytes streamed and the number of launches.
+ * Classes: 0 rhs build, 1 forward small fronts, 2 forward large fronts, 3 backward large, 4 backward small,
+ * 5 pressure update + trace.                                                                                   */
+#define MMMFE_N_KERNEL_CLASSES 6
+int mmmfe_profile_step(mmmfe_ctx *ctx, double ms[MMMFE_N_KERNEL_CLASSES], double bytes[MMMFE_N_KERNEL_CLASSES],
+                       int64_t launches[MMMFE_N_KERNEL_CLASSES]);
 
 /* ---- diagnostics (host only, no device needed) ------------------------------------------------------------------- */
 /* The nested-dissection tree the engine builds for an nx x ny RT0 grid, in canonical flux numbering.

@@ -35,7 +35,7 @@ class SubdomainDesc(ctypes.Structure):
 
 class GmresInfo(ctypes.Structure):
     _fields_ = [("iterations", ctypes.c_int32), ("converged", ctypes.c_int32), ("r_norm", ctypes.c_double),
-                ("final_residual", ctypes.c_double), ("seconds", ctypes.c_double)]
+                ("final_residual", ctypes.c_double), ("seconds", ctypes.c_double), ("device_ms", ctypes.c_double)]
 
 
 _engine = None
@@ -60,6 +60,8 @@ def load_engine():
         "mmmfe_comm_unique_id": (ctypes.c_int, [vp]),
         "mmmfe_comm_init": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp]),
         "mmmfe_set_owners": (ctypes.c_int, [vp, ctypes.c_int32, c_i32p]),
+        "mmmfe_comm_allreduce_sum": (ctypes.c_int, [vp, c_f64p, ctypes.c_int32]),
+        "mmmfe_kernel_launches": (ctypes.c_int64, [vp]),
         "mmmfe_add_subdomain": (ctypes.c_int, [vp, ctypes.POINTER(SubdomainDesc), c_i32p]),
         "mmmfe_setup": (ctypes.c_int, [vp]),
         "mmmfe_interface_length": (ctypes.c_int64, [vp]),
@@ -72,6 +74,9 @@ def load_engine():
         "mmmfe_bar_set_data": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p, c_f64p, ctypes.c_int32, c_i32p, c_f64p]),
         "mmmfe_bar_sweep": (ctypes.c_int, [vp]),
         "mmmfe_apply_interface_operator": (ctypes.c_int, [vp, c_f64p, c_f64p]),
+        "mmmfe_get_initial_residual": (ctypes.c_int, [vp, c_f64p]),
+        "mmmfe_alloc_pinned": (ctypes.c_void_p, [ctypes.c_int64]),
+        "mmmfe_free_pinned": (None, [ctypes.c_void_p]),
         "mmmfe_apply_interface_operator_device": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p]),
         "mmmfe_gmres_solve": (ctypes.c_int, [vp, ctypes.c_double, ctypes.c_int32, ctypes.POINTER(GmresInfo), c_f64p,
                                              ctypes.c_int32, c_f64p]),
@@ -79,6 +84,7 @@ def load_engine():
         "mmmfe_get_solution": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p]),
         "mmmfe_get_star_trace": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.c_int32, c_f64p]),
         "mmmfe_solve_saddle": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p, c_f64p]),
+        "mmmfe_profile_step": (ctypes.c_int, [vp, c_f64p, c_f64p, c_i64p]),
         "mmmfe_debug_get_factor": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p, ctypes.c_int64]),
         "mmmfe_nd_tree_sizes": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_i64p]),
         "mmmfe_nd_tree_fill": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_i32p, c_i64p, c_i32p,
@@ -199,6 +205,10 @@ class Engine:
                     factor_flops=float(self.lib.mmmfe_factor_flops(self.h)),
                     factor_seconds=float(self.lib.mmmfe_factor_seconds(self.h)))
 
+    @property
+    def kernel_launches(self):
+        return int(self.lib.mmmfe_kernel_launches(self.h))
+
     def bar_set_data(self, li, p0, src, fr_dofs, fr_vals):
         p0 = _f64(p0) if p0 is not None else None
         src = _f64(src)
@@ -228,7 +238,7 @@ class Engine:
         self._check(self.lib.mmmfe_gmres_solve(self.h, tol, max_iter, ctypes.byref(info), _ptr(hist, c_f64p),
                                                len(hist), _ptr(lam, c_f64p)))
         return dict(iterations=info.iterations, converged=bool(info.converged), r_norm=info.r_norm,
-                    final_residual=info.final_residual, seconds=info.seconds,
+                    final_residual=info.final_residual, seconds=info.seconds, device_ms=info.device_ms,
                     residuals=hist[:info.iterations + 1].copy(), lam=lam)
 
     def final_sweep(self):
@@ -245,6 +255,12 @@ class Engine:
         out = np.empty((s["nt"], s["n_side"][side]))
         self._check(self.lib.mmmfe_get_star_trace(self.h, li, side, _ptr(out, c_f64p)))
         return out
+
+    def profile_step(self):
+        ms, by, ln = np.zeros(6), np.zeros(6), np.zeros(6, dtype=np.int64)
+        self._check(self.lib.mmmfe_profile_step(self.h, _ptr(ms, c_f64p), _ptr(by, c_f64p), _ptr(ln, c_i64p)))
+        names = ["rhs_build", "forward_small", "forward_large", "backward_large", "backward_small", "update_trace"]
+        return {n: dict(ms=float(ms[i]), bytes=float(by[i]), launches=int(ln[i])) for i, n in enumerate(names)}
 
     def debug_get_factor(self, li, r_total):
         out = np.empty(r_total)
@@ -272,3 +288,110 @@ def nd_tree(nx, ny, leaf_cells=4):
                            _ptr(src, c_i32p))
     return dict(nodes=nodes, offsets=offs, idx=idx, src=src, r_total=int(sizes[3]), z_total=int(sizes[4]),
                 n_heights=int(sizes[5]))
+
+
+# ---- C++ host front-end (include/mmmfe_host.h) --------------------------------------------------------------------
+class HostOptions(ctypes.Structure):
+    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("nccl_id", ctypes.c_void_p),
+                ("device", ctypes.c_int32), ("compute_errors", ctypes.c_int32), ("write_output", ctypes.c_int32),
+                ("final_sweep", ctypes.c_int32), ("verbose", ctypes.c_int32), ("only_cycle", ctypes.c_int32),
+                ("fixed_iterations", ctypes.c_int32), ("apply_repeat", ctypes.c_int32),
+                ("num_refinement", ctypes.c_int32), ("mortar_degree", ctypes.c_int32), ("output_dir", ctypes.c_char_p),
+                ("warmup_iterations", ctypes.c_int32), ("e2e_iterations", ctypes.c_int32), ("profile", ctypes.c_int32)]
+
+
+class HostReport(ctypes.Structure):
+    _fields_ = [("cycle", ctypes.c_int32), ("gmres_iterations", ctypes.c_int32), ("converged", ctypes.c_int32),
+                ("factor_groups", ctypes.c_int32), ("r_norm", ctypes.c_double), ("velocity_l2l2", ctypes.c_double),
+                ("pressure_dg", ctypes.c_double), ("pressure_l2l2", ctypes.c_double), ("lambda_l2", ctypes.c_double),
+                ("t_assemble", ctypes.c_double), ("t_factor", ctypes.c_double), ("t_bar_data", ctypes.c_double),
+                ("t_bar", ctypes.c_double), ("t_gmres", ctypes.c_double), ("t_final", ctypes.c_double),
+                ("t_errors", ctypes.c_double), ("t_output", ctypes.c_double), ("gmres_device_ms", ctypes.c_double),
+                ("apply_ms", ctypes.c_double), ("factor_flops", ctypes.c_double),
+                ("interface_length", ctypes.c_int64), ("dof_steps", ctypes.c_int64), ("step_bytes", ctypes.c_int64),
+                ("factor_values", ctypes.c_int64), ("kernel_launches", ctypes.c_int64),
+                ("e2e_ms_per_iteration", ctypes.c_double), ("e2e_h2d_bytes", ctypes.c_int64),
+                ("e2e_d2h_bytes", ctypes.c_int64), ("gmres_kernel_launches", ctypes.c_int64),
+                ("prof_ms", ctypes.c_double * 6), ("prof_bytes", ctypes.c_double * 6),
+                ("prof_launches", ctypes.c_int64 * 6)]
+
+
+_host = None
+
+
+def load_host():
+    """dlopen libmmmfe_host.so (the C++ front-end); raises when it is absent."""
+    global _host
+    if _host is not None:
+        return _host
+    load_engine()
+    if not os.path.exists(HOST_PATH):
+        raise MmmfeError(f"{HOST_PATH} is missing: run `python mmmfe-st-dd_b200/build.py`")
+    lib = ctypes.CDLL(HOST_PATH)
+    sig = {
+        "mmmfe_host_default_options": (None, [ctypes.POINTER(HostOptions)]),
+        "mmmfe_host_run": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(HostOptions), ctypes.POINTER(HostReport),
+                                          ctypes.c_int32]),
+        "mmmfe_host_last_residuals": (ctypes.c_int, [c_f64p, ctypes.c_int32]),
+        "mmmfe_host_last_lambda": (ctypes.c_int64, [c_f64p, ctypes.c_int64]),
+        "mmmfe_host_last_error": (ctypes.c_char_p, []),
+        "mmmfe_host_dump_subdomain": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                                     ctypes.c_char_p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    lib._signatures = sig
+    _host = lib
+    return lib
+
+
+def host_run(parameter_file, nccl_id=None, **options):
+    """Runs the DarcyVT front-end on a parameter file; returns (reports, residuals, lambda)."""
+    lib = load_host()
+    opt = HostOptions()
+    lib.mmmfe_host_default_options(ctypes.byref(opt))
+    keep = None
+    if nccl_id is not None:
+        keep = ctypes.create_string_buffer(nccl_id, len(nccl_id))
+        opt.nccl_id = ctypes.cast(keep, ctypes.c_void_p)
+    for k, v in options.items():
+        if k == "output_dir":
+            v = v.encode()
+        setattr(opt, k, v)
+    reps = (HostReport * 16)()
+    n = lib.mmmfe_host_run(os.fsencode(parameter_file), ctypes.byref(opt), reps, 16)
+    if n < 0:
+        raise MmmfeError(lib.mmmfe_host_last_error().decode())
+    out = []
+    for i in range(min(n, 16)):
+        d = {}
+        for f, _ in HostReport._fields_:
+            v = getattr(reps[i], f)
+            d[f] = list(v) if hasattr(v, "__len__") else v
+        out.append(d)
+    nres = lib.mmmfe_host_last_residuals(None, 0)
+    res = np.zeros(nres)
+    lib.mmmfe_host_last_residuals(_ptr(res, c_f64p), nres)
+    nl = lib.mmmfe_host_last_lambda(None, 0)
+    lam = np.zeros(nl)
+    lib.mmmfe_host_last_lambda(_ptr(lam, c_f64p), nl)
+    return out, res, lam
+
+
+def write_parameter_file(path, mesh, mortar, mortar_degree=1, num_refinement=1, c0=1.0, final_time=0.5, tol=1e-6,
+                         max_iteration=500, is_manufact=1, bc=("D 0.0", "D 0.0", "D 0.0", "D 0.0"), plots=0):
+    """Writes a parameter.txt in the reference's positional format (inc/filecheck_utility.h:44-84)."""
+    lines = ["synthetic DarcyVT parameter file", "-" * 40, "positional format: keep one key/value per line", "-" * 40,
+             f"c0: {c0}", "", "alpha: 1.0", "", "space_degree: 0", "", f"mortar_degree: {mortar_degree}", "",
+             f"num_refinement: {num_refinement}", "", f"final_time: {final_time}", "", f"tolerence: {tol}", "",
+             f"max_iteration: {max_iteration}", "", f"need_plot_at_each_time_step(bool): {plots}", "",
+             f"left_bc: {bc[0]}", f"bottom_bc: {bc[1]}", f"right_bc: {bc[2]}", f"top_bc: {bc[3]}", "",
+             f"is_manufact_soln(bool): {is_manufact}", ""]
+    for i, m in enumerate(mesh):
+        lines.append(f"mesh_pattern_sub_d{i}: {m[0]} {m[1]} {m[2]}")
+    lines.append(f"mesh_pattern_mortar: {mortar[0]} {mortar[1]} {mortar[2]}")
+    with open(path, "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    return path

@@ -166,6 +166,7 @@ struct LevelWork {
   DevBuf<int32_t> small_nodes;
   DevBuf<WorkItem> fwd, bwd;
   int32_t n_small = 0, n_fwd = 0, n_bwd = 0;
+  double bytes_fwd_small = 0, bytes_fwd_large = 0, bytes_bwd_small = 0, bytes_bwd_large = 0;
 };
 
 struct Factor {
@@ -196,6 +197,7 @@ struct Batch {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   cudaGraphExec_t graph_star = nullptr;
+  long long graph_kernels = 0;
   StepArgs step{};
 };
 
@@ -246,6 +248,7 @@ struct mmmfe_ctx {
   DevBuf<double> Q, h_dev, norm_dev;
   int64_t q_rows = 0;
   double factor_seconds = 0.0;
+  long long launch_base = 0;
   // temporaries of the factorisation
   DevBuf<GemmProb> d_gemm;
   DevBuf<int32_t> d_tiles;
@@ -490,7 +493,11 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd) {
       const NdNode &n = tr.nodes[id];
       const int64_t f = n.s + n.b;
       bytes += 8 * (int64_t(n.s) * n.b + int64_t(n.s) * f) + 4 * (2 * f + 2 * f);
-      if (n.s <= 32 && n.b <= 64) { small.push_back(id); continue; }
+      LevelWork &lwb = F->levels[h];
+      const bool is_small = n.s <= 32 && n.b <= 64;
+      (is_small ? lwb.bytes_fwd_small : lwb.bytes_fwd_large) += 8.0 * n.s * n.b + 4.0 * 3 * f;
+      (is_small ? lwb.bytes_bwd_small : lwb.bytes_bwd_large) += 8.0 * n.s * f + 4.0 * f;
+      if (is_small) { small.push_back(id); continue; }
       const int rows_per = (n.s + n.nsplit - 1) / n.nsplit;
       for (int sp = 0; sp < n.nsplit; ++sp) {
         const int r0 = sp * rows_per, r1 = std::min(n.s, r0 + rows_per);
@@ -557,13 +564,17 @@ static void run_star_sweeps(mmmfe_ctx *c, SweepMode mode) {
     if (mode == SWEEP_STAR && c->use_graphs) {
       if (!b.graph_star) {
         cudaGraph_t g = nullptr;
+        const long long before = launch_counter();
         CUDA_CHECK(cudaStreamBeginCapture(b.stream, cudaStreamCaptureModeThreadLocal));
         enqueue_sweep(c, b, SWEEP_STAR);
         CUDA_CHECK(cudaStreamEndCapture(b.stream, &g));
+        b.graph_kernels = launch_counter() - before;
+        launch_counter_add(-b.graph_kernels);  // capture launches nothing; every replay adds them back
         CUDA_CHECK(cudaGraphInstantiate(&b.graph_star, g, 0));
         CUDA_CHECK(cudaGraphDestroy(g));
       }
       CUDA_CHECK(cudaGraphLaunch(b.graph_star, b.stream));
+      launch_counter_add(b.graph_kernels);
     } else {
       enqueue_sweep(c, b, mode);
     }
@@ -620,7 +631,7 @@ static void setup(mmmfe_ctx *c) {
   if (c->is_setup) fail(MMMFE_E_INVALID, "mmmfe_setup called twice");
   if (c->subs.empty()) fail(MMMFE_E_INVALID, "no subdomains registered");
   CUDA_CHECK(cudaSetDevice(c->device));
-  CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  if (!c->stream) CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreate(&c->ev_t0));
   CUDA_CHECK(cudaEventCreate(&c->ev_t1));
@@ -812,6 +823,7 @@ static void gmres(mmmfe_ctx *c, double tol, int max_iter, mmmfe_gmres_info *info
   std::vector<double> res{1.0};
   std::vector<double> hh(size_t(max_iter) + 4);
   int k = 0, its = 0, converged = 0;
+  CUDA_CHECK(cudaEventRecord(c->ev_t0, st));
   while (k < max_iter) {
     apply_operator(c, Q + int64_t(k) * len, c->ap.p);
     ++its;  // cg_iteration++, :1363
@@ -847,6 +859,7 @@ static void gmres(mmmfe_ctx *c, double tol, int max_iter, mmmfe_gmres_info *info
     if (err < tol) { converged = 1; break; }  // :1488-1492, k not incremented (quirk Q1)
     ++k;
   }
+  CUDA_CHECK(cudaEventRecord(c->ev_t1, st));
   // back_solve over k columns, :1121-1135; y[k] stays 0
   std::vector<double> y(size_t(k) + 1, 0.0);
   for (int i = k - 1; i >= 0; --i) {
@@ -860,6 +873,9 @@ static void gmres(mmmfe_ctx *c, double tol, int max_iter, mmmfe_gmres_info *info
   if (info) {
     info->iterations = its; info->converged = converged; info->r_norm = r_norm; info->final_residual = res.back();
     info->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+    info->device_ms = ms;
   }
   if (hist) for (int i = 0; i < hist_cap && i < int(res.size()); ++i) hist[i] = res[i];
 }
@@ -893,6 +909,7 @@ int mmmfe_create(mmmfe_ctx **out, int device) {
   auto *c = new mmmfe_ctx();
   if (device < 0) cudaGetDevice(&device);
   c->device = device;
+  c->launch_base = launch_counter();
   if (cudaSetDevice(device) != cudaSuccess) { delete c; return MMMFE_E_CUDA; }
   *out = c;
   return MMMFE_OK;
@@ -973,6 +990,21 @@ int mmmfe_set_owners(mmmfe_ctx *c, int32_t n_global, const int32_t *owner_rank) 
   c->owner.assign(owner_rank, owner_rank + n_global);
   return MMMFE_OK;
 }
+
+int mmmfe_comm_allreduce_sum(mmmfe_ctx *c, double *inout, int32_t n) {
+  if (!c || !inout || n < 0) return MMMFE_E_INVALID;
+  if (c->world <= 1 || n == 0) return MMMFE_OK;
+  MMMFE_TRY(c, {
+    DevBuf<double> d;
+    d.upload(inout, size_t(n));
+    if (!c->stream) CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    allreduce_sum(c, d.p, size_t(n));
+    CUDA_CHECK(cudaMemcpyAsync(inout, d.p, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int64_t mmmfe_kernel_launches(const mmmfe_ctx *c) { return c ? launch_counter() - c->launch_base : 0; }
 
 int mmmfe_add_subdomain(mmmfe_ctx *c, const mmmfe_subdomain *d, int32_t *local_index) {
   if (!c || !d) return MMMFE_E_INVALID;
@@ -1072,6 +1104,24 @@ int mmmfe_apply_interface_operator(mmmfe_ctx *c, const double *q, double *ap) {
   });
 }
 
+int mmmfe_get_initial_residual(mmmfe_ctx *c, double *r) {
+  if (!c || !r) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, {
+    if (!c->bar_done) fail(MMMFE_E_INVALID, "bar sweep first");
+    CUDA_CHECK(cudaMemcpy(r, c->r0.p, size_t(c->n_iface) * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
+void *mmmfe_alloc_pinned(int64_t bytes) {
+  void *p = nullptr;
+  if (bytes <= 0 || cudaMallocHost(&p, size_t(bytes)) != cudaSuccess) return nullptr;
+  return p;
+}
+
+void mmmfe_free_pinned(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
 int mmmfe_apply_interface_operator_device(mmmfe_ctx *c, int32_t repeat, double *ms) {
   if (!c || repeat < 1) return MMMFE_E_INVALID;
   MMMFE_TRY(c, {
@@ -1151,6 +1201,57 @@ int mmmfe_solve_saddle(mmmfe_ctx *c, int32_t li, const double *rhs, double *x) {
     launch_update(a, nullptr, 0, nullptr, F.np, d_histp.p, int64_t(F.nf) + F.np, 0, st);
     CUDA_CHECK(cudaMemcpyAsync(x, out.p, out.n * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int mmmfe_profile_step(mmmfe_ctx *c, double ms[MMMFE_N_KERNEL_CLASSES], double bytes[MMMFE_N_KERNEL_CLASSES],
+                       int64_t launches[MMMFE_N_KERNEL_CLASSES]) {
+  if (!c || !ms || !bytes || !launches) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, {
+    if (!c->is_setup) fail(MMMFE_E_INVALID, "mmmfe_setup first");
+    for (int k = 0; k < MMMFE_N_KERNEL_CLASSES; ++k) { ms[k] = 0; bytes[k] = 0; launches[k] = 0; }
+    cudaStream_t st = c->stream;
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> cls;
+    auto mark = [&](int k) {
+      cudaEvent_t e;
+      CUDA_CHECK(cudaEventCreate(&e));
+      CUDA_CHECK(cudaEventRecord(e, st));
+      ev.push_back(e);
+      cls.push_back(k);
+    };
+    for (auto &bp : c->batches) {
+      Batch &b = *bp;
+      const Factor &F = *b.factor;
+      const int M = b.M;
+      SolveArgs a{F.fronts.p, F.R.p, F.idx_user.p, F.src.p, b.z.p, b.x.p};
+      const double vec = 8.0 * M;
+      mark(-1);
+      launch_build_rhs(b.step, c->lam_bar.p, 0, st);
+      mark(0); bytes[0] += vec * (F.nf + 2.0 * F.nf) + 12.0 * 2 * F.nf; launches[0] += 1;
+      const int H = int(F.levels.size());
+      for (int h = 0; h < H; ++h) {
+        const LevelWork &lw = F.levels[h];
+        if (lw.n_small) { launch_forward_small(M, a, lw.small_nodes.p, lw.n_small, st); mark(1); bytes[1] += lw.bytes_fwd_small; launches[1] += 1; }
+        if (lw.n_fwd) { launch_forward_large(M, a, lw.fwd.p, lw.n_fwd, st); mark(2); bytes[2] += lw.bytes_fwd_large; launches[2] += 1; }
+      }
+      for (int h = H - 1; h >= 0; --h) {
+        const LevelWork &lw = F.levels[h];
+        if (lw.n_bwd) { launch_backward_large(M, a, lw.bwd.p, lw.n_bwd, st); mark(3); bytes[3] += lw.bytes_bwd_large; launches[3] += 1; }
+        if (lw.n_small) { launch_backward_small(M, a, lw.small_nodes.p, lw.n_small, st); mark(4); bytes[4] += lw.bytes_bwd_small; launches[4] += 1; }
+      }
+      launch_update(b.step, c->trace.p, 0, nullptr, F.np, nullptr, int64_t(F.nf) + F.np, 0, st);
+      mark(5); bytes[5] += vec * (4.0 * F.np + 2.0 * F.np) + 12.0 * 4 * F.np; launches[5] += 1;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    for (size_t i = 1; i < ev.size(); ++i)
+      if (cls[i] >= 0) {
+        float t = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&t, ev[i - 1], ev[i]));
+        ms[cls[i]] += t;
+      }
+    for (auto e : ev) cudaEventDestroy(e);
   });
 }
 

@@ -7,7 +7,13 @@
 //  * time stepping, projector SpMV, exchange/combine and the classical Gram-Schmidt kernels.
 #include "kernels.cuh"
 
+#include <atomic>
+
 namespace mmmfe {
+
+static std::atomic<long long> g_launches{0};
+long long launch_counter() { return g_launches.load(); }
+void launch_counter_add(long long n) { g_launches.fetch_add(n); }
 
 // =================================================================================================================
 // grouped GEMM  C = alpha * A * B + beta * C   (FP64, DMMA)
@@ -98,6 +104,7 @@ void launch_grouped_gemm(const GemmProb *d_probs, const int32_t *d_tile_start, i
                          cudaStream_t st) {
   if (n_tiles <= 0) return;
   k_grouped_gemm<<<n_tiles, 256, 0, st>>>(d_probs, d_tile_start, n_probs);
+  launch_counter_add(1);
 }
 
 // =================================================================================================================
@@ -147,6 +154,7 @@ __global__ void __launch_bounds__(64) k_small_chol_inv(const InvProb *__restrict
 void launch_small_inverse(const InvProb *d_probs, int32_t n_probs, int32_t *d_fail, cudaStream_t st) {
   if (n_probs <= 0) return;
   k_small_chol_inv<<<(n_probs + 1) / 2, 64, 0, st>>>(d_probs, n_probs, d_fail);
+  launch_counter_add(1);
 }
 
 __global__ void __launch_bounds__(256) k_transpose(const TransProb *__restrict__ probs) {
@@ -161,6 +169,7 @@ void launch_transpose(const TransProb *d_probs, int32_t n_probs, cudaStream_t st
   for (int32_t off = 0; off < n_probs; off += 32768) {
     const int32_t cnt = n_probs - off < 32768 ? n_probs - off : 32768;
     k_transpose<<<dim3(cnt, 16), 256, 0, st>>>(d_probs + off);
+    launch_counter_add(1);
   }
 }
 
@@ -210,6 +219,7 @@ void launch_assemble_original(int64_t n_flux, const int64_t *s_rp, const int32_t
                               const int32_t *idx_canon, double *F, cudaStream_t st) {
   k_assemble_original<<<unsigned((n_flux + 255) / 256), 256, 0, st>>>(n_flux, s_rp, s_col, s_val, canon_of_dof,
                                                                       node_of, pos_of, fronts, f_off, idx_canon, F);
+  launch_counter_add(1);
 }
 
 __global__ void __launch_bounds__(256)
@@ -242,6 +252,7 @@ void launch_extend_add(const int32_t *d_nodes, int32_t n_nodes, const FrontDesc 
   for (int32_t off = 0; off < n_nodes; off += 32768) {
     const int32_t cnt = n_nodes - off < 32768 ? n_nodes - off : 32768;
     k_extend_add<<<dim3(cnt, 32), 256, 0, st>>>(d_nodes + off, fronts, f_off, src, F);
+    launch_counter_add(1);
   }
 }
 
@@ -482,18 +493,22 @@ __global__ void __launch_bounds__(256) k_backward_small(SolveArgs a, const int32
 void launch_forward_large(int M, const SolveArgs &a, const WorkItem *items, int32_t n_items, cudaStream_t st) {
   if (n_items <= 0) return;
   MMMFE_DISPATCH_M(M, (k_forward_large<MM><<<n_items, 256, 0, st>>>(a, items)));
+  launch_counter_add(1);
 }
 void launch_forward_small(int M, const SolveArgs &a, const int32_t *nodes, int32_t n_nodes, cudaStream_t st) {
   if (n_nodes <= 0) return;
   MMMFE_DISPATCH_M(M, (k_forward_small<MM><<<(n_nodes + 7) / 8, 256, 0, st>>>(a, nodes, n_nodes)));
+  launch_counter_add(1);
 }
 void launch_backward_large(int M, const SolveArgs &a, const WorkItem *items, int32_t n_items, cudaStream_t st) {
   if (n_items <= 0) return;
   MMMFE_DISPATCH_M(M, (k_backward_large<MM><<<n_items, 256, 0, st>>>(a, items)));
+  launch_counter_add(1);
 }
 void launch_backward_small(int M, const SolveArgs &a, const int32_t *nodes, int32_t n_nodes, cudaStream_t st) {
   if (n_nodes <= 0) return;
   MMMFE_DISPATCH_M(M, (k_backward_small<MM><<<(n_nodes + 7) / 8, 256, 0, st>>>(a, nodes, n_nodes)));
+  launch_counter_add(1);
 }
 
 // =================================================================================================================
@@ -516,6 +531,7 @@ __global__ void __launch_bounds__(256) k_build_rhs(StepArgs a, const double *__r
 
 void launch_build_rhs(const StepArgs &a, const double *lam_bar, int32_t level, cudaStream_t st) {
   k_build_rhs<<<unsigned((a.n_flux + 255) / 256), 256, 0, st>>>(a, lam_bar, level);
+  launch_counter_add(1);
 }
 
 __global__ void __launch_bounds__(256) k_add_sparse(double *x, int32_t M, int32_t member,
@@ -529,6 +545,7 @@ void launch_add_sparse(double *x, int32_t M, int32_t member, const int32_t *dofs
                        cudaStream_t st) {
   if (n <= 0) return;
   k_add_sparse<<<(n + 255) / 256, 256, 0, st>>>(x, M, member, dofs, vals, n);
+  launch_counter_add(1);
 }
 
 __global__ void __launch_bounds__(256)
@@ -575,6 +592,7 @@ void launch_update(const StepArgs &a, double *trace, int32_t level, const double
   const int64_t n = a.n_pressure + a.n_tr + (hist ? a.n_flux : 0);
   k_update<<<unsigned((n + 255) / 256), 256, 0, st>>>(a, trace, level, src_next, src_stride, hist,
                                                       hist_level_stride, add_hist);
+  launch_counter_add(1);
 }
 
 __global__ void __launch_bounds__(256) k_init_ptil(StepArgs a, const double *const *__restrict__ p0,
@@ -591,6 +609,7 @@ __global__ void __launch_bounds__(256) k_init_ptil(StepArgs a, const double *con
 
 void launch_init_ptil(const StepArgs &a, const double *const *p0, const double *const *src0, cudaStream_t st) {
   k_init_ptil<<<unsigned((a.n_pressure + 255) / 256), 256, 0, st>>>(a, p0, src0);
+  launch_counter_add(1);
 }
 
 // =================================================================================================================
@@ -610,6 +629,7 @@ void launch_spmv(int64_t n_rows, const int64_t *rp, const int32_t *col, const do
                  double *y, cudaStream_t st) {
   if (n_rows <= 0) return;
   k_spmv<<<unsigned((n_rows + 255) / 256), 256, 0, st>>>(n_rows, rp, col, val, x, y);
+  launch_counter_add(1);
 }
 
 __global__ void __launch_bounds__(256) k_exchange_combine(int64_t n, const double *__restrict__ send,
@@ -627,6 +647,7 @@ void launch_exchange_combine(int64_t n, const double *send, const int64_t *partn
                              double *out, cudaStream_t st) {
   if (n <= 0) return;
   k_exchange_combine<<<unsigned((n + 255) / 256), 256, 0, st>>>(n, send, partner, recv, sign, out);
+  launch_counter_add(1);
 }
 
 __global__ void __launch_bounds__(256) k_gather(int64_t n, const double *__restrict__ srcv,
@@ -638,6 +659,7 @@ __global__ void __launch_bounds__(256) k_gather(int64_t n, const double *__restr
 void launch_gather(int64_t n, const double *srcv, const int64_t *index, double *dst, cudaStream_t st) {
   if (n <= 0) return;
   k_gather<<<unsigned((n + 255) / 256), 256, 0, st>>>(n, srcv, index, dst);
+  launch_counter_add(1);
 }
 
 __device__ __forceinline__ double block_sum_512(double v, double *sm) {
@@ -669,6 +691,7 @@ __global__ void __launch_bounds__(512) k_multi_dot(int64_t len, const double *__
 void launch_multi_dot(int64_t len, const double *w, const double *Q, int64_t ldq, int32_t k_plus_1, double *h,
                       cudaStream_t st) {
   k_multi_dot<<<k_plus_1, 512, 0, st>>>(len, w, Q, ldq, h);
+  launch_counter_add(1);
 }
 
 constexpr int CGS_BLOCKS = 592;  // 4 per SM
@@ -700,7 +723,9 @@ __global__ void __launch_bounds__(512) k_final_sum(const double *__restrict__ pa
 void launch_cgs_update(int64_t len, double *w, const double *Q, int64_t ldq, int32_t k_plus_1, const double *h,
                        double *norm2, cudaStream_t st) {
   k_cgs_update<<<CGS_BLOCKS, 512, 0, st>>>(len, w, Q, ldq, k_plus_1, h, norm2 + 1);
+  launch_counter_add(1);
   k_final_sum<<<1, 512, 0, st>>>(norm2 + 1, CGS_BLOCKS, norm2);
+  launch_counter_add(1);
 }
 
 __global__ void __launch_bounds__(256) k_scale_store(int64_t len, const double *__restrict__ w, double inv,
@@ -713,6 +738,7 @@ __global__ void __launch_bounds__(256) k_scale_store(int64_t len, const double *
 void launch_scale_store(int64_t len, const double *w, double inv, double *dst, cudaStream_t st) {
   if (len <= 0) return;
   k_scale_store<<<unsigned((len + 255) / 256), 256, 0, st>>>(len, w, inv, dst);
+  launch_counter_add(1);
 }
 
 __global__ void __launch_bounds__(256) k_axpy_rows(int64_t len, const double *__restrict__ Q, int64_t ldq,
@@ -730,6 +756,7 @@ void launch_axpy_rows(int64_t len, const double *Q, int64_t ldq, int32_t n_rows,
                       cudaStream_t st) {
   if (len <= 0) return;
   k_axpy_rows<<<unsigned((len + 255) / 256), 256, 0, st>>>(len, Q, ldq, n_rows, y, out);
+  launch_counter_add(1);
 }
 
 }  // namespace mmmfe

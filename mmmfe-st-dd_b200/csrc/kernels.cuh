@@ -6,6 +6,10 @@
 
 namespace mmmfe {
 
+// kernels launched through the wrappers below (graph capture counts once; replays are added by the engine)
+long long launch_counter();
+void launch_counter_add(long long n);
+
 // One front of the nested-dissection tree as the solve kernels see it.
 struct FrontDesc {
   int32_t s, b, ldr, nsplit;

@@ -1,0 +1,873 @@
+// Host front-end: see darcy_vt.h.  Everything here is one-time work per refinement cycle (or one pass over the
+// solution); the interface-GMRES hot path runs in the CUDA engine behind include/mmmfe_b200.h.
+#include "darcy_vt.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <thread>
+
+#include "mmmfe_b200.h"
+
+#ifndef MMMFE_DATA_HEADER
+#define MMMFE_DATA_HEADER "data_default.h"
+#endif
+#include MMMFE_DATA_HEADER
+
+namespace vt_darcy {
+
+namespace {
+
+using clk = std::chrono::steady_clock;
+double since(clk::time_point t0) { return std::chrono::duration<double>(clk::now() - t0).count(); }
+
+const double kNormal[4] = {-1.0, 1.0, 1.0, -1.0};  // get_normal_direction, inc/utilities.h:79-91
+enum { BOTTOM = 0, RIGHT = 1, TOP = 2, LEFT = 3 };
+
+// QGauss<1>(n) on [0,1]
+void gauss01(int n, std::vector<double> &x, std::vector<double> &w) {
+  x.assign(n, 0.0);
+  w.assign(n, 0.0);
+  const double pi = std::acos(-1.0);
+  for (int i = 0; i < n; ++i) {
+    double z = std::cos(pi * (i + 0.75) / (n + 0.5)), pp = 1.0;
+    for (int it = 0; it < 100; ++it) {
+      double p1 = 1.0, p2 = 0.0;
+      for (int j = 0; j < n; ++j) {
+        const double p3 = p2;
+        p2 = p1;
+        p1 = ((2.0 * j + 1.0) * z * p2 - j * p3) / (j + 1.0);
+      }
+      pp = n * (z * p1 - p2) / (z * z - 1.0);
+      const double dz = p1 / pp;
+      z -= dz;
+      if (std::fabs(dz) < 1e-16) break;
+    }
+    x[n - 1 - i] = 0.5 * (z + 1.0);
+    w[n - 1 - i] = 1.0 / ((1.0 - z * z) * pp * pp);
+  }
+}
+
+// orthonormal Legendre polynomial of degree a on [0,1] (deal.II Polynomials::Legendre)
+double legendre01(int a, double xi) {
+  const double s = 2.0 * xi - 1.0;
+  double p0 = 1.0, p1 = s;
+  if (a == 0) return 1.0;
+  for (int j = 1; j < a; ++j) {
+    const double p2 = ((2.0 * j + 1.0) * s * p1 - j * p0) / (j + 1.0);
+    p0 = p1;
+    p1 = p2;
+  }
+  return std::sqrt(2.0 * a + 1.0) * p1;
+}
+
+// find_2_divisors, inc/utilities.h:94-110
+void find_divisors(unsigned n, unsigned &n0, unsigned &n1) {
+  unsigned tmp = unsigned(std::floor(std::sqrt(double(n))));
+  while (n % tmp != 0) --tmp;
+  n0 = n / tmp;
+  n1 = tmp;
+}
+
+// find_neighbors (dim == 2), inc/utilities.h:183-205, 297-305; order bottom, right, top, left
+void find_neighbors(int r, int n0, int n1, int nb[4]) {
+  nb[0] = r - n0; nb[1] = r + 1; nb[2] = r + n0; nb[3] = r - 1;
+  if (r % n0 == 0) nb[3] = -1;
+  if ((r + 1) % n0 == 0) nb[1] = -1;
+  for (int s = 0; s < 4; ++s)
+    if (nb[s] < 0 || nb[s] >= n0 * n1) nb[s] = -1;
+}
+
+struct Csr {
+  long long n_rows = 0, n_cols = 0;
+  std::vector<long long> rp;
+  std::vector<int> col;
+  std::vector<double> val;
+  mmmfe_csr view() const { return mmmfe_csr{n_rows, n_cols, (const int64_t *)rp.data(), col.data(), val.data()}; }
+};
+
+// One subdomain: canonical dof order x-edges (i=0..nx, j) at j*(nx+1)+i, y-edges at nxe + j*nx + i, cells after.
+struct Sub {
+  int r, ix, iy, nx, ny, nt;
+  double x0, y0, Lx, Ly, hx, hy, dt;
+  int nxe, nye, nf, np, n;
+  int nb[4], n_side[4];
+  double edge_len[4];
+  std::vector<int> side_edges[4];
+  Csr matrix, f2c[4], c2f[4];
+  int mortar_len[4] = {0, 0, 0, 0};
+  int local = -1;
+  std::vector<double> solution;  // [nt][n] after the final sweep
+  std::vector<double> levels_t;  // accumulated times t += dt
+};
+
+void init_sub(Sub &s, int r, int n0, int n1, const std::vector<int> &pat, double final_time) {
+  s.r = r; s.ix = r % n0; s.iy = r / n0;
+  s.Lx = 1.0 / n0; s.Ly = 1.0 / n1;
+  s.x0 = s.ix * s.Lx;                                   // get_subdomain_coordinates, inc/utilities.h:152-157
+  s.y0 = s.Ly * std::floor(double(r) / double(n0));
+  s.nx = pat[0]; s.ny = pat[1]; s.nt = pat[2];
+  s.hx = s.Lx / s.nx; s.hy = s.Ly / s.ny;
+  s.dt = final_time / double(s.nt);                     // src/darcy_vtdd.cc:2083
+  s.nxe = (s.nx + 1) * s.ny; s.nye = s.nx * (s.ny + 1);
+  s.nf = s.nxe + s.nye; s.np = s.nx * s.ny; s.n = s.nf + s.np;
+  find_neighbors(r, n0, n1, s.nb);
+  s.n_side[0] = s.n_side[2] = s.nx; s.n_side[1] = s.n_side[3] = s.ny;
+  s.edge_len[0] = s.edge_len[2] = s.hx; s.edge_len[1] = s.edge_len[3] = s.hy;
+  for (int k = 0; k < 4; ++k) s.side_edges[k].clear();
+  for (int i = 0; i < s.nx; ++i) { s.side_edges[BOTTOM].push_back(s.nxe + i); s.side_edges[TOP].push_back(s.nxe + s.ny * s.nx + i); }
+  for (int j = 0; j < s.ny; ++j) { s.side_edges[RIGHT].push_back(j * (s.nx + 1) + s.nx); s.side_edges[LEFT].push_back(j * (s.nx + 1)); }
+  s.levels_t.resize(s.nt);
+  double t = 0.0;
+  for (int l = 0; l < s.nt; ++l) { t += s.dt; s.levels_t[l] = t; }  // prm.time += prm.time_step, :887
+}
+
+// assemble_system, src/darcy_vtdd.cc:401-484: [[A, -B^T], [dt B, c0 M]], QGauss<2>(degree+2) = 2x2 points
+void assemble_matrix(Sub &s, double c0) {
+  const int n = s.n, W = 12;
+  std::vector<int> cnt(n, 0), cols(size_t(n) * W);
+  std::vector<double> vals(size_t(n) * W);
+  auto add = [&](int r, int c, double v) {
+    int *rc = &cols[size_t(r) * W];
+    double *rv = &vals[size_t(r) * W];
+    for (int t = 0; t < cnt[r]; ++t) if (rc[t] == c) { rv[t] += v; return; }
+    if (cnt[r] >= W) throw std::runtime_error("matrix row overflow");
+    rc[cnt[r]] = c; rv[cnt[r]] = v; ++cnt[r];
+  };
+  std::vector<double> g, w;
+  gauss01(2, g, w);
+  const KInverse<2> k_inverse;
+  std::vector<dealii::Point<2>> pts(4);
+  std::vector<dealii::Tensor<2, 2>> kin(4);
+  const double div[4] = {-1.0, 1.0, -1.0, 1.0};
+  for (int j = 0; j < s.ny; ++j)
+    for (int i = 0; i < s.nx; ++i) {
+      const int loc[4] = {j * (s.nx + 1) + i, j * (s.nx + 1) + i + 1, s.nxe + j * s.nx + i, s.nxe + (j + 1) * s.nx + i};
+      const int cell = s.nf + j * s.nx + i;
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) pts[a * 2 + b] = dealii::Point<2>(s.x0 + (i + g[a]) * s.hx, s.y0 + (j + g[b]) * s.hy);
+      k_inverse.value_list(pts, kin);
+      double aloc[4][4] = {{0}};
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) {
+          const int q = a * 2 + b;
+          const double jxw = w[a] * w[b] * s.hx * s.hy;
+          // basis values (flux-integral normalised): x-left, x-right, y-bottom, y-top
+          const double phi[4][2] = {{(1 - g[a]) / s.hy, 0}, {g[a] / s.hy, 0}, {0, (1 - g[b]) / s.hx}, {0, g[b] / s.hx}};
+          for (int e = 0; e < 4; ++e)
+            for (int f = 0; f < 4; ++f) {
+              double v = 0;
+              for (int d = 0; d < 2; ++d)
+                for (int d2 = 0; d2 < 2; ++d2) v += phi[e][d] * kin[q][d][d2] * phi[f][d2];
+              aloc[e][f] += jxw * v;
+            }
+        }
+      for (int e = 0; e < 4; ++e) {
+        for (int f = 0; f < 4; ++f) add(loc[e], loc[f], aloc[e][f]);
+        add(loc[e], cell, -div[e]);         // -phi_p div phi_u
+        add(cell, loc[e], s.dt * div[e]);   // dt div phi_u phi_p
+      }
+      add(cell, cell, c0 * s.hx * s.hy);
+    }
+  Csr &m = s.matrix;
+  m.n_rows = m.n_cols = n;
+  m.rp.assign(n + 1, 0);
+  for (int r = 0; r < n; ++r) m.rp[r + 1] = m.rp[r] + cnt[r];
+  m.col.resize(m.rp[n]);
+  m.val.resize(m.rp[n]);
+  for (int r = 0; r < n; ++r) {
+    std::vector<std::pair<int, double>> row(cnt[r]);
+    for (int t = 0; t < cnt[r]; ++t) row[t] = {cols[size_t(r) * W + t], vals[size_t(r) * W + t]};
+    std::sort(row.begin(), row.end());
+    for (int t = 0; t < cnt[r]; ++t) { m.col[m.rp[r] + t] = row[t].first; m.val[m.rp[r] + t] = row[t].second; }
+  }
+}
+
+// cell index of a coordinate given in units of cells; ties go to the lower cell / earlier level (quirk Q5)
+int locate(double u, int n) {
+  const double r = std::nearbyint(u);
+  int idx = (std::fabs(u - r) < 1e-9) ? int(r) - 1 : int(std::floor(u));
+  return std::min(std::max(idx, 0), n - 1);
+}
+
+void push_merged(std::vector<int> &rc, std::vector<double> &rv, int c, double v) {
+  for (size_t t = 0; t < rc.size(); ++t) if (rc[t] == c) { rv[t] += v; return; }
+  rc.push_back(c); rv.push_back(v);
+}
+
+void finish_row(Csr &m, std::vector<int> &rc, std::vector<double> &rv) {
+  std::vector<std::pair<int, double>> row(rc.size());
+  for (size_t t = 0; t < rc.size(); ++t) row[t] = {rc[t], rv[t]};
+  std::sort(row.begin(), row.end());
+  for (auto &e : row) { m.col.push_back(e.first); m.val.push_back(e.second); }
+  m.rp.push_back((long long)m.col.size());
+  rc.clear(); rv.clear();
+}
+
+// project_mortar as two explicit sampling operators (inc/utilities.h:471-505, inc/projector.h:150-207, 445-524;
+// SURVEY.md appendix A.4).  Mortar layout ((ft*ms + fs)*(k+1) + b)*(k+1) + a; fine layout level*n_side + m.
+void projector_tables(Sub &s, int side, const std::vector<int> &mortar, int k) {
+  const int ms = (side == BOTTOM || side == TOP) ? mortar[0] : mortar[1], mnt = mortar[2];
+  const int ns = s.n_side[side], nt = s.nt, nq = k + 1, nd = nq * nq;
+  std::vector<double> xi, w;
+  gauss01(nq, xi, w);
+  std::vector<double> leg(size_t(nq) * nq);
+  for (int a = 0; a < nq; ++a) for (int q = 0; q < nq; ++q) leg[a * nq + q] = legendre01(a, xi[q]);
+  const double H = ((side == BOTTOM || side == TOP) ? s.Lx : s.Ly) / ms, T = (s.nt * s.dt) / mnt, e_len = s.edge_len[side];
+  s.mortar_len[side] = ms * mnt * nd;
+  Csr &f2c = s.f2c[side], &c2f = s.c2f[side];
+  f2c = Csr(); c2f = Csr();
+  f2c.n_rows = s.mortar_len[side]; f2c.n_cols = (long long)ns * nt; f2c.rp.assign(1, 0);
+  c2f.n_rows = (long long)ns * nt; c2f.n_cols = s.mortar_len[side]; c2f.rp.assign(1, 0);
+  std::vector<int> rc;
+  std::vector<double> rv;
+  // f2c: Gauss points of each mortar face sample the piecewise-constant fine normal flux U/|e|
+  const double coef = H * T / e_len;
+  for (int ft = 0; ft < mnt; ++ft)
+    for (int fs = 0; fs < ms; ++fs)
+      for (int b = 0; b < nq; ++b)
+        for (int a = 0; a < nq; ++a) {
+          for (int r = 0; r < nq; ++r) {
+            const int lvl = locate((ft + xi[r]) / mnt * nt, nt);
+            for (int q = 0; q < nq; ++q) {
+              const int m = locate((fs + xi[q]) / ms * ns, ns);
+              push_merged(rc, rv, lvl * ns + m, coef * w[q] * w[r] * leg[a * nq + q] * leg[b * nq + r]);
+            }
+          }
+          finish_row(f2c, rc, rv);
+        }
+  // c2f: Gauss points of each fine space-time face sample the mortar polynomial; result is (2-D dof)/|e|
+  for (int lvl = 0; lvl < nt; ++lvl)
+    for (int m = 0; m < ns; ++m) {
+      for (int r = 0; r < nq; ++r) {
+        const double ut = (lvl + xi[r]) / nt * mnt;
+        const int ft = locate(ut, mnt);
+        for (int q = 0; q < nq; ++q) {
+          const double us = (m + xi[q]) / ns * ms;
+          const int fs = locate(us, ms);
+          for (int b = 0; b < nq; ++b)
+            for (int a = 0; a < nq; ++a)
+              push_merged(rc, rv, ((ft * ms + fs) * nq + b) * nq + a,
+                          w[q] * w[r] * legendre01(a, us - fs) * legendre01(b, ut - ft) / (H * T));
+        }
+      }
+      finish_row(c2f, rc, rv);
+    }
+}
+
+void side_point(const Sub &s, int side, int m, double xi, double &x, double &y) {
+  if (side == BOTTOM || side == TOP) { x = s.x0 + (m + xi) * s.hx; y = (side == BOTTOM) ? s.y0 : s.y0 + s.Ly; }
+  else { y = s.y0 + (m + xi) * s.hy; x = (side == LEFT) ? s.x0 : s.x0 + s.Lx; }
+}
+
+int side_to_bc(int side) { return side == LEFT ? 0 : side == BOTTOM ? 1 : side == RIGHT ? 2 : 3; }
+
+struct BarData {
+  std::vector<double> p0, src, fr_vals;
+  std::vector<int> fr_dofs;
+};
+
+// The data-dependent part of assemble_rhs_bar (src/darcy_vtdd.cc:632-766): dt (f, w) per cell and the outer
+// Dirichlet rows -s * int g; the c0 (p_old, w) term is added on the device.
+void bar_data(const Sub &s, int qdegree, bool manufact, const std::vector<char> &bc_type,
+              const std::vector<double> &bc_val, double c0, double alpha, BarData &out) {
+  std::vector<double> g2, w2, g5, w5, gq, wq;
+  gauss01(2, g2, w2);
+  gauss01(5, g5, w5);
+  gauss01(qdegree, gq, wq);
+  // VectorTools::project(IC, QGauss(degree+5)) onto DGQ0 = cell mean (src/darcy_vtdd.cc:2172-2176)
+  out.p0.assign(s.np, 0.0);
+  {
+    const InitialCondition<2> ic;
+    dealii::Vector<double> v(3);
+    for (int j = 0; j < s.ny; ++j)
+      for (int i = 0; i < s.nx; ++i) {
+        double acc = 0;
+        for (int a = 0; a < 5; ++a)
+          for (int b = 0; b < 5; ++b) {
+            ic.vector_value(dealii::Point<2>(s.x0 + (i + g5[a]) * s.hx, s.y0 + (j + g5[b]) * s.hy), v);
+            acc += w5[a] * w5[b] * v(2);
+          }
+        out.p0[j * s.nx + i] = acc;
+      }
+  }
+  out.src.assign(size_t(s.nt) * s.np, 0.0);
+  const double area = s.hx * s.hy;
+#pragma omp parallel for schedule(static)
+  for (int lvl = 0; lvl < s.nt; ++lvl) {
+    RightHandSidePressure<2> f(c0, alpha);
+    f.set_time(s.levels_t[lvl]);
+    double *dst = &out.src[size_t(lvl) * s.np];
+    for (int j = 0; j < s.ny; ++j)
+      for (int i = 0; i < s.nx; ++i) {
+        double acc = 0;
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b)
+            acc += w2[a] * w2[b] * f.value(dealii::Point<2>(s.x0 + (i + g2[a]) * s.hx, s.y0 + (j + g2[b]) * s.hy));
+        dst[j * s.nx + i] = s.dt * acc * area;  // :718
+      }
+  }
+  out.fr_dofs.clear();
+  std::vector<int> fr_side;
+  for (int side = 0; side < 4; ++side) {
+    if (s.nb[side] >= 0) continue;
+    if (!manufact && bc_type[side_to_bc(side)] != 'D') continue;  // Neumann sides: essential, see DESIGN.md
+    for (int m = 0; m < s.n_side[side]; ++m) { out.fr_dofs.push_back(s.side_edges[side][m]); fr_side.push_back(side * (1 << 24) + m); }
+  }
+  const int nfr = int(out.fr_dofs.size());
+  out.fr_vals.assign(size_t(s.nt) * nfr, 0.0);
+#pragma omp parallel for schedule(static)
+  for (int lvl = 0; lvl < s.nt; ++lvl) {
+    PressureBoundaryValues<2> gfun;
+    gfun.set_time(s.levels_t[lvl]);
+    for (int e = 0; e < nfr; ++e) {
+      const int side = fr_side[e] >> 24, m = fr_side[e] & ((1 << 24) - 1);
+      double acc = 0;
+      for (int q = 0; q < qdegree; ++q) {
+        double x, y;
+        side_point(s, side, m, gq[q], x, y);
+        double gv;
+        if (manufact) gv = gfun.value(dealii::Point<2>(x, y));
+        else gv = (side == TOP) ? bc_val[1] : bc_val[side_to_bc(side)];  // the reference reads [1] for the top (:673)
+        acc += wq[q] * gv;
+      }
+      out.fr_vals[size_t(lvl) * nfr + e] = -kNormal[side] * acc;  // :748-751
+    }
+  }
+}
+
+// compute_errors per subdomain, src/darcy_vtdd.cc:1657-1775; numerators/denominators {velocity, pressure L2, DG}
+void subdomain_errors(const Sub &s, double num[3], double den[3]) {
+  const double tq[3] = {0.0, 0.5, 1.0}, tw[3] = {0.25, 0.5, 0.25};  // QIterated(QTrapezoid, 2)
+  const int nt = s.nt;
+  std::vector<double> n0(nt, 0), d0(nt, 0), n1(nt, 0), d1(nt, 0), jump(nt, 0);
+  const double area = s.hx * s.hy;
+#pragma omp parallel for schedule(dynamic)
+  for (int lvl = 0; lvl < nt; ++lvl) {
+    ExactSolution<2> ex;
+    ex.set_time(s.levels_t[lvl]);
+    PressureBoundaryValues<2> proj_now, proj_old;
+    proj_now.set_time(s.levels_t[lvl] + 0.5 * s.dt);  // :1669-1670
+    if (lvl > 0) proj_old.set_time(s.levels_t[lvl - 1] + 0.5 * s.dt);
+    const double *x = &s.solution[size_t(lvl) * s.n];
+    const double *xo = lvl > 0 ? &s.solution[size_t(lvl - 1) * s.n] : nullptr;
+    dealii::Vector<double> v(3);
+    double a0 = 0, b0 = 0, a1 = 0, b1 = 0, jj = 0;
+    for (int j = 0; j < s.ny; ++j)
+      for (int i = 0; i < s.nx; ++i) {
+        const double p = x[s.nf + j * s.nx + i];
+        const double uxl = x[j * (s.nx + 1) + i], uxr = x[j * (s.nx + 1) + i + 1];
+        const double uyb = x[s.nxe + j * s.nx + i], uyt = x[s.nxe + (j + 1) * s.nx + i];
+        for (int a = 0; a < 3; ++a)
+          for (int b = 0; b < 3; ++b) {
+            const double wq = tw[a] * tw[b] * area;
+            ex.vector_value(dealii::Point<2>(s.x0 + (i + tq[a]) * s.hx, s.y0 + (j + tq[b]) * s.hy), v);
+            const double uhx = (uxl * (1 - tq[a]) + uxr * tq[a]) / s.hy, uhy = (uyb * (1 - tq[b]) + uyt * tq[b]) / s.hx;
+            a0 += wq * ((uhx - v(0)) * (uhx - v(0)) + (uhy - v(1)) * (uhy - v(1)));
+            b0 += wq * (v(0) * v(0) + v(1) * v(1));
+            a1 += wq * (p - v(2)) * (p - v(2));
+            b1 += wq * v(2) * v(2);
+          }
+        if (lvl > 0) {  // :1728-1743
+          const dealii::Point<2> c(s.x0 + (i + 0.5) * s.hx, s.y0 + (j + 0.5) * s.hy);
+          const double d = xo[s.nf + j * s.nx + i] + proj_now.value(c) - p - proj_old.value(c);
+          jj += d * d * area;
+        }
+      }
+    n0[lvl] = a0; d0[lvl] = b0; n1[lvl] = a1; d1[lvl] = b1; jump[lvl] = jj;
+  }
+  for (int k = 0; k < 3; ++k) num[k] = den[k] = 0;
+  const double final_time = s.dt * s.nt;
+  for (int lvl = 0; lvl < nt; ++lvl) {
+    num[0] += n0[lvl]; den[0] += d0[lvl];                // :1774-1775, no dt weight
+    num[1] += s.dt * n1[lvl]; den[1] += s.dt * d1[lvl];  // :1714-1715
+    num[2] += jump[lvl];
+    if (std::fabs(s.levels_t[lvl] - final_time) < 1e-12) { num[2] += n1[lvl]; den[2] += d1[lvl]; }  // :1744-1749
+  }
+}
+
+// compute_interface_error_l2, src/darcy_vtdd.cc:1566-1616
+void lambda_error(const Sub &s, int side, const double *coef, const std::vector<int> &mortar, int k, int qdegree,
+                  double &num, double &den) {
+  const int ms = (side == BOTTOM || side == TOP) ? mortar[0] : mortar[1], mnt = mortar[2], nq = k + 1;
+  std::vector<double> xi, w;
+  gauss01(qdegree, xi, w);
+  const double H = ((side == BOTTOM || side == TOP) ? s.Lx : s.Ly) / ms, T = (s.nt * s.dt) / mnt;
+  PressureBoundaryValues<3> pfun;
+  for (int ft = 0; ft < mnt; ++ft)
+    for (int fs = 0; fs < ms; ++fs) {
+      const double *c = coef + size_t(ft * ms + fs) * nq * nq;
+      for (int r = 0; r < qdegree; ++r)
+        for (int q = 0; q < qdegree; ++q) {
+          double val = 0;
+          for (int b = 0; b < nq; ++b)
+            for (int a = 0; a < nq; ++a) val += c[b * nq + a] * legendre01(a, xi[q]) * legendre01(b, xi[r]);
+          val /= (H * T);
+          const double sc = (fs + xi[q]) * H, tc = (ft + xi[r]) * T;
+          double x, y;
+          if (side == BOTTOM || side == TOP) { x = s.x0 + sc; y = (side == BOTTOM) ? s.y0 : s.y0 + s.Ly; }
+          else { y = s.y0 + sc; x = (side == LEFT) ? s.x0 : s.x0 + s.Lx; }
+          const double pe = pfun.value(dealii::Point<3>(x, y, tc));
+          const double jxw = w[q] * w[r] * H * T;
+          num += (val - pe) * (val - pe) * jxw;
+          den += pe * pe * jxw;
+        }
+    }
+}
+
+std::string pad4(int v) {
+  char b[16];
+  std::snprintf(b, sizeof b, "%04d", v);
+  return b;
+}
+
+// output_results, src/darcy_vtdd.cc:1906-1948: one patch per space-time cell, values at its 8 vertices; u3 = 0
+void write_st_vtu(const Sub &s, const std::string &dir) {
+  std::ofstream o(dir + "/space-time-plots/st_solution_d3_p" + pad4(s.r) + ".vtu");
+  if (!o) return;
+  const long long nc = (long long)s.nx * s.ny * s.nt;
+  o << std::setprecision(12);
+  o << "<?xml version=\"1.0\" ?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n<UnstructuredGrid>\n";
+  o << "<Piece NumberOfPoints=\"" << nc * 8 << "\" NumberOfCells=\"" << nc << "\">\n<Points>\n<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n";
+  for (int l = 0; l < s.nt; ++l)
+    for (int j = 0; j < s.ny; ++j)
+      for (int i = 0; i < s.nx; ++i)
+        for (int v = 0; v < 8; ++v)
+          o << s.x0 + (i + (v & 1)) * s.hx << ' ' << s.y0 + (j + ((v >> 1) & 1)) * s.hy << ' ' << (l + ((v >> 2) & 1)) * s.dt << '\n';
+  o << "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int64\" Name=\"connectivity\" format=\"ascii\">\n";
+  const int perm[8] = {0, 1, 3, 2, 4, 5, 7, 6};  // lexicographic -> VTK_HEXAHEDRON
+  for (long long c = 0; c < nc; ++c) { for (int v = 0; v < 8; ++v) o << c * 8 + perm[v] << ' '; o << '\n'; }
+  o << "</DataArray>\n<DataArray type=\"Int64\" Name=\"offsets\" format=\"ascii\">\n";
+  for (long long c = 1; c <= nc; ++c) o << c * 8 << '\n';
+  o << "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n";
+  for (long long c = 0; c < nc; ++c) o << "12\n";
+  o << "</DataArray>\n</Cells>\n<PointData Scalars=\"scalars\">\n<DataArray type=\"Float64\" Name=\"u\" NumberOfComponents=\"3\" format=\"ascii\">\n";
+  for (int l = 0; l < s.nt; ++l) {
+    const double *x = &s.solution[size_t(l) * s.n];
+    for (int j = 0; j < s.ny; ++j)
+      for (int i = 0; i < s.nx; ++i)
+        for (int v = 0; v < 8; ++v) {
+          const double u1 = x[j * (s.nx + 1) + i + (v & 1)] / s.hy, u2 = x[s.nxe + (j + ((v >> 1) & 1)) * s.nx + i] / s.hx;
+          o << u1 << ' ' << u2 << " 0\n";
+        }
+  }
+  o << "</DataArray>\n<DataArray type=\"Float64\" Name=\"p\" format=\"ascii\">\n";
+  for (int l = 0; l < s.nt; ++l) {
+    const double *x = &s.solution[size_t(l) * s.n];
+    for (int j = 0; j < s.ny; ++j)
+      for (int i = 0; i < s.nx; ++i)
+        for (int v = 0; v < 8; ++v) o << x[s.nf + j * s.nx + i] << '\n';
+  }
+  o << "</DataArray>\n</PointData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n";
+}
+
+void write_st_pvtu(int n_sub, const std::string &dir) {
+  std::ofstream o(dir + "/space-time-plots/st_solution_d3.pvtu");
+  if (!o) return;
+  o << "<?xml version=\"1.0\"?>\n<VTKFile type=\"PUnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n<PUnstructuredGrid GhostLevel=\"0\">\n";
+  o << "<PPointData Scalars=\"scalars\">\n<PDataArray type=\"Float64\" Name=\"u\" NumberOfComponents=\"3\" format=\"ascii\"/>\n<PDataArray type=\"Float64\" Name=\"p\" format=\"ascii\"/>\n</PPointData>\n";
+  o << "<PPoints>\n<PDataArray type=\"Float64\" NumberOfComponents=\"3\"/>\n</PPoints>\n";
+  for (int r = 0; r < n_sub; ++r) o << "<Piece Source=\"st_solution_d3_p" << pad4(r) << ".vtu\"/>\n";
+  o << "</PUnstructuredGrid>\n</VTKFile>\n";
+}
+
+// per-level 2-D output, src/darcy_vtdd.cc:1872-1903
+void write_level_vtu(const Sub &s, int level, const std::string &dir, int n_sub, bool master) {
+  {
+    std::ofstream o(dir + "/time-step-plots/solution_d2_p" + pad4(s.r) + "-" + std::to_string(level + 1) + ".vtu");
+    if (!o) return;
+    const long long nc = (long long)s.nx * s.ny;
+    const double *x = &s.solution[size_t(level) * s.n];
+    o << std::setprecision(12);
+    o << "<?xml version=\"1.0\" ?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n<UnstructuredGrid>\n";
+    o << "<Piece NumberOfPoints=\"" << nc * 4 << "\" NumberOfCells=\"" << nc << "\">\n<Points>\n<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n";
+    for (int j = 0; j < s.ny; ++j) for (int i = 0; i < s.nx; ++i) for (int v = 0; v < 4; ++v)
+      o << s.x0 + (i + (v & 1)) * s.hx << ' ' << s.y0 + (j + (v >> 1)) * s.hy << " 0\n";
+    o << "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int64\" Name=\"connectivity\" format=\"ascii\">\n";
+    const int perm[4] = {0, 1, 3, 2};
+    for (long long c = 0; c < nc; ++c) { for (int v = 0; v < 4; ++v) o << c * 4 + perm[v] << ' '; o << '\n'; }
+    o << "</DataArray>\n<DataArray type=\"Int64\" Name=\"offsets\" format=\"ascii\">\n";
+    for (long long c = 1; c <= nc; ++c) o << c * 4 << '\n';
+    o << "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n";
+    for (long long c = 0; c < nc; ++c) o << "9\n";
+    o << "</DataArray>\n</Cells>\n<PointData Scalars=\"scalars\">\n<DataArray type=\"Float64\" Name=\"u\" NumberOfComponents=\"3\" format=\"ascii\">\n";
+    for (int j = 0; j < s.ny; ++j) for (int i = 0; i < s.nx; ++i) for (int v = 0; v < 4; ++v)
+      o << x[j * (s.nx + 1) + i + (v & 1)] / s.hy << ' ' << x[s.nxe + (j + (v >> 1)) * s.nx + i] / s.hx << " 0\n";
+    o << "</DataArray>\n<DataArray type=\"Float64\" Name=\"p\" format=\"ascii\">\n";
+    for (int j = 0; j < s.ny; ++j) for (int i = 0; i < s.nx; ++i) for (int v = 0; v < 4; ++v) o << x[s.nf + j * s.nx + i] << '\n';
+    o << "</DataArray>\n</PointData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n";
+  }
+  if (master) {
+    std::ofstream o(dir + "/time-step-plots/solution_d2-" + std::to_string(level + 1) + ".pvtu");
+    if (!o) return;
+    o << "<?xml version=\"1.0\"?>\n<VTKFile type=\"PUnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n<PUnstructuredGrid GhostLevel=\"0\">\n";
+    o << "<PPointData Scalars=\"scalars\">\n<PDataArray type=\"Float64\" Name=\"u\" NumberOfComponents=\"3\" format=\"ascii\"/>\n<PDataArray type=\"Float64\" Name=\"p\" format=\"ascii\"/>\n</PPointData>\n";
+    o << "<PPoints>\n<PDataArray type=\"Float64\" NumberOfComponents=\"3\"/>\n</PPoints>\n";
+    for (int r = 0; r < n_sub; ++r) o << "<Piece Source=\"solution_d2_p" << pad4(r) << "-" << level + 1 << ".vtu\"/>\n";
+    o << "</PUnstructuredGrid>\n</VTKFile>\n";
+  }
+}
+
+void check(mmmfe_ctx *ctx, int rc, const char *what) {
+  if (rc != 0) throw std::runtime_error(std::string(what) + ": " + mmmfe_last_error(ctx));
+}
+
+}  // namespace
+
+unsigned int count_subdomain_lines(const std::string &file_name) {
+  std::ifstream f(file_name);
+  if (!f.is_open()) throw std::runtime_error("cannot open " + file_name);
+  std::string line;
+  unsigned n = 0;
+  while (std::getline(f, line)) {
+    const size_t p = line.find_first_not_of(" \t");
+    if (p != std::string::npos && line.compare(p, 18, "mesh_pattern_sub_d") == 0) ++n;
+  }
+  return n;
+}
+
+// inc/filecheck_utility.h:34-95: positional, key strings ignored
+void parameter_pull_in(double &c_0, double &alpha, int &space_degree, int &mortar_degree, int &num_refinement,
+                       double &final_time, double &tolerence, int &max_iteration, bool &need_each_time_step_plot,
+                       std::vector<char> &bc_con, std::vector<double> &nm_bc_con_funcs, bool &is_manufact_solution,
+                       std::vector<std::vector<int>> &mesh_m3d, unsigned int n_processes, std::string file_name) {
+  std::string dummy;
+  std::ifstream in(file_name);
+  if (!in.is_open()) throw std::runtime_error("parameter file " + file_name + " could not be opened");
+  for (int skip = 0; skip < 4; ++skip) std::getline(in, dummy);
+  in >> dummy >> c_0; std::getline(in, dummy);
+  in >> dummy >> alpha; std::getline(in, dummy);
+  in >> dummy >> space_degree; std::getline(in, dummy);
+  in >> dummy >> mortar_degree; std::getline(in, dummy);
+  in >> dummy >> num_refinement; std::getline(in, dummy);
+  in >> dummy >> final_time; std::getline(in, dummy);
+  in >> dummy >> tolerence; std::getline(in, dummy);
+  in >> dummy >> max_iteration; std::getline(in, dummy);
+  in >> dummy >> need_each_time_step_plot; std::getline(in, dummy);
+  bc_con.resize(4); nm_bc_con_funcs.resize(4);
+  for (int k = 0; k < 4; ++k) in >> dummy >> bc_con[k] >> nm_bc_con_funcs[k];
+  std::getline(in, dummy);
+  in >> dummy >> is_manufact_solution; std::getline(in, dummy);
+  mesh_m3d.assign(n_processes + 1, std::vector<int>(3, 0));
+  for (unsigned sub = 0; sub < n_processes + 1; ++sub) in >> dummy >> mesh_m3d[sub][0] >> mesh_m3d[sub][1] >> mesh_m3d[sub][2];
+  if (!in) throw std::runtime_error("parameter file " + file_name + " is incomplete");
+  for (char b : bc_con)
+    if (b != 'D' && b != 'N')
+      throw std::runtime_error("incompatible boundary condition read from parameter file: provide either D or N");
+}
+
+// Host-only diagnostic: writes what the front-end would hand to the engine for subdomain r of a cycle as raw
+// little-endian arrays under `dir` (used by the CPU tests to compare with the oracle; no device needed).
+void dump_subdomain(const std::vector<std::vector<int>> &reps, int r, double final_time, double c0, double alpha,
+                    int mortar_degree, bool manufact, const std::vector<char> &bc_type,
+                    const std::vector<double> &bc_val, const std::string &dir) {
+  const unsigned n_sub = unsigned(reps.size()) - 1;
+  unsigned n0, n1;
+  find_divisors(n_sub, n0, n1);
+  Sub s;
+  init_sub(s, r, int(n0), int(n1), reps[r], final_time);
+  assemble_matrix(s, c0);
+  auto wr = [&](const std::string &name, const void *p, size_t bytes) {
+    std::ofstream f(dir + "/" + name, std::ios::binary);
+    f.write(static_cast<const char *>(p), std::streamsize(bytes));
+  };
+  auto wr_csr = [&](const std::string &name, const Csr &m) {
+    const long long shape[2] = {m.n_rows, m.n_cols};
+    wr(name + ".shape", shape, sizeof shape);
+    wr(name + ".rp", m.rp.data(), m.rp.size() * sizeof(long long));
+    wr(name + ".col", m.col.data(), m.col.size() * sizeof(int));
+    wr(name + ".val", m.val.data(), m.val.size() * sizeof(double));
+  };
+  wr_csr("matrix", s.matrix);
+  for (int side = 0; side < 4; ++side)
+    if (s.nb[side] >= 0) {
+      projector_tables(s, side, reps.back(), mortar_degree);
+      wr_csr("f2c" + std::to_string(side), s.f2c[side]);
+      wr_csr("c2f" + std::to_string(side), s.c2f[side]);
+    }
+  BarData bd;
+  bar_data(s, mortar_degree + 1, manufact, bc_type, bc_val, c0, alpha, bd);
+  wr("p0", bd.p0.data(), bd.p0.size() * sizeof(double));
+  wr("src", bd.src.data(), bd.src.size() * sizeof(double));
+  wr("fr_dofs", bd.fr_dofs.data(), bd.fr_dofs.size() * sizeof(int));
+  wr("fr_vals", bd.fr_vals.data(), bd.fr_vals.size() * sizeof(double));
+  const int nb[4] = {s.nb[0], s.nb[1], s.nb[2], s.nb[3]};
+  wr("neighbors", nb, sizeof nb);
+}
+
+template <int dim>
+DarcyVTProblem<dim>::DarcyVTProblem(const unsigned int degree_, const BiotParameters &bprm, const unsigned int mortar_flag_,
+                                    const unsigned int mortar_degree_, std::vector<char> bc, std::vector<double> bcv,
+                                    const bool manufact, const bool plots)
+    : prm(bprm), bc_condition_vect(bc), bc_const_functs(bcv), is_manufact_solution(manufact),
+      need_each_time_step_plot(plots), degree(degree_), mortar_degree(mortar_degree_), mortar_flag(mortar_flag_) {}
+
+template <int dim>
+void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::vector<int>> &reps_st, double tol,
+                              unsigned int maxiter, unsigned int quad_degree) {
+  const int rank = control.rank, world = control.world;
+  const bool root = rank == 0;
+  const bool say = root && control.verbose;
+  if (reps_st.empty() || reps_st[0].size() != 3) throw std::runtime_error("mesh patterns must have 3 entries");
+  const unsigned n_sub = unsigned(reps_st.size()) - 1;
+  if (say) std::cout << "\n\n Total number of processes is " << n_sub << "\n\n";
+  if (mortar_flag != 1) throw std::runtime_error("only the mortar path (mortar_flag = 1) exists, as in the reference driver");
+  if (n_sub <= 1) throw std::runtime_error("Mortar MFEM is impossible with 1 subdomain");  // :2066
+  if (degree != 0) throw std::runtime_error("space_degree >= 1 is not valid on the space-time mortar path (see DESIGN.md, quirk Q7)");
+  const int qdegree = int(quad_degree);
+  unsigned n0, n1;
+  find_divisors(n_sub, n0, n1);
+  std::vector<std::vector<int>> reps = reps_st;
+  reports_.clear();
+
+  for (unsigned cycle = 0; cycle < refine; ++cycle) {
+    if (cycle > 0) {  // src/darcy_vtdd.cc:2124-2142
+      for (unsigned i = 0; i + 1 < reps.size(); ++i) for (int d = 0; d < 3; ++d) reps[i][d] *= 2;
+      if (mortar_degree == 1 || cycle % 2 == 0) for (int d = 0; d < 3; ++d) reps.back()[d] *= 2;
+    }
+    if (control.only_cycle >= 0 && int(cycle) != control.only_cycle) continue;
+    CycleReport rep;
+    rep.cycle = int(cycle);
+    const std::vector<int> &mortar = reps.back();
+    if (say) {
+      std::cout << "Final time= " << prm.final_time << "\n";
+      std::cout << "Mortar mesh has " << (long long)mortar[0] * mortar[1] * mortar[2] << " cells" << std::endl;
+      std::cout << "Making grid and DOFs...\n";
+    }
+    // ---- ownership: contiguous blocks of subdomains balanced by nt * cells ----
+    std::vector<int> owner(n_sub, 0);
+    if (world > 1) {
+      std::vector<double> cost(n_sub);
+      double total = 0;
+      for (unsigned r = 0; r < n_sub; ++r) { cost[r] = double(reps[r][0]) * reps[r][1] * reps[r][2]; total += cost[r]; }
+      double acc = 0;
+      for (unsigned r = 0; r < n_sub; ++r) {
+        owner[r] = std::min(world - 1, int(acc / total * world));
+        acc += cost[r];
+      }
+    }
+    auto t0 = clk::now();
+    std::vector<std::unique_ptr<Sub>> subs;
+    for (unsigned r = 0; r < n_sub; ++r) {
+      if (owner[r] != rank) continue;
+      auto s = std::make_unique<Sub>();
+      init_sub(*s, int(r), int(n0), int(n1), reps[r], prm.final_time);
+      subs.push_back(std::move(s));
+    }
+#pragma omp parallel for schedule(dynamic)
+    for (int li = 0; li < int(subs.size()); ++li) {
+      Sub &s = *subs[li];
+      assemble_matrix(s, prm.c_0);
+      for (int side = 0; side < 4; ++side)
+        if (s.nb[side] >= 0) projector_tables(s, side, mortar, int(mortar_degree));
+    }
+    rep.t_assemble = since(t0);
+    if (say && !subs.empty()) {
+      std::cout << "N flux subdom dofs: " << subs[0]->nf << std::endl;
+      std::cout << "N pressure subdom dofs: " << subs[0]->np << std::endl;
+      std::cout << "Assembling system...\n";
+    }
+    // ---- engine ----
+    mmmfe_ctx *ctx = nullptr;
+    if (mmmfe_create(&ctx, control.device) != 0)
+      throw std::runtime_error("no usable CUDA device: the interface-GMRES path has no CPU fallback");
+    struct Guard { mmmfe_ctx *c; ~Guard() { mmmfe_destroy(c); } } guard{ctx};
+    mmmfe_set_option(ctx, "keep_history", control.final_sweep ? 1 : 0);
+    if (world > 1) {
+      check(ctx, mmmfe_comm_init(ctx, rank, world, control.nccl_id), "mmmfe_comm_init");
+      check(ctx, mmmfe_set_owners(ctx, int(n_sub), owner.data()), "mmmfe_set_owners");
+    }
+    for (auto &sp : subs) {
+      Sub &s = *sp;
+      mmmfe_subdomain d{};
+      d.global_id = s.r; d.nx = s.nx; d.ny = s.ny; d.nt = s.nt; d.dt = s.dt;
+      d.matrix = s.matrix.view(); d.n_flux = s.nf; d.n_pressure = s.np; d.canon_of_dof = nullptr;
+      for (int k = 0; k < 4; ++k) {
+        d.neighbor[k] = s.nb[k]; d.n_side[k] = s.n_side[k]; d.side_dofs[k] = s.side_edges[k].data();
+        d.mortar_len[k] = s.mortar_len[k];
+        if (s.nb[k] >= 0) { d.f2c[k] = s.f2c[k].view(); d.c2f[k] = s.c2f[k].view(); }
+      }
+      check(ctx, mmmfe_add_subdomain(ctx, &d, &s.local), "mmmfe_add_subdomain");
+    }
+    t0 = clk::now();
+    check(ctx, mmmfe_setup(ctx), "mmmfe_setup");
+    rep.t_factor = since(t0);
+    if (say) std::cout << "  ...factorized..." << "\n";
+    rep.interface_length = mmmfe_interface_length(ctx);
+    rep.step_bytes = mmmfe_step_bytes(ctx);
+    rep.factor_values = mmmfe_factor_values(ctx);
+    rep.factor_flops = mmmfe_factor_flops(ctx);
+    rep.factor_groups = mmmfe_num_factor_groups(ctx);
+    for (auto &sp : subs) { rep.dof_steps += (long long)sp->n * sp->nt; sp->matrix = Csr(); }
+    // ---- bar problems ----
+    t0 = clk::now();
+    for (auto &sp : subs) {
+      BarData bd;
+      bar_data(*sp, qdegree, is_manufact_solution, bc_condition_vect, bc_const_functs, prm.c_0, prm.alpha, bd);
+      check(ctx, mmmfe_bar_set_data(ctx, sp->local, bd.p0.data(), bd.src.data(), int(bd.fr_dofs.size()),
+                                    bd.fr_dofs.data(), bd.fr_vals.data()), "mmmfe_bar_set_data");
+    }
+    rep.t_bar_data = since(t0);
+    t0 = clk::now();
+    check(ctx, mmmfe_bar_sweep(ctx), "mmmfe_bar_sweep");
+    rep.t_bar = since(t0);
+    if (say) std::cout << "\nStarting GMRES iterations.........\n";
+    // ---- interface GMRES ----
+    const bool fixed = control.fixed_iterations >= 0;
+    const int max_it = fixed ? std::max(1, control.fixed_iterations) : int(maxiter);
+    mmmfe_gmres_info info{};
+    std::vector<double> hist(size_t(max_it) + 2, 0.0);
+    rep.lambda.assign(size_t(rep.interface_length), 0.0);
+    if (fixed && control.warmup_iterations > 0)
+      check(ctx, mmmfe_gmres_solve(ctx, 0.0, control.warmup_iterations, &info, nullptr, 0, nullptr), "gmres warm-up");
+    const long long launches_before = mmmfe_kernel_launches(ctx);
+    t0 = clk::now();
+    check(ctx, mmmfe_gmres_solve(ctx, fixed ? 0.0 : tol, max_it, &info, hist.data(), int(hist.size()), rep.lambda.data()),
+          "mmmfe_gmres_solve");
+    rep.t_gmres = since(t0);
+    rep.gmres_kernel_launches = mmmfe_kernel_launches(ctx) - launches_before;
+    rep.gmres_iterations = info.iterations; rep.converged = info.converged; rep.r_norm = info.r_norm;
+    rep.gmres_device_ms = info.device_ms;
+    rep.residuals.assign(hist.begin(), hist.begin() + std::min<size_t>(hist.size(), size_t(info.iterations) + 1));
+    if (say) {
+      std::cout << "\n\n r_norm is " << info.r_norm << " target is " << info.r_norm * tol << "\n\n";
+      if (info.converged)
+        std::cout << "\n  GMRES converges in " << info.iterations << " iterations!\n and residual is "
+                  << info.final_residual * info.r_norm << "\n";
+      else if (!fixed)
+        std::cout << "\n  GMRES doesn't converge after  " << info.iterations << " iterations!\n";
+    }
+    if (control.apply_repeat > 0)
+      check(ctx, mmmfe_apply_interface_operator_device(ctx, control.apply_repeat, &control.apply_ms), "apply");
+    if (control.profile)
+      check(ctx, mmmfe_profile_step(ctx, rep.prof_ms, rep.prof_bytes, (int64_t *)rep.prof_launches), "profile");
+    if (control.e2e_iterations > 0) {
+      // The same iteration driven from host memory: every step copies the Krylov vector host -> device from a
+      // pinned buffer, applies the operator, copies A q back and does the Arnoldi update on the host
+      // (what local_gmres does between its MPI calls, src/darcy_vtdd.cc:1413-1463).
+      const long long len = rep.interface_length;
+      const int ne = control.e2e_iterations;
+      double *q = static_cast<double *>(mmmfe_alloc_pinned((len + 1) * sizeof(double)));
+      double *ap = static_cast<double *>(mmmfe_alloc_pinned((len + 1) * sizeof(double)));
+      if (!q || !ap) throw std::runtime_error("pinned allocation failed");
+      std::vector<std::vector<double>> Q;
+      std::vector<double> r(size_t(len) + 1);
+      check(ctx, mmmfe_get_initial_residual(ctx, r.data()), "initial residual");
+      double nn[1] = {0};
+      for (long long i = 0; i < len; ++i) nn[0] += r[i] * r[i];
+      check(ctx, mmmfe_comm_allreduce_sum(ctx, nn, 1), "allreduce");
+      Q.emplace_back(r.begin(), r.begin() + len);
+      for (auto &v : Q[0]) v /= std::sqrt(nn[0]);
+      double total = 0;
+      for (int k = 0; k < ne + 1; ++k) {  // iteration 0 is an untimed warm-up
+        const auto ti = clk::now();
+        std::copy(Q[k].begin(), Q[k].end(), q);
+        check(ctx, mmmfe_apply_interface_operator(ctx, q, ap), "apply (host buffers)");
+        std::vector<double> h(size_t(k) + 2, 0.0);
+        for (int i = 0; i <= k; ++i) { double a = 0; for (long long j = 0; j < len; ++j) a += ap[j] * Q[i][j]; h[i] = a; }
+        check(ctx, mmmfe_comm_allreduce_sum(ctx, h.data(), k + 1), "allreduce");
+        for (int i = 0; i <= k; ++i) for (long long j = 0; j < len; ++j) ap[j] -= h[i] * Q[i][j];
+        double n2[1] = {0};
+        for (long long j = 0; j < len; ++j) n2[0] += ap[j] * ap[j];
+        check(ctx, mmmfe_comm_allreduce_sum(ctx, n2, 1), "allreduce");
+        const double hk = std::sqrt(n2[0]);
+        Q.emplace_back(ap, ap + len);
+        for (auto &v : Q.back()) v /= hk;
+        if (k > 0) total += since(ti);
+      }
+      rep.e2e_ms_per_iteration = 1e3 * total / ne;
+      rep.e2e_h2d_bytes = len * 8;
+      rep.e2e_d2h_bytes = len * 8;
+      mmmfe_free_pinned(q);
+      mmmfe_free_pinned(ap);
+    }
+    // ---- final sweep, errors, output ----
+    if (control.final_sweep) {
+      t0 = clk::now();
+      check(ctx, mmmfe_final_sweep(ctx), "mmmfe_final_sweep");
+      for (auto &sp : subs) {
+        sp->solution.resize(size_t(sp->nt) * sp->n);
+        check(ctx, mmmfe_get_solution(ctx, sp->local, sp->solution.data()), "mmmfe_get_solution");
+      }
+      rep.t_final = since(t0);
+      if (say) std::cout << "finished local_gmres" << "\n";
+      if (is_manufact_solution && control.compute_errors) {
+        t0 = clk::now();
+        double buf[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // num{vel, pL2, DG, lambda}, den{...}
+        for (auto &sp : subs) {
+          double num[3], den[3];
+          subdomain_errors(*sp, num, den);
+          for (int k = 0; k < 3; ++k) { buf[k] += num[k]; buf[4 + k] += den[k]; }
+          for (int side = 0; side < 4; ++side)
+            if (sp->nb[side] >= 0) {
+              const long long off = mmmfe_interface_offset(ctx, sp->local, side);
+              lambda_error(*sp, side, rep.lambda.data() + off, mortar, int(mortar_degree), qdegree, buf[3], buf[7]);
+            }
+        }
+        if (world > 1) check(ctx, mmmfe_comm_allreduce_sum(ctx, buf, 8), "allreduce");  // MPI_Reduce, :1812-1813
+        rep.velocity_l2l2 = std::sqrt(buf[0]) / std::sqrt(buf[4]);
+        rep.pressure_l2l2 = std::sqrt(buf[1]) / std::sqrt(buf[5]);
+        rep.pressure_dg = std::sqrt(buf[2]) / std::sqrt(buf[6]);
+        rep.lambda_l2 = std::sqrt(buf[3]) / std::sqrt(buf[7]);
+        rep.t_errors = since(t0);
+      }
+      if (control.write_output && cycle + 1 == refine) {  // :1847
+        t0 = clk::now();
+        for (auto &sp : subs) {
+          write_st_vtu(*sp, control.output_dir);
+          if (need_each_time_step_plot)
+            for (int l = 0; l < sp->nt; ++l) write_level_vtu(*sp, l, control.output_dir, int(n_sub), root && sp->local == 0);
+        }
+        if (root) write_st_pvtu(int(n_sub), control.output_dir);
+        rep.t_output = since(t0);
+      }
+    }
+    rep.kernel_launches = mmmfe_kernel_launches(ctx);
+    if (!control.keep_lambda) rep.lambda.clear();
+    reports_.push_back(rep);
+  }
+  // convergence table, src/darcy_vtdd.cc:1957-1996
+  if (root && is_manufact_solution && control.compute_errors && control.final_sweep && !reports_.empty()) {
+    std::ostringstream txt, tex;
+    txt << "cycle # GMRES Velocity,L2-L2 Pressure,DG Pressure,L2-L2 Lambda,Darcy_L2\n";
+    tex << "\\begin{table}[H]\n\\begin{center}\n\\begin{tabular}{|c|c|c|c|c|c|c|c|c|c|c|}\\hline\ncycle & \\# gmres & & $ \\|z - z_h\\|_{L^{2}(L^2)} $ & & $ \\|p - p_h\\|_{DG} $ & & $ \\|p - p_h\\|_{L^{2}(L^2)} $ & & $ \\|p - \\lambda_p_H\\|_{L^{2}(L^2)} $ & \\\\ \\hline\n";
+    for (size_t i = 0; i < reports_.size(); ++i) {
+      const CycleReport &r = reports_[i];
+      auto rate = [&](double cur, double prev) {
+        std::ostringstream s;
+        if (i == 0) s << "-"; else s << std::fixed << std::setprecision(2) << std::log2(prev / cur);
+        return s.str();
+      };
+      const CycleReport &p = reports_[i ? i - 1 : 0];
+      std::ostringstream row;
+      row << std::scientific << std::setprecision(3);
+      txt << r.cycle << " " << r.gmres_iterations << " " << rate(r.gmres_iterations, p.gmres_iterations) << " ";
+      txt << std::scientific << std::setprecision(3) << r.velocity_l2l2 << " " << rate(r.velocity_l2l2, p.velocity_l2l2) << " "
+          << r.pressure_dg << " " << rate(r.pressure_dg, p.pressure_dg) << " " << r.pressure_l2l2 << " "
+          << rate(r.pressure_l2l2, p.pressure_l2l2) << " " << r.lambda_l2 << " " << rate(r.lambda_l2, p.lambda_l2) << "\n";
+      tex << r.cycle << " & " << r.gmres_iterations << " & " << rate(r.gmres_iterations, p.gmres_iterations) << " & "
+          << std::scientific << std::setprecision(3) << r.velocity_l2l2 << " & " << rate(r.velocity_l2l2, p.velocity_l2l2)
+          << " & " << r.pressure_dg << " & " << rate(r.pressure_dg, p.pressure_dg) << " & " << r.pressure_l2l2 << " & "
+          << rate(r.pressure_l2l2, p.pressure_l2l2) << " & " << r.lambda_l2 << " & " << rate(r.lambda_l2, p.lambda_l2)
+          << "\\\\ \\hline\n";
+    }
+    tex << "\\end{tabular}\n\\end{center}\n\\end{table}\n";
+    if (control.verbose) std::cout << std::endl << txt.str();
+    if (control.write_output) {
+      std::ofstream f(control.output_dir + "/error" + std::to_string(n_sub) + "domains.tex");
+      f << tex.str();
+    }
+  }
+}
+
+template class DarcyVTProblem<2>;
+
+}  // namespace vt_darcy

@@ -296,10 +296,18 @@ class Subdomain:
         mat.sum_duplicates()
         return mat
 
-    def factorize(self):
-        """A_direct.initialize, src/darcy_vtdd.cc:483 (UMFPACK there, SuperLU here)."""
+    def factorize(self, ordering="colamd"):
+        """A_direct.initialize, src/darcy_vtdd.cc:483 (UMFPACK there, SuperLU here).
+
+        ordering="nd": geometric nested-dissection column order (fill ~ n log n; what makes the large
+        CPU-baseline cases fit) instead of SuperLU's COLAMD.
+        """
         self.matrix = self.assemble_matrix()
-        self.lu = spla.splu(self.matrix)
+        if ordering == "nd":
+            perm = nested_dissection_order(self.nx, self.ny)
+            self.lu = _PermutedLU(self.matrix, perm)
+        else:
+            self.lu = spla.splu(self.matrix)
 
     # -- right-hand sides -----------------------------------------------------------------
     def project_initial_condition(self):
@@ -347,6 +355,67 @@ class Subdomain:
             if self.neighbors[side] >= 0:
                 rhs[self.side_edges[side]] += -NORMAL_SIGN[side] * lam_bar[side]  # :840-844
         return rhs
+
+
+def nested_dissection_order(nx, ny, leaf=8):
+    """Elimination order of the saddle unknowns (canonical numbering): leaves first, separators last.
+
+    A separator is a line of edges; every cell is ordered after the edges of its leaf that are not separators
+    (keeps the pivots of the quasi-definite matrix well defined without pivoting).
+    """
+    nxe = (nx + 1) * ny
+    nf = nxe + nx * (ny + 1)
+    order = []
+
+    def xe(i, j):
+        return j * (nx + 1) + i
+
+    def ye(i, j):
+        return nxe + j * nx + i
+
+    def rec(i0, i1, j0, j1):
+        w, h = i1 - i0, j1 - j0
+        if w * h <= leaf * leaf or (w == 1 and h == 1):
+            for j in range(j0, j1):
+                for i in range(i0, i1 + 1):
+                    if (i0 < i < i1) or (i == i0 and i0 == 0) or (i == i1 and i1 == nx):
+                        order.append(xe(i, j))
+            for j in range(j0, j1 + 1):
+                if (j0 < j < j1) or (j == j0 and j0 == 0) or (j == j1 and j1 == ny):
+                    for i in range(i0, i1):
+                        order.append(ye(i, j))
+            for j in range(j0, j1):
+                for i in range(i0, i1):
+                    order.append(nf + j * nx + i)
+            return
+        if w >= h:
+            m = i0 + w // 2
+            rec(i0, m, j0, j1)
+            rec(m, i1, j0, j1)
+            order.extend(xe(m, j) for j in range(j0, j1))
+        else:
+            m = j0 + h // 2
+            rec(i0, i1, j0, m)
+            rec(i0, i1, m, j1)
+            order.extend(ye(i, m) for i in range(i0, i1))
+
+    rec(0, nx, 0, ny)
+    return np.asarray(order, dtype=np.int64)
+
+
+class _PermutedLU:
+    """splu of P K P^T with the natural column order (no COLAMD), presented like a SuperLU object."""
+
+    def __init__(self, mat, perm):
+        self.perm = perm
+        pm = mat.tocsr()[perm][:, perm].tocsc()
+        self.lu = spla.splu(pm, permc_spec="NATURAL", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
+        self.nnz = self.lu.L.nnz + self.lu.U.nnz
+
+    def solve(self, rhs):
+        out = np.empty_like(rhs)
+        out[self.perm] = self.lu.solve(rhs[self.perm])
+        return out
 
 
 def _side_to_bc(side):

@@ -1,0 +1,96 @@
+"""The product path end to end on a B200: DarcyVT front-end (C++) -> C ABI -> CUDA engine, against the oracle and
+the reference's published tables."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, default_params, mo, pkg, rel_l2
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "report_tables.json")))
+COLS = ["velocity_l2l2", "pressure_dg", "pressure_l2l2", "lambda_l2"]
+
+
+def test_default_parameter_file_matches_oracle_per_cycle():
+    reps, res, lam = pkg().host_run(os.path.join(ROOT, "parameter.txt"), verbose=0, write_output=0, num_refinement=3)
+    prm = default_params(1, 3)
+    ref = mo.run(prm)
+    assert len(reps) == 3
+    for r, o in zip(reps, ref):
+        assert r["gmres_iterations"] == o.gmres_iterations
+        assert r["r_norm"] == pytest.approx(o.r_norm, rel=1e-12)
+        for c in COLS:
+            assert r[c] == pytest.approx(o.errors[c], rel=1e-9), c
+        assert r["factor_groups"] == 3
+    np.testing.assert_allclose(res, ref[-1].residuals, rtol=1e-6, atol=1e-13)
+    assert rel_l2(lam, ref[-1].lam) < 1e-10
+
+
+def test_report_tables_through_the_product_path():
+    """report.pdf Table 2 rows 1-4 and Table 4 row 1, every printed digit, from the CUDA path."""
+    reps, _, _ = pkg().host_run(os.path.join(ROOT, "parameter.txt"), verbose=0, write_output=0, num_refinement=4)
+    for r, row in zip(reps, GOLD["table2_linear_mortar"]["rows"]):
+        for c in COLS:
+            assert float(f"{r[c]:.3e}") == pytest.approx(row[c], rel=1.01e-3)
+        assert abs(r["gmres_iterations"] - row["gmres"]) <= 1
+    reps, _, _ = pkg().host_run(os.path.join(ROOT, "parameter.txt"), verbose=0, write_output=0, num_refinement=1,
+                                mortar_degree=2)
+    row = GOLD["table4_quadratic_mortar"]["rows"][0]
+    for c in COLS:
+        assert float(f"{reps[0][c]:.3e}") == pytest.approx(row[c], rel=1.01e-3)
+    assert abs(reps[0]["gmres_iterations"] - row["gmres"]) <= 1
+
+
+def test_medium_nonmatching_grids_match_oracle(tmp_path):
+    """2x2, ratio-2 non-matching space and time grids (BASELINE configs[1] scaled down): 96^2x24 / 48^2x12."""
+    mesh = [[96, 96, 24], [48, 48, 12], [48, 48, 12], [96, 96, 24]]
+    mortar = [24, 24, 6]
+    p = pkg().write_parameter_file(str(tmp_path / "parameter.txt"), mesh, mortar)
+    reps, res, lam = pkg().host_run(p, verbose=0, write_output=0)
+    prm = mo.parse_parameter_file(p)
+    o = mo.run(prm)[0]
+    r = reps[0]
+    assert abs(r["gmres_iterations"] - o.gmres_iterations) <= 1
+    assert r["r_norm"] == pytest.approx(o.r_norm, rel=1e-11)
+    if r["gmres_iterations"] == o.gmres_iterations:
+        assert rel_l2(lam, o.lam) < 1e-9
+        for c in COLS:
+            assert r[c] == pytest.approx(o.errors[c], rel=1e-8), c
+    assert r["factor_groups"] == 2
+
+
+def test_darcyvt_executable_is_a_drop_in(tmp_path):
+    """Run from a directory holding parameter.txt and the two plot directories, like the reference (README:64)."""
+    exe = os.path.join(ROOT, "DarcyVT")
+    if not os.path.exists(exe):
+        pytest.skip("DarcyVT not built")
+    os.makedirs(tmp_path / "space-time-plots")
+    os.makedirs(tmp_path / "time-step-plots")
+    src = open(os.path.join(ROOT, "parameter.txt")).read().replace("need_plot_at_each_time_step(bool): 0",
+                                                                    "need_plot_at_each_time_step(bool): 1")
+    (tmp_path / "parameter.txt").write_text(src)
+    out = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    for needle in ("Total number of processes is 4", "Starting GMRES iterations", "GMRES converges in 12 iterations!",
+                   "GMRES converges in 24 iterations!", "finished local_gmres", "r_norm is"):
+        assert needle in out.stdout, needle
+    for r in range(4):
+        assert (tmp_path / "space-time-plots" / f"st_solution_d3_p{r:04d}.vtu").exists()
+    assert (tmp_path / "space-time-plots" / "st_solution_d3.pvtu").exists()
+    assert (tmp_path / "time-step-plots" / "solution_d2_p0000-1.vtu").exists()
+    assert (tmp_path / "time-step-plots" / "solution_d2-6.pvtu").exists()
+    tex = (tmp_path / "error4domains.tex").read_text()
+    assert "3.628e-01" in tex and "6.504e-01" in tex
+    vtu = (tmp_path / "space-time-plots" / "st_solution_d3_p0002.vtu").read_text()
+    assert 'Name="u"' in vtu and 'Name="p"' in vtu and 'NumberOfCells="512"' in vtu
+
+
+def test_missing_parameter_file_is_an_error(tmp_path):
+    exe = os.path.join(ROOT, "DarcyVT")
+    if not os.path.exists(exe):
+        pytest.skip("DarcyVT not built")
+    out = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "Exception on processing" in out.stderr

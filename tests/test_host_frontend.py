@@ -1,0 +1,84 @@
+"""CPU checks of the C++ host front-end against the oracle: parameter parsing, matrix assembly, projector
+tables and bar right-hand-side data are identical (no device involved)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import ROOT, bar_data, default_params, make_problem, mo, pkg
+
+
+def _load_csr(d, name):
+    shape = np.fromfile(os.path.join(d, name + ".shape"), dtype=np.int64)
+    rp = np.fromfile(os.path.join(d, name + ".rp"), dtype=np.int64)
+    col = np.fromfile(os.path.join(d, name + ".col"), dtype=np.int32)
+    val = np.fromfile(os.path.join(d, name + ".val"), dtype=np.float64)
+    return sp.csr_matrix((val, col, rp), shape=tuple(shape))
+
+
+def _maxdiff(a, b):
+    d = (a - b).tocoo()
+    return 0.0 if d.nnz == 0 else float(np.abs(d.data).max())
+
+
+@pytest.mark.parametrize("k,cycle", [(1, 0), (1, 1), (2, 0), (2, 2)])
+def test_front_end_setup_matches_oracle(k, cycle):
+    lib = pkg().load_host()
+    prm = default_params(k, cycle + 1)
+    prob = make_problem(prm, cycle)
+    for sd in prob.subs:
+        with tempfile.TemporaryDirectory() as d:
+            rc = lib.mmmfe_host_dump_subdomain(os.path.join(ROOT, "parameter.txt").encode(), cycle, sd.r, k, d.encode())
+            assert rc == 0, lib.mmmfe_host_last_error()
+            assert list(np.fromfile(os.path.join(d, "neighbors"), dtype=np.int32)) == sd.neighbors
+            K = _load_csr(d, "matrix")
+            assert K.shape == sd.matrix.shape
+            assert _maxdiff(K, sd.matrix.tocsr()) < 1e-14 * abs(sd.matrix).max()
+            for side in range(4):
+                if sd.neighbors[side] < 0:
+                    continue
+                f2c, c2f = _load_csr(d, f"f2c{side}"), _load_csr(d, f"c2f{side}")
+                assert _maxdiff(f2c, sd.f2c[side]) < 1e-13 * abs(sd.f2c[side]).max()
+                assert _maxdiff(c2f, sd.c2f[side]) < 1e-13 * abs(sd.c2f[side]).max()
+            p0, src, fr_dofs, fr_vals = bar_data(prob, sd)
+            np.testing.assert_allclose(np.fromfile(os.path.join(d, "p0")), p0, atol=1e-15)
+            np.testing.assert_allclose(np.fromfile(os.path.join(d, "src")).reshape(src.shape), src, rtol=1e-12, atol=1e-16)
+            got_dofs = np.fromfile(os.path.join(d, "fr_dofs"), dtype=np.int32)
+            assert list(got_dofs) == list(fr_dofs)
+            np.testing.assert_allclose(np.fromfile(os.path.join(d, "fr_vals")).reshape(fr_vals.shape), fr_vals,
+                                       rtol=1e-12, atol=1e-16)
+
+
+def test_parameter_file_round_trip(tmp_path):
+    p = pkg().write_parameter_file(str(tmp_path / "parameter.txt"), [[8, 8, 4], [4, 4, 2]], [2, 2, 1], mortar_degree=2,
+                                   num_refinement=3)
+    prm = mo.parse_parameter_file(p)
+    assert prm.mesh == [[8, 8, 4], [4, 4, 2], [2, 2, 1]] and prm.mortar_degree == 2 and prm.num_refinement == 3
+    lib = pkg().load_host()
+    assert lib.mmmfe_host_dump_subdomain(p.encode(), 0, 5, -1, str(tmp_path).encode()) == -1
+    assert b"out of range" in lib.mmmfe_host_last_error()
+
+
+def test_front_end_refuses_to_run_without_a_device(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg().MmmfeError, match="no CPU fallback"):
+        pkg().host_run(os.path.join(ROOT, "parameter.txt"), verbose=0, write_output=0)
+
+
+def test_reference_data_headers_compile_against_the_shim():
+    """inc/data*.h of the reference must build unmodified against host/shim (drop-in surface)."""
+    import glob
+    import subprocess
+    files = sorted(glob.glob("/root/reference/inc/data*.h"))
+    if not files:
+        pytest.skip("/root/reference is not present on this machine")
+    shim = os.path.join(ROOT, "mmmfe-st-dd_b200", "host", "shim")
+    for f in files:
+        src = f'#include "{f}"\nint main(){{ vt_darcy::ExactSolution<2> e; (void)e; return 0; }}\n'
+        r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", shim, "-x", "c++", "-"], input=src, text=True,
+                           capture_output=True)
+        assert r.returncode == 0, (f, r.stderr[:500])
