@@ -239,7 +239,7 @@ def main():
     value = dof_steps / (ms_per_step * 1e-3)
     peak, peak_src = measured_peak_gbs()
     # roofline of the dominant kernel class of one star step (live CUDA-event timing, mmmfe_profile_step)
-    names = ["rhs_build", "forward_small", "forward_large", "backward_large", "backward_small", "update_trace"]
+    names = ["rhs_build", "subtree_forward", "forward_top", "backward_top", "subtree_backward", "update_trace"]
     prof = {n: {"ms": r["prof_ms"][i], "MB": r["prof_bytes"][i] / 1e6, "launches": r["prof_launches"][i],
                 "GBps": (r["prof_bytes"][i] / 1e9) / (r["prof_ms"][i] * 1e-3) if r["prof_ms"][i] > 0 else 0.0}
             for i, n in enumerate(names)}

@@ -79,7 +79,8 @@ const char *mmmfe_version(void);
 
 /* Options (set before mmmfe_setup): "keep_history" (default 1: keep every bar level on the device so that the
  * final sweep can return full solutions), "use_graphs" (default 1: replay each sweep as a CUDA graph),
- * "leaf_cells" (default 4: nested-dissection leaf size).                                                       */
+ * "leaf_cells" (default 4: nested-dissection leaf size), "subtree_cells" (default 256: largest box solved by one CTA
+ * from shared memory; 0 disables the subtree kernels).                                                      */
 int mmmfe_set_option(mmmfe_ctx *ctx, const char *key, double value);
 
 /* ---- multi-GPU: one process per GPU, subdomains sharded over ranks ------------------------------------------ */
@@ -178,8 +179,8 @@ int mmmfe_solve_saddle(mmmfe_ctx *ctx, int32_t local_index, const double *rhs, d
 /* ---- profiling ---------------------------------------------------------------------------------------------------- */
 /* Runs ONE star time step of every batch without graphs, with a CUDA event between kernel classes, and reports
  * per class the device milliseconds, the algorithmic bytes streamed and the number of launches.
- * Classes: 0 rhs build, 1 forward small fronts, 2 forward large fronts, 3 backward large, 4 backward small,
- * 5 pressure update + trace.                                                                                   */
+ * Classes: 0 rhs build, 1 subtree forward (bottom of the tree, one CTA per subtree), 2 forward top levels,
+ * 3 backward top levels, 4 subtree backward, 5 pressure update + trace.                                                                                  */
 #define MMMFE_N_KERNEL_CLASSES 6
 int mmmfe_profile_step(mmmfe_ctx *ctx, double ms[MMMFE_N_KERNEL_CLASSES], double bytes[MMMFE_N_KERNEL_CLASSES],
                        int64_t launches[MMMFE_N_KERNEL_CLASSES]);

@@ -259,7 +259,7 @@ class Engine:
     def profile_step(self):
         ms, by, ln = np.zeros(6), np.zeros(6), np.zeros(6, dtype=np.int64)
         self._check(self.lib.mmmfe_profile_step(self.h, _ptr(ms, c_f64p), _ptr(by, c_f64p), _ptr(ln, c_i64p)))
-        names = ["rhs_build", "forward_small", "forward_large", "backward_large", "backward_small", "update_trace"]
+        names = ["rhs_build", "subtree_forward", "forward_top", "backward_top", "subtree_backward", "update_trace"]
         return {n: dict(ms=float(ms[i]), bytes=float(by[i]), launches=int(ln[i])) for i, n in enumerate(names)}
 
     def debug_get_factor(self, li, r_total):

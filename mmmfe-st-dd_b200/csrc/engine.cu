@@ -162,11 +162,10 @@ struct Sub {
 };
 
 // ---- one factor: nested-dissection tree + block-inverse fronts on the device -------------------------------------
-struct LevelWork {
-  DevBuf<int32_t> small_nodes;
+struct LevelWork {  // one height level of the top of the tree
   DevBuf<WorkItem> fwd, bwd;
-  int32_t n_small = 0, n_fwd = 0, n_bwd = 0;
-  double bytes_fwd_small = 0, bytes_fwd_large = 0, bytes_bwd_small = 0, bytes_bwd_large = 0;
+  int32_t n_fwd = 0, n_bwd = 0;
+  double bytes_fwd = 0, bytes_bwd = 0;
 };
 
 struct Factor {
@@ -176,6 +175,13 @@ struct Factor {
   DevBuf<double> R;
   DevBuf<int32_t> idx_user, src;
   std::vector<LevelWork> levels;
+  // subtrees (bottom of the tree): templates shared by shape, one instance per subtree
+  DevBuf<int32_t> tmpl_pool, dof_of_canon;
+  DevBuf<TemplateDev> tmpl_dev;
+  DevBuf<InstanceDev> inst_dev;
+  int32_t n_inst = 0;
+  size_t smem_fwd[5] = {0, 0, 0, 0, 0}, smem_bwd[5] = {0, 0, 0, 0, 0};  // by M
+  double bytes_sub_fwd = 0, bytes_sub_bwd = 0;
   DevCsr kup, kpu;
   DevBuf<double> minv;
   int64_t solve_bytes = 0;  // factor + index bytes one forward+backward pass streams
@@ -220,7 +226,7 @@ struct mmmfe_ctx {
   int device = 0;
   std::string err;
   bool keep_history = true, use_graphs = true;
-  int leaf_cells = 4;
+  int leaf_cells = 4, subtree_cells = 256;
   bool is_setup = false, bar_done = false, final_done = false;
   int rank = 0, world = 1;
   std::vector<int32_t> owner;
@@ -383,7 +389,7 @@ static void build_schur(const Sub &sd, HostCsr &S, HostCsr &kup, HostCsr &kpu, s
   }
 }
 
-static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd) {
+static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax) {
   const auto t0 = std::chrono::steady_clock::now();
   auto F = std::make_shared<Factor>();
   F->nx = sd.nx; F->ny = sd.ny; F->nf = sd.nf; F->np = sd.np;
@@ -392,7 +398,17 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd) {
   build_schur(sd, S, kup, kpu, minv);
   F->kup.upload(kup); F->kpu.upload(kpu); F->minv.upload(minv);
   NdTree &tr = F->tree;
-  tr.build(sd.nx, sd.ny, c->leaf_cells);
+  const size_t smem_limit = subtree_smem_limit();
+  for (int cells = c->subtree_cells;; cells /= 2) {  // largest subtrees whose factor blob + vectors fit on chip twice per SM
+    tr.build(sd.nx, sd.ny, c->leaf_cells, cells);
+    for (int M = 1; M <= 4; M *= 2) F->smem_fwd[M] = F->smem_bwd[M] = 0;
+    for (const auto &T : tr.templates)
+      for (int M = 1; M <= 4; M *= 2) {
+        F->smem_fwd[M] = std::max(F->smem_fwd[M], 16 + 8 * (size_t(T.rf_size) + size_t(T.zl_size) * M + size_t(T.n_int) * M));
+        F->smem_bwd[M] = std::max(F->smem_bwd[M], 16 + 8 * (size_t(T.rb_size) + size_t(2 * T.n_int + T.n_rootb) * M));
+      }
+    if (cells == 0 || (F->smem_fwd[Mmax] <= smem_limit / 2 && F->smem_bwd[Mmax] <= smem_limit / 2)) break;
+  }
   if (tr.n_flux != sd.nf) fail(MMMFE_E_INVALID, "n_flux %d does not match an RT0 grid %dx%d", sd.nf, sd.nx, sd.ny);
   const int32_t nn = int32_t(tr.nodes.size());
   // user numbering of the front variables
@@ -411,7 +427,7 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd) {
   std::vector<int64_t> f_off(nn);
   for (int32_t i = 0; i < nn; ++i) {
     const NdNode &n = tr.nodes[i];
-    fd[i] = {n.s, n.b, n.ldr, n.nsplit, n.child[0], n.child[1], n.r_off, n.idx_off, n.src_off, n.z_off};
+    fd[i] = {n.s, n.b, n.ldr, n.ldf, n.nsplit, n.child[0], n.child[1], n.rb_off, n.rf_off, n.idx_off, n.src_off, n.z_off};
     f_off[i] = n.f_off;
   }
   F->fronts.upload(fd);
@@ -419,6 +435,45 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd) {
   F->src.upload(tr.src);
   F->R.alloc(size_t(tr.r_total));
   F->R.zero(c->stream);
+  if (!dof_of_canon.empty()) F->dof_of_canon.upload(dof_of_canon);
+  {  // subtree templates: one int32 pool, pointers patched on the host
+    std::vector<int32_t> pool;
+    std::vector<std::vector<size_t>> offs;
+    for (const auto &T : tr.templates) {
+      std::vector<size_t> o;
+      for (const std::vector<int32_t> *v : {&T.node_s, &T.node_b, &T.node_rf, &T.node_rb, &T.node_sep, &T.node_bnd, &T.node_zl,
+                                            &T.var_code, &T.rootb_code, &T.sep_node, &T.sep_c0, &T.sep_c1, &T.out_node,
+                                            &T.out_c0, &T.out_c1, &T.bnd_var, &T.lvl_sep, &T.lvl_out}) {
+        o.push_back(pool.size());
+        pool.insert(pool.end(), v->begin(), v->end());
+      }
+      offs.push_back(o);
+    }
+    pool.push_back(0);
+    F->tmpl_pool.upload(pool);
+    std::vector<TemplateDev> td;
+    for (size_t t = 0; t < tr.templates.size(); ++t) {
+      const auto &T = tr.templates[t];
+      const int32_t *b = F->tmpl_pool.p;
+      const auto &o = offs[t];
+      td.push_back({T.n_nodes, T.n_levels, T.n_int, T.n_rootb, T.zl_size, T.rf_size, T.rb_size, b + o[0], b + o[1], b + o[2],
+                    b + o[3], b + o[4], b + o[5], b + o[6], b + o[7], b + o[8], b + o[9], b + o[10], b + o[11], b + o[12],
+                    b + o[13], b + o[14], b + o[15], b + o[16], b + o[17]});
+    }
+    td.push_back(TemplateDev{});
+    F->tmpl_dev.upload(td);
+    std::vector<InstanceDev> id;
+    for (const auto &in : tr.instances) {
+      const NdNode &root = tr.nodes[in.root];
+      const auto &T = tr.templates[in.tmpl];
+      id.push_back({in.tmpl, in.I0, in.J0, 0, in.rf_base, in.rb_base, root.z_off + root.s});
+      F->bytes_sub_fwd += 8.0 * T.rf_size;
+      F->bytes_sub_bwd += 8.0 * T.rb_size;
+    }
+    F->n_inst = int32_t(id.size());
+    id.push_back(InstanceDev{});
+    F->inst_dev.upload(id);
+  }
 
   // ---- numeric phase ----
   DevCsr dS;
@@ -460,55 +515,61 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd) {
       inv.push_back({W.p + n.f_off, n.s, n.s + n.b});
     }
     chol_inv_batch(c, inv, arena);  // F11 block now holds Li = L^-1
-    std::vector<GemmProb> gW, gU, gX, gG;
+    std::vector<GemmProb> gW, gU, gX, gG, gF;
     for (int32_t id : lvl) {
       const NdNode &n = tr.nodes[id];
       const int s = n.s, b = n.b, f = s + b;
       double *Fp = W.p + n.f_off;
-      double *Rp = F->R.p + n.r_off;
-      gX.push_back({Fp, Fp, Rp, s, s, s, n.ldr, 1, f, f, 1, 1.0, 0.0});  // F11^-1 = Li^T Li -> R[:, :s]
+      double *Rb = F->R.p + n.rb_off, *Rf = F->R.p + n.rf_off;
+      const bool sub = n.subtree >= 0;
+      // F11^-1 = Li^T Li: rows of R (top node, stride ldr) or the first s rows of R^T (subtree node, stride s)
+      gX.push_back({Fp, Fp, Rb, s, s, s, sub ? s : n.ldr, 1, f, f, 1, 1.0, 0.0});
       if (b == 0) continue;
       double *Wt = arena.take(size_t(b) * s);
       double *F21 = Fp + int64_t(s) * f, *F22 = F21 + s;
       gW.push_back({F21, Fp, Wt, b, s, s, s, f, 1, 1, f, 1.0, 0.0});          // Wt = F21 Li^T        (b x s)
       gU.push_back({Wt, Wt, F22, b, b, s, f, s, 1, 1, s, -1.0, 1.0});         // U  = F22 - Wt Wt^T
-      gG.push_back({Fp, Wt, Rp + s, s, b, s, n.ldr, 1, f, 1, s, -1.0, 0.0});  // R[:, s:] = -(Wt Li)^T = -Li^T Wt^T
+      // -G^T = -Li^T Wt^T (s x b): forward copy, and the right part of R for top nodes
+      gF.push_back({Fp, Wt, Rf, s, b, s, n.ldf, 1, f, 1, s, -1.0, 0.0});
+      if (sub) gG.push_back({Wt, Fp, Rb + int64_t(s) * s, b, s, s, s, s, 1, f, 1, -1.0, 0.0});  // rows s.. of R^T = -G = -Wt Li
+      else gG.push_back({Fp, Wt, Rb + s, s, b, s, n.ldr, 1, f, 1, s, -1.0, 0.0});
     }
     run_gemm_batch(c, gW);
     run_gemm_batch(c, gU);
     run_gemm_batch(c, gX);
     run_gemm_batch(c, gG);
+    run_gemm_batch(c, gF);
   }
   int32_t failed = 0;
   CUDA_CHECK(cudaMemcpy(&failed, c->d_fail.p, sizeof(int32_t), cudaMemcpyDeviceToHost));
   if (failed) fail(MMMFE_E_NUMERIC, "non-positive pivot in a front: the flux Schur complement is not SPD");
 
-  // ---- work lists of the solve ----
-  F->levels.resize(tr.by_height.size());
+  // ---- work lists of the solve (top of the tree only; subtrees are one CTA each) ----
   int64_t bytes = 0;
-  for (size_t h = 0; h < tr.by_height.size(); ++h) {
-    std::vector<int32_t> small;
+  for (const auto &n : tr.nodes) bytes += 8 * (int64_t(n.s) * n.b + int64_t(n.s) * (n.s + n.b));
+  for (size_t h = 0; h < tr.top_by_height.size(); ++h) {
+    if (tr.top_by_height[h].empty()) continue;
+    F->levels.emplace_back();
+    LevelWork &lw = F->levels.back();
     std::vector<WorkItem> fwd, bwd;
-    for (int32_t id : tr.by_height[h]) {
+    for (int32_t id : tr.top_by_height[h]) {
       const NdNode &n = tr.nodes[id];
       const int64_t f = n.s + n.b;
-      bytes += 8 * (int64_t(n.s) * n.b + int64_t(n.s) * f) + 4 * (2 * f + 2 * f);
-      LevelWork &lwb = F->levels[h];
-      const bool is_small = n.s <= 32 && n.b <= 64;
-      (is_small ? lwb.bytes_fwd_small : lwb.bytes_fwd_large) += 8.0 * n.s * n.b + 4.0 * 3 * f;
-      (is_small ? lwb.bytes_bwd_small : lwb.bytes_bwd_large) += 8.0 * n.s * f + 4.0 * f;
-      if (is_small) { small.push_back(id); continue; }
-      const int rows_per = (n.s + n.nsplit - 1) / n.nsplit;
+      bytes += 4 * (2 * f + 2 * f);
+      lw.bytes_fwd += 8.0 * n.s * n.b + 4.0 * 3 * f;
+      lw.bytes_bwd += 8.0 * n.s * f + 4.0 * f;
+      const int rows_per = (n.s + n.nsplit - 1) / n.nsplit;  // <= 32
       for (int sp = 0; sp < n.nsplit; ++sp) {
         const int r0 = sp * rows_per, r1 = std::min(n.s, r0 + rows_per);
         if (n.b == 0) fwd.push_back({id, r0, r1, 0, 0, sp});
         for (int c0 = 0; c0 < n.b; c0 += 256) fwd.push_back({id, r0, r1, c0, std::min(n.b, c0 + 256), sp});
       }
-      for (int r0 = 0; r0 < n.s; r0 += 32) bwd.push_back({id, r0, std::min(n.s, r0 + 32), 0, 0, 0});
+      // ~64 KB of R per backward item: 8..32 rows (1..4 per warp)
+      const int rows_b = int(std::min<int64_t>(32, std::max<int64_t>(8, (65536 / (8 * f)) / 8 * 8)));
+      for (int r0 = 0; r0 < n.s; r0 += rows_b) bwd.push_back({id, r0, std::min(n.s, r0 + rows_b), 0, 0, 0});
     }
-    LevelWork &lw = F->levels[h];
-    lw.n_small = int32_t(small.size()); lw.n_fwd = int32_t(fwd.size()); lw.n_bwd = int32_t(bwd.size());
-    lw.small_nodes.upload(small); lw.fwd.upload(fwd); lw.bwd.upload(bwd);
+    lw.n_fwd = int32_t(fwd.size()); lw.n_bwd = int32_t(bwd.size());
+    lw.fwd.upload(fwd); lw.bwd.upload(bwd);
   }
   F->solve_bytes = bytes;
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -516,19 +577,17 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd) {
   return F;
 }
 
+static SubtreeArgs subtree_args(const Factor &F, double *x, double *z) {
+  return SubtreeArgs{F.tmpl_dev.p, F.inst_dev.p, F.R.p, x, z, F.dof_of_canon.p, F.nx, int64_t(F.nx + 1) * F.ny};
+}
+
 static void run_solve(const Factor &F, int M, double *x, double *z, cudaStream_t st) {
   SolveArgs a{F.fronts.p, F.R.p, F.idx_user.p, F.src.p, z, x};
-  const int H = int(F.levels.size());
-  for (int h = 0; h < H; ++h) {
-    const LevelWork &lw = F.levels[h];
-    launch_forward_small(M, a, lw.small_nodes.p, lw.n_small, st);
-    launch_forward_large(M, a, lw.fwd.p, lw.n_fwd, st);
-  }
-  for (int h = H - 1; h >= 0; --h) {
-    const LevelWork &lw = F.levels[h];
-    launch_backward_large(M, a, lw.bwd.p, lw.n_bwd, st);
-    launch_backward_small(M, a, lw.small_nodes.p, lw.n_small, st);
-  }
+  const SubtreeArgs sa = subtree_args(F, x, z);
+  launch_subtree_forward(M, sa, F.n_inst, F.smem_fwd[M], st);
+  for (const LevelWork &lw : F.levels) launch_forward_large(M, a, lw.fwd.p, lw.n_fwd, st);
+  for (auto it = F.levels.rbegin(); it != F.levels.rend(); ++it) launch_backward_large(M, a, it->bwd.p, it->n_bwd, st);
+  launch_subtree_backward(M, sa, F.n_inst, F.smem_bwd[M], st);
 }
 
 // =================================================================================================================
@@ -644,8 +703,10 @@ static void setup(mmmfe_ctx *c) {
       if (same_matrix(*c->subs[reps[g]], *c->subs[i])) { group_of[i] = int(g); break; }
     if (group_of[i] < 0) { group_of[i] = int(reps.size()); reps.push_back(i); }
   }
-  for (int rep : reps) {
-    c->factors.push_back(factorize(c, *c->subs[rep]));
+  for (size_t g = 0; g < reps.size(); ++g) {
+    int cnt = 0;
+    for (int i = 0; i < ns; ++i) cnt += group_of[i] == int(g);
+    c->factors.push_back(factorize(c, *c->subs[reps[g]], cnt <= 1 ? 1 : (cnt == 2 ? 2 : 4)));
     c->factor_seconds += c->factors.back()->seconds;
   }
   // ---- interface and fine-trace layouts ----
@@ -943,6 +1004,7 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   if (k == "keep_history") c->keep_history = value != 0;
   else if (k == "use_graphs") c->use_graphs = value != 0;
   else if (k == "leaf_cells") c->leaf_cells = std::max(1, int(value));
+  else if (k == "subtree_cells") c->subtree_cells = std::max(0, int(value));
   else { c->err = "unknown option " + k; return MMMFE_E_INVALID; }
   return MMMFE_OK;
 }
@@ -1230,17 +1292,13 @@ int mmmfe_profile_step(mmmfe_ctx *c, double ms[MMMFE_N_KERNEL_CLASSES], double b
       mark(-1);
       launch_build_rhs(b.step, c->lam_bar.p, 0, st);
       mark(0); bytes[0] += vec * (F.nf + 2.0 * F.nf) + 12.0 * 2 * F.nf; launches[0] += 1;
-      const int H = int(F.levels.size());
-      for (int h = 0; h < H; ++h) {
-        const LevelWork &lw = F.levels[h];
-        if (lw.n_small) { launch_forward_small(M, a, lw.small_nodes.p, lw.n_small, st); mark(1); bytes[1] += lw.bytes_fwd_small; launches[1] += 1; }
-        if (lw.n_fwd) { launch_forward_large(M, a, lw.fwd.p, lw.n_fwd, st); mark(2); bytes[2] += lw.bytes_fwd_large; launches[2] += 1; }
-      }
-      for (int h = H - 1; h >= 0; --h) {
-        const LevelWork &lw = F.levels[h];
-        if (lw.n_bwd) { launch_backward_large(M, a, lw.bwd.p, lw.n_bwd, st); mark(3); bytes[3] += lw.bytes_bwd_large; launches[3] += 1; }
-        if (lw.n_small) { launch_backward_small(M, a, lw.small_nodes.p, lw.n_small, st); mark(4); bytes[4] += lw.bytes_bwd_small; launches[4] += 1; }
-      }
+      const SubtreeArgs sa = subtree_args(F, b.x.p, b.z.p);
+      if (F.n_inst) { launch_subtree_forward(M, sa, F.n_inst, F.smem_fwd[M], st); mark(1); bytes[1] += F.bytes_sub_fwd + vec * F.nf; launches[1] += 1; }
+      for (const LevelWork &lw : F.levels)
+        if (lw.n_fwd) { launch_forward_large(M, a, lw.fwd.p, lw.n_fwd, st); mark(2); bytes[2] += lw.bytes_fwd; launches[2] += 1; }
+      for (auto it = F.levels.rbegin(); it != F.levels.rend(); ++it)
+        if (it->n_bwd) { launch_backward_large(M, a, it->bwd.p, it->n_bwd, st); mark(3); bytes[3] += it->bytes_bwd; launches[3] += 1; }
+      if (F.n_inst) { launch_subtree_backward(M, sa, F.n_inst, F.smem_bwd[M], st); mark(4); bytes[4] += F.bytes_sub_bwd + 2 * vec * F.nf; launches[4] += 1; }
       launch_update(b.step, c->trace.p, 0, nullptr, F.np, nullptr, int64_t(F.nf) + F.np, 0, st);
       mark(5); bytes[5] += vec * (4.0 * F.np + 2.0 * F.np) + 12.0 * 4 * F.np; launches[5] += 1;
     }

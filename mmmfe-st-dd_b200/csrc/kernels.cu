@@ -257,7 +257,7 @@ void launch_extend_add(const int32_t *d_nodes, int32_t n_nodes, const FrontDesc 
 }
 
 // =================================================================================================================
-// multifrontal solve
+// multifrontal solve, top of the tree: one launch per level and direction
 // =================================================================================================================
 template <int M>
 __device__ __forceinline__ void gather_children(const SolveArgs &a, const FrontDesc &fd, int32_t f, int32_t p,
@@ -276,8 +276,9 @@ __device__ __forceinline__ void gather_children(const SolveArgs &a, const FrontD
   }
 }
 
-constexpr int FWD_ROWS = 128;  // rows of R per forward item (== NdNode::nsplit granularity)
+constexpr int FWD_ROWS = 32;  // rows of -G^T per forward item (== NdNode::nsplit granularity)
 
+// item = rows [r0,r1) x boundary columns [c0,c1) of one front: partial contribution `split`
 template <int M>
 __global__ void __launch_bounds__(256) k_forward_large(SolveArgs a, const WorkItem *__restrict__ items) {
   __shared__ double vs[FWD_ROWS * M];
@@ -287,15 +288,15 @@ __global__ void __launch_bounds__(256) k_forward_large(SolveArgs a, const WorkIt
   const int32_t s = fd.s, f = fd.s + fd.b;
   const int tid = threadIdx.x;
   const int nr = it.r1 - it.r0;
-  for (int t = tid; t < nr; t += 256) {
-    const int32_t p = it.r0 + t;
+  if (tid < nr) {
+    const int32_t p = it.r0 + tid;
     double val[M];
     const int64_t d = a.idx[fd.idx_off + p];
 #pragma unroll
     for (int j = 0; j < M; ++j) val[j] = a.x[d * M + j];
     gather_children<M>(a, fd, f, p, val);
 #pragma unroll
-    for (int j = 0; j < M; ++j) vs[t * M + j] = val[j];
+    for (int j = 0; j < M; ++j) vs[tid * M + j] = val[j];
     if (it.c0 == 0)
 #pragma unroll
       for (int j = 0; j < M; ++j) a.z[(fd.z_off + p) * M + j] = val[j];
@@ -311,71 +312,42 @@ __global__ void __launch_bounds__(256) k_forward_large(SolveArgs a, const WorkIt
 #pragma unroll
   for (int j = 0; j < M; ++j) acc[j] = 0.0;
   if (cid < nc) {
-    const double *Rc = a.R + fd.r_off + int64_t(it.r0) * fd.ldr + s + it.c0 + cid;
-    for (int i = rgid; i < nr; i += rg) {
-      const double r = __ldg(Rc + int64_t(i) * fd.ldr);
+    const double *Rc = a.R + fd.rf_off + int64_t(it.r0) * fd.ldf + it.c0 + cid;
+    int i = rgid;
+    for (; i + 3 * rg < nr; i += 4 * rg) {  // four independent loads in flight per thread
+      const double r0 = __ldg(Rc + int64_t(i) * fd.ldf), r1 = __ldg(Rc + int64_t(i + rg) * fd.ldf);
+      const double r2 = __ldg(Rc + int64_t(i + 2 * rg) * fd.ldf), r3 = __ldg(Rc + int64_t(i + 3 * rg) * fd.ldf);
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+        acc[j] += r0 * vs[i * M + j] + r1 * vs[(i + rg) * M + j] + r2 * vs[(i + 2 * rg) * M + j] +
+                  r3 * vs[(i + 3 * rg) * M + j];
+    }
+    for (; i < nr; i += rg) {
+      const double r = __ldg(Rc + int64_t(i) * fd.ldf);
 #pragma unroll
       for (int j = 0; j < M; ++j) acc[j] += r * vs[i * M + j];
     }
   }
+  if (rg > 1) {
 #pragma unroll
-  for (int j = 0; j < M; ++j) red[tid * M + j] = acc[j];
-  __syncthreads();
+    for (int j = 0; j < M; ++j) red[tid * M + j] = acc[j];
+    __syncthreads();
+    if (rgid == 0 && cid < nc)
+      for (int g = 1; g < rg; ++g)
+#pragma unroll
+        for (int j = 0; j < M; ++j) acc[j] += red[(g * cw + cid) * M + j];
+  }
   if (rgid == 0 && cid < nc) {
-    double tot[M];
-#pragma unroll
-    for (int j = 0; j < M; ++j) tot[j] = 0.0;
-    for (int g = 0; g < rg; ++g)
-#pragma unroll
-      for (int j = 0; j < M; ++j) tot[j] += red[(g * cw + cid) * M + j];
     const int32_t q = it.c0 + cid;
-    if (it.split == 0) gather_children<M>(a, fd, f, s + q, tot);
+    if (it.split == 0) gather_children<M>(a, fd, f, s + q, acc);
 #pragma unroll
-    for (int j = 0; j < M; ++j) a.z[(fd.z_off + s + int64_t(it.split) * fd.b + q) * M + j] = tot[j];
-  }
-}
-
-// fronts with s <= 32 and b <= 64: one warp per front
-template <int M>
-__global__ void __launch_bounds__(256) k_forward_small(SolveArgs a, const int32_t *__restrict__ nodes,
-                                                       int32_t n_nodes) {
-  __shared__ double vs[8][32 * M];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int w = blockIdx.x * 8 + warp;
-  if (w >= n_nodes) return;
-  const FrontDesc fd = a.fronts[nodes[w]];
-  const int32_t s = fd.s, f = fd.s + fd.b;
-  if (lane < s) {
-    double val[M];
-    const int64_t d = a.idx[fd.idx_off + lane];
-#pragma unroll
-    for (int j = 0; j < M; ++j) val[j] = a.x[d * M + j];
-    gather_children<M>(a, fd, f, lane, val);
-#pragma unroll
-    for (int j = 0; j < M; ++j) {
-      vs[warp][lane * M + j] = val[j];
-      a.z[(fd.z_off + lane) * M + j] = val[j];
-    }
-  }
-  __syncwarp();
-  for (int q = lane; q < fd.b; q += 32) {
-    double acc[M];
-#pragma unroll
-    for (int j = 0; j < M; ++j) acc[j] = 0.0;
-    gather_children<M>(a, fd, f, s + q, acc);
-    const double *Rc = a.R + fd.r_off + s + q;
-    for (int i = 0; i < s; ++i) {
-      const double r = __ldg(Rc + int64_t(i) * fd.ldr);
-#pragma unroll
-      for (int j = 0; j < M; ++j) acc[j] += r * vs[warp][i * M + j];
-    }
-#pragma unroll
-    for (int j = 0; j < M; ++j) a.z[(fd.z_off + s + q) * M + j] = acc[j];
+    for (int j = 0; j < M; ++j) a.z[(fd.z_off + s + int64_t(it.split) * fd.b + q) * M + j] = acc[j];
   }
 }
 
 constexpr int BWD_CHUNK = 512;
 
+// item = rows [r0,r1) of R = [F11^-1 | -G^T] (at most 32 rows, 4 per warp)
 template <int M>
 __global__ void __launch_bounds__(256) k_backward_large(SolveArgs a, const WorkItem *__restrict__ items) {
   __shared__ double ws[BWD_CHUNK * M];
@@ -383,13 +355,15 @@ __global__ void __launch_bounds__(256) k_backward_large(SolveArgs a, const WorkI
   const FrontDesc fd = a.fronts[it.node];
   const int32_t s = fd.s, f = fd.s + fd.b;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rbase = it.r0 + warp * 4;
+  const int nrow = it.r1 - it.r0;
+  const int per_warp = (nrow + 7) / 8;  // 1..4
+  const int rbase = it.r0 + warp * per_warp;
   double acc[4][M];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int j = 0; j < M; ++j) acc[r][j] = 0.0;
-  const double *Rr = a.R + fd.r_off + int64_t(rbase) * fd.ldr;
+  const double *Rr = a.R + fd.rb_off + int64_t(rbase) * fd.ldr;
   for (int pc = 0; pc < f; pc += BWD_CHUNK) {
     const int chunk = min(BWD_CHUNK, f - pc);
     for (int t = tid; t < chunk; t += 256) {
@@ -410,7 +384,7 @@ __global__ void __launch_bounds__(256) k_backward_large(SolveArgs a, const WorkI
       for (int j = 0; j < M; ++j) wv[j] = ws[t * M + j];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
-        if (rbase + r < it.r1) {
+        if (r < per_warp && rbase + r < it.r1) {
           const double rv = __ldg(Rr + int64_t(r) * fd.ldr + pc + t);
 #pragma unroll
           for (int j = 0; j < M; ++j) acc[r][j] += rv * wv[j];
@@ -430,55 +404,184 @@ __global__ void __launch_bounds__(256) k_backward_large(SolveArgs a, const WorkI
   if (lane == 0)
 #pragma unroll
     for (int r = 0; r < 4; ++r)
-      if (rbase + r < it.r1) {
+      if (r < per_warp && rbase + r < it.r1) {
         const int64_t d = a.idx[fd.idx_off + rbase + r];
 #pragma unroll
         for (int j = 0; j < M; ++j) a.x[d * M + j] = acc[r][j];
       }
 }
 
-template <int M>
-__global__ void __launch_bounds__(256) k_backward_small(SolveArgs a, const int32_t *__restrict__ nodes,
-                                                        int32_t n_nodes) {
-  __shared__ double ws[8][96 * M];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int w = blockIdx.x * 8 + warp;
-  if (w >= n_nodes) return;
-  const FrontDesc fd = a.fronts[nodes[w]];
-  const int32_t s = fd.s, f = fd.s + fd.b;
-  for (int p = lane; p < f; p += 32) {
-    if (p < s) {
-#pragma unroll
-      for (int j = 0; j < M; ++j) ws[warp][p * M + j] = a.z[(fd.z_off + p) * M + j];
-    } else {
-      const int64_t d = a.idx[fd.idx_off + p];
-#pragma unroll
-      for (int j = 0; j < M; ++j) ws[warp][p * M + j] = a.x[d * M + j];
-    }
+// =================================================================================================================
+// multifrontal solve, bottom of the tree: one CTA per subtree.  The subtree's factor blob is contiguous in HBM and
+// is staged into shared memory by one TMA bulk copy (cp.async.bulk + mbarrier); all index structure comes from
+// the shared template, so HBM traffic is the factor, the right-hand side and the solution.
+// =================================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void bulk_load_start(double *dst, const double *src, uint32_t bytes, uint64_t *bar) {
+  // one thread: arm the barrier with the byte count, then issue the bulk copies (<= 64 KB each)
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  uint32_t done = 0;
+  while (done < bytes) {
+    const uint32_t n = min(bytes - done, 65536u);
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+            smem_u32(reinterpret_cast<char *>(dst) + done)),
+        "l"(reinterpret_cast<const char *>(src) + done), "r"(n), "r"(smem_u32(bar))
+        : "memory");
+    done += n;
   }
-  __syncwarp();
-  for (int i = 0; i < s; ++i) {
-    double acc[M];
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ int64_t subtree_dof(const SubtreeArgs &a, const InstanceDev &in, int32_t code) {
+  const int type = code >> 30, dj = (code >> 15) & 0x7fff, di = code & 0x7fff;
+  const int64_t canon = type == 0 ? int64_t(in.J0 + dj) * (a.nx + 1) + in.I0 + di
+                                  : a.nxe + int64_t(in.J0 + dj) * a.nx + in.I0 + di;
+  return a.dof_of_canon ? int64_t(a.dof_of_canon[canon]) : canon;
+}
+
+template <int M>
+__global__ void __launch_bounds__(256) k_subtree_forward(SubtreeArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const InstanceDev in = a.inst[blockIdx.x];
+  const TemplateDev T = a.tmpl[in.tmpl];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(sm);
+  double *blob = sm + 2;
+  double *zl = blob + T.rf_size;
+  double *vs = zl + int64_t(T.zl_size) * M;
+  const int tid = threadIdx.x;
+  if (tid == 0) mbar_init(bar);
+  __syncthreads();
+  if (tid == 0 && T.rf_size > 0) bulk_load_start(blob, a.R + in.rf_base, uint32_t(T.rf_size) * 8u, bar);
+  for (int l = tid; l < T.n_int; l += 256) {
+    const int64_t d = subtree_dof(a, in, T.var_code[l]);
 #pragma unroll
-    for (int j = 0; j < M; ++j) acc[j] = 0.0;
-    const double *Rr = a.R + fd.r_off + int64_t(i) * fd.ldr;
-    for (int p = lane; p < f; p += 32) {
-      const double rv = __ldg(Rr + p);
+    for (int j = 0; j < M; ++j) vs[l * M + j] = a.x[d * M + j];
+  }
+  __syncthreads();
+  if (T.rf_size > 0) mbar_wait(bar, 0);
+  for (int lv = 0; lv < T.n_levels; ++lv) {
+    if (lv > 0) {  // leaves have no children
+      for (int e = T.lvl_sep[lv] + tid; e < T.lvl_sep[lv + 1]; e += 256) {
+        const int32_t c0 = T.sep_c0[e], c1 = T.sep_c1[e];
 #pragma unroll
-      for (int j = 0; j < M; ++j) acc[j] += rv * ws[warp][p * M + j];
+        for (int j = 0; j < M; ++j) {
+          double v = vs[e * M + j];
+          if (c0 >= 0) v += zl[c0 * M + j];
+          if (c1 >= 0) v += zl[c1 * M + j];
+          vs[e * M + j] = v;
+        }
+      }
+      __syncthreads();
     }
+    for (int e = T.lvl_out[lv] + tid; e < T.lvl_out[lv + 1]; e += 256) {
+      const int32_t n = T.out_node[e];
+      const int32_t s = T.node_s[n], b = T.node_b[n];
+      const double *rf = blob + T.node_rf[n] + (e - T.node_zl[n]);
+      const double *v = vs + int64_t(T.node_sep[n]) * M;
+      double acc[M];
+      const int32_t c0 = T.out_c0[e], c1 = T.out_c1[e];
 #pragma unroll
-    for (int j = 0; j < M; ++j) {
-      double v = acc[j];
+      for (int j = 0; j < M; ++j) {
+        acc[j] = 0.0;
+        if (c0 >= 0) acc[j] += zl[c0 * M + j];
+        if (c1 >= 0) acc[j] += zl[c1 * M + j];
+      }
+      for (int i = 0; i < s; ++i) {
+        const double r = rf[i * b];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      acc[j] = v;
+        for (int j = 0; j < M; ++j) acc[j] += r * v[i * M + j];
+      }
+#pragma unroll
+      for (int j = 0; j < M; ++j) zl[e * M + j] = acc[j];
     }
-    if (lane == 0) {
-      const int64_t d = a.idx[fd.idx_off + i];
+    __syncthreads();
+  }
+  for (int l = tid; l < T.n_int; l += 256) {
+    const int64_t d = subtree_dof(a, in, T.var_code[l]);
 #pragma unroll
-      for (int j = 0; j < M; ++j) a.x[d * M + j] = acc[j];
+    for (int j = 0; j < M; ++j) a.x[d * M + j] = vs[l * M + j];
+  }
+  const int32_t zr = T.node_zl[T.n_nodes - 1];
+  for (int q = tid; q < T.n_rootb; q += 256)
+#pragma unroll
+    for (int j = 0; j < M; ++j) a.z[(in.z_root + q) * M + j] = zl[(zr + q) * M + j];
+}
+
+template <int M>
+__global__ void __launch_bounds__(256) k_subtree_backward(SubtreeArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  const InstanceDev in = a.inst[blockIdx.x];
+  const TemplateDev T = a.tmpl[in.tmpl];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(sm);
+  double *blob = sm + 2;
+  double *zs = blob + T.rb_size;             // accumulated right-hand sides of the interior variables
+  double *xs = zs + int64_t(T.n_int) * M;    // solution: [interior | root boundary]
+  const int tid = threadIdx.x;
+  if (tid == 0) mbar_init(bar);
+  __syncthreads();
+  if (tid == 0) bulk_load_start(blob, a.R + in.rb_base, uint32_t(T.rb_size) * 8u, bar);
+  for (int l = tid; l < T.n_int; l += 256) {
+    const int64_t d = subtree_dof(a, in, T.var_code[l]);
+#pragma unroll
+    for (int j = 0; j < M; ++j) zs[l * M + j] = a.x[d * M + j];
+  }
+  for (int q = tid; q < T.n_rootb; q += 256) {
+    const int64_t d = subtree_dof(a, in, T.rootb_code[q]);
+#pragma unroll
+    for (int j = 0; j < M; ++j) xs[(T.n_int + q) * M + j] = a.x[d * M + j];
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+  for (int lv = T.n_levels - 1; lv >= 0; --lv) {
+    for (int e = T.lvl_sep[lv] + tid; e < T.lvl_sep[lv + 1]; e += 256) {
+      const int32_t n = T.sep_node[e];
+      const int32_t s = T.node_s[n], b = T.node_b[n], sep0 = T.node_sep[n];
+      const double *rb = blob + T.node_rb[n] + (e - sep0);  // R^T[p][i] at p * s + i
+      const int32_t *bv = T.bnd_var + T.node_bnd[n];
+      double acc[M];
+#pragma unroll
+      for (int j = 0; j < M; ++j) acc[j] = 0.0;
+      for (int p = 0; p < s; ++p) {
+        const double r = rb[p * s];
+#pragma unroll
+        for (int j = 0; j < M; ++j) acc[j] += r * zs[(sep0 + p) * M + j];
+      }
+      rb += s * s;
+      for (int q = 0; q < b; ++q) {
+        const double r = rb[q * s];
+        const int32_t l = bv[q];
+#pragma unroll
+        for (int j = 0; j < M; ++j) acc[j] += r * xs[l * M + j];
+      }
+#pragma unroll
+      for (int j = 0; j < M; ++j) xs[e * M + j] = acc[j];
     }
+    __syncthreads();
+  }
+  for (int l = tid; l < T.n_int; l += 256) {
+    const int64_t d = subtree_dof(a, in, T.var_code[l]);
+#pragma unroll
+    for (int j = 0; j < M; ++j) a.x[d * M + j] = xs[l * M + j];
   }
 }
 
@@ -495,19 +598,34 @@ void launch_forward_large(int M, const SolveArgs &a, const WorkItem *items, int3
   MMMFE_DISPATCH_M(M, (k_forward_large<MM><<<n_items, 256, 0, st>>>(a, items)));
   launch_counter_add(1);
 }
-void launch_forward_small(int M, const SolveArgs &a, const int32_t *nodes, int32_t n_nodes, cudaStream_t st) {
-  if (n_nodes <= 0) return;
-  MMMFE_DISPATCH_M(M, (k_forward_small<MM><<<(n_nodes + 7) / 8, 256, 0, st>>>(a, nodes, n_nodes)));
-  launch_counter_add(1);
-}
 void launch_backward_large(int M, const SolveArgs &a, const WorkItem *items, int32_t n_items, cudaStream_t st) {
   if (n_items <= 0) return;
   MMMFE_DISPATCH_M(M, (k_backward_large<MM><<<n_items, 256, 0, st>>>(a, items)));
   launch_counter_add(1);
 }
-void launch_backward_small(int M, const SolveArgs &a, const int32_t *nodes, int32_t n_nodes, cudaStream_t st) {
-  if (n_nodes <= 0) return;
-  MMMFE_DISPATCH_M(M, (k_backward_small<MM><<<(n_nodes + 7) / 8, 256, 0, st>>>(a, nodes, n_nodes)));
+
+size_t subtree_smem_limit() {
+  int dev = 0, optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const size_t lim = size_t(optin);
+  cudaFuncSetAttribute(k_subtree_forward<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lim));
+  cudaFuncSetAttribute(k_subtree_forward<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lim));
+  cudaFuncSetAttribute(k_subtree_forward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lim));
+  cudaFuncSetAttribute(k_subtree_backward<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lim));
+  cudaFuncSetAttribute(k_subtree_backward<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lim));
+  cudaFuncSetAttribute(k_subtree_backward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lim));
+  return lim;
+}
+
+void launch_subtree_forward(int M, const SubtreeArgs &a, int32_t n_inst, size_t smem_bytes, cudaStream_t st) {
+  if (n_inst <= 0) return;
+  MMMFE_DISPATCH_M(M, (k_subtree_forward<MM><<<n_inst, 256, smem_bytes, st>>>(a)));
+  launch_counter_add(1);
+}
+void launch_subtree_backward(int M, const SubtreeArgs &a, int32_t n_inst, size_t smem_bytes, cudaStream_t st) {
+  if (n_inst <= 0) return;
+  MMMFE_DISPATCH_M(M, (k_subtree_backward<MM><<<n_inst, 256, smem_bytes, st>>>(a)));
   launch_counter_add(1);
 }
 

@@ -12,13 +12,41 @@ void launch_counter_add(long long n);
 
 // One front of the nested-dissection tree as the solve kernels see it.
 struct FrontDesc {
-  int32_t s, b, ldr, nsplit;
+  int32_t s, b, ldr, ldf, nsplit;
   int32_t child0, child1;
-  int64_t r_off;    // R = [F11^-1 | -G^T], s rows of ldr doubles
+  int64_t rb_off;   // R = [F11^-1 | -G^T], s rows of ldr doubles (backward)
+  int64_t rf_off;   // -G^T, s rows of ldf doubles (forward copy, contiguous)
   int64_t idx_off;  // s + b user flux dof indices (separator first)
   int64_t src_off;  // 2 * (s + b) child gather maps
   int64_t z_off;    // s + nsplit * b per-front vector entries
 };
+
+// Subtree templates / instances on the device (see nd_tree.h).
+struct TemplateDev {
+  int32_t n_nodes, n_levels, n_int, n_rootb, zl_size, rf_size, rb_size;
+  const int32_t *node_s, *node_b, *node_rf, *node_rb, *node_sep, *node_bnd, *node_zl;
+  const int32_t *var_code, *rootb_code, *sep_node, *sep_c0, *sep_c1, *out_node, *out_c0, *out_c1, *bnd_var;
+  const int32_t *lvl_sep, *lvl_out;
+};
+
+struct InstanceDev {
+  int32_t tmpl, I0, J0, pad;
+  int64_t rf_base, rb_base, z_root;  // z_root: first boundary-contribution entry of the root in z
+};
+
+struct SubtreeArgs {
+  const TemplateDev *tmpl;
+  const InstanceDev *inst;
+  const double *R;
+  double *x, *z;
+  const int32_t *dof_of_canon;  // nullptr when the user numbering is canonical
+  int32_t nx;
+  int64_t nxe;
+};
+void launch_subtree_forward(int M, const SubtreeArgs &a, int32_t n_inst, size_t smem_bytes, cudaStream_t st);
+void launch_subtree_backward(int M, const SubtreeArgs &a, int32_t n_inst, size_t smem_bytes, cudaStream_t st);
+// sets the dynamic shared memory limit of the subtree kernels; returns the device's opt-in maximum
+size_t subtree_smem_limit();
 
 // Work item of the large-front kernels.
 //  forward : rows [r0,r1) of R times boundary columns [c0,c1); writes partial contribution `split`
@@ -70,9 +98,7 @@ struct SolveArgs {
   double *x;  // rhs in / solution out, [flux dof][M]
 };
 void launch_forward_large(int M, const SolveArgs &a, const WorkItem *items, int32_t n_items, cudaStream_t st);
-void launch_forward_small(int M, const SolveArgs &a, const int32_t *nodes, int32_t n_nodes, cudaStream_t st);
 void launch_backward_large(int M, const SolveArgs &a, const WorkItem *items, int32_t n_items, cudaStream_t st);
-void launch_backward_small(int M, const SolveArgs &a, const int32_t *nodes, int32_t n_nodes, cudaStream_t st);
 
 // ---- time stepping ---------------------------------------------------------------------------------------------
 struct StepArgs {

@@ -55,10 +55,14 @@ def test_medium_nonmatching_grids_match_oracle(tmp_path):
     r = reps[0]
     assert abs(r["gmres_iterations"] - o.gmres_iterations) <= 1
     assert r["r_norm"] == pytest.approx(o.r_norm, rel=1e-11)
-    if r["gmres_iterations"] == o.gmres_iterations:
-        assert rel_l2(lam, o.lam) < 1e-9
-        for c in COLS:
-            assert r[c] == pytest.approx(o.errors[c], rel=1e-8), c
+    # ~95 iterations of un-restarted classical Gram-Schmidt GMRES amplify 1-ulp differences of the operator to
+    # ~4e-7 in lambda (measured on the oracle against itself): the computed lambda is only
+    # defined to the stop tolerance (1e-6), the early residual history and the error columns are reproducible.
+    n = min(len(res), len(o.residuals), 20)
+    np.testing.assert_allclose(res[:n], o.residuals[:n], rtol=1e-5)
+    assert rel_l2(lam, o.lam) < 5 * prm.tolerance
+    for c in COLS:
+        assert r[c] == pytest.approx(o.errors[c], rel=1e-5), c
     assert r["factor_groups"] == 2
 
 
