@@ -164,7 +164,7 @@ struct Sub {
 // ---- one factor: nested-dissection tree + block-inverse fronts on the device -------------------------------------
 struct LevelWork {  // one height level of the top of the tree
   DevBuf<WorkItem> fwd, bwd;
-  int32_t n_fwd = 0, n_bwd = 0;
+  int32_t n_fwd = 0, n_bwd = 0, f_max = 0;
   double bytes_fwd = 0, bytes_bwd = 0;
 };
 
@@ -556,6 +556,7 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax) 
       const NdNode &n = tr.nodes[id];
       const int64_t f = n.s + n.b;
       bytes += 4 * (2 * f + 2 * f);
+      lw.f_max = std::max(lw.f_max, int32_t(f));
       lw.bytes_fwd += 8.0 * n.s * n.b + 4.0 * 3 * f;
       lw.bytes_bwd += 8.0 * n.s * f + 4.0 * f;
       const int rows_per = (n.s + n.nsplit - 1) / n.nsplit;  // <= 32
@@ -586,7 +587,7 @@ static void run_solve(const Factor &F, int M, double *x, double *z, cudaStream_t
   const SubtreeArgs sa = subtree_args(F, x, z);
   launch_subtree_forward(M, sa, F.n_inst, F.smem_fwd[M], st);
   for (const LevelWork &lw : F.levels) launch_forward_large(M, a, lw.fwd.p, lw.n_fwd, st);
-  for (auto it = F.levels.rbegin(); it != F.levels.rend(); ++it) launch_backward_large(M, a, it->bwd.p, it->n_bwd, st);
+  for (auto it = F.levels.rbegin(); it != F.levels.rend(); ++it) launch_backward_large(M, a, it->bwd.p, it->n_bwd, it->f_max, st);
   launch_subtree_backward(M, sa, F.n_inst, F.smem_bwd[M], st);
 }
 
@@ -1297,7 +1298,7 @@ int mmmfe_profile_step(mmmfe_ctx *c, double ms[MMMFE_N_KERNEL_CLASSES], double b
       for (const LevelWork &lw : F.levels)
         if (lw.n_fwd) { launch_forward_large(M, a, lw.fwd.p, lw.n_fwd, st); mark(2); bytes[2] += lw.bytes_fwd; launches[2] += 1; }
       for (auto it = F.levels.rbegin(); it != F.levels.rend(); ++it)
-        if (it->n_bwd) { launch_backward_large(M, a, it->bwd.p, it->n_bwd, st); mark(3); bytes[3] += it->bytes_bwd; launches[3] += 1; }
+        if (it->n_bwd) { launch_backward_large(M, a, it->bwd.p, it->n_bwd, it->f_max, st); mark(3); bytes[3] += it->bytes_bwd; launches[3] += 1; }
       if (F.n_inst) { launch_subtree_backward(M, sa, F.n_inst, F.smem_bwd[M], st); mark(4); bytes[4] += F.bytes_sub_bwd + 2 * vec * F.nf; launches[4] += 1; }
       launch_update(b.step, c->trace.p, 0, nullptr, F.np, nullptr, int64_t(F.nf) + F.np, 0, st);
       mark(5); bytes[5] += vec * (4.0 * F.np + 2.0 * F.np) + 12.0 * 4 * F.np; launches[5] += 1;

@@ -278,7 +278,9 @@ __device__ __forceinline__ void gather_children(const SolveArgs &a, const FrontD
 
 constexpr int FWD_ROWS = 32;  // rows of -G^T per forward item (== NdNode::nsplit granularity)
 
-// item = rows [r0,r1) x boundary columns [c0,c1) of one front: partial contribution `split`
+// item = rows [r0,r1) x boundary columns [c0,c1) of one front: partial contribution `split`.
+// All (<= 32) matrix loads of a thread are issued before anything else, so the gather chain of the input vector
+// (index -> child descriptor -> child contribution) overlaps the HBM latency of the factor.
 template <int M>
 __global__ void __launch_bounds__(256) k_forward_large(SolveArgs a, const WorkItem *__restrict__ items) {
   __shared__ double vs[FWD_ROWS * M];
@@ -288,6 +290,20 @@ __global__ void __launch_bounds__(256) k_forward_large(SolveArgs a, const WorkIt
   const int32_t s = fd.s, f = fd.s + fd.b;
   const int tid = threadIdx.x;
   const int nr = it.r1 - it.r0;
+  const int nc = it.c1 - it.c0;
+  int cw = 32;
+  while (cw < nc && cw < 256) cw <<= 1;
+  const int rg = 256 / cw;
+  const int cid = tid % cw, rgid = tid / cw;
+  double rv[FWD_ROWS];
+  {
+    const double *Rc = a.R + fd.rf_off + int64_t(it.r0) * fd.ldf + it.c0 + cid;
+#pragma unroll
+    for (int k = 0; k < FWD_ROWS; ++k) {
+      const int i = rgid + k * rg;
+      rv[k] = (cid < nc && i < nr) ? __ldg(Rc + int64_t(i) * fd.ldf) : 0.0;
+    }
+  }
   if (tid < nr) {
     const int32_t p = it.r0 + tid;
     double val[M];
@@ -301,56 +317,43 @@ __global__ void __launch_bounds__(256) k_forward_large(SolveArgs a, const WorkIt
 #pragma unroll
       for (int j = 0; j < M; ++j) a.z[(fd.z_off + p) * M + j] = val[j];
   }
-  __syncthreads();
-  const int nc = it.c1 - it.c0;
-  if (nc <= 0) return;
-  int cw = 32;
-  while (cw < nc && cw < 256) cw <<= 1;
-  const int rg = 256 / cw;
-  const int cid = tid % cw, rgid = tid / cw;
   double acc[M];
 #pragma unroll
   for (int j = 0; j < M; ++j) acc[j] = 0.0;
-  if (cid < nc) {
-    const double *Rc = a.R + fd.rf_off + int64_t(it.r0) * fd.ldf + it.c0 + cid;
-    int i = rgid;
-    for (; i + 3 * rg < nr; i += 4 * rg) {  // four independent loads in flight per thread
-      const double r0 = __ldg(Rc + int64_t(i) * fd.ldf), r1 = __ldg(Rc + int64_t(i + rg) * fd.ldf);
-      const double r2 = __ldg(Rc + int64_t(i + 2 * rg) * fd.ldf), r3 = __ldg(Rc + int64_t(i + 3 * rg) * fd.ldf);
+  const bool writer = rgid == 0 && cid < nc;
+  if (writer && it.split == 0) gather_children<M>(a, fd, f, s + it.c0 + cid, acc);
+  __syncthreads();
+  if (nc <= 0) return;
 #pragma unroll
-      for (int j = 0; j < M; ++j)
-        acc[j] += r0 * vs[i * M + j] + r1 * vs[(i + rg) * M + j] + r2 * vs[(i + 2 * rg) * M + j] +
-                  r3 * vs[(i + 3 * rg) * M + j];
-    }
-    for (; i < nr; i += rg) {
-      const double r = __ldg(Rc + int64_t(i) * fd.ldf);
+  for (int k = 0; k < FWD_ROWS; ++k) {
+    const int i = rgid + k * rg;
+    if (i < nr) {
 #pragma unroll
-      for (int j = 0; j < M; ++j) acc[j] += r * vs[i * M + j];
+      for (int j = 0; j < M; ++j) acc[j] += rv[k] * vs[i * M + j];
     }
   }
   if (rg > 1) {
+    if (rgid > 0)
 #pragma unroll
-    for (int j = 0; j < M; ++j) red[tid * M + j] = acc[j];
+      for (int j = 0; j < M; ++j) red[tid * M + j] = acc[j];
     __syncthreads();
-    if (rgid == 0 && cid < nc)
+    if (writer)
       for (int g = 1; g < rg; ++g)
 #pragma unroll
         for (int j = 0; j < M; ++j) acc[j] += red[(g * cw + cid) * M + j];
   }
-  if (rgid == 0 && cid < nc) {
+  if (writer) {
     const int32_t q = it.c0 + cid;
-    if (it.split == 0) gather_children<M>(a, fd, f, s + q, acc);
 #pragma unroll
     for (int j = 0; j < M; ++j) a.z[(fd.z_off + s + int64_t(it.split) * fd.b + q) * M + j] = acc[j];
   }
 }
 
-constexpr int BWD_CHUNK = 512;
-
-// item = rows [r0,r1) of R = [F11^-1 | -G^T] (at most 32 rows, 4 per warp)
+// item = rows [r0,r1) of R = [F11^-1 | -G^T] (at most 32 rows, 4 per warp); the input vector of the whole front
+// is staged once in dynamic shared memory, 8 x rows loads are in flight per lane
 template <int M>
 __global__ void __launch_bounds__(256) k_backward_large(SolveArgs a, const WorkItem *__restrict__ items) {
-  __shared__ double ws[BWD_CHUNK * M];
+  extern __shared__ __align__(16) double ws[];
   const WorkItem it = items[blockIdx.x];
   const FrontDesc fd = a.fronts[it.node];
   const int32_t s = fd.s, f = fd.s + fd.b;
@@ -358,39 +361,63 @@ __global__ void __launch_bounds__(256) k_backward_large(SolveArgs a, const WorkI
   const int nrow = it.r1 - it.r0;
   const int per_warp = (nrow + 7) / 8;  // 1..4
   const int rbase = it.r0 + warp * per_warp;
+  const double *Rr = a.R + fd.rb_off + int64_t(rbase) * fd.ldr;
   double acc[4][M];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int j = 0; j < M; ++j) acc[r][j] = 0.0;
-  const double *Rr = a.R + fd.rb_off + int64_t(rbase) * fd.ldr;
-  for (int pc = 0; pc < f; pc += BWD_CHUNK) {
-    const int chunk = min(BWD_CHUNK, f - pc);
-    for (int t = tid; t < chunk; t += 256) {
-      const int32_t p = pc + t;
-      if (p < s) {
+  // first batch of matrix loads goes out before the input vector is gathered
+  double rv[4][8];
 #pragma unroll
-        for (int j = 0; j < M; ++j) ws[t * M + j] = a.z[(fd.z_off + p) * M + j];
-      } else {
-        const int64_t d = a.idx[fd.idx_off + p];
+  for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int j = 0; j < M; ++j) ws[t * M + j] = a.x[d * M + j];
-      }
+    for (int u = 0; u < 8; ++u) {
+      const int t = lane + 32 * u;
+      rv[r][u] = (r < per_warp && rbase + r < it.r1 && t < f) ? __ldg(Rr + int64_t(r) * fd.ldr + t) : 0.0;
     }
-    __syncthreads();
-    for (int t = lane; t < chunk; t += 32) {
-      double wv[M];
+  for (int p = tid; p < f; p += 256) {
+    if (p < s) {
 #pragma unroll
-      for (int j = 0; j < M; ++j) wv[j] = ws[t * M + j];
+      for (int j = 0; j < M; ++j) ws[p * M + j] = a.z[(fd.z_off + p) * M + j];
+    } else {
+      const int64_t d = a.idx[fd.idx_off + p];
+#pragma unroll
+      for (int j = 0; j < M; ++j) ws[p * M + j] = a.x[d * M + j];
+    }
+  }
+  __syncthreads();
+  for (int t0 = 0; t0 < f; t0 += 256) {
+    double nx_[4][8];
+    const int t1 = t0 + 256;
+    if (t1 < f) {
 #pragma unroll
       for (int r = 0; r < 4; ++r)
-        if (r < per_warp && rbase + r < it.r1) {
-          const double rv = __ldg(Rr + int64_t(r) * fd.ldr + pc + t);
 #pragma unroll
-          for (int j = 0; j < M; ++j) acc[r][j] += rv * wv[j];
+        for (int u = 0; u < 8; ++u) {
+          const int t = t1 + lane + 32 * u;
+          nx_[r][u] = (r < per_warp && rbase + r < it.r1 && t < f) ? __ldg(Rr + int64_t(r) * fd.ldr + t) : 0.0;
         }
     }
-    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int t = t0 + lane + 32 * u;
+      if (t < f) {
+        double wv[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) wv[j] = ws[t * M + j];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int j = 0; j < M; ++j) acc[r][j] += rv[r][u] * wv[j];
+      }
+    }
+    if (t1 < f) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) rv[r][u] = nx_[r][u];
+    }
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r)
@@ -598,9 +625,11 @@ void launch_forward_large(int M, const SolveArgs &a, const WorkItem *items, int3
   MMMFE_DISPATCH_M(M, (k_forward_large<MM><<<n_items, 256, 0, st>>>(a, items)));
   launch_counter_add(1);
 }
-void launch_backward_large(int M, const SolveArgs &a, const WorkItem *items, int32_t n_items, cudaStream_t st) {
+void launch_backward_large(int M, const SolveArgs &a, const WorkItem *items, int32_t n_items, int32_t f_max,
+                           cudaStream_t st) {
   if (n_items <= 0) return;
-  MMMFE_DISPATCH_M(M, (k_backward_large<MM><<<n_items, 256, 0, st>>>(a, items)));
+  const size_t smem = size_t(f_max) * M * sizeof(double);
+  MMMFE_DISPATCH_M(M, (k_backward_large<MM><<<n_items, 256, smem, st>>>(a, items)));
   launch_counter_add(1);
 }
 
@@ -609,6 +638,9 @@ size_t subtree_smem_limit() {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const size_t lim = size_t(optin);
+  cudaFuncSetAttribute(k_backward_large<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lim));
+  cudaFuncSetAttribute(k_backward_large<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lim));
+  cudaFuncSetAttribute(k_backward_large<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lim));
   cudaFuncSetAttribute(k_subtree_forward<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lim));
   cudaFuncSetAttribute(k_subtree_forward<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lim));
   cudaFuncSetAttribute(k_subtree_forward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lim));

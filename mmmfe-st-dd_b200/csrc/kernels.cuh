@@ -98,7 +98,8 @@ struct SolveArgs {
   double *x;  // rhs in / solution out, [flux dof][M]
 };
 void launch_forward_large(int M, const SolveArgs &a, const WorkItem *items, int32_t n_items, cudaStream_t st);
-void launch_backward_large(int M, const SolveArgs &a, const WorkItem *items, int32_t n_items, cudaStream_t st);
+void launch_backward_large(int M, const SolveArgs &a, const WorkItem *items, int32_t n_items, int32_t f_max,
+                           cudaStream_t st);
 
 // ---- time stepping ---------------------------------------------------------------------------------------------
 struct StepArgs {

@@ -27,6 +27,10 @@ if __name__ == "__main__":
     reps = int(sys.argv[7]) if len(sys.argv) > 7 else 3
     prob = build(nf, ntf, nc, ntc, [ms, ms, mt])
     eng = pkg().Engine()
+    import os
+    for key in ("subtree_cells", "leaf_cells", "use_graphs"):
+        if os.environ.get("MMMFE_" + key.upper()):
+            eng.set_option(key, float(os.environ["MMMFE_" + key.upper()]))
     for sd in prob.subs:
         eng.add_subdomain(global_id=sd.r, nx=sd.nx, ny=sd.ny, nt=sd.nt, dt=sd.dt, matrix=sd.matrix.tocsr(),
                           n_flux=sd.nf, n_pressure=sd.np, neighbor=sd.neighbors,
@@ -45,4 +49,6 @@ if __name__ == "__main__":
     print(f"apply {ms_:.3f} ms  ({1e3 / ms_:.2f} applies/s)  step_bytes(all batches, 1 step) {st['step_bytes'] / 1e6:.1f} MB")
     dofsteps = sum(sd.n * sd.nt for sd in prob.subs)
     print(f"DOF*steps/s {dofsteps / (ms_ * 1e-3):.3e}")
+    for k, v in eng.profile_step().items():
+        print(f"  {k:18s} {v['ms']*1e3:8.1f} us  {v['bytes']/1e6:8.1f} MB  {v['launches']:3d} launches  {v['bytes']/1e9/max(v['ms'],1e-9)*1e3:7.0f} GB/s")
     eng.close()
