@@ -80,7 +80,9 @@ const char *mmmfe_version(void);
 /* Options (set before mmmfe_setup): "keep_history" (default 1: keep every bar level on the device so that the
  * final sweep can return full solutions), "use_graphs" (default 1: replay each sweep as a CUDA graph),
  * "leaf_cells" (default 4: nested-dissection leaf size), "subtree_cells" (default 256: largest box solved by one CTA
- * from shared memory; 0 disables the subtree kernels).                                                      */
+ * from shared memory; 0 disables the subtree kernels), "use_sweep" (default 1: run the star sweeps in the
+ * persistent sweep kernel when the matrix has the RT0 structure), "sweep_chunk" (doubles per streamed chunk),
+ * "sweep_min_fill" (entries the shared-memory ring must hold), "sweep_evict_first" (L2 hint of the factor stream). */
 int mmmfe_set_option(mmmfe_ctx *ctx, const char *key, double value);
 
 /* ---- multi-GPU: one process per GPU, subdomains sharded over ranks ------------------------------------------ */
@@ -185,6 +187,18 @@ int mmmfe_solve_saddle(mmmfe_ctx *ctx, int32_t local_index, const double *rhs, d
 int mmmfe_profile_step(mmmfe_ctx *ctx, double ms[MMMFE_N_KERNEL_CLASSES], double bytes[MMMFE_N_KERNEL_CLASSES],
                        int64_t launches[MMMFE_N_KERNEL_CLASSES]);
 
+/* Times ONE full star sweep (all local time steps, one cooperative launch of the persistent sweep kernel) of every
+ * batch that runs on the sweep path: device milliseconds, algorithmic bytes per time step, steps.  n_out = batches
+ * reported (0 when the generic kernels are in use).                                                          */
+int mmmfe_profile_sweeps(mmmfe_ctx *ctx, int32_t cap, double *ms, double *bytes_per_step, int32_t *n_steps,
+                         int32_t *n_out);
+/* One instrumented star sweep of sweep batch `batch`: mean SM cycles per CTA spent in {subtree forward, top forward,
+ * top backward, subtree backward} entries, in completion-counter waits, in TMA (mbarrier) waits; out[6] = entries. */
+int mmmfe_profile_sweep_cycles(mmmfe_ctx *ctx, int32_t batch, double out[8]);
+/* Integer facts about the set-up context: "batches", "sweep_batches", "sweep_ctas", "sweep_smem_bytes",
+ * "sweep_entries", "sweep_factor_bytes", "rt0_factors"; -1 for an unknown key.                                */
+int64_t mmmfe_stat(const mmmfe_ctx *ctx, const char *key);
+
 /* ---- diagnostics (host only, no device needed) ------------------------------------------------------------------- */
 /* The nested-dissection tree the engine builds for an nx x ny RT0 grid, in canonical flux numbering.
  * sizes = {n_nodes, idx_len, src_len, r_total, z_total, n_heights}.
@@ -193,6 +207,14 @@ int mmmfe_profile_step(mmmfe_ctx *ctx, double ms[MMMFE_N_KERNEL_CLASSES], double
 /* Copies the stored factor (R blocks, layout given by the nd-tree offsets/ldr) of a local subdomain's group. */
 int mmmfe_debug_get_factor(mmmfe_ctx *ctx, int32_t local_index, double *r_out, int64_t capacity);
 int mmmfe_nd_tree_sizes(int32_t nx, int32_t ny, int32_t leaf_cells, int64_t sizes[6]);
+/* Builds the static schedule of the persistent sweep kernel for an nx x ny grid (n_cta CTAs, M right-hand sides,
+ * smem_bytes of dynamic shared memory per CTA) and replays n_steps of it on the CPU against the kernel's ring,
+ * barrier and completion-counter rules.  0 = every entry completes and no ring range is overwritten early;
+ * negative = failure with a message.  stats = {sweep nodes, top fronts, entries, factor doubles, ring doubles,
+ * workspace doubles, largest entry doubles, shared memory bytes}.                                             */
+int mmmfe_sweep_plan_check(int32_t nx, int32_t ny, int32_t leaf_cells, int32_t subtree_cells, int32_t M,
+                           int32_t n_cta, int64_t smem_bytes, int32_t n_steps, int64_t stats[8], char *msg,
+                           int32_t msg_cap);
 int mmmfe_nd_tree_fill(int32_t nx, int32_t ny, int32_t leaf_cells, int32_t *node_table, int64_t *offsets,
                        int32_t *idx, int32_t *src);
 

@@ -86,6 +86,11 @@ def load_engine():
         "mmmfe_solve_saddle": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p, c_f64p]),
         "mmmfe_profile_step": (ctypes.c_int, [vp, c_f64p, c_f64p, c_i64p]),
         "mmmfe_debug_get_factor": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p, ctypes.c_int64]),
+        "mmmfe_profile_sweeps": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p, c_f64p, c_i32p, c_i32p]),
+        "mmmfe_stat": (ctypes.c_int64, [vp, ctypes.c_char_p]),
+        "mmmfe_profile_sweep_cycles": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p]),
+        "mmmfe_sweep_plan_check": (ctypes.c_int, [ctypes.c_int32] * 6 + [ctypes.c_int64, ctypes.c_int32, c_i64p,
+                                                  ctypes.c_char_p, ctypes.c_int32]),
         "mmmfe_nd_tree_sizes": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_i64p]),
         "mmmfe_nd_tree_fill": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_i32p, c_i64p, c_i32p,
                                               c_i32p]),
@@ -262,6 +267,24 @@ class Engine:
         names = ["rhs_build", "subtree_forward", "forward_top", "backward_top", "subtree_backward", "update_trace"]
         return {n: dict(ms=float(ms[i]), bytes=float(by[i]), launches=int(ln[i])) for i, n in enumerate(names)}
 
+    def stat(self, key):
+        return int(self.lib.mmmfe_stat(self.h, key.encode()))
+
+    def profile_sweeps(self):
+        """One timed star sweep per batch on the persistent-kernel path: [(ms, bytes_per_step, n_steps)]."""
+        cap = 64
+        ms, by = np.zeros(cap), np.zeros(cap)
+        ns, n = np.zeros(cap, dtype=np.int32), np.zeros(1, dtype=np.int32)
+        self._check(self.lib.mmmfe_profile_sweeps(self.h, cap, _ptr(ms, c_f64p), _ptr(by, c_f64p), _ptr(ns, c_i32p),
+                                                  _ptr(n, c_i32p)))
+        return [(float(ms[i]), float(by[i]), int(ns[i])) for i in range(int(n[0]))]
+
+    def profile_sweep_cycles(self, batch):
+        out = np.zeros(8)
+        self._check(self.lib.mmmfe_profile_sweep_cycles(self.h, batch, _ptr(out, c_f64p)))
+        names = ["sub_fwd", "top_fwd", "top_bwd", "sub_bwd", "counter_wait", "tma_wait", "entries"]
+        return dict(zip(names, (float(v) for v in out)))
+
     def debug_get_factor(self, li, r_total):
         out = np.empty(r_total)
         self._check(self.lib.mmmfe_debug_get_factor(self.h, li, _ptr(out, c_f64p), r_total))
@@ -272,6 +295,18 @@ class Engine:
         out = np.empty_like(rhs)
         self._check(self.lib.mmmfe_solve_saddle(self.h, li, _ptr(rhs, c_f64p), _ptr(out, c_f64p)))
         return out
+
+
+def sweep_plan_check(nx, ny, leaf_cells=4, subtree_cells=128, M=1, n_cta=296, smem_bytes=115000, n_steps=3):
+    """Builds the persistent-kernel schedule on the host and replays it on the CPU; returns (rc, stats, message)."""
+    lib = load_engine()
+    stats = np.zeros(8, dtype=np.int64)
+    msg = ctypes.create_string_buffer(256)
+    rc = lib.mmmfe_sweep_plan_check(nx, ny, leaf_cells, subtree_cells, M, n_cta, smem_bytes, n_steps,
+                                    _ptr(stats, c_i64p), msg, 256)
+    keys = ["nodes", "top_fronts", "entries", "factor_doubles", "ring_doubles", "ws_doubles", "max_entry_doubles",
+            "smem_bytes"]
+    return rc, dict(zip(keys, (int(v) for v in stats))), msg.value.decode()
 
 
 def nd_tree(nx, ny, leaf_cells=4):

@@ -37,13 +37,13 @@ def _run(cmd):
 
 
 def build_engine(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("kernels.cu", "engine.cu", "nd_tree.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("kernels.cuh", "nd_tree.h")] + \
+    srcs = [os.path.join(CSRC, f) for f in ("kernels.cu", "sweep.cu", "engine.cu", "nd_tree.cpp", "sweep_plan.cpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("kernels.cuh", "nd_tree.h", "sweep.cuh", "sweep_plan.h", "common.h")] + \
         [os.path.join(ROOT, "include", "mmmfe_b200.h")]
     if not force and not _newer(LIB_ENGINE, deps):
         return LIB_ENGINE
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB_ENGINE] + srcs
+    cmd = [nvcc] + NVCC_FLAGS + ["-x", "cu", "-shared", "-o", LIB_ENGINE] + srcs
     if os.path.exists("/usr/include/nccl.h"):
         cmd += ["-DMMMFE_WITH_NCCL", "-ldl"]  # NCCL is dlopen'ed at run time
     if verbose:

@@ -14,8 +14,11 @@
 #include <vector>
 
 #include "../../include/mmmfe_b200.h"
+#include "common.h"
 #include "kernels.cuh"
 #include "nd_tree.h"
+#include "sweep.cuh"
+#include "sweep_plan.h"
 
 #ifdef MMMFE_WITH_NCCL
 #include <dlfcn.h>
@@ -61,87 +64,6 @@ static NcclApi &nccl() {
 static const double kNormalSign[4] = {-1.0, 1.0, 1.0, -1.0};  // inc/utilities.h:79-91
 static const int kOpposite[4] = {2, 3, 0, 1};
 
-struct Error {
-  int code;
-  std::string msg;
-};
-
-[[noreturn]] static void fail(int code, const char *fmt, ...) {
-  char buf[1024];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof buf, fmt, ap);
-  va_end(ap);
-  throw Error{code, buf};
-}
-
-#define CUDA_CHECK(x)                                                                              \
-  do {                                                                                             \
-    cudaError_t e_ = (x);                                                                          \
-    if (e_ != cudaSuccess) fail(MMMFE_E_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), \
-                                __FILE__, __LINE__);                                               \
-  } while (0)
-
-template <class T>
-struct DevBuf {
-  T *p = nullptr;
-  size_t n = 0;
-  DevBuf() = default;
-  DevBuf(const DevBuf &) = delete;
-  DevBuf &operator=(const DevBuf &) = delete;
-  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
-  DevBuf &operator=(DevBuf &&o) noexcept {
-    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
-    return *this;
-  }
-  ~DevBuf() { release(); }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    n = 0;
-  }
-  void alloc(size_t count) {
-    release();
-    n = count;
-    if (count) CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
-  }
-  void zero(cudaStream_t st = 0) {
-    if (n) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), st));
-  }
-  void upload(const T *h, size_t count) {
-    alloc(count);
-    if (count) CUDA_CHECK(cudaMemcpy(p, h, count * sizeof(T), cudaMemcpyHostToDevice));
-  }
-  void upload(const std::vector<T> &v) { upload(v.data(), v.size()); }
-};
-
-struct HostCsr {
-  int64_t n_rows = 0, n_cols = 0;
-  std::vector<int64_t> rp;
-  std::vector<int32_t> col;
-  std::vector<double> val;
-  void from(const mmmfe_csr &c) {
-    n_rows = c.n_rows;
-    n_cols = c.n_cols;
-    rp.assign(c.row_ptr, c.row_ptr + c.n_rows + 1);
-    col.assign(c.col, c.col + rp.back());
-    val.assign(c.val, c.val + rp.back());
-  }
-};
-
-struct DevCsr {
-  int64_t n_rows = 0;
-  DevBuf<int64_t> rp;
-  DevBuf<int32_t> col;
-  DevBuf<double> val;
-  void upload(const HostCsr &h) {
-    n_rows = h.n_rows;
-    rp.upload(h.rp);
-    col.upload(h.col);
-    val.upload(h.val);
-  }
-};
-
 // ---- one registered subdomain ------------------------------------------------------------------------------------
 struct Sub {
   int32_t gid, nx, ny, nt, nf, np;
@@ -186,6 +108,18 @@ struct Factor {
   DevBuf<double> minv;
   int64_t solve_bytes = 0;  // factor + index bytes one forward+backward pass streams
   double seconds = 0.0;
+  // ---- persistent sweep path (sweep.cuh): RT0 structure of the saddle matrix + factor in streaming layout ----
+  bool rt0 = false, sweep_ok = false;
+  double kup_c[4] = {0, 0, 0, 0}, kpu_c[4] = {0, 0, 0, 0};
+  std::vector<int32_t> p_of_cell_h;  // canonical cell -> user pressure index
+  bool p_identity = true;
+  SweepLayout lay;
+  int32_t sweep_n_cta = 0;
+  size_t sweep_budget = 0;
+  DevBuf<double> Rs, minv_c;
+  DevBuf<int32_t> top_cell, p_of_cell;
+  DevBuf<uint16_t> tmpl16;
+  DevBuf<int64_t> tmpl_off;
 };
 
 // ---- one batch: up to 4 subdomains solved as simultaneous right-hand sides of one factor ---------------------------
@@ -205,6 +139,17 @@ struct Batch {
   cudaGraphExec_t graph_star = nullptr;
   long long graph_kernels = 0;
   StepArgs step{};
+  // persistent sweep path
+  bool sweep = false;
+  size_t sweep_smem = 0;
+  DevBuf<SweepEntry> s_entries;
+  DevBuf<SweepIssue> s_issue;
+  DevBuf<int32_t> s_cta_begin, s_cta_pro, s_sub_q, s_bq_stride;
+  DevBuf<double> s_z, s_xi, s_ptil, s_bq_coef;
+  DevBuf<uint32_t> s_cnt;
+  DevBuf<const double *> s_bq_data;
+  DevBuf<double *> s_bq_trace;
+  SweepArgs sargs{};
 };
 
 struct Arena {
@@ -225,8 +170,9 @@ using namespace mmmfe;
 struct mmmfe_ctx {
   int device = 0;
   std::string err;
-  bool keep_history = true, use_graphs = true;
-  int leaf_cells = 4, subtree_cells = 256;
+  bool keep_history = true, use_graphs = true, use_sweep = true, sweep_evict_first = true;
+  int leaf_cells = 4, subtree_cells = 256, sweep_chunk = 2048;
+  double sweep_min_fill = 2.0;
   bool is_setup = false, bar_done = false, final_done = false;
   int rank = 0, world = 1;
   std::vector<int32_t> owner;
@@ -255,6 +201,7 @@ struct mmmfe_ctx {
   int64_t q_rows = 0;
   double factor_seconds = 0.0;
   long long launch_base = 0;
+  int *abort_flag = nullptr;  // pinned: raised by the sweep kernel's watchdog
   // temporaries of the factorisation
   DevBuf<GemmProb> d_gemm;
   DevBuf<int32_t> d_tiles;
@@ -389,6 +336,115 @@ static void build_schur(const Sub &sd, HostCsr &S, HostCsr &kup, HostCsr &kpu, s
   }
 }
 
+// RT0 structure of the off-diagonal blocks (src/darcy_vtdd.cc:464-466): every flux row of K_up holds the same two
+// constants for its lower/upper cell, every pressure row of K_pu the same four for its left/right/bottom/top edge.
+// Recovers the cell of every user pressure index from the matrix itself (x-edges, walking each row of cells from the
+// left boundary).  False = some other discretisation: the generic kernels are used.
+static bool detect_rt0(const Sub &sd, const HostCsr &kup, const HostCsr &kpu, const std::vector<int32_t> &dof_of_canon,
+                       Factor &F) {
+  const int nx = sd.nx, ny = sd.ny;
+  const int64_t nxe = int64_t(nx + 1) * ny;
+  auto user = [&](int64_t canon) { return dof_of_canon.empty() ? int32_t(canon) : dof_of_canon[canon]; };
+  std::vector<int32_t> p_of_cell(size_t(nx) * ny, -1), cell_of_p(size_t(nx) * ny, -1);
+  double k[4] = {0, 0, 0, 0};
+  bool have[4] = {false, false, false, false};
+  auto set_const = [&](int slot, double v) {
+    if (!have[slot]) { have[slot] = true; k[slot] = v; return true; }
+    return k[slot] == v;
+  };
+  for (int j = 0; j < ny; ++j)
+    for (int i = 0; i <= nx; ++i) {
+      const int32_t d = user(int64_t(j) * (nx + 1) + i);
+      const int64_t e0 = kup.rp[d], e1 = kup.rp[d + 1];
+      const int expect = (i > 0) + (i < nx);
+      if (e1 - e0 != expect) return false;
+      int32_t right = -1;
+      for (int64_t e = e0; e < e1; ++e) {
+        const int32_t col = kup.col[e];
+        if (i > 0 && col == p_of_cell[size_t(j) * nx + i - 1]) { if (!set_const(0, kup.val[e])) return false; }
+        else if (right < 0 && i < nx) { right = col; if (!set_const(1, kup.val[e])) return false; }
+        else return false;
+      }
+      if (i < nx) {
+        if (right < 0 || right >= nx * ny || cell_of_p[right] >= 0) return false;
+        p_of_cell[size_t(j) * nx + i] = right;
+        cell_of_p[right] = j * nx + i;
+      }
+    }
+  for (int j = 0; j <= ny; ++j)
+    for (int i = 0; i < nx; ++i) {
+      const int32_t d = user(nxe + int64_t(j) * nx + i);
+      const int64_t e0 = kup.rp[d], e1 = kup.rp[d + 1];
+      if (e1 - e0 != (j > 0) + (j < ny)) return false;
+      for (int64_t e = e0; e < e1; ++e) {
+        const int32_t col = kup.col[e];
+        if (j > 0 && col == p_of_cell[size_t(j - 1) * nx + i]) { if (!set_const(2, kup.val[e])) return false; }
+        else if (j < ny && col == p_of_cell[size_t(j) * nx + i]) { if (!set_const(3, kup.val[e])) return false; }
+        else return false;
+      }
+    }
+  double q[4] = {0, 0, 0, 0};
+  bool hq[4] = {false, false, false, false};
+  for (int j = 0; j < ny; ++j)
+    for (int i = 0; i < nx; ++i) {
+      const int32_t r = p_of_cell[size_t(j) * nx + i];
+      const int32_t edge[4] = {user(int64_t(j) * (nx + 1) + i), user(int64_t(j) * (nx + 1) + i + 1),
+                               user(nxe + int64_t(j) * nx + i), user(nxe + int64_t(j + 1) * nx + i)};
+      if (kpu.rp[r + 1] - kpu.rp[r] != 4) return false;
+      for (int64_t e = kpu.rp[r]; e < kpu.rp[r + 1]; ++e) {
+        int slot = -1;
+        for (int t = 0; t < 4; ++t) if (kpu.col[e] == edge[t]) slot = t;
+        if (slot < 0) return false;
+        if (!hq[slot]) { hq[slot] = true; q[slot] = kpu.val[e]; }
+        else if (q[slot] != kpu.val[e]) return false;
+      }
+    }
+  for (int t = 0; t < 4; ++t) { F.kup_c[t] = k[t]; F.kpu_c[t] = q[t]; }
+  F.p_identity = true;
+  for (size_t cidx = 0; cidx < p_of_cell.size(); ++cidx) if (p_of_cell[cidx] != int32_t(cidx)) F.p_identity = false;
+  F.p_of_cell_h = std::move(p_of_cell);
+  return true;
+}
+
+// resident sweep CTAs per SM and the dynamic shared memory each may use
+static void sweep_geometry(int device, int M, int32_t &n_cta, size_t &budget) {
+  int sms = 0, per_sm = 0, reserved = 0, optin = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+  cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, device);
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  budget = std::min<size_t>(size_t(optin), size_t(per_sm) / 2 - size_t(reserved)) - 256;
+  int per = sweep_ctas_per_sm(M, budget);
+  if (per < 2) {  // register-limited: one CTA per SM with the whole shared memory
+    budget = size_t(optin) - 256;
+    per = std::max(1, sweep_ctas_per_sm(M, budget));
+  }
+  n_cta = std::min(per, 2) * sms;
+}
+
+// Factor in streaming order + the device copies of the layout tables (after the numeric factorisation).
+static void build_sweep_factor(mmmfe_ctx *c, Factor &F, const std::vector<double> &minv) {
+  const SweepLayout &L = F.lay;
+  CUDA_CHECK(cudaDeviceSynchronize());
+  F.Rs.alloc(size_t(L.rs_total) + 2);
+  DevBuf<RepackDesc> d_desc;
+  d_desc.upload(L.repack);
+  launch_repack(d_desc.p, int32_t(L.repack.size()), F.R.p, F.Rs.p, c->stream);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  CUDA_CHECK(cudaMemcpyAsync(F.Rs.p + L.sub_rs_base, F.R.p + L.sub_old_base, size_t(L.sub_dbl) * sizeof(double),
+                             cudaMemcpyDeviceToDevice, c->stream));
+  F.top_cell.upload(L.top_cell);
+  F.tmpl16.upload(L.tmpl16);
+  F.tmpl_off.upload(L.tmpl_off);
+  std::vector<double> mc(minv.size());
+  for (size_t cell = 0; cell < mc.size(); ++cell) mc[cell] = minv[F.p_of_cell_h[cell]];
+  F.minv_c.upload(mc);
+  if (!F.p_identity) F.p_of_cell.upload(F.p_of_cell_h);
+  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  F.sweep_ok = true;
+}
+
 static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax) {
   const auto t0 = std::chrono::steady_clock::now();
   auto F = std::make_shared<Factor>();
@@ -399,19 +455,6 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax) 
   F->kup.upload(kup); F->kpu.upload(kpu); F->minv.upload(minv);
   NdTree &tr = F->tree;
   const size_t smem_limit = subtree_smem_limit();
-  for (int cells = c->subtree_cells;; cells /= 2) {  // largest subtrees whose factor blob + vectors fit on chip twice per SM
-    tr.build(sd.nx, sd.ny, c->leaf_cells, cells);
-    for (int M = 1; M <= 4; M *= 2) F->smem_fwd[M] = F->smem_bwd[M] = 0;
-    for (const auto &T : tr.templates)
-      for (int M = 1; M <= 4; M *= 2) {
-        F->smem_fwd[M] = std::max(F->smem_fwd[M], 16 + 8 * (size_t(T.rf_size) + size_t(T.zl_size) * M + size_t(T.n_int) * M));
-        F->smem_bwd[M] = std::max(F->smem_bwd[M], 16 + 8 * (size_t(T.rb_size) + size_t(2 * T.n_int + T.n_rootb) * M));
-      }
-    if (cells == 0 || (F->smem_fwd[Mmax] <= smem_limit / 2 && F->smem_bwd[Mmax] <= smem_limit / 2)) break;
-  }
-  if (tr.n_flux != sd.nf) fail(MMMFE_E_INVALID, "n_flux %d does not match an RT0 grid %dx%d", sd.nf, sd.nx, sd.ny);
-  const int32_t nn = int32_t(tr.nodes.size());
-  // user numbering of the front variables
   std::vector<int32_t> dof_of_canon;
   if (!sd.canon.empty()) {
     dof_of_canon.assign(sd.nf, -1);
@@ -421,6 +464,34 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax) 
       dof_of_canon[cidx] = d;
     }
   }
+  if (int64_t(sd.nx + 1) * sd.ny + int64_t(sd.nx) * (sd.ny + 1) != sd.nf)
+    fail(MMMFE_E_INVALID, "n_flux %d does not match an RT0 grid %dx%d", sd.nf, sd.nx, sd.ny);
+  F->rt0 = detect_rt0(sd, kup, kpu, dof_of_canon, *F);
+  bool want_sweep = c->use_sweep && F->rt0 && c->subtree_cells > 0;
+  if (want_sweep) sweep_geometry(c->device, Mmax, F->sweep_n_cta, F->sweep_budget);
+  bool sweep_planned = false;
+  for (int cells = c->subtree_cells;; cells /= 2) {  // largest subtrees whose factor blob + vectors fit on chip twice per SM
+    tr.build(sd.nx, sd.ny, c->leaf_cells, cells);
+    for (int M = 1; M <= 4; M *= 2) F->smem_fwd[M] = F->smem_bwd[M] = 0;
+    for (const auto &T : tr.templates)
+      for (int M = 1; M <= 4; M *= 2) {
+        F->smem_fwd[M] = std::max(F->smem_fwd[M], 16 + 8 * (size_t(T.rf_size) + size_t(T.zl_size) * M + size_t(T.n_int) * M));
+        F->smem_bwd[M] = std::max(F->smem_bwd[M], 16 + 8 * (size_t(T.rb_size) + size_t(2 * T.n_int + T.n_rootb) * M));
+      }
+    if (cells == 0) break;
+    if (F->smem_fwd[Mmax] > smem_limit / 2 || F->smem_bwd[Mmax] > smem_limit / 2) continue;
+    if (!want_sweep) break;
+    // the persistent sweep kernel additionally wants a ring of several entries
+    if (build_sweep_layout(tr, F->sweep_n_cta, c->sweep_chunk, F->lay) != nullptr) { want_sweep = false; break; }
+    SweepSchedule probe;
+    if (build_sweep_schedule(tr, F->lay, Mmax, F->sweep_budget, c->sweep_min_fill, probe) == nullptr) { sweep_planned = true; break; }
+    if (cells / 2 < std::max(1, c->leaf_cells)) {  // cannot shrink further: generic kernels with the widest subtrees
+      want_sweep = false;
+      cells = c->subtree_cells * 2;
+    }
+  }
+  const int32_t nn = int32_t(tr.nodes.size());
+  // user numbering of the front variables
   std::vector<int32_t> idx_user(tr.idx.size());
   for (size_t i = 0; i < tr.idx.size(); ++i) idx_user[i] = dof_of_canon.empty() ? tr.idx[i] : dof_of_canon[tr.idx[i]];
   std::vector<FrontDesc> fd(nn);
@@ -574,8 +645,17 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax) 
   }
   F->solve_bytes = bytes;
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (sweep_planned) build_sweep_factor(c, *F, minv);
   F->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return F;
+}
+
+// after a stream synchronisation: did a spin-wait of the sweep kernel give up?
+static void check_watchdog(mmmfe_ctx *c) {
+  if (c->abort_flag && *c->abort_flag) {
+    *c->abort_flag = 0;
+    fail(MMMFE_E_CUDA, "sweep kernel watchdog: a data-flow wait did not complete (results discarded)");
+  }
 }
 
 static SubtreeArgs subtree_args(const Factor &F, double *x, double *z) {
@@ -595,6 +675,11 @@ static void run_solve(const Factor &F, int M, double *x, double *z, cudaStream_t
 // sweeps
 // =================================================================================================================
 enum SweepMode { SWEEP_BAR, SWEEP_STAR, SWEEP_FINAL };
+
+static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> &iface_q,
+                             const std::vector<int64_t> &tr_base, const std::vector<int32_t> &tr_stride,
+                             const std::vector<double> &tr_sign);
+static void run_sweep_kernel(mmmfe_ctx *c, Batch &b);
 
 static void enqueue_sweep(mmmfe_ctx *c, Batch &b, SweepMode mode) {
   const Factor &F = *b.factor;
@@ -620,6 +705,10 @@ static void run_star_sweeps(mmmfe_ctx *c, SweepMode mode) {
   CUDA_CHECK(cudaEventRecord(c->ev_start, c->stream));
   for (auto &bp : c->batches) {
     Batch &b = *bp;
+    if (mode == SWEEP_STAR && b.sweep) {  // persistent kernels own the whole GPU: one after the other
+      run_sweep_kernel(c, b);
+      continue;
+    }
     CUDA_CHECK(cudaStreamWaitEvent(b.stream, c->ev_start, 0));
     if (mode == SWEEP_STAR && c->use_graphs) {
       if (!b.graph_star) {
@@ -828,11 +917,109 @@ static void setup(mmmfe_ctx *c) {
       b->step = StepArgs{b->M, F.nf, F.np, F.kup.rp.p, F.kup.col.p, F.kup.val.p, F.kpu.rp.p, F.kpu.col.p,
                          F.kpu.val.p, F.minv.p, b->x.p, b->ptil.p, b->n_tr, b->tr_dof.p, b->tr_mem.p,
                          b->tr_stride.p, b->tr_base.p, b->tr_sign.p, b->iface_q.p};
+      if (c->use_sweep) plan_batch_sweep(c, *b, iface_q, tr_base, tr_stride, tr_sign);
       c->batches.push_back(std::move(b));
     }
   }
   CUDA_CHECK(cudaDeviceSynchronize());
   c->is_setup = true;
+}
+
+// Entry lists, ring schedule and boundary-entry tables of one batch for the persistent sweep kernel.
+static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> &iface_q,
+                             const std::vector<int64_t> &tr_base, const std::vector<int32_t> &tr_stride,
+                             const std::vector<double> &tr_sign) {
+  Factor &F = *b.factor;
+  if (!F.sweep_ok) return;
+  const NdTree &tr = F.tree;
+  SweepSchedule S;
+  if (build_sweep_schedule(tr, F.lay, b.M, F.sweep_budget, 2.0, S) != nullptr) return;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  if (sweep_ctas_per_sm(b.M, S.smem_bytes) * sms < F.sweep_n_cta) return;  // grid would not be co-resident
+  const int M = b.M;
+  // boundary entries: the interface dofs of every member (same enumeration as tr_*); per boundary subtree a table
+  // [interior variable][member] -> entry
+  const int64_t nxe = int64_t(F.nx + 1) * F.ny;
+  std::vector<int32_t> dof_of_canon;
+  if (F.dof_of_canon.n) {
+    dof_of_canon.resize(F.dof_of_canon.n);
+    CUDA_CHECK(cudaMemcpy(dof_of_canon.data(), F.dof_of_canon.p, F.dof_of_canon.n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  }
+  std::vector<int32_t> sub_q, bq_off(tr.instances.size(), -1);
+  for (size_t k = 0; k < tr.instances.size(); ++k) {
+    const SubtreeInstance &in = tr.instances[k];
+    const SubtreeTemplate &T = tr.templates[in.tmpl];
+    if (T.flags == 0) continue;
+    const size_t base = sub_q.size();
+    bool any = false;
+    for (int32_t l = 0; l < T.n_int; ++l) {
+      const int32_t code = T.var_code[l];
+      const int type = code >> 30, dj = (code >> 15) & 0x7fff, di = code & 0x7fff;
+      const int64_t canon = type == 0 ? int64_t(in.J0 + dj) * (F.nx + 1) + in.I0 + di : nxe + int64_t(in.J0 + dj) * F.nx + in.I0 + di;
+      const int64_t d = dof_of_canon.empty() ? canon : dof_of_canon[canon];
+      for (int j = 0; j < M; ++j) {
+        const int32_t q = iface_q[size_t(d) * M + j];
+        sub_q.push_back(q);
+        any |= q >= 0;
+      }
+    }
+    if (any) bq_off[k] = int32_t(base);
+    else sub_q.resize(base);
+  }
+  for (auto &e : S.entries)
+    if (e.kind == SW_SUB_FWD || e.kind == SW_SUB_BWD) e.a1 = bq_off[e.a7];
+  sub_q.push_back(-1);
+  const size_t nq = tr_base.size();
+  std::vector<const double *> data(nq + 1, nullptr);
+  std::vector<double *> trace(nq + 1, nullptr);
+  std::vector<double> coef(nq + 1, 0.0);
+  std::vector<int32_t> stride(nq + 1, 0);
+  for (size_t q = 0; q < nq; ++q) {
+    data[q] = c->lam_bar.p + tr_base[q];
+    trace[q] = c->trace.p + tr_base[q];
+    coef[q] = -tr_sign[q];  // rhs_i = -s * lam_bar, src/darcy_vtdd.cc:840-844
+    stride[q] = tr_stride[q];
+  }
+  b.s_entries.upload(S.entries); b.s_issue.upload(S.issue);
+  b.s_cta_begin.upload(S.cta_begin); b.s_cta_pro.upload(S.cta_prologue);
+  b.s_sub_q.upload(sub_q); b.s_bq_stride.upload(stride); b.s_bq_coef.upload(coef);
+  b.s_bq_data.upload(data); b.s_bq_trace.upload(trace);
+  b.s_z.alloc(size_t(F.lay.z_total + 1) * M); b.s_z.zero();
+  b.s_xi.alloc(size_t(F.lay.xi_total + 1) * M); b.s_xi.zero();
+  b.s_ptil.alloc(size_t(F.np) * M); b.s_ptil.zero();
+  b.s_cnt.alloc(2 * F.lay.nodes.size() + 2); b.s_cnt.zero();
+  SweepArgs &a = b.sargs;
+  std::memset(&a, 0, sizeof a);
+  a.entries = b.s_entries.p; a.issue = b.s_issue.p; a.cta_begin = b.s_cta_begin.p; a.cta_prologue = b.s_cta_pro.p;
+  a.Rs = F.Rs.p; a.idx_user = F.idx_user.p; a.src = F.src.p;
+  a.top_cell = reinterpret_cast<const int2 *>(F.top_cell.p);
+  a.tmpl16 = F.tmpl16.p; a.tmpl_off = F.tmpl_off.p; a.dof_of_canon = F.dof_of_canon.p;
+  a.x = b.x.p; a.z = b.s_z.p; a.xi = b.s_xi.p; a.ptil = b.s_ptil.p; a.cnt = b.s_cnt.p; a.minv = F.minv_c.p;
+  a.sub_q = b.s_sub_q.p; a.bq_data = b.s_bq_data.p; a.bq_trace = b.s_bq_trace.p; a.bq_stride = b.s_bq_stride.p;
+  a.bq_coef = b.s_bq_coef.p;
+  a.p_of_cell = F.p_of_cell.p;
+  a.kx0 = F.kup_c[0]; a.kx1 = F.kup_c[1]; a.ky0 = F.kup_c[2]; a.ky1 = F.kup_c[3];
+  a.cl = F.kpu_c[0]; a.cr = F.kpu_c[1]; a.cb = F.kpu_c[2]; a.ct = F.kpu_c[3];
+  a.nx = F.nx; a.ny = F.ny; a.nxe = nxe; a.n_flux = F.nf; a.n_pressure = F.np;
+  a.n_steps = b.nt; a.level0 = 0;
+  a.tmpl_dbl = S.tmpl_dbl; a.ws_dbl = S.ws_dbl; a.ring_dbl = S.ring_dbl;
+  a.evict_first = c->sweep_evict_first ? 1 : 0;
+  if (!c->abort_flag) {
+    CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void **>(&c->abort_flag), sizeof(int), cudaHostAllocMapped));
+    *c->abort_flag = 0;
+  }
+  a.abort_flag = c->abort_flag;
+  b.sweep_smem = S.smem_bytes;
+  b.sweep = true;
+}
+
+// all nt star steps of one batch in one cooperative launch on the interface stream
+static void run_sweep_kernel(mmmfe_ctx *c, Batch &b) {
+  CUDA_CHECK(cudaMemsetAsync(b.s_ptil.p, 0, b.s_ptil.n * sizeof(double), c->stream));
+  CUDA_CHECK(cudaMemsetAsync(b.s_cnt.p, 0, b.s_cnt.n * sizeof(uint32_t), c->stream));
+  const cudaError_t err = launch_sweep(b.M, b.sargs, b.factor->sweep_n_cta, b.sweep_smem, c->stream);
+  if (err != cudaSuccess) fail(MMMFE_E_CUDA, "sweep kernel launch failed: %s", cudaGetErrorString(err));
 }
 
 static void bar_sweep(mmmfe_ctx *c) {
@@ -897,6 +1084,7 @@ static void gmres(mmmfe_ctx *c, double tol, int max_iter, mmmfe_gmres_info *info
     double n2 = 0.0;
     CUDA_CHECK(cudaMemcpyAsync(&n2, c->norm_dev.p, sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
+    check_watchdog(c);
     std::vector<double> h(hh.begin(), hh.begin() + k + 1);
     h.push_back(std::sqrt(n2));  // :1455
     launch_scale_store(len, c->ap.p, h[k + 1], Q + int64_t(k + 1) * len, st);  // :1458-1463
@@ -993,6 +1181,7 @@ int mmmfe_destroy(mmmfe_ctx *c) {
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->abort_flag) cudaFreeHost(c->abort_flag);
   delete c;
   return MMMFE_OK;
 }
@@ -1006,6 +1195,10 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   else if (k == "use_graphs") c->use_graphs = value != 0;
   else if (k == "leaf_cells") c->leaf_cells = std::max(1, int(value));
   else if (k == "subtree_cells") c->subtree_cells = std::max(0, int(value));
+  else if (k == "use_sweep") c->use_sweep = value != 0;
+  else if (k == "sweep_evict_first") c->sweep_evict_first = value != 0;
+  else if (k == "sweep_chunk") c->sweep_chunk = std::max(256, int(value)) & ~1;
+  else if (k == "sweep_min_fill") c->sweep_min_fill = value;
   else { c->err = "unknown option " + k; return MMMFE_E_INVALID; }
   return MMMFE_OK;
 }
@@ -1164,6 +1357,7 @@ int mmmfe_apply_interface_operator(mmmfe_ctx *c, const double *q, double *ap) {
     apply_operator(c, c->qin.p, c->ap.p);
     CUDA_CHECK(cudaMemcpyAsync(ap, c->ap.p, bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    check_watchdog(c);
   });
 }
 
@@ -1193,6 +1387,7 @@ int mmmfe_apply_interface_operator_device(mmmfe_ctx *c, int32_t repeat, double *
     for (int i = 0; i < repeat; ++i) apply_operator(c, c->qin.p, c->ap.p);
     CUDA_CHECK(cudaEventRecord(c->ev_t1, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    check_watchdog(c);
     float t = 0;
     CUDA_CHECK(cudaEventElapsedTime(&t, c->ev_t0, c->ev_t1));
     if (ms) *ms = double(t) / repeat;
@@ -1213,6 +1408,7 @@ int mmmfe_final_sweep(mmmfe_ctx *c) {
     launch_spmv(c->n_fine, c->c2f_all.rp.p, c->c2f_all.col.p, c->c2f_all.val.p, c->lam.p, c->lam_bar.p, c->stream);
     run_star_sweeps(c, SWEEP_FINAL);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    check_watchdog(c);
     c->final_done = true;
   });
 }
@@ -1311,6 +1507,83 @@ int mmmfe_profile_step(mmmfe_ctx *c, double ms[MMMFE_N_KERNEL_CLASSES], double b
         ms[cls[i]] += t;
       }
     for (auto e : ev) cudaEventDestroy(e);
+  });
+}
+
+int64_t mmmfe_stat(const mmmfe_ctx *c, const char *key) {
+  if (!c || !key) return -1;
+  const std::string k(key);
+  int64_t v = 0;
+  if (k == "batches") return int64_t(c->batches.size());
+  if (k == "sweep_batches") { for (auto &b : c->batches) v += b->sweep; return v; }
+  if (k == "sweep_ctas") { for (auto &b : c->batches) if (b->sweep) v = std::max<int64_t>(v, b->factor->sweep_n_cta); return v; }
+  if (k == "sweep_smem_bytes") { for (auto &b : c->batches) if (b->sweep) v = std::max<int64_t>(v, int64_t(b->sweep_smem)); return v; }
+  if (k == "sweep_entries") { for (auto &b : c->batches) if (b->sweep) v += int64_t(b->s_entries.n); return v; }
+  if (k == "sweep_factor_bytes") { for (auto &f : c->factors) if (f->sweep_ok) v += int64_t(f->lay.bytes_per_step); return v; }
+  if (k == "rt0_factors") { for (auto &f : c->factors) v += f->rt0; return v; }
+  return -1;
+}
+
+int mmmfe_profile_sweep_cycles(mmmfe_ctx *c, int32_t batch, double out[8]) {
+  if (!c || !out) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, {
+    if (!c->is_setup) fail(MMMFE_E_INVALID, "mmmfe_setup first");
+    int32_t k = 0;
+    for (auto &bp : c->batches) {
+      Batch &b = *bp;
+      if (!b.sweep) continue;
+      if (k++ != batch) continue;
+      const int32_t n_cta = b.factor->sweep_n_cta;
+      DevBuf<long long> prof;
+      prof.alloc(size_t(n_cta) * 8);
+      prof.zero(c->stream);
+      SweepArgs a = b.sargs;
+      a.prof = prof.p;
+      CUDA_CHECK(cudaMemsetAsync(b.s_ptil.p, 0, b.s_ptil.n * sizeof(double), c->stream));
+      CUDA_CHECK(cudaMemsetAsync(b.s_cnt.p, 0, b.s_cnt.n * sizeof(uint32_t), c->stream));
+      const cudaError_t err = launch_sweep(b.M, a, n_cta, b.sweep_smem, c->stream);
+      if (err != cudaSuccess) fail(MMMFE_E_CUDA, "sweep kernel launch failed: %s", cudaGetErrorString(err));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      check_watchdog(c);
+      std::vector<long long> h(size_t(n_cta) * 8);
+      CUDA_CHECK(cudaMemcpy(h.data(), prof.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      for (int t = 0; t < 8; ++t) out[t] = 0;
+      for (int32_t cta = 0; cta < n_cta; ++cta)
+        for (int t = 0; t < 8; ++t) out[t] += double(h[size_t(cta) * 8 + t]) / n_cta;
+      return MMMFE_OK;
+    }
+    fail(MMMFE_E_INVALID, "no such sweep batch");
+  });
+}
+
+int mmmfe_profile_sweeps(mmmfe_ctx *c, int32_t cap, double *ms, double *bytes_per_step, int32_t *n_steps,
+                         int32_t *n_out) {
+  if (!c || !ms || !bytes_per_step || !n_steps || !n_out) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, {
+    if (!c->is_setup) fail(MMMFE_E_INVALID, "mmmfe_setup first");
+    int32_t k = 0;
+    for (auto &bp : c->batches) {
+      Batch &b = *bp;
+      if (!b.sweep || k >= cap) continue;
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      CUDA_CHECK(cudaMemsetAsync(b.s_ptil.p, 0, b.s_ptil.n * sizeof(double), c->stream));
+      CUDA_CHECK(cudaMemsetAsync(b.s_cnt.p, 0, b.s_cnt.n * sizeof(uint32_t), c->stream));
+      CUDA_CHECK(cudaEventRecord(c->ev_t0, c->stream));
+      const cudaError_t err = launch_sweep(b.M, b.sargs, b.factor->sweep_n_cta, b.sweep_smem, c->stream);
+      if (err != cudaSuccess) fail(MMMFE_E_CUDA, "sweep kernel launch failed: %s", cudaGetErrorString(err));
+      CUDA_CHECK(cudaEventRecord(c->ev_t1, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      check_watchdog(c);
+      float t = 0;
+      CUDA_CHECK(cudaEventElapsedTime(&t, c->ev_t0, c->ev_t1));
+      ms[k] = t;
+      // factor stream + 8 (2 n + 2 sum n_side) bytes of vector traffic per member
+      bytes_per_step[k] = double(b.factor->solve_bytes) +
+                          double(b.members.size()) * 16.0 * (double(b.factor->nf) + b.factor->np) + 16.0 * b.n_tr;
+      n_steps[k] = b.nt;
+      ++k;
+    }
+    *n_out = k;
   });
 }
 

@@ -180,6 +180,16 @@ void NdTree::build(int32_t nx_, int32_t ny_, int32_t leaf_cells, int32_t subtree
           else T.bnd_var.push_back(T.n_int + rootb_pos.at(v));
         }
       }
+      {
+        std::map<int32_t, int32_t> local_of;  // canonical flux index -> local variable
+        int32_t l = 0;
+        for (int32_t k : order)
+          for (int32_t p = 0; p < nodes[k].s; ++p) local_of[idx[nodes[k].idx_off + p]] = l++;
+        for (const auto &kv : rootb_pos) local_of[kv.first] = T.n_int + kv.second;
+        for (int j = root.j0; j < root.j1; ++j)
+          for (int i = root.i0; i < root.i1; ++i)
+            for (int32_t v : {xe(i, j), xe(i + 1, j), ye(i, j), ye(i, j + 1)}) T.cell_edge.push_back(local_of.at(v));
+      }
       T.n_levels = int32_t(T.lvl_sep.size());
       T.lvl_sep.push_back(T.n_int);
       T.lvl_out.push_back(T.zl_size);

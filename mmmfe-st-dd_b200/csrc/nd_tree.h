@@ -59,6 +59,9 @@ struct SubtreeTemplate {
   std::vector<int32_t> bnd_var;
   // level ranges (by height ascending) into the flat sep / out lists
   std::vector<int32_t> lvl_sep, lvl_out;
+  // per cell of the box (row-major, dj * w + di): local index (into [interior | root boundary]) of its four
+  // edges x(di,dj), x(di+1,dj), y(di,dj), y(di,dj+1) -- the fused pressure update of the sweep kernel
+  std::vector<int32_t> cell_edge;
 };
 
 struct SubtreeInstance {

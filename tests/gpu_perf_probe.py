@@ -28,7 +28,7 @@ if __name__ == "__main__":
     prob = build(nf, ntf, nc, ntc, [ms, ms, mt])
     eng = pkg().Engine()
     import os
-    for key in ("subtree_cells", "leaf_cells", "use_graphs"):
+    for key in ("subtree_cells", "leaf_cells", "use_graphs", "use_sweep", "sweep_chunk", "sweep_min_fill", "sweep_evict_first"):
         if os.environ.get("MMMFE_" + key.upper()):
             eng.set_option(key, float(os.environ["MMMFE_" + key.upper()]))
     for sd in prob.subs:
@@ -49,6 +49,14 @@ if __name__ == "__main__":
     print(f"apply {ms_:.3f} ms  ({1e3 / ms_:.2f} applies/s)  step_bytes(all batches, 1 step) {st['step_bytes'] / 1e6:.1f} MB")
     dofsteps = sum(sd.n * sd.nt for sd in prob.subs)
     print(f"DOF*steps/s {dofsteps / (ms_ * 1e-3):.3e}")
+    print("sweep batches", eng.stat("sweep_batches"), "of", eng.stat("batches"), "ctas", eng.stat("sweep_ctas"),
+          "smem", eng.stat("sweep_smem_bytes"), "entries", eng.stat("sweep_entries"))
+    for ms_sw, by, ns in eng.profile_sweeps():
+        print(f"  sweep kernel: {ms_sw:9.3f} ms for {ns} steps = {ms_sw / ns * 1e3:8.1f} us/step, "
+              f"{by / 1e6:8.1f} MB/step -> {by * ns / ms_sw / 1e6:7.0f} GB/s")
+    for bi in range(eng.stat("sweep_batches")):
+        cyc = eng.profile_sweep_cycles(bi)
+        print("  cycles/CTA:", {k: round(v) for k, v in cyc.items()})
     for k, v in eng.profile_step().items():
         print(f"  {k:18s} {v['ms']*1e3:8.1f} us  {v['bytes']/1e6:8.1f} MB  {v['launches']:3d} launches  {v['bytes']/1e9/max(v['ms'],1e-9)*1e3:7.0f} GB/s")
     eng.close()
