@@ -117,7 +117,9 @@ struct Factor {
   int32_t sweep_n_cta = 0;
   size_t sweep_budget = 0;
   DevBuf<double> Rs, minv_c;
-  DevBuf<int32_t> top_cell, p_of_cell;
+  double minv_const = 0.0;
+  bool minv_uniform = false;
+  DevBuf<int32_t> sweep_index, p_of_cell;
   DevBuf<uint16_t> tmpl16;
   DevBuf<int64_t> tmpl_off;
 };
@@ -428,17 +430,25 @@ static void build_sweep_factor(mmmfe_ctx *c, Factor &F, const std::vector<double
   CUDA_CHECK(cudaDeviceSynchronize());
   F.Rs.alloc(size_t(L.rs_total) + 2);
   DevBuf<RepackDesc> d_desc;
+  DevBuf<RepackSub> d_sub;
+  DevBuf<int32_t> d_perm;
   d_desc.upload(L.repack);
+  d_sub.upload(L.repack_sub);
+  d_perm.upload(L.perm);
   launch_repack(d_desc.p, int32_t(L.repack.size()), F.R.p, F.Rs.p, c->stream);
+  launch_repack_sub(d_sub.p, int32_t(L.repack_sub.size()), d_perm.p, F.R.p, F.Rs.p, c->stream);
   CUDA_CHECK(cudaGetLastError());
-  CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  CUDA_CHECK(cudaMemcpyAsync(F.Rs.p + L.sub_rs_base, F.R.p + L.sub_old_base, size_t(L.sub_dbl) * sizeof(double),
-                             cudaMemcpyDeviceToDevice, c->stream));
-  F.top_cell.upload(L.top_cell);
+  F.sweep_index.upload(L.index);
   F.tmpl16.upload(L.tmpl16);
   F.tmpl_off.upload(L.tmpl_off);
-  std::vector<double> mc(minv.size());
-  for (size_t cell = 0; cell < mc.size(); ++cell) mc[cell] = minv[F.p_of_cell_h[cell]];
+  // 1 / (c0 |cell|) in box-major cell order (a scalar on uniform grids)
+  std::vector<double> mc(size_t(L.pb_total) + 2, 0.0);
+  F.minv_uniform = true;
+  for (size_t cell = 0; cell < L.cell_box.size(); ++cell) {
+    mc[L.cell_box[cell]] = minv[F.p_of_cell_h[cell]];
+    if (mc[L.cell_box[cell]] != minv[F.p_of_cell_h[0]]) F.minv_uniform = false;
+  }
+  F.minv_const = minv[F.p_of_cell_h[0]];
   F.minv_c.upload(mc);
   if (!F.p_identity) F.p_of_cell.upload(F.p_of_cell_h);
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -482,7 +492,11 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax) 
     if (F->smem_fwd[Mmax] > smem_limit / 2 || F->smem_bwd[Mmax] > smem_limit / 2) continue;
     if (!want_sweep) break;
     // the persistent sweep kernel additionally wants a ring of several entries
-    if (build_sweep_layout(tr, F->sweep_n_cta, c->sweep_chunk, F->lay) != nullptr) { want_sweep = false; break; }
+    {
+      std::vector<int32_t> iu(tr.idx.size());
+      for (size_t i = 0; i < tr.idx.size(); ++i) iu[i] = dof_of_canon.empty() ? tr.idx[i] : dof_of_canon[tr.idx[i]];
+      if (build_sweep_layout(tr, iu, dof_of_canon, F->sweep_n_cta, c->sweep_chunk, F->lay) != nullptr) { want_sweep = false; break; }
+    }
     SweepSchedule probe;
     if (build_sweep_schedule(tr, F->lay, Mmax, F->sweep_budget, c->sweep_min_fill, probe) == nullptr) { sweep_planned = true; break; }
     if (cells / 2 < std::max(1, c->leaf_cells)) {  // cannot shrink further: generic kernels with the widest subtrees
@@ -986,16 +1000,16 @@ static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> 
   b.s_sub_q.upload(sub_q); b.s_bq_stride.upload(stride); b.s_bq_coef.upload(coef);
   b.s_bq_data.upload(data); b.s_bq_trace.upload(trace);
   b.s_z.alloc(size_t(F.lay.z_total + 1) * M); b.s_z.zero();
-  b.s_xi.alloc(size_t(F.lay.xi_total + 1) * M); b.s_xi.zero();
-  b.s_ptil.alloc(size_t(F.np) * M); b.s_ptil.zero();
+  b.s_xi.alloc(size_t(F.lay.xi_total + 2) * M); b.s_xi.zero();
+  b.s_ptil.alloc(size_t(F.lay.pb_total + 2) * M); b.s_ptil.zero();
   b.s_cnt.alloc(2 * F.lay.nodes.size() + 2); b.s_cnt.zero();
   SweepArgs &a = b.sargs;
   std::memset(&a, 0, sizeof a);
   a.entries = b.s_entries.p; a.issue = b.s_issue.p; a.cta_begin = b.s_cta_begin.p; a.cta_prologue = b.s_cta_pro.p;
-  a.Rs = F.Rs.p; a.idx_user = F.idx_user.p; a.src = F.src.p;
-  a.top_cell = reinterpret_cast<const int2 *>(F.top_cell.p);
+  a.Rs = F.Rs.p; a.index = F.sweep_index.p;
   a.tmpl16 = F.tmpl16.p; a.tmpl_off = F.tmpl_off.p; a.dof_of_canon = F.dof_of_canon.p;
-  a.x = b.x.p; a.z = b.s_z.p; a.xi = b.s_xi.p; a.ptil = b.s_ptil.p; a.cnt = b.s_cnt.p; a.minv = F.minv_c.p;
+  a.x = b.x.p; a.z = b.s_z.p; a.xi = b.s_xi.p; a.ptil = b.s_ptil.p; a.cnt = b.s_cnt.p;
+  a.minv = F.minv_uniform ? nullptr : F.minv_c.p; a.minv_const = F.minv_const;
   a.sub_q = b.s_sub_q.p; a.bq_data = b.s_bq_data.p; a.bq_trace = b.s_bq_trace.p; a.bq_stride = b.s_bq_stride.p;
   a.bq_coef = b.s_bq_coef.p;
   a.p_of_cell = F.p_of_cell.p;

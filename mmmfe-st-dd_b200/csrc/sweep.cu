@@ -6,7 +6,7 @@
 namespace mmmfe {
 
 // =================================================================================================================
-// repack: old front storage -> contiguous column blocks
+// repack: old front storage -> contiguous column blocks / row-major subtree blobs
 // =================================================================================================================
 __global__ void __launch_bounds__(256) k_repack(const RepackDesc *__restrict__ desc, const double *__restrict__ R,
                                                 double *__restrict__ Rs) {
@@ -35,15 +35,39 @@ void launch_repack(const RepackDesc *d_desc, int32_t n_desc, const double *R_old
   }
 }
 
+__global__ void __launch_bounds__(256) k_repack_sub(const RepackSub *__restrict__ desc, const int32_t *__restrict__ perm,
+                                                    const double *__restrict__ R, double *__restrict__ Rs) {
+  const RepackSub d = desc[blockIdx.x];
+  for (int k = threadIdx.x; k < d.rf_size; k += blockDim.x) Rs[d.new_rf + k] = R[d.old_rf + k];
+  const int32_t *pm = perm + d.perm_off;
+  for (int k = threadIdx.x; k < d.rb_size; k += blockDim.x) Rs[d.new_rb + k] = R[d.old_rb + pm[k]];
+}
+
+void launch_repack_sub(const RepackSub *d_desc, int32_t n_desc, const int32_t *perm, const double *R_old, double *Rs,
+                       cudaStream_t st) {
+  for (int32_t off = 0; off < n_desc; off += 1 << 20) {
+    const int32_t cnt = n_desc - off < (1 << 20) ? n_desc - off : (1 << 20);
+    k_repack_sub<<<cnt, 256, 0, st>>>(d_desc + off, perm, R_old, Rs);
+    launch_counter_add(1);
+  }
+}
+
 // =================================================================================================================
 // device helpers
 // =================================================================================================================
 namespace {
 
+constexpr int NB = SWEEP_NBAR;
+constexpr int CT = SWEEP_COMPUTE;
+
 __device__ __forceinline__ uint32_t s_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
-__device__ __forceinline__ void bar_init(uint64_t *bar) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(s_u32(bar)) : "memory");
+__device__ __forceinline__ void bar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(s_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void bar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(s_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ bool bar_try(uint64_t *bar, uint32_t parity) {
@@ -60,7 +84,7 @@ __device__ __forceinline__ bool bar_try(uint64_t *bar, uint32_t parity) {
   return ok != 0;
 }
 
-// Every spin in the kernel is bounded: after ~4 s (or when another CTA gave up) the waiter raises the abort flag
+// Every spin in the kernel is bounded: after ~4 s (or when another thread gave up) the waiter raises the abort flag
 // (pinned host memory) and carries on with whatever data it has; the host reports the failure after the launch.
 constexpr long long SWEEP_SPIN_LIMIT = 8000000000LL;
 
@@ -78,29 +102,6 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity, volatil
   const long long t0 = clock64();
   for (int n = 0; !bar_try(bar, parity); ++n)
     if ((n & 1023) == 1023 && spin_expired(t0, abort_flag)) return;
-}
-
-// arm the barrier with the byte count and start the bulk copies (one thread)
-__device__ __forceinline__ void tma_issue(double *dst, const double *src, uint32_t bytes, uint64_t *bar,
-                                          bool evict_first, uint64_t policy) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
-  uint32_t done = 0;
-  while (done < bytes) {
-    const uint32_t n = min(bytes - done, 32768u);
-    if (evict_first) {
-      asm volatile(
-          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::
-              "r"(s_u32(reinterpret_cast<char *>(dst) + done)),
-          "l"(reinterpret_cast<const char *>(src) + done), "r"(n), "r"(s_u32(bar)), "l"(policy)
-          : "memory");
-    } else {
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                       s_u32(reinterpret_cast<char *>(dst) + done)),
-                   "l"(reinterpret_cast<const char *>(src) + done), "r"(n), "r"(s_u32(bar))
-                   : "memory");
-    }
-    done += n;
-  }
 }
 
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p) {
@@ -122,25 +123,28 @@ __device__ __forceinline__ void wait_counter(const uint32_t *p, uint32_t target,
   }
 }
 
-// packed template accessors (uint16, 0xFFFF = none)
+// compute warps only
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;\n" ::"n"(CT) : "memory"); }
+
+// generic-proxy global writes that a later TMA (async proxy) read of this CTA must see
+__device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy.async.global;\n" ::: "memory"); }
+
 __device__ __forceinline__ int t16(const uint16_t *p, int i) {
   const int v = p[i];
   return v == 0xFFFF ? -1 : v;
 }
 
-struct Tmpl {  // views into the shared-memory copy of a packed template
-  int n_nodes, n_levels, n_int, n_rootb, zl_size, rf_size, rb_size, w, h;
-  const uint16_t *node_s, *node_b, *node_rf, *node_rb, *node_sep, *node_bnd, *node_zl, *var_code, *rootb_code,
-      *sep_node, *sep_c0, *sep_c1, *out_node, *out_c0, *out_c1, *bnd_var, *lvl_sep, *lvl_out, *cell_edge;
+struct Tmpl {  // views into the shared-memory copy of a packed template (layout: sweep_plan.cpp pack_template)
+  int n_levels, n_int, n_rootb, zl_size, w, h, scratch;
+  const uint16_t *var_code, *sep_c0, *sep_c1, *out_rf, *out_sb, *out_v, *out_c0, *out_c1, *lvl_sep, *lvl_out,
+      *cell_edge, *row_off, *row_len, *row_w, *gl_lvl, *gl_src, *tpo;
   __device__ __forceinline__ explicit Tmpl(const uint16_t *tb) {
     const int *h32 = reinterpret_cast<const int *>(tb);
-    n_nodes = h32[0]; n_levels = h32[1]; n_int = h32[2]; n_rootb = h32[3]; zl_size = h32[4]; rf_size = h32[5];
-    rb_size = h32[6]; w = h32[7]; h = h32[8];
-    node_s = tb + h32[10]; node_b = tb + h32[11]; node_rf = tb + h32[12]; node_rb = tb + h32[13];
-    node_sep = tb + h32[14]; node_bnd = tb + h32[15]; node_zl = tb + h32[16]; var_code = tb + h32[17];
-    rootb_code = tb + h32[18]; sep_node = tb + h32[19]; sep_c0 = tb + h32[20]; sep_c1 = tb + h32[21];
-    out_node = tb + h32[22]; out_c0 = tb + h32[23]; out_c1 = tb + h32[24]; bnd_var = tb + h32[25];
-    lvl_sep = tb + h32[26]; lvl_out = tb + h32[27]; cell_edge = tb + h32[28];
+    n_levels = h32[1]; n_int = h32[2]; n_rootb = h32[3]; zl_size = h32[4]; w = h32[7]; h = h32[8]; scratch = h32[27];
+    var_code = tb + h32[10]; sep_c0 = tb + h32[11]; sep_c1 = tb + h32[12]; out_rf = tb + h32[13];
+    out_sb = tb + h32[14]; out_v = tb + h32[15]; out_c0 = tb + h32[16]; out_c1 = tb + h32[17];
+    lvl_sep = tb + h32[18]; lvl_out = tb + h32[19]; cell_edge = tb + h32[20]; row_off = tb + h32[21];
+    row_len = tb + h32[22]; row_w = tb + h32[23]; gl_lvl = tb + h32[24]; gl_src = tb + h32[25]; tpo = tb + h32[26];
   }
 };
 
@@ -148,16 +152,6 @@ __device__ __forceinline__ int64_t sweep_dof(const SweepArgs &a, int I0, int J0,
   const int type = code >> 14, dj = (code >> 7) & 127, di = code & 127;
   const int64_t canon = type == 0 ? int64_t(J0 + dj) * (a.nx + 1) + I0 + di : a.nxe + int64_t(J0 + dj) * a.nx + I0 + di;
   return a.dof_of_canon ? int64_t(a.dof_of_canon[canon]) : canon;
-}
-
-__device__ __forceinline__ void bar_wait_prof(uint64_t *bar, uint32_t parity, const SweepArgs &a, int cta, int tid) {
-  if (a.prof && tid == 0) {
-    const long long t0 = clock64();
-    bar_wait(bar, parity, a.abort_flag);
-    a.prof[cta * 8 + 5] += clock64() - t0;
-  } else {
-    bar_wait(bar, parity, a.abort_flag);
-  }
 }
 
 }  // namespace
@@ -168,15 +162,16 @@ __device__ __forceinline__ void bar_wait_prof(uint64_t *bar, uint32_t parity, co
 template <int M>
 __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
   extern __shared__ __align__(128) double sm[];
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sm);
-  SweepEntry *ebuf = reinterpret_cast<SweepEntry *>(sm + SWEEP_NBAR);  // two staged entries
-  double *red = sm + SWEEP_NBAR + 32;
-  uint16_t *tb = reinterpret_cast<uint16_t *>(red + SWEEP_THREADS * M);
-  double *ws = red + SWEEP_THREADS * M + a.tmpl_dbl;
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(sm);  // TMA data of the entry landed
+  uint64_t *done_bar = full_bar + NB;                     // all compute warps finished the entry
+  uint64_t *dep_bar = done_bar + NB;                      // descriptor staged, dependencies satisfied
+  SweepEntry *edesc = reinterpret_cast<SweepEntry *>(sm + 3 * NB);
+  double *red = sm + 19 * NB;                             // two reduction buffers
+  uint16_t *tb = reinterpret_cast<uint16_t *>(red + 2 * CT * M);
+  double *ws = red + 2 * CT * M + a.tmpl_dbl;
   double *ring = ws + a.ws_dbl;
-  __shared__ int cur_tmpl;
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x;
   const int e_first = a.cta_begin[cta];
   const int P = a.cta_begin[cta + 1] - e_first;
@@ -185,38 +180,140 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
   const SweepIssue *iss = a.issue + e_first;
   const long long total = (long long)P * a.n_steps;
 
-  uint64_t policy = 0;
-  if (a.evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(policy));
-
   if (tid == 0) {
-    for (int k = 0; k < SWEEP_NBAR; ++k) bar_init(bars + k);
+    for (int k = 0; k < NB; ++k) {
+      bar_init(full_bar + k, 1);
+      bar_init(done_bar + k, CT / 32);
+      bar_init(dep_bar + k, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    cur_tmpl = -1;
   }
-  if (tid < 32) reinterpret_cast<int *>(&ebuf[0])[tid] = reinterpret_cast<const int *>(&ents[0])[tid];
   __syncthreads();
 
-  // ---- TMA issue state (thread 0 only) ----
-  long long issued = 0;
-  int issue_i = 0;  // issued % P
-  auto issue_one = [&](int64_t src, int32_t n_dbl, int32_t ring_off) {
-    uint64_t *ib = bars + (issued % SWEEP_NBAR);
-    if (n_dbl > 0) tma_issue(ring + ring_off, a.Rs + src, uint32_t(n_dbl) * 8u, ib, a.evict_first != 0, policy);
-    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(s_u32(ib)) : "memory");  // keeps the phase count
-    ++issued;
-    if (++issue_i == P) issue_i = 0;
-  };
-  if (tid == 0) {
-    long long target = a.cta_prologue[cta];
-    if (target > total) target = total;
-    while (issued < target) {
-      const SweepIssue s = iss[issue_i];
-      issue_one(s.src, s.n_dbl, s.ring_off);
+  if (warp == CT / 32) {
+    // =============================================================================================================
+    // RETIRE warp: completion -> release counter -> free ring space -> next TMA copies
+    // =============================================================================================================
+    if (lane != 0) return;
+    uint64_t policy = 0;
+    if (a.evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(policy));
+    long long issued = 0;
+    int issue_i = 0;
+    auto issue_one = [&](const SweepIssue &s) {
+      uint64_t *fb = full_bar + (issued % NB);
+      const uint32_t bytes = uint32_t(s.n[0] + s.n[1] + s.n[2] + s.n[3]) * 8u;
+      if (bytes == 0) {
+        bar_arrive(fb);  // keeps the phase count
+      } else {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(s_u32(fb)), "r"(bytes) : "memory");
+        double *dst = ring + s.ring_off;
+#pragma unroll
+        for (int t = 0; t < SWEEP_SEGS; ++t) {
+          if (s.n[t] <= 0) continue;
+          const double *base = s.kind[t] == SRC_FACTOR ? a.Rs
+                               : s.kind[t] == SRC_INDEX ? reinterpret_cast<const double *>(a.index)
+                               : s.kind[t] == SRC_XI    ? a.xi
+                                                        : a.ptil;
+          const char *src = reinterpret_cast<const char *>(base + s.off[t]);
+          const bool hint = a.evict_first && s.kind[t] == SRC_FACTOR;
+          uint32_t left = uint32_t(s.n[t]) * 8u, done = 0;
+          while (left > 0) {
+            const uint32_t n = left < 32768u ? left : 32768u;
+            if (hint)
+              asm volatile(
+                  "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::
+                      "r"(s_u32(reinterpret_cast<char *>(dst) + done)),
+                  "l"(src + done), "r"(n), "r"(s_u32(fb)), "l"(policy)
+                  : "memory");
+            else
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                               s_u32(reinterpret_cast<char *>(dst) + done)),
+                           "l"(src + done), "r"(n), "r"(s_u32(fb))
+                           : "memory");
+            done += n;
+            left -= n;
+          }
+          dst += s.n[t];
+        }
+      }
+      ++issued;
+      if (++issue_i == P) issue_i = 0;
+    };
+    {
+      long long target = a.cta_prologue[cta];
+      if (target > total) target = total;
+      while (issued < target) issue_one(iss[issue_i]);
     }
+    SweepIssue nxt;
+    long long nxt_for = -1;
+    long long G = 0;
+    for (int step = 0; step < a.n_steps; ++step)
+      for (int i = 0; i < P; ++i, ++G) {
+        // what this entry's retirement needs, fetched while the compute warps work on it
+        const int flags = ents[i].flags, sig = ents[i].sig, upto_rel = ents[i].issue_upto;
+        if (nxt_for != issued && issued < total) {
+          nxt = iss[issue_i];
+          nxt_for = issued;
+        }
+        bar_wait(done_bar + (G % NB), uint32_t((G / NB) & 1), a.abort_flag);
+        if ((flags & SWF_LAST) && sig >= 0) {
+          __threadfence();
+          red_release(a.cnt + sig);
+        }
+        long long target = (long long)step * P + upto_rel;
+        if (target > total) target = total;
+        while (issued < target) {
+          if (nxt_for != issued) {
+            nxt = iss[issue_i];
+            nxt_for = issued;
+          }
+          issue_one(nxt);
+        }
+      }
+    return;
   }
 
+  if (warp == CT / 32 + 1) {
+    // =============================================================================================================
+    // DEPENDENCY warp: stages descriptors up to NB entries ahead and waits for the producers of other CTAs
+    // =============================================================================================================
+    int nxt = reinterpret_cast<const int *>(&ents[0])[lane];
+    long long G = 0;
+    for (int step = 0; step < a.n_steps; ++step)
+      for (int i = 0; i < P; ++i, ++G) {
+        const int slot = int(G % NB);
+        const int cur = nxt;
+        {
+          const int inext = (i + 1 == P) ? 0 : i + 1;
+          nxt = reinterpret_cast<const int *>(&ents[inext])[lane];
+        }
+        if (G >= NB) {  // the slot's previous user must be finished by every compute warp
+          if (lane == 0) bar_wait(done_bar + slot, uint32_t(((G / NB) - 1) & 1), a.abort_flag);
+          __syncwarp();
+        }
+        reinterpret_cast<int *>(&edesc[slot])[lane] = cur;
+        __syncwarp();
+        if (lane == 0) {
+          const SweepEntry &e = edesc[slot];
+          const bool waits = e.kind == SW_SUB_BWD || ((e.kind == SW_TOP_FWD || e.kind == SW_TOP_BWD) && (e.flags & SWF_NEW_RUN));
+          if (waits) {
+            const long long t0 = a.prof ? clock64() : 0;
+            if (e.dep0 >= 0) wait_counter(a.cnt + e.dep0, uint32_t(step + 1) * uint32_t(e.dep0_n), a.abort_flag);
+            if (e.dep1 >= 0) wait_counter(a.cnt + e.dep1, uint32_t(step + 1) * uint32_t(e.dep1_n), a.abort_flag);
+            if (a.prof) a.prof[cta * 8 + 4] += clock64() - t0;
+          }
+          bar_arrive(dep_bar + slot);
+        }
+        __syncwarp();
+      }
+    return;
+  }
+
+  // ===============================================================================================================
+  // COMPUTE warps
+  // ===============================================================================================================
   double acc[M], pass[M];
-  int out_dof = -1;
+  int out_dof = -1, cur_tmpl = -1, nlast = 0;
 #pragma unroll
   for (int j = 0; j < M; ++j) acc[j] = pass[j] = 0.0;
 
@@ -224,16 +321,21 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
   for (int step = 0; step < a.n_steps; ++step) {
     const int level = a.level0 + step;
     for (int i = 0; i < P; ++i, ++G) {
-      const SweepEntry &e = ebuf[G & 1];
-      int pre = 0;
-      if (tid >= 32 && tid < 64) {
-        const int inext = (i + 1 == P) ? 0 : i + 1;
-        pre = reinterpret_cast<const int *>(&ents[inext])[tid - 32];
-      }
+      const int slot = int(G % NB);
+      const uint32_t parity = uint32_t((G / NB) & 1);
+      long long t_entry = 0, t_w = 0;
+      if (a.prof && tid == 0) t_entry = clock64();
+      bar_wait(dep_bar + slot, parity, a.abort_flag);
+      if (a.prof && tid == 0) t_w = clock64();
+      const SweepEntry &e = edesc[slot];
       const int kind = e.kind, flags = e.flags;
-      const long long t_entry = (a.prof && tid == 0) ? clock64() : 0;
-      const uint32_t parity = uint32_t((G / SWEEP_NBAR) & 1);
-      uint64_t *bar = bars + (G % SWEEP_NBAR);
+      const double *reg = ring + e.ring_off;
+      bar_wait(full_bar + slot, parity, a.abort_flag);
+      if (a.prof && tid == 0) {
+        const long long t = clock64();
+        a.prof[cta * 8 + 7] += t_w - t_entry;  // waiting for the dependency warp
+        a.prof[cta * 8 + 5] += t - t_w;        // waiting for TMA data
+      }
 
       if (kind == SW_TOP_FWD || kind == SW_TOP_BWD) {
         // ---------------------------------------------------------------------------------------------------------
@@ -242,30 +344,26 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
         const bool fwd = kind == SW_TOP_FWD;
         const int s = e.a4, b = e.a5, f = s + b;
         const int cw = e.a1, col0 = e.a0;  // cw: power of two below 32, any even width from 32 to 256
+        const int *gl = reinterpret_cast<const int *>(reg);
+        const int *cl = reinterpret_cast<const int *>(reg + e.n[0]);
+        const double *tile = reg + e.n[0] + e.n[1];
         if (flags & SWF_NEW_RUN) {
-          if (tid == 0) {
-            const long long t0 = a.prof ? clock64() : 0;
-            if (e.dep0 >= 0) wait_counter(a.cnt + e.dep0, uint32_t(step + 1) * uint32_t(e.dep0_n), a.abort_flag);
-            if (e.dep1 >= 0) wait_counter(a.cnt + e.dep1, uint32_t(step + 1) * uint32_t(e.dep1_n), a.abort_flag);
-            if (a.prof) a.prof[cta * 8 + 4] += clock64() - t0;
-          }
-          __syncthreads();
+          csync();  // every warp is done with the previous run's vector
           if (fwd) {
             // v = rhs of the separator dofs + children contributions (assemble_rhs_star fused: rhs = -K_up p_old)
             const double k0 = e.a6 ? a.ky0 : a.kx0, k1 = e.a6 ? a.ky1 : a.kx1;
-            for (int p = tid; p < s; p += SWEEP_THREADS) {
-              const int2 cc = a.top_cell[e.o0 + p];
+            for (int p = tid; p < s; p += CT) {
+              const int4 gi = reinterpret_cast<const int4 *>(gl)[p];
               double val[M];
 #pragma unroll
               for (int j = 0; j < M; ++j)
-                val[j] = -(k0 * __ldcg(a.ptil + int64_t(cc.x) * M + j) + k1 * __ldcg(a.ptil + int64_t(cc.y) * M + j));
-              const int q0 = a.src[e.o1 + p], q1 = a.src[e.o1 + f + p];
-              if (q0 >= 0 && e.o4 >= 0)
+                val[j] = -(k0 * __ldcg(a.ptil + int64_t(gi.x) * M + j) + k1 * __ldcg(a.ptil + int64_t(gi.y) * M + j));
+              if (gi.z >= 0)
 #pragma unroll
-                for (int j = 0; j < M; ++j) val[j] += __ldcg(a.z + int64_t(e.o4 + q0) * M + j);
-              if (q1 >= 0 && e.o5 >= 0)
+                for (int j = 0; j < M; ++j) val[j] += __ldcg(a.z + int64_t(gi.z) * M + j);
+              if (gi.w >= 0)
 #pragma unroll
-                for (int j = 0; j < M; ++j) val[j] += __ldcg(a.z + int64_t(e.o5 + q1) * M + j);
+                for (int j = 0; j < M; ++j) val[j] += __ldcg(a.z + int64_t(gi.w) * M + j);
 #pragma unroll
               for (int j = 0; j < M; ++j) ws[p * M + j] = val[j];
               if (flags & SWF_WRITE_ZS)
@@ -274,57 +372,53 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
             }
           } else {
             // w = [accumulated separator rhs ; solution of the boundary dofs (ancestors' separators)]
-            for (int p = tid; p < f; p += SWEEP_THREADS) {
+            for (int p = tid; p < f; p += CT) {
               if (p < s) {
 #pragma unroll
                 for (int j = 0; j < M; ++j) ws[p * M + j] = __ldcg(a.z + int64_t(e.o2 + p) * M + j);
               } else {
-                const int64_t d = a.idx_user[e.o0 + p];
+                const int64_t d = gl[p - s];
 #pragma unroll
                 for (int j = 0; j < M; ++j) ws[p * M + j] = __ldcg(a.x + d * M + j);
               }
             }
           }
-          __syncthreads();
+          csync();
         }
         if (flags & SWF_FIRST) {
 #pragma unroll
           for (int j = 0; j < M; ++j) acc[j] = pass[j] = 0.0;
           out_dof = -1;
-          if (tid < cw) {
+          if (tid < cw && e.n[1] > 0) {
+            const int2 ci = reinterpret_cast<const int2 *>(cl)[tid];
             if (fwd) {  // pass-through of the children's contributions to this boundary dof
-              const int q = col0 + tid;
-              if (q < b) {
-                const int q0 = a.src[e.o1 + s + q], q1 = a.src[e.o1 + f + s + q];
-                if (q0 >= 0 && e.o4 >= 0)
+              if (ci.x >= 0)
 #pragma unroll
-                  for (int j = 0; j < M; ++j) pass[j] += __ldcg(a.z + int64_t(e.o4 + q0) * M + j);
-                if (q1 >= 0 && e.o5 >= 0)
+                for (int j = 0; j < M; ++j) pass[j] += __ldcg(a.z + int64_t(ci.x) * M + j);
+              if (ci.y >= 0)
 #pragma unroll
-                  for (int j = 0; j < M; ++j) pass[j] += __ldcg(a.z + int64_t(e.o5 + q1) * M + j);
-              }
-            } else if (col0 + tid < s) {
-              out_dof = a.idx_user[e.o0 + col0 + tid];
+                for (int j = 0; j < M; ++j) pass[j] += __ldcg(a.z + int64_t(ci.y) * M + j);
+            } else {
+              out_dof = ci.x;
             }
           }
         }
-        if (e.n_dbl > 0) {
-          bar_wait_prof(bar, parity, a, cta, tid);
-          const int g = tid / cw, col = tid - g * cw, gn = SWEEP_THREADS / cw;
+        if (e.n[2] > 0) {
+          const int g = tid / cw, col = tid - g * cw, gn = CT / cw;
           if (g < gn) {
-            const double *tile = ring + e.ring_off + col;
+            const double *tl = tile + col;
             const int r_beg = e.a2, r_end = e.a3;
             int r = r_beg + g;
             for (; r + 3 * gn < r_end; r += 4 * gn) {
-              const double m0 = tile[(r - r_beg) * cw], m1 = tile[(r + gn - r_beg) * cw];
-              const double m2 = tile[(r + 2 * gn - r_beg) * cw], m3 = tile[(r + 3 * gn - r_beg) * cw];
+              const double m0 = tl[(r - r_beg) * cw], m1 = tl[(r + gn - r_beg) * cw];
+              const double m2 = tl[(r + 2 * gn - r_beg) * cw], m3 = tl[(r + 3 * gn - r_beg) * cw];
 #pragma unroll
               for (int j = 0; j < M; ++j)
                 acc[j] += m0 * ws[r * M + j] + m1 * ws[(r + gn) * M + j] + m2 * ws[(r + 2 * gn) * M + j] +
                           m3 * ws[(r + 3 * gn) * M + j];
             }
             for (; r < r_end; r += gn) {
-              const double m0 = tile[(r - r_beg) * cw];
+              const double m0 = tl[(r - r_beg) * cw];
 #pragma unroll
               for (int j = 0; j < M; ++j) acc[j] += m0 * ws[r * M + j];
             }
@@ -335,17 +429,19 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
             for (int off = 16; off >= cw; off >>= 1)
 #pragma unroll
               for (int j = 0; j < M; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+          double *rb = red + (nlast & 1) * CT * M;  // double buffered: one barrier per block is enough
+          ++nlast;
 #pragma unroll
-          for (int j = 0; j < M; ++j) red[tid * M + j] = acc[j];
-          __syncthreads();
+          for (int j = 0; j < M; ++j) rb[tid * M + j] = acc[j];
+          csync();
           if (tid < cw) {
             const int stride = cw < 32 ? 32 : cw;
             double tot[M];
 #pragma unroll
             for (int j = 0; j < M; ++j) tot[j] = 0.0;
-            for (int t = tid; t < SWEEP_THREADS; t += stride)
+            for (int t = tid; t < CT; t += stride)
 #pragma unroll
-              for (int j = 0; j < M; ++j) tot[j] += red[t * M + j];
+              for (int j = 0; j < M; ++j) tot[j] += rb[t * M + j];
             if (fwd) {
               const int q = col0 + tid;
               if (q < b)
@@ -366,32 +462,27 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
         }
       } else {
         // ---------------------------------------------------------------------------------------------------------
-        // subtree: the whole factor blob of the box is in the ring; walk its levels in shared memory
+        // subtree: factor blob, index lists and this CTA's own vectors are in the ring; walk the levels on chip
         // ---------------------------------------------------------------------------------------------------------
-        if (e.a0 != cur_tmpl) {  // uniform branch: cur_tmpl only changes behind the barrier below
+        csync();  // every warp is done with the workspace (and the template) of the previous entry
+        if (e.a0 != cur_tmpl) {
           const int64_t off = a.tmpl_off[e.a0];
           const int n16 = reinterpret_cast<const int *>(a.tmpl16 + off)[9];
           const int4 *g4 = reinterpret_cast<const int4 *>(a.tmpl16 + off);
           int4 *s4 = reinterpret_cast<int4 *>(tb);
-          for (int k = tid; k < (n16 + 7) / 8; k += SWEEP_THREADS) s4[k] = g4[k];
-          __syncthreads();
-          if (tid == 0) cur_tmpl = e.a0;
+          for (int k = tid; k < (n16 + 7) / 8; k += CT) s4[k] = g4[k];
+          cur_tmpl = e.a0;
+          csync();
         }
         const Tmpl T(tb);
         const int I0 = e.a2, J0 = e.a3, bq = e.a1;
         const int ncell = T.w * T.h;
-        double *pc = ws;
+        const double *blob = reg;
+        const double *pc = reg + e.n[0] + e.n[1] + e.n[2];  // pressures of the box (this CTA wrote them last step)
         if (kind == SW_SUB_FWD) {
-          double *vs = pc + ncell * M;
+          double *vs = ws;
           double *zl = vs + T.n_int * M;
-          for (int c = tid; c < ncell; c += SWEEP_THREADS) {
-            const int dj = c / T.w, di = c - dj * T.w;
-            const int64_t cell = int64_t(J0 + dj) * a.nx + I0 + di;
-#pragma unroll
-            for (int j = 0; j < M; ++j) pc[c * M + j] = __ldcg(a.ptil + cell * M + j);
-          }
-          __syncthreads();
-          for (int l = tid; l < T.n_int; l += SWEEP_THREADS) {
+          for (int l = tid; l < T.n_int; l += CT) {
             const int code = T.var_code[l];
             const int type = code >> 14, dj = (code >> 7) & 127, di = code & 127;
             double val[M];
@@ -419,12 +510,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
 #pragma unroll
             for (int j = 0; j < M; ++j) vs[l * M + j] = val[j];
           }
-          if (e.n_dbl > 0) bar_wait_prof(bar, parity, a, cta, tid);
-          __syncthreads();
-          const double *blob = ring + e.ring_off;
+          csync();
           for (int lv = 0; lv < T.n_levels; ++lv) {
             if (lv > 0) {  // leaves have no children
-              for (int v = T.lvl_sep[lv] + tid; v < T.lvl_sep[lv + 1]; v += SWEEP_THREADS) {
+              for (int v = T.lvl_sep[lv] + tid; v < T.lvl_sep[lv + 1]; v += CT) {
                 const int c0 = t16(T.sep_c0, v), c1 = t16(T.sep_c1, v);
 #pragma unroll
                 for (int j = 0; j < M; ++j) {
@@ -434,13 +523,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
                   vs[v * M + j] = val;
                 }
               }
-              __syncthreads();
+              csync();
             }
-            for (int o = T.lvl_out[lv] + tid; o < T.lvl_out[lv + 1]; o += SWEEP_THREADS) {
-              const int n = T.out_node[o];
-              const int s = T.node_s[n], b = T.node_b[n];
-              const double *rf = blob + T.node_rf[n] + (o - T.node_zl[n]);
-              const double *v = vs + int(T.node_sep[n]) * M;
+            for (int o = T.lvl_out[lv] + tid; o < T.lvl_out[lv + 1]; o += CT) {
+              const int sb = T.out_sb[o], s = sb >> 8, b = sb & 255;
+              const double *rf = blob + T.out_rf[o];
+              const double *v = vs + int(T.out_v[o]) * M;
               const int c0 = t16(T.out_c0, o), c1 = t16(T.out_c1, o);
               double av[M];
 #pragma unroll
@@ -449,6 +537,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
                 if (c0 >= 0) av[j] += zl[c0 * M + j];
                 if (c1 >= 0) av[j] += zl[c1 * M + j];
               }
+#pragma unroll 4
               for (int k = 0; k < s; ++k) {
                 const double r = rf[k * b];
 #pragma unroll
@@ -457,69 +546,74 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
 #pragma unroll
               for (int j = 0; j < M; ++j) zl[o * M + j] = av[j];
             }
-            __syncthreads();
+            csync();
           }
-          for (int l = tid; l < T.n_int * M; l += SWEEP_THREADS) a.xi[int64_t(e.o1) * M + l] = vs[l];
-          const int zr = T.node_zl[T.n_nodes - 1];
-          for (int q = tid; q < T.n_rootb * M; q += SWEEP_THREADS) a.z[int64_t(e.o0) * M + q] = zl[zr * M + q];
+          for (int l = tid; l < T.n_int * M; l += CT) a.xi[int64_t(e.o1) * M + l] = vs[l];
+          const int zr = T.zl_size - T.n_rootb;  // the root is the last node
+          for (int q = tid; q < T.n_rootb * M; q += CT) a.z[int64_t(e.o0) * M + q] = zl[zr * M + q];
+          fence_async_global();  // xi is streamed back by TMA in the backward entry
         } else {
-          double *zs = pc + ncell * M;        // accumulated right-hand sides of the interior variables
-          double *xs = zs + T.n_int * M;      // solution: [interior | root boundary]
-          for (int l = tid; l < T.n_int * M; l += SWEEP_THREADS) zs[l] = __ldcg(a.xi + int64_t(e.o1) * M + l);
-          for (int c = tid; c < ncell; c += SWEEP_THREADS) {
-            const int dj = c / T.w, di = c - dj * T.w;
-            const int64_t cell = int64_t(J0 + dj) * a.nx + I0 + di;
-#pragma unroll
-            for (int j = 0; j < M; ++j) pc[c * M + j] = __ldcg(a.ptil + cell * M + j);
-          }
-          if (tid == 0 && e.dep0 >= 0) {
-            const long long t0 = a.prof ? clock64() : 0;
-            wait_counter(a.cnt + e.dep0, uint32_t(step + 1) * uint32_t(e.dep0_n), a.abort_flag);
-            if (a.prof) a.prof[cta * 8 + 4] += clock64() - t0;
-          }
-          __syncthreads();
-          for (int q = tid; q < T.n_rootb; q += SWEEP_THREADS) {
-            const int64_t d = sweep_dof(a, I0, J0, T.rootb_code[q]);
+          const int *xb = reinterpret_cast<const int *>(reg + e.n[0]);
+          const double *zs = reg + e.n[0] + e.n[1];  // accumulated right-hand sides of the interior variables
+          double *xs = ws;                          // solution: [interior | root boundary]
+          double *scr = xs + (T.n_int + T.n_rootb) * M;
+          for (int q = tid; q < T.n_rootb; q += CT) {
+            const int64_t d = xb[q];
 #pragma unroll
             for (int j = 0; j < M; ++j) xs[(T.n_int + q) * M + j] = __ldcg(a.x + d * M + j);
           }
-          if (e.n_dbl > 0) bar_wait_prof(bar, parity, a, cta, tid);
-          __syncthreads();
-          const double *blob = ring + e.ring_off;
+          csync();
           for (int lv = T.n_levels - 1; lv >= 0; --lv) {
-            for (int v = T.lvl_sep[lv] + tid; v < T.lvl_sep[lv + 1]; v += SWEEP_THREADS) {
-              const int n = T.sep_node[v];
-              const int s = T.node_s[n], b = T.node_b[n], sep0 = T.node_sep[n];
-              const double *rb = blob + T.node_rb[n] + (v - sep0);  // R^T[p][i] at p * s + i
-              const uint16_t *bv = T.bnd_var + T.node_bnd[n];
+            // input vectors [z_s ; x_b] of the level's fronts
+            const int g0 = T.gl_lvl[lv], g1 = T.gl_lvl[lv + 1];
+            for (int k = g0 + tid; k < g1; k += CT) {
+              const int sidx = T.gl_src[k];
+              const double *from = (sidx & 0x8000) ? xs + (sidx & 0x7fff) * M : zs + sidx * M;
+#pragma unroll
+              for (int j = 0; j < M; ++j) scr[(k - g0) * M + j] = from[j];
+            }
+            csync();
+            // x_s = [F11^-1 | -G^T] [z_s ; x_b]: tpo lanes per row, rows of the level side by side
+            const int tpo = T.tpo[lv], per = CT / tpo;
+            const int grp = tid / tpo, rl = tid - grp * tpo;
+            const int v0 = T.lvl_sep[lv], n_out = T.lvl_sep[lv + 1] - v0;
+            for (int o0 = 0; o0 < n_out; o0 += per) {
+              const int o = o0 + grp;
               double av[M];
 #pragma unroll
               for (int j = 0; j < M; ++j) av[j] = 0.0;
-              for (int p = 0; p < s; ++p) {
-                const double r = rb[p * s];
+              if (o < n_out) {
+                const int v = v0 + o;
+                const double *row = blob + T.row_off[v];
+                const double *w = scr + int(T.row_w[v]) * M;
+                const int len = T.row_len[v];
+#pragma unroll 4
+                for (int p = rl; p < len; p += tpo) {
+                  const double r = row[p];
 #pragma unroll
-                for (int j = 0; j < M; ++j) av[j] += r * zs[(sep0 + p) * M + j];
+                  for (int j = 0; j < M; ++j) av[j] += r * w[p * M + j];
+                }
               }
-              rb += s * s;
-              for (int q = 0; q < b; ++q) {
-                const double r = rb[q * s];
-                const int l = bv[q];
+              for (int off = tpo >> 1; off > 0; off >>= 1)
 #pragma unroll
-                for (int j = 0; j < M; ++j) av[j] += r * xs[l * M + j];
-              }
+                for (int j = 0; j < M; ++j) av[j] += __shfl_xor_sync(0xffffffffu, av[j], off);
+              if (o < n_out && rl == 0)
 #pragma unroll
-              for (int j = 0; j < M; ++j) xs[v * M + j] = av[j];
+                for (int j = 0; j < M; ++j) xs[(v0 + o) * M + j] = av[j];
             }
-            __syncthreads();
+            csync();
           }
           // pressure recovery p = p_old - M^-1 K_pu u for the cells of the box; next right-hand side source
-          for (int c = tid; c < ncell; c += SWEEP_THREADS) {
-            const int dj = c / T.w, di = c - dj * T.w;
-            const int64_t cell = int64_t(J0 + dj) * a.nx + I0 + di;
+          for (int c = tid; c < ncell; c += CT) {
             const int el = T.cell_edge[4 * c], er = T.cell_edge[4 * c + 1], eb = T.cell_edge[4 * c + 2],
                       et = T.cell_edge[4 * c + 3];
-            const double mi = a.minv[cell];
-            const int64_t pidx = a.p_of_cell ? int64_t(a.p_of_cell[cell]) : cell;
+            const double mi = a.minv ? a.minv[e.o2 + c] : a.minv_const;
+            int64_t pidx = 0;
+            if (a.hist || a.has_src) {
+              const int dj = c / T.w, di = c - dj * T.w;
+              const int64_t cell = int64_t(J0 + dj) * a.nx + I0 + di;
+              pidx = a.p_of_cell ? int64_t(a.p_of_cell[cell]) : cell;
+            }
 #pragma unroll
             for (int j = 0; j < M; ++j) {
               const double div = a.cl * xs[el * M + j] + a.cr * xs[er * M + j] + a.cb * xs[eb * M + j] +
@@ -532,11 +626,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
               double nxt = p;
               if (a.has_src && a.src_next[j] && step + 1 < a.n_steps)
                 nxt += mi * a.src_next[j][int64_t(level + 1) * a.n_pressure + pidx];
-              a.ptil[cell * M + j] = nxt;
+              a.ptil[int64_t(e.o2 + c) * M + j] = nxt;
             }
           }
+          fence_async_global();  // the box pressures are streamed back by TMA in the next step
           if (bq >= 0) {  // subdom_to_st_distribute: flux traces of the interface dofs
-            for (int l = tid; l < T.n_int * M; l += SWEEP_THREADS) {
+            for (int l = tid; l < T.n_int * M; l += CT) {
               const int q = a.sub_q[bq + l];
               if (q >= 0) {
                 double *tp = a.bq_trace[q];
@@ -545,7 +640,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
             }
           }
           if (a.hist) {
-            for (int l = tid; l < T.n_int; l += SWEEP_THREADS) {
+            for (int l = tid; l < T.n_int; l += CT) {
               const int64_t d = sweep_dof(a, I0, J0, T.var_code[l]);
 #pragma unroll
               for (int j = 0; j < M; ++j)
@@ -558,31 +653,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
         }
       }
 
-      // ---- end of entry: stage the next descriptor, publish completion, release ring space --------------------
-      const int sig = (flags & SWF_LAST) ? e.sig : -1;
-      const long long upto = (long long)step * P + e.issue_upto;
-      const int64_t t_src = e.t_src;
-      const int32_t t_n = e.t_n_dbl, t_ro = e.t_ring_off;
-      if (tid >= 32 && tid < 64) reinterpret_cast<int *>(&ebuf[(G + 1) & 1])[tid - 32] = pre;
-      __syncthreads();
-      if (tid == 0) {
-        if (a.prof) {
-          a.prof[cta * 8 + kind] += clock64() - t_entry;
-          a.prof[cta * 8 + 6] += 1;
-        }
-        if (sig >= 0) {
-          __threadfence();
-          red_release(a.cnt + sig);
-        }
-        const long long target = upto < total ? upto : total;
-        if (issued < target) {
-          issue_one(t_src, t_n, t_ro);
-          while (issued < target) {
-            const SweepIssue s = iss[issue_i];
-            issue_one(s.src, s.n_dbl, s.ring_off);
-          }
-        }
+      // ---- end of entry: every warp reports on its own ----------------------------------------------------------
+      if (a.prof && tid == 0) {
+        a.prof[cta * 8 + kind] += clock64() - t_entry;
+        a.prof[cta * 8 + 6] += 1;
       }
+      __syncwarp();
+      if (lane == 0) bar_arrive(done_bar + slot);
     }
   }
 }
@@ -593,6 +670,8 @@ size_t sweep_smem_optin() {
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   return size_t(optin);
 }
+
+int sweep_fixed_dbl(int M) { return 19 * SWEEP_NBAR + 2 * SWEEP_COMPUTE * M; }
 
 template <int M>
 static int ctas_per_sm_t(size_t smem) {

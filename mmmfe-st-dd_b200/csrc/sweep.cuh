@@ -3,10 +3,15 @@
 // ONE cooperative launch.
 //
 //  * every CTA owns a static, ordered list of ENTRIES (a subtree, or a column block of one top-level front) that is
-//    identical for every time step; the factor bytes of an entry are contiguous in HBM ("sweep layout", built once
-//    by launch_repack) and are streamed into a shared-memory ring by TMA bulk copies (cp.async.bulk + mbarrier)
-//    that run several entries AHEAD of the arithmetic -- the loads do not depend on the right-hand side, so the
-//    HBM stream never stops at a tree level;
+//    identical for every time step.  Everything an entry reads that is known ahead of time -- its factor bytes
+//    ("sweep layout", contiguous per entry, built once by the repack kernels), its index lists, and the vectors this
+//    CTA itself produced earlier (subtree right-hand sides, the pressures of the box) -- is streamed into a
+//    shared-memory ring by TMA bulk copies (cp.async.bulk + mbarrier) that run several entries AHEAD of the
+//    arithmetic: the HBM stream never stops at a tree level;
+//  * warp-specialised: 8 compute warps, one RETIRE warp (publishes completions with release semantics, frees ring
+//    space, issues the next TMA copies) and one DEPENDENCY warp (stages entry descriptors, waits on the completion
+//    counters of other CTAs ahead of the compute warps).  Hand-offs are shared-memory mbarriers; the compute warps
+//    only ever synchronise among themselves (named barrier);
 //  * ordering between fronts is data flow: per-front completion counters in global memory (release/acquire), no
 //    grid-wide barrier anywhere, also not between time steps;
 //  * the RT0 structure of the saddle matrix (K_up = -+1, K_pu = +-dt, diagonal M) is exploited to fuse
@@ -19,36 +24,44 @@
 
 namespace mmmfe {
 
-constexpr int SWEEP_THREADS = 256;
-constexpr int SWEEP_NBAR = 8;       // mbarriers = most entries in flight per CTA
-constexpr int SWEEP_TMPL_HDR = 32;  // int32 header words of a packed subtree template
+constexpr int SWEEP_COMPUTE = 256;                 // compute threads (8 warps)
+constexpr int SWEEP_THREADS = SWEEP_COMPUTE + 64;  // + retire warp + dependency warp
+constexpr int SWEEP_NBAR = 16;                     // barrier slots = most entries in flight per CTA
+constexpr int SWEEP_TMPL_HDR = 48;                 // int32 header words of a packed subtree template
+constexpr int SWEEP_SEGS = 4;                      // TMA copies per entry
 
 enum SweepKind : int32_t { SW_SUB_FWD = 0, SW_TOP_FWD = 1, SW_TOP_BWD = 2, SW_SUB_BWD = 3 };
 enum SweepFlag : int32_t { SWF_FIRST = 1, SWF_LAST = 2, SWF_NEW_RUN = 4, SWF_WRITE_ZS = 8 };
+enum SweepSrc : int32_t { SRC_FACTOR = 0, SRC_INDEX = 1, SRC_XI = 2, SRC_PTIL = 3 };
 
-// One unit of work of one CTA (128 bytes, staged through shared memory one entry ahead).
-//   top entries  (column block [col0, col0 + cw) of a front, tile rows [r_beg, r_end)):
-//     a0 col0, a1 cw, a2 r_beg, a3 r_end, a4 s, a5 b, a6 separator type (0 x-edges, 1 y-edges)
-//     o0 idx_off, o1 src_off, o2 zs_off, o3 zc_off, o4 / o5 zc_off of child 0 / 1 (-1: none)
-//     FWD tile = -G^T (s x b), reduces over the s separator rows;  BWD tile = [F11^-1 ; -G] ((s+b) x s)
-//   subtree entries: a0 template, a1 boundary-entry table offset (-1: box touches no domain side), a2 I0, a3 J0,
-//     o0 zc_off (root boundary contributions), o1 xi_off (interior right-hand sides kept between the passes)
+// One unit of work of one CTA (128 bytes).  The ring region of an entry holds its segments back to back
+// (n[0..3] doubles each).
+//   top entries (column block [col0, col0 + cw) of a front, tile rows [r_beg, r_end)):
+//     a0 col0, a1 cw, a2 r_beg, a3 r_end, a4 s, a5 b, a6 separator type (0 x-edges, 1 y-edges), o2 zs_off, o3 zc_off
+//     segments: 0 gather list (first entry of a run), 1 column list (first chunk of a block), 2 tile
+//       FWD tile = -G^T (s x b), reduces over the s separator rows; gather list int4 {cell A, cell B, child-0 z,
+//       child-1 z} per separator row; column list int2 {child-0 z, child-1 z} per boundary column
+//       BWD tile = [F11^-1 ; -G] ((s+b) x s); gather list int {x dof} per boundary row; column list int2 {dof, -}
+//   subtree entries: a0 template, a1 boundary-entry table offset (-1: none), a2 I0, a3 J0, a7 instance,
+//     o0 zc_off (root boundary contributions), o1 xi_off, o2 ptil offset of the box (box-major cell order)
+//     segments: 0 factor blob, 1 root-boundary x dofs (BWD), 2 interior right-hand sides xi (BWD), 3 box pressures
 struct alignas(16) SweepEntry {
-  int32_t kind, flags, n_dbl, ring_off;
-  int32_t issue_upto, sig, dep0, dep0_n;  // sig: counter bumped on completion; dep: counter >= (step+1) * dep_n
-  int32_t dep1, dep1_n, a0, a1;
-  int32_t a2, a3, a4, a5;
-  int32_t a6, a7, o0, o1;
-  int32_t o2, o3, o4, o5;
-  int64_t src, t_src;              // factor offsets (doubles) of this entry / of the first entry it releases
-  int32_t t_n_dbl, t_ring_off, pad0, pad1;
+  int32_t kind, flags, ring_off, issue_upto;
+  int32_t sig, dep0, dep0_n, dep1;  // sig: counter bumped on completion; dep: counter >= (step+1) * dep_n
+  int32_t dep1_n, a0, a1, a2;
+  int32_t a3, a4, a5, a6;
+  int32_t a7, o0, o1, o2;
+  int32_t o3, n[SWEEP_SEGS], pad[7];
 };
 static_assert(sizeof(SweepEntry) == 128, "SweepEntry must be 128 bytes");
 
-struct SweepIssue {  // what the TMA issuer needs of an entry
-  int64_t src;
-  int32_t n_dbl, ring_off;
+struct alignas(16) SweepIssue {  // what the TMA issuer needs of an entry
+  int64_t off[SWEEP_SEGS];       // in doubles, relative to the base of the source
+  int32_t n[SWEEP_SEGS];         // doubles
+  int32_t kind[SWEEP_SEGS];      // SweepSrc
+  int32_t ring_off, pad[3];
 };
+static_assert(sizeof(SweepIssue) == 80, "SweepIssue must be 80 bytes");
 
 struct SweepArgs {
   const SweepEntry *entries;
@@ -56,20 +69,19 @@ struct SweepArgs {
   const int32_t *cta_begin;     // n_cta + 1
   const int32_t *cta_prologue;  // entries issued before the first one is processed
   const double *Rs;             // factor in sweep layout
-  const int32_t *idx_user;      // front variables -> user flux dof (separator first)
-  const int32_t *src;           // child gather maps
-  const int2 *top_cell;         // front variables -> the two canonical cells of the edge
+  const int32_t *index;         // static index lists (gather / column lists, root-boundary dofs)
   const uint16_t *tmpl16;       // packed subtree templates
   const int64_t *tmpl_off;      // per template, in uint16 units
   const int32_t *dof_of_canon;  // nullptr when the user numbering is canonical
   double *x;                    // [n_flux][M]   solution of top-level separator dofs
   double *z;                    // per-front vectors
   double *xi;                   // subtree-interior right-hand sides after the forward pass
-  double *ptil;                 // [cell][M] canonical cell order
+  double *ptil;                 // [cell][M], box-major cell order
   uint32_t *cnt;                // completion counters (2 per sweep node: forward, backward)
   volatile int *abort_flag;     // pinned host memory: set when a spin-wait gave up
-  long long *prof;              // optional [n_cta][8] cycle counters: per entry kind 0..3, 4 counter waits, 5 TMA waits
-  const double *minv;           // 1 / (c0 |cell|), canonical cell order
+  long long *prof;              // optional [n_cta][8] cycle counters
+  const double *minv;           // 1 / (c0 |cell|), box-major cell order; nullptr: minv_const everywhere
+  double minv_const;
   // boundary entries of the batch (interface dofs; in the bar problem also outer Dirichlet dofs)
   const int32_t *sub_q;            // per boundary subtree: [n_int][M] -> entry or -1
   const double *const *bq_data;    // entry -> right-hand-side data of level 0 (nullptr: none)
@@ -77,7 +89,7 @@ struct SweepArgs {
   const int32_t *bq_stride;        // entry -> stride per time level (data and trace)
   const double *bq_coef;           // rhs += coef * data[level * stride]
   // optional per-member arrays (bar / final sweeps), M pointers each, user numbering
-  const double *const *src_next;  // ptil_next += minv * src[(level+1) * n_pressure + cell]
+  const double *const *src_next;  // ptil_next += minv * src[(level+1) * n_pressure + p]
   double *const *hist;            // solution history [level][n_flux + n_pressure]
   const int32_t *p_of_cell;       // canonical cell -> user pressure index (nullptr: identity)
   int32_t hist_add, has_src;
@@ -100,9 +112,19 @@ struct RepackDesc {
 };
 void launch_repack(const RepackDesc *d_desc, int32_t n_desc, const double *R_old, double *Rs, cudaStream_t st);
 
+// Subtree blobs: forward blob copied, backward blob permuted (perm[k] = old position of new element k, per template)
+struct RepackSub {
+  int64_t old_rf, old_rb, new_rf, new_rb;
+  int32_t rf_size, rb_size, perm_off, pad;
+};
+void launch_repack_sub(const RepackSub *d_desc, int32_t n_desc, const int32_t *perm, const double *R_old, double *Rs,
+                       cudaStream_t st);
+
 size_t sweep_smem_optin();
 // resident CTAs per SM of the sweep kernel for this much dynamic shared memory
 int sweep_ctas_per_sm(int M, size_t smem_bytes);
+// fixed shared-memory doubles of the kernel besides template, workspace and ring
+int sweep_fixed_dbl(int M);
 // cooperative launch; returns the CUDA error code
 cudaError_t launch_sweep(int M, const SweepArgs &a, int32_t n_cta, size_t smem_bytes, cudaStream_t st);
 

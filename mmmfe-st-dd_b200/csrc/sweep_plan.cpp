@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <map>
 
 namespace mmmfe {
 
@@ -18,11 +19,15 @@ int32_t pow2_ceil(int64_t v) {
   while (p < v) p *= 2;
   return p;
 }
+int32_t even(int64_t v) { return int32_t((v + 1) & ~int64_t(1)); }
 
 char g_msg[256];
 
-// uint16 arrays of one template behind a 32-word int32 header (offsets in uint16 units from the blob start)
-const char *pack_template(const SubtreeTemplate &T, std::vector<uint16_t> &out) {
+// Template header (int32 words): 0 n_nodes, 1 n_levels, 2 n_int, 3 n_rootb, 4 zl_size, 5 rf_size, 6 rb_size, 7 w, 8 h,
+// 9 uint16 words in total, 27 scratch entries of the widest backward level; 10.. offsets (uint16 units from the blob
+// start) of: 10 var_code, 11 sep_c0, 12 sep_c1, 13 out_rf, 14 out_sb, 15 out_v, 16 out_c0, 17 out_c1, 18 lvl_sep,
+// 19 lvl_out, 20 cell_edge, 21 row_off, 22 row_len, 23 row_w, 24 gl_lvl, 25 gl_src, 26 tpo.
+const char *pack_template(const SubtreeTemplate &T, std::vector<uint16_t> &out, std::vector<int32_t> &perm) {
   if (T.w > 127 || T.h > 127) return "subtree box wider than 127 cells";
   const size_t base = out.size();
   out.resize(base + 2 * SWEEP_TMPL_HDR, 0);
@@ -30,20 +35,59 @@ const char *pack_template(const SubtreeTemplate &T, std::vector<uint16_t> &out) 
   hdr[0] = T.n_nodes; hdr[1] = T.n_levels; hdr[2] = T.n_int; hdr[3] = T.n_rootb; hdr[4] = T.zl_size;
   hdr[5] = T.rf_size; hdr[6] = T.rb_size; hdr[7] = T.w; hdr[8] = T.h;
   bool overflow = false;
-  auto put = [&](int slot, const std::vector<int32_t> &v, bool is_code) {
+  auto put = [&](int slot, const std::vector<int32_t> &v) {
     hdr[slot] = int32_t(out.size() - base);
-    for (int32_t x : v) {
-      int32_t y = x;
-      if (is_code) y = ((x >> 30) << 14) | (((x >> 15) & 0x7fff) << 7) | (x & 0x7fff);
+    for (int32_t y : v) {
       if (y < -1 || y >= 0xFFFF) overflow = true;
       out.push_back(y < 0 ? uint16_t(0xFFFF) : uint16_t(y));
     }
   };
-  put(10, T.node_s, false); put(11, T.node_b, false); put(12, T.node_rf, false); put(13, T.node_rb, false);
-  put(14, T.node_sep, false); put(15, T.node_bnd, false); put(16, T.node_zl, false); put(17, T.var_code, true);
-  put(18, T.rootb_code, true); put(19, T.sep_node, false); put(20, T.sep_c0, false); put(21, T.sep_c1, false);
-  put(22, T.out_node, false); put(23, T.out_c0, false); put(24, T.out_c1, false); put(25, T.bnd_var, false);
-  put(26, T.lvl_sep, false); put(27, T.lvl_out, false); put(28, T.cell_edge, false);
+  std::vector<int32_t> code(T.var_code.size());
+  for (size_t l = 0; l < code.size(); ++l) {
+    const int32_t x = T.var_code[l];
+    code[l] = ((x >> 30) << 14) | (((x >> 15) & 0x7fff) << 7) | (x & 0x7fff);
+  }
+  // forward: everything an output needs, indexed by the output itself
+  std::vector<int32_t> out_rf(T.zl_size), out_sb(T.zl_size), out_v(T.zl_size);
+  for (int32_t o = 0; o < T.zl_size; ++o) {
+    const int32_t n = T.out_node[o];
+    out_rf[o] = T.node_rf[n] + (o - T.node_zl[n]);
+    if (T.node_s[n] > 255 || T.node_b[n] > 255) overflow = true;
+    out_sb[o] = (T.node_s[n] << 8) | T.node_b[n];
+    out_v[o] = T.node_sep[n];
+  }
+  // backward: one row task per separator variable; per level a gather list builds the nodes' input vectors
+  std::vector<int32_t> row_off(T.n_int), row_len(T.n_int), row_w(T.n_int), gl_lvl, gl_src, tpo;
+  int32_t scratch_max = 0;
+  perm.assign(T.rb_size, 0);
+  for (int32_t k = 0; k < T.rb_size; ++k) perm[k] = k;
+  int32_t node = 0;
+  for (int32_t lv = 0; lv < T.n_levels; ++lv) {
+    gl_lvl.push_back(int32_t(gl_src.size()));
+    const int32_t lvl_begin = int32_t(gl_src.size());
+    while (node < T.n_nodes && T.node_sep[node] < T.lvl_sep[lv + 1]) {
+      const int32_t s = T.node_s[node], b = T.node_b[node], f = s + b, sep0 = T.node_sep[node];
+      const int32_t w_off = int32_t(gl_src.size()) - lvl_begin;
+      for (int32_t p = 0; p < s; ++p) gl_src.push_back(sep0 + p);
+      for (int32_t q = 0; q < b; ++q) gl_src.push_back(0x8000 | T.bnd_var[T.node_bnd[node] + q]);
+      for (int32_t i = 0; i < s; ++i) {
+        row_off[sep0 + i] = T.node_rb[node] + i * f;
+        row_len[sep0 + i] = f;
+        row_w[sep0 + i] = w_off;
+        for (int32_t p = 0; p < f; ++p) perm[T.node_rb[node] + i * f + p] = T.node_rb[node] + p * s + i;
+      }
+      ++node;
+    }
+    scratch_max = std::max(scratch_max, int32_t(gl_src.size()) - lvl_begin);
+    const int32_t n_out = T.lvl_sep[lv + 1] - T.lvl_sep[lv];
+    tpo.push_back(std::max(1, std::min(32, pow2_floor(std::max(1, SWEEP_COMPUTE / std::max(1, n_out))))));
+  }
+  gl_lvl.push_back(int32_t(gl_src.size()));
+  if (T.n_int + T.n_rootb >= 0x8000) overflow = true;
+  put(10, code); put(11, T.sep_c0); put(12, T.sep_c1); put(13, out_rf); put(14, out_sb); put(15, out_v);
+  put(16, T.out_c0); put(17, T.out_c1); put(18, T.lvl_sep); put(19, T.lvl_out); put(20, T.cell_edge);
+  put(21, row_off); put(22, row_len); put(23, row_w); put(24, gl_lvl); put(25, gl_src); put(26, tpo);
+  hdr[27] = scratch_max;
   while ((out.size() - base) % 8) out.push_back(0);  // 16-byte granules
   hdr[9] = int32_t(out.size() - base);
   std::memcpy(out.data() + base, hdr.data(), SWEEP_TMPL_HDR * sizeof(int32_t));
@@ -52,7 +96,9 @@ const char *pack_template(const SubtreeTemplate &T, std::vector<uint16_t> &out) 
 
 }  // namespace
 
-const char *build_sweep_layout(const NdTree &tr, int32_t n_cta, int32_t chunk_dbl, SweepLayout &L) {
+const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx_user,
+                               const std::vector<int32_t> &dof_of_canon, int32_t n_cta, int32_t chunk_dbl,
+                               SweepLayout &L) {
   L = SweepLayout();
   L.n_cta = n_cta;
   L.chunk_dbl = chunk_dbl;
@@ -60,6 +106,50 @@ const char *build_sweep_layout(const NdTree &tr, int32_t n_cta, int32_t chunk_db
   if (tr.instances.empty()) return "no subtrees (subtree_cells = 0)";
   if (tr.idx.size() >= (size_t(1) << 30) || tr.src.size() >= (size_t(1) << 31)) return "index structure beyond 32 bits";
   const int64_t nxe = int64_t(tr.nx + 1) * tr.ny;
+  auto user = [&](int64_t canon) { return dof_of_canon.empty() ? int32_t(canon) : dof_of_canon[canon]; };
+
+  // ---- templates, instances, box-major cell order ----
+  std::vector<int32_t> perm_off;
+  for (const auto &T : tr.templates) {
+    L.tmpl_off.push_back(int64_t(L.tmpl16.size()));
+    const size_t before = L.tmpl16.size();
+    std::vector<int32_t> perm;
+    if (const char *err = pack_template(T, L.tmpl16, perm)) return err;
+    L.tmpl16_max = std::max(L.tmpl16_max, int32_t(L.tmpl16.size() - before));
+    perm_off.push_back(int32_t(L.perm.size()));
+    L.perm.insert(L.perm.end(), perm.begin(), perm.end());
+    int32_t scratch;
+    std::memcpy(&scratch, L.tmpl16.data() + before + 2 * 27, sizeof scratch);
+    L.sub_ws_max = std::max(L.sub_ws_max, std::max(T.n_int + T.zl_size, T.n_int + T.n_rootb + scratch));
+  }
+  L.perm.push_back(0);
+  L.cell_box.assign(size_t(tr.nx) * tr.ny, -1);
+  L.inst.resize(tr.instances.size());
+  for (size_t k = 0; k < tr.instances.size(); ++k) {
+    const SubtreeInstance &in = tr.instances[k];
+    const SubtreeTemplate &T = tr.templates[in.tmpl];
+    SweepInstH &h = L.inst[k];
+    h.xi_off = int32_t(L.xi_total);
+    L.xi_total += even(T.n_int);
+    h.pb_off = int32_t(L.pb_total);
+    L.pb_total += even(int64_t(T.w) * T.h);
+    for (int dj = 0; dj < T.h; ++dj)
+      for (int di = 0; di < T.w; ++di) L.cell_box[size_t(in.J0 + dj) * tr.nx + in.I0 + di] = h.pb_off + dj * T.w + di;
+    h.xb = int64_t(L.index.size());
+    for (int32_t q = 0; q < T.n_rootb; ++q) {
+      const int32_t c = T.rootb_code[q];
+      const int type = c >> 30, dj = (c >> 15) & 0x7fff, di = c & 0x7fff;
+      const int64_t canon = type == 0 ? int64_t(in.J0 + dj) * (tr.nx + 1) + in.I0 + di
+                                      : nxe + int64_t(in.J0 + dj) * tr.nx + in.I0 + di;
+      L.index.push_back(user(canon));
+    }
+    while (L.index.size() % 4) L.index.push_back(0);
+  }
+  for (int32_t cb : L.cell_box)
+    if (cb < 0) return "a cell lies outside every subtree";
+  if (L.xi_total >= (int64_t(1) << 29) || L.pb_total >= (int64_t(1) << 29)) return "vector storage beyond 32 bits";
+
+  // ---- sweep nodes ----
   std::vector<int32_t> sid(nn, -1);
   for (int32_t i = 0; i < nn; ++i) {
     const NdNode &n = tr.nodes[i];
@@ -68,22 +158,18 @@ const char *build_sweep_layout(const NdTree &tr, int32_t n_cta, int32_t chunk_db
     sid[i] = int32_t(L.nodes.size());
     SweepNodeH h;
     h.old_id = i; h.s = n.s; h.b = n.b; h.height = n.height;
-    h.idx_off = int32_t(n.idx_off); h.src_off = int32_t(n.src_off);
     h.sep_type = tr.idx[n.idx_off] < nxe ? 0 : 1;
     L.nodes.push_back(h);
     L.f_max = std::max(L.f_max, n.s + n.b);
   }
   L.n_top = int32_t(L.nodes.size());
-  L.inst_xi.resize(tr.instances.size());
   for (size_t k = 0; k < tr.instances.size(); ++k) {
     const SubtreeInstance &in = tr.instances[k];
-    const SubtreeTemplate &T = tr.templates[in.tmpl];
     sid[in.root] = int32_t(L.nodes.size());
     SweepNodeH h;
-    h.old_id = in.root; h.s = 0; h.b = T.n_rootb; h.height = tr.nodes[in.root].height; h.n_fwd = 1; h.n_bwd = 1;
+    h.old_id = in.root; h.s = 0; h.b = tr.templates[in.tmpl].n_rootb; h.height = tr.nodes[in.root].height;
+    h.n_fwd = 1; h.n_bwd = 1;
     L.nodes.push_back(h);
-    L.inst_xi[k] = int32_t(L.xi_total);
-    L.xi_total += T.n_int;
   }
   for (auto &h : L.nodes) {
     const NdNode &n = tr.nodes[h.old_id];
@@ -98,31 +184,9 @@ const char *build_sweep_layout(const NdTree &tr, int32_t n_cta, int32_t chunk_db
     h.zc_off = int32_t(L.z_total);
     L.z_total += h.b;
   }
-  if (L.z_total >= (int64_t(1) << 30) || L.xi_total >= (int64_t(1) << 30)) return "vector storage beyond 32 bits";
+  if (L.z_total >= (int64_t(1) << 29)) return "vector storage beyond 32 bits";
 
-  // cells of the separator edges of the top fronts (right-hand side -K_up p_old is formed on the fly)
-  L.top_cell.assign(2 * tr.idx.size(), -1);
-  for (int32_t t = 0; t < L.n_top; ++t) {
-    const NdNode &n = tr.nodes[L.nodes[t].old_id];
-    for (int32_t p = 0; p < n.s; ++p) {
-      const int64_t v = tr.idx[n.idx_off + p];
-      int32_t c0, c1;
-      if (v < nxe) {
-        const int32_t j = int32_t(v / (tr.nx + 1)), i = int32_t(v % (tr.nx + 1));
-        if (i <= 0 || i >= tr.nx) return "separator edge on the domain boundary";
-        c0 = j * tr.nx + i - 1; c1 = j * tr.nx + i;
-      } else {
-        const int64_t k = v - nxe;
-        const int32_t j = int32_t(k / tr.nx), i = int32_t(k % tr.nx);
-        if (j <= 0 || j >= tr.ny) return "separator edge on the domain boundary";
-        c0 = (j - 1) * tr.nx + i; c1 = j * tr.nx + i;
-      }
-      L.top_cell[2 * (n.idx_off + p)] = c0;
-      L.top_cell[2 * (n.idx_off + p) + 1] = c1;
-    }
-  }
-
-  // ---- top items: column blocks, sized per level so that every CTA gets work ----
+  // ---- top items: column blocks, sized per level so that every CTA gets work; static index lists ----
   const size_t nh = tr.top_by_height.size();
   L.fwd.assign(nh, {});
   L.bwd.assign(nh, {});
@@ -142,20 +206,63 @@ const char *build_sweep_layout(const NdTree &tr, int32_t n_cta, int32_t chunk_db
         SweepNodeH &sn = L.nodes[sid[id]];
         const int32_t rlen = pass == 0 ? n.s : n.s + n.b;
         const int32_t ncols = pass == 0 ? n.b : n.s;
+        const int32_t f = n.s + n.b;
         auto &items = pass == 0 ? L.fwd[h] : L.bwd[h];
+        auto child_z = [&](int c, int32_t p) -> int32_t {
+          if (sn.child[c] < 0) return -1;
+          const int32_t q = tr.src[n.src_off + int64_t(c) * f + p];
+          return q < 0 ? -1 : L.nodes[sn.child[c]].zc_off + q;
+        };
+        if (pass == 0) {  // gather list of the run: cells of the separator edges and the children's contributions
+          sn.gl_f = int64_t(L.index.size());
+          for (int32_t p = 0; p < n.s; ++p) {
+            const int64_t v = tr.idx[n.idx_off + p];
+            int32_t c0, c1;
+            if (v < nxe) {
+              const int32_t j = int32_t(v / (tr.nx + 1)), i = int32_t(v % (tr.nx + 1));
+              if (i <= 0 || i >= tr.nx) return "separator edge on the domain boundary";
+              c0 = j * tr.nx + i - 1; c1 = j * tr.nx + i;
+            } else {
+              const int64_t k = v - nxe;
+              const int32_t j = int32_t(k / tr.nx), i = int32_t(k % tr.nx);
+              if (j <= 0 || j >= tr.ny) return "separator edge on the domain boundary";
+              c0 = (j - 1) * tr.nx + i; c1 = j * tr.nx + i;
+            }
+            L.index.push_back(L.cell_box[c0]); L.index.push_back(L.cell_box[c1]);
+            L.index.push_back(child_z(0, p)); L.index.push_back(child_z(1, p));
+          }
+        } else {
+          sn.gl_b = int64_t(L.index.size());
+          for (int32_t q = 0; q < n.b; ++q) L.index.push_back(idx_user[n.idx_off + n.s + q]);
+          while (L.index.size() % 4) L.index.push_back(0);
+        }
         if (ncols == 0) {  // root: forward entry that only accumulates the separator right-hand side
           items.push_back({SW_TOP_FWD, sid[id], 0, 2, 0, 0});
           sn.n_fwd = 1;
+          sn.cl_f = int64_t(L.index.size());
           continue;
         }
         // block width: a power of two below 32 (shuffle reduction), else any even width up to 256 with at most
         // one padded column per block
         const int64_t cap = std::max<int64_t>(2, std::min<int64_t>(256, target / rlen));
         int32_t cw;
-        if (cap >= ncols) cw = ncols >= 32 ? ((ncols + 1) & ~1) : std::max(2, pow2_ceil(ncols));
-        else if (cap >= 32) { const int32_t nb = int32_t((ncols + cap - 1) / cap); cw = (((ncols + nb - 1) / nb) + 1) & ~1; }
+        if (cap >= ncols) cw = ncols >= 32 ? even(ncols) : std::max(2, pow2_ceil(ncols));
+        else if (cap >= 32) { const int32_t nb = int32_t((ncols + cap - 1) / cap); cw = even((ncols + nb - 1) / nb); }
         else cw = pow2_floor(cap);
         const int32_t nblk = (ncols + cw - 1) / cw;
+        // column list, padded to whole blocks
+        (pass == 0 ? sn.cl_f : sn.cl_b) = int64_t(L.index.size());
+        (pass == 0 ? sn.cl_f_len : sn.cl_b_len) = nblk * cw;
+        for (int32_t c = 0; c < nblk * cw; ++c) {
+          if (pass == 0) {
+            L.index.push_back(c < ncols ? child_z(0, n.s + c) : -1);
+            L.index.push_back(c < ncols ? child_z(1, n.s + c) : -1);
+          } else {
+            L.index.push_back(c < ncols ? idx_user[n.idx_off + c] : -1);
+            L.index.push_back(0);
+          }
+        }
+        while (L.index.size() % 4) L.index.push_back(0);
         for (int32_t k = 0; k < nblk; ++k) {
           items.push_back({pass == 0 ? SW_TOP_FWD : SW_TOP_BWD, sid[id], k * cw, cw, rlen, rs});
           RepackDesc d;
@@ -170,24 +277,21 @@ const char *build_sweep_layout(const NdTree &tr, int32_t n_cta, int32_t chunk_db
       }
     }
   }
-  L.bytes_per_step = 8.0 * double(rs);
-  // ---- subtree blobs: one contiguous range of the front storage, copied verbatim ----
-  L.sub_old_base = tr.instances.front().rf_base;
-  L.sub_dbl = tr.r_total - L.sub_old_base;
-  L.sub_rs_base = rs;
-  rs += L.sub_dbl;
-  L.rs_total = rs;
-  L.bytes_per_step += 8.0 * double(L.sub_dbl);
-  L.blob_max = chunk_dbl;
-  for (const auto &T : tr.templates) {
-    L.tmpl_off.push_back(int64_t(L.tmpl16.size()));
-    const size_t before = L.tmpl16.size();
-    if (const char *err = pack_template(T, L.tmpl16)) return err;
-    L.tmpl16_max = std::max(L.tmpl16_max, int32_t(L.tmpl16.size() - before));
-    const int32_t ncell = T.w * T.h;
-    L.sub_ws_max = std::max(L.sub_ws_max, ncell + std::max(T.n_int + T.zl_size, 2 * T.n_int + T.n_rootb));
-    L.blob_max = std::max(L.blob_max, std::max(T.rf_size, T.rb_size));
+  // ---- subtree blobs ----
+  for (size_t k = 0; k < tr.instances.size(); ++k) {
+    const SubtreeInstance &in = tr.instances[k];
+    const SubtreeTemplate &T = tr.templates[in.tmpl];
+    L.inst[k].rf = rs; rs += T.rf_size;
+    L.inst[k].rb = rs; rs += T.rb_size;
+    RepackSub d;
+    d.old_rf = in.rf_base; d.old_rb = in.rb_base; d.new_rf = L.inst[k].rf; d.new_rb = L.inst[k].rb;
+    d.rf_size = T.rf_size; d.rb_size = T.rb_size; d.perm_off = perm_off[in.tmpl]; d.pad = 0;
+    L.repack_sub.push_back(d);
   }
+  L.rs_total = rs;
+  L.bytes_per_step = 8.0 * double(rs);
+  for (int t = 0; t < 8; ++t) L.index.push_back(0);  // the padded tail of the last list may be read
+  if (L.index.size() >= (size_t(1) << 31)) return "index lists beyond 32 bits";
   return nullptr;
 }
 
@@ -195,47 +299,61 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
                                  double min_fill, SweepSchedule &S) {
   S = SweepSchedule();
   const int32_t n_cta = L.n_cta;
-  // ---- shared-memory partition (doubles) ----
-  const int64_t total_dbl = int64_t(smem_budget / 8) - 16;  // static shared memory of the kernel
-  const int64_t fixed = SWEEP_NBAR + 32 + int64_t(SWEEP_THREADS) * M;
-  S.tmpl_dbl = int32_t(((L.tmpl16_max + 3) / 4 + 1) & ~1);
-  S.ws_dbl = int32_t((int64_t(std::max(L.f_max, L.sub_ws_max)) * M + 1) & ~int64_t(1));
-  const int64_t ring = (total_dbl - fixed - S.tmpl_dbl - S.ws_dbl) & ~int64_t(1);
-  if (double(ring) < std::max(2.0, min_fill) * double(L.blob_max)) {
-    std::snprintf(g_msg, sizeof g_msg, "shared-memory ring (%lld doubles) is too small for entries of %d doubles",
-                  (long long)ring, L.blob_max);
-    return g_msg;
-  }
-  S.ring_dbl = int32_t(ring);
-  S.smem_bytes = size_t(fixed + S.tmpl_dbl + S.ws_dbl + S.ring_dbl) * 8;
-
   // ---- static assignment ----
   std::vector<std::vector<SweepEntry>> per(n_cta);
+  std::vector<std::vector<SweepIssue>> per_iss(n_cta);
   auto blank = [] {
     SweepEntry e;
     std::memset(&e, 0, sizeof e);
     e.sig = e.dep0 = e.dep1 = -1;
-    e.o4 = e.o5 = -1;
     return e;
   };
+  auto blank_issue = [] {
+    SweepIssue s;
+    std::memset(&s, 0, sizeof s);
+    return s;
+  };
   const int32_t n_inst = int32_t(tr.instances.size());
-  auto sub_entry = [&](int32_t k, bool fwd) {
+  auto sub_entry = [&](int32_t k, bool fwd, SweepIssue &iss) {
     const SubtreeInstance &in = tr.instances[k];
     const SubtreeTemplate &T = tr.templates[in.tmpl];
     const SweepNodeH &sn = L.nodes[L.n_top + k];
+    const SweepInstH &ih = L.inst[k];
     SweepEntry e = blank();
+    iss = blank_issue();
     e.kind = fwd ? SW_SUB_FWD : SW_SUB_BWD;
     e.flags = SWF_FIRST | SWF_LAST;
-    e.n_dbl = fwd ? T.rf_size : T.rb_size;
-    e.src = L.sub_rs_base + ((fwd ? in.rf_base : in.rb_base) - L.sub_old_base);
     e.a0 = in.tmpl; e.a1 = -1; e.a2 = in.I0; e.a3 = in.J0; e.a7 = k;
-    e.o0 = sn.zc_off; e.o1 = L.inst_xi[k];
+    e.o0 = sn.zc_off; e.o1 = ih.xi_off; e.o2 = ih.pb_off;
+    e.n[0] = fwd ? T.rf_size : T.rb_size;
+    iss.off[0] = fwd ? ih.rf : ih.rb; iss.kind[0] = SRC_FACTOR;
+    if (!fwd) {
+      e.n[1] = even((T.n_rootb + 1) / 2);
+      iss.off[1] = ih.xb / 2; iss.kind[1] = SRC_INDEX;
+      e.n[2] = even(T.n_int) * M;
+      iss.off[2] = int64_t(ih.xi_off) * M; iss.kind[2] = SRC_XI;
+    }
+    e.n[3] = even(int64_t(T.w) * T.h) * M;
+    iss.off[3] = int64_t(ih.pb_off) * M; iss.kind[3] = SRC_PTIL;
+    for (int t = 0; t < SWEEP_SEGS; ++t) iss.n[t] = e.n[t];
     if (fwd) e.sig = 2 * (L.n_top + k);
     else if (sn.parent >= 0) { e.dep0 = 2 * sn.parent + 1; e.dep0_n = L.nodes[sn.parent].n_bwd; }
     return e;
   };
-  auto cta_of_inst = [&](int32_t k) { return int32_t(int64_t(k) * n_cta / n_inst); };
-  for (int32_t k = 0; k < n_inst; ++k) per[cta_of_inst(k)].push_back(sub_entry(k, true));
+  // interior and boundary subtrees are dealt out separately so that every CTA gets its share of both
+  std::vector<int32_t> cta_of_inst(n_inst, 0);
+  {
+    std::vector<int32_t> interior, boundary;
+    for (int32_t k = 0; k < n_inst; ++k) (tr.templates[tr.instances[k].tmpl].flags == 0 ? interior : boundary).push_back(k);
+    for (size_t t = 0; t < interior.size(); ++t) cta_of_inst[interior[t]] = int32_t(int64_t(t) * n_cta / int64_t(interior.size()));
+    for (size_t t = 0; t < boundary.size(); ++t)
+      cta_of_inst[boundary[t]] = n_cta - 1 - int32_t(int64_t(t) * n_cta / int64_t(boundary.size()));
+  }
+  for (int32_t k = 0; k < n_inst; ++k) {
+    SweepIssue iss;
+    per[cta_of_inst[k]].push_back(sub_entry(k, true, iss));
+    per_iss[cta_of_inst[k]].push_back(iss);
+  }
 
   int32_t rot = 0;
   auto place_level = [&](const std::vector<SweepItem> &items) {
@@ -250,7 +368,8 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
       slot = std::min(slot, n_cta - 1);
       used = std::max(used, slot + 1);
       cum += sz;
-      auto &list = per[(slot + rot) % n_cta];
+      const int32_t cta = (slot + rot) % n_cta;
+      auto &list = per[cta];
       const SweepNodeH &sn = L.nodes[it.node];
       const bool fwd = it.kind == SW_TOP_FWD;
       const int32_t cw = it.cw;
@@ -259,20 +378,28 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
       do {
         const int32_t r1 = std::min(it.rlen, r + rows_per);
         SweepEntry e = blank();
+        SweepIssue iss = blank_issue();
         e.kind = it.kind;
         e.flags = (r == 0 ? SWF_FIRST : 0) | (r1 >= it.rlen ? SWF_LAST : 0);
+        e.a0 = it.col0; e.a1 = cw; e.a2 = r; e.a3 = r1; e.a4 = sn.s; e.a5 = sn.b; e.a6 = sn.sep_type;
+        e.a7 = it.node;
+        e.o2 = sn.zs_off; e.o3 = sn.zc_off;
         if (r == 0) {
           const bool same_run = !list.empty() && list.back().kind == it.kind && list.back().a7 == it.node;
-          if (!same_run) e.flags |= SWF_NEW_RUN;
+          if (!same_run) {
+            e.flags |= SWF_NEW_RUN;
+            e.n[0] = fwd ? 2 * sn.s : even((sn.b + 1) / 2);
+            iss.off[0] = (fwd ? sn.gl_f : sn.gl_b) / 2; iss.kind[0] = SRC_INDEX;
+          }
           if (fwd && it.col0 == 0) e.flags |= SWF_WRITE_ZS;
+          if ((fwd ? sn.b : sn.s) > 0) {
+            e.n[1] = cw;
+            iss.off[1] = (fwd ? sn.cl_f : sn.cl_b) / 2 + it.col0; iss.kind[1] = SRC_INDEX;
+          }
         }
-        e.n_dbl = (r1 - r) * cw;
-        e.src = it.src + int64_t(r) * cw;
-        e.a0 = it.col0; e.a1 = it.cw; e.a2 = r; e.a3 = r1; e.a4 = sn.s; e.a5 = sn.b; e.a6 = sn.sep_type;
-        e.a7 = it.node;
-        e.o0 = sn.idx_off; e.o1 = sn.src_off; e.o2 = sn.zs_off; e.o3 = sn.zc_off;
-        e.o4 = sn.child[0] >= 0 ? L.nodes[sn.child[0]].zc_off : -1;
-        e.o5 = sn.child[1] >= 0 ? L.nodes[sn.child[1]].zc_off : -1;
+        e.n[2] = (r1 - r) * cw;
+        iss.off[2] = it.src + int64_t(r) * cw; iss.kind[2] = SRC_FACTOR;
+        for (int t = 0; t < SWEEP_SEGS; ++t) iss.n[t] = e.n[t];
         if (fwd) {
           e.sig = 2 * it.node;
           if (sn.child[0] >= 0) { e.dep0 = 2 * sn.child[0]; e.dep0_n = L.nodes[sn.child[0]].n_fwd; }
@@ -283,6 +410,7 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
           else { e.dep0 = 2 * it.node; e.dep0_n = sn.n_fwd; }
         }
         list.push_back(e);
+        per_iss[cta].push_back(iss);
         r = r1;
       } while (r < it.rlen);
     }
@@ -290,7 +418,27 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
   };
   for (size_t h = 0; h < L.fwd.size(); ++h) place_level(L.fwd[h]);
   for (size_t h = L.bwd.size(); h-- > 0;) place_level(L.bwd[h]);
-  for (int32_t k = 0; k < n_inst; ++k) per[cta_of_inst(k)].push_back(sub_entry(k, false));
+  for (int32_t k = 0; k < n_inst; ++k) {
+    SweepIssue iss;
+    per[cta_of_inst[k]].push_back(sub_entry(k, false, iss));
+    per_iss[cta_of_inst[k]].push_back(iss);
+  }
+
+  // ---- shared-memory partition (doubles) ----
+  for (const auto &list : per)
+    for (const auto &e : list) S.entry_max = std::max(S.entry_max, e.n[0] + e.n[1] + e.n[2] + e.n[3]);
+  const int64_t total_dbl = int64_t(smem_budget / 8);
+  const int64_t fixed = sweep_fixed_dbl(M);
+  S.tmpl_dbl = even((L.tmpl16_max + 3) / 4);
+  S.ws_dbl = even(int64_t(std::max(L.f_max, L.sub_ws_max)) * M);
+  const int64_t ring = (total_dbl - fixed - S.tmpl_dbl - S.ws_dbl) & ~int64_t(1);
+  if (double(ring) < std::max(2.0, min_fill) * double(S.entry_max)) {
+    std::snprintf(g_msg, sizeof g_msg, "shared-memory ring (%lld doubles) is too small for entries of %d doubles",
+                  (long long)ring, S.entry_max);
+    return g_msg;
+  }
+  S.ring_dbl = int32_t(ring);
+  S.smem_bytes = size_t(fixed + S.tmpl_dbl + S.ws_dbl + S.ring_dbl) * 8;
 
   // ---- ring schedule per CTA ----
   S.cta_begin.assign(n_cta + 1, 0);
@@ -300,28 +448,46 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
     const int32_t P = int32_t(list.size());
     S.cta_begin[c + 1] = S.cta_begin[c] + P;
     if (P == 0) continue;
-    int64_t pos = 0;
-    for (auto &e : list) {
-      if (e.n_dbl > 0) {
-        if (pos + e.n_dbl > S.ring_dbl) pos = 0;
-        e.ring_off = int32_t(pos);
-        pos += e.n_dbl;
+    std::vector<int32_t> size(P), producer(P, -1);  // producer: distance back to the entry that writes what this streams
+    {
+      std::map<int32_t, int32_t> fwd_at, bwd_at;
+      for (int32_t i = 0; i < P; ++i) {
+        if (list[i].kind == SW_SUB_FWD) fwd_at[list[i].a7] = i;
+        if (list[i].kind == SW_SUB_BWD) bwd_at[list[i].a7] = i;
+      }
+      for (int32_t i = 0; i < P; ++i) {
+        if (list[i].kind == SW_SUB_BWD) producer[i] = i - fwd_at.at(list[i].a7);        // xi of this step
+        if (list[i].kind == SW_SUB_FWD) producer[i] = P - (bwd_at.at(list[i].a7) - i);  // pressures of the last step
       }
     }
-    // dependency of every entry on the completion of an earlier one (ring space and barrier reuse), over three
-    // periods of the periodic sequence; eff = running maximum because issue order is entry order
+    int64_t pos = 0;
+    for (int32_t i = 0; i < P; ++i) {
+      SweepEntry &e = list[i];
+      size[i] = e.n[0] + e.n[1] + e.n[2] + e.n[3];
+      if (size[i] > 0) {
+        if (pos + size[i] > S.ring_dbl) pos = 0;
+        e.ring_off = int32_t(pos);
+        pos += size[i];
+      }
+    }
+    // dependency of every entry on the completion of an earlier one (ring space, barrier reuse, producer of a
+    // streamed vector), over three periods of the periodic sequence; eff = running maximum because issue order is
+    // entry order
     const int32_t U = 3 * P;
     std::vector<int64_t> eff(U);
     for (int32_t u = 0; u < U; ++u) {
-      const SweepEntry &e = list[u % P];
+      const int32_t i = u % P;
+      const SweepEntry &e = list[i];
       int64_t dep = int64_t(u) - SWEEP_NBAR;
-      if (e.n_dbl > 0) {
+      if (producer[i] > 0) dep = std::max<int64_t>(dep, int64_t(u) - producer[i]);
+      if (size[i] > 0) {
         int64_t seen = 0;
         for (int32_t v = u - 1, n = 0; v >= 0 && n < 4096 && seen < 2 * int64_t(S.ring_dbl); --v, ++n) {
           const SweepEntry &o = list[v % P];
-          if (o.n_dbl <= 0) continue;
-          seen += o.n_dbl;
-          if (o.ring_off < e.ring_off + e.n_dbl && e.ring_off < o.ring_off + o.n_dbl) { dep = std::max<int64_t>(dep, v); break; }
+          const int32_t osz = size[v % P];
+          if (osz <= 0) continue;
+          seen += osz;
+          if (o.ring_off < e.ring_off + size[i] && e.ring_off < o.ring_off + osz) { dep = std::max<int64_t>(dep, v); break; }
         }
       }
       eff[u] = u > 0 ? std::max(dep, eff[u - 1]) : dep;
@@ -329,23 +495,20 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
     // steady state relative to the start of a step: rel(u') = eff[2P + u' mod P] - 2P + (u' div P) P
     auto rel = [&](int64_t up) { return eff[2 * P + up % P] - 2 * int64_t(P) + (up / P) * P; };
     int64_t ptr = 0;
-    while (ptr < 2 * int64_t(P) && rel(ptr) < 0) ++ptr;
-    S.cta_prologue[c] = int32_t(std::min<int64_t>(ptr, SWEEP_NBAR));
-    int64_t upto = S.cta_prologue[c];
+    while (ptr < SWEEP_NBAR && rel(ptr) < 0) ++ptr;
+    S.cta_prologue[c] = int32_t(ptr);
+    int64_t upto = ptr;
     for (int32_t i = 0; i < P; ++i) {
-      const int64_t first = upto;
       while (upto < int64_t(i) + 1 + SWEEP_NBAR && rel(upto) <= i) ++upto;
-      if (upto < i + 2 && P > 1) upto = i + 2;  // cannot happen: entry i + 1 only depends on entries <= i
       list[i].issue_upto = int32_t(upto);
-      const SweepEntry &t = list[first % P];
-      list[i].t_src = t.src; list[i].t_n_dbl = t.n_dbl; list[i].t_ring_off = t.ring_off;
     }
   }
   S.entries.reserve(S.cta_begin[n_cta]);
   for (int32_t c = 0; c < n_cta; ++c)
-    for (const auto &e : per[c]) {
-      S.entries.push_back(e);
-      S.issue.push_back({e.src, e.n_dbl, e.ring_off});
+    for (size_t i = 0; i < per[c].size(); ++i) {
+      per_iss[c][i].ring_off = per[c][i].ring_off;
+      S.entries.push_back(per[c][i]);
+      S.issue.push_back(per_iss[c][i]);
     }
   return nullptr;
 }
@@ -353,8 +516,17 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
 const char *check_sweep_schedule(const SweepLayout &L, const SweepSchedule &S, int32_t n_steps) {
   const int32_t n_cta = L.n_cta;
   std::vector<uint32_t> cnt(2 * L.nodes.size(), 0);
-  struct Cta { int64_t G = 0, issued = 0; };
+  struct Cta { int64_t G = 0, issued = 0; std::map<int32_t, int32_t> fwd_at, bwd_at; };
   std::vector<Cta> st(n_cta);
+  for (int32_t c = 0; c < n_cta; ++c) {
+    const int32_t b0 = S.cta_begin[c], P = S.cta_begin[c + 1] - b0;
+    for (int32_t i = 0; i < P; ++i) {
+      const SweepEntry &e = S.entries[b0 + i];
+      if (e.kind == SW_SUB_FWD) st[c].fwd_at[e.a7] = i;
+      if (e.kind == SW_SUB_BWD) st[c].bwd_at[e.a7] = i;
+    }
+  }
+  auto size_of = [](const SweepEntry &e) { return e.n[0] + e.n[1] + e.n[2] + e.n[3]; };
   auto issue_check = [&](int32_t c, int64_t upto) -> const char * {
     const int32_t b0 = S.cta_begin[c], P = S.cta_begin[c + 1] - b0;
     Cta &s = st[c];
@@ -362,12 +534,20 @@ const char *check_sweep_schedule(const SweepLayout &L, const SweepSchedule &S, i
     upto = std::min(upto, total);
     for (; s.issued < upto; ++s.issued) {
       const SweepEntry &e = S.entries[b0 + s.issued % P];
+      const int64_t step = s.issued / P;
       if (s.issued - SWEEP_NBAR >= s.G) { std::snprintf(g_msg, sizeof g_msg, "cta %d: barrier of entry %lld re-armed before use", c, (long long)s.issued); return g_msg; }
-      if (e.n_dbl <= 0) continue;
-      if (e.ring_off < 0 || e.ring_off + e.n_dbl > S.ring_dbl || (e.ring_off & 1) || (e.n_dbl & 1)) { std::snprintf(g_msg, sizeof g_msg, "cta %d: ring range of entry %lld out of bounds or misaligned", c, (long long)s.issued); return g_msg; }
+      // streamed vectors must have been written by a retired entry
+      if (e.kind == SW_SUB_BWD && step * P + s.fwd_at.at(e.a7) >= s.G) { std::snprintf(g_msg, sizeof g_msg, "cta %d: entry %lld streams xi before its forward pass retired", c, (long long)s.issued); return g_msg; }
+      if (e.kind == SW_SUB_FWD && step > 0 && (step - 1) * P + s.bwd_at.at(e.a7) >= s.G) { std::snprintf(g_msg, sizeof g_msg, "cta %d: entry %lld streams pressures before the last step's backward pass retired", c, (long long)s.issued); return g_msg; }
+      const int32_t sz = size_of(e);
+      if (sz <= 0) continue;
+      bool bad = e.ring_off < 0 || e.ring_off + sz > S.ring_dbl || (e.ring_off & 1);
+      for (int t = 0; t < SWEEP_SEGS; ++t) bad |= (e.n[t] & 1) != 0;
+      if (bad) { std::snprintf(g_msg, sizeof g_msg, "cta %d: ring range of entry %lld out of bounds or misaligned", c, (long long)s.issued); return g_msg; }
       for (int64_t v = s.G; v < s.issued; ++v) {
         const SweepEntry &o = S.entries[b0 + v % P];
-        if (o.n_dbl > 0 && o.ring_off < e.ring_off + e.n_dbl && e.ring_off < o.ring_off + o.n_dbl) {
+        const int32_t osz = size_of(o);
+        if (osz > 0 && o.ring_off < e.ring_off + sz && e.ring_off < o.ring_off + osz) {
           std::snprintf(g_msg, sizeof g_msg, "cta %d: entry %lld overwrites the ring range of unfinished entry %lld", c, (long long)s.issued, (long long)v);
           return g_msg;
         }
@@ -423,12 +603,12 @@ extern "C" int mmmfe_sweep_plan_check(int32_t nx, int32_t ny, int32_t leaf_cells
   mmmfe::NdTree t;
   t.build(nx, ny, leaf_cells, subtree_cells);
   mmmfe::SweepLayout L;
-  if (const char *e = mmmfe::build_sweep_layout(t, n_cta, 2048, L)) { say(e); return -2; }
+  if (const char *e = mmmfe::build_sweep_layout(t, t.idx, std::vector<int32_t>(), n_cta, 2048, L)) { say(e); return -2; }
   mmmfe::SweepSchedule S;
   if (const char *e = mmmfe::build_sweep_schedule(t, L, M, size_t(smem_bytes), 2.0, S)) { say(e); return -3; }
   if (stats) {
     stats[0] = int64_t(L.nodes.size()); stats[1] = L.n_top; stats[2] = int64_t(S.entries.size()); stats[3] = L.rs_total;
-    stats[4] = S.ring_dbl; stats[5] = S.ws_dbl; stats[6] = L.blob_max; stats[7] = int64_t(S.smem_bytes);
+    stats[4] = S.ring_dbl; stats[5] = S.ws_dbl; stats[6] = S.entry_max; stats[7] = int64_t(S.smem_bytes);
   }
   if (const char *e = mmmfe::check_sweep_schedule(L, S, n_steps)) { say(e); return -4; }
   return 0;

@@ -12,11 +12,11 @@ import mmmfe_import
     (2, 2, 4, 256, 1, 296),
     (16, 16, 4, 64, 2, 296),
     (37, 23, 4, 64, 2, 296),       # ragged boxes
-    (96, 96, 4, 128, 2, 296),
-    (150, 130, 4, 128, 4, 148),
+    (96, 96, 4, 64, 2, 296),
+    (150, 130, 4, 64, 4, 148),
     (5, 7, 1, 2, 1, 8),            # tiny leaves, few CTAs
     (256, 256, 4, 64, 4, 296),     # BASELINE configs[3] fine subdomain, 4 right-hand sides
-    (512, 512, 4, 128, 2, 296),    # BASELINE configs[1] coarse subdomain
+    (512, 512, 4, 64, 2, 296),     # BASELINE configs[1] coarse subdomain
 ])
 def test_schedule_replays_without_hazards(nx, ny, leaf, sub, M, ncta):
     pkg = mmmfe_import.load()
