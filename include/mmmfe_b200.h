@@ -193,8 +193,10 @@ int mmmfe_profile_step(mmmfe_ctx *ctx, double ms[MMMFE_N_KERNEL_CLASSES], double
 int mmmfe_profile_sweeps(mmmfe_ctx *ctx, int32_t cap, double *ms, double *bytes_per_step, int32_t *n_steps,
                          int32_t *n_out);
 /* One instrumented star sweep of sweep batch `batch`: mean SM cycles per CTA spent in {subtree forward, top forward,
- * top backward, subtree backward} entries, in completion-counter waits, in TMA (mbarrier) waits; out[6] = entries. */
-int mmmfe_profile_sweep_cycles(mmmfe_ctx *ctx, int32_t batch, double out[8]);
+ * top backward, subtree backward} entries, [4] completion-counter waits of the dependency warp, [5] TMA (mbarrier)
+ * waits, [6] entries, [7] waits for the dependency warp, [8..10] subtree backward: input gather / levels / epilogue,
+ * [11..13] subtree forward: right-hand side / levels / output, [14] top-level vector gathers, [15] top-level tiles. */
+int mmmfe_profile_sweep_cycles(mmmfe_ctx *ctx, int32_t batch, double out[16]);
 /* Integer facts about the set-up context: "batches", "sweep_batches", "sweep_ctas", "sweep_smem_bytes",
  * "sweep_entries", "sweep_factor_bytes", "rt0_factors"; -1 for an unknown key.                                */
 int64_t mmmfe_stat(const mmmfe_ctx *ctx, const char *key);

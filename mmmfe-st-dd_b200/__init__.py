@@ -280,9 +280,10 @@ class Engine:
         return [(float(ms[i]), float(by[i]), int(ns[i])) for i in range(int(n[0]))]
 
     def profile_sweep_cycles(self, batch):
-        out = np.zeros(8)
+        out = np.zeros(16)
         self._check(self.lib.mmmfe_profile_sweep_cycles(self.h, batch, _ptr(out, c_f64p)))
-        names = ["sub_fwd", "top_fwd", "top_bwd", "sub_bwd", "counter_wait", "tma_wait", "entries"]
+        names = ["sub_fwd", "top_fwd", "top_bwd", "sub_bwd", "counter_wait", "tma_wait", "entries", "open_wait",
+                 "sb_gather", "sb_levels", "sb_epilogue", "sf_rhs", "sf_levels", "sf_output", "top_gather", "top_tile"]
         return dict(zip(names, (float(v) for v in out)))
 
     def debug_get_factor(self, li, r_total):

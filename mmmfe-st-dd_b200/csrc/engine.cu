@@ -203,7 +203,7 @@ struct mmmfe_ctx {
   int64_t q_rows = 0;
   double factor_seconds = 0.0;
   long long launch_base = 0;
-  int *abort_flag = nullptr;  // pinned: raised by the sweep kernel's watchdog
+  int *abort_flag = nullptr;  // device memory: raised by the sweep kernel's watchdog
   // temporaries of the factorisation
   DevBuf<GemmProb> d_gemm;
   DevBuf<int32_t> d_tiles;
@@ -666,8 +666,11 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax) 
 
 // after a stream synchronisation: did a spin-wait of the sweep kernel give up?
 static void check_watchdog(mmmfe_ctx *c) {
-  if (c->abort_flag && *c->abort_flag) {
-    *c->abort_flag = 0;
+  if (!c->abort_flag) return;
+  int flag = 0;
+  CUDA_CHECK(cudaMemcpy(&flag, c->abort_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) {
+    CUDA_CHECK(cudaMemset(c->abort_flag, 0, sizeof(int)));
     fail(MMMFE_E_CUDA, "sweep kernel watchdog: a data-flow wait did not complete (results discarded)");
   }
 }
@@ -947,7 +950,7 @@ static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> 
   if (!F.sweep_ok) return;
   const NdTree &tr = F.tree;
   SweepSchedule S;
-  if (build_sweep_schedule(tr, F.lay, b.M, F.sweep_budget, 2.0, S) != nullptr) return;
+  if (build_sweep_schedule(tr, F.lay, b.M, F.sweep_budget, 1.0, S) != nullptr) return;
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
   if (sweep_ctas_per_sm(b.M, S.smem_bytes) * sms < F.sweep_n_cta) return;  // grid would not be co-resident
@@ -1020,8 +1023,8 @@ static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> 
   a.tmpl_dbl = S.tmpl_dbl; a.ws_dbl = S.ws_dbl; a.ring_dbl = S.ring_dbl;
   a.evict_first = c->sweep_evict_first ? 1 : 0;
   if (!c->abort_flag) {
-    CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void **>(&c->abort_flag), sizeof(int), cudaHostAllocMapped));
-    *c->abort_flag = 0;
+    CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&c->abort_flag), sizeof(int)));
+    CUDA_CHECK(cudaMemset(c->abort_flag, 0, sizeof(int)));
   }
   a.abort_flag = c->abort_flag;
   b.sweep_smem = S.smem_bytes;
@@ -1195,7 +1198,7 @@ int mmmfe_destroy(mmmfe_ctx *c) {
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
   if (c->stream) cudaStreamDestroy(c->stream);
-  if (c->abort_flag) cudaFreeHost(c->abort_flag);
+  if (c->abort_flag) cudaFree(c->abort_flag);
   delete c;
   return MMMFE_OK;
 }
@@ -1538,7 +1541,7 @@ int64_t mmmfe_stat(const mmmfe_ctx *c, const char *key) {
   return -1;
 }
 
-int mmmfe_profile_sweep_cycles(mmmfe_ctx *c, int32_t batch, double out[8]) {
+int mmmfe_profile_sweep_cycles(mmmfe_ctx *c, int32_t batch, double out[16]) {
   if (!c || !out) return MMMFE_E_INVALID;
   MMMFE_TRY(c, {
     if (!c->is_setup) fail(MMMFE_E_INVALID, "mmmfe_setup first");
@@ -1549,7 +1552,7 @@ int mmmfe_profile_sweep_cycles(mmmfe_ctx *c, int32_t batch, double out[8]) {
       if (k++ != batch) continue;
       const int32_t n_cta = b.factor->sweep_n_cta;
       DevBuf<long long> prof;
-      prof.alloc(size_t(n_cta) * 8);
+      prof.alloc(size_t(n_cta) * 16);
       prof.zero(c->stream);
       SweepArgs a = b.sargs;
       a.prof = prof.p;
@@ -1559,11 +1562,11 @@ int mmmfe_profile_sweep_cycles(mmmfe_ctx *c, int32_t batch, double out[8]) {
       if (err != cudaSuccess) fail(MMMFE_E_CUDA, "sweep kernel launch failed: %s", cudaGetErrorString(err));
       CUDA_CHECK(cudaStreamSynchronize(c->stream));
       check_watchdog(c);
-      std::vector<long long> h(size_t(n_cta) * 8);
+      std::vector<long long> h(size_t(n_cta) * 16);
       CUDA_CHECK(cudaMemcpy(h.data(), prof.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-      for (int t = 0; t < 8; ++t) out[t] = 0;
+      for (int t = 0; t < 16; ++t) out[t] = 0;
       for (int32_t cta = 0; cta < n_cta; ++cta)
-        for (int t = 0; t < 8; ++t) out[t] += double(h[size_t(cta) * 8 + t]) / n_cta;
+        for (int t = 0; t < 16; ++t) out[t] += double(h[size_t(cta) * 16 + t]) / n_cta;
       return MMMFE_OK;
     }
     fail(MMMFE_E_INVALID, "no such sweep batch");

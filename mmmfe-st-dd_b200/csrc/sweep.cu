@@ -59,6 +59,7 @@ namespace {
 
 constexpr int NB = SWEEP_NBAR;
 constexpr int CT = SWEEP_COMPUTE;
+constexpr int SWEEP_POLL_WINDOW = 4;  // entries ahead of the oldest unopened one that poll completion counters
 
 __device__ __forceinline__ uint32_t s_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
@@ -88,9 +89,12 @@ __device__ __forceinline__ bool bar_try(uint64_t *bar, uint32_t parity) {
 // (pinned host memory) and carries on with whatever data it has; the host reports the failure after the launch.
 constexpr long long SWEEP_SPIN_LIMIT = 8000000000LL;
 
+// (The flag lives in device memory: a poll is an L2 hit.  It is still only looked at after a long wait.)
 __device__ __forceinline__ bool spin_expired(long long t0, volatile int *abort_flag) {
+  const long long waited = clock64() - t0;
+  if (waited < (1LL << 24)) return false;  // < ~9 ms: nothing can be wrong yet
   if (*abort_flag) return true;
-  if (clock64() - t0 > SWEEP_SPIN_LIMIT) {
+  if (waited > SWEEP_SPIN_LIMIT) {
     *abort_flag = 1;
     return true;
   }
@@ -118,6 +122,27 @@ __device__ __forceinline__ void wait_counter(const uint32_t *p, uint32_t target,
   if (ld_acquire(p) >= target) return;
   const long long t0 = clock64();
   for (int n = 0; ld_acquire(p) < target; ++n) {
+    __nanosleep(20);
+    if ((n & 255) == 255 && spin_expired(t0, abort_flag)) return;
+  }
+}
+
+// Completion of entries inside the CTA: monotonic shared-memory counters (one per slot, bumped once per compute
+// warp).  The retire and dependency lanes may lag arbitrarily far behind the compute warps, so a phase-parity
+// barrier could be missed; a counter cannot.
+__device__ __forceinline__ void done_signal(uint32_t *cnt) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;\n" ::"r"(s_u32(cnt)) : "memory");
+}
+
+__device__ __forceinline__ void done_wait(const uint32_t *cnt, uint32_t target, volatile int *abort_flag) {
+  uint32_t v;
+  const uint32_t addr = s_u32(cnt);
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
+  if (v >= target) return;
+  const long long t0 = clock64();
+  for (int n = 0;; ++n) {
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
+    if (v >= target) return;
     __nanosleep(20);
     if ((n & 255) == 255 && spin_expired(t0, abort_flag)) return;
   }
@@ -159,12 +184,19 @@ __device__ __forceinline__ int64_t sweep_dof(const SweepArgs &a, int I0, int J0,
 // =================================================================================================================
 // the sweep kernel
 // =================================================================================================================
+#define SWEEP_PROF(slot)                                     \
+  if (a.prof && tid == 0) {                                  \
+    const long long t_now = clock64();                       \
+    a.prof[cta * 16 + (slot)] += t_now - t_mark;             \
+    t_mark = t_now;                                          \
+  }
+
 template <int M>
 __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
   extern __shared__ __align__(128) double sm[];
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(sm);  // TMA data of the entry landed
-  uint64_t *done_bar = full_bar + NB;                     // all compute warps finished the entry
-  uint64_t *dep_bar = done_bar + NB;                      // descriptor staged, dependencies satisfied
+  uint32_t *done_cnt = reinterpret_cast<uint32_t *>(full_bar + NB);  // compute warps that finished the slot's entries
+  uint64_t *dep_bar = full_bar + 2 * NB;                  // descriptor staged, dependencies satisfied
   SweepEntry *edesc = reinterpret_cast<SweepEntry *>(sm + 3 * NB);
   double *red = sm + 19 * NB;                             // two reduction buffers
   uint16_t *tb = reinterpret_cast<uint16_t *>(red + 2 * CT * M);
@@ -183,7 +215,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
   if (tid == 0) {
     for (int k = 0; k < NB; ++k) {
       bar_init(full_bar + k, 1);
-      bar_init(done_bar + k, CT / 32);
+      done_cnt[k] = 0;
       bar_init(dep_bar + k, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -192,120 +224,157 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
 
   if (warp == CT / 32) {
     // =============================================================================================================
-    // RETIRE warp: completion -> release counter -> free ring space -> next TMA copies
+    // RETIRE warp: 32 independent lanes, lane l retires the entries G = l (mod 32): completion -> release counter ->
+    // TMA copies of the entries this completion frees ring space for.  Which entries a completion releases is
+    // static (issue_upto of the previous entry .. issue_upto of this one), so the lanes share no state.
     // =============================================================================================================
-    if (lane != 0) return;
     uint64_t policy = 0;
     if (a.evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(policy));
-    long long issued = 0;
-    int issue_i = 0;
-    auto issue_one = [&](const SweepIssue &s) {
-      uint64_t *fb = full_bar + (issued % NB);
+    auto issue_one = [&](long long g, const SweepIssue &s) {
+      uint64_t *fb = full_bar + (g % NB);
       const uint32_t bytes = uint32_t(s.n[0] + s.n[1] + s.n[2] + s.n[3]) * 8u;
       if (bytes == 0) {
         bar_arrive(fb);  // keeps the phase count
-      } else {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(s_u32(fb)), "r"(bytes) : "memory");
-        double *dst = ring + s.ring_off;
-#pragma unroll
-        for (int t = 0; t < SWEEP_SEGS; ++t) {
-          if (s.n[t] <= 0) continue;
-          const double *base = s.kind[t] == SRC_FACTOR ? a.Rs
-                               : s.kind[t] == SRC_INDEX ? reinterpret_cast<const double *>(a.index)
-                               : s.kind[t] == SRC_XI    ? a.xi
-                                                        : a.ptil;
-          const char *src = reinterpret_cast<const char *>(base + s.off[t]);
-          const bool hint = a.evict_first && s.kind[t] == SRC_FACTOR;
-          uint32_t left = uint32_t(s.n[t]) * 8u, done = 0;
-          while (left > 0) {
-            const uint32_t n = left < 32768u ? left : 32768u;
-            if (hint)
-              asm volatile(
-                  "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::
-                      "r"(s_u32(reinterpret_cast<char *>(dst) + done)),
-                  "l"(src + done), "r"(n), "r"(s_u32(fb)), "l"(policy)
-                  : "memory");
-            else
-              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                               s_u32(reinterpret_cast<char *>(dst) + done)),
-                           "l"(src + done), "r"(n), "r"(s_u32(fb))
-                           : "memory");
-            done += n;
-            left -= n;
-          }
-          dst += s.n[t];
-        }
+        return;
       }
-      ++issued;
-      if (++issue_i == P) issue_i = 0;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(s_u32(fb)), "r"(bytes) : "memory");
+      double *dst = ring + s.ring_off;
+#pragma unroll
+      for (int t = 0; t < SWEEP_SEGS; ++t) {
+        if (s.n[t] <= 0) continue;
+        const double *base = s.kind[t] == SRC_FACTOR ? a.Rs
+                             : s.kind[t] == SRC_INDEX ? reinterpret_cast<const double *>(a.index)
+                             : s.kind[t] == SRC_XI    ? a.xi
+                                                      : a.ptil;
+        const char *src = reinterpret_cast<const char *>(base + s.off[t]);
+        const bool hint = a.evict_first && s.kind[t] == SRC_FACTOR;
+        uint32_t left = uint32_t(s.n[t]) * 8u, done = 0;
+        while (left > 0) {
+          const uint32_t n = left < 32768u ? left : 32768u;
+          if (hint)
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::
+                    "r"(s_u32(reinterpret_cast<char *>(dst) + done)),
+                "l"(src + done), "r"(n), "r"(s_u32(fb)), "l"(policy)
+                : "memory");
+          else
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                             s_u32(reinterpret_cast<char *>(dst) + done)),
+                         "l"(src + done), "r"(n), "r"(s_u32(fb))
+                         : "memory");
+          done += n;
+          left -= n;
+        }
+        dst += s.n[t];
+      }
     };
-    {
+    if (lane == 0) {
       long long target = a.cta_prologue[cta];
       if (target > total) target = total;
-      while (issued < target) issue_one(iss[issue_i]);
+      for (long long g = 0; g < target; ++g) issue_one(g, iss[g % P]);
     }
-    SweepIssue nxt;
-    long long nxt_for = -1;
-    long long G = 0;
-    for (int step = 0; step < a.n_steps; ++step)
-      for (int i = 0; i < P; ++i, ++G) {
-        // what this entry's retirement needs, fetched while the compute warps work on it
-        const int flags = ents[i].flags, sig = ents[i].sig, upto_rel = ents[i].issue_upto;
-        if (nxt_for != issued && issued < total) {
-          nxt = iss[issue_i];
-          nxt_for = issued;
-        }
-        bar_wait(done_bar + (G % NB), uint32_t((G / NB) & 1), a.abort_flag);
-        if ((flags & SWF_LAST) && sig >= 0) {
-          __threadfence();
-          red_release(a.cnt + sig);
-        }
-        long long target = (long long)step * P + upto_rel;
-        if (target > total) target = total;
-        while (issued < target) {
-          if (nxt_for != issued) {
-            nxt = iss[issue_i];
-            nxt_for = issued;
-          }
-          issue_one(nxt);
+    // One converged polling loop: lane l owns slot l and retires the entries G = l (mod NB) in turn.
+    long long G = lane;
+    int flags = 0, sig = -1;
+    long long first = 0, upto = 0;
+    auto load_info = [&](long long g) {
+      const int step = int(g / P), i = int(g - (long long)step * P);
+      flags = ents[i].flags;
+      sig = ents[i].sig;
+      first = (i == 0) ? (step == 0 ? (long long)a.cta_prologue[cta] : (long long)(step - 1) * P + ents[P - 1].issue_upto)
+                       : (long long)step * P + ents[i - 1].issue_upto;
+      upto = (long long)step * P + ents[i].issue_upto;
+      if (upto > total) upto = total;
+    };
+    bool have = G < total;
+    if (have) load_info(G);
+    long long t0 = clock64();
+    for (int spins = 1; __any_sync(0xffffffffu, have); ++spins) {
+      bool progress = false;
+      if (have) {
+        uint32_t v;
+        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];\n" : "=r"(v) : "r"(s_u32(done_cnt + lane)) : "memory");
+        if (v >= uint32_t(G / NB + 1) * uint32_t(CT / 32)) {
+          progress = true;
+          if ((flags & SWF_LAST) && sig >= 0) red_release(a.cnt + sig);
+          for (long long g = first; g < upto; ++g) issue_one(g, iss[g % P]);
+          G += NB;
+          have = G < total;
+          if (have) load_info(G);
+          t0 = clock64();
         }
       }
+      if (!__any_sync(0xffffffffu, progress)) __nanosleep(100);
+      if ((spins & 1023) == 0 && have && spin_expired(t0, a.abort_flag)) have = false;
+    }
     return;
   }
 
   if (warp == CT / 32 + 1) {
     // =============================================================================================================
-    // DEPENDENCY warp: stages descriptors up to NB entries ahead and waits for the producers of other CTAs
+    // DEPENDENCY warp: one converged polling loop, lane l owns slot l: stages the descriptor of its next entry as
+    // soon as the slot is free (up to NB entries ahead of the compute warps), then waits for the entry's producers
+    // on other CTAs, then opens the slot for the compute warps
     // =============================================================================================================
-    int nxt = reinterpret_cast<const int *>(&ents[0])[lane];
-    long long G = 0;
-    for (int step = 0; step < a.n_steps; ++step)
-      for (int i = 0; i < P; ++i, ++G) {
-        const int slot = int(G % NB);
-        const int cur = nxt;
-        {
-          const int inext = (i + 1 == P) ? 0 : i + 1;
-          nxt = reinterpret_cast<const int *>(&ents[inext])[lane];
+    long long G = lane;
+    bool have = G < total;
+    int state = 0;
+    int4 d[8];
+    int dep0 = -1, dep1 = -1;
+    uint32_t need0 = 0, need1 = 0;
+    auto load_desc = [&](long long g) {
+      const int i = int(g % P);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) d[t] = reinterpret_cast<const int4 *>(&ents[i])[t];
+    };
+    if (have) load_desc(G);
+    long long t0 = clock64(), t_wait = 0;
+    for (int spins = 1; __any_sync(0xffffffffu, have); ++spins) {
+      bool progress = false;
+      if (have && state == 0) {
+        bool free_slot = G < NB;
+        if (!free_slot) {
+          uint32_t v;
+          asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];\n" : "=r"(v) : "r"(s_u32(done_cnt + lane)) : "memory");
+          free_slot = v >= uint32_t(G / NB) * uint32_t(CT / 32);
         }
-        if (G >= NB) {  // the slot's previous user must be finished by every compute warp
-          if (lane == 0) bar_wait(done_bar + slot, uint32_t(((G / NB) - 1) & 1), a.abort_flag);
-          __syncwarp();
+        if (free_slot) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) reinterpret_cast<int4 *>(&edesc[lane])[t] = d[t];
+          const int kind = d[0].x, fl = d[0].y;
+          const bool waits = kind == SW_SUB_BWD || ((kind == SW_TOP_FWD || kind == SW_TOP_BWD) && (fl & SWF_NEW_RUN));
+          const uint32_t step1 = uint32_t(G / P) + 1u;
+          dep0 = waits ? d[1].y : -1;
+          dep1 = waits ? d[1].w : -1;
+          need0 = step1 * uint32_t(d[1].z);
+          need1 = step1 * uint32_t(d[2].x);
+          state = 1;
+          progress = true;
+          if (a.prof) t_wait = clock64();
         }
-        reinterpret_cast<int *>(&edesc[slot])[lane] = cur;
-        __syncwarp();
-        if (lane == 0) {
-          const SweepEntry &e = edesc[slot];
-          const bool waits = e.kind == SW_SUB_BWD || ((e.kind == SW_TOP_FWD || e.kind == SW_TOP_BWD) && (e.flags & SWF_NEW_RUN));
-          if (waits) {
-            const long long t0 = a.prof ? clock64() : 0;
-            if (e.dep0 >= 0) wait_counter(a.cnt + e.dep0, uint32_t(step + 1) * uint32_t(e.dep0_n), a.abort_flag);
-            if (e.dep1 >= 0) wait_counter(a.cnt + e.dep1, uint32_t(step + 1) * uint32_t(e.dep1_n), a.abort_flag);
-            if (a.prof) a.prof[cta * 8 + 4] += clock64() - t0;
-          }
-          bar_arrive(dep_bar + slot);
-        }
-        __syncwarp();
       }
+      // only the few entries the compute warps need next poll the global counters: the others could not be used yet
+      // anyway and would only load the L2 slices that hold hot counters
+      const long long g_min = __reduce_min_sync(0xffffffffu, have ? (unsigned)(G & 0x7fffffff) : 0x7fffffffu);
+      if (have && state == 1 && (dep0 < 0 && dep1 < 0 || (long long)(G & 0x7fffffff) < g_min + SWEEP_POLL_WINDOW)) {
+        bool ok = true;
+        if (dep0 >= 0 && ld_acquire(a.cnt + dep0) < need0) ok = false;
+        if (ok && dep1 >= 0 && ld_acquire(a.cnt + dep1) < need1) ok = false;
+        if (ok) {
+          if (a.prof && (dep0 >= 0 || dep1 >= 0))
+            atomicAdd(reinterpret_cast<unsigned long long *>(a.prof + cta * 16 + 4), (unsigned long long)(clock64() - t_wait));
+          bar_arrive(dep_bar + lane);  // release: the descriptor stores above are visible to the waiters
+          G += NB;
+          have = G < total;
+          state = 0;
+          if (have) load_desc(G);
+          t0 = clock64();
+          progress = true;
+        }
+      }
+      if (!__any_sync(0xffffffffu, progress)) __nanosleep(100);
+      if ((spins & 255) == 0 && have && spin_expired(t0, a.abort_flag)) have = false;
+    }
     return;
   }
 
@@ -333,9 +402,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
       bar_wait(full_bar + slot, parity, a.abort_flag);
       if (a.prof && tid == 0) {
         const long long t = clock64();
-        a.prof[cta * 8 + 7] += t_w - t_entry;  // waiting for the dependency warp
-        a.prof[cta * 8 + 5] += t - t_w;        // waiting for TMA data
+        a.prof[cta * 16 + 7] += t_w - t_entry;  // waiting for the dependency warp
+        a.prof[cta * 16 + 5] += t - t_w;        // waiting for TMA data
       }
+      long long t_mark = (a.prof && tid == 0) ? clock64() : 0;
 
       if (kind == SW_TOP_FWD || kind == SW_TOP_BWD) {
         // ---------------------------------------------------------------------------------------------------------
@@ -384,6 +454,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
             }
           }
           csync();
+          SWEEP_PROF(14)
         }
         if (flags & SWF_FIRST) {
 #pragma unroll
@@ -460,6 +531,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
             }
           }
         }
+        SWEEP_PROF(15)
       } else {
         // ---------------------------------------------------------------------------------------------------------
         // subtree: factor blob, index lists and this CTA's own vectors are in the ring; walk the levels on chip
@@ -511,6 +583,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
             for (int j = 0; j < M; ++j) vs[l * M + j] = val[j];
           }
           csync();
+          SWEEP_PROF(11)
           for (int lv = 0; lv < T.n_levels; ++lv) {
             if (lv > 0) {  // leaves have no children
               for (int v = T.lvl_sep[lv] + tid; v < T.lvl_sep[lv + 1]; v += CT) {
@@ -548,10 +621,12 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
             }
             csync();
           }
+          SWEEP_PROF(12)
           for (int l = tid; l < T.n_int * M; l += CT) a.xi[int64_t(e.o1) * M + l] = vs[l];
           const int zr = T.zl_size - T.n_rootb;  // the root is the last node
           for (int q = tid; q < T.n_rootb * M; q += CT) a.z[int64_t(e.o0) * M + q] = zl[zr * M + q];
           fence_async_global();  // xi is streamed back by TMA in the backward entry
+          SWEEP_PROF(13)
         } else {
           const int *xb = reinterpret_cast<const int *>(reg + e.n[0]);
           const double *zs = reg + e.n[0] + e.n[1];  // accumulated right-hand sides of the interior variables
@@ -563,6 +638,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
             for (int j = 0; j < M; ++j) xs[(T.n_int + q) * M + j] = __ldcg(a.x + d * M + j);
           }
           csync();
+          SWEEP_PROF(8)
           for (int lv = T.n_levels - 1; lv >= 0; --lv) {
             // input vectors [z_s ; x_b] of the level's fronts
             const int g0 = T.gl_lvl[lv], g1 = T.gl_lvl[lv + 1];
@@ -603,6 +679,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
             }
             csync();
           }
+          SWEEP_PROF(9)
           // pressure recovery p = p_old - M^-1 K_pu u for the cells of the box; next right-hand side source
           for (int c = tid; c < ncell; c += CT) {
             const int el = T.cell_edge[4 * c], er = T.cell_edge[4 * c + 1], eb = T.cell_edge[4 * c + 2],
@@ -630,6 +707,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
             }
           }
           fence_async_global();  // the box pressures are streamed back by TMA in the next step
+          SWEEP_PROF(10)
           if (bq >= 0) {  // subdom_to_st_distribute: flux traces of the interface dofs
             for (int l = tid; l < T.n_int * M; l += CT) {
               const int q = a.sub_q[bq + l];
@@ -655,11 +733,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
 
       // ---- end of entry: every warp reports on its own ----------------------------------------------------------
       if (a.prof && tid == 0) {
-        a.prof[cta * 8 + kind] += clock64() - t_entry;
-        a.prof[cta * 8 + 6] += 1;
+        a.prof[cta * 16 + kind] += clock64() - t_entry;
+        a.prof[cta * 16 + 6] += 1;
       }
       __syncwarp();
-      if (lane == 0) bar_arrive(done_bar + slot);
+      if (lane == 0) done_signal(done_cnt + slot);
     }
   }
 }

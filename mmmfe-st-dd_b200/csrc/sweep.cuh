@@ -26,7 +26,7 @@ namespace mmmfe {
 
 constexpr int SWEEP_COMPUTE = 256;                 // compute threads (8 warps)
 constexpr int SWEEP_THREADS = SWEEP_COMPUTE + 64;  // + retire warp + dependency warp
-constexpr int SWEEP_NBAR = 16;                     // barrier slots = most entries in flight per CTA
+constexpr int SWEEP_NBAR = 32;                     // slots = most entries in flight per CTA (one service lane each)
 constexpr int SWEEP_TMPL_HDR = 48;                 // int32 header words of a packed subtree template
 constexpr int SWEEP_SEGS = 4;                      // TMA copies per entry
 
@@ -78,7 +78,7 @@ struct SweepArgs {
   double *xi;                   // subtree-interior right-hand sides after the forward pass
   double *ptil;                 // [cell][M], box-major cell order
   uint32_t *cnt;                // completion counters (2 per sweep node: forward, backward)
-  volatile int *abort_flag;     // pinned host memory: set when a spin-wait gave up
+  volatile int *abort_flag;     // device memory: set when a spin-wait gave up
   long long *prof;              // optional [n_cta][8] cycle counters
   const double *minv;           // 1 / (c0 |cell|), box-major cell order; nullptr: minv_const everywhere
   double minv_const;

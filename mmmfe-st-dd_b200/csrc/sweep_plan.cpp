@@ -432,7 +432,7 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
   S.tmpl_dbl = even((L.tmpl16_max + 3) / 4);
   S.ws_dbl = even(int64_t(std::max(L.f_max, L.sub_ws_max)) * M);
   const int64_t ring = (total_dbl - fixed - S.tmpl_dbl - S.ws_dbl) & ~int64_t(1);
-  if (double(ring) < std::max(2.0, min_fill) * double(S.entry_max)) {
+  if (double(ring) < std::max(1.0, min_fill) * double(S.entry_max)) {
     std::snprintf(g_msg, sizeof g_msg, "shared-memory ring (%lld doubles) is too small for entries of %d doubles",
                   (long long)ring, S.entry_max);
     return g_msg;
