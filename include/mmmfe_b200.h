@@ -82,7 +82,8 @@ const char *mmmfe_version(void);
  * "leaf_cells" (default 4: nested-dissection leaf size), "subtree_cells" (default 256: largest box solved by one CTA
  * from shared memory; 0 disables the subtree kernels), "use_sweep" (default 1: run the star sweeps in the
  * persistent sweep kernel when the matrix has the RT0 structure), "sweep_chunk" (doubles per streamed chunk),
- * "sweep_min_fill" (entries the shared-memory ring must hold), "sweep_evict_first" (L2 hint of the factor stream). */
+ * "sweep_min_fill" (entries the shared-memory ring must hold), "sweep_evict_first" (L2 hint of the factor stream),
+ * "sweep_compute_threads" (64, 128 or 256 compute threads per CTA), "sweep_ctas_per_sm" (resident CTAs per SM). */
 int mmmfe_set_option(mmmfe_ctx *ctx, const char *key, double value);
 
 /* ---- multi-GPU: one process per GPU, subdomains sharded over ranks ------------------------------------------ */
@@ -215,8 +216,8 @@ int mmmfe_nd_tree_sizes(int32_t nx, int32_t ny, int32_t leaf_cells, int64_t size
  * negative = failure with a message.  stats = {sweep nodes, top fronts, entries, factor doubles, ring doubles,
  * workspace doubles, largest entry doubles, shared memory bytes}.                                             */
 int mmmfe_sweep_plan_check(int32_t nx, int32_t ny, int32_t leaf_cells, int32_t subtree_cells, int32_t M,
-                           int32_t n_cta, int64_t smem_bytes, int32_t n_steps, int64_t stats[8], char *msg,
-                           int32_t msg_cap);
+                           int32_t n_cta, int64_t smem_bytes, int32_t n_steps, int32_t compute_threads,
+                           int32_t chunk_doubles, int64_t stats[8], char *msg, int32_t msg_cap);
 int mmmfe_nd_tree_fill(int32_t nx, int32_t ny, int32_t leaf_cells, int32_t *node_table, int64_t *offsets,
                        int32_t *idx, int32_t *src);
 

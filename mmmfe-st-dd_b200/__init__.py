@@ -89,8 +89,8 @@ def load_engine():
         "mmmfe_profile_sweeps": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p, c_f64p, c_i32p, c_i32p]),
         "mmmfe_stat": (ctypes.c_int64, [vp, ctypes.c_char_p]),
         "mmmfe_profile_sweep_cycles": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p]),
-        "mmmfe_sweep_plan_check": (ctypes.c_int, [ctypes.c_int32] * 6 + [ctypes.c_int64, ctypes.c_int32, c_i64p,
-                                                  ctypes.c_char_p, ctypes.c_int32]),
+        "mmmfe_sweep_plan_check": (ctypes.c_int, [ctypes.c_int32] * 6 + [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                                  ctypes.c_int32, c_i64p, ctypes.c_char_p, ctypes.c_int32]),
         "mmmfe_nd_tree_sizes": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_i64p]),
         "mmmfe_nd_tree_fill": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_i32p, c_i64p, c_i32p,
                                               c_i32p]),
@@ -298,13 +298,14 @@ class Engine:
         return out
 
 
-def sweep_plan_check(nx, ny, leaf_cells=4, subtree_cells=128, M=1, n_cta=296, smem_bytes=115000, n_steps=3):
+def sweep_plan_check(nx, ny, leaf_cells=4, subtree_cells=128, M=1, n_cta=296, smem_bytes=115000, n_steps=3,
+                     compute_threads=256, chunk_doubles=2048):
     """Builds the persistent-kernel schedule on the host and replays it on the CPU; returns (rc, stats, message)."""
     lib = load_engine()
     stats = np.zeros(8, dtype=np.int64)
     msg = ctypes.create_string_buffer(256)
     rc = lib.mmmfe_sweep_plan_check(nx, ny, leaf_cells, subtree_cells, M, n_cta, smem_bytes, n_steps,
-                                    _ptr(stats, c_i64p), msg, 256)
+                                    compute_threads, chunk_doubles, _ptr(stats, c_i64p), msg, 256)
     keys = ["nodes", "top_fronts", "entries", "factor_doubles", "ring_doubles", "ws_doubles", "max_entry_doubles",
             "smem_bytes"]
     return rc, dict(zip(keys, (int(v) for v in stats))), msg.value.decode()

@@ -114,7 +114,7 @@ struct Factor {
   std::vector<int32_t> p_of_cell_h;  // canonical cell -> user pressure index
   bool p_identity = true;
   SweepLayout lay;
-  int32_t sweep_n_cta = 0;
+  int32_t sweep_n_cta = 0, sweep_ct = 128;
   size_t sweep_budget = 0;
   DevBuf<double> Rs, minv_c;
   double minv_const = 0.0;
@@ -173,8 +173,9 @@ struct mmmfe_ctx {
   int device = 0;
   std::string err;
   bool keep_history = true, use_graphs = true, use_sweep = true, sweep_evict_first = true;
-  int leaf_cells = 4, subtree_cells = 256, sweep_chunk = 2048;
-  double sweep_min_fill = 2.0;
+  int leaf_cells = 4, subtree_cells = 256, sweep_chunk = 1024, sweep_ct = 128, sweep_ctas_per_sm = 4;
+  double sweep_min_fill = 1.75;
+  int sweep_spin_ns = 100;
   bool is_setup = false, bar_done = false, final_done = false;
   int rank = 0, world = 1;
   std::vector<int32_t> owner;
@@ -409,19 +410,19 @@ static bool detect_rt0(const Sub &sd, const HostCsr &kup, const HostCsr &kpu, co
 }
 
 // resident sweep CTAs per SM and the dynamic shared memory each may use
-static void sweep_geometry(int device, int M, int32_t &n_cta, size_t &budget) {
+static void sweep_geometry(int device, int M, int ct, int want_per_sm, int32_t &n_cta, size_t &budget) {
   int sms = 0, per_sm = 0, reserved = 0, optin = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
   cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, device);
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-  budget = std::min<size_t>(size_t(optin), size_t(per_sm) / 2 - size_t(reserved)) - 256;
-  int per = sweep_ctas_per_sm(M, budget);
-  if (per < 2) {  // register-limited: one CTA per SM with the whole shared memory
-    budget = size_t(optin) - 256;
-    per = std::max(1, sweep_ctas_per_sm(M, budget));
+  int per = std::max(1, want_per_sm);
+  for (; per >= 1; --per) {  // as many CTAs per SM as asked for, fewer when registers or threads do not allow it
+    budget = (std::min<size_t>(size_t(optin), size_t(per_sm) / per - size_t(reserved)) - 128) & ~size_t(127);
+    if (sweep_ctas_per_sm(M, ct, budget) >= per) break;
   }
-  n_cta = std::min(per, 2) * sms;
+  per = std::max(per, 1);
+  n_cta = per * sms;
 }
 
 // Factor in streaming order + the device copies of the layout tables (after the numeric factorisation).
@@ -478,7 +479,8 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax) 
     fail(MMMFE_E_INVALID, "n_flux %d does not match an RT0 grid %dx%d", sd.nf, sd.nx, sd.ny);
   F->rt0 = detect_rt0(sd, kup, kpu, dof_of_canon, *F);
   bool want_sweep = c->use_sweep && F->rt0 && c->subtree_cells > 0;
-  if (want_sweep) sweep_geometry(c->device, Mmax, F->sweep_n_cta, F->sweep_budget);
+  F->sweep_ct = c->sweep_ct;
+  if (want_sweep) sweep_geometry(c->device, Mmax, F->sweep_ct, c->sweep_ctas_per_sm, F->sweep_n_cta, F->sweep_budget);
   bool sweep_planned = false;
   for (int cells = c->subtree_cells;; cells /= 2) {  // largest subtrees whose factor blob + vectors fit on chip twice per SM
     tr.build(sd.nx, sd.ny, c->leaf_cells, cells);
@@ -495,7 +497,7 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax) 
     {
       std::vector<int32_t> iu(tr.idx.size());
       for (size_t i = 0; i < tr.idx.size(); ++i) iu[i] = dof_of_canon.empty() ? tr.idx[i] : dof_of_canon[tr.idx[i]];
-      if (build_sweep_layout(tr, iu, dof_of_canon, F->sweep_n_cta, c->sweep_chunk, F->lay) != nullptr) { want_sweep = false; break; }
+      if (build_sweep_layout(tr, iu, dof_of_canon, F->sweep_n_cta, c->sweep_chunk, F->sweep_ct, F->lay) != nullptr) { want_sweep = false; break; }
     }
     SweepSchedule probe;
     if (build_sweep_schedule(tr, F->lay, Mmax, F->sweep_budget, c->sweep_min_fill, probe) == nullptr) { sweep_planned = true; break; }
@@ -953,7 +955,7 @@ static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> 
   if (build_sweep_schedule(tr, F.lay, b.M, F.sweep_budget, 1.0, S) != nullptr) return;
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-  if (sweep_ctas_per_sm(b.M, S.smem_bytes) * sms < F.sweep_n_cta) return;  // grid would not be co-resident
+  if (sweep_ctas_per_sm(b.M, F.sweep_ct, S.smem_bytes) * sms < F.sweep_n_cta) return;  // grid would not be co-resident
   const int M = b.M;
   // boundary entries: the interface dofs of every member (same enumeration as tr_*); per boundary subtree a table
   // [interior variable][member] -> entry
@@ -1022,6 +1024,7 @@ static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> 
   a.n_steps = b.nt; a.level0 = 0;
   a.tmpl_dbl = S.tmpl_dbl; a.ws_dbl = S.ws_dbl; a.ring_dbl = S.ring_dbl;
   a.evict_first = c->sweep_evict_first ? 1 : 0;
+  a.spin_ns = uint32_t(c->sweep_spin_ns);
   if (!c->abort_flag) {
     CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&c->abort_flag), sizeof(int)));
     CUDA_CHECK(cudaMemset(c->abort_flag, 0, sizeof(int)));
@@ -1035,7 +1038,7 @@ static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> 
 static void run_sweep_kernel(mmmfe_ctx *c, Batch &b) {
   CUDA_CHECK(cudaMemsetAsync(b.s_ptil.p, 0, b.s_ptil.n * sizeof(double), c->stream));
   CUDA_CHECK(cudaMemsetAsync(b.s_cnt.p, 0, b.s_cnt.n * sizeof(uint32_t), c->stream));
-  const cudaError_t err = launch_sweep(b.M, b.sargs, b.factor->sweep_n_cta, b.sweep_smem, c->stream);
+  const cudaError_t err = launch_sweep(b.M, b.factor->sweep_ct, b.sargs, b.factor->sweep_n_cta, b.sweep_smem, c->stream);
   if (err != cudaSuccess) fail(MMMFE_E_CUDA, "sweep kernel launch failed: %s", cudaGetErrorString(err));
 }
 
@@ -1215,6 +1218,12 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   else if (k == "use_sweep") c->use_sweep = value != 0;
   else if (k == "sweep_evict_first") c->sweep_evict_first = value != 0;
   else if (k == "sweep_chunk") c->sweep_chunk = std::max(256, int(value)) & ~1;
+  else if (k == "sweep_compute_threads") {
+    if (value != 64 && value != 128 && value != 256) { c->err = "sweep_compute_threads must be 64, 128 or 256"; return MMMFE_E_INVALID; }
+    c->sweep_ct = int(value);
+  }
+  else if (k == "sweep_ctas_per_sm") c->sweep_ctas_per_sm = std::max(1, int(value));
+  else if (k == "sweep_spin_ns") c->sweep_spin_ns = std::max(0, int(value));
   else if (k == "sweep_min_fill") c->sweep_min_fill = value;
   else { c->err = "unknown option " + k; return MMMFE_E_INVALID; }
   return MMMFE_OK;
@@ -1558,7 +1567,7 @@ int mmmfe_profile_sweep_cycles(mmmfe_ctx *c, int32_t batch, double out[16]) {
       a.prof = prof.p;
       CUDA_CHECK(cudaMemsetAsync(b.s_ptil.p, 0, b.s_ptil.n * sizeof(double), c->stream));
       CUDA_CHECK(cudaMemsetAsync(b.s_cnt.p, 0, b.s_cnt.n * sizeof(uint32_t), c->stream));
-      const cudaError_t err = launch_sweep(b.M, a, n_cta, b.sweep_smem, c->stream);
+      const cudaError_t err = launch_sweep(b.M, b.factor->sweep_ct, a, n_cta, b.sweep_smem, c->stream);
       if (err != cudaSuccess) fail(MMMFE_E_CUDA, "sweep kernel launch failed: %s", cudaGetErrorString(err));
       CUDA_CHECK(cudaStreamSynchronize(c->stream));
       check_watchdog(c);
@@ -1586,7 +1595,7 @@ int mmmfe_profile_sweeps(mmmfe_ctx *c, int32_t cap, double *ms, double *bytes_pe
       CUDA_CHECK(cudaMemsetAsync(b.s_ptil.p, 0, b.s_ptil.n * sizeof(double), c->stream));
       CUDA_CHECK(cudaMemsetAsync(b.s_cnt.p, 0, b.s_cnt.n * sizeof(uint32_t), c->stream));
       CUDA_CHECK(cudaEventRecord(c->ev_t0, c->stream));
-      const cudaError_t err = launch_sweep(b.M, b.sargs, b.factor->sweep_n_cta, b.sweep_smem, c->stream);
+      const cudaError_t err = launch_sweep(b.M, b.factor->sweep_ct, b.sargs, b.factor->sweep_n_cta, b.sweep_smem, c->stream);
       if (err != cudaSuccess) fail(MMMFE_E_CUDA, "sweep kernel launch failed: %s", cudaGetErrorString(err));
       CUDA_CHECK(cudaEventRecord(c->ev_t1, c->stream));
       CUDA_CHECK(cudaStreamSynchronize(c->stream));

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) k_repack_sub(const RepackSub *__restrict_
   const RepackSub d = desc[blockIdx.x];
   for (int k = threadIdx.x; k < d.rf_size; k += blockDim.x) Rs[d.new_rf + k] = R[d.old_rf + k];
   const int32_t *pm = perm + d.perm_off;
-  for (int k = threadIdx.x; k < d.rb_size; k += blockDim.x) Rs[d.new_rb + k] = R[d.old_rb + pm[k]];
+  for (int k = threadIdx.x; k < d.rb_size; k += blockDim.x) Rs[d.new_rb + k] = pm[k] < 0 ? 0.0 : R[d.old_rb + pm[k]];
 }
 
 void launch_repack_sub(const RepackSub *d_desc, int32_t n_desc, const int32_t *perm, const double *R_old, double *Rs,
@@ -58,7 +58,6 @@ void launch_repack_sub(const RepackSub *d_desc, int32_t n_desc, const int32_t *p
 namespace {
 
 constexpr int NB = SWEEP_NBAR;
-constexpr int CT = SWEEP_COMPUTE;
 constexpr int SWEEP_POLL_WINDOW = 4;  // entries ahead of the oldest unopened one that poll completion counters
 
 __device__ __forceinline__ uint32_t s_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -149,7 +148,10 @@ __device__ __forceinline__ void done_wait(const uint32_t *cnt, uint32_t target, 
 }
 
 // compute warps only
-__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;\n" ::"n"(CT) : "memory"); }
+template <int CT>
+__device__ __forceinline__ void csync_t() {
+  asm volatile("bar.sync 1, %0;\n" ::"n"(CT) : "memory");
+}
 
 // generic-proxy global writes that a later TMA (async proxy) read of this CTA must see
 __device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy.async.global;\n" ::: "memory"); }
@@ -160,16 +162,21 @@ __device__ __forceinline__ int t16(const uint16_t *p, int i) {
 }
 
 struct Tmpl {  // views into the shared-memory copy of a packed template (layout: sweep_plan.cpp pack_template)
-  int n_levels, n_int, n_rootb, zl_size, w, h, scratch;
-  const uint16_t *var_code, *sep_c0, *sep_c1, *out_rf, *out_sb, *out_v, *out_c0, *out_c1, *lvl_sep, *lvl_out,
-      *cell_edge, *row_off, *row_len, *row_w, *gl_lvl, *gl_src, *tpo;
+  int n_levels, n_int, n_rootb, zl_size, w, h;
+  const uint16_t *var_code, *cell_edge, *lvl_out, *in_idx;
+  const uint4 *fdesc;   // 8 uint16 per forward output
+  const uint32_t *sc;   // 2 uint16 per separator variable
+  const int4 *lvlb;     // per backward level
+  const uint2 *bdesc;   // 4 uint16 per variable
   __device__ __forceinline__ explicit Tmpl(const uint16_t *tb) {
     const int *h32 = reinterpret_cast<const int *>(tb);
-    n_levels = h32[1]; n_int = h32[2]; n_rootb = h32[3]; zl_size = h32[4]; w = h32[7]; h = h32[8]; scratch = h32[27];
-    var_code = tb + h32[10]; sep_c0 = tb + h32[11]; sep_c1 = tb + h32[12]; out_rf = tb + h32[13];
-    out_sb = tb + h32[14]; out_v = tb + h32[15]; out_c0 = tb + h32[16]; out_c1 = tb + h32[17];
-    lvl_sep = tb + h32[18]; lvl_out = tb + h32[19]; cell_edge = tb + h32[20]; row_off = tb + h32[21];
-    row_len = tb + h32[22]; row_w = tb + h32[23]; gl_lvl = tb + h32[24]; gl_src = tb + h32[25]; tpo = tb + h32[26];
+    n_levels = h32[0]; n_int = h32[1]; n_rootb = h32[2]; zl_size = h32[3]; w = h32[4]; h = h32[5];
+    var_code = tb + h32[9]; cell_edge = tb + h32[10]; lvl_out = tb + h32[11];
+    fdesc = reinterpret_cast<const uint4 *>(tb + h32[12]);
+    sc = reinterpret_cast<const uint32_t *>(tb + h32[13]);
+    lvlb = reinterpret_cast<const int4 *>(tb + h32[14]);
+    bdesc = reinterpret_cast<const uint2 *>(tb + h32[15]);
+    in_idx = tb + h32[16];
   }
 };
 
@@ -191,8 +198,9 @@ __device__ __forceinline__ int64_t sweep_dof(const SweepArgs &a, int I0, int J0,
     t_mark = t_now;                                          \
   }
 
-template <int M>
-__global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
+template <int M, int CT>
+__global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))) k_sweep(const SweepArgs a) {
+  auto csync = [] { csync_t<CT>(); };
   extern __shared__ __align__(128) double sm[];
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(sm);  // TMA data of the entry landed
   uint32_t *done_cnt = reinterpret_cast<uint32_t *>(full_bar + NB);  // compute warps that finished the slot's entries
@@ -274,7 +282,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
       for (long long g = 0; g < target; ++g) issue_one(g, iss[g % P]);
     }
     // One converged polling loop: lane l owns slot l and retires the entries G = l (mod NB) in turn.
-    long long G = lane;
+    long long G = lane < NB ? lane : total;
     int flags = 0, sig = -1;
     long long first = 0, upto = 0;
     auto load_info = [&](long long g) {
@@ -293,7 +301,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
       bool progress = false;
       if (have) {
         uint32_t v;
-        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];\n" : "=r"(v) : "r"(s_u32(done_cnt + lane)) : "memory");
+        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];\n" : "=r"(v) : "r"(s_u32(done_cnt + (lane & (NB - 1)))) : "memory");
         if (v >= uint32_t(G / NB + 1) * uint32_t(CT / 32)) {
           progress = true;
           if ((flags & SWF_LAST) && sig >= 0) red_release(a.cnt + sig);
@@ -304,7 +312,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
           t0 = clock64();
         }
       }
-      if (!__any_sync(0xffffffffu, progress)) __nanosleep(100);
+      if (!__any_sync(0xffffffffu, progress)) __nanosleep(a.spin_ns);
       if ((spins & 1023) == 0 && have && spin_expired(t0, a.abort_flag)) have = false;
     }
     return;
@@ -316,7 +324,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
     // soon as the slot is free (up to NB entries ahead of the compute warps), then waits for the entry's producers
     // on other CTAs, then opens the slot for the compute warps
     // =============================================================================================================
-    long long G = lane;
+    long long G = lane < NB ? lane : total;
     bool have = G < total;
     int state = 0;
     int4 d[8];
@@ -335,14 +343,15 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
         bool free_slot = G < NB;
         if (!free_slot) {
           uint32_t v;
-          asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];\n" : "=r"(v) : "r"(s_u32(done_cnt + lane)) : "memory");
+          asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];\n" : "=r"(v) : "r"(s_u32(done_cnt + (lane & (NB - 1)))) : "memory");
           free_slot = v >= uint32_t(G / NB) * uint32_t(CT / 32);
         }
         if (free_slot) {
 #pragma unroll
-          for (int t = 0; t < 8; ++t) reinterpret_cast<int4 *>(&edesc[lane])[t] = d[t];
+          for (int t = 0; t < 8; ++t) reinterpret_cast<int4 *>(&edesc[lane & (NB - 1)])[t] = d[t];
           const int kind = d[0].x, fl = d[0].y;
-          const bool waits = kind == SW_SUB_BWD || ((kind == SW_TOP_FWD || kind == SW_TOP_BWD) && (fl & SWF_NEW_RUN));
+          const bool waits = kind == SW_SUB_BWD || ((kind == SW_TOP_FWD || kind == SW_TOP_BWD) &&
+                                                    (fl & SWF_NEW_RUN) && (fl & SWF_FIRST));
           const uint32_t step1 = uint32_t(G / P) + 1u;
           dep0 = waits ? d[1].y : -1;
           dep1 = waits ? d[1].w : -1;
@@ -363,7 +372,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
         if (ok) {
           if (a.prof && (dep0 >= 0 || dep1 >= 0))
             atomicAdd(reinterpret_cast<unsigned long long *>(a.prof + cta * 16 + 4), (unsigned long long)(clock64() - t_wait));
-          bar_arrive(dep_bar + lane);  // release: the descriptor stores above are visible to the waiters
+          bar_arrive(dep_bar + (lane & (NB - 1)));  // release: the descriptor stores above are visible to the waiters
           G += NB;
           have = G < total;
           state = 0;
@@ -372,7 +381,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
           progress = true;
         }
       }
-      if (!__any_sync(0xffffffffu, progress)) __nanosleep(100);
+      if (!__any_sync(0xffffffffu, progress)) __nanosleep(a.spin_ns);
       if ((spins & 255) == 0 && have && spin_expired(t0, a.abort_flag)) have = false;
     }
     return;
@@ -412,18 +421,20 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
         // column block of a top-level front
         // ---------------------------------------------------------------------------------------------------------
         const bool fwd = kind == SW_TOP_FWD;
-        const int s = e.a4, b = e.a5, f = s + b;
+        const int s = e.a4, b = e.a5;
         const int cw = e.a1, col0 = e.a0;  // cw: power of two below 32, any even width from 32 to 256
         const int *gl = reinterpret_cast<const int *>(reg);
         const int *cl = reinterpret_cast<const int *>(reg + e.n[0]);
         const double *tile = reg + e.n[0] + e.n[1];
+        const int r_beg = e.a2, r_end = e.a3;
         if (flags & SWF_NEW_RUN) {
-          csync();  // every warp is done with the previous run's vector
+          csync();  // every warp is done with the previous vector
           if (fwd) {
-            // v = rhs of the separator dofs + children contributions (assemble_rhs_star fused: rhs = -K_up p_old)
+            // rows [r_beg, r_end) of v = rhs of the separator dofs + children contributions (assemble_rhs_star
+            // fused: rhs = -K_up p_old)
             const double k0 = e.a6 ? a.ky0 : a.kx0, k1 = e.a6 ? a.ky1 : a.kx1;
-            for (int p = tid; p < s; p += CT) {
-              const int4 gi = reinterpret_cast<const int4 *>(gl)[p];
+            for (int p = r_beg + tid; p < r_end; p += CT) {
+              const int4 gi = reinterpret_cast<const int4 *>(gl)[p - r_beg];
               double val[M];
 #pragma unroll
               for (int j = 0; j < M; ++j)
@@ -435,21 +446,21 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
 #pragma unroll
                 for (int j = 0; j < M; ++j) val[j] += __ldcg(a.z + int64_t(gi.w) * M + j);
 #pragma unroll
-              for (int j = 0; j < M; ++j) ws[p * M + j] = val[j];
+              for (int j = 0; j < M; ++j) ws[(p - r_beg) * M + j] = val[j];
               if (flags & SWF_WRITE_ZS)
 #pragma unroll
                 for (int j = 0; j < M; ++j) a.z[int64_t(e.o2 + p) * M + j] = val[j];
             }
           } else {
-            // w = [accumulated separator rhs ; solution of the boundary dofs (ancestors' separators)]
-            for (int p = tid; p < f; p += CT) {
+            // rows [r_beg, r_end) of w = [accumulated separator rhs ; solution of the boundary dofs]
+            for (int p = r_beg + tid; p < r_end; p += CT) {
               if (p < s) {
 #pragma unroll
-                for (int j = 0; j < M; ++j) ws[p * M + j] = __ldcg(a.z + int64_t(e.o2 + p) * M + j);
+                for (int j = 0; j < M; ++j) ws[(p - r_beg) * M + j] = __ldcg(a.z + int64_t(e.o2 + p) * M + j);
               } else {
-                const int64_t d = gl[p - s];
+                const int64_t d = gl[p - r_beg];
 #pragma unroll
-                for (int j = 0; j < M; ++j) ws[p * M + j] = __ldcg(a.x + d * M + j);
+                for (int j = 0; j < M; ++j) ws[(p - r_beg) * M + j] = __ldcg(a.x + d * M + j);
               }
             }
           }
@@ -478,18 +489,18 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
           const int g = tid / cw, col = tid - g * cw, gn = CT / cw;
           if (g < gn) {
             const double *tl = tile + col;
-            const int r_beg = e.a2, r_end = e.a3;
-            int r = r_beg + g;
-            for (; r + 3 * gn < r_end; r += 4 * gn) {
-              const double m0 = tl[(r - r_beg) * cw], m1 = tl[(r + gn - r_beg) * cw];
-              const double m2 = tl[(r + 2 * gn - r_beg) * cw], m3 = tl[(r + 3 * gn - r_beg) * cw];
+            const int nr = r_end - r_beg;
+            int r = g;
+            for (; r + 3 * gn < nr; r += 4 * gn) {
+              const double m0 = tl[r * cw], m1 = tl[(r + gn) * cw];
+              const double m2 = tl[(r + 2 * gn) * cw], m3 = tl[(r + 3 * gn) * cw];
 #pragma unroll
               for (int j = 0; j < M; ++j)
                 acc[j] += m0 * ws[r * M + j] + m1 * ws[(r + gn) * M + j] + m2 * ws[(r + 2 * gn) * M + j] +
                           m3 * ws[(r + 3 * gn) * M + j];
             }
-            for (; r < r_end; r += gn) {
-              const double m0 = tl[(r - r_beg) * cw];
+            for (; r < nr; r += gn) {
+              const double m0 = tl[r * cw];
 #pragma unroll
               for (int j = 0; j < M; ++j) acc[j] += m0 * ws[r * M + j];
             }
@@ -539,7 +550,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
         csync();  // every warp is done with the workspace (and the template) of the previous entry
         if (e.a0 != cur_tmpl) {
           const int64_t off = a.tmpl_off[e.a0];
-          const int n16 = reinterpret_cast<const int *>(a.tmpl16 + off)[9];
+          const int n16 = reinterpret_cast<const int *>(a.tmpl16 + off)[8];
           const int4 *g4 = reinterpret_cast<const int4 *>(a.tmpl16 + off);
           int4 *s4 = reinterpret_cast<int4 *>(tb);
           for (int k = tid; k < (n16 + 7) / 8; k += CT) s4[k] = g4[k];
@@ -552,8 +563,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
         const double *blob = reg;
         const double *pc = reg + e.n[0] + e.n[1] + e.n[2];  // pressures of the box (this CTA wrote them last step)
         if (kind == SW_SUB_FWD) {
-          double *vs = ws;
-          double *zl = vs + T.n_int * M;
+          double *vs = ws;                   // right-hand sides of the interior variables
+          double *va = vs + T.n_int * M;     // the same after the children's contributions (kept for the backward pass)
+          double *zl = va + T.n_int * M;     // boundary contributions of every node
           for (int l = tid; l < T.n_int; l += CT) {
             const int code = T.var_code[l];
             const int type = code >> 14, dj = (code >> 7) & 127, di = code & 127;
@@ -584,37 +596,43 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
           }
           csync();
           SWEEP_PROF(11)
+          // one phase per level: every boundary output of every node of the level; the separator values a node
+          // needs (own rhs + children's contributions) are formed on the fly, its first output stores them
           for (int lv = 0; lv < T.n_levels; ++lv) {
-            if (lv > 0) {  // leaves have no children
-              for (int v = T.lvl_sep[lv] + tid; v < T.lvl_sep[lv + 1]; v += CT) {
-                const int c0 = t16(T.sep_c0, v), c1 = t16(T.sep_c1, v);
-#pragma unroll
-                for (int j = 0; j < M; ++j) {
-                  double val = vs[v * M + j];
-                  if (c0 >= 0) val += zl[c0 * M + j];
-                  if (c1 >= 0) val += zl[c1 * M + j];
-                  vs[v * M + j] = val;
-                }
-              }
-              csync();
-            }
             for (int o = T.lvl_out[lv] + tid; o < T.lvl_out[lv + 1]; o += CT) {
-              const int sb = T.out_sb[o], s = sb >> 8, b = sb & 255;
-              const double *rf = blob + T.out_rf[o];
-              const double *v = vs + int(T.out_v[o]) * M;
-              const int c0 = t16(T.out_c0, o), c1 = t16(T.out_c1, o);
+              const uint4 D = T.fdesc[o];
+              const int rf_off = D.x & 0xFFFF, sb = D.x >> 16, sep0 = D.y & 0xFFFF, writer = D.y >> 16;
+              const int c0 = D.z & 0xFFFF, c1 = D.z >> 16;
+              const int s = sb >> 8, b = sb & 255;
+              const double *rf = blob + rf_off;
               double av[M];
 #pragma unroll
               for (int j = 0; j < M; ++j) {
                 av[j] = 0.0;
-                if (c0 >= 0) av[j] += zl[c0 * M + j];
-                if (c1 >= 0) av[j] += zl[c1 * M + j];
+                if (c0 != 0xFFFF) av[j] += zl[c0 * M + j];
+                if (c1 != 0xFFFF) av[j] += zl[c1 * M + j];
               }
-#pragma unroll 4
+#pragma unroll 2
               for (int k = 0; k < s; ++k) {
+                double vk[M];
+#pragma unroll
+                for (int j = 0; j < M; ++j) vk[j] = vs[(sep0 + k) * M + j];
+                if (lv > 0) {  // leaves have no children
+                  const uint32_t cc = T.sc[sep0 + k];
+                  const int k0 = cc & 0xFFFF, k1 = cc >> 16;
+                  if (k0 != 0xFFFF)
+#pragma unroll
+                    for (int j = 0; j < M; ++j) vk[j] += zl[k0 * M + j];
+                  if (k1 != 0xFFFF)
+#pragma unroll
+                    for (int j = 0; j < M; ++j) vk[j] += zl[k1 * M + j];
+                }
                 const double r = rf[k * b];
 #pragma unroll
-                for (int j = 0; j < M; ++j) av[j] += r * v[k * M + j];
+                for (int j = 0; j < M; ++j) av[j] += r * vk[j];
+                if (writer)
+#pragma unroll
+                  for (int j = 0; j < M; ++j) va[(sep0 + k) * M + j] = vk[j];
               }
 #pragma unroll
               for (int j = 0; j < M; ++j) zl[o * M + j] = av[j];
@@ -622,7 +640,22 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
             csync();
           }
           SWEEP_PROF(12)
-          for (int l = tid; l < T.n_int * M; l += CT) a.xi[int64_t(e.o1) * M + l] = vs[l];
+          if (T.n_rootb == 0) {  // the subtree is the whole subdomain: its root has no boundary, hence no output
+            const int v0 = T.lvlb[T.n_levels - 1].x, n_out = T.lvlb[T.n_levels - 1].y;
+            for (int v = v0 + tid; v < v0 + n_out; v += CT) {
+              const uint32_t cc = T.sc[v];
+              const int k0 = cc & 0xFFFF, k1 = cc >> 16;
+#pragma unroll
+              for (int j = 0; j < M; ++j) {
+                double vk = vs[v * M + j];
+                if (T.n_levels > 1 && k0 != 0xFFFF) vk += zl[k0 * M + j];
+                if (T.n_levels > 1 && k1 != 0xFFFF) vk += zl[k1 * M + j];
+                va[v * M + j] = vk;
+              }
+            }
+            csync();
+          }
+          for (int l = tid; l < T.n_int * M; l += CT) a.xi[int64_t(e.o1) * M + l] = va[l];
           const int zr = T.zl_size - T.n_rootb;  // the root is the last node
           for (int q = tid; q < T.n_rootb * M; q += CT) a.z[int64_t(e.o0) * M + q] = zl[zr * M + q];
           fence_async_global();  // xi is streamed back by TMA in the backward entry
@@ -631,7 +664,6 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
           const int *xb = reinterpret_cast<const int *>(reg + e.n[0]);
           const double *zs = reg + e.n[0] + e.n[1];  // accumulated right-hand sides of the interior variables
           double *xs = ws;                          // solution: [interior | root boundary]
-          double *scr = xs + (T.n_int + T.n_rootb) * M;
           for (int q = tid; q < T.n_rootb; q += CT) {
             const int64_t d = xb[q];
 #pragma unroll
@@ -639,35 +671,29 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 2) k_sweep(const SweepArgs a) {
           }
           csync();
           SWEEP_PROF(8)
+          // one phase per level: x_s = [F11^-1 | -G^T] [z_s ; x_b], 2^tl lanes per row, inputs read in place
           for (int lv = T.n_levels - 1; lv >= 0; --lv) {
-            // input vectors [z_s ; x_b] of the level's fronts
-            const int g0 = T.gl_lvl[lv], g1 = T.gl_lvl[lv + 1];
-            for (int k = g0 + tid; k < g1; k += CT) {
-              const int sidx = T.gl_src[k];
-              const double *from = (sidx & 0x8000) ? xs + (sidx & 0x7fff) * M : zs + sidx * M;
-#pragma unroll
-              for (int j = 0; j < M; ++j) scr[(k - g0) * M + j] = from[j];
-            }
-            csync();
-            // x_s = [F11^-1 | -G^T] [z_s ; x_b]: tpo lanes per row, rows of the level side by side
-            const int tpo = T.tpo[lv], per = CT / tpo;
-            const int grp = tid / tpo, rl = tid - grp * tpo;
-            const int v0 = T.lvl_sep[lv], n_out = T.lvl_sep[lv + 1] - v0;
+            const int4 Lh = T.lvlb[lv];
+            const int v0 = Lh.x, n_out = Lh.y, tl = Lh.z, estep = Lh.w;
+            const int tpo = 1 << tl, per = CT >> tl;
+            const int grp = tid >> tl, rl = tid & (tpo - 1);
             for (int o0 = 0; o0 < n_out; o0 += per) {
               const int o = o0 + grp;
               double av[M];
 #pragma unroll
               for (int j = 0; j < M; ++j) av[j] = 0.0;
               if (o < n_out) {
-                const int v = v0 + o;
-                const double *row = blob + T.row_off[v];
-                const double *w = scr + int(T.row_w[v]) * M;
-                const int len = T.row_len[v];
+                const uint2 D = T.bdesc[v0 + o];
+                const int row_off = D.x & 0xFFFF, len = D.x >> 16, in_off = D.y & 0xFFFF;
+                const double *row = blob + row_off;
+                const uint16_t *in = T.in_idx + in_off;
 #pragma unroll 4
                 for (int p = rl; p < len; p += tpo) {
-                  const double r = row[p];
+                  const int sidx = in[p * estep];
+                  const double r = row[p * estep];
+                  const double *from = (sidx & 0x8000) ? xs + (sidx & 0x7fff) * M : zs + sidx * M;
 #pragma unroll
-                  for (int j = 0; j < M; ++j) av[j] += r * w[p * M + j];
+                  for (int j = 0; j < M; ++j) av[j] += r * from[j];
                 }
               }
               for (int off = tpo >> 1; off > 0; off >>= 1)
@@ -749,37 +775,48 @@ size_t sweep_smem_optin() {
   return size_t(optin);
 }
 
-int sweep_fixed_dbl(int M) { return 19 * SWEEP_NBAR + 2 * SWEEP_COMPUTE * M; }
+int sweep_fixed_dbl(int M, int ct) { return 19 * SWEEP_NBAR + 2 * ct * M; }
 
-template <int M>
+template <int M, int CT>
 static int ctas_per_sm_t(size_t smem) {
-  cudaFuncSetAttribute(k_sweep<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  cudaFuncSetAttribute(k_sweep<M, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   int n = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sweep<M>, SWEEP_THREADS, smem) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_sweep<M, CT>, CT + 64, smem) != cudaSuccess) return 0;
   return n;
 }
 
-int sweep_ctas_per_sm(int M, size_t smem_bytes) {
-  switch (M) {
-    case 1: return ctas_per_sm_t<1>(smem_bytes);
-    case 2: return ctas_per_sm_t<2>(smem_bytes);
-    case 4: return ctas_per_sm_t<4>(smem_bytes);
-    default: return 0;
-  }
-}
-
-cudaError_t launch_sweep(int M, const SweepArgs &a, int32_t n_cta, size_t smem_bytes, cudaStream_t st) {
+template <int M, int CT>
+static cudaError_t launch_t(const SweepArgs &a, int32_t n_cta, size_t smem_bytes, cudaStream_t st) {
   void *args[] = {const_cast<SweepArgs *>(&a)};
-  const void *fn = nullptr;
-  switch (M) {
-    case 1: fn = reinterpret_cast<const void *>(k_sweep<1>); break;
-    case 2: fn = reinterpret_cast<const void *>(k_sweep<2>); break;
-    case 4: fn = reinterpret_cast<const void *>(k_sweep<4>); break;
-    default: return cudaErrorInvalidValue;
-  }
+  const void *fn = reinterpret_cast<const void *>(k_sweep<M, CT>);
   cudaError_t err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes));
   if (err != cudaSuccess) return err;
-  err = cudaLaunchCooperativeKernel(fn, dim3(n_cta), dim3(SWEEP_THREADS), args, smem_bytes, st);
+  return cudaLaunchCooperativeKernel(fn, dim3(n_cta), dim3(CT + 64), args, smem_bytes, st);
+}
+
+#define SWEEP_DISPATCH(M, CT, CALL)                                            \
+  switch ((M) * 1000 + (CT)) {                                                 \
+    case 1256: { constexpr int MM = 1, CC = 256; CALL; } break;                \
+    case 2256: { constexpr int MM = 2, CC = 256; CALL; } break;                \
+    case 4256: { constexpr int MM = 4, CC = 256; CALL; } break;                \
+    case 1128: { constexpr int MM = 1, CC = 128; CALL; } break;                \
+    case 2128: { constexpr int MM = 2, CC = 128; CALL; } break;                \
+    case 4128: { constexpr int MM = 4, CC = 128; CALL; } break;                \
+    case 1064: { constexpr int MM = 1, CC = 64; CALL; } break;                 \
+    case 2064: { constexpr int MM = 2, CC = 64; CALL; } break;                 \
+    case 4064: { constexpr int MM = 4, CC = 64; CALL; } break;                 \
+    default: break;                                                            \
+  }
+
+int sweep_ctas_per_sm(int M, int ct, size_t smem_bytes) {
+  int n = 0;
+  SWEEP_DISPATCH(M, ct, (n = ctas_per_sm_t<MM, CC>(smem_bytes)));
+  return n;
+}
+
+cudaError_t launch_sweep(int M, int ct, const SweepArgs &a, int32_t n_cta, size_t smem_bytes, cudaStream_t st) {
+  cudaError_t err = cudaErrorInvalidValue;
+  SWEEP_DISPATCH(M, ct, (err = launch_t<MM, CC>(a, n_cta, smem_bytes, st)));
   if (err == cudaSuccess) launch_counter_add(1);
   return err;
 }

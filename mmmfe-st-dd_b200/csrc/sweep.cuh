@@ -24,9 +24,8 @@
 
 namespace mmmfe {
 
-constexpr int SWEEP_COMPUTE = 256;                 // compute threads (8 warps)
-constexpr int SWEEP_THREADS = SWEEP_COMPUTE + 64;  // + retire warp + dependency warp
-constexpr int SWEEP_NBAR = 32;                     // slots = most entries in flight per CTA (one service lane each)
+// compute threads per CTA: 256, 128 or 64 (template parameter of the kernel); + retire warp + dependency warp
+constexpr int SWEEP_NBAR = 16;                     // slots = most entries in flight per CTA (one service lane each)
 constexpr int SWEEP_TMPL_HDR = 48;                 // int32 header words of a packed subtree template
 constexpr int SWEEP_SEGS = 4;                      // TMA copies per entry
 
@@ -38,10 +37,12 @@ enum SweepSrc : int32_t { SRC_FACTOR = 0, SRC_INDEX = 1, SRC_XI = 2, SRC_PTIL = 
 // (n[0..3] doubles each).
 //   top entries (column block [col0, col0 + cw) of a front, tile rows [r_beg, r_end)):
 //     a0 col0, a1 cw, a2 r_beg, a3 r_end, a4 s, a5 b, a6 separator type (0 x-edges, 1 y-edges), o2 zs_off, o3 zc_off
-//     segments: 0 gather list (first entry of a run), 1 column list (first chunk of a block), 2 tile
+//     segments: 0 gather list of the chunk's rows (unless the previous entry staged the same rows), 1 column list
+//     (first chunk of a block), 2 tile
 //       FWD tile = -G^T (s x b), reduces over the s separator rows; gather list int4 {cell A, cell B, child-0 z,
 //       child-1 z} per separator row; column list int2 {child-0 z, child-1 z} per boundary column
-//       BWD tile = [F11^-1 ; -G] ((s+b) x s); gather list int {x dof} per boundary row; column list int2 {dof, -}
+//       BWD tile = [F11^-1 ; -G] ((s+b) x s); gather list int {x dof} per row (separator rows unused); column list
+//       int2 {dof, -}
 //   subtree entries: a0 template, a1 boundary-entry table offset (-1: none), a2 I0, a3 J0, a7 instance,
 //     o0 zc_off (root boundary contributions), o1 xi_off, o2 ptil offset of the box (box-major cell order)
 //     segments: 0 factor blob, 1 root-boundary x dofs (BWD), 2 interior right-hand sides xi (BWD), 3 box pressures
@@ -101,6 +102,7 @@ struct SweepArgs {
   int32_t n_steps, level0;
   int32_t tmpl_dbl, ws_dbl, ring_dbl;  // shared-memory partition in doubles
   int32_t evict_first;
+  uint32_t spin_ns;             // back-off of the service warps' polling loops
 };
 
 // One block of the sweep layout: dst[r * cw + c] = value(r, col0 + c) (0 beyond ncols), r < rlen.
@@ -121,11 +123,11 @@ void launch_repack_sub(const RepackSub *d_desc, int32_t n_desc, const int32_t *p
                        cudaStream_t st);
 
 size_t sweep_smem_optin();
-// resident CTAs per SM of the sweep kernel for this much dynamic shared memory
-int sweep_ctas_per_sm(int M, size_t smem_bytes);
+// resident CTAs per SM of the sweep kernel (ct compute threads) for this much dynamic shared memory
+int sweep_ctas_per_sm(int M, int ct, size_t smem_bytes);
 // fixed shared-memory doubles of the kernel besides template, workspace and ring
-int sweep_fixed_dbl(int M);
+int sweep_fixed_dbl(int M, int ct);
 // cooperative launch; returns the CUDA error code
-cudaError_t launch_sweep(int M, const SweepArgs &a, int32_t n_cta, size_t smem_bytes, cudaStream_t st);
+cudaError_t launch_sweep(int M, int ct, const SweepArgs &a, int32_t n_cta, size_t smem_bytes, cudaStream_t st);
 
 }  // namespace mmmfe

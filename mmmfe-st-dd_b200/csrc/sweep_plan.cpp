@@ -23,23 +23,37 @@ int32_t even(int64_t v) { return int32_t((v + 1) & ~int64_t(1)); }
 
 char g_msg[256];
 
-// Template header (int32 words): 0 n_nodes, 1 n_levels, 2 n_int, 3 n_rootb, 4 zl_size, 5 rf_size, 6 rb_size, 7 w, 8 h,
-// 9 uint16 words in total, 27 scratch entries of the widest backward level; 10.. offsets (uint16 units from the blob
-// start) of: 10 var_code, 11 sep_c0, 12 sep_c1, 13 out_rf, 14 out_sb, 15 out_v, 16 out_c0, 17 out_c1, 18 lvl_sep,
-// 19 lvl_out, 20 cell_edge, 21 row_off, 22 row_len, 23 row_w, 24 gl_lvl, 25 gl_src, 26 tpo.
-const char *pack_template(const SubtreeTemplate &T, std::vector<uint16_t> &out, std::vector<int32_t> &perm) {
+// Packed subtree template (shared-memory resident while its subtrees are processed).
+// Header, int32 words: 0 n_levels, 1 n_int, 2 n_rootb, 3 zl_size, 4 w, 5 h, 6 rf_size, 7 rb_size (sweep layout),
+// 8 uint16 words in total; offsets in uint16 units from the blob start: 9 var_code, 10 cell_edge, 11 lvl_out,
+// 12 fdesc (8 uint16 per forward output: rf_off, s << 8 | b, sep0, writer flag, child-0 zl, child-1 zl, -, -),
+// 13 sc (2 uint16 per separator variable: child-0 zl, child-1 zl), 14 lvlb (4 int32 per backward level: first
+// variable, outputs, log2 lanes per output, element step), 15 bdesc (4 uint16 per variable: row offset, row
+// length, input-list offset, -), 16 in_idx (input of every row element: separator rhs index, or 0x8000 | solution
+// index).
+// Backward blob: levels with one lane per output are stored interleaved (element p of output o at
+// base + p * n_out + o: conflict-free), the others row-major; perm[k] = old position of element k, or -1 (zero).
+const char *pack_template(const SubtreeTemplate &T, int32_t ct, std::vector<uint16_t> &out, std::vector<int32_t> &perm,
+                          int32_t &rb2_size) {
   if (T.w > 127 || T.h > 127) return "subtree box wider than 127 cells";
   const size_t base = out.size();
   out.resize(base + 2 * SWEEP_TMPL_HDR, 0);
   std::vector<int32_t> hdr(SWEEP_TMPL_HDR, 0);
-  hdr[0] = T.n_nodes; hdr[1] = T.n_levels; hdr[2] = T.n_int; hdr[3] = T.n_rootb; hdr[4] = T.zl_size;
-  hdr[5] = T.rf_size; hdr[6] = T.rb_size; hdr[7] = T.w; hdr[8] = T.h;
   bool overflow = false;
   auto put = [&](int slot, const std::vector<int32_t> &v) {
+    while ((out.size() - base) % 8) out.push_back(0);  // every array starts on a 16-byte boundary
     hdr[slot] = int32_t(out.size() - base);
     for (int32_t y : v) {
       if (y < -1 || y >= 0xFFFF) overflow = true;
       out.push_back(y < 0 ? uint16_t(0xFFFF) : uint16_t(y));
+    }
+  };
+  auto put32 = [&](int slot, const std::vector<int32_t> &v) {
+    while ((out.size() - base) % 8) out.push_back(0);
+    hdr[slot] = int32_t(out.size() - base);
+    for (int32_t y : v) {
+      out.push_back(uint16_t(uint32_t(y) & 0xFFFF));
+      out.push_back(uint16_t(uint32_t(y) >> 16));
     }
   };
   std::vector<int32_t> code(T.var_code.size());
@@ -47,49 +61,63 @@ const char *pack_template(const SubtreeTemplate &T, std::vector<uint16_t> &out, 
     const int32_t x = T.var_code[l];
     code[l] = ((x >> 30) << 14) | (((x >> 15) & 0x7fff) << 7) | (x & 0x7fff);
   }
-  // forward: everything an output needs, indexed by the output itself
-  std::vector<int32_t> out_rf(T.zl_size), out_sb(T.zl_size), out_v(T.zl_size);
+  // forward
+  std::vector<int32_t> fdesc(size_t(T.zl_size) * 8, 0), sc(size_t(T.n_int) * 2, -1);
   for (int32_t o = 0; o < T.zl_size; ++o) {
     const int32_t n = T.out_node[o];
-    out_rf[o] = T.node_rf[n] + (o - T.node_zl[n]);
     if (T.node_s[n] > 255 || T.node_b[n] > 255) overflow = true;
-    out_sb[o] = (T.node_s[n] << 8) | T.node_b[n];
-    out_v[o] = T.node_sep[n];
+    fdesc[8 * o + 0] = T.node_rf[n] + (o - T.node_zl[n]);
+    fdesc[8 * o + 1] = (T.node_s[n] << 8) | T.node_b[n];
+    fdesc[8 * o + 2] = T.node_sep[n];
+    fdesc[8 * o + 3] = (o == T.node_zl[n]) ? 1 : 0;  // the first output of a node stores its accumulated rhs
+    fdesc[8 * o + 4] = T.out_c0[o];
+    fdesc[8 * o + 5] = T.out_c1[o];
   }
-  // backward: one row task per separator variable; per level a gather list builds the nodes' input vectors
-  std::vector<int32_t> row_off(T.n_int), row_len(T.n_int), row_w(T.n_int), gl_lvl, gl_src, tpo;
-  int32_t scratch_max = 0;
-  perm.assign(T.rb_size, 0);
-  for (int32_t k = 0; k < T.rb_size; ++k) perm[k] = k;
+  for (int32_t v = 0; v < T.n_int; ++v) { sc[2 * v] = T.sep_c0[v]; sc[2 * v + 1] = T.sep_c1[v]; }
+  // backward
+  std::vector<int32_t> lvlb(size_t(T.n_levels) * 4, 0), bdesc(size_t(T.n_int) * 4, 0), in_idx;
+  perm.clear();
   int32_t node = 0;
   for (int32_t lv = 0; lv < T.n_levels; ++lv) {
-    gl_lvl.push_back(int32_t(gl_src.size()));
-    const int32_t lvl_begin = int32_t(gl_src.size());
-    while (node < T.n_nodes && T.node_sep[node] < T.lvl_sep[lv + 1]) {
-      const int32_t s = T.node_s[node], b = T.node_b[node], f = s + b, sep0 = T.node_sep[node];
-      const int32_t w_off = int32_t(gl_src.size()) - lvl_begin;
-      for (int32_t p = 0; p < s; ++p) gl_src.push_back(sep0 + p);
-      for (int32_t q = 0; q < b; ++q) gl_src.push_back(0x8000 | T.bnd_var[T.node_bnd[node] + q]);
-      for (int32_t i = 0; i < s; ++i) {
-        row_off[sep0 + i] = T.node_rb[node] + i * f;
-        row_len[sep0 + i] = f;
-        row_w[sep0 + i] = w_off;
-        for (int32_t p = 0; p < f; ++p) perm[T.node_rb[node] + i * f + p] = T.node_rb[node] + p * s + i;
-      }
-      ++node;
+    const int32_t v0 = T.lvl_sep[lv], n_out = T.lvl_sep[lv + 1] - v0;
+    const int32_t tpo = std::max(1, std::min(32, pow2_floor(std::max(1, ct / std::max(1, n_out)))));
+    int32_t tl = 0;
+    while ((1 << tl) < tpo) ++tl;
+    const int32_t node0 = node;
+    int32_t max_len = 0;
+    while (node < T.n_nodes && T.node_sep[node] < T.lvl_sep[lv + 1]) { max_len = std::max(max_len, T.node_s[node] + T.node_b[node]); ++node; }
+    const bool interleaved = tpo == 1;
+    const int32_t estep = interleaved ? n_out : 1;
+    lvlb[4 * lv + 0] = v0; lvlb[4 * lv + 1] = n_out; lvlb[4 * lv + 2] = tl; lvlb[4 * lv + 3] = estep;
+    const int32_t blob0 = int32_t(perm.size()), idx0 = int32_t(in_idx.size());
+    if (interleaved) {
+      perm.resize(size_t(blob0) + size_t(max_len) * n_out, -1);
+      in_idx.resize(size_t(idx0) + size_t(max_len) * n_out, 0);
     }
-    scratch_max = std::max(scratch_max, int32_t(gl_src.size()) - lvl_begin);
-    const int32_t n_out = T.lvl_sep[lv + 1] - T.lvl_sep[lv];
-    tpo.push_back(std::max(1, std::min(32, pow2_floor(std::max(1, SWEEP_COMPUTE / std::max(1, n_out))))));
+    for (int32_t nd = node0; nd < node; ++nd) {
+      const int32_t s = T.node_s[nd], b = T.node_b[nd], f = s + b, sep0 = T.node_sep[nd];
+      for (int32_t i = 0; i < s; ++i) {
+        const int32_t v = sep0 + i, o = v - v0;
+        int32_t row_off, in_off;
+        if (interleaved) { row_off = blob0 + o; in_off = idx0 + o; }
+        else { row_off = int32_t(perm.size()); in_off = int32_t(in_idx.size()); perm.resize(perm.size() + f, -1); in_idx.resize(in_idx.size() + f, 0); }
+        for (int32_t pp = 0; pp < f; ++pp) {
+          perm[size_t(row_off) + size_t(pp) * estep] = T.node_rb[nd] + pp * s + i;  // old layout: R^T[p][i]
+          in_idx[size_t(in_off) + size_t(pp) * estep] = pp < s ? sep0 + pp : (0x8000 | T.bnd_var[T.node_bnd[nd] + pp - s]);
+        }
+        bdesc[4 * v + 0] = row_off; bdesc[4 * v + 1] = interleaved ? max_len : f; bdesc[4 * v + 2] = in_off;
+      }
+    }
   }
-  gl_lvl.push_back(int32_t(gl_src.size()));
+  if (perm.size() % 2) perm.push_back(-1);
+  rb2_size = int32_t(perm.size());
   if (T.n_int + T.n_rootb >= 0x8000) overflow = true;
-  put(10, code); put(11, T.sep_c0); put(12, T.sep_c1); put(13, out_rf); put(14, out_sb); put(15, out_v);
-  put(16, T.out_c0); put(17, T.out_c1); put(18, T.lvl_sep); put(19, T.lvl_out); put(20, T.cell_edge);
-  put(21, row_off); put(22, row_len); put(23, row_w); put(24, gl_lvl); put(25, gl_src); put(26, tpo);
-  hdr[27] = scratch_max;
+  hdr[0] = T.n_levels; hdr[1] = T.n_int; hdr[2] = T.n_rootb; hdr[3] = T.zl_size; hdr[4] = T.w; hdr[5] = T.h;
+  hdr[6] = T.rf_size; hdr[7] = rb2_size;
+  put(9, code); put(10, T.cell_edge); put(11, T.lvl_out); put(12, fdesc); put(13, sc); put32(14, lvlb);
+  put(15, bdesc); put(16, in_idx);
   while ((out.size() - base) % 8) out.push_back(0);  // 16-byte granules
-  hdr[9] = int32_t(out.size() - base);
+  hdr[8] = int32_t(out.size() - base);
   std::memcpy(out.data() + base, hdr.data(), SWEEP_TMPL_HDR * sizeof(int32_t));
   return overflow ? "subtree template field beyond 16 bits" : nullptr;
 }
@@ -97,11 +125,12 @@ const char *pack_template(const SubtreeTemplate &T, std::vector<uint16_t> &out, 
 }  // namespace
 
 const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx_user,
-                               const std::vector<int32_t> &dof_of_canon, int32_t n_cta, int32_t chunk_dbl,
+                               const std::vector<int32_t> &dof_of_canon, int32_t n_cta, int32_t chunk_dbl, int32_t ct,
                                SweepLayout &L) {
   L = SweepLayout();
   L.n_cta = n_cta;
   L.chunk_dbl = chunk_dbl;
+  L.ct = ct;
   const int32_t nn = int32_t(tr.nodes.size());
   if (tr.instances.empty()) return "no subtrees (subtree_cells = 0)";
   if (tr.idx.size() >= (size_t(1) << 30) || tr.src.size() >= (size_t(1) << 31)) return "index structure beyond 32 bits";
@@ -114,13 +143,13 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
     L.tmpl_off.push_back(int64_t(L.tmpl16.size()));
     const size_t before = L.tmpl16.size();
     std::vector<int32_t> perm;
-    if (const char *err = pack_template(T, L.tmpl16, perm)) return err;
+    int32_t rb2 = 0;
+    if (const char *err = pack_template(T, ct, L.tmpl16, perm, rb2)) return err;
     L.tmpl16_max = std::max(L.tmpl16_max, int32_t(L.tmpl16.size() - before));
     perm_off.push_back(int32_t(L.perm.size()));
     L.perm.insert(L.perm.end(), perm.begin(), perm.end());
-    int32_t scratch;
-    std::memcpy(&scratch, L.tmpl16.data() + before + 2 * 27, sizeof scratch);
-    L.sub_ws_max = std::max(L.sub_ws_max, std::max(T.n_int + T.zl_size, T.n_int + T.n_rootb + scratch));
+    L.rb2_size.push_back(rb2);
+    L.sub_ws_max = std::max(L.sub_ws_max, std::max(2 * T.n_int + T.zl_size, T.n_int + T.n_rootb));
   }
   L.perm.push_back(0);
   L.cell_box.assign(size_t(tr.nx) * tr.ny, -1);
@@ -160,7 +189,6 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
     h.old_id = i; h.s = n.s; h.b = n.b; h.height = n.height;
     h.sep_type = tr.idx[n.idx_off] < nxe ? 0 : 1;
     L.nodes.push_back(h);
-    L.f_max = std::max(L.f_max, n.s + n.b);
   }
   L.n_top = int32_t(L.nodes.size());
   for (size_t k = 0; k < tr.instances.size(); ++k) {
@@ -232,8 +260,8 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
             L.index.push_back(child_z(0, p)); L.index.push_back(child_z(1, p));
           }
         } else {
-          sn.gl_b = int64_t(L.index.size());
-          for (int32_t q = 0; q < n.b; ++q) L.index.push_back(idx_user[n.idx_off + n.s + q]);
+          sn.gl_b = int64_t(L.index.size());  // one entry per tile row; separator rows come from z_s, no index
+          for (int32_t q = 0; q < f; ++q) L.index.push_back(q < n.s ? -1 : idx_user[n.idx_off + q]);
           while (L.index.size() % 4) L.index.push_back(0);
         }
         if (ncols == 0) {  // root: forward entry that only accumulates the separator right-hand side
@@ -244,7 +272,7 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
         }
         // block width: a power of two below 32 (shuffle reduction), else any even width up to 256 with at most
         // one padded column per block
-        const int64_t cap = std::max<int64_t>(2, std::min<int64_t>(256, target / rlen));
+        const int64_t cap = std::max<int64_t>(2, std::min<int64_t>(std::min(256, ct), target / rlen));
         int32_t cw;
         if (cap >= ncols) cw = ncols >= 32 ? even(ncols) : std::max(2, pow2_ceil(ncols));
         else if (cap >= 32) { const int32_t nb = int32_t((ncols + cap - 1) / cap); cw = even((ncols + nb - 1) / nb); }
@@ -282,10 +310,10 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
     const SubtreeInstance &in = tr.instances[k];
     const SubtreeTemplate &T = tr.templates[in.tmpl];
     L.inst[k].rf = rs; rs += T.rf_size;
-    L.inst[k].rb = rs; rs += T.rb_size;
+    L.inst[k].rb = rs; rs += L.rb2_size[in.tmpl];
     RepackSub d;
     d.old_rf = in.rf_base; d.old_rb = in.rb_base; d.new_rf = L.inst[k].rf; d.new_rb = L.inst[k].rb;
-    d.rf_size = T.rf_size; d.rb_size = T.rb_size; d.perm_off = perm_off[in.tmpl]; d.pad = 0;
+    d.rf_size = T.rf_size; d.rb_size = L.rb2_size[in.tmpl]; d.perm_off = perm_off[in.tmpl]; d.pad = 0;
     L.repack_sub.push_back(d);
   }
   L.rs_total = rs;
@@ -325,7 +353,7 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
     e.flags = SWF_FIRST | SWF_LAST;
     e.a0 = in.tmpl; e.a1 = -1; e.a2 = in.I0; e.a3 = in.J0; e.a7 = k;
     e.o0 = sn.zc_off; e.o1 = ih.xi_off; e.o2 = ih.pb_off;
-    e.n[0] = fwd ? T.rf_size : T.rb_size;
+    e.n[0] = fwd ? T.rf_size : L.rb2_size[in.tmpl];
     iss.off[0] = fwd ? ih.rf : ih.rb; iss.kind[0] = SRC_FACTOR;
     if (!fwd) {
       e.n[1] = even((T.n_rootb + 1) / 2);
@@ -373,7 +401,7 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
       const SweepNodeH &sn = L.nodes[it.node];
       const bool fwd = it.kind == SW_TOP_FWD;
       const int32_t cw = it.cw;
-      const int32_t rows_per = std::max(1, L.chunk_dbl / cw);
+      const int32_t rows_per = std::max(4, (L.chunk_dbl / cw) & ~3);  // multiples of 4: aligned index-list slices
       int32_t r = 0;
       do {
         const int32_t r1 = std::min(it.rlen, r + rows_per);
@@ -384,18 +412,30 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
         e.a0 = it.col0; e.a1 = cw; e.a2 = r; e.a3 = r1; e.a4 = sn.s; e.a5 = sn.b; e.a6 = sn.sep_type;
         e.a7 = it.node;
         e.o2 = sn.zs_off; e.o3 = sn.zc_off;
-        if (r == 0) {
-          const bool same_run = !list.empty() && list.back().kind == it.kind && list.back().a7 == it.node;
-          if (!same_run) {
-            e.flags |= SWF_NEW_RUN;
-            e.n[0] = fwd ? 2 * sn.s : even((sn.b + 1) / 2);
-            iss.off[0] = (fwd ? sn.gl_f : sn.gl_b) / 2; iss.kind[0] = SRC_INDEX;
+        // the vector rows [r, r1) are staged by this entry unless the previous one left exactly them in place
+        const bool same_rows = !list.empty() && list.back().kind == it.kind && list.back().a7 == it.node &&
+                               list.back().a2 == r && list.back().a3 == r1;
+        if (!same_rows && r1 > r) {
+          e.flags |= SWF_NEW_RUN;
+          if (fwd) {
+            e.n[0] = 2 * (r1 - r);
+            iss.off[0] = sn.gl_f / 2 + 2 * int64_t(r);
+          } else {
+            e.n[0] = even((r1 - r + 1) / 2);
+            iss.off[0] = sn.gl_b / 2 + r / 2;
           }
-          if (fwd && it.col0 == 0) e.flags |= SWF_WRITE_ZS;
-          if ((fwd ? sn.b : sn.s) > 0) {
-            e.n[1] = cw;
-            iss.off[1] = (fwd ? sn.cl_f : sn.cl_b) / 2 + it.col0; iss.kind[1] = SRC_INDEX;
-          }
+          iss.kind[0] = SRC_INDEX;
+        }
+        if (it.rlen == 0) {  // root forward entry: no tile, but it accumulates and stores the separator rhs
+          e.flags |= SWF_NEW_RUN;
+          e.a2 = 0; e.a3 = sn.s;
+          e.n[0] = 2 * sn.s;
+          iss.off[0] = sn.gl_f / 2; iss.kind[0] = SRC_INDEX;
+        }
+        if (fwd && it.col0 == 0) e.flags |= SWF_WRITE_ZS;
+        if (r == 0 && (fwd ? sn.b : sn.s) > 0) {
+          e.n[1] = cw;
+          iss.off[1] = (fwd ? sn.cl_f : sn.cl_b) / 2 + it.col0; iss.kind[1] = SRC_INDEX;
         }
         e.n[2] = (r1 - r) * cw;
         iss.off[2] = it.src + int64_t(r) * cw; iss.kind[2] = SRC_FACTOR;
@@ -428,9 +468,13 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
   for (const auto &list : per)
     for (const auto &e : list) S.entry_max = std::max(S.entry_max, e.n[0] + e.n[1] + e.n[2] + e.n[3]);
   const int64_t total_dbl = int64_t(smem_budget / 8);
-  const int64_t fixed = sweep_fixed_dbl(M);
+  const int64_t fixed = sweep_fixed_dbl(M, L.ct);
   S.tmpl_dbl = even((L.tmpl16_max + 3) / 4);
-  S.ws_dbl = even(int64_t(std::max(L.f_max, L.sub_ws_max)) * M);
+  int32_t rows_max = 0;
+  for (const auto &list : per)
+    for (const auto &e : list)
+      if (e.kind == SW_TOP_FWD || e.kind == SW_TOP_BWD) rows_max = std::max(rows_max, e.a3 - e.a2);
+  S.ws_dbl = even(int64_t(std::max(rows_max, L.sub_ws_max)) * M);
   const int64_t ring = (total_dbl - fixed - S.tmpl_dbl - S.ws_dbl) & ~int64_t(1);
   if (double(ring) < std::max(1.0, min_fill) * double(S.entry_max)) {
     std::snprintf(g_msg, sizeof g_msg, "shared-memory ring (%lld doubles) is too small for entries of %d doubles",
@@ -569,7 +613,7 @@ const char *check_sweep_schedule(const SweepLayout &L, const SweepSchedule &S, i
         const int64_t step = s.G / P;
         const SweepEntry &e = S.entries[b0 + s.G % P];
         if (s.issued <= s.G) { std::snprintf(g_msg, sizeof g_msg, "cta %d: entry %lld consumed before it was issued", c, (long long)s.G); return g_msg; }
-        const bool waits = (e.kind == SW_SUB_BWD) || ((e.kind == SW_TOP_FWD || e.kind == SW_TOP_BWD) && (e.flags & SWF_NEW_RUN));
+        const bool waits = (e.kind == SW_SUB_BWD) || ((e.kind == SW_TOP_FWD || e.kind == SW_TOP_BWD) && (e.flags & SWF_NEW_RUN) && (e.flags & SWF_FIRST));
         if (waits) {
           if (e.dep0 >= 0 && cnt[e.dep0] < uint32_t(step + 1) * uint32_t(e.dep0_n)) break;
           if (e.dep1 >= 0 && cnt[e.dep1] < uint32_t(step + 1) * uint32_t(e.dep1_n)) break;
@@ -593,17 +637,18 @@ const char *check_sweep_schedule(const SweepLayout &L, const SweepSchedule &S, i
 
 // ---- diagnostics of include/mmmfe_b200.h (host only) ---------------------------------------------------------------
 extern "C" int mmmfe_sweep_plan_check(int32_t nx, int32_t ny, int32_t leaf_cells, int32_t subtree_cells, int32_t M,
-                                      int32_t n_cta, int64_t smem_bytes, int32_t n_steps, int64_t stats[8], char *msg,
-                                      int32_t msg_cap) {
+                                      int32_t n_cta, int64_t smem_bytes, int32_t n_steps, int32_t ct,
+                                      int32_t chunk_dbl, int64_t stats[8], char *msg, int32_t msg_cap) {
   auto say = [&](const char *m) {
     if (msg && msg_cap > 0) std::snprintf(msg, size_t(msg_cap), "%s", m ? m : "");
   };
   say("");
-  if (nx < 1 || ny < 1 || n_cta < 1 || (M != 1 && M != 2 && M != 4) || n_steps < 1) { say("bad argument"); return -1; }
+  if (nx < 1 || ny < 1 || n_cta < 1 || (M != 1 && M != 2 && M != 4) || n_steps < 1 || chunk_dbl < 64 ||
+      (ct != 64 && ct != 128 && ct != 256)) { say("bad argument"); return -1; }
   mmmfe::NdTree t;
   t.build(nx, ny, leaf_cells, subtree_cells);
   mmmfe::SweepLayout L;
-  if (const char *e = mmmfe::build_sweep_layout(t, t.idx, std::vector<int32_t>(), n_cta, 2048, L)) { say(e); return -2; }
+  if (const char *e = mmmfe::build_sweep_layout(t, t.idx, std::vector<int32_t>(), n_cta, chunk_dbl, ct, L)) { say(e); return -2; }
   mmmfe::SweepSchedule S;
   if (const char *e = mmmfe::build_sweep_schedule(t, L, M, size_t(smem_bytes), 2.0, S)) { say(e); return -3; }
   if (stats) {

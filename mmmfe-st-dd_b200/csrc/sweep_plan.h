@@ -33,21 +33,22 @@ struct SweepInstH {       // one subtree instance
 };
 
 struct SweepLayout {
-  int32_t n_cta = 0, chunk_dbl = 2048;
+  int32_t n_cta = 0, chunk_dbl = 2048, ct = 256;  // CTAs, doubles per streamed chunk, compute threads per CTA
   int32_t n_top = 0;
   std::vector<SweepNodeH> nodes;                 // top fronts (any order), then one pseudo node per subtree instance
   std::vector<SweepInstH> inst;
   std::vector<std::vector<SweepItem>> fwd, bwd;  // top items by height (ascending)
   std::vector<RepackDesc> repack;                // top part of the sweep layout from the front storage
   std::vector<RepackSub> repack_sub;             // subtree blobs
-  std::vector<int32_t> perm;                     // backward-blob permutations of the templates
+  std::vector<int32_t> perm;                     // backward-blob permutations of the templates (-1: zero padding)
+  std::vector<int32_t> rb2_size;                 // doubles of the backward blob of each template in sweep layout
   int64_t rs_total = 0;                          // doubles of the sweep-layout factor
   std::vector<int32_t> index;                    // static index lists
   std::vector<int32_t> cell_box;                 // canonical cell -> box-major position
   std::vector<uint16_t> tmpl16;                  // packed templates
   std::vector<int64_t> tmpl_off;
   int64_t z_total = 0, xi_total = 0, pb_total = 0;
-  int32_t f_max = 0;                             // longest top-level gather vector
+  int32_t rows_max = 0;                          // most tile rows of one streamed chunk (gather vector length)
   int32_t tmpl16_max = 0;                        // uint16 words of the largest template
   int32_t sub_ws_max = 0;                        // vector workspace entries (per right-hand side) of a subtree entry
   double bytes_per_step = 0;                     // factor bytes one step streams (with block padding)
@@ -65,7 +66,7 @@ struct SweepSchedule {
 // Fails (returns a message) when the tree cannot be run by the sweep kernel: a leaf or a cell outside every subtree,
 // boxes wider than 127 cells, template fields beyond 16 bits.
 const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx_user,
-                               const std::vector<int32_t> &dof_of_canon, int32_t n_cta, int32_t chunk_dbl,
+                               const std::vector<int32_t> &dof_of_canon, int32_t n_cta, int32_t chunk_dbl, int32_t ct,
                                SweepLayout &L);
 
 // Shared-memory partition for M right-hand sides within smem_budget bytes per CTA, entry lists and ring schedule.
