@@ -83,7 +83,9 @@ const char *mmmfe_version(void);
  * from shared memory; 0 disables the subtree kernels), "use_sweep" (default 1: run the star sweeps in the
  * persistent sweep kernel when the matrix has the RT0 structure), "sweep_chunk" (doubles per streamed chunk),
  * "sweep_min_fill" (entries the shared-memory ring must hold), "sweep_evict_first" (L2 hint of the factor stream),
- * "sweep_compute_threads" (64, 128 or 256 compute threads per CTA), "sweep_ctas_per_sm" (resident CTAs per SM). */
+ * "sweep_compute_threads" (64, 128 or 256 compute threads per CTA), "sweep_ctas_per_sm" (resident CTAs per SM),
+ * "sweep_groups" (independent compute groups per CTA), "sweep_autotune" (default 1: time one star sweep with the
+ * persistent kernel and one with the per-level kernels at set-up and keep the faster).                         */
 int mmmfe_set_option(mmmfe_ctx *ctx, const char *key, double value);
 
 /* ---- multi-GPU: one process per GPU, subdomains sharded over ranks ------------------------------------------ */
@@ -196,10 +198,18 @@ int mmmfe_profile_sweeps(mmmfe_ctx *ctx, int32_t cap, double *ms, double *bytes_
 /* One instrumented star sweep of sweep batch `batch`: mean SM cycles per CTA spent in {subtree forward, top forward,
  * top backward, subtree backward} entries, [4] completion-counter waits of the dependency warp, [5] TMA (mbarrier)
  * waits, [6] entries, [7] waits for the dependency warp, [8..10] subtree backward: input gather / levels / epilogue,
- * [11..13] subtree forward: right-hand side / levels / output, [14] top-level vector gathers, [15] top-level tiles. */
-int mmmfe_profile_sweep_cycles(mmmfe_ctx *ctx, int32_t batch, double out[16]);
+ * [11..13] subtree forward: right-hand side / levels / output, [14] top-level vector gathers, [15] top-level tiles,
+ * [16..19] dependency waits by entry kind, [20..23] entries by kind that waited more than 2000 cycles. */
+int mmmfe_profile_sweep_cycles(mmmfe_ctx *ctx, int32_t batch, double out[24]);
+/* Clock stamps (start, opened by the dependency warp, end) of every entry of compute group 0 during the second time
+ * step of one instrumented sweep of sweep batch `batch`, with {kind, tree height} per entry and the per-CTA entry
+ * ranges (sweep_ctas + 1 ints).  Call with stamps = NULL to obtain n_entries.                                   */
+int mmmfe_debug_sweep_trace(mmmfe_ctx *ctx, int32_t batch, int64_t cap, int64_t *n_entries, int32_t *cta_begin,
+                            int32_t *kind_height, int64_t *stamps);
 /* Integer facts about the set-up context: "batches", "sweep_batches", "sweep_ctas", "sweep_smem_bytes",
- * "sweep_entries", "sweep_factor_bytes", "rt0_factors"; -1 for an unknown key.                                */
+ * "sweep_entries", "sweep_factor_bytes", "rt0_factors", "sweep_planned" (batches with a sweep plan, whether or
+ * not the auto-tuner kept it), "tune_us_sweep" / "tune_us_levels" (microseconds of the timed star sweep of each
+ * implementation); -1 for an unknown key.                                                                    */
 int64_t mmmfe_stat(const mmmfe_ctx *ctx, const char *key);
 
 /* ---- diagnostics (host only, no device needed) ------------------------------------------------------------------- */

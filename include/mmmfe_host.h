@@ -46,6 +46,10 @@ typedef struct {
   int64_t gmres_kernel_launches;        /* kernels launched inside the timed GMRES loop                        */
   double prof_ms[6], prof_bytes[6];
   int64_t prof_launches[6];
+  /* persistent sweep kernel: batches it runs (0: the per-level kernels were selected), one timed star sweep each */
+  int32_t sweep_batches, sweep_steps[4];
+  double sweep_ms[4], sweep_bytes_per_step[4];
+  int64_t tune_us_sweep, tune_us_levels, sweep_planned;
 } mmmfe_host_report;
 
 void mmmfe_host_default_options(mmmfe_host_options *opt);

@@ -89,6 +89,7 @@ def load_engine():
         "mmmfe_profile_sweeps": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p, c_f64p, c_i32p, c_i32p]),
         "mmmfe_stat": (ctypes.c_int64, [vp, ctypes.c_char_p]),
         "mmmfe_profile_sweep_cycles": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p]),
+        "mmmfe_debug_sweep_trace": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.c_int64, c_i64p, c_i32p, c_i32p, c_i64p]),
         "mmmfe_sweep_plan_check": (ctypes.c_int, [ctypes.c_int32] * 6 + [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                                   ctypes.c_int32, c_i64p, ctypes.c_char_p, ctypes.c_int32]),
         "mmmfe_nd_tree_sizes": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_i64p]),
@@ -279,11 +280,24 @@ class Engine:
                                                   _ptr(n, c_i32p)))
         return [(float(ms[i]), float(by[i]), int(ns[i])) for i in range(int(n[0]))]
 
+    def sweep_trace(self, batch):
+        n = np.zeros(1, dtype=np.int64)
+        self._check(self.lib.mmmfe_debug_sweep_trace(self.h, batch, 0, _ptr(n, c_i64p), None, None, None))
+        ne, ncta = int(n[0]), self.stat("sweep_ctas")
+        cb = np.zeros(ncta + 1, dtype=np.int32)
+        kh = np.zeros((ne, 2), dtype=np.int32)
+        st = np.zeros((ne, 3), dtype=np.int64)
+        self._check(self.lib.mmmfe_debug_sweep_trace(self.h, batch, ne, _ptr(n, c_i64p), _ptr(cb, c_i32p), _ptr(kh, c_i32p),
+                                                     _ptr(st, c_i64p)))
+        return cb, kh, st
+
     def profile_sweep_cycles(self, batch):
-        out = np.zeros(16)
+        out = np.zeros(24)
         self._check(self.lib.mmmfe_profile_sweep_cycles(self.h, batch, _ptr(out, c_f64p)))
         names = ["sub_fwd", "top_fwd", "top_bwd", "sub_bwd", "counter_wait", "tma_wait", "entries", "open_wait",
-                 "sb_gather", "sb_levels", "sb_epilogue", "sf_rhs", "sf_levels", "sf_output", "top_gather", "top_tile"]
+                 "sb_gather", "sb_levels", "sb_epilogue", "sf_rhs", "sf_levels", "sf_output", "top_gather", "top_tile",
+                 "wait_sub_fwd", "wait_top_fwd", "wait_top_bwd", "wait_sub_bwd", "nwait_sub_fwd", "nwait_top_fwd",
+                 "nwait_top_bwd", "nwait_sub_bwd"]
         return dict(zip(names, (float(v) for v in out)))
 
     def debug_get_factor(self, li, r_total):
@@ -350,7 +364,10 @@ class HostReport(ctypes.Structure):
                 ("e2e_ms_per_iteration", ctypes.c_double), ("e2e_h2d_bytes", ctypes.c_int64),
                 ("e2e_d2h_bytes", ctypes.c_int64), ("gmres_kernel_launches", ctypes.c_int64),
                 ("prof_ms", ctypes.c_double * 6), ("prof_bytes", ctypes.c_double * 6),
-                ("prof_launches", ctypes.c_int64 * 6)]
+                ("prof_launches", ctypes.c_int64 * 6), ("sweep_batches", ctypes.c_int32),
+                ("sweep_steps", ctypes.c_int32 * 4), ("sweep_ms", ctypes.c_double * 4),
+                ("sweep_bytes_per_step", ctypes.c_double * 4), ("tune_us_sweep", ctypes.c_int64),
+                ("tune_us_levels", ctypes.c_int64), ("sweep_planned", ctypes.c_int64)]
 
 
 _host = None

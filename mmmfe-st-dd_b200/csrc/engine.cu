@@ -114,7 +114,7 @@ struct Factor {
   std::vector<int32_t> p_of_cell_h;  // canonical cell -> user pressure index
   bool p_identity = true;
   SweepLayout lay;
-  int32_t sweep_n_cta = 0, sweep_ct = 128;
+  int32_t sweep_n_cta = 0, sweep_ct = 128, sweep_ng = 1;
   size_t sweep_budget = 0;
   DevBuf<double> Rs, minv_c;
   double minv_const = 0.0;
@@ -147,6 +147,7 @@ struct Batch {
   DevBuf<SweepEntry> s_entries;
   DevBuf<SweepIssue> s_issue;
   DevBuf<int32_t> s_cta_begin, s_cta_pro, s_sub_q, s_bq_stride;
+  DevBuf<uint8_t> s_grp;
   DevBuf<double> s_z, s_xi, s_ptil, s_bq_coef;
   DevBuf<uint32_t> s_cnt;
   DevBuf<const double *> s_bq_data;
@@ -173,7 +174,9 @@ struct mmmfe_ctx {
   int device = 0;
   std::string err;
   bool keep_history = true, use_graphs = true, use_sweep = true, sweep_evict_first = true;
-  int leaf_cells = 4, subtree_cells = 256, sweep_chunk = 1024, sweep_ct = 128, sweep_ctas_per_sm = 4;
+  int leaf_cells = 4, subtree_cells = 256, sweep_chunk = 8192, sweep_ct = 256, sweep_ctas_per_sm = 1, sweep_groups = 1;
+  bool sweep_autotune = true;
+  double tune_ms_sweep = 0.0, tune_ms_levels = 0.0;
   double sweep_min_fill = 1.75;
   int sweep_spin_ns = 100;
   bool is_setup = false, bar_done = false, final_done = false;
@@ -480,6 +483,7 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax) 
   F->rt0 = detect_rt0(sd, kup, kpu, dof_of_canon, *F);
   bool want_sweep = c->use_sweep && F->rt0 && c->subtree_cells > 0;
   F->sweep_ct = c->sweep_ct;
+  F->sweep_ng = (c->sweep_ct / c->sweep_groups >= 32) ? c->sweep_groups : 1;
   if (want_sweep) sweep_geometry(c->device, Mmax, F->sweep_ct, c->sweep_ctas_per_sm, F->sweep_n_cta, F->sweep_budget);
   bool sweep_planned = false;
   for (int cells = c->subtree_cells;; cells /= 2) {  // largest subtrees whose factor blob + vectors fit on chip twice per SM
@@ -497,10 +501,10 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax) 
     {
       std::vector<int32_t> iu(tr.idx.size());
       for (size_t i = 0; i < tr.idx.size(); ++i) iu[i] = dof_of_canon.empty() ? tr.idx[i] : dof_of_canon[tr.idx[i]];
-      if (build_sweep_layout(tr, iu, dof_of_canon, F->sweep_n_cta, c->sweep_chunk, F->sweep_ct, F->lay) != nullptr) { want_sweep = false; break; }
+      if (build_sweep_layout(tr, iu, dof_of_canon, F->sweep_n_cta, c->sweep_chunk, F->sweep_ct / F->sweep_ng, F->lay) != nullptr) { want_sweep = false; break; }
     }
     SweepSchedule probe;
-    if (build_sweep_schedule(tr, F->lay, Mmax, F->sweep_budget, c->sweep_min_fill, probe) == nullptr) { sweep_planned = true; break; }
+    if (build_sweep_schedule(tr, F->lay, Mmax, F->sweep_ng, F->sweep_budget, c->sweep_min_fill, probe) == nullptr) { sweep_planned = true; break; }
     if (cells / 2 < std::max(1, c->leaf_cells)) {  // cannot shrink further: generic kernels with the widest subtrees
       want_sweep = false;
       cells = c->subtree_cells * 2;
@@ -942,6 +946,32 @@ static void setup(mmmfe_ctx *c) {
   }
   CUDA_CHECK(cudaDeviceSynchronize());
   c->is_setup = true;
+  // Both star-sweep implementations are exact; keep the one that is faster for THIS configuration (one timed star
+  // sweep each with the interface data at zero).  The persistent kernel runs the batches one after the other, the
+  // per-level kernels run them concurrently on their own streams, so the winner depends on the mix of subdomains.
+  bool any_sweep = false;
+  for (auto &b : c->batches) any_sweep |= b->sweep;
+  if (any_sweep && c->sweep_autotune) {
+    auto timed = [&](bool with_sweep) {
+      std::vector<bool> keep;
+      for (auto &b : c->batches) { keep.push_back(b->sweep); b->sweep = b->sweep && with_sweep; }
+      float best = 0;
+      for (int rep = 0; rep < 2; ++rep) {  // the first pass of the per-level path captures its graphs
+        CUDA_CHECK(cudaEventRecord(c->ev_t0, c->stream));
+        run_star_sweeps(c, SWEEP_STAR);
+        CUDA_CHECK(cudaEventRecord(c->ev_t1, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        CUDA_CHECK(cudaEventElapsedTime(&best, c->ev_t0, c->ev_t1));
+      }
+      for (size_t i = 0; i < keep.size(); ++i) c->batches[i]->sweep = keep[i];
+      return double(best);
+    };
+    c->tune_ms_sweep = timed(true);
+    check_watchdog(c);
+    c->tune_ms_levels = timed(false);
+    if (c->tune_ms_levels < c->tune_ms_sweep)
+      for (auto &b : c->batches) b->sweep = false;
+  }
 }
 
 // Entry lists, ring schedule and boundary-entry tables of one batch for the persistent sweep kernel.
@@ -952,7 +982,7 @@ static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> 
   if (!F.sweep_ok) return;
   const NdTree &tr = F.tree;
   SweepSchedule S;
-  if (build_sweep_schedule(tr, F.lay, b.M, F.sweep_budget, 1.0, S) != nullptr) return;
+  if (build_sweep_schedule(tr, F.lay, b.M, F.sweep_ng, F.sweep_budget, 1.0, S) != nullptr) return;
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
   if (sweep_ctas_per_sm(b.M, F.sweep_ct, S.smem_bytes) * sms < F.sweep_n_cta) return;  // grid would not be co-resident
@@ -1002,6 +1032,8 @@ static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> 
   }
   b.s_entries.upload(S.entries); b.s_issue.upload(S.issue);
   b.s_cta_begin.upload(S.cta_begin); b.s_cta_pro.upload(S.cta_prologue);
+  S.grp.push_back(0);
+  b.s_grp.upload(S.grp);
   b.s_sub_q.upload(sub_q); b.s_bq_stride.upload(stride); b.s_bq_coef.upload(coef);
   b.s_bq_data.upload(data); b.s_bq_trace.upload(trace);
   b.s_z.alloc(size_t(F.lay.z_total + 1) * M); b.s_z.zero();
@@ -1011,6 +1043,7 @@ static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> 
   SweepArgs &a = b.sargs;
   std::memset(&a, 0, sizeof a);
   a.entries = b.s_entries.p; a.issue = b.s_issue.p; a.cta_begin = b.s_cta_begin.p; a.cta_prologue = b.s_cta_pro.p;
+  a.grp = b.s_grp.p; a.ng = F.sweep_ng;
   a.Rs = F.Rs.p; a.index = F.sweep_index.p;
   a.tmpl16 = F.tmpl16.p; a.tmpl_off = F.tmpl_off.p; a.dof_of_canon = F.dof_of_canon.p;
   a.x = b.x.p; a.z = b.s_z.p; a.xi = b.s_xi.p; a.ptil = b.s_ptil.p; a.cnt = b.s_cnt.p;
@@ -1224,6 +1257,11 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   }
   else if (k == "sweep_ctas_per_sm") c->sweep_ctas_per_sm = std::max(1, int(value));
   else if (k == "sweep_spin_ns") c->sweep_spin_ns = std::max(0, int(value));
+  else if (k == "sweep_autotune") c->sweep_autotune = value != 0;
+  else if (k == "sweep_groups") {
+    if (value != 1 && value != 2 && value != 4) { c->err = "sweep_groups must be 1, 2 or 4"; return MMMFE_E_INVALID; }
+    c->sweep_groups = int(value);
+  }
   else if (k == "sweep_min_fill") c->sweep_min_fill = value;
   else { c->err = "unknown option " + k; return MMMFE_E_INVALID; }
   return MMMFE_OK;
@@ -1547,10 +1585,52 @@ int64_t mmmfe_stat(const mmmfe_ctx *c, const char *key) {
   if (k == "sweep_entries") { for (auto &b : c->batches) if (b->sweep) v += int64_t(b->s_entries.n); return v; }
   if (k == "sweep_factor_bytes") { for (auto &f : c->factors) if (f->sweep_ok) v += int64_t(f->lay.bytes_per_step); return v; }
   if (k == "rt0_factors") { for (auto &f : c->factors) v += f->rt0; return v; }
+  if (k == "sweep_planned") { for (auto &b : c->batches) v += b->s_entries.n > 0; return v; }
+  if (k == "tune_us_sweep") return int64_t(c->tune_ms_sweep * 1e3);
+  if (k == "tune_us_levels") return int64_t(c->tune_ms_levels * 1e3);
   return -1;
 }
 
-int mmmfe_profile_sweep_cycles(mmmfe_ctx *c, int32_t batch, double out[16]) {
+int mmmfe_debug_sweep_trace(mmmfe_ctx *c, int32_t batch, int64_t cap, int64_t *n_entries, int32_t *cta_begin_out,
+                            int32_t *kind_height, int64_t *stamps) {
+  if (!c || !n_entries) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, {
+    int32_t k = 0;
+    for (auto &bp : c->batches) {
+      Batch &b = *bp;
+      if (!b.sweep) continue;
+      if (k++ != batch) continue;
+      const int32_t n_cta = b.factor->sweep_n_cta;
+      const int64_t ne = int64_t(b.s_entries.n);
+      *n_entries = ne;
+      if (!stamps || cap < ne) return MMMFE_OK;
+      DevBuf<long long> prof, trace;
+      prof.alloc(size_t(n_cta) * 24); prof.zero(c->stream);
+      trace.alloc(size_t(ne) * 3); trace.zero(c->stream);
+      SweepArgs a = b.sargs;
+      a.prof = prof.p; a.trace = trace.p;
+      CUDA_CHECK(cudaMemsetAsync(b.s_ptil.p, 0, b.s_ptil.n * sizeof(double), c->stream));
+      CUDA_CHECK(cudaMemsetAsync(b.s_cnt.p, 0, b.s_cnt.n * sizeof(uint32_t), c->stream));
+      const cudaError_t err = launch_sweep(b.M, b.factor->sweep_ct, a, n_cta, b.sweep_smem, c->stream);
+      if (err != cudaSuccess) fail(MMMFE_E_CUDA, "sweep kernel launch failed: %s", cudaGetErrorString(err));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      check_watchdog(c);
+      CUDA_CHECK(cudaMemcpy(stamps, trace.p, size_t(ne) * 3 * sizeof(long long), cudaMemcpyDeviceToHost));
+      std::vector<SweepEntry> he(static_cast<size_t>(ne));
+      CUDA_CHECK(cudaMemcpy(he.data(), b.s_entries.p, size_t(ne) * sizeof(SweepEntry), cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i < ne; ++i) {
+        kind_height[2 * i] = he[i].kind;
+        const bool top = he[i].kind == SW_TOP_FWD || he[i].kind == SW_TOP_BWD;
+        kind_height[2 * i + 1] = top ? b.factor->lay.nodes[he[i].a7].height : 0;
+      }
+      CUDA_CHECK(cudaMemcpy(cta_begin_out, b.s_cta_begin.p, size_t(n_cta + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      return MMMFE_OK;
+    }
+    fail(MMMFE_E_INVALID, "no such sweep batch");
+  });
+}
+
+int mmmfe_profile_sweep_cycles(mmmfe_ctx *c, int32_t batch, double out[24]) {
   if (!c || !out) return MMMFE_E_INVALID;
   MMMFE_TRY(c, {
     if (!c->is_setup) fail(MMMFE_E_INVALID, "mmmfe_setup first");
@@ -1561,7 +1641,7 @@ int mmmfe_profile_sweep_cycles(mmmfe_ctx *c, int32_t batch, double out[16]) {
       if (k++ != batch) continue;
       const int32_t n_cta = b.factor->sweep_n_cta;
       DevBuf<long long> prof;
-      prof.alloc(size_t(n_cta) * 16);
+      prof.alloc(size_t(n_cta) * 24);
       prof.zero(c->stream);
       SweepArgs a = b.sargs;
       a.prof = prof.p;
@@ -1571,11 +1651,11 @@ int mmmfe_profile_sweep_cycles(mmmfe_ctx *c, int32_t batch, double out[16]) {
       if (err != cudaSuccess) fail(MMMFE_E_CUDA, "sweep kernel launch failed: %s", cudaGetErrorString(err));
       CUDA_CHECK(cudaStreamSynchronize(c->stream));
       check_watchdog(c);
-      std::vector<long long> h(size_t(n_cta) * 16);
+      std::vector<long long> h(size_t(n_cta) * 24);
       CUDA_CHECK(cudaMemcpy(h.data(), prof.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-      for (int t = 0; t < 16; ++t) out[t] = 0;
+      for (int t = 0; t < 24; ++t) out[t] = 0;
       for (int32_t cta = 0; cta < n_cta; ++cta)
-        for (int t = 0; t < 16; ++t) out[t] += double(h[size_t(cta) * 16 + t]) / n_cta;
+        for (int t = 0; t < 24; ++t) out[t] += double(h[size_t(cta) * 24 + t]) / n_cta;
       return MMMFE_OK;
     }
     fail(MMMFE_E_INVALID, "no such sweep batch");

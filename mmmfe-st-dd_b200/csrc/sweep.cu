@@ -194,22 +194,23 @@ __device__ __forceinline__ int64_t sweep_dof(const SweepArgs &a, int I0, int J0,
 #define SWEEP_PROF(slot)                                     \
   if (a.prof && tid == 0) {                                  \
     const long long t_now = clock64();                       \
-    a.prof[cta * 16 + (slot)] += t_now - t_mark;             \
+    a.prof[cta * 24 + (slot)] += t_now - t_mark;             \
     t_mark = t_now;                                          \
   }
 
 template <int M, int CT>
 __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))) k_sweep(const SweepArgs a) {
-  auto csync = [] { csync_t<CT>(); };
   extern __shared__ __align__(128) double sm[];
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(sm);  // TMA data of the entry landed
   uint32_t *done_cnt = reinterpret_cast<uint32_t *>(full_bar + NB);  // compute warps that finished the slot's entries
   uint64_t *dep_bar = full_bar + 2 * NB;                  // descriptor staged, dependencies satisfied
   SweepEntry *edesc = reinterpret_cast<SweepEntry *>(sm + 3 * NB);
-  double *red = sm + 19 * NB;                             // two reduction buffers
-  uint16_t *tb = reinterpret_cast<uint16_t *>(red + 2 * CT * M);
-  double *ws = red + 2 * CT * M + a.tmpl_dbl;
-  double *ring = ws + a.ws_dbl;
+  uint8_t *gtab = reinterpret_cast<uint8_t *>(sm + 19 * NB);  // compute group of every entry of this CTA
+  uint32_t *retired = reinterpret_cast<uint32_t *>(sm + 19 * NB + SWEEP_GTAB_DBL - 1);
+  double *red_all = sm + 19 * NB + SWEEP_GTAB_DBL;           // two reduction buffers per group
+  uint16_t *tb_all = reinterpret_cast<uint16_t *>(red_all + 2 * CT * M);
+  double *ws_all = red_all + 2 * CT * M + a.ng * a.tmpl_dbl;
+  double *ring = ws_all + a.ng * a.ws_dbl;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x;
@@ -226,8 +227,10 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
       done_cnt[k] = 0;
       bar_init(dep_bar + k, 1);
     }
+    *retired = 0;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  for (int t = tid; t < P; t += CT + 64) gtab[t] = a.grp[e_first + t];
   __syncthreads();
 
   if (warp == CT / 32) {
@@ -296,20 +299,33 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
     };
     bool have = G < total;
     if (have) load_info(G);
+    int state = 0;  // 0: waiting for the compute warps, 1: completion published, waiting for my turn to free the ring
     long long t0 = clock64();
     for (int spins = 1; __any_sync(0xffffffffu, have); ++spins) {
       bool progress = false;
-      if (have) {
+      if (have && state == 0) {
         uint32_t v;
         asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];\n" : "=r"(v) : "r"(s_u32(done_cnt + (lane & (NB - 1)))) : "memory");
-        if (v >= uint32_t(G / NB + 1) * uint32_t(CT / 32)) {
-          progress = true;
+        if (v >= uint32_t(G / NB + 1) * uint32_t(CT / 32 / a.ng)) {
           if ((flags & SWF_LAST) && sig >= 0) red_release(a.cnt + sig);
+          state = 1;
+          progress = true;
+        }
+      }
+      // ring space is freed in entry order (the compute groups may finish out of order; the static ring schedule
+      // assumes that everything before a finished entry is finished too)
+      if (have && state == 1) {
+        uint32_t r;
+        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];\n" : "=r"(r) : "r"(s_u32(retired)) : "memory");
+        if (a.ng == 1 || r == uint32_t(G)) {  // one group finishes in order by itself
           for (long long g = first; g < upto; ++g) issue_one(g, iss[g % P]);
+          asm volatile("st.release.cta.shared::cta.u32 [%0], %1;\n" ::"r"(s_u32(retired)), "r"(uint32_t(G + 1)) : "memory");
           G += NB;
           have = G < total;
+          state = 0;
           if (have) load_info(G);
           t0 = clock64();
+          progress = true;
         }
       }
       if (!__any_sync(0xffffffffu, progress)) __nanosleep(a.spin_ns);
@@ -344,7 +360,7 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
         if (!free_slot) {
           uint32_t v;
           asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];\n" : "=r"(v) : "r"(s_u32(done_cnt + (lane & (NB - 1)))) : "memory");
-          free_slot = v >= uint32_t(G / NB) * uint32_t(CT / 32);
+          free_slot = v >= uint32_t(G / NB) * uint32_t(CT / 32 / a.ng);
         }
         if (free_slot) {
 #pragma unroll
@@ -371,7 +387,7 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
         if (ok && dep1 >= 0 && ld_acquire(a.cnt + dep1) < need1) ok = false;
         if (ok) {
           if (a.prof && (dep0 >= 0 || dep1 >= 0))
-            atomicAdd(reinterpret_cast<unsigned long long *>(a.prof + cta * 16 + 4), (unsigned long long)(clock64() - t_wait));
+            atomicAdd(reinterpret_cast<unsigned long long *>(a.prof + cta * 24 + 4), (unsigned long long)(clock64() - t_wait));
           bar_arrive(dep_bar + (lane & (NB - 1)));  // release: the descriptor stores above are visible to the waiters
           G += NB;
           have = G < total;
@@ -390,6 +406,13 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
   // ===============================================================================================================
   // COMPUTE warps
   // ===============================================================================================================
+  // The compute warps form a.ng independent groups of GT threads; group g processes the entries tagged g (static,
+  // all chunks of a block carry the same tag) and has its own workspace, reduction buffers and template cache.
+  const int GT = CT / a.ng, cgrp = tid / GT, gt = tid - cgrp * GT;
+  double *ws = ws_all + cgrp * a.ws_dbl;
+  double *red = red_all + cgrp * 2 * GT * M;
+  uint16_t *tb = tb_all + cgrp * a.tmpl_dbl * 4;
+  auto gsync = [&] { asm volatile("bar.sync %0, %1;\n" ::"r"(cgrp + 1), "r"(GT) : "memory"); };
   double acc[M], pass[M];
   int out_dof = -1, cur_tmpl = -1, nlast = 0;
 #pragma unroll
@@ -399,6 +422,7 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
   for (int step = 0; step < a.n_steps; ++step) {
     const int level = a.level0 + step;
     for (int i = 0; i < P; ++i, ++G) {
+      if (gtab[i] != cgrp) continue;
       const int slot = int(G % NB);
       const uint32_t parity = uint32_t((G / NB) & 1);
       long long t_entry = 0, t_w = 0;
@@ -411,8 +435,10 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
       bar_wait(full_bar + slot, parity, a.abort_flag);
       if (a.prof && tid == 0) {
         const long long t = clock64();
-        a.prof[cta * 16 + 7] += t_w - t_entry;  // waiting for the dependency warp
-        a.prof[cta * 16 + 5] += t - t_w;        // waiting for TMA data
+        a.prof[cta * 24 + 7] += t_w - t_entry;  // waiting for the dependency warp
+        a.prof[cta * 24 + 16 + kind] += t_w - t_entry;
+        if (t_w - t_entry > 2000) a.prof[cta * 24 + 20 + kind] += 1;
+        a.prof[cta * 24 + 5] += t - t_w;        // waiting for TMA data
       }
       long long t_mark = (a.prof && tid == 0) ? clock64() : 0;
 
@@ -428,12 +454,12 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
         const double *tile = reg + e.n[0] + e.n[1];
         const int r_beg = e.a2, r_end = e.a3;
         if (flags & SWF_NEW_RUN) {
-          csync();  // every warp is done with the previous vector
+          gsync();  // every warp is done with the previous vector
           if (fwd) {
             // rows [r_beg, r_end) of v = rhs of the separator dofs + children contributions (assemble_rhs_star
             // fused: rhs = -K_up p_old)
             const double k0 = e.a6 ? a.ky0 : a.kx0, k1 = e.a6 ? a.ky1 : a.kx1;
-            for (int p = r_beg + tid; p < r_end; p += CT) {
+            for (int p = r_beg + gt; p < r_end; p += GT) {
               const int4 gi = reinterpret_cast<const int4 *>(gl)[p - r_beg];
               double val[M];
 #pragma unroll
@@ -453,7 +479,7 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
             }
           } else {
             // rows [r_beg, r_end) of w = [accumulated separator rhs ; solution of the boundary dofs]
-            for (int p = r_beg + tid; p < r_end; p += CT) {
+            for (int p = r_beg + gt; p < r_end; p += GT) {
               if (p < s) {
 #pragma unroll
                 for (int j = 0; j < M; ++j) ws[(p - r_beg) * M + j] = __ldcg(a.z + int64_t(e.o2 + p) * M + j);
@@ -464,15 +490,15 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
               }
             }
           }
-          csync();
+          gsync();
           SWEEP_PROF(14)
         }
         if (flags & SWF_FIRST) {
 #pragma unroll
           for (int j = 0; j < M; ++j) acc[j] = pass[j] = 0.0;
           out_dof = -1;
-          if (tid < cw && e.n[1] > 0) {
-            const int2 ci = reinterpret_cast<const int2 *>(cl)[tid];
+          if (gt < cw && e.n[1] > 0) {
+            const int2 ci = reinterpret_cast<const int2 *>(cl)[gt];
             if (fwd) {  // pass-through of the children's contributions to this boundary dof
               if (ci.x >= 0)
 #pragma unroll
@@ -486,7 +512,7 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
           }
         }
         if (e.n[2] > 0) {
-          const int g = tid / cw, col = tid - g * cw, gn = CT / cw;
+          const int g = gt / cw, col = gt - g * cw, gn = GT / cw;
           if (g < gn) {
             const double *tl = tile + col;
             const int nr = r_end - r_beg;
@@ -511,21 +537,21 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
             for (int off = 16; off >= cw; off >>= 1)
 #pragma unroll
               for (int j = 0; j < M; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
-          double *rb = red + (nlast & 1) * CT * M;  // double buffered: one barrier per block is enough
+          double *rb = red + (nlast & 1) * GT * M;  // double buffered: one barrier per block is enough
           ++nlast;
 #pragma unroll
-          for (int j = 0; j < M; ++j) rb[tid * M + j] = acc[j];
-          csync();
-          if (tid < cw) {
+          for (int j = 0; j < M; ++j) rb[gt * M + j] = acc[j];
+          gsync();
+          if (gt < cw) {
             const int stride = cw < 32 ? 32 : cw;
             double tot[M];
 #pragma unroll
             for (int j = 0; j < M; ++j) tot[j] = 0.0;
-            for (int t = tid; t < CT; t += stride)
+            for (int t = gt; t < GT; t += stride)
 #pragma unroll
               for (int j = 0; j < M; ++j) tot[j] += rb[t * M + j];
             if (fwd) {
-              const int q = col0 + tid;
+              const int q = col0 + gt;
               if (q < b)
 #pragma unroll
                 for (int j = 0; j < M; ++j) a.z[int64_t(e.o3 + q) * M + j] = tot[j] + pass[j];
@@ -547,15 +573,15 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
         // ---------------------------------------------------------------------------------------------------------
         // subtree: factor blob, index lists and this CTA's own vectors are in the ring; walk the levels on chip
         // ---------------------------------------------------------------------------------------------------------
-        csync();  // every warp is done with the workspace (and the template) of the previous entry
+        gsync();  // every warp is done with the workspace (and the template) of the previous entry
         if (e.a0 != cur_tmpl) {
           const int64_t off = a.tmpl_off[e.a0];
           const int n16 = reinterpret_cast<const int *>(a.tmpl16 + off)[8];
           const int4 *g4 = reinterpret_cast<const int4 *>(a.tmpl16 + off);
           int4 *s4 = reinterpret_cast<int4 *>(tb);
-          for (int k = tid; k < (n16 + 7) / 8; k += CT) s4[k] = g4[k];
+          for (int k = gt; k < (n16 + 7) / 8; k += GT) s4[k] = g4[k];
           cur_tmpl = e.a0;
-          csync();
+          gsync();
         }
         const Tmpl T(tb);
         const int I0 = e.a2, J0 = e.a3, bq = e.a1;
@@ -566,7 +592,7 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
           double *vs = ws;                   // right-hand sides of the interior variables
           double *va = vs + T.n_int * M;     // the same after the children's contributions (kept for the backward pass)
           double *zl = va + T.n_int * M;     // boundary contributions of every node
-          for (int l = tid; l < T.n_int; l += CT) {
+          for (int l = gt; l < T.n_int; l += GT) {
             const int code = T.var_code[l];
             const int type = code >> 14, dj = (code >> 7) & 127, di = code & 127;
             double val[M];
@@ -594,12 +620,12 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
 #pragma unroll
             for (int j = 0; j < M; ++j) vs[l * M + j] = val[j];
           }
-          csync();
+          gsync();
           SWEEP_PROF(11)
           // one phase per level: every boundary output of every node of the level; the separator values a node
           // needs (own rhs + children's contributions) are formed on the fly, its first output stores them
           for (int lv = 0; lv < T.n_levels; ++lv) {
-            for (int o = T.lvl_out[lv] + tid; o < T.lvl_out[lv + 1]; o += CT) {
+            for (int o = T.lvl_out[lv] + gt; o < T.lvl_out[lv + 1]; o += GT) {
               const uint4 D = T.fdesc[o];
               const int rf_off = D.x & 0xFFFF, sb = D.x >> 16, sep0 = D.y & 0xFFFF, writer = D.y >> 16;
               const int c0 = D.z & 0xFFFF, c1 = D.z >> 16;
@@ -637,12 +663,12 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
 #pragma unroll
               for (int j = 0; j < M; ++j) zl[o * M + j] = av[j];
             }
-            csync();
+            gsync();
           }
           SWEEP_PROF(12)
           if (T.n_rootb == 0) {  // the subtree is the whole subdomain: its root has no boundary, hence no output
             const int v0 = T.lvlb[T.n_levels - 1].x, n_out = T.lvlb[T.n_levels - 1].y;
-            for (int v = v0 + tid; v < v0 + n_out; v += CT) {
+            for (int v = v0 + gt; v < v0 + n_out; v += GT) {
               const uint32_t cc = T.sc[v];
               const int k0 = cc & 0xFFFF, k1 = cc >> 16;
 #pragma unroll
@@ -653,30 +679,30 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
                 va[v * M + j] = vk;
               }
             }
-            csync();
+            gsync();
           }
-          for (int l = tid; l < T.n_int * M; l += CT) a.xi[int64_t(e.o1) * M + l] = va[l];
+          for (int l = gt; l < T.n_int * M; l += GT) a.xi[int64_t(e.o1) * M + l] = va[l];
           const int zr = T.zl_size - T.n_rootb;  // the root is the last node
-          for (int q = tid; q < T.n_rootb * M; q += CT) a.z[int64_t(e.o0) * M + q] = zl[zr * M + q];
+          for (int q = gt; q < T.n_rootb * M; q += GT) a.z[int64_t(e.o0) * M + q] = zl[zr * M + q];
           fence_async_global();  // xi is streamed back by TMA in the backward entry
           SWEEP_PROF(13)
         } else {
           const int *xb = reinterpret_cast<const int *>(reg + e.n[0]);
           const double *zs = reg + e.n[0] + e.n[1];  // accumulated right-hand sides of the interior variables
           double *xs = ws;                          // solution: [interior | root boundary]
-          for (int q = tid; q < T.n_rootb; q += CT) {
+          for (int q = gt; q < T.n_rootb; q += GT) {
             const int64_t d = xb[q];
 #pragma unroll
             for (int j = 0; j < M; ++j) xs[(T.n_int + q) * M + j] = __ldcg(a.x + d * M + j);
           }
-          csync();
+          gsync();
           SWEEP_PROF(8)
           // one phase per level: x_s = [F11^-1 | -G^T] [z_s ; x_b], 2^tl lanes per row, inputs read in place
           for (int lv = T.n_levels - 1; lv >= 0; --lv) {
             const int4 Lh = T.lvlb[lv];
             const int v0 = Lh.x, n_out = Lh.y, tl = Lh.z, estep = Lh.w;
-            const int tpo = 1 << tl, per = CT >> tl;
-            const int grp = tid >> tl, rl = tid & (tpo - 1);
+            const int tpo = 1 << tl, per = GT >> tl;
+            const int grp = gt >> tl, rl = gt & (tpo - 1);
             for (int o0 = 0; o0 < n_out; o0 += per) {
               const int o = o0 + grp;
               double av[M];
@@ -703,11 +729,11 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
 #pragma unroll
                 for (int j = 0; j < M; ++j) xs[(v0 + o) * M + j] = av[j];
             }
-            csync();
+            gsync();
           }
           SWEEP_PROF(9)
           // pressure recovery p = p_old - M^-1 K_pu u for the cells of the box; next right-hand side source
-          for (int c = tid; c < ncell; c += CT) {
+          for (int c = gt; c < ncell; c += GT) {
             const int el = T.cell_edge[4 * c], er = T.cell_edge[4 * c + 1], eb = T.cell_edge[4 * c + 2],
                       et = T.cell_edge[4 * c + 3];
             const double mi = a.minv ? a.minv[e.o2 + c] : a.minv_const;
@@ -735,7 +761,7 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
           fence_async_global();  // the box pressures are streamed back by TMA in the next step
           SWEEP_PROF(10)
           if (bq >= 0) {  // subdom_to_st_distribute: flux traces of the interface dofs
-            for (int l = tid; l < T.n_int * M; l += CT) {
+            for (int l = gt; l < T.n_int * M; l += GT) {
               const int q = a.sub_q[bq + l];
               if (q >= 0) {
                 double *tp = a.bq_trace[q];
@@ -744,7 +770,7 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
             }
           }
           if (a.hist) {
-            for (int l = tid; l < T.n_int; l += CT) {
+            for (int l = gt; l < T.n_int; l += GT) {
               const int64_t d = sweep_dof(a, I0, J0, T.var_code[l]);
 #pragma unroll
               for (int j = 0; j < M; ++j)
@@ -759,8 +785,13 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
 
       // ---- end of entry: every warp reports on its own ----------------------------------------------------------
       if (a.prof && tid == 0) {
-        a.prof[cta * 16 + kind] += clock64() - t_entry;
-        a.prof[cta * 16 + 6] += 1;
+        const long long t_end = clock64();
+        a.prof[cta * 24 + kind] += t_end - t_entry;
+        a.prof[cta * 24 + 6] += 1;
+        if (a.trace && step == 1) {
+          long long *tr = a.trace + (int64_t(e_first) + i) * 3;
+          tr[0] = t_entry; tr[1] = t_w; tr[2] = t_end;
+        }
       }
       __syncwarp();
       if (lane == 0) done_signal(done_cnt + slot);
@@ -775,7 +806,7 @@ size_t sweep_smem_optin() {
   return size_t(optin);
 }
 
-int sweep_fixed_dbl(int M, int ct) { return 19 * SWEEP_NBAR + 2 * ct * M; }
+int sweep_fixed_dbl(int M, int ct) { return 19 * SWEEP_NBAR + SWEEP_GTAB_DBL + 2 * ct * M; }
 
 template <int M, int CT>
 static int ctas_per_sm_t(size_t smem) {

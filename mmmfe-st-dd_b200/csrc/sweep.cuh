@@ -28,6 +28,8 @@ namespace mmmfe {
 constexpr int SWEEP_NBAR = 16;                     // slots = most entries in flight per CTA (one service lane each)
 constexpr int SWEEP_TMPL_HDR = 48;                 // int32 header words of a packed subtree template
 constexpr int SWEEP_SEGS = 4;                      // TMA copies per entry
+constexpr int SWEEP_GTAB_DBL = 128;                // shared-memory doubles of the per-entry group table (+ counter)
+constexpr int SWEEP_MAX_ENTRIES = 8 * SWEEP_GTAB_DBL - 8;  // entries per CTA and step the group table can hold
 
 enum SweepKind : int32_t { SW_SUB_FWD = 0, SW_TOP_FWD = 1, SW_TOP_BWD = 2, SW_SUB_BWD = 3 };
 enum SweepFlag : int32_t { SWF_FIRST = 1, SWF_LAST = 2, SWF_NEW_RUN = 4, SWF_WRITE_ZS = 8 };
@@ -69,6 +71,8 @@ struct SweepArgs {
   const SweepIssue *issue;
   const int32_t *cta_begin;     // n_cta + 1
   const int32_t *cta_prologue;  // entries issued before the first one is processed
+  const uint8_t *grp;           // compute group of every entry
+  int32_t ng;                   // compute groups per CTA (1, 2 or 4)
   const double *Rs;             // factor in sweep layout
   const int32_t *index;         // static index lists (gather / column lists, root-boundary dofs)
   const uint16_t *tmpl16;       // packed subtree templates
@@ -80,7 +84,8 @@ struct SweepArgs {
   double *ptil;                 // [cell][M], box-major cell order
   uint32_t *cnt;                // completion counters (2 per sweep node: forward, backward)
   volatile int *abort_flag;     // device memory: set when a spin-wait gave up
-  long long *prof;              // optional [n_cta][8] cycle counters
+  long long *prof;              // optional [n_cta][24] cycle counters
+  long long *trace;             // optional [entries][3] clock stamps of step 1 (start, opened, end)
   const double *minv;           // 1 / (c0 |cell|), box-major cell order; nullptr: minv_const everywhere
   double minv_const;
   // boundary entries of the batch (interface dofs; in the bar problem also outer Dirichlet dofs)
@@ -100,7 +105,7 @@ struct SweepArgs {
   int32_t nx, ny;
   int64_t nxe, n_flux, n_pressure;
   int32_t n_steps, level0;
-  int32_t tmpl_dbl, ws_dbl, ring_dbl;  // shared-memory partition in doubles
+  int32_t tmpl_dbl, ws_dbl, ring_dbl;  // shared-memory partition in doubles (template and workspace: per group)
   int32_t evict_first;
   uint32_t spin_ns;             // back-off of the service warps' polling loops
 };

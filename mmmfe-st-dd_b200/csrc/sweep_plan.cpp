@@ -323,10 +323,15 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
   return nullptr;
 }
 
-const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t M, size_t smem_budget,
+const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t M, int32_t ng, size_t smem_budget,
                                  double min_fill, SweepSchedule &S) {
   S = SweepSchedule();
+  S.ng = ng;
   const int32_t n_cta = L.n_cta;
+  // compute group of every entry: blocks (with all their chunks) and subtrees are dealt out round-robin
+  std::vector<std::vector<uint8_t>> per_grp(n_cta);
+  std::vector<int32_t> next_grp(n_cta, 0);
+  std::vector<std::vector<int32_t>> last_of_grp(n_cta, std::vector<int32_t>(ng, -1));
   // ---- static assignment ----
   std::vector<std::vector<SweepEntry>> per(n_cta);
   std::vector<std::vector<SweepIssue>> per_iss(n_cta);
@@ -377,10 +382,17 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
     for (size_t t = 0; t < boundary.size(); ++t)
       cta_of_inst[boundary[t]] = n_cta - 1 - int32_t(int64_t(t) * n_cta / int64_t(boundary.size()));
   }
+  auto take_grp = [&](int32_t cta) {
+    const int32_t g = next_grp[cta];
+    next_grp[cta] = (g + 1) % ng;
+    return g;
+  };
   for (int32_t k = 0; k < n_inst; ++k) {
     SweepIssue iss;
-    per[cta_of_inst[k]].push_back(sub_entry(k, true, iss));
-    per_iss[cta_of_inst[k]].push_back(iss);
+    const int32_t cta = cta_of_inst[k];
+    per[cta].push_back(sub_entry(k, true, iss));
+    per_iss[cta].push_back(iss);
+    per_grp[cta].push_back(uint8_t(take_grp(cta)));
   }
 
   int32_t rot = 0;
@@ -402,6 +414,7 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
       const bool fwd = it.kind == SW_TOP_FWD;
       const int32_t cw = it.cw;
       const int32_t rows_per = std::max(4, (L.chunk_dbl / cw) & ~3);  // multiples of 4: aligned index-list slices
+      const int32_t grp = take_grp(cta);
       int32_t r = 0;
       do {
         const int32_t r1 = std::min(it.rlen, r + rows_per);
@@ -413,8 +426,9 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
         e.a7 = it.node;
         e.o2 = sn.zs_off; e.o3 = sn.zc_off;
         // the vector rows [r, r1) are staged by this entry unless the previous one left exactly them in place
-        const bool same_rows = !list.empty() && list.back().kind == it.kind && list.back().a7 == it.node &&
-                               list.back().a2 == r && list.back().a3 == r1;
+        const int32_t prev = last_of_grp[cta][grp];  // the vector the group's previous entry left in its workspace
+        const bool same_rows = prev >= 0 && list[prev].kind == it.kind && list[prev].a7 == it.node &&
+                               list[prev].a2 == r && list[prev].a3 == r1;
         if (!same_rows && r1 > r) {
           e.flags |= SWF_NEW_RUN;
           if (fwd) {
@@ -449,40 +463,46 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
           if (sn.parent >= 0) { e.dep0 = 2 * sn.parent + 1; e.dep0_n = L.nodes[sn.parent].n_bwd; }
           else { e.dep0 = 2 * it.node; e.dep0_n = sn.n_fwd; }
         }
+        last_of_grp[cta][grp] = int32_t(list.size());
         list.push_back(e);
         per_iss[cta].push_back(iss);
+        per_grp[cta].push_back(uint8_t(grp));
         r = r1;
       } while (r < it.rlen);
     }
-    rot = (rot + used + 1) % n_cta;
+    (void)used;  // no rotation between levels: the children of a CTA's fronts are mostly its own earlier entries
   };
   for (size_t h = 0; h < L.fwd.size(); ++h) place_level(L.fwd[h]);
   for (size_t h = L.bwd.size(); h-- > 0;) place_level(L.bwd[h]);
   for (int32_t k = 0; k < n_inst; ++k) {
     SweepIssue iss;
-    per[cta_of_inst[k]].push_back(sub_entry(k, false, iss));
-    per_iss[cta_of_inst[k]].push_back(iss);
+    const int32_t cta = cta_of_inst[k];
+    per[cta].push_back(sub_entry(k, false, iss));
+    per_iss[cta].push_back(iss);
+    per_grp[cta].push_back(uint8_t(take_grp(cta)));
   }
 
   // ---- shared-memory partition (doubles) ----
   for (const auto &list : per)
     for (const auto &e : list) S.entry_max = std::max(S.entry_max, e.n[0] + e.n[1] + e.n[2] + e.n[3]);
   const int64_t total_dbl = int64_t(smem_budget / 8);
-  const int64_t fixed = sweep_fixed_dbl(M, L.ct);
+  const int64_t fixed = sweep_fixed_dbl(M, L.ct * ng);
+  for (const auto &list : per)
+    if (int64_t(list.size()) > SWEEP_MAX_ENTRIES) return "too many entries per CTA for the group table";
   S.tmpl_dbl = even((L.tmpl16_max + 3) / 4);
   int32_t rows_max = 0;
   for (const auto &list : per)
     for (const auto &e : list)
       if (e.kind == SW_TOP_FWD || e.kind == SW_TOP_BWD) rows_max = std::max(rows_max, e.a3 - e.a2);
   S.ws_dbl = even(int64_t(std::max(rows_max, L.sub_ws_max)) * M);
-  const int64_t ring = (total_dbl - fixed - S.tmpl_dbl - S.ws_dbl) & ~int64_t(1);
+  const int64_t ring = (total_dbl - fixed - int64_t(ng) * (S.tmpl_dbl + S.ws_dbl)) & ~int64_t(1);
   if (double(ring) < std::max(1.0, min_fill) * double(S.entry_max)) {
     std::snprintf(g_msg, sizeof g_msg, "shared-memory ring (%lld doubles) is too small for entries of %d doubles",
                   (long long)ring, S.entry_max);
     return g_msg;
   }
   S.ring_dbl = int32_t(ring);
-  S.smem_bytes = size_t(fixed + S.tmpl_dbl + S.ws_dbl + S.ring_dbl) * 8;
+  S.smem_bytes = size_t(fixed + int64_t(ng) * (S.tmpl_dbl + S.ws_dbl) + S.ring_dbl) * 8;
 
   // ---- ring schedule per CTA ----
   S.cta_begin.assign(n_cta + 1, 0);
@@ -553,6 +573,7 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
       per_iss[c][i].ring_off = per[c][i].ring_off;
       S.entries.push_back(per[c][i]);
       S.issue.push_back(per_iss[c][i]);
+      S.grp.push_back(per_grp[c][i]);
     }
   return nullptr;
 }
@@ -650,7 +671,7 @@ extern "C" int mmmfe_sweep_plan_check(int32_t nx, int32_t ny, int32_t leaf_cells
   mmmfe::SweepLayout L;
   if (const char *e = mmmfe::build_sweep_layout(t, t.idx, std::vector<int32_t>(), n_cta, chunk_dbl, ct, L)) { say(e); return -2; }
   mmmfe::SweepSchedule S;
-  if (const char *e = mmmfe::build_sweep_schedule(t, L, M, size_t(smem_bytes), 2.0, S)) { say(e); return -3; }
+  if (const char *e = mmmfe::build_sweep_schedule(t, L, M, 1, size_t(smem_bytes), 2.0, S)) { say(e); return -3; }
   if (stats) {
     stats[0] = int64_t(L.nodes.size()); stats[1] = L.n_top; stats[2] = int64_t(S.entries.size()); stats[3] = L.rs_total;
     stats[4] = S.ring_dbl; stats[5] = S.ws_dbl; stats[6] = S.entry_max; stats[7] = int64_t(S.smem_bytes);

@@ -33,7 +33,7 @@ struct SweepInstH {       // one subtree instance
 };
 
 struct SweepLayout {
-  int32_t n_cta = 0, chunk_dbl = 2048, ct = 256;  // CTAs, doubles per streamed chunk, compute threads per CTA
+  int32_t n_cta = 0, chunk_dbl = 2048, ct = 256;  // CTAs, doubles per streamed chunk, compute threads per GROUP
   int32_t n_top = 0;
   std::vector<SweepNodeH> nodes;                 // top fronts (any order), then one pseudo node per subtree instance
   std::vector<SweepInstH> inst;
@@ -58,6 +58,8 @@ struct SweepSchedule {
   std::vector<SweepEntry> entries;
   std::vector<SweepIssue> issue;
   std::vector<int32_t> cta_begin, cta_prologue;
+  std::vector<uint8_t> grp;      // compute group of every entry
+  int32_t ng = 1;
   int32_t tmpl_dbl = 0, ws_dbl = 0, ring_dbl = 0, entry_max = 0;
   size_t smem_bytes = 0;
 };
@@ -71,7 +73,7 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
 
 // Shared-memory partition for M right-hand sides within smem_budget bytes per CTA, entry lists and ring schedule.
 // Returns nullptr on success; a message when the ring cannot hold max(2, min_fill) of the largest entries.
-const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t M, size_t smem_budget,
+const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t M, int32_t ng, size_t smem_budget,
                                  double min_fill, SweepSchedule &S);
 
 // CPU model of the kernel's control flow: replays n_steps of every CTA's entry list against the completion counters

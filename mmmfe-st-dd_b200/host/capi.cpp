@@ -68,6 +68,9 @@ int mmmfe_host_run(const char *parameter_file, const mmmfe_host_options *opt, mm
         d.e2e_ms_per_iteration = r.e2e_ms_per_iteration; d.e2e_h2d_bytes = r.e2e_h2d_bytes; d.e2e_d2h_bytes = r.e2e_d2h_bytes;
         d.gmres_kernel_launches = r.gmres_kernel_launches;
         for (int k = 0; k < 6; ++k) { d.prof_ms[k] = r.prof_ms[k]; d.prof_bytes[k] = r.prof_bytes[k]; d.prof_launches[k] = r.prof_launches[k]; }
+        d.sweep_batches = r.sweep_batches;
+        for (int k = 0; k < 4; ++k) { d.sweep_steps[k] = r.sweep_steps[k]; d.sweep_ms[k] = r.sweep_ms[k]; d.sweep_bytes_per_step[k] = r.sweep_bytes_per_step[k]; }
+        d.tune_us_sweep = r.tune_us_sweep; d.tune_us_levels = r.tune_us_levels; d.sweep_planned = r.sweep_planned;
       }
       ++n;
     }

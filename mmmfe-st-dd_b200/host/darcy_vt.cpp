@@ -747,8 +747,15 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
     }
     if (control.apply_repeat > 0)
       check(ctx, mmmfe_apply_interface_operator_device(ctx, control.apply_repeat, &control.apply_ms), "apply");
-    if (control.profile)
+    if (control.profile) {
       check(ctx, mmmfe_profile_step(ctx, rep.prof_ms, rep.prof_bytes, (int64_t *)rep.prof_launches), "profile");
+      int32_t nsw = 0;
+      check(ctx, mmmfe_profile_sweeps(ctx, 4, rep.sweep_ms, rep.sweep_bytes_per_step, rep.sweep_steps, &nsw), "profile sweeps");
+      rep.sweep_batches = nsw;
+      rep.tune_us_sweep = mmmfe_stat(ctx, "tune_us_sweep");
+      rep.tune_us_levels = mmmfe_stat(ctx, "tune_us_levels");
+      rep.sweep_planned = mmmfe_stat(ctx, "sweep_planned");
+    }
     if (control.e2e_iterations > 0) {
       // The same iteration driven from host memory: every step copies the Krylov vector host -> device from a
       // pinned buffer, applies the operator, copies A q back and does the Arnoldi update on the host

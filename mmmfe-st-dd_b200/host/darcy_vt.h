@@ -46,6 +46,10 @@ struct CycleReport {
   long long e2e_h2d_bytes = 0, e2e_d2h_bytes = 0, gmres_kernel_launches = 0;
   double prof_ms[6] = {0, 0, 0, 0, 0, 0}, prof_bytes[6] = {0, 0, 0, 0, 0, 0};
   long long prof_launches[6] = {0, 0, 0, 0, 0, 0};
+  // persistent sweep kernel (when the engine selected it): per batch one timed star sweep
+  int sweep_batches = 0, sweep_steps[4] = {0, 0, 0, 0};
+  double sweep_ms[4] = {0, 0, 0, 0}, sweep_bytes_per_step[4] = {0, 0, 0, 0};
+  long long tune_us_sweep = 0, tune_us_levels = 0, sweep_planned = 0;
 };
 
 struct RunControl {

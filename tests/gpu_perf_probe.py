@@ -28,7 +28,7 @@ if __name__ == "__main__":
     prob = build(nf, ntf, nc, ntc, [ms, ms, mt])
     eng = pkg().Engine()
     import os
-    for key in ("subtree_cells", "leaf_cells", "use_graphs", "use_sweep", "sweep_chunk", "sweep_min_fill", "sweep_evict_first", "sweep_compute_threads", "sweep_ctas_per_sm", "sweep_spin_ns"):
+    for key in ("subtree_cells", "leaf_cells", "use_graphs", "use_sweep", "sweep_chunk", "sweep_min_fill", "sweep_evict_first", "sweep_compute_threads", "sweep_ctas_per_sm", "sweep_spin_ns", "sweep_groups"):
         if os.environ.get("MMMFE_" + key.upper()):
             eng.set_option(key, float(os.environ["MMMFE_" + key.upper()]))
     for sd in prob.subs:
@@ -57,6 +57,20 @@ if __name__ == "__main__":
     for bi in range(eng.stat("sweep_batches")):
         cyc = eng.profile_sweep_cycles(bi)
         print("  cycles/CTA:", {k: round(v) for k, v in cyc.items()})
+    if os.environ.get("MMMFE_TRACE_ALL"):
+        cb, kh, st = eng.sweep_trace(0)
+        np.savez(os.environ["MMMFE_TRACE_ALL"], cb=cb, kh=kh, st=st)
+    if os.environ.get("MMMFE_TRACE"):
+        cb, kh, st = eng.sweep_trace(0)
+        for cta in [int(x) for x in os.environ["MMMFE_TRACE"].split(",")]:
+            b0, b1 = cb[cta], cb[cta + 1]
+            t0 = st[b0:b1, 0][st[b0:b1, 0] > 0].min()
+            print(f"--- cta {cta}: entries {b1 - b0}")
+            for i in range(b0, b1):
+                if st[i, 0] == 0:
+                    continue
+                print(f"  {i - b0:4d} kind {kh[i, 0]} h {kh[i, 1]:2d} start {st[i, 0] - t0:8d} wait {st[i, 1] - st[i, 0]:7d} "
+                      f"run {st[i, 2] - st[i, 1]:7d}")
     for k, v in eng.profile_step().items():
         print(f"  {k:18s} {v['ms']*1e3:8.1f} us  {v['bytes']/1e6:8.1f} MB  {v['launches']:3d} launches  {v['bytes']/1e9/max(v['ms'],1e-9)*1e3:7.0f} GB/s")
     eng.close()

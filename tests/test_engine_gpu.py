@@ -85,7 +85,7 @@ def test_persistent_sweep_kernel_matches_oracle_and_generic_kernels(nxs, nts, mo
     ref = prob.apply_S(q)
     outs = {}
     for sweep in (1, 0):
-        eng = engine_from_oracle(prob, options={"use_sweep": sweep, "subtree_cells": 64})
+        eng = engine_from_oracle(prob, options={"use_sweep": sweep, "subtree_cells": 64, "sweep_autotune": 0})
         eng.setup()
         assert eng.stat("rt0_factors") == eng.stats()["factor_groups"]
         assert eng.stat("sweep_batches") == (eng.stat("batches") if sweep else 0)
@@ -104,7 +104,7 @@ def test_persistent_sweep_kernel_with_permuted_dofs():
     prm = default_params(1, 2)
     prob = make_problem(prm, 1)
     q = np.random.default_rng(9).standard_normal(prob.n_iface)
-    eng = engine_from_oracle(prob, perm_seed=21)
+    eng = engine_from_oracle(prob, perm_seed=21, options={"sweep_autotune": 0})
     eng.setup()
     assert eng.stat("sweep_batches") == eng.stat("batches")
     assert rel_l2(eng.apply(q), prob.apply_S(q)) < TOL
