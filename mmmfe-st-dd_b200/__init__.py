@@ -296,8 +296,8 @@ class Engine:
         self._check(self.lib.mmmfe_profile_sweep_cycles(self.h, batch, _ptr(out, c_f64p)))
         names = ["sub_fwd", "top_fwd", "top_bwd", "sub_bwd", "counter_wait", "tma_wait", "entries", "open_wait",
                  "sb_gather", "sb_levels", "sb_epilogue", "sf_rhs", "sf_levels", "sf_output", "top_gather", "top_tile",
-                 "wait_sub_fwd", "wait_top_fwd", "wait_top_bwd", "wait_sub_bwd", "nwait_sub_fwd", "nwait_top_fwd",
-                 "nwait_top_bwd", "nwait_sub_bwd"]
+                 "wait_sub_fwd", "wait_top_fwd", "wait_top_bwd", "wait_sub_bwd", "wave_sync0", "wave_tile",
+                 "wave_sync1", "wave_out"]
         return dict(zip(names, (float(v) for v in out)))
 
     def debug_get_factor(self, li, r_total):

@@ -174,10 +174,11 @@ struct mmmfe_ctx {
   int device = 0;
   std::string err;
   bool keep_history = true, use_graphs = true, use_sweep = true, sweep_evict_first = true;
-  int leaf_cells = 4, subtree_cells = 256, sweep_chunk = 8192, sweep_ct = 256, sweep_ctas_per_sm = 1, sweep_groups = 1;
+  int leaf_cells = 4, subtree_cells = 256, sweep_chunk = 4096, sweep_ct = 256, sweep_ctas_per_sm = 1, sweep_groups = 1;
   bool sweep_autotune = true;
   double tune_ms_sweep = 0.0, tune_ms_levels = 0.0;
   double sweep_min_fill = 1.75;
+  int sweep_mt = 512;
   int sweep_spin_ns = 100;
   bool is_setup = false, bar_done = false, final_done = false;
   int rank = 0, world = 1;
@@ -501,7 +502,7 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax) 
     {
       std::vector<int32_t> iu(tr.idx.size());
       for (size_t i = 0; i < tr.idx.size(); ++i) iu[i] = dof_of_canon.empty() ? tr.idx[i] : dof_of_canon[tr.idx[i]];
-      if (build_sweep_layout(tr, iu, dof_of_canon, F->sweep_n_cta, c->sweep_chunk, F->sweep_ct / F->sweep_ng, F->lay) != nullptr) { want_sweep = false; break; }
+      if (build_sweep_layout(tr, iu, dof_of_canon, F->sweep_n_cta, c->sweep_chunk, F->sweep_ct / F->sweep_ng, F->lay, F->sweep_ng, c->sweep_mt) != nullptr) { want_sweep = false; break; }
     }
     SweepSchedule probe;
     if (build_sweep_schedule(tr, F->lay, Mmax, F->sweep_ng, F->sweep_budget, c->sweep_min_fill, probe) == nullptr) { sweep_planned = true; break; }
@@ -1058,6 +1059,7 @@ static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> 
   a.tmpl_dbl = S.tmpl_dbl; a.ws_dbl = S.ws_dbl; a.ring_dbl = S.ring_dbl;
   a.evict_first = c->sweep_evict_first ? 1 : 0;
   a.spin_ns = uint32_t(c->sweep_spin_ns);
+  a.poll_window = std::max(4, 2 * F.sweep_ng);
   if (!c->abort_flag) {
     CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&c->abort_flag), sizeof(int)));
     CUDA_CHECK(cudaMemset(c->abort_flag, 0, sizeof(int)));
@@ -1259,10 +1261,11 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   else if (k == "sweep_spin_ns") c->sweep_spin_ns = std::max(0, int(value));
   else if (k == "sweep_autotune") c->sweep_autotune = value != 0;
   else if (k == "sweep_groups") {
-    if (value != 1 && value != 2 && value != 4) { c->err = "sweep_groups must be 1, 2 or 4"; return MMMFE_E_INVALID; }
+    if (value != 1 && value != 2 && value != 4 && value != 8) { c->err = "sweep_groups must be 1, 2, 4 or 8"; return MMMFE_E_INVALID; }
     c->sweep_groups = int(value);
   }
   else if (k == "sweep_min_fill") c->sweep_min_fill = value;
+  else if (k == "sweep_micro_tile") c->sweep_mt = std::max(64, int(value));
   else { c->err = "unknown option " + k; return MMMFE_E_INVALID; }
   return MMMFE_OK;
 }
@@ -1621,7 +1624,7 @@ int mmmfe_debug_sweep_trace(mmmfe_ctx *c, int32_t batch, int64_t cap, int64_t *n
       for (int64_t i = 0; i < ne; ++i) {
         kind_height[2 * i] = he[i].kind;
         const bool top = he[i].kind == SW_TOP_FWD || he[i].kind == SW_TOP_BWD;
-        kind_height[2 * i + 1] = top ? b.factor->lay.nodes[he[i].a7].height : 0;
+        kind_height[2 * i + 1] = top ? he[i].a7 : 0;
       }
       CUDA_CHECK(cudaMemcpy(cta_begin_out, b.s_cta_begin.p, size_t(n_cta + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
       return MMMFE_OK;

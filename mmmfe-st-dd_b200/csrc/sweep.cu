@@ -58,7 +58,6 @@ void launch_repack_sub(const RepackSub *d_desc, int32_t n_desc, const int32_t *p
 namespace {
 
 constexpr int NB = SWEEP_NBAR;
-constexpr int SWEEP_POLL_WINDOW = 4;  // entries ahead of the oldest unopened one that poll completion counters
 
 __device__ __forceinline__ uint32_t s_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
@@ -161,6 +160,20 @@ __device__ __forceinline__ int t16(const uint16_t *p, int i) {
   return v == 0xFFFF ? -1 : v;
 }
 
+template <int M>
+__device__ __forceinline__ void ld_vec(const double *p, double (&v)[M]) {  // L2 load of the M right-hand sides of one entry
+  if constexpr (M == 1) {
+    v[0] = __ldcg(p);
+  } else {
+#pragma unroll
+    for (int j = 0; j < M; j += 2) {
+      const double2 t = __ldcg(reinterpret_cast<const double2 *>(p) + j / 2);
+      v[j] = t.x;
+      v[j + 1] = t.y;
+    }
+  }
+}
+
 struct Tmpl {  // views into the shared-memory copy of a packed template (layout: sweep_plan.cpp pack_template)
   int n_levels, n_int, n_rootb, zl_size, w, h;
   const uint16_t *var_code, *cell_edge, *lvl_out, *in_idx;
@@ -199,7 +212,7 @@ __device__ __forceinline__ int64_t sweep_dof(const SweepArgs &a, int I0, int J0,
   }
 
 template <int M, int CT>
-__global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))) k_sweep(const SweepArgs a) {
+__global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))) k_sweep(const SweepArgs a) {
   extern __shared__ __align__(128) double sm[];
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(sm);  // TMA data of the entry landed
   uint32_t *done_cnt = reinterpret_cast<uint32_t *>(full_bar + NB);  // compute warps that finished the slot's entries
@@ -207,9 +220,8 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
   SweepEntry *edesc = reinterpret_cast<SweepEntry *>(sm + 3 * NB);
   uint8_t *gtab = reinterpret_cast<uint8_t *>(sm + 19 * NB);  // compute group of every entry of this CTA
   uint32_t *retired = reinterpret_cast<uint32_t *>(sm + 19 * NB + SWEEP_GTAB_DBL - 1);
-  double *red_all = sm + 19 * NB + SWEEP_GTAB_DBL;           // two reduction buffers per group
-  uint16_t *tb_all = reinterpret_cast<uint16_t *>(red_all + 2 * CT * M);
-  double *ws_all = red_all + 2 * CT * M + a.ng * a.tmpl_dbl;
+  uint16_t *tb_all = reinterpret_cast<uint16_t *>(sm + 19 * NB + SWEEP_GTAB_DBL);
+  double *ws_all = sm + 19 * NB + SWEEP_GTAB_DBL + a.ng * a.tmpl_dbl;
   double *ring = ws_all + a.ng * a.ws_dbl;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -286,12 +298,13 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
     }
     // One converged polling loop: lane l owns slot l and retires the entries G = l (mod NB) in turn.
     long long G = lane < NB ? lane : total;
-    int flags = 0, sig = -1;
+    int sig = -1, n_sig = 0, sig_off = 0;
     long long first = 0, upto = 0;
     auto load_info = [&](long long g) {
       const int step = int(g / P), i = int(g - (long long)step * P);
-      flags = ents[i].flags;
       sig = ents[i].sig;
+      n_sig = ents[i].n_sig;
+      sig_off = ents[i].sig_off;
       first = (i == 0) ? (step == 0 ? (long long)a.cta_prologue[cta] : (long long)(step - 1) * P + ents[P - 1].issue_upto)
                        : (long long)step * P + ents[i - 1].issue_upto;
       upto = (long long)step * P + ents[i].issue_upto;
@@ -307,7 +320,8 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
         uint32_t v;
         asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];\n" : "=r"(v) : "r"(s_u32(done_cnt + (lane & (NB - 1)))) : "memory");
         if (v >= uint32_t(G / NB + 1) * uint32_t(CT / 32 / a.ng)) {
-          if ((flags & SWF_LAST) && sig >= 0) red_release(a.cnt + sig);
+          if (sig >= 0) red_release(a.cnt + sig);
+          for (int t = 0; t < n_sig; ++t) red_release(a.cnt + a.index[sig_off + t]);
           state = 1;
           progress = true;
         }
@@ -344,8 +358,8 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
     bool have = G < total;
     int state = 0;
     int4 d[8];
-    int dep0 = -1, dep1 = -1;
-    uint32_t need0 = 0, need1 = 0;
+    int n_dep = 0;
+    uint32_t step1 = 0;
     auto load_desc = [&](long long g) {
       const int i = int(g % P);
 #pragma unroll
@@ -365,14 +379,8 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
         if (free_slot) {
 #pragma unroll
           for (int t = 0; t < 8; ++t) reinterpret_cast<int4 *>(&edesc[lane & (NB - 1)])[t] = d[t];
-          const int kind = d[0].x, fl = d[0].y;
-          const bool waits = kind == SW_SUB_BWD || ((kind == SW_TOP_FWD || kind == SW_TOP_BWD) &&
-                                                    (fl & SWF_NEW_RUN) && (fl & SWF_FIRST));
-          const uint32_t step1 = uint32_t(G / P) + 1u;
-          dep0 = waits ? d[1].y : -1;
-          dep1 = waits ? d[1].w : -1;
-          need0 = step1 * uint32_t(d[1].z);
-          need1 = step1 * uint32_t(d[2].x);
+          step1 = uint32_t(G / P) + 1u;
+          n_dep = d[1].w;
           state = 1;
           progress = true;
           if (a.prof) t_wait = clock64();
@@ -381,12 +389,16 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
       // only the few entries the compute warps need next poll the global counters: the others could not be used yet
       // anyway and would only load the L2 slices that hold hot counters
       const long long g_min = __reduce_min_sync(0xffffffffu, have ? (unsigned)(G & 0x7fffffff) : 0x7fffffffu);
-      if (have && state == 1 && (dep0 < 0 && dep1 < 0 || (long long)(G & 0x7fffffff) < g_min + SWEEP_POLL_WINDOW)) {
+      if (have && state == 1 && (n_dep == 0 || (long long)(G & 0x7fffffff) < g_min + a.poll_window)) {
         bool ok = true;
-        if (dep0 >= 0 && ld_acquire(a.cnt + dep0) < need0) ok = false;
-        if (ok && dep1 >= 0 && ld_acquire(a.cnt + dep1) < need1) ok = false;
+        const int deps[SWEEP_MAX_DEPS] = {d[2].x, d[2].y, d[2].z, d[2].w, d[3].x, d[3].y, d[3].z, d[3].w};
+#pragma unroll
+        for (int t = 0; t < SWEEP_MAX_DEPS; ++t)
+          if (ok && t < n_dep &&
+              ld_acquire(a.cnt + (deps[t] & ((1 << SWEEP_DEP_SHIFT) - 1))) < step1 * uint32_t(deps[t] >> SWEEP_DEP_SHIFT))
+            ok = false;
         if (ok) {
-          if (a.prof && (dep0 >= 0 || dep1 >= 0))
+          if (a.prof && n_dep > 0)
             atomicAdd(reinterpret_cast<unsigned long long *>(a.prof + cta * 24 + 4), (unsigned long long)(clock64() - t_wait));
           bar_arrive(dep_bar + (lane & (NB - 1)));  // release: the descriptor stores above are visible to the waiters
           G += NB;
@@ -410,13 +422,9 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
   // all chunks of a block carry the same tag) and has its own workspace, reduction buffers and template cache.
   const int GT = CT / a.ng, cgrp = tid / GT, gt = tid - cgrp * GT;
   double *ws = ws_all + cgrp * a.ws_dbl;
-  double *red = red_all + cgrp * 2 * GT * M;
   uint16_t *tb = tb_all + cgrp * a.tmpl_dbl * 4;
   auto gsync = [&] { asm volatile("bar.sync %0, %1;\n" ::"r"(cgrp + 1), "r"(GT) : "memory"); };
-  double acc[M], pass[M];
-  int out_dof = -1, cur_tmpl = -1, nlast = 0;
-#pragma unroll
-  for (int j = 0; j < M; ++j) acc[j] = pass[j] = 0.0;
+  int cur_tmpl = -1;
 
   long long G = 0;
   for (int step = 0; step < a.n_steps; ++step) {
@@ -437,138 +445,200 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 2 : (CT >= 128 ? 4 : 6))
         const long long t = clock64();
         a.prof[cta * 24 + 7] += t_w - t_entry;  // waiting for the dependency warp
         a.prof[cta * 24 + 16 + kind] += t_w - t_entry;
-        if (t_w - t_entry > 2000) a.prof[cta * 24 + 20 + kind] += 1;
         a.prof[cta * 24 + 5] += t - t_w;        // waiting for TMA data
       }
       long long t_mark = (a.prof && tid == 0) ? clock64() : 0;
 
       if (kind == SW_TOP_FWD || kind == SW_TOP_BWD) {
         // ---------------------------------------------------------------------------------------------------------
-        // column block of a top-level front
+        // wave: gather | micro-tiles (one warp each) | reduction of the row parts + output
         // ---------------------------------------------------------------------------------------------------------
         const bool fwd = kind == SW_TOP_FWD;
-        const int s = e.a4, b = e.a5;
-        const int cw = e.a1, col0 = e.a0;  // cw: power of two below 32, any even width from 32 to 256
-        const int *gl = reinterpret_cast<const int *>(reg);
-        const int *cl = reinterpret_cast<const int *>(reg + e.n[0]);
-        const double *tile = reg + e.n[0] + e.n[1];
-        const int r_beg = e.a2, r_end = e.a3;
-        if (flags & SWF_NEW_RUN) {
-          gsync();  // every warp is done with the previous vector
-          if (fwd) {
-            // rows [r_beg, r_end) of v = rhs of the separator dofs + children contributions (assemble_rhs_star
-            // fused: rhs = -K_up p_old)
-            const double k0 = e.a6 ? a.ky0 : a.kx0, k1 = e.a6 ? a.ky1 : a.kx1;
-            for (int p = r_beg + gt; p < r_end; p += GT) {
-              const int4 gi = reinterpret_cast<const int4 *>(gl)[p - r_beg];
-              double val[M];
+        const int n_rows = e.a0, n_mt = e.a1, n_cols = e.a2;
+        const int32_t *ix = reinterpret_cast<const int32_t *>(reg);
+        const double *tiles = reg + e.n[0];
+        double *scratch = const_cast<double *>(reg) + e.n[0] + e.n[1];
+        double *wsv = (flags & SWF_ROWS_WS) ? ws : scratch;         // [n_rows][M]
+        double *passv = (flags & SWF_ROWS_WS) ? scratch : scratch + n_rows * M;  // [n_cols][M], forward only
+        double *part = passv + (fwd ? n_cols * M : 0);              // [partial slots][M]
+        const int4 *colA = reinterpret_cast<const int4 *>(ix + e.a6);
+        gsync();  // global writes of this CTA's earlier entries are visible to all its threads
+        SWEEP_PROF(20)
+        if (fwd) {
+          // rows of v = rhs of the separator dofs (assemble_rhs_star fused: -K_up p_old) + children's contributions
+          const int4 *rows = reinterpret_cast<const int4 *>(ix + e.a4);
+          const int32_t *zsd = ix + e.o0;
+          const int32_t *colB = ix + e.o3;
+          constexpr int RB = 2;  // rows per thread in flight
+          for (int r0 = gt; r0 < n_rows && !(flags & SWF_REUSE); r0 += RB * GT) {
+            int4 gi[RB];
+            double pa[RB][M], pb[RB][M], za[RB][M], zb[RB][M];
 #pragma unroll
-              for (int j = 0; j < M; ++j)
-                val[j] = -(k0 * __ldcg(a.ptil + int64_t(gi.x) * M + j) + k1 * __ldcg(a.ptil + int64_t(gi.y) * M + j));
-              if (gi.z >= 0)
-#pragma unroll
-                for (int j = 0; j < M; ++j) val[j] += __ldcg(a.z + int64_t(gi.z) * M + j);
-              if (gi.w >= 0)
-#pragma unroll
-                for (int j = 0; j < M; ++j) val[j] += __ldcg(a.z + int64_t(gi.w) * M + j);
-#pragma unroll
-              for (int j = 0; j < M; ++j) ws[(p - r_beg) * M + j] = val[j];
-              if (flags & SWF_WRITE_ZS)
-#pragma unroll
-                for (int j = 0; j < M; ++j) a.z[int64_t(e.o2 + p) * M + j] = val[j];
+            for (int u = 0; u < RB; ++u) {
+              const int r = r0 + u * GT;
+              gi[u] = r < n_rows ? rows[r] : make_int4(0, 0, -1, -1);
             }
-          } else {
-            // rows [r_beg, r_end) of w = [accumulated separator rhs ; solution of the boundary dofs]
-            for (int p = r_beg + gt; p < r_end; p += GT) {
-              if (p < s) {
 #pragma unroll
-                for (int j = 0; j < M; ++j) ws[(p - r_beg) * M + j] = __ldcg(a.z + int64_t(e.o2 + p) * M + j);
-              } else {
-                const int64_t d = gl[p - r_beg];
+            for (int u = 0; u < RB; ++u) {
+              ld_vec<M>(a.ptil + int64_t(gi[u].x & 0x3fffffff) * M, pa[u]);
+              ld_vec<M>(a.ptil + int64_t(gi[u].y) * M, pb[u]);
+              if (gi[u].z >= 0) ld_vec<M>(a.z + int64_t(gi[u].z) * M, za[u]);
+              if (gi[u].w >= 0) ld_vec<M>(a.z + int64_t(gi[u].w) * M, zb[u]);
+            }
 #pragma unroll
-                for (int j = 0; j < M; ++j) ws[(p - r_beg) * M + j] = __ldcg(a.x + d * M + j);
+            for (int u = 0; u < RB; ++u) {
+              const int r = r0 + u * GT;
+              if (r < n_rows) {
+                const bool ty = (gi[u].x >> 30) & 1;
+                const double k0 = ty ? a.ky0 : a.kx0, k1 = ty ? a.ky1 : a.kx1;
+                const int zd = zsd[r];
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                  double val = -(k0 * pa[u][j] + k1 * pb[u][j]);
+                  if (gi[u].z >= 0) val += za[u][j];
+                  if (gi[u].w >= 0) val += zb[u][j];
+                  wsv[r * M + j] = val;
+                  if (zd >= 0) a.z[int64_t(zd) * M + j] = val;
+                }
               }
             }
           }
-          gsync();
-          SWEEP_PROF(14)
-        }
-        if (flags & SWF_FIRST) {
+          // pass-through of the children's contributions to the boundary dofs of this wave's columns
+          for (int o = gt; o < n_cols; o += GT) {
+            const int c0 = colA[o].w, c1 = colB[o];
+            double p0[M], p1[M];
+            if (c0 >= 0) ld_vec<M>(a.z + int64_t(c0) * M, p0);
+            if (c1 >= 0) ld_vec<M>(a.z + int64_t(c1) * M, p1);
 #pragma unroll
-          for (int j = 0; j < M; ++j) acc[j] = pass[j] = 0.0;
-          out_dof = -1;
-          if (gt < cw && e.n[1] > 0) {
-            const int2 ci = reinterpret_cast<const int2 *>(cl)[gt];
-            if (fwd) {  // pass-through of the children's contributions to this boundary dof
-              if (ci.x >= 0)
+            for (int j = 0; j < M; ++j) passv[o * M + j] = (c0 >= 0 ? p0[j] : 0.0) + (c1 >= 0 ? p1[j] : 0.0);
+          }
+        } else {
+          // rows of w = [accumulated separator rhs ; solution of the boundary dofs]
+          const int32_t *rows = ix + e.a4;
+          constexpr int RB = 4;
+          for (int r0 = gt; r0 < n_rows && !(flags & SWF_REUSE); r0 += RB * GT) {
+            double v[RB][M];
 #pragma unroll
-                for (int j = 0; j < M; ++j) pass[j] += __ldcg(a.z + int64_t(ci.x) * M + j);
-              if (ci.y >= 0)
+            for (int u = 0; u < RB; ++u) {
+              const int r = r0 + u * GT;
+              if (r < n_rows) {
+                const int32_t d = rows[r];
+                const double *src = d < 0 ? a.z + int64_t(d & 0x7fffffff) * M : a.x + int64_t(d) * M;
+                ld_vec<M>(src, v[u]);
+              }
+            }
 #pragma unroll
-                for (int j = 0; j < M; ++j) pass[j] += __ldcg(a.z + int64_t(ci.y) * M + j);
-            } else {
-              out_dof = ci.x;
+            for (int u = 0; u < RB; ++u) {
+              const int r = r0 + u * GT;
+              if (r < n_rows)
+#pragma unroll
+                for (int j = 0; j < M; ++j) wsv[r * M + j] = v[u][j];
             }
           }
         }
-        if (e.n[2] > 0) {
-          const int g = gt / cw, col = gt - g * cw, gn = GT / cw;
-          if (g < gn) {
-            const double *tl = tile + col;
-            const int nr = r_end - r_beg;
-            int r = g;
-            for (; r + 3 * gn < nr; r += 4 * gn) {
-              const double m0 = tl[r * cw], m1 = tl[(r + gn) * cw];
-              const double m2 = tl[(r + 2 * gn) * cw], m3 = tl[(r + 3 * gn) * cw];
+        gsync();
+        SWEEP_PROF(14)
+        {
+          const SweepMt *mts = reinterpret_cast<const SweepMt *>(ix + e.a5);
+          const int wig = gt >> 5, nw = GT >> 5;
+          for (int m = wig; m < n_mt; m += nw) {
+            const int4 md = *reinterpret_cast<const int4 *>(&mts[m]);  // tile_off, row0, nrows, ncols
+            const int part_off = mts[m].part_off;
+            const int nrows = md.z, ncols = md.w;
+            const double *vp = wsv + md.y * M;
+            if (ncols == 1) {
+              const double *tp = tiles + md.x;
+              double acc[M];
+#pragma unroll
+              for (int j = 0; j < M; ++j) acc[j] = 0.0;
+              for (int r = lane; r < nrows; r += 32) {
+                const double t = tp[r];
+#pragma unroll
+                for (int j = 0; j < M; ++j) acc[j] += t * vp[r * M + j];
+              }
+#pragma unroll
+              for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+                for (int j = 0; j < M; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+              if (lane == 0)
+#pragma unroll
+                for (int j = 0; j < M; ++j) part[part_off * M + j] = acc[j];
+            } else {
+              const int cp = ncols >> 1;                  // lanes per row: each owns two adjacent columns
+              const int rg = 32 / cp;                     // rows in flight per warp instruction
+              const int my_cp = lane & (cp - 1), my_rg = lane / cp;
+              const double *tp = tiles + md.x + 2 * my_cp;
+              double a0[M], a1[M], b0[M], b1[M];
+#pragma unroll
+              for (int j = 0; j < M; ++j) a0[j] = a1[j] = b0[j] = b1[j] = 0.0;
+              int r = my_rg;
+              for (; r + rg < nrows; r += 2 * rg) {
+                const double2 t0 = *reinterpret_cast<const double2 *>(tp + r * ncols);
+                const double2 t1 = *reinterpret_cast<const double2 *>(tp + (r + rg) * ncols);
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                  const double v0 = vp[r * M + j], v1 = vp[(r + rg) * M + j];
+                  a0[j] += t0.x * v0;
+                  a1[j] += t0.y * v0;
+                  b0[j] += t1.x * v1;
+                  b1[j] += t1.y * v1;
+                }
+              }
+              if (r < nrows) {
+                const double2 t0 = *reinterpret_cast<const double2 *>(tp + r * ncols);
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                  const double v0 = vp[r * M + j];
+                  a0[j] += t0.x * v0;
+                  a1[j] += t0.y * v0;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < M; ++j) { a0[j] += b0[j]; a1[j] += b1[j]; }
+              for (int off = cp; off < 32; off <<= 1)
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                  a0[j] += __shfl_xor_sync(0xffffffffu, a0[j], off);
+                  a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], off);
+                }
+              if (my_rg == 0)
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                  part[(part_off + 2 * my_cp) * M + j] = a0[j];
+                  part[(part_off + 2 * my_cp + 1) * M + j] = a1[j];
+                }
+            }
+          }
+        }
+        SWEEP_PROF(21)
+        gsync();
+        SWEEP_PROF(22)
+        // outputs: the row parts of every column are added in a fixed order
+        for (int o = gt; o < n_cols; o += GT) {
+          const int4 ca = colA[o];
+          const int np = ca.y & 0xFFFF, stride = ca.y >> 16;
+          double tot[M];
+#pragma unroll
+          for (int j = 0; j < M; ++j) tot[j] = part[ca.x * M + j];
+          for (int q = 1; q < np; ++q)
+#pragma unroll
+            for (int j = 0; j < M; ++j) tot[j] += part[(ca.x + q * stride) * M + j];
+          if (fwd) {
+#pragma unroll
+            for (int j = 0; j < M; ++j) a.z[int64_t(ca.z) * M + j] = tot[j] + passv[o * M + j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < M; ++j) a.x[int64_t(ca.z) * M + j] = tot[j];
+            if (a.hist)
 #pragma unroll
               for (int j = 0; j < M; ++j)
-                acc[j] += m0 * ws[r * M + j] + m1 * ws[(r + gn) * M + j] + m2 * ws[(r + 2 * gn) * M + j] +
-                          m3 * ws[(r + 3 * gn) * M + j];
-            }
-            for (; r < nr; r += gn) {
-              const double m0 = tl[r * cw];
-#pragma unroll
-              for (int j = 0; j < M; ++j) acc[j] += m0 * ws[r * M + j];
-            }
+                if (a.hist[j]) {
+                  double *hp = a.hist[j] + int64_t(level) * a.hist_stride + ca.z;
+                  *hp = a.hist_add ? *hp + tot[j] : tot[j];
+                }
           }
         }
-        if (flags & SWF_LAST) {
-          if (cw < 32)
-            for (int off = 16; off >= cw; off >>= 1)
-#pragma unroll
-              for (int j = 0; j < M; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
-          double *rb = red + (nlast & 1) * GT * M;  // double buffered: one barrier per block is enough
-          ++nlast;
-#pragma unroll
-          for (int j = 0; j < M; ++j) rb[gt * M + j] = acc[j];
-          gsync();
-          if (gt < cw) {
-            const int stride = cw < 32 ? 32 : cw;
-            double tot[M];
-#pragma unroll
-            for (int j = 0; j < M; ++j) tot[j] = 0.0;
-            for (int t = gt; t < GT; t += stride)
-#pragma unroll
-              for (int j = 0; j < M; ++j) tot[j] += rb[t * M + j];
-            if (fwd) {
-              const int q = col0 + gt;
-              if (q < b)
-#pragma unroll
-                for (int j = 0; j < M; ++j) a.z[int64_t(e.o3 + q) * M + j] = tot[j] + pass[j];
-            } else if (out_dof >= 0) {
-#pragma unroll
-              for (int j = 0; j < M; ++j) a.x[int64_t(out_dof) * M + j] = tot[j];
-              if (a.hist)
-#pragma unroll
-                for (int j = 0; j < M; ++j)
-                  if (a.hist[j]) {
-                    double *hp = a.hist[j] + int64_t(level) * a.hist_stride + out_dof;
-                    *hp = a.hist_add ? *hp + tot[j] : tot[j];
-                  }
-            }
-          }
-        }
-        SWEEP_PROF(15)
+        SWEEP_PROF(23)
       } else {
         // ---------------------------------------------------------------------------------------------------------
         // subtree: factor blob, index lists and this CTA's own vectors are in the ring; walk the levels on chip
@@ -806,7 +876,7 @@ size_t sweep_smem_optin() {
   return size_t(optin);
 }
 
-int sweep_fixed_dbl(int M, int ct) { return 19 * SWEEP_NBAR + SWEEP_GTAB_DBL + 2 * ct * M; }
+int sweep_fixed_dbl(int, int) { return 19 * SWEEP_NBAR + SWEEP_GTAB_DBL; }
 
 template <int M, int CT>
 static int ctas_per_sm_t(size_t smem) {

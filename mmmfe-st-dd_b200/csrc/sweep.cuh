@@ -32,31 +32,57 @@ constexpr int SWEEP_GTAB_DBL = 128;                // shared-memory doubles of t
 constexpr int SWEEP_MAX_ENTRIES = 8 * SWEEP_GTAB_DBL - 8;  // entries per CTA and step the group table can hold
 
 enum SweepKind : int32_t { SW_SUB_FWD = 0, SW_TOP_FWD = 1, SW_TOP_BWD = 2, SW_SUB_BWD = 3 };
-enum SweepFlag : int32_t { SWF_FIRST = 1, SWF_LAST = 2, SWF_NEW_RUN = 4, SWF_WRITE_ZS = 8 };
+// SWF_ROWS_WS: the gathered rows of a wave live in the group's workspace (not in the ring scratch); SWF_REUSE: the
+// previous wave of this CTA gathered exactly these rows and left them there
+enum SweepFlag : int32_t { SWF_FIRST = 1, SWF_LAST = 2, SWF_ROWS_WS = 4, SWF_REUSE = 8 };
 enum SweepSrc : int32_t { SRC_FACTOR = 0, SRC_INDEX = 1, SRC_XI = 2, SRC_PTIL = 3 };
 
-// One unit of work of one CTA (128 bytes).  The ring region of an entry holds its segments back to back
-// (n[0..3] doubles each).
-//   top entries (column block [col0, col0 + cw) of a front, tile rows [r_beg, r_end)):
-//     a0 col0, a1 cw, a2 r_beg, a3 r_end, a4 s, a5 b, a6 separator type (0 x-edges, 1 y-edges), o2 zs_off, o3 zc_off
-//     segments: 0 gather list of the chunk's rows (unless the previous entry staged the same rows), 1 column list
-//     (first chunk of a block), 2 tile
-//       FWD tile = -G^T (s x b), reduces over the s separator rows; gather list int4 {cell A, cell B, child-0 z,
-//       child-1 z} per separator row; column list int2 {child-0 z, child-1 z} per boundary column
-//       BWD tile = [F11^-1 ; -G] ((s+b) x s); gather list int {x dof} per row (separator rows unused); column list
-//       int2 {dof, -}
+// One unit of work of one CTA (128 bytes).  The ring region of an entry holds its streamed segments back to back
+// (n[0..3] doubles each; a segment that the TMA issuer does not copy -- SweepIssue::n = 0 -- is scratch space).
+//
+//   WAVES (SW_TOP_FWD / SW_TOP_BWD): everything ONE CTA does for one tree level and direction within a shared-memory
+//   budget: pieces (column ranges, all rows) of one or more top fronts, cut into MICRO-TILES of nrows x ncols doubles
+//   (ncols = 2..64, a power of two; stored row-major and contiguous) that single warps multiply independently.
+//     segment 0 (index array): row records, column records, micro-tile descriptors
+//     segment 1 (factor):      the micro-tiles
+//     segment 2 (scratch):     gathered vector rows [n_rows][M] (unless SWF_ROWS_WS), pass-through [n_cols][M]
+//                              (forward), partial sums
+//     a0 n_rows, a1 n_mt, a2 n_cols, a3 partial slots, a4 rows, a5 micro-tiles, a6 column records A, o3 column
+//     records B (forward), o0 zs destinations (forward)   (offsets in int32 units from the start of segment 0),
+//     a7 tree height
+//     phases: gather (rows and pass-through from L2) | micro-tiles (one warp each, partial sums to shared memory) |
+//     reduction of the row parts in a fixed order + output.
+//       FWD  row record int4 {cell A | sep-type << 30, cell B, child-0 z, child-1 z} (+ zs destination or -1):
+//            v = -(K_up p_old) + children (assemble_rhs_star fused); column record A {partial slot, parts | stride
+//            << 16, z destination, child-0 z}, B {child-1 z};  micro-tile of -G^T (rows: separator, columns: boundary)
+//       BWD  row record int {x dof, or 1 << 31 | z index for the separator rows}; column record A {slot, parts |
+//            stride << 16, x dof, -}; micro-tile of [F11^-1 ; -G] (rows: separator + boundary, columns: separator)
 //   subtree entries: a0 template, a1 boundary-entry table offset (-1: none), a2 I0, a3 J0, a7 instance,
 //     o0 zc_off (root boundary contributions), o1 xi_off, o2 ptil offset of the box (box-major cell order)
 //     segments: 0 factor blob, 1 root-boundary x dofs (BWD), 2 interior right-hand sides xi (BWD), 3 box pressures
+//
+// Completion: sig >= 0: one counter (subtrees); n_sig > 0: the counters index[sig_off ...] (waves: one per front).
+// Dependencies: dep[t] = counter | count << 21; satisfied when counter >= (step + 1) * count.
+constexpr int SWEEP_MAX_DEPS = 8;
+constexpr int SWEEP_DEP_SHIFT = 21;
 struct alignas(16) SweepEntry {
   int32_t kind, flags, ring_off, issue_upto;
-  int32_t sig, dep0, dep0_n, dep1;  // sig: counter bumped on completion; dep: counter >= (step+1) * dep_n
-  int32_t dep1_n, a0, a1, a2;
-  int32_t a3, a4, a5, a6;
-  int32_t a7, o0, o1, o2;
-  int32_t o3, n[SWEEP_SEGS], pad[7];
+  int32_t sig, n_sig, sig_off, n_dep;
+  int32_t dep[SWEEP_MAX_DEPS];
+  int32_t a0, a1, a2, a3;
+  int32_t a4, a5, a6, a7;
+  int32_t o0, o1, o2, o3;
+  int32_t n[SWEEP_SEGS];
 };
 static_assert(sizeof(SweepEntry) == 128, "SweepEntry must be 128 bytes");
+
+struct alignas(16) SweepMt {  // micro-tile descriptor (32 bytes)
+  int32_t tile_off;           // doubles from the start of segment 1
+  int32_t row0, nrows;        // rows [row0, row0 + nrows) of the wave's gathered vector
+  int32_t ncols;              // 2, 4, ..., 64
+  int32_t part_off;           // first partial slot
+  int32_t pad[3];
+};
 
 struct alignas(16) SweepIssue {  // what the TMA issuer needs of an entry
   int64_t off[SWEEP_SEGS];       // in doubles, relative to the base of the source
@@ -108,6 +134,7 @@ struct SweepArgs {
   int32_t tmpl_dbl, ws_dbl, ring_dbl;  // shared-memory partition in doubles (template and workspace: per group)
   int32_t evict_first;
   uint32_t spin_ns;             // back-off of the service warps' polling loops
+  int32_t poll_window;          // entries ahead of the oldest unopened one that poll the completion counters
 };
 
 // One block of the sweep layout: dst[r * cw + c] = value(r, col0 + c) (0 beyond ncols), r < rlen.

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -126,11 +127,14 @@ const char *pack_template(const SubtreeTemplate &T, int32_t ct, std::vector<uint
 
 const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx_user,
                                const std::vector<int32_t> &dof_of_canon, int32_t n_cta, int32_t chunk_dbl, int32_t ct,
-                               SweepLayout &L) {
+                               SweepLayout &L, int32_t ng, int32_t mt_dbl) {
   L = SweepLayout();
   L.n_cta = n_cta;
   L.chunk_dbl = chunk_dbl;
   L.ct = ct;
+  L.ng = std::max(1, ng);
+  L.mt_dbl = std::max(64, mt_dbl);
+  if (const char *env = std::getenv("MMMFE_SWEEP_WS_ROWS")) L.ws_rows = std::atoi(env);
   const int32_t nn = int32_t(tr.nodes.size());
   if (tr.instances.empty()) return "no subtrees (subtree_cells = 0)";
   if (tr.idx.size() >= (size_t(1) << 30) || tr.src.size() >= (size_t(1) << 31)) return "index structure beyond 32 bits";
@@ -214,97 +218,254 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
   }
   if (L.z_total >= (int64_t(1) << 29)) return "vector storage beyond 32 bits";
 
-  // ---- top items: column blocks, sized per level so that every CTA gets work; static index lists ----
+  // ---- subtrees -> CTAs: interior and boundary subtrees are dealt out separately so that every CTA gets its share
+  // of both ----
+  const int32_t n_inst = int32_t(tr.instances.size());
+  L.cta_of_inst.assign(n_inst, 0);
+  {
+    std::vector<int32_t> interior, boundary;
+    for (int32_t k = 0; k < n_inst; ++k) (tr.templates[tr.instances[k].tmpl].flags == 0 ? interior : boundary).push_back(k);
+    for (size_t t = 0; t < interior.size(); ++t) L.cta_of_inst[interior[t]] = int32_t(int64_t(t) * n_cta / int64_t(interior.size()));
+    for (size_t t = 0; t < boundary.size(); ++t)
+      L.cta_of_inst[boundary[t]] = n_cta - 1 - int32_t(int64_t(t) * n_cta / int64_t(boundary.size()));
+  }
+  // producers of every completion counter (2 * node: forward, 2 * node + 1: backward): the CTA when it is a single
+  // one.  A consumer that runs later on the same CTA needs no counter (one compute group: program order + barrier).
+  std::vector<int32_t> prod_cta(2 * L.nodes.size(), -1);  // -1 none yet, -2 several CTAs
+  auto add_producer = [&](int32_t counter, int32_t cta) {
+    int32_t &p = prod_cta[counter];
+    p = (p == -1 || p == cta) ? cta : -2;
+  };
+  for (int32_t k = 0; k < n_inst; ++k) add_producer(2 * (L.n_top + k), L.cta_of_inst[k]);
+
+  // ---- waves: per level and direction, the level's tile doubles are cut into n_cta contiguous shares (whole small
+  // fronts, column ranges of large ones); a CTA's share is packed into waves of at most chunk_dbl tile doubles ----
   const size_t nh = tr.top_by_height.size();
   L.fwd.assign(nh, {});
   L.bwd.assign(nh, {});
   int64_t rs = 0;
-  for (size_t h = 0; h < nh; ++h) {
-    int64_t fdbl = 0, bdbl = 0;
-    for (int32_t id : tr.top_by_height[h]) {
+  struct Piece { int32_t node, c0, nc; };
+  auto plan_level = [&](size_t h, int pass) -> const char * {
+    auto &waves = pass == 0 ? L.fwd[h] : L.bwd[h];
+    const auto &ids = tr.top_by_height[h];
+    double level_dbl = 0;
+    for (int32_t id : ids) {
       const NdNode &n = tr.nodes[id];
-      fdbl += int64_t(n.s) * n.b;
-      bdbl += int64_t(n.s) * (n.s + n.b);
+      level_dbl += pass == 0 ? double(n.s) * n.b : double(n.s) * (n.s + n.b);
     }
-    for (int pass = 0; pass < 2; ++pass) {
-      const int64_t level_dbl = pass == 0 ? fdbl : bdbl;
-      const int64_t target = std::min<int64_t>(chunk_dbl, std::max<int64_t>(256, level_dbl / std::max(1, n_cta)));
-      for (int32_t id : tr.top_by_height[h]) {
-        const NdNode &n = tr.nodes[id];
-        SweepNodeH &sn = L.nodes[sid[id]];
-        const int32_t rlen = pass == 0 ? n.s : n.s + n.b;
-        const int32_t ncols = pass == 0 ? n.b : n.s;
-        const int32_t f = n.s + n.b;
-        auto &items = pass == 0 ? L.fwd[h] : L.bwd[h];
-        auto child_z = [&](int c, int32_t p) -> int32_t {
-          if (sn.child[c] < 0) return -1;
-          const int32_t q = tr.src[n.src_off + int64_t(c) * f + p];
-          return q < 0 ? -1 : L.nodes[sn.child[c]].zc_off + q;
-        };
-        if (pass == 0) {  // gather list of the run: cells of the separator edges and the children's contributions
-          sn.gl_f = int64_t(L.index.size());
-          for (int32_t p = 0; p < n.s; ++p) {
-            const int64_t v = tr.idx[n.idx_off + p];
-            int32_t c0, c1;
-            if (v < nxe) {
-              const int32_t j = int32_t(v / (tr.nx + 1)), i = int32_t(v % (tr.nx + 1));
-              if (i <= 0 || i >= tr.nx) return "separator edge on the domain boundary";
-              c0 = j * tr.nx + i - 1; c1 = j * tr.nx + i;
+    const double share = std::max(1.0, level_dbl / n_cta);
+    std::vector<std::vector<Piece>> pieces(n_cta);
+    double cum = 0;
+    for (int32_t id : ids) {
+      const NdNode &n = tr.nodes[id];
+      const int32_t rlen = pass == 0 ? n.s : n.s + n.b, ncols = pass == 0 ? n.b : n.s;
+      const double dbl = double(rlen) * ncols;
+      auto cta_at = [&](double pos) { return std::max(0, std::min(n_cta - 1, int32_t(pos / share))); };
+      if (ncols == 0) {  // root, forward: rows only (accumulates and stores the separator right-hand side)
+        pieces[cta_at(cum)].push_back({sid[id], 0, 0});
+      } else if (dbl <= 0.75 * share || ncols <= 4) {
+        pieces[cta_at(cum + 0.5 * dbl)].push_back({sid[id], 0, ncols});
+      } else {
+        int32_t c = 0, k = cta_at(cum + 0.5 * rlen);
+        while (c < ncols) {
+          const double pos = cum + double(c) * rlen;
+          int32_t take = int32_t(((k + 1) * share - pos) / rlen + 0.5);
+          take = std::max(take, 1);
+          if (k == n_cta - 1 || ncols - (c + take) < 2) take = ncols - c;
+          take = std::min(take, ncols - c);
+          pieces[k].push_back({sid[id], c, take});
+          c += take;
+          k = std::min(k + 1, n_cta - 1);
+        }
+      }
+      cum += dbl;
+    }
+    for (int32_t cta = 0; cta < n_cta; ++cta) {
+      if (pieces[cta].empty()) continue;
+      // strips of every piece: widths 64, then the binary digits of the rest; never more than chunk_dbl doubles
+      struct Strip { int32_t node, c0, w, parts; };
+      std::vector<Strip> strips;
+      for (const Piece &pc : pieces[cta]) {
+        const SweepNodeH &sn = L.nodes[pc.node];
+        const int32_t rlen = pass == 0 ? sn.s : sn.s + sn.b;
+        if (pc.nc == 0) { strips.push_back({pc.node, 0, 0, 0}); continue; }
+        const int32_t wmax = std::max(1, std::min(64, pow2_floor(std::max<int64_t>(1, L.chunk_dbl / std::max(1, rlen)))));
+        int32_t c = pc.c0, left = pc.nc;
+        while (left > 0) {
+          const int32_t w = std::min(wmax, pow2_floor(left));
+          const int32_t parts = std::max(1, std::min(rlen, int32_t((int64_t(rlen) * w + L.mt_dbl / 2) / L.mt_dbl)));
+          strips.push_back({pc.node, c, w, parts});
+          c += w; left -= w;
+        }
+      }
+      size_t i = 0;
+      std::vector<int32_t> prev_fronts;
+      while (i < strips.size()) {
+        SweepWaveH W;
+        W.kind = pass == 0 ? SW_TOP_FWD : SW_TOP_BWD; W.cta = cta; W.height = int32_t(h);
+        std::vector<int32_t> row0_of;      // per front of the wave: first row in the gathered vector
+        std::vector<int32_t> rows, zsd, colA, colB;
+        std::vector<SweepMt> mts;
+        std::vector<RepackDesc> reps;
+        int64_t tile = 0;
+        for (; i < strips.size(); ++i) {
+          const Strip &sp = strips[i];
+          const SweepNodeH &sn = L.nodes[sp.node];
+          const NdNode &n = tr.nodes[sn.old_id];
+          const int32_t rlen = pass == 0 ? sn.s : sn.s + sn.b, ncols = pass == 0 ? sn.b : sn.s, f = sn.s + sn.b;
+          auto child_z = [&](int c, int32_t p) -> int32_t {
+            if (sn.child[c] < 0) return -1;
+            const int32_t q = tr.src[n.src_off + int64_t(c) * f + p];
+            return q < 0 ? -1 : L.nodes[sn.child[c]].zc_off + q;
+          };
+          int64_t sdbl = 0;
+          for (int32_t q = 0; q < sp.parts; ++q) {
+            const int32_t r0 = int32_t(int64_t(rlen) * q / sp.parts), r1 = int32_t(int64_t(rlen) * (q + 1) / sp.parts);
+            sdbl += even(int64_t(r1 - r0) * sp.w);
+          }
+          auto it = std::find(W.fronts.begin(), W.fronts.end(), sp.node);
+          const bool new_front = it == W.fronts.end();
+          // dependencies the new front would add
+          std::vector<int32_t> nd;
+          if (new_front) {
+            auto want = [&](int32_t counter, int32_t count) {
+              if (L.ng == 1 && prod_cta[counter] == cta) return;
+              const int32_t packed = counter | (count << SWEEP_DEP_SHIFT);
+              if (std::find(W.deps.begin(), W.deps.end(), packed) == W.deps.end() &&
+                  std::find(nd.begin(), nd.end(), packed) == nd.end()) nd.push_back(packed);
+            };
+            if (pass == 0) {
+              for (int c = 0; c < 2; ++c)
+                if (sn.child[c] >= 0) want(2 * sn.child[c], L.nodes[sn.child[c]].n_fwd);
+            } else if (sn.parent >= 0) want(2 * sn.parent + 1, L.nodes[sn.parent].n_bwd);
+            else want(2 * sp.node, sn.n_fwd);
+          }
+          if (!W.fronts.empty() && (tile + sdbl > L.chunk_dbl || W.deps.size() + nd.size() > size_t(SWEEP_MAX_DEPS))) break;
+          if (nd.size() > size_t(SWEEP_MAX_DEPS)) return "a front has more dependencies than an entry can hold";
+          int32_t fi;
+          if (new_front) {
+            fi = int32_t(W.fronts.size());
+            W.fronts.push_back(sp.node);
+            W.deps.insert(W.deps.end(), nd.begin(), nd.end());
+            row0_of.push_back(int32_t(pass == 0 ? rows.size() / 4 : rows.size()));
+            if (pass == 0) {
+              // the wave that holds column 0 of the front (or its only, column-less piece) stores the accumulated
+              // separator right-hand side for the backward pass
+              const bool writes_zs = sp.c0 == 0;
+              for (int32_t p = 0; p < sn.s; ++p) {
+                const int64_t v = tr.idx[n.idx_off + p];
+                int32_t c0, c1;
+                if (v < nxe) {
+                  const int32_t j = int32_t(v / (tr.nx + 1)), ii = int32_t(v % (tr.nx + 1));
+                  if (ii <= 0 || ii >= tr.nx) return "separator edge on the domain boundary";
+                  c0 = j * tr.nx + ii - 1; c1 = j * tr.nx + ii;
+                } else {
+                  const int64_t k = v - nxe;
+                  const int32_t j = int32_t(k / tr.nx), ii = int32_t(k % tr.nx);
+                  if (j <= 0 || j >= tr.ny) return "separator edge on the domain boundary";
+                  c0 = (j - 1) * tr.nx + ii; c1 = j * tr.nx + ii;
+                }
+                rows.push_back(L.cell_box[c0] | (sn.sep_type << 30)); rows.push_back(L.cell_box[c1]);
+                rows.push_back(child_z(0, p)); rows.push_back(child_z(1, p));
+                zsd.push_back(writes_zs ? sn.zs_off + p : -1);
+              }
             } else {
-              const int64_t k = v - nxe;
-              const int32_t j = int32_t(k / tr.nx), i = int32_t(k % tr.nx);
-              if (j <= 0 || j >= tr.ny) return "separator edge on the domain boundary";
-              c0 = (j - 1) * tr.nx + i; c1 = j * tr.nx + i;
+              for (int32_t q = 0; q < f; ++q) rows.push_back(q < sn.s ? int32_t(0x80000000u | uint32_t(sn.zs_off + q)) : idx_user[n.idx_off + q]);
             }
-            L.index.push_back(L.cell_box[c0]); L.index.push_back(L.cell_box[c1]);
-            L.index.push_back(child_z(0, p)); L.index.push_back(child_z(1, p));
-          }
-        } else {
-          sn.gl_b = int64_t(L.index.size());  // one entry per tile row; separator rows come from z_s, no index
-          for (int32_t q = 0; q < f; ++q) L.index.push_back(q < n.s ? -1 : idx_user[n.idx_off + q]);
-          while (L.index.size() % 4) L.index.push_back(0);
-        }
-        if (ncols == 0) {  // root: forward entry that only accumulates the separator right-hand side
-          items.push_back({SW_TOP_FWD, sid[id], 0, 2, 0, 0});
-          sn.n_fwd = 1;
-          sn.cl_f = int64_t(L.index.size());
-          continue;
-        }
-        // block width: a power of two below 32 (shuffle reduction), else any even width up to 256 with at most
-        // one padded column per block
-        const int64_t cap = std::max<int64_t>(2, std::min<int64_t>(std::min(256, ct), target / rlen));
-        int32_t cw;
-        if (cap >= ncols) cw = ncols >= 32 ? even(ncols) : std::max(2, pow2_ceil(ncols));
-        else if (cap >= 32) { const int32_t nb = int32_t((ncols + cap - 1) / cap); cw = even((ncols + nb - 1) / nb); }
-        else cw = pow2_floor(cap);
-        const int32_t nblk = (ncols + cw - 1) / cw;
-        // column list, padded to whole blocks
-        (pass == 0 ? sn.cl_f : sn.cl_b) = int64_t(L.index.size());
-        (pass == 0 ? sn.cl_f_len : sn.cl_b_len) = nblk * cw;
-        for (int32_t c = 0; c < nblk * cw; ++c) {
-          if (pass == 0) {
-            L.index.push_back(c < ncols ? child_z(0, n.s + c) : -1);
-            L.index.push_back(c < ncols ? child_z(1, n.s + c) : -1);
           } else {
-            L.index.push_back(c < ncols ? idx_user[n.idx_off + c] : -1);
-            L.index.push_back(0);
+            fi = int32_t(it - W.fronts.begin());
+          }
+          if (sp.w == 0) continue;  // rows only
+          const int32_t part0 = W.n_parts;
+          for (int32_t q = 0; q < sp.parts; ++q) {
+            const int32_t r0 = int32_t(int64_t(rlen) * q / sp.parts), r1 = int32_t(int64_t(rlen) * (q + 1) / sp.parts);
+            SweepMt m;
+            std::memset(&m, 0, sizeof m);
+            m.tile_off = int32_t(tile); m.row0 = row0_of[fi] + r0; m.nrows = r1 - r0; m.ncols = sp.w;
+            m.part_off = W.n_parts;
+            mts.push_back(m);
+            RepackDesc d;
+            d.dst = tile;  // relative to the wave; rebased below
+            d.src = pass == 0 ? n.rf_off + int64_t(r0) * n.ldf : n.rb_off + r0;
+            d.ld = pass == 0 ? n.ldf : n.ldr;
+            d.rlen = r1 - r0; d.col0 = sp.c0; d.cw = sp.w; d.ncols = ncols; d.mode = pass;
+            reps.push_back(d);
+            tile += even(int64_t(r1 - r0) * sp.w);
+            W.n_parts += sp.w;
+          }
+          for (int32_t c = 0; c < sp.w; ++c) {
+            const int32_t col = sp.c0 + c;  // < ncols: strips never pad
+            colA.push_back(part0 + c); colA.push_back(sp.parts | (sp.w << 16));
+            if (pass == 0) {
+              colA.push_back(sn.zc_off + col); colA.push_back(child_z(0, sn.s + col));
+              colB.push_back(child_z(1, sn.s + col));
+            } else {
+              colA.push_back(idx_user[n.idx_off + col]); colA.push_back(0);
+            }
           }
         }
-        while (L.index.size() % 4) L.index.push_back(0);
-        for (int32_t k = 0; k < nblk; ++k) {
-          items.push_back({pass == 0 ? SW_TOP_FWD : SW_TOP_BWD, sid[id], k * cw, cw, rlen, rs});
-          RepackDesc d;
-          d.dst = rs;
-          d.src = pass == 0 ? n.rf_off : n.rb_off;
-          d.ld = pass == 0 ? n.ldf : n.ldr;
-          d.rlen = rlen; d.col0 = k * cw; d.cw = cw; d.ncols = ncols; d.mode = pass;
-          L.repack.push_back(d);
-          rs += int64_t(rlen) * cw;
+        // balance the micro-tiles over the warps: largest first, dealt round-robin (warp w takes m = w, w + nw, ...)
+        std::vector<int32_t> order(mts.size());
+        for (size_t m = 0; m < order.size(); ++m) order[m] = int32_t(m);
+        std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+          return int64_t(mts[x].nrows) * mts[x].ncols > int64_t(mts[y].nrows) * mts[y].ncols;
+        });
+        W.n_rows = int32_t(pass == 0 ? rows.size() / 4 : rows.size());
+        if (W.n_rows <= L.ws_rows) {
+          W.flags |= SWF_ROWS_WS;
+          L.wave_ws_rows = std::max(L.wave_ws_rows, W.n_rows);
+          if (L.ng == 1 && W.fronts == prev_fronts) {  // the previous wave of this CTA left exactly these rows in place
+            W.flags |= SWF_REUSE;
+            rows.clear();
+            zsd.clear();
+          }
+          prev_fronts = W.fronts;
+        } else {
+          prev_fronts.clear();
         }
-        (pass == 0 ? sn.n_fwd : sn.n_bwd) = nblk;
+        W.n_mt = int32_t(mts.size());
+        W.n_cols = int32_t(colA.size() / 4);
+        W.tile_src = rs; W.tile_dbl = int32_t(tile);
+        for (auto &d : reps) { d.dst += rs; L.repack.push_back(d); }
+        rs += tile;
+        // segment 0
+        auto pad4 = [&] { while (L.index.size() % 4) L.index.push_back(0); };
+        pad4();
+        W.idx_off = int64_t(L.index.size());
+        auto here = [&] { pad4(); return int32_t(int64_t(L.index.size()) - W.idx_off); };
+        W.off_rows = here(); L.index.insert(L.index.end(), rows.begin(), rows.end());
+        W.off_zs = here(); L.index.insert(L.index.end(), zsd.begin(), zsd.end());
+        W.off_colA = here(); L.index.insert(L.index.end(), colA.begin(), colA.end());
+        W.off_colB = here(); L.index.insert(L.index.end(), colB.begin(), colB.end());
+        W.off_mt = here();
+        for (int32_t m : order) {
+          const int32_t *raw = reinterpret_cast<const int32_t *>(&mts[m]);
+          L.index.insert(L.index.end(), raw, raw + sizeof(SweepMt) / 4);
+        }
+        W.idx_len = here();
+        W.sig_off = int64_t(L.index.size());
+        W.n_sig = int32_t(W.fronts.size());
+        for (int32_t fnode : W.fronts) {
+          L.index.push_back(2 * fnode + pass);
+          (pass == 0 ? L.nodes[fnode].n_fwd : L.nodes[fnode].n_bwd) += 1;
+        }
+        pad4();
+        waves.push_back(std::move(W));
       }
     }
-  }
+    // (the counts n_fwd / n_bwd of this level are final now: consumers are planned after their producers)
+    for (const auto &W : waves)
+      for (int32_t fnode : W.fronts) add_producer(2 * fnode + pass, W.cta);
+    return nullptr;
+  };
+  for (size_t h = 0; h < nh; ++h)
+    if (const char *err = plan_level(h, 0)) return err;
+  for (size_t h = nh; h-- > 0;)
+    if (const char *err = plan_level(h, 1)) return err;
+  for (const auto &sn : L.nodes)
+    if (std::max(sn.n_fwd, sn.n_bwd) >= (1 << (31 - SWEEP_DEP_SHIFT))) return "too many waves per front";
+  if (2 * L.nodes.size() >= (size_t(1) << SWEEP_DEP_SHIFT)) return "too many completion counters";
+  L.prod_cta = prod_cta;
   // ---- subtree blobs ----
   for (size_t k = 0; k < tr.instances.size(); ++k) {
     const SubtreeInstance &in = tr.instances[k];
@@ -331,14 +492,13 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
   // compute group of every entry: blocks (with all their chunks) and subtrees are dealt out round-robin
   std::vector<std::vector<uint8_t>> per_grp(n_cta);
   std::vector<int32_t> next_grp(n_cta, 0);
-  std::vector<std::vector<int32_t>> last_of_grp(n_cta, std::vector<int32_t>(ng, -1));
   // ---- static assignment ----
   std::vector<std::vector<SweepEntry>> per(n_cta);
   std::vector<std::vector<SweepIssue>> per_iss(n_cta);
   auto blank = [] {
     SweepEntry e;
     std::memset(&e, 0, sizeof e);
-    e.sig = e.dep0 = e.dep1 = -1;
+    e.sig = -1;
     return e;
   };
   auto blank_issue = [] {
@@ -347,6 +507,8 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
     return s;
   };
   const int32_t n_inst = int32_t(tr.instances.size());
+  const std::vector<int32_t> &cta_of_inst = L.cta_of_inst;
+  auto pack_dep = [](int32_t counter, int32_t count) { return counter | (count << SWEEP_DEP_SHIFT); };
   auto sub_entry = [&](int32_t k, bool fwd, SweepIssue &iss) {
     const SubtreeInstance &in = tr.instances[k];
     const SubtreeTemplate &T = tr.templates[in.tmpl];
@@ -370,18 +532,12 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
     iss.off[3] = int64_t(ih.pb_off) * M; iss.kind[3] = SRC_PTIL;
     for (int t = 0; t < SWEEP_SEGS; ++t) iss.n[t] = e.n[t];
     if (fwd) e.sig = 2 * (L.n_top + k);
-    else if (sn.parent >= 0) { e.dep0 = 2 * sn.parent + 1; e.dep0_n = L.nodes[sn.parent].n_bwd; }
+    else if (sn.parent >= 0 && !(ng == 1 && L.prod_cta[2 * sn.parent + 1] == cta_of_inst[k])) {
+      e.dep[0] = pack_dep(2 * sn.parent + 1, L.nodes[sn.parent].n_bwd);
+      e.n_dep = 1;
+    }
     return e;
   };
-  // interior and boundary subtrees are dealt out separately so that every CTA gets its share of both
-  std::vector<int32_t> cta_of_inst(n_inst, 0);
-  {
-    std::vector<int32_t> interior, boundary;
-    for (int32_t k = 0; k < n_inst; ++k) (tr.templates[tr.instances[k].tmpl].flags == 0 ? interior : boundary).push_back(k);
-    for (size_t t = 0; t < interior.size(); ++t) cta_of_inst[interior[t]] = int32_t(int64_t(t) * n_cta / int64_t(interior.size()));
-    for (size_t t = 0; t < boundary.size(); ++t)
-      cta_of_inst[boundary[t]] = n_cta - 1 - int32_t(int64_t(t) * n_cta / int64_t(boundary.size()));
-  }
   auto take_grp = [&](int32_t cta) {
     const int32_t g = next_grp[cta];
     next_grp[cta] = (g + 1) % ng;
@@ -394,86 +550,35 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
     per_iss[cta].push_back(iss);
     per_grp[cta].push_back(uint8_t(take_grp(cta)));
   }
-
-  int32_t rot = 0;
-  auto place_level = [&](const std::vector<SweepItem> &items) {
-    if (items.empty()) return;
-    int64_t level_dbl = 0;
-    for (const auto &it : items) level_dbl += int64_t(it.rlen) * it.cw;
-    int64_t cum = 0;
-    int32_t used = 0;
-    for (const auto &it : items) {
-      const int64_t sz = int64_t(it.rlen) * it.cw;
-      int32_t slot = level_dbl > 0 ? int32_t((cum + sz / 2) * n_cta / level_dbl) : 0;
-      slot = std::min(slot, n_cta - 1);
-      used = std::max(used, slot + 1);
-      cum += sz;
-      const int32_t cta = (slot + rot) % n_cta;
-      auto &list = per[cta];
-      const SweepNodeH &sn = L.nodes[it.node];
-      const bool fwd = it.kind == SW_TOP_FWD;
-      const int32_t cw = it.cw;
-      const int32_t rows_per = std::max(4, (L.chunk_dbl / cw) & ~3);  // multiples of 4: aligned index-list slices
-      const int32_t grp = take_grp(cta);
-      int32_t r = 0;
-      do {
-        const int32_t r1 = std::min(it.rlen, r + rows_per);
-        SweepEntry e = blank();
-        SweepIssue iss = blank_issue();
-        e.kind = it.kind;
-        e.flags = (r == 0 ? SWF_FIRST : 0) | (r1 >= it.rlen ? SWF_LAST : 0);
-        e.a0 = it.col0; e.a1 = cw; e.a2 = r; e.a3 = r1; e.a4 = sn.s; e.a5 = sn.b; e.a6 = sn.sep_type;
-        e.a7 = it.node;
-        e.o2 = sn.zs_off; e.o3 = sn.zc_off;
-        // the vector rows [r, r1) are staged by this entry unless the previous one left exactly them in place
-        const int32_t prev = last_of_grp[cta][grp];  // the vector the group's previous entry left in its workspace
-        const bool same_rows = prev >= 0 && list[prev].kind == it.kind && list[prev].a7 == it.node &&
-                               list[prev].a2 == r && list[prev].a3 == r1;
-        if (!same_rows && r1 > r) {
-          e.flags |= SWF_NEW_RUN;
-          if (fwd) {
-            e.n[0] = 2 * (r1 - r);
-            iss.off[0] = sn.gl_f / 2 + 2 * int64_t(r);
-          } else {
-            e.n[0] = even((r1 - r + 1) / 2);
-            iss.off[0] = sn.gl_b / 2 + r / 2;
-          }
-          iss.kind[0] = SRC_INDEX;
-        }
-        if (it.rlen == 0) {  // root forward entry: no tile, but it accumulates and stores the separator rhs
-          e.flags |= SWF_NEW_RUN;
-          e.a2 = 0; e.a3 = sn.s;
-          e.n[0] = 2 * sn.s;
-          iss.off[0] = sn.gl_f / 2; iss.kind[0] = SRC_INDEX;
-        }
-        if (fwd && it.col0 == 0) e.flags |= SWF_WRITE_ZS;
-        if (r == 0 && (fwd ? sn.b : sn.s) > 0) {
-          e.n[1] = cw;
-          iss.off[1] = (fwd ? sn.cl_f : sn.cl_b) / 2 + it.col0; iss.kind[1] = SRC_INDEX;
-        }
-        e.n[2] = (r1 - r) * cw;
-        iss.off[2] = it.src + int64_t(r) * cw; iss.kind[2] = SRC_FACTOR;
-        for (int t = 0; t < SWEEP_SEGS; ++t) iss.n[t] = e.n[t];
-        if (fwd) {
-          e.sig = 2 * it.node;
-          if (sn.child[0] >= 0) { e.dep0 = 2 * sn.child[0]; e.dep0_n = L.nodes[sn.child[0]].n_fwd; }
-          if (sn.child[1] >= 0) { e.dep1 = 2 * sn.child[1]; e.dep1_n = L.nodes[sn.child[1]].n_fwd; }
-        } else {
-          e.sig = 2 * it.node + 1;
-          if (sn.parent >= 0) { e.dep0 = 2 * sn.parent + 1; e.dep0_n = L.nodes[sn.parent].n_bwd; }
-          else { e.dep0 = 2 * it.node; e.dep0_n = sn.n_fwd; }
-        }
-        last_of_grp[cta][grp] = int32_t(list.size());
-        list.push_back(e);
-        per_iss[cta].push_back(iss);
-        per_grp[cta].push_back(uint8_t(grp));
-        r = r1;
-      } while (r < it.rlen);
+  auto place_waves = [&](const std::vector<SweepWaveH> &waves) -> const char * {
+    for (const SweepWaveH &W : waves) {
+      const bool fwd = W.kind == SW_TOP_FWD;
+      SweepEntry e = blank();
+      SweepIssue iss = blank_issue();
+      e.kind = W.kind;
+      e.flags = SWF_FIRST | SWF_LAST | W.flags;
+      e.a0 = W.n_rows; e.a1 = W.n_mt; e.a2 = W.n_cols; e.a3 = W.n_parts;
+      e.a4 = W.off_rows; e.a5 = W.off_mt; e.a6 = W.off_colA; e.a7 = W.height;
+      e.o0 = W.off_zs; e.o3 = W.off_colB;
+      e.n[0] = W.idx_len / 2; iss.off[0] = W.idx_off / 2; iss.kind[0] = SRC_INDEX; iss.n[0] = e.n[0];
+      e.n[1] = W.tile_dbl; iss.off[1] = W.tile_src; iss.kind[1] = SRC_FACTOR; iss.n[1] = e.n[1];
+      e.n[2] = even((int64_t((W.flags & SWF_ROWS_WS) ? 0 : W.n_rows) + (fwd ? W.n_cols : 0) + W.n_parts) * M);  // scratch
+      e.sig = -1; e.n_sig = W.n_sig;
+      if (W.sig_off >= (int64_t(1) << 31)) return "index lists beyond 32 bits";
+      e.sig_off = int32_t(W.sig_off);
+      if (W.deps.size() > size_t(SWEEP_MAX_DEPS)) return "wave with too many dependencies";
+      e.n_dep = int32_t(W.deps.size());
+      for (size_t t = 0; t < W.deps.size(); ++t) e.dep[t] = W.deps[t];
+      per[W.cta].push_back(e);
+      per_iss[W.cta].push_back(iss);
+      per_grp[W.cta].push_back(uint8_t(take_grp(W.cta)));
     }
-    (void)used;  // no rotation between levels: the children of a CTA's fronts are mostly its own earlier entries
+    return nullptr;
   };
-  for (size_t h = 0; h < L.fwd.size(); ++h) place_level(L.fwd[h]);
-  for (size_t h = L.bwd.size(); h-- > 0;) place_level(L.bwd[h]);
+  for (size_t h = 0; h < L.fwd.size(); ++h)
+    if (const char *err = place_waves(L.fwd[h])) return err;
+  for (size_t h = L.bwd.size(); h-- > 0;)
+    if (const char *err = place_waves(L.bwd[h])) return err;
   for (int32_t k = 0; k < n_inst; ++k) {
     SweepIssue iss;
     const int32_t cta = cta_of_inst[k];
@@ -490,11 +595,7 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
   for (const auto &list : per)
     if (int64_t(list.size()) > SWEEP_MAX_ENTRIES) return "too many entries per CTA for the group table";
   S.tmpl_dbl = even((L.tmpl16_max + 3) / 4);
-  int32_t rows_max = 0;
-  for (const auto &list : per)
-    for (const auto &e : list)
-      if (e.kind == SW_TOP_FWD || e.kind == SW_TOP_BWD) rows_max = std::max(rows_max, e.a3 - e.a2);
-  S.ws_dbl = even(int64_t(std::max(rows_max, L.sub_ws_max)) * M);
+  S.ws_dbl = even(int64_t(std::max(L.sub_ws_max, L.wave_ws_rows)) * M);
   const int64_t ring = (total_dbl - fixed - int64_t(ng) * (S.tmpl_dbl + S.ws_dbl)) & ~int64_t(1);
   if (double(ring) < std::max(1.0, min_fill) * double(S.entry_max)) {
     std::snprintf(g_msg, sizeof g_msg, "shared-memory ring (%lld doubles) is too small for entries of %d doubles",
@@ -634,12 +735,14 @@ const char *check_sweep_schedule(const SweepLayout &L, const SweepSchedule &S, i
         const int64_t step = s.G / P;
         const SweepEntry &e = S.entries[b0 + s.G % P];
         if (s.issued <= s.G) { std::snprintf(g_msg, sizeof g_msg, "cta %d: entry %lld consumed before it was issued", c, (long long)s.G); return g_msg; }
-        const bool waits = (e.kind == SW_SUB_BWD) || ((e.kind == SW_TOP_FWD || e.kind == SW_TOP_BWD) && (e.flags & SWF_NEW_RUN) && (e.flags & SWF_FIRST));
-        if (waits) {
-          if (e.dep0 >= 0 && cnt[e.dep0] < uint32_t(step + 1) * uint32_t(e.dep0_n)) break;
-          if (e.dep1 >= 0 && cnt[e.dep1] < uint32_t(step + 1) * uint32_t(e.dep1_n)) break;
+        bool blocked = false;
+        for (int32_t t = 0; t < e.n_dep; ++t) {
+          const int32_t counter = e.dep[t] & ((1 << SWEEP_DEP_SHIFT) - 1), count = e.dep[t] >> SWEEP_DEP_SHIFT;
+          if (cnt[counter] < uint32_t(step + 1) * uint32_t(count)) blocked = true;
         }
-        if ((e.flags & SWF_LAST) && e.sig >= 0) ++cnt[e.sig];
+        if (blocked) break;
+        if (e.sig >= 0) ++cnt[e.sig];
+        for (int32_t t = 0; t < e.n_sig; ++t) ++cnt[L.index[size_t(e.sig_off) + t]];
         ++s.G;
         --remaining;
         progress = true;
@@ -650,6 +753,7 @@ const char *check_sweep_schedule(const SweepLayout &L, const SweepSchedule &S, i
   }
   for (size_t n = 0; n < L.nodes.size(); ++n) {
     if (cnt[2 * n] != uint32_t(n_steps) * uint32_t(L.nodes[n].n_fwd)) { std::snprintf(g_msg, sizeof g_msg, "forward counter of node %zu ends at %u", n, cnt[2 * n]); return g_msg; }
+    if (int32_t(n) < L.n_top && cnt[2 * n + 1] != uint32_t(n_steps) * uint32_t(L.nodes[n].n_bwd)) { std::snprintf(g_msg, sizeof g_msg, "backward counter of node %zu ends at %u", n, cnt[2 * n + 1]); return g_msg; }
   }
   return nullptr;
 }
@@ -670,6 +774,19 @@ extern "C" int mmmfe_sweep_plan_check(int32_t nx, int32_t ny, int32_t leaf_cells
   t.build(nx, ny, leaf_cells, subtree_cells);
   mmmfe::SweepLayout L;
   if (const char *e = mmmfe::build_sweep_layout(t, t.idx, std::vector<int32_t>(), n_cta, chunk_dbl, ct, L)) { say(e); return -2; }
+  if (std::getenv("MMMFE_PLAN_DEBUG")) {
+    for (int pass = 0; pass < 2; ++pass)
+      for (size_t h = 0; h < L.fwd.size(); ++h) {
+        const auto &ws = pass == 0 ? L.fwd[h] : L.bwd[h];
+        if (ws.empty()) continue;
+        int64_t tile = 0, rows = 0, mts = 0, deps = 0, fr = 0;
+        std::vector<int> per(n_cta, 0);
+        for (const auto &w : ws) { tile += w.tile_dbl; rows += w.n_rows; mts += w.n_mt; deps += int64_t(w.deps.size()); fr += int64_t(w.fronts.size()); ++per[w.cta]; }
+        std::fprintf(stderr, "%s h %2zu: waves %5zu (max/cta %d) tile/wave %6lld rows/wave %5lld mt/wave %4.1f fronts/wave %4.1f deps/wave %4.2f\n",
+                     pass == 0 ? "fwd" : "bwd", h, ws.size(), *std::max_element(per.begin(), per.end()), (long long)(tile / int64_t(ws.size())),
+                     (long long)(rows / int64_t(ws.size())), double(mts) / ws.size(), double(fr) / ws.size(), double(deps) / ws.size());
+      }
+  }
   mmmfe::SweepSchedule S;
   if (const char *e = mmmfe::build_sweep_schedule(t, L, M, 1, size_t(smem_bytes), 2.0, S)) { say(e); return -3; }
   if (stats) {

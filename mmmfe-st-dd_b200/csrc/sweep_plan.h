@@ -17,13 +17,20 @@ struct SweepNodeH {       // top front, or the root of a subtree (pseudo node: s
   int32_t n_fwd = 0, n_bwd = 0;              // completions per time step
   int32_t sep_type = 0, height = 0;
   int32_t zs_off = -1, zc_off = -1;
-  int64_t gl_f = 0, cl_f = 0, gl_b = 0, cl_b = 0;  // index lists (offsets in int32 units, multiples of 4)
-  int32_t cl_f_len = 0, cl_b_len = 0;              // padded column counts
 };
 
-struct SweepItem {        // one column block of a top front, streamed as one or more row chunks
-  int32_t kind, node, col0, cw, rlen;
-  int64_t src;            // offset of the tile (rlen x cw doubles) in the sweep-layout factor
+struct SweepWaveH {       // one wave: the work of ONE CTA at one tree level and direction (sweep.cuh)
+  int32_t kind = 0, cta = 0, height = 0, flags = 0;  // flags: SWF_ROWS_WS, SWF_REUSE
+  int32_t n_rows = 0, n_mt = 0, n_cols = 0, n_parts = 0;
+  int64_t idx_off = 0;    // segment 0 in the index array (int32 units, multiple of 4)
+  int32_t idx_len = 0;    // int32 units, multiple of 4
+  int32_t off_rows = 0, off_zs = 0, off_colA = 0, off_colB = 0, off_mt = 0;  // int32 units from idx_off
+  int64_t sig_off = 0;    // completion counters of the wave (index array, int32 units)
+  int32_t n_sig = 0;
+  int64_t tile_src = 0;   // micro-tiles in the sweep-layout factor (doubles)
+  int32_t tile_dbl = 0;
+  std::vector<int32_t> fronts;  // sweep nodes with a piece in the wave
+  std::vector<int32_t> deps;    // packed dependencies (counter | count << SWEEP_DEP_SHIFT)
 };
 
 struct SweepInstH {       // one subtree instance
@@ -33,12 +40,17 @@ struct SweepInstH {       // one subtree instance
 };
 
 struct SweepLayout {
-  int32_t n_cta = 0, chunk_dbl = 2048, ct = 256;  // CTAs, doubles per streamed chunk, compute threads per GROUP
+  int32_t n_cta = 0, chunk_dbl = 2048, ct = 256;  // CTAs, micro-tile doubles per wave, compute threads per GROUP
   int32_t n_top = 0;
   std::vector<SweepNodeH> nodes;                 // top fronts (any order), then one pseudo node per subtree instance
   std::vector<SweepInstH> inst;
-  std::vector<std::vector<SweepItem>> fwd, bwd;  // top items by height (ascending)
-  std::vector<RepackDesc> repack;                // top part of the sweep layout from the front storage
+  std::vector<int32_t> cta_of_inst;              // CTA that runs each subtree
+  std::vector<int32_t> prod_cta;                 // per completion counter: the CTA when a single one bumps it, else -2
+  int32_t ng = 1, mt_dbl = 512;                  // compute groups per CTA; target doubles of a micro-tile
+  int32_t ws_rows = 4096;                        // waves with at most this many rows gather them into the workspace
+  int32_t wave_ws_rows = 0;                      // most rows any wave keeps in the workspace
+  std::vector<std::vector<SweepWaveH>> fwd, bwd;  // waves by height (ascending), CTA-major within a height
+  std::vector<RepackDesc> repack;                // micro-tiles of the sweep layout from the front storage
   std::vector<RepackSub> repack_sub;             // subtree blobs
   std::vector<int32_t> perm;                     // backward-blob permutations of the templates (-1: zero padding)
   std::vector<int32_t> rb2_size;                 // doubles of the backward blob of each template in sweep layout
@@ -48,7 +60,6 @@ struct SweepLayout {
   std::vector<uint16_t> tmpl16;                  // packed templates
   std::vector<int64_t> tmpl_off;
   int64_t z_total = 0, xi_total = 0, pb_total = 0;
-  int32_t rows_max = 0;                          // most tile rows of one streamed chunk (gather vector length)
   int32_t tmpl16_max = 0;                        // uint16 words of the largest template
   int32_t sub_ws_max = 0;                        // vector workspace entries (per right-hand side) of a subtree entry
   double bytes_per_step = 0;                     // factor bytes one step streams (with block padding)
@@ -69,7 +80,7 @@ struct SweepSchedule {
 // boxes wider than 127 cells, template fields beyond 16 bits.
 const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx_user,
                                const std::vector<int32_t> &dof_of_canon, int32_t n_cta, int32_t chunk_dbl, int32_t ct,
-                               SweepLayout &L);
+                               SweepLayout &L, int32_t ng = 1, int32_t mt_dbl = 512);
 
 // Shared-memory partition for M right-hand sides within smem_budget bytes per CTA, entry lists and ring schedule.
 // Returns nullptr on success; a message when the ring cannot hold max(2, min_fill) of the largest entries.

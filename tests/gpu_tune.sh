@@ -1,0 +1,25 @@
+#!/bin/bash
+# tuning matrix of the persistent sweep kernel on configs[1] (run under gpurun); output: gpurun_out/tune_*.log
+cd "$(dirname "$0")"
+run() {  # name, env...
+  name=$1; shift
+  env MMMFE_SWEEP_AUTOTUNE=0 "$@" timeout 300 python gpu_perf_probe.py 1024 256 512 128 256 64 3 > ../gpurun_out/tune_$name.log 2>&1
+  grep -E "^apply|sweep kernel:|sweep batches|cycles/CTA|rror" ../gpurun_out/tune_$name.log | sed "s/^/[$name] /"
+}
+for cfg in "$@"; do
+  case $cfg in
+    base) run base ;;
+    k6) run k6 MMMFE_SWEEP_CHUNK=6144 ;;
+    k8) run k8 MMMFE_SWEEP_CHUNK=8192 ;;
+    k3) run k3 MMMFE_SWEEP_CHUNK=3072 ;;
+    m256) run m256 MMMFE_SWEEP_MICRO_TILE=256 ;;
+    m1024) run m1024 MMMFE_SWEEP_MICRO_TILE=1024 ;;
+    c2) run c2 MMMFE_SWEEP_CTAS_PER_SM=2 MMMFE_SWEEP_CHUNK=2048 ;;
+    c2k3) run c2k3 MMMFE_SWEEP_CTAS_PER_SM=2 MMMFE_SWEEP_CHUNK=3072 ;;
+    c2s64) run c2s64 MMMFE_SWEEP_CTAS_PER_SM=2 MMMFE_SWEEP_CHUNK=3072 MMMFE_SUBTREE_CELLS=64 ;;
+    t128c3) run t128c3 MMMFE_SWEEP_COMPUTE_THREADS=128 MMMFE_SWEEP_CTAS_PER_SM=3 MMMFE_SWEEP_CHUNK=2048 MMMFE_SUBTREE_CELLS=64 ;;
+    c2k2) run c2k2 MMMFE_SWEEP_COMPUTE_THREADS=128 MMMFE_SWEEP_CTAS_PER_SM=2 MMMFE_SWEEP_CHUNK=2048 ;;
+    s64) run s64 MMMFE_SUBTREE_CELLS=64 ;;
+    s256) run s256 MMMFE_SUBTREE_CELLS=256 ;;
+  esac
+done
