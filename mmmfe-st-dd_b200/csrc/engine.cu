@@ -119,7 +119,7 @@ struct Factor {
   DevBuf<double> Rs, minv_c;
   double minv_const = 0.0;
   bool minv_uniform = false;
-  DevBuf<int32_t> sweep_index, p_of_cell;
+  DevBuf<int32_t> sweep_index, p_of_cell, inst_ij;
   DevBuf<uint16_t> tmpl16;
   DevBuf<int64_t> tmpl_off;
 };
@@ -146,7 +146,7 @@ struct Batch {
   size_t sweep_smem = 0;
   DevBuf<SweepEntry> s_entries;
   DevBuf<SweepIssue> s_issue;
-  DevBuf<int32_t> s_cta_begin, s_cta_pro, s_sub_q, s_bq_stride;
+  DevBuf<int32_t> s_cta_begin, s_cta_pro, s_sub_q, s_bq_stride, s_inst_bq;
   DevBuf<uint8_t> s_grp;
   DevBuf<double> s_z, s_xi, s_ptil, s_bq_coef;
   DevBuf<uint32_t> s_cnt;
@@ -178,7 +178,7 @@ struct mmmfe_ctx {
   bool sweep_autotune = true;
   double tune_ms_sweep = 0.0, tune_ms_levels = 0.0;
   double sweep_min_fill = 1.75;
-  int sweep_mt = 512;
+  int sweep_mt = 512, sweep_pack = 1;
   int sweep_spin_ns = 100;
   bool is_setup = false, bar_done = false, final_done = false;
   int rank = 0, world = 1;
@@ -444,6 +444,11 @@ static void build_sweep_factor(mmmfe_ctx *c, Factor &F, const std::vector<double
   launch_repack_sub(d_sub.p, int32_t(L.repack_sub.size()), d_perm.p, F.R.p, F.Rs.p, c->stream);
   CUDA_CHECK(cudaGetLastError());
   F.sweep_index.upload(L.index);
+  {
+    std::vector<int32_t> ij = L.inst_ij;
+    ij.push_back(0); ij.push_back(0);
+    F.inst_ij.upload(ij);
+  }
   F.tmpl16.upload(L.tmpl16);
   F.tmpl_off.upload(L.tmpl_off);
   // 1 / (c0 |cell|) in box-major cell order (a scalar on uniform grids)
@@ -502,7 +507,7 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax) 
     {
       std::vector<int32_t> iu(tr.idx.size());
       for (size_t i = 0; i < tr.idx.size(); ++i) iu[i] = dof_of_canon.empty() ? tr.idx[i] : dof_of_canon[tr.idx[i]];
-      if (build_sweep_layout(tr, iu, dof_of_canon, F->sweep_n_cta, c->sweep_chunk, F->sweep_ct / F->sweep_ng, F->lay, F->sweep_ng, c->sweep_mt) != nullptr) { want_sweep = false; break; }
+      if (build_sweep_layout(tr, iu, dof_of_canon, F->sweep_n_cta, c->sweep_chunk, F->sweep_ct / F->sweep_ng, F->lay, F->sweep_ng, c->sweep_mt, c->sweep_pack) != nullptr) { want_sweep = false; break; }
     }
     SweepSchedule probe;
     if (build_sweep_schedule(tr, F->lay, Mmax, F->sweep_ng, F->sweep_budget, c->sweep_min_fill, probe) == nullptr) { sweep_planned = true; break; }
@@ -1017,8 +1022,11 @@ static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> 
     if (any) bq_off[k] = int32_t(base);
     else sub_q.resize(base);
   }
-  for (auto &e : S.entries)
-    if (e.kind == SW_SUB_FWD || e.kind == SW_SUB_BWD) e.a1 = bq_off[e.a7];
+  {
+    std::vector<int32_t> bq_pos(bq_off.size() + 1, -1);
+    for (size_t pos = 0; pos < bq_off.size(); ++pos) bq_pos[pos] = bq_off[F.lay.inst_at_pos[pos]];
+    b.s_inst_bq.upload(bq_pos);
+  }
   sub_q.push_back(-1);
   const size_t nq = tr_base.size();
   std::vector<const double *> data(nq + 1, nullptr);
@@ -1057,6 +1065,8 @@ static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> 
   a.nx = F.nx; a.ny = F.ny; a.nxe = nxe; a.n_flux = F.nf; a.n_pressure = F.np;
   a.n_steps = b.nt; a.level0 = 0;
   a.tmpl_dbl = S.tmpl_dbl; a.ws_dbl = S.ws_dbl; a.ring_dbl = S.ring_dbl;
+  a.pack = F.lay.pack; a.ws_sub_dbl = S.ws_sub_dbl;
+  a.inst_bq = b.s_inst_bq.p; a.inst_ij = F.inst_ij.p;
   a.evict_first = c->sweep_evict_first ? 1 : 0;
   a.spin_ns = uint32_t(c->sweep_spin_ns);
   a.poll_window = std::max(4, 2 * F.sweep_ng);
@@ -1254,7 +1264,7 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   else if (k == "sweep_evict_first") c->sweep_evict_first = value != 0;
   else if (k == "sweep_chunk") c->sweep_chunk = std::max(256, int(value)) & ~1;
   else if (k == "sweep_compute_threads") {
-    if (value != 64 && value != 128 && value != 256) { c->err = "sweep_compute_threads must be 64, 128 or 256"; return MMMFE_E_INVALID; }
+    if (value != 64 && value != 128 && value != 256 && value != 512) { c->err = "sweep_compute_threads must be 64, 128, 256 or 512"; return MMMFE_E_INVALID; }
     c->sweep_ct = int(value);
   }
   else if (k == "sweep_ctas_per_sm") c->sweep_ctas_per_sm = std::max(1, int(value));
@@ -1266,6 +1276,10 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   }
   else if (k == "sweep_min_fill") c->sweep_min_fill = value;
   else if (k == "sweep_micro_tile") c->sweep_mt = std::max(64, int(value));
+  else if (k == "sweep_pack") {
+    if (value != 1 && value != 2 && value != 4) { c->err = "sweep_pack must be 1, 2 or 4"; return MMMFE_E_INVALID; }
+    c->sweep_pack = int(value);
+  }
   else { c->err = "unknown option " + k; return MMMFE_E_INVALID; }
   return MMMFE_OK;
 }

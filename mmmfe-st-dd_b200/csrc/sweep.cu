@@ -654,15 +654,22 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
           gsync();
         }
         const Tmpl T(tb);
-        const int I0 = e.a2, J0 = e.a3, bq = e.a1;
-        const int ncell = T.w * T.h;
-        const double *blob = reg;
-        const double *pc = reg + e.n[0] + e.n[1] + e.n[2];  // pressures of the box (this CTA wrote them last step)
+        // pack: up to a.pack subtrees of this template, TPS threads each, walked in lockstep (same barriers)
+        const int TPS = GT / a.pack, sub = gt / TPS, lt = gt - sub * TPS;
+        const bool act = sub < e.a2;
+        const int pos = e.a7 + (act ? sub : 0);
+        const int bq = act ? a.inst_bq[pos] : -1;
+        const int ncell = T.w * T.h, ncell_e = (ncell + 1) & ~1, nint_e = (T.n_int + 1) & ~1;
+        const int rf_size = reinterpret_cast<const int *>(tb)[6], rb_size = reinterpret_cast<const int *>(tb)[7];
+        // pressures of the box (this CTA wrote them last step)
+        const double *pc = reg + e.n[0] + e.n[1] + e.n[2] + sub * ncell_e * M;
+        double *wsm = ws + sub * a.ws_sub_dbl;
         if (kind == SW_SUB_FWD) {
-          double *vs = ws;                   // right-hand sides of the interior variables
-          double *va = vs + T.n_int * M;     // the same after the children's contributions (kept for the backward pass)
+          const double *blob = reg + sub * rf_size;
+          double *va = wsm;                  // right-hand sides of the interior variables (+ children, level by level)
           double *zl = va + T.n_int * M;     // boundary contributions of every node
-          for (int l = gt; l < T.n_int; l += GT) {
+          if (act)
+          for (int l = lt; l < T.n_int; l += TPS) {
             const int code = T.var_code[l];
             const int type = code >> 14, dj = (code >> 7) & 127, di = code & 127;
             double val[M];
@@ -688,19 +695,37 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
               }
             }
 #pragma unroll
-            for (int j = 0; j < M; ++j) vs[l * M + j] = val[j];
+            for (int j = 0; j < M; ++j) va[l * M + j] = val[j];
           }
           gsync();
           SWEEP_PROF(11)
-          // one phase per level: every boundary output of every node of the level; the separator values a node
-          // needs (own rhs + children's contributions) are formed on the fly, its first output stores them
+          // two phases per level: (i) the separator variables of the level's nodes collect their children's
+          // contributions, (ii) every boundary output of every node: pass-through + (-G^T)^T-row times those values
           for (int lv = 0; lv < T.n_levels; ++lv) {
-            for (int o = T.lvl_out[lv] + gt; o < T.lvl_out[lv + 1]; o += GT) {
+            if (lv > 0) {
+              const int4 Lh = T.lvlb[lv];
+              if (act)
+              for (int v = Lh.x + lt; v < Lh.x + Lh.y; v += TPS) {
+                const uint32_t cc = T.sc[v];
+                const int k0 = cc & 0xFFFF, k1 = cc >> 16;
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                  double vk = va[v * M + j];
+                  if (k0 != 0xFFFF) vk += zl[k0 * M + j];
+                  if (k1 != 0xFFFF) vk += zl[k1 * M + j];
+                  va[v * M + j] = vk;
+                }
+              }
+              gsync();
+            }
+            if (act)
+            for (int o = T.lvl_out[lv] + lt; o < T.lvl_out[lv + 1]; o += TPS) {
               const uint4 D = T.fdesc[o];
-              const int rf_off = D.x & 0xFFFF, sb = D.x >> 16, sep0 = D.y & 0xFFFF, writer = D.y >> 16;
+              const int rf_off = D.x & 0xFFFF, sb = D.x >> 16, sep0 = D.y & 0xFFFF;
               const int c0 = D.z & 0xFFFF, c1 = D.z >> 16;
               const int s = sb >> 8, b = sb & 255;
               const double *rf = blob + rf_off;
+              const double *vv = va + sep0 * M;
               double av[M];
 #pragma unroll
               for (int j = 0; j < M; ++j) {
@@ -708,27 +733,17 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
                 if (c0 != 0xFFFF) av[j] += zl[c0 * M + j];
                 if (c1 != 0xFFFF) av[j] += zl[c1 * M + j];
               }
-#pragma unroll 2
-              for (int k = 0; k < s; ++k) {
-                double vk[M];
+              int k = 0;
+              for (; k + 4 <= s; k += 4) {
+                const double r0 = rf[k * b], r1 = rf[(k + 1) * b], r2 = rf[(k + 2) * b], r3 = rf[(k + 3) * b];
 #pragma unroll
-                for (int j = 0; j < M; ++j) vk[j] = vs[(sep0 + k) * M + j];
-                if (lv > 0) {  // leaves have no children
-                  const uint32_t cc = T.sc[sep0 + k];
-                  const int k0 = cc & 0xFFFF, k1 = cc >> 16;
-                  if (k0 != 0xFFFF)
+                for (int j = 0; j < M; ++j)
+                  av[j] += r0 * vv[k * M + j] + r1 * vv[(k + 1) * M + j] + r2 * vv[(k + 2) * M + j] + r3 * vv[(k + 3) * M + j];
+              }
+              for (; k < s; ++k) {
+                const double r0 = rf[k * b];
 #pragma unroll
-                    for (int j = 0; j < M; ++j) vk[j] += zl[k0 * M + j];
-                  if (k1 != 0xFFFF)
-#pragma unroll
-                    for (int j = 0; j < M; ++j) vk[j] += zl[k1 * M + j];
-                }
-                const double r = rf[k * b];
-#pragma unroll
-                for (int j = 0; j < M; ++j) av[j] += r * vk[j];
-                if (writer)
-#pragma unroll
-                  for (int j = 0; j < M; ++j) va[(sep0 + k) * M + j] = vk[j];
+                for (int j = 0; j < M; ++j) av[j] += r0 * vv[k * M + j];
               }
 #pragma unroll
               for (int j = 0; j < M; ++j) zl[o * M + j] = av[j];
@@ -736,34 +751,25 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
             gsync();
           }
           SWEEP_PROF(12)
-          if (T.n_rootb == 0) {  // the subtree is the whole subdomain: its root has no boundary, hence no output
-            const int v0 = T.lvlb[T.n_levels - 1].x, n_out = T.lvlb[T.n_levels - 1].y;
-            for (int v = v0 + gt; v < v0 + n_out; v += GT) {
-              const uint32_t cc = T.sc[v];
-              const int k0 = cc & 0xFFFF, k1 = cc >> 16;
-#pragma unroll
-              for (int j = 0; j < M; ++j) {
-                double vk = vs[v * M + j];
-                if (T.n_levels > 1 && k0 != 0xFFFF) vk += zl[k0 * M + j];
-                if (T.n_levels > 1 && k1 != 0xFFFF) vk += zl[k1 * M + j];
-                va[v * M + j] = vk;
-              }
-            }
-            gsync();
+          if (act) {
+            for (int l = lt; l < T.n_int * M; l += TPS) a.xi[int64_t(e.o1 + sub * nint_e) * M + l] = va[l];
+            const int zr = T.zl_size - T.n_rootb;  // the root is the last node
+            for (int q = lt; q < T.n_rootb * M; q += TPS) a.z[int64_t(e.o0 + sub * T.n_rootb) * M + q] = zl[zr * M + q];
           }
-          for (int l = gt; l < T.n_int * M; l += GT) a.xi[int64_t(e.o1) * M + l] = va[l];
-          const int zr = T.zl_size - T.n_rootb;  // the root is the last node
-          for (int q = gt; q < T.n_rootb * M; q += GT) a.z[int64_t(e.o0) * M + q] = zl[zr * M + q];
           fence_async_global();  // xi is streamed back by TMA in the backward entry
           SWEEP_PROF(13)
         } else {
-          const int *xb = reinterpret_cast<const int *>(reg + e.n[0]);
-          const double *zs = reg + e.n[0] + e.n[1];  // accumulated right-hand sides of the interior variables
-          double *xs = ws;                          // solution: [interior | root boundary]
-          for (int q = gt; q < T.n_rootb; q += GT) {
-            const int64_t d = xb[q];
+          const double *blob = reg + sub * rb_size;
+          const int xb_stride = (T.n_rootb + 3) & ~3;  // int32 entries per member
+          const int *xb = reinterpret_cast<const int *>(reg + e.n[0]) + sub * xb_stride;
+          const double *zs = reg + e.n[0] + e.n[1] + sub * nint_e * M;  // accumulated rhs of the interior variables
+          double *xs = wsm;                         // solution: [interior | root boundary]
+          if (act)
+          for (int q = lt; q < T.n_rootb; q += TPS) {
+            double v[M];
+            ld_vec<M>(a.x + int64_t(xb[q]) * M, v);
 #pragma unroll
-            for (int j = 0; j < M; ++j) xs[(T.n_int + q) * M + j] = __ldcg(a.x + d * M + j);
+            for (int j = 0; j < M; ++j) xs[(T.n_int + q) * M + j] = v[j];
           }
           gsync();
           SWEEP_PROF(8)
@@ -771,8 +777,9 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
           for (int lv = T.n_levels - 1; lv >= 0; --lv) {
             const int4 Lh = T.lvlb[lv];
             const int v0 = Lh.x, n_out = Lh.y, tl = Lh.z, estep = Lh.w;
-            const int tpo = 1 << tl, per = GT >> tl;
-            const int grp = gt >> tl, rl = gt & (tpo - 1);
+            const int tpo = 1 << tl, per = TPS >> tl;
+            const int grp = lt >> tl, rl = lt & (tpo - 1);
+            if (act)  // whole warps: TPS is a multiple of 32
             for (int o0 = 0; o0 < n_out; o0 += per) {
               const int o = o0 + grp;
               double av[M];
@@ -802,11 +809,15 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
             gsync();
           }
           SWEEP_PROF(9)
+          int I0 = 0, J0 = 0;
+          if (act && (a.hist || a.has_src)) { I0 = a.inst_ij[2 * pos]; J0 = a.inst_ij[2 * pos + 1]; }
+          const int64_t pb = int64_t(e.o2) + sub * ncell_e;
           // pressure recovery p = p_old - M^-1 K_pu u for the cells of the box; next right-hand side source
-          for (int c = gt; c < ncell; c += GT) {
+          if (act)
+          for (int c = lt; c < ncell; c += TPS) {
             const int el = T.cell_edge[4 * c], er = T.cell_edge[4 * c + 1], eb = T.cell_edge[4 * c + 2],
                       et = T.cell_edge[4 * c + 3];
-            const double mi = a.minv ? a.minv[e.o2 + c] : a.minv_const;
+            const double mi = a.minv ? a.minv[pb + c] : a.minv_const;
             int64_t pidx = 0;
             if (a.hist || a.has_src) {
               const int dj = c / T.w, di = c - dj * T.w;
@@ -825,13 +836,13 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
               double nxt = p;
               if (a.has_src && a.src_next[j] && step + 1 < a.n_steps)
                 nxt += mi * a.src_next[j][int64_t(level + 1) * a.n_pressure + pidx];
-              a.ptil[int64_t(e.o2 + c) * M + j] = nxt;
+              a.ptil[(pb + c) * M + j] = nxt;
             }
           }
           fence_async_global();  // the box pressures are streamed back by TMA in the next step
           SWEEP_PROF(10)
           if (bq >= 0) {  // subdom_to_st_distribute: flux traces of the interface dofs
-            for (int l = gt; l < T.n_int * M; l += GT) {
+            for (int l = lt; l < T.n_int * M; l += TPS) {
               const int q = a.sub_q[bq + l];
               if (q >= 0) {
                 double *tp = a.bq_trace[q];
@@ -839,8 +850,8 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
               }
             }
           }
-          if (a.hist) {
-            for (int l = gt; l < T.n_int; l += GT) {
+          if (a.hist && act) {
+            for (int l = lt; l < T.n_int; l += TPS) {
               const int64_t d = sweep_dof(a, I0, J0, T.var_code[l]);
 #pragma unroll
               for (int j = 0; j < M; ++j)
@@ -897,6 +908,9 @@ static cudaError_t launch_t(const SweepArgs &a, int32_t n_cta, size_t smem_bytes
 
 #define SWEEP_DISPATCH(M, CT, CALL)                                            \
   switch ((M) * 1000 + (CT)) {                                                 \
+    case 1512: { constexpr int MM = 1, CC = 512; CALL; } break;                \
+    case 2512: { constexpr int MM = 2, CC = 512; CALL; } break;                \
+    case 4512: { constexpr int MM = 4, CC = 512; CALL; } break;                \
     case 1256: { constexpr int MM = 1, CC = 256; CALL; } break;                \
     case 2256: { constexpr int MM = 2, CC = 256; CALL; } break;                \
     case 4256: { constexpr int MM = 4, CC = 256; CALL; } break;                \

@@ -57,9 +57,11 @@ enum SweepSrc : int32_t { SRC_FACTOR = 0, SRC_INDEX = 1, SRC_XI = 2, SRC_PTIL = 
 //            << 16, z destination, child-0 z}, B {child-1 z};  micro-tile of -G^T (rows: separator, columns: boundary)
 //       BWD  row record int {x dof, or 1 << 31 | z index for the separator rows}; column record A {slot, parts |
 //            stride << 16, x dof, -}; micro-tile of [F11^-1 ; -G] (rows: separator + boundary, columns: separator)
-//   subtree entries: a0 template, a1 boundary-entry table offset (-1: none), a2 I0, a3 J0, a7 instance,
-//     o0 zc_off (root boundary contributions), o1 xi_off, o2 ptil offset of the box (box-major cell order)
-//     segments: 0 factor blob, 1 root-boundary x dofs (BWD), 2 interior right-hand sides xi (BWD), 3 box pressures
+//   subtree entries (PACKS of a2 <= SweepArgs::pack subtrees of one template, neighbours in every array, walked in
+//     lockstep by GT / pack threads each): a0 template, a2 members, a7 allocation position of the first member,
+//     o0 zc_off (root boundary contributions), o1 xi_off, o2 ptil offset of the box (box-major cell order) of the
+//     first member; segments (members back to back): 0 factor blobs, 1 root-boundary x dofs (BWD), 2 interior
+//     right-hand sides xi (BWD), 3 box pressures
 //
 // Completion: sig >= 0: one counter (subtrees); n_sig > 0: the counters index[sig_off ...] (waves: one per front).
 // Dependencies: dep[t] = counter | count << 21; satisfied when counter >= (step + 1) * count.
@@ -132,6 +134,9 @@ struct SweepArgs {
   int64_t nxe, n_flux, n_pressure;
   int32_t n_steps, level0;
   int32_t tmpl_dbl, ws_dbl, ring_dbl;  // shared-memory partition in doubles (template and workspace: per group)
+  int32_t pack, ws_sub_dbl;            // subtrees per pack (1, 2, 4) and workspace doubles of one pack member
+  const int32_t *inst_bq;              // per subtree (allocation order): boundary-entry table offset or -1
+  const int32_t *inst_ij;              // per subtree (allocation order): I0, J0
   int32_t evict_first;
   uint32_t spin_ns;             // back-off of the service warps' polling loops
   int32_t poll_window;          // entries ahead of the oldest unopened one that poll the completion counters

@@ -127,13 +127,14 @@ const char *pack_template(const SubtreeTemplate &T, int32_t ct, std::vector<uint
 
 const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx_user,
                                const std::vector<int32_t> &dof_of_canon, int32_t n_cta, int32_t chunk_dbl, int32_t ct,
-                               SweepLayout &L, int32_t ng, int32_t mt_dbl) {
+                               SweepLayout &L, int32_t ng, int32_t mt_dbl, int32_t pack) {
   L = SweepLayout();
   L.n_cta = n_cta;
   L.chunk_dbl = chunk_dbl;
   L.ct = ct;
   L.ng = std::max(1, ng);
   L.mt_dbl = std::max(64, mt_dbl);
+  L.pack = (pack == 2 || pack == 4) && ct / pack >= 32 ? pack : 1;
   if (const char *env = std::getenv("MMMFE_SWEEP_WS_ROWS")) L.ws_rows = std::atoi(env);
   const int32_t nn = int32_t(tr.nodes.size());
   if (tr.instances.empty()) return "no subtrees (subtree_cells = 0)";
@@ -148,20 +149,41 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
     const size_t before = L.tmpl16.size();
     std::vector<int32_t> perm;
     int32_t rb2 = 0;
-    if (const char *err = pack_template(T, ct, L.tmpl16, perm, rb2)) return err;
+    if (const char *err = pack_template(T, ct / L.pack, L.tmpl16, perm, rb2)) return err;
     L.tmpl16_max = std::max(L.tmpl16_max, int32_t(L.tmpl16.size() - before));
     perm_off.push_back(int32_t(L.perm.size()));
     L.perm.insert(L.perm.end(), perm.begin(), perm.end());
     L.rb2_size.push_back(rb2);
-    L.sub_ws_max = std::max(L.sub_ws_max, std::max(2 * T.n_int + T.zl_size, T.n_int + T.n_rootb));
+    L.sub_ws_max = std::max(L.sub_ws_max, std::max(T.n_int + T.zl_size, T.n_int + T.n_rootb));
   }
   L.perm.push_back(0);
+  // ---- subtrees -> CTAs: interior and boundary subtrees are dealt out separately so that every CTA gets its share
+  // of both ----
+  const int32_t n_inst = int32_t(tr.instances.size());
+  L.cta_of_inst.assign(n_inst, 0);
+  {
+    std::vector<int32_t> interior, boundary;
+    for (int32_t k = 0; k < n_inst; ++k) (tr.templates[tr.instances[k].tmpl].flags == 0 ? interior : boundary).push_back(k);
+    for (size_t t = 0; t < interior.size(); ++t) L.cta_of_inst[interior[t]] = int32_t(int64_t(t) * n_cta / int64_t(interior.size()));
+    for (size_t t = 0; t < boundary.size(); ++t)
+      L.cta_of_inst[boundary[t]] = n_cta - 1 - int32_t(int64_t(t) * n_cta / int64_t(boundary.size()));
+  }
+  // allocation order (CTA, template, instance): the members of a pack are neighbours in every array
+  L.inst_at_pos.resize(n_inst);
+  for (int32_t k = 0; k < n_inst; ++k) L.inst_at_pos[k] = k;
+  std::stable_sort(L.inst_at_pos.begin(), L.inst_at_pos.end(), [&](int32_t x, int32_t y) {
+    if (L.cta_of_inst[x] != L.cta_of_inst[y]) return L.cta_of_inst[x] < L.cta_of_inst[y];
+    return tr.instances[x].tmpl < tr.instances[y].tmpl;
+  });
   L.cell_box.assign(size_t(tr.nx) * tr.ny, -1);
   L.inst.resize(tr.instances.size());
-  for (size_t k = 0; k < tr.instances.size(); ++k) {
+  for (int32_t pos = 0; pos < n_inst; ++pos) {
+    const int32_t k = L.inst_at_pos[pos];
     const SubtreeInstance &in = tr.instances[k];
     const SubtreeTemplate &T = tr.templates[in.tmpl];
     SweepInstH &h = L.inst[k];
+    h.pos = pos;
+    L.inst_ij.push_back(in.I0); L.inst_ij.push_back(in.J0);
     h.xi_off = int32_t(L.xi_total);
     L.xi_total += even(T.n_int);
     h.pb_off = int32_t(L.pb_total);
@@ -177,6 +199,10 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
       L.index.push_back(user(canon));
     }
     while (L.index.size() % 4) L.index.push_back(0);
+    if (L.packs.empty() || L.packs.back().n >= L.pack || L.packs.back().tmpl != in.tmpl ||
+        L.packs.back().cta != L.cta_of_inst[k])
+      L.packs.push_back({pos, 0, in.tmpl, L.cta_of_inst[k], 0});
+    L.packs.back().n += 1;
   }
   for (int32_t cb : L.cell_box)
     if (cb < 0) return "a cell lies outside every subtree";
@@ -212,23 +238,18 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
           h.child[c] = sid[n.child[c]];
         }
     if (n.parent >= 0) h.parent = sid[n.parent];
-    if (h.s > 0) { h.zs_off = int32_t(L.z_total); L.z_total += h.s; }
+    if (h.s > 0) {
+      h.zs_off = int32_t(L.z_total); L.z_total += h.s;
+      h.zc_off = int32_t(L.z_total); L.z_total += h.b;
+    }
+  }
+  for (int32_t pos = 0; pos < n_inst; ++pos) {  // root-boundary contributions of the subtrees: allocation order
+    SweepNodeH &h = L.nodes[L.n_top + L.inst_at_pos[pos]];
     h.zc_off = int32_t(L.z_total);
     L.z_total += h.b;
   }
   if (L.z_total >= (int64_t(1) << 29)) return "vector storage beyond 32 bits";
 
-  // ---- subtrees -> CTAs: interior and boundary subtrees are dealt out separately so that every CTA gets its share
-  // of both ----
-  const int32_t n_inst = int32_t(tr.instances.size());
-  L.cta_of_inst.assign(n_inst, 0);
-  {
-    std::vector<int32_t> interior, boundary;
-    for (int32_t k = 0; k < n_inst; ++k) (tr.templates[tr.instances[k].tmpl].flags == 0 ? interior : boundary).push_back(k);
-    for (size_t t = 0; t < interior.size(); ++t) L.cta_of_inst[interior[t]] = int32_t(int64_t(t) * n_cta / int64_t(interior.size()));
-    for (size_t t = 0; t < boundary.size(); ++t)
-      L.cta_of_inst[boundary[t]] = n_cta - 1 - int32_t(int64_t(t) * n_cta / int64_t(boundary.size()));
-  }
   // producers of every completion counter (2 * node: forward, 2 * node + 1: backward): the CTA when it is a single
   // one.  A consumer that runs later on the same CTA needs no counter (one compute group: program order + barrier).
   std::vector<int32_t> prod_cta(2 * L.nodes.size(), -1);  // -1 none yet, -2 several CTAs
@@ -466,12 +487,22 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
     if (std::max(sn.n_fwd, sn.n_bwd) >= (1 << (31 - SWEEP_DEP_SHIFT))) return "too many waves per front";
   if (2 * L.nodes.size() >= (size_t(1) << SWEEP_DEP_SHIFT)) return "too many completion counters";
   L.prod_cta = prod_cta;
-  // ---- subtree blobs ----
+  // ---- subtree blobs: per pack the forward blobs of the members, then their backward blobs ----
+  for (SweepPackH &P : L.packs) {
+    for (int pass = 0; pass < 2; ++pass)
+      for (int32_t m = 0; m < P.n; ++m) {
+        const int32_t k = L.inst_at_pos[P.pos0 + m];
+        const SubtreeTemplate &T = tr.templates[tr.instances[k].tmpl];
+        if (pass == 0) { L.inst[k].rf = rs; rs += T.rf_size; }
+        else { L.inst[k].rb = rs; rs += L.rb2_size[tr.instances[k].tmpl]; }
+      }
+    P.sig_off = int64_t(L.index.size());
+    for (int32_t m = 0; m < P.n; ++m) L.index.push_back(2 * (L.n_top + L.inst_at_pos[P.pos0 + m]));
+    while (L.index.size() % 4) L.index.push_back(0);
+  }
   for (size_t k = 0; k < tr.instances.size(); ++k) {
     const SubtreeInstance &in = tr.instances[k];
     const SubtreeTemplate &T = tr.templates[in.tmpl];
-    L.inst[k].rf = rs; rs += T.rf_size;
-    L.inst[k].rb = rs; rs += L.rb2_size[in.tmpl];
     RepackSub d;
     d.old_rf = in.rf_base; d.old_rb = in.rb_base; d.new_rf = L.inst[k].rf; d.new_rb = L.inst[k].rb;
     d.rf_size = T.rf_size; d.rb_size = L.rb2_size[in.tmpl]; d.perm_off = perm_off[in.tmpl]; d.pad = 0;
@@ -506,35 +537,39 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
     std::memset(&s, 0, sizeof s);
     return s;
   };
-  const int32_t n_inst = int32_t(tr.instances.size());
-  const std::vector<int32_t> &cta_of_inst = L.cta_of_inst;
   auto pack_dep = [](int32_t counter, int32_t count) { return counter | (count << SWEEP_DEP_SHIFT); };
-  auto sub_entry = [&](int32_t k, bool fwd, SweepIssue &iss) {
-    const SubtreeInstance &in = tr.instances[k];
+  auto sub_entry = [&](const SweepPackH &P, bool fwd, SweepIssue &iss) {
+    const int32_t k0 = L.inst_at_pos[P.pos0];
+    const SubtreeInstance &in = tr.instances[k0];
     const SubtreeTemplate &T = tr.templates[in.tmpl];
-    const SweepNodeH &sn = L.nodes[L.n_top + k];
-    const SweepInstH &ih = L.inst[k];
+    const SweepInstH &ih = L.inst[k0];
     SweepEntry e = blank();
     iss = blank_issue();
     e.kind = fwd ? SW_SUB_FWD : SW_SUB_BWD;
     e.flags = SWF_FIRST | SWF_LAST;
-    e.a0 = in.tmpl; e.a1 = -1; e.a2 = in.I0; e.a3 = in.J0; e.a7 = k;
-    e.o0 = sn.zc_off; e.o1 = ih.xi_off; e.o2 = ih.pb_off;
-    e.n[0] = fwd ? T.rf_size : L.rb2_size[in.tmpl];
+    e.a0 = in.tmpl; e.a1 = -1; e.a2 = P.n; e.a7 = P.pos0;
+    e.o0 = L.nodes[L.n_top + k0].zc_off; e.o1 = ih.xi_off; e.o2 = ih.pb_off;
+    e.n[0] = P.n * (fwd ? T.rf_size : L.rb2_size[in.tmpl]);
     iss.off[0] = fwd ? ih.rf : ih.rb; iss.kind[0] = SRC_FACTOR;
     if (!fwd) {
-      e.n[1] = even((T.n_rootb + 1) / 2);
+      e.n[1] = P.n * even((T.n_rootb + 1) / 2);
       iss.off[1] = ih.xb / 2; iss.kind[1] = SRC_INDEX;
-      e.n[2] = even(T.n_int) * M;
+      e.n[2] = P.n * even(T.n_int) * M;
       iss.off[2] = int64_t(ih.xi_off) * M; iss.kind[2] = SRC_XI;
     }
-    e.n[3] = even(int64_t(T.w) * T.h) * M;
+    e.n[3] = P.n * even(int64_t(T.w) * T.h) * M;
     iss.off[3] = int64_t(ih.pb_off) * M; iss.kind[3] = SRC_PTIL;
     for (int t = 0; t < SWEEP_SEGS; ++t) iss.n[t] = e.n[t];
-    if (fwd) e.sig = 2 * (L.n_top + k);
-    else if (sn.parent >= 0 && !(ng == 1 && L.prod_cta[2 * sn.parent + 1] == cta_of_inst[k])) {
-      e.dep[0] = pack_dep(2 * sn.parent + 1, L.nodes[sn.parent].n_bwd);
-      e.n_dep = 1;
+    if (fwd) {
+      e.n_sig = P.n;
+      e.sig_off = int32_t(P.sig_off);
+    } else {
+      for (int32_t m = 0; m < P.n; ++m) {
+        const SweepNodeH &sn = L.nodes[L.n_top + L.inst_at_pos[P.pos0 + m]];
+        if (sn.parent < 0 || (ng == 1 && L.prod_cta[2 * sn.parent + 1] == P.cta)) continue;
+        const int32_t d = pack_dep(2 * sn.parent + 1, L.nodes[sn.parent].n_bwd);
+        if (std::find(e.dep, e.dep + e.n_dep, d) == e.dep + e.n_dep) e.dep[e.n_dep++] = d;
+      }
     }
     return e;
   };
@@ -543,12 +578,11 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
     next_grp[cta] = (g + 1) % ng;
     return g;
   };
-  for (int32_t k = 0; k < n_inst; ++k) {
+  for (const SweepPackH &P : L.packs) {
     SweepIssue iss;
-    const int32_t cta = cta_of_inst[k];
-    per[cta].push_back(sub_entry(k, true, iss));
-    per_iss[cta].push_back(iss);
-    per_grp[cta].push_back(uint8_t(take_grp(cta)));
+    per[P.cta].push_back(sub_entry(P, true, iss));
+    per_iss[P.cta].push_back(iss);
+    per_grp[P.cta].push_back(uint8_t(take_grp(P.cta)));
   }
   auto place_waves = [&](const std::vector<SweepWaveH> &waves) -> const char * {
     for (const SweepWaveH &W : waves) {
@@ -579,12 +613,12 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
     if (const char *err = place_waves(L.fwd[h])) return err;
   for (size_t h = L.bwd.size(); h-- > 0;)
     if (const char *err = place_waves(L.bwd[h])) return err;
-  for (int32_t k = 0; k < n_inst; ++k) {
+  for (const SweepPackH &P : L.packs) {
+    if (P.sig_off >= (int64_t(1) << 31)) return "index lists beyond 32 bits";
     SweepIssue iss;
-    const int32_t cta = cta_of_inst[k];
-    per[cta].push_back(sub_entry(k, false, iss));
-    per_iss[cta].push_back(iss);
-    per_grp[cta].push_back(uint8_t(take_grp(cta)));
+    per[P.cta].push_back(sub_entry(P, false, iss));
+    per_iss[P.cta].push_back(iss);
+    per_grp[P.cta].push_back(uint8_t(take_grp(P.cta)));
   }
 
   // ---- shared-memory partition (doubles) ----
@@ -595,7 +629,8 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
   for (const auto &list : per)
     if (int64_t(list.size()) > SWEEP_MAX_ENTRIES) return "too many entries per CTA for the group table";
   S.tmpl_dbl = even((L.tmpl16_max + 3) / 4);
-  S.ws_dbl = even(int64_t(std::max(L.sub_ws_max, L.wave_ws_rows)) * M);
+  S.ws_sub_dbl = even(int64_t(L.sub_ws_max) * M);
+  S.ws_dbl = std::max(L.pack * S.ws_sub_dbl, even(int64_t(L.wave_ws_rows) * M));
   const int64_t ring = (total_dbl - fixed - int64_t(ng) * (S.tmpl_dbl + S.ws_dbl)) & ~int64_t(1);
   if (double(ring) < std::max(1.0, min_fill) * double(S.entry_max)) {
     std::snprintf(g_msg, sizeof g_msg, "shared-memory ring (%lld doubles) is too small for entries of %d doubles",
@@ -773,7 +808,8 @@ extern "C" int mmmfe_sweep_plan_check(int32_t nx, int32_t ny, int32_t leaf_cells
   mmmfe::NdTree t;
   t.build(nx, ny, leaf_cells, subtree_cells);
   mmmfe::SweepLayout L;
-  if (const char *e = mmmfe::build_sweep_layout(t, t.idx, std::vector<int32_t>(), n_cta, chunk_dbl, ct, L)) { say(e); return -2; }
+  const int32_t pack = std::getenv("MMMFE_PLAN_PACK") ? std::atoi(std::getenv("MMMFE_PLAN_PACK")) : 1;
+  if (const char *e = mmmfe::build_sweep_layout(t, t.idx, std::vector<int32_t>(), n_cta, chunk_dbl, ct, L, 1, 512, pack)) { say(e); return -2; }
   if (std::getenv("MMMFE_PLAN_DEBUG")) {
     for (int pass = 0; pass < 2; ++pass)
       for (size_t h = 0; h < L.fwd.size(); ++h) {

@@ -33,7 +33,13 @@ struct SweepWaveH {       // one wave: the work of ONE CTA at one tree level and
   std::vector<int32_t> deps;    // packed dependencies (counter | count << SWEEP_DEP_SHIFT)
 };
 
+struct SweepPackH {       // up to SweepLayout::pack subtrees of one template that one CTA walks in lockstep
+  int32_t pos0 = 0, n = 0, tmpl = 0, cta = 0;
+  int64_t sig_off = 0;    // forward completion counters of the members (index array, int32 units)
+};
+
 struct SweepInstH {       // one subtree instance
+  int32_t pos = 0;                 // position in allocation order: (CTA, template, instance)
   int32_t xi_off = 0, pb_off = 0;  // entries (per right-hand side) into xi / box-major ptil; both even
   int64_t xb = 0;                  // root-boundary user dofs (offset into the index array, int32 units)
   int64_t rf = 0, rb = 0;          // blobs in the sweep-layout factor
@@ -45,6 +51,10 @@ struct SweepLayout {
   std::vector<SweepNodeH> nodes;                 // top fronts (any order), then one pseudo node per subtree instance
   std::vector<SweepInstH> inst;
   std::vector<int32_t> cta_of_inst;              // CTA that runs each subtree
+  std::vector<int32_t> inst_at_pos;              // allocation order -> instance
+  std::vector<int32_t> inst_ij;                  // (I0, J0) of the instance at every position
+  std::vector<SweepPackH> packs;                 // CTA-major
+  int32_t pack = 1;                              // subtrees per pack (1, 2 or 4)
   std::vector<int32_t> prod_cta;                 // per completion counter: the CTA when a single one bumps it, else -2
   int32_t ng = 1, mt_dbl = 512;                  // compute groups per CTA; target doubles of a micro-tile
   int32_t ws_rows = 4096;                        // waves with at most this many rows gather them into the workspace
@@ -71,7 +81,7 @@ struct SweepSchedule {
   std::vector<int32_t> cta_begin, cta_prologue;
   std::vector<uint8_t> grp;      // compute group of every entry
   int32_t ng = 1;
-  int32_t tmpl_dbl = 0, ws_dbl = 0, ring_dbl = 0, entry_max = 0;
+  int32_t tmpl_dbl = 0, ws_dbl = 0, ws_sub_dbl = 0, ring_dbl = 0, entry_max = 0;  // ws_sub_dbl: per pack member
   size_t smem_bytes = 0;
 };
 
@@ -80,7 +90,7 @@ struct SweepSchedule {
 // boxes wider than 127 cells, template fields beyond 16 bits.
 const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx_user,
                                const std::vector<int32_t> &dof_of_canon, int32_t n_cta, int32_t chunk_dbl, int32_t ct,
-                               SweepLayout &L, int32_t ng = 1, int32_t mt_dbl = 512);
+                               SweepLayout &L, int32_t ng = 1, int32_t mt_dbl = 512, int32_t pack = 1);
 
 // Shared-memory partition for M right-hand sides within smem_budget bytes per CTA, entry lists and ring schedule.
 // Returns nullptr on success; a message when the ring cannot hold max(2, min_fill) of the largest entries.

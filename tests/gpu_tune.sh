@@ -19,6 +19,20 @@ for cfg in "$@"; do
     c2s64) run c2s64 MMMFE_SWEEP_CTAS_PER_SM=2 MMMFE_SWEEP_CHUNK=3072 MMMFE_SUBTREE_CELLS=64 ;;
     t128c3) run t128c3 MMMFE_SWEEP_COMPUTE_THREADS=128 MMMFE_SWEEP_CTAS_PER_SM=3 MMMFE_SWEEP_CHUNK=2048 MMMFE_SUBTREE_CELLS=64 ;;
     c2k2) run c2k2 MMMFE_SWEEP_COMPUTE_THREADS=128 MMMFE_SWEEP_CTAS_PER_SM=2 MMMFE_SWEEP_CHUNK=2048 ;;
+    l8) run l8 MMMFE_LEAF_CELLS=8 ;;
+    l16) run l16 MMMFE_LEAF_CELLS=16 ;;
+    l16s256) run l16s256 MMMFE_LEAF_CELLS=16 MMMFE_SUBTREE_CELLS=256 ;;
+    t512) run t512 MMMFE_SWEEP_COMPUTE_THREADS=512 ;;
+    sp300) run sp300 MMMFE_SWEEP_SPIN_NS=300 ;;
+    sp1000) run sp1000 MMMFE_SWEEP_SPIN_NS=1000 ;;
+    g2) run g2 MMMFE_SWEEP_GROUPS=2 ;;
+    g4) run g4 MMMFE_SWEEP_GROUPS=4 ;;
+    g2t512) run g2t512 MMMFE_SWEEP_GROUPS=2 MMMFE_SWEEP_COMPUTE_THREADS=512 ;;
+    g4t512) run g4t512 MMMFE_SWEEP_GROUPS=4 MMMFE_SWEEP_COMPUTE_THREADS=512 ;;
+    p2) run p2 MMMFE_SWEEP_PACK=2 ;;
+    p4) run p4 MMMFE_SWEEP_PACK=4 ;;
+    p4s64) run p4s64 MMMFE_SWEEP_PACK=4 MMMFE_SUBTREE_CELLS=64 ;;
+    p2s64) run p2s64 MMMFE_SWEEP_PACK=2 MMMFE_SUBTREE_CELLS=64 ;;
     s64) run s64 MMMFE_SUBTREE_CELLS=64 ;;
     s256) run s256 MMMFE_SUBTREE_CELLS=256 ;;
   esac

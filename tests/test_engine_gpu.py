@@ -100,6 +100,29 @@ def test_persistent_sweep_kernel_matches_oracle_and_generic_kernels(nxs, nts, mo
     assert rel_l2(outs[1], outs[0]) < 1e-12
 
 
+@pytest.mark.parametrize("pack", [2, 4])
+@pytest.mark.parametrize("nxs,nts,mortar,k,cells", [
+    ((16, 8, 8, 16), (8, 4, 4, 8), [4, 4, 2], 1, 16),       # several packs of interior and boundary subtrees per CTA
+    ((37, 23, 23, 37), (6, 3, 3, 6), [5, 5, 3], 2, 64),     # ragged boxes: many templates, short packs
+    ((96, 48, 48, 96), (8, 4, 4, 8), [12, 12, 2], 1, 32),
+])
+def test_sweep_kernel_subtree_packs_match_oracle(nxs, nts, mortar, k, cells, pack):
+    """Packs of 2 or 4 same-shape subtrees walked in lockstep by one CTA (csrc/sweep.cu) give the same operator."""
+    prob = _two_by_two(nxs, nts, mortar, k)
+    q = np.random.default_rng(18).standard_normal(prob.n_iface)
+    eng = engine_from_oracle(prob, options={"use_sweep": 1, "subtree_cells": cells, "sweep_autotune": 0, "sweep_pack": pack})
+    eng.setup()
+    assert eng.stat("sweep_batches") == eng.stat("batches")
+    out = eng.apply(q)
+    assert np.array_equal(out, eng.apply(q))
+    assert rel_l2(out, prob.apply_S(q)) < TOL
+    for li in (0, 3):
+        tr, _ = prob.star_sweep(prob.subs[li], prob.split(q, prob.subs[li]))
+        for side, t in tr.items():
+            assert rel_l2(eng.get_star_trace(li, side).ravel(), t) < TOL
+    eng.close()
+
+
 def test_persistent_sweep_kernel_with_permuted_dofs():
     prm = default_params(1, 2)
     prob = make_problem(prm, 1)
