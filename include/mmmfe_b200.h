@@ -230,6 +230,20 @@ int mmmfe_sweep_plan_check(int32_t nx, int32_t ny, int32_t leaf_cells, int32_t s
                            int32_t chunk_doubles, int64_t stats[8], char *msg, int32_t msg_cap);
 int mmmfe_nd_tree_fill(int32_t nx, int32_t ny, int32_t leaf_cells, int32_t *node_table, int64_t *offsets,
                        int32_t *idx, int32_t *src);
+/* Host-only (no device): the plan of the mortar-face exchange that mmmfe_setup builds for a rank -- replaces the
+ * per-side MPI_Sendrecv of src/darcy_vtdd.cc:1390-1401.  Inputs: the interface sides of the rank's subdomains
+ * (global id, side, neighbour's global id, offset and length in the rank's interface vector) and the owner rank of
+ * every global subdomain.  Outputs: partner[i] >= 0 local partner entry, <= -2 entry -(v + 2) of the receive buffer;
+ * send_index = interface entries in send-buffer order; per peer (ascending rank) the slices of the packed buffers.
+ * Sender and receiver order a peer's faces by (global id, side) of the sending subdomain.                       */
+int mmmfe_exchange_plan(int32_t n_sides, const int32_t *gid, const int32_t *side, const int32_t *neighbor,
+                        const int64_t *off, const int64_t *len, int64_t n_iface, int32_t n_global,
+                        const int32_t *owner, int32_t rank, int32_t world, int64_t *partner, int64_t *send_index,
+                        int64_t send_cap, int64_t *n_send, int32_t *peer_rank, int64_t *peer_send_off,
+                        int64_t *peer_recv_off, int64_t *peer_count, int32_t peer_cap, int32_t *n_peers);
+/* Host-only: the front-end's ownership rule -- contiguous blocks of subdomains in the reference's rank order
+ * (README.md:64), balanced by cost[r] = nx * ny * nt.                                                           */
+int mmmfe_assign_owners(int32_t n_global, const double *cost, int32_t world, int32_t *owner);
 
 #ifdef __cplusplus
 }

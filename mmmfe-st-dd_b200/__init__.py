@@ -92,6 +92,11 @@ def load_engine():
         "mmmfe_debug_sweep_trace": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.c_int64, c_i64p, c_i32p, c_i32p, c_i64p]),
         "mmmfe_sweep_plan_check": (ctypes.c_int, [ctypes.c_int32] * 6 + [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                                   ctypes.c_int32, c_i64p, ctypes.c_char_p, ctypes.c_int32]),
+        "mmmfe_exchange_plan": (ctypes.c_int, [ctypes.c_int32, c_i32p, c_i32p, c_i32p, c_i64p, c_i64p, ctypes.c_int64,
+                                               ctypes.c_int32, c_i32p, ctypes.c_int32, ctypes.c_int32, c_i64p, c_i64p,
+                                               ctypes.c_int64, c_i64p, c_i32p, c_i64p, c_i64p, c_i64p, ctypes.c_int32,
+                                               c_i32p]),
+        "mmmfe_assign_owners": (ctypes.c_int, [ctypes.c_int32, c_f64p, ctypes.c_int32, c_i32p]),
         "mmmfe_nd_tree_sizes": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_i64p]),
         "mmmfe_nd_tree_fill": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, c_i32p, c_i64p, c_i32p,
                                               c_i32p]),
@@ -323,6 +328,46 @@ def sweep_plan_check(nx, ny, leaf_cells=4, subtree_cells=128, M=1, n_cta=296, sm
     keys = ["nodes", "top_fronts", "entries", "factor_doubles", "ring_doubles", "ws_doubles", "max_entry_doubles",
             "smem_bytes"]
     return rc, dict(zip(keys, (int(v) for v in stats))), msg.value.decode()
+
+
+def exchange_plan(sides, n_iface, owner, rank, world):
+    """Host only: the face-exchange plan mmmfe_setup builds for `rank` (csrc/exchange_plan.cpp).
+    sides: list of (global id, side, neighbour global id, offset, length).  Returns (partner, send_index, peers) with
+    peers = [(rank, send_off, recv_off, count)]."""
+    lib = load_engine()
+    n = len(sides)
+    gid = np.array([s[0] for s in sides], dtype=np.int32)
+    side = np.array([s[1] for s in sides], dtype=np.int32)
+    nb = np.array([s[2] for s in sides], dtype=np.int32)
+    off = np.array([s[3] for s in sides], dtype=np.int64)
+    ln = np.array([s[4] for s in sides], dtype=np.int64)
+    own = np.asarray(owner, dtype=np.int32)
+    partner = np.zeros(max(1, n_iface), dtype=np.int64)
+    send_index = np.zeros(max(1, n_iface), dtype=np.int64)
+    n_send = np.zeros(1, dtype=np.int64)
+    cap = max(1, world)
+    pr = np.zeros(cap, dtype=np.int32)
+    ps, prc, pc = (np.zeros(cap, dtype=np.int64) for _ in range(3))
+    n_peers = np.zeros(1, dtype=np.int32)
+    rc = lib.mmmfe_exchange_plan(n, _ptr(gid, c_i32p), _ptr(side, c_i32p), _ptr(nb, c_i32p), _ptr(off, c_i64p),
+                                 _ptr(ln, c_i64p), ctypes.c_int64(n_iface), len(own), _ptr(own, c_i32p), rank, world,
+                                 _ptr(partner, c_i64p), _ptr(send_index, c_i64p), ctypes.c_int64(len(send_index)),
+                                 _ptr(n_send, c_i64p), _ptr(pr, c_i32p), _ptr(ps, c_i64p), _ptr(prc, c_i64p),
+                                 _ptr(pc, c_i64p), cap, _ptr(n_peers, c_i32p))
+    if rc != 0:
+        raise MmmfeError(f"mmmfe_exchange_plan failed ({rc})")
+    k = int(n_peers[0])
+    return partner[:n_iface], send_index[:int(n_send[0])], [(int(pr[i]), int(ps[i]), int(prc[i]), int(pc[i])) for i in range(k)]
+
+
+def assign_owners(cost, world):
+    """Host only: the front-end's ownership rule (contiguous blocks balanced by nx*ny*nt)."""
+    lib = load_engine()
+    cost = np.asarray(cost, dtype=np.float64)
+    owner = np.zeros(len(cost), dtype=np.int32)
+    if lib.mmmfe_assign_owners(len(cost), _ptr(cost, c_f64p), world, _ptr(owner, c_i32p)) != 0:
+        raise MmmfeError("mmmfe_assign_owners failed")
+    return owner
 
 
 def nd_tree(nx, ny, leaf_cells=4):

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -15,6 +16,7 @@
 
 #include "../../include/mmmfe_b200.h"
 #include "common.h"
+#include "exchange_plan.h"
 #include "kernels.cuh"
 #include "nd_tree.h"
 #include "sweep.cuh"
@@ -178,7 +180,7 @@ struct mmmfe_ctx {
   bool sweep_autotune = true;
   double tune_ms_sweep = 0.0, tune_ms_levels = 0.0;
   double sweep_min_fill = 1.75;
-  int sweep_mt = 512, sweep_pack = 1;
+  int sweep_mt = 512, sweep_pack = 2;
   int sweep_spin_ns = 100;
   bool is_setup = false, bar_done = false, final_done = false;
   int rank = 0, world = 1;
@@ -863,41 +865,16 @@ static void setup(mmmfe_ctx *c) {
         }
       }
   c->c2f_all.upload(c2f); c->f2c_all.upload(f2c);
-  // ---- exchange plan ----
-  std::vector<int64_t> partner(size_t(io), -1);
-  struct Seg { int peer; int key_gid, key_side; int64_t off, len; };
-  std::vector<Seg> send_segs, recv_segs;
+  // ---- exchange plan (exchange_plan.cpp: host only, checked by the 2-rank CPU tests) ----
+  std::vector<ExchangeSide> ex_sides;
   for (auto &sp : c->subs)
     for (int s = 0; s < 4; ++s)
-      if (sp->neighbor[s] >= 0) {
-        const int nb = sp->neighbor[s];
-        const int owner = (c->world > 1 && !c->owner.empty()) ? c->owner[nb] : c->rank;
-        if (owner == c->rank) {
-          auto it = local_off.find({nb, kOpposite[s]});
-          if (it == local_off.end()) fail(MMMFE_E_INVALID, "neighbour %d of subdomain %d is not registered", nb, sp->gid);
-          for (int64_t i = 0; i < sp->mortar_len[s]; ++i) partner[sp->iface_off[s] + i] = it->second + i;
-        } else {
-          send_segs.push_back({owner, sp->gid, s, sp->iface_off[s], sp->mortar_len[s]});
-          recv_segs.push_back({owner, nb, kOpposite[s], sp->iface_off[s], sp->mortar_len[s]});
-        }
-      }
-  auto by_key = [](const Seg &a, const Seg &b) {
-    if (a.peer != b.peer) return a.peer < b.peer;
-    if (a.key_gid != b.key_gid) return a.key_gid < b.key_gid;
-    return a.key_side < b.key_side;
-  };
-  std::sort(send_segs.begin(), send_segs.end(), by_key);
-  std::sort(recv_segs.begin(), recv_segs.end(), by_key);
-  std::vector<int64_t> send_index;
+      if (sp->neighbor[s] >= 0) ex_sides.push_back({sp->gid, s, sp->neighbor[s], sp->iface_off[s], sp->mortar_len[s]});
+  ExchangePlan xp;
+  if (const char *err = build_exchange_plan(ex_sides, io, c->owner, c->rank, c->world, xp)) fail(MMMFE_E_INVALID, "%s", err);
+  std::vector<int64_t> &partner = xp.partner, &send_index = xp.send_index;
   int64_t roff = 0;
-  for (size_t i = 0; i < send_segs.size(); ++i) {
-    const Seg &sg = send_segs[i], &rg = recv_segs[i];
-    if (c->peers.empty() || c->peers.back().rank != sg.peer) c->peers.push_back({sg.peer, int64_t(send_index.size()), roff, 0});
-    for (int64_t k = 0; k < sg.len; ++k) send_index.push_back(sg.off + k);
-    for (int64_t k = 0; k < rg.len; ++k) partner[rg.off + k] = -(roff + k) - 2;
-    roff += rg.len;
-    c->peers.back().count += sg.len;
-  }
+  for (const ExchangePeer &p : xp.peers) { c->peers.push_back({p.rank, p.send_off, p.recv_off, p.count}); roff += p.count; }
   for (int64_t v : partner) if (v == -1) fail(MMMFE_E_INVALID, "interface entry without a partner");
   c->partner.upload(partner);
   c->send_index.upload(send_index);
@@ -1673,6 +1650,15 @@ int mmmfe_profile_sweep_cycles(mmmfe_ctx *c, int32_t batch, double out[24]) {
       for (int t = 0; t < 24; ++t) out[t] = 0;
       for (int32_t cta = 0; cta < n_cta; ++cta)
         for (int t = 0; t < 24; ++t) out[t] += double(h[size_t(cta) * 24 + t]) / n_cta;
+      if (const char *dump = std::getenv("MMMFE_PROF_DUMP")) {  // per-CTA counters (slot 15: SM id)
+        if (FILE *f = std::fopen((std::string(dump) + "." + std::to_string(batch)).c_str(), "w")) {
+          for (int32_t cta = 0; cta < n_cta; ++cta) {
+            for (int t = 0; t < 24; ++t) std::fprintf(f, "%lld ", h[size_t(cta) * 24 + t]);
+            std::fprintf(f, "\n");
+          }
+          std::fclose(f);
+        }
+      }
       return MMMFE_OK;
     }
     fail(MMMFE_E_INVALID, "no such sweep batch");

@@ -106,6 +106,12 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity, volatil
     if ((n & 1023) == 1023 && spin_expired(t0, abort_flag)) return;
 }
 
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
@@ -168,6 +174,20 @@ __device__ __forceinline__ void ld_vec(const double *p, double (&v)[M]) {  // L2
 #pragma unroll
     for (int j = 0; j < M; j += 2) {
       const double2 t = __ldcg(reinterpret_cast<const double2 *>(p) + j / 2);
+      v[j] = t.x;
+      v[j + 1] = t.y;
+    }
+  }
+}
+
+template <int M>
+__device__ __forceinline__ void lds_vec(const double *p, double (&v)[M]) {  // shared-memory load of one vector entry
+  if constexpr (M == 1) {
+    v[0] = *p;
+  } else {
+#pragma unroll
+    for (int j = 0; j < M; j += 2) {
+      const double2 t = *(reinterpret_cast<const double2 *>(p) + j / 2);
       v[j] = t.x;
       v[j + 1] = t.y;
     }
@@ -241,6 +261,11 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
     }
     *retired = 0;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (a.prof && tid == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;\n" : "=r"(smid));
+    a.prof[cta * 24 + 15] = smid;
   }
   for (int t = tid; t < P; t += CT + 64) gtab[t] = a.grp[e_first + t];
   __syncthreads();
@@ -433,10 +458,16 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
       if (gtab[i] != cgrp) continue;
       const int slot = int(G % NB);
       const uint32_t parity = uint32_t((G / NB) & 1);
-      long long t_entry = 0, t_w = 0;
-      if (a.prof && tid == 0) t_entry = clock64();
+      long long t_entry = 0, t_w = 0, g_entry = 0, g_w = 0;
+      if (a.prof && tid == 0) {
+        t_entry = clock64();
+        if (a.trace && step == 1) g_entry = global_ns();
+      }
       bar_wait(dep_bar + slot, parity, a.abort_flag);
-      if (a.prof && tid == 0) t_w = clock64();
+      if (a.prof && tid == 0) {
+        t_w = clock64();
+        if (a.trace && step == 1) g_w = global_ns();
+      }
       const SweepEntry &e = edesc[slot];
       const int kind = e.kind, flags = e.flags;
       const double *reg = ring + e.ring_off;
@@ -459,16 +490,38 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
         const double *tiles = reg + e.n[0];
         double *scratch = const_cast<double *>(reg) + e.n[0] + e.n[1];
         double *wsv = (flags & SWF_ROWS_WS) ? ws : scratch;         // [n_rows][M]
-        double *passv = (flags & SWF_ROWS_WS) ? scratch : scratch + n_rows * M;  // [n_cols][M], forward only
-        double *part = passv + (fwd ? n_cols * M : 0);              // [partial slots][M]
+        double *part = (flags & SWF_ROWS_WS) ? scratch : scratch + n_rows * M;  // [partial slots][M]
         const int4 *colA = reinterpret_cast<const int4 *>(ix + e.a6);
-        gsync();  // global writes of this CTA's earlier entries are visible to all its threads
+        // A wave that reuses the gathered rows of the previous wave (same fronts, same CTA) needs no barrier here:
+        // the previous wave's first barrier already ordered this CTA's earlier entries before every thread.
+        const bool reuse = (flags & SWF_REUSE) != 0;
+        if (!reuse) gsync();  // global writes of this CTA's earlier entries are visible to all its threads
         SWEEP_PROF(20)
+        // pass-through of the children's contributions to this wave's boundary columns: loaded into registers now,
+        // added in the output phase (the L2 round trip overlaps the micro-tiles)
+        constexpr int PV = 2;
+        double pv[PV][M];
+        if (fwd) {
+          const int32_t *colB = ix + e.o3;
+#pragma unroll
+          for (int u = 0; u < PV; ++u) {
+            const int o = gt + u * GT;
+#pragma unroll
+            for (int j = 0; j < M; ++j) pv[u][j] = 0.0;
+            if (o < n_cols) {
+              const int c0 = colA[o].w, c1 = colB[o];
+              double p0[M], p1[M];
+              if (c0 >= 0) ld_vec<M>(a.z + int64_t(c0) * M, p0);
+              if (c1 >= 0) ld_vec<M>(a.z + int64_t(c1) * M, p1);
+#pragma unroll
+              for (int j = 0; j < M; ++j) pv[u][j] = (c0 >= 0 ? p0[j] : 0.0) + (c1 >= 0 ? p1[j] : 0.0);
+            }
+          }
+        }
         if (fwd) {
           // rows of v = rhs of the separator dofs (assemble_rhs_star fused: -K_up p_old) + children's contributions
           const int4 *rows = reinterpret_cast<const int4 *>(ix + e.a4);
           const int32_t *zsd = ix + e.o0;
-          const int32_t *colB = ix + e.o3;
           constexpr int RB = 2;  // rows per thread in flight
           for (int r0 = gt; r0 < n_rows && !(flags & SWF_REUSE); r0 += RB * GT) {
             int4 gi[RB];
@@ -503,15 +556,6 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
               }
             }
           }
-          // pass-through of the children's contributions to the boundary dofs of this wave's columns
-          for (int o = gt; o < n_cols; o += GT) {
-            const int c0 = colA[o].w, c1 = colB[o];
-            double p0[M], p1[M];
-            if (c0 >= 0) ld_vec<M>(a.z + int64_t(c0) * M, p0);
-            if (c1 >= 0) ld_vec<M>(a.z + int64_t(c1) * M, p1);
-#pragma unroll
-            for (int j = 0; j < M; ++j) passv[o * M + j] = (c0 >= 0 ? p0[j] : 0.0) + (c1 >= 0 ? p1[j] : 0.0);
-          }
         } else {
           // rows of w = [accumulated separator rhs ; solution of the boundary dofs]
           const int32_t *rows = ix + e.a4;
@@ -536,7 +580,7 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
             }
           }
         }
-        gsync();
+        if (!reuse) gsync();
         SWEEP_PROF(14)
         {
           const SweepMt *mts = reinterpret_cast<const SweepMt *>(ix + e.a5);
@@ -565,8 +609,9 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
                 for (int j = 0; j < M; ++j) part[part_off * M + j] = acc[j];
             } else {
               const int cp = ncols >> 1;                  // lanes per row: each owns two adjacent columns
-              const int rg = 32 / cp;                     // rows in flight per warp instruction
-              const int my_cp = lane & (cp - 1), my_rg = lane / cp;
+              const int lcp = 31 - __clz(cp);
+              const int rg = 32 >> lcp;                   // rows in flight per warp instruction
+              const int my_cp = lane & (cp - 1), my_rg = lane >> lcp;
               const double *tp = tiles + md.x + 2 * my_cp;
               double a0[M], a1[M], b0[M], b1[M];
 #pragma unroll
@@ -575,22 +620,25 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
               for (; r + rg < nrows; r += 2 * rg) {
                 const double2 t0 = *reinterpret_cast<const double2 *>(tp + r * ncols);
                 const double2 t1 = *reinterpret_cast<const double2 *>(tp + (r + rg) * ncols);
+                double v0[M], v1[M];
+                lds_vec<M>(vp + r * M, v0);
+                lds_vec<M>(vp + (r + rg) * M, v1);
 #pragma unroll
                 for (int j = 0; j < M; ++j) {
-                  const double v0 = vp[r * M + j], v1 = vp[(r + rg) * M + j];
-                  a0[j] += t0.x * v0;
-                  a1[j] += t0.y * v0;
-                  b0[j] += t1.x * v1;
-                  b1[j] += t1.y * v1;
+                  a0[j] += t0.x * v0[j];
+                  a1[j] += t0.y * v0[j];
+                  b0[j] += t1.x * v1[j];
+                  b1[j] += t1.y * v1[j];
                 }
               }
               if (r < nrows) {
                 const double2 t0 = *reinterpret_cast<const double2 *>(tp + r * ncols);
+                double v0[M];
+                lds_vec<M>(vp + r * M, v0);
 #pragma unroll
                 for (int j = 0; j < M; ++j) {
-                  const double v0 = vp[r * M + j];
-                  a0[j] += t0.x * v0;
-                  a1[j] += t0.y * v0;
+                  a0[j] += t0.x * v0[j];
+                  a1[j] += t0.y * v0[j];
                 }
               }
 #pragma unroll
@@ -614,7 +662,7 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
         gsync();
         SWEEP_PROF(22)
         // outputs: the row parts of every column are added in a fixed order
-        for (int o = gt; o < n_cols; o += GT) {
+        for (int o = gt, u = 0; o < n_cols; o += GT, ++u) {
           const int4 ca = colA[o];
           const int np = ca.y & 0xFFFF, stride = ca.y >> 16;
           double tot[M];
@@ -624,8 +672,23 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
 #pragma unroll
             for (int j = 0; j < M; ++j) tot[j] += part[(ca.x + q * stride) * M + j];
           if (fwd) {
+            double pass[M];
+            if (u == 0) {
 #pragma unroll
-            for (int j = 0; j < M; ++j) a.z[int64_t(ca.z) * M + j] = tot[j] + passv[o * M + j];
+              for (int j = 0; j < M; ++j) pass[j] = pv[0][j];
+            } else if (u == 1) {
+#pragma unroll
+              for (int j = 0; j < M; ++j) pass[j] = pv[1][j];
+            } else {  // more than PV * GT columns in one wave: load here
+              const int c0 = ca.w, c1 = (ix + e.o3)[o];
+              double p0[M], p1[M];
+              if (c0 >= 0) ld_vec<M>(a.z + int64_t(c0) * M, p0);
+              if (c1 >= 0) ld_vec<M>(a.z + int64_t(c1) * M, p1);
+#pragma unroll
+              for (int j = 0; j < M; ++j) pass[j] = (c0 >= 0 ? p0[j] : 0.0) + (c1 >= 0 ? p1[j] : 0.0);
+            }
+#pragma unroll
+            for (int j = 0; j < M; ++j) a.z[int64_t(ca.z) * M + j] = tot[j] + pass[j];
           } else {
 #pragma unroll
             for (int j = 0; j < M; ++j) a.x[int64_t(ca.z) * M + j] = tot[j];
@@ -871,7 +934,7 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
         a.prof[cta * 24 + 6] += 1;
         if (a.trace && step == 1) {
           long long *tr = a.trace + (int64_t(e_first) + i) * 3;
-          tr[0] = t_entry; tr[1] = t_w; tr[2] = t_end;
+          tr[0] = g_entry; tr[1] = g_w; tr[2] = global_ns();  // nanoseconds of the global timer: comparable across SMs
         }
       }
       __syncwarp();

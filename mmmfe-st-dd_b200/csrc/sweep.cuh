@@ -45,8 +45,7 @@ enum SweepSrc : int32_t { SRC_FACTOR = 0, SRC_INDEX = 1, SRC_XI = 2, SRC_PTIL = 
 //   (ncols = 2..64, a power of two; stored row-major and contiguous) that single warps multiply independently.
 //     segment 0 (index array): row records, column records, micro-tile descriptors
 //     segment 1 (factor):      the micro-tiles
-//     segment 2 (scratch):     gathered vector rows [n_rows][M] (unless SWF_ROWS_WS), pass-through [n_cols][M]
-//                              (forward), partial sums
+//     segment 2 (scratch):     gathered vector rows [n_rows][M] (unless SWF_ROWS_WS), partial sums
 //     a0 n_rows, a1 n_mt, a2 n_cols, a3 partial slots, a4 rows, a5 micro-tiles, a6 column records A, o3 column
 //     records B (forward), o0 zs destinations (forward)   (offsets in int32 units from the start of segment 0),
 //     a7 tree height

@@ -586,7 +586,6 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
   }
   auto place_waves = [&](const std::vector<SweepWaveH> &waves) -> const char * {
     for (const SweepWaveH &W : waves) {
-      const bool fwd = W.kind == SW_TOP_FWD;
       SweepEntry e = blank();
       SweepIssue iss = blank_issue();
       e.kind = W.kind;
@@ -596,7 +595,7 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
       e.o0 = W.off_zs; e.o3 = W.off_colB;
       e.n[0] = W.idx_len / 2; iss.off[0] = W.idx_off / 2; iss.kind[0] = SRC_INDEX; iss.n[0] = e.n[0];
       e.n[1] = W.tile_dbl; iss.off[1] = W.tile_src; iss.kind[1] = SRC_FACTOR; iss.n[1] = e.n[1];
-      e.n[2] = even((int64_t((W.flags & SWF_ROWS_WS) ? 0 : W.n_rows) + (fwd ? W.n_cols : 0) + W.n_parts) * M);  // scratch
+      e.n[2] = even((int64_t((W.flags & SWF_ROWS_WS) ? 0 : W.n_rows) + W.n_parts) * M);  // scratch (not streamed)
       e.sig = -1; e.n_sig = W.n_sig;
       if (W.sig_off >= (int64_t(1) << 31)) return "index lists beyond 32 bits";
       e.sig_off = int32_t(W.sig_off);

@@ -644,15 +644,10 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
     }
     // ---- ownership: contiguous blocks of subdomains balanced by nt * cells ----
     std::vector<int> owner(n_sub, 0);
-    if (world > 1) {
+    {
       std::vector<double> cost(n_sub);
-      double total = 0;
-      for (unsigned r = 0; r < n_sub; ++r) { cost[r] = double(reps[r][0]) * reps[r][1] * reps[r][2]; total += cost[r]; }
-      double acc = 0;
-      for (unsigned r = 0; r < n_sub; ++r) {
-        owner[r] = std::min(world - 1, int(acc / total * world));
-        acc += cost[r];
-      }
+      for (unsigned r = 0; r < n_sub; ++r) cost[r] = double(reps[r][0]) * reps[r][1] * reps[r][2];
+      if (mmmfe_assign_owners(int(n_sub), cost.data(), world, owner.data()) != 0) throw std::runtime_error("mmmfe_assign_owners failed");
     }
     auto t0 = clk::now();
     std::vector<std::unique_ptr<Sub>> subs;

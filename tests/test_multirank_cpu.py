@@ -1,0 +1,157 @@
+"""N > 1 host logic on the CPU (world_size 2, gloo): the ownership rule of the front-end and the face-exchange plan
+the engine builds at set-up (csrc/exchange_plan.cpp) -- sender and receiver must agree on the order of the packed
+faces without negotiation, and exchange + combine over two ranks must equal the single-rank result.
+
+Reference: per-side MPI_Sendrecv + `Ap = -(send + recv)` (src/darcy_vtdd.cc:1379-1411), inner products by
+MPI_Allreduce over both copies of every interface (:1416-1432, quirk Q2).  No device code runs here."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import mmmfe_import
+
+OPP = [2, 3, 0, 1]
+
+
+def _topology(n0, n1):
+    """Neighbours per side (bottom, right, top, left) of an n0 x n1 brick decomposition (inc/utilities.h:146-206)."""
+    nb = {}
+    for r in range(n0 * n1):
+        ix, iy = r % n0, r // n0
+        nb[r] = [r - n0 if iy > 0 else -1, r + 1 if ix < n0 - 1 else -1, r + n0 if iy < n1 - 1 else -1,
+                 r - 1 if ix > 0 else -1]
+    return nb
+
+
+def _mortar_len(r, s, n0):
+    # different lengths for horizontal and vertical faces and per position, so a mis-ordered pack cannot pass
+    ix, iy = r % n0, r // n0
+    return 6 + 2 * (ix if s in (0, 2) else iy) + (3 if s in (1, 3) else 0)
+
+
+def _face_len(r, s, nb, n0):
+    # both sides of a face must use the same length: take it from the lower global id
+    o = nb[r][s]
+    return _mortar_len(min(r, o), s if r < o else OPP[s], n0)
+
+
+def _local_sides(gids, nb, n0):
+    sides, off = [], 0
+    for r in gids:
+        for s in range(4):
+            if nb[r][s] >= 0:
+                ln = _face_len(r, s, nb, n0)
+                sides.append((r, s, nb[r][s], off, ln))
+                off += ln
+    return sides, off
+
+
+def _values(sides, n_iface):
+    """Deterministic 'send' vector: value depends on (gid, side, i) only."""
+    v = np.zeros(n_iface)
+    for gid, s, _, off, ln in sides:
+        v[off:off + ln] = np.sin(1.0 + 7.0 * gid + 1.3 * s + 0.11 * np.arange(ln))
+    return v
+
+
+def _combine(send, partner, recv):
+    out = np.empty_like(send)
+    for i, p in enumerate(partner):
+        out[i] = -(send[i] + (send[p] if p >= 0 else recv[-(p + 2)]))
+    return out
+
+
+def _reference(n0, n1):
+    """Single rank: every face is local.  Returns {(gid, side): Ap values}."""
+    pkg = mmmfe_import.load()
+    nb = _topology(n0, n1)
+    sides, n_iface = _local_sides(range(n0 * n1), nb, n0)
+    partner, send_index, peers = pkg.exchange_plan(sides, n_iface, [], 0, 1)
+    assert len(send_index) == 0 and peers == []
+    send = _values(sides, n_iface)
+    out = _combine(send, partner, np.zeros(0))
+    return {(g, s): out[off:off + ln] for g, s, _, off, ln in sides}, send @ send
+
+
+def _worker(rank, world, port, n0, n1, cost, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pkg = mmmfe_import.load()
+        nb = _topology(n0, n1)
+        owner = pkg.assign_owners(cost, world)
+        mine = [r for r in range(n0 * n1) if owner[r] == rank]
+        sides, n_iface = _local_sides(mine, nb, n0)
+        partner, send_index, peers = pkg.exchange_plan(sides, n_iface, owner, rank, world)
+        send = _values(sides, n_iface)
+        send_buf = torch.from_numpy(send[send_index].copy())
+        recv_buf = torch.zeros(int(sum(p[3] for p in peers)), dtype=torch.float64)
+        # grouped send/recv like ncclGroupStart/End: post everything, then wait
+        reqs = []
+        for prank, soff, roff, cnt in peers:
+            reqs.append(dist.isend(send_buf[soff:soff + cnt], prank))
+            reqs.append(dist.irecv(recv_buf[roff:roff + cnt], prank))
+        for rq in reqs:
+            rq.wait()
+        out = _combine(send, partner, recv_buf.numpy())
+        dot = torch.tensor([float(send @ send)], dtype=torch.float64)
+        dist.all_reduce(dot)  # C5/C6: inner products count both copies of every interface
+        q.put((rank, {(g, s): out[off:off + ln].tolist() for g, s, _, off, ln in sides}, float(dot[0]),
+               [int(o) for o in owner], [p[0] for p in peers]))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("n0,n1,fine_first", [(2, 2, True), (4, 4, True), (4, 2, False)])
+def test_two_rank_exchange_equals_single_rank(n0, n1, fine_first):
+    import torch.multiprocessing as mp
+    n = n0 * n1
+    # checkerboard fine / coarse cost like BASELINE configs[1-3]
+    cost = [(8.0 if (((r % n0) + (r // n0)) % 2 == 0) == fine_first else 1.0) for r in range(n)]
+    ref, ref_dot = _reference(n0, n1)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(rk, 2, port, n0, n1, cost, q)) for rk in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    seen = {}
+    for rank, faces, dot, owner, peer_ranks in results:
+        assert dot == pytest.approx(ref_dot, rel=1e-14)       # allreduce over both copies == single-rank sum
+        assert sorted(set(owner)) == [0, 1] and owner == sorted(owner)  # contiguous blocks, both ranks used
+        assert peer_ranks == [1 - rank]
+        seen.update(faces)
+    assert set(seen) == set(ref)
+    for key, vals in seen.items():
+        assert np.array_equal(np.asarray(vals), ref[key]), key  # bitwise: a + b is commutative, order is fixed
+
+
+def test_owner_rule_balances_cost_in_contiguous_blocks():
+    pkg = mmmfe_import.load()
+    cost = [8.0 if ((r % 8) + (r // 8)) % 2 == 0 else 1.0 for r in range(64)]  # configs[3]: 8x8 checkerboard
+    for world in (1, 2, 4, 8):
+        owner = pkg.assign_owners(cost, world)
+        assert list(owner) == sorted(owner) and set(owner) == set(range(world))
+        loads = [sum(c for c, o in zip(cost, owner) if o == w) for w in range(world)]
+        assert max(loads) <= 1.15 * (sum(cost) / world)
+
+
+def test_exchange_plan_reports_missing_neighbours():
+    pkg = mmmfe_import.load()
+    with pytest.raises(Exception):
+        pkg.exchange_plan([(0, 1, 1, 0, 4)], 4, [], 0, 1)  # neighbour 1 is neither local nor owned elsewhere
