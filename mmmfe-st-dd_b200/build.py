@@ -43,12 +43,14 @@ def build_engine(force=False, verbose=False):
     if not force and not _newer(LIB_ENGINE, deps):
         return LIB_ENGINE
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + ["-x", "cu", "-shared", "-o", LIB_ENGINE] + srcs
+    tmp = LIB_ENGINE + ".tmp"  # built aside and renamed: a snapshot of the tree never sees a half-written library
+    cmd = [nvcc] + NVCC_FLAGS + ["-x", "cu", "-shared", "-o", tmp] + srcs
     if os.path.exists("/usr/include/nccl.h"):
         cmd += ["-DMMMFE_WITH_NCCL", "-ldl"]  # NCCL is dlopen'ed at run time
     if verbose:
         cmd += ["-Xptxas", "-v"]
     out = _run(cmd)
+    os.replace(tmp, LIB_ENGINE)
     if verbose:
         print(out)
     return LIB_ENGINE

@@ -117,6 +117,7 @@ struct Factor {
   bool p_identity = true;
   SweepLayout lay;
   int32_t sweep_n_cta = 0, sweep_ct = 128, sweep_ng = 1;
+  int64_t shared_blob_pairs = 0;
   size_t sweep_budget = 0;
   DevBuf<double> Rs, minv_c;
   double minv_const = 0.0;
@@ -181,6 +182,7 @@ struct mmmfe_ctx {
   double tune_ms_sweep = 0.0, tune_ms_levels = 0.0;
   double sweep_min_fill = 1.75;
   int sweep_mt = 512, sweep_pack = 2;
+  bool sweep_share_blobs = true;
   int sweep_spin_ns = 100;
   bool is_setup = false, bar_done = false, final_done = false;
   int rank = 0, world = 1;
@@ -442,6 +444,32 @@ static void build_sweep_factor(mmmfe_ctx *c, Factor &F, const std::vector<double
   d_desc.upload(L.repack);
   d_sub.upload(L.repack_sub);
   d_perm.upload(L.perm);
+  {  // shared subtree blobs: the members of such a pack must hold bitwise identical factors
+    std::vector<BlobPair> pairs;
+    const NdTree &tr = F.tree;
+    for (const SweepPackH &P : L.packs) {
+      if (!P.shared) continue;
+      const SubtreeInstance &i0 = tr.instances[L.inst_at_pos[P.pos0]];
+      const SubtreeTemplate &T = tr.templates[i0.tmpl];
+      for (int32_t m = 1; m < P.n; ++m) {
+        const SubtreeInstance &im = tr.instances[L.inst_at_pos[P.pos0 + m]];
+        pairs.push_back({i0.rf_base, im.rf_base, T.rf_size});
+        pairs.push_back({i0.rb_base, im.rb_base, T.rb_size});
+      }
+    }
+    F.shared_blob_pairs = int64_t(pairs.size());
+    if (!pairs.empty()) {
+      DevBuf<BlobPair> d_pairs;
+      DevBuf<int> d_bad;
+      d_pairs.upload(pairs);
+      d_bad.alloc(1); d_bad.zero(c->stream);
+      launch_blob_compare(d_pairs.p, int32_t(pairs.size()), F.R.p, d_bad.p, c->stream);
+      int bad = 0;
+      CUDA_CHECK(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      if (bad) fail(MMMFE_E_NUMERIC, "%d subtree factor blobs that were planned as shared differ (set option sweep_share_blobs = 0)", bad);
+    }
+  }
   launch_repack(d_desc.p, int32_t(L.repack.size()), F.R.p, F.Rs.p, c->stream);
   launch_repack_sub(d_sub.p, int32_t(L.repack_sub.size()), d_perm.p, F.R.p, F.Rs.p, c->stream);
   CUDA_CHECK(cudaGetLastError());
@@ -465,6 +493,48 @@ static void build_sweep_factor(mmmfe_ctx *c, Factor &F, const std::vector<double
   if (!F.p_identity) F.p_of_cell.upload(F.p_of_cell_h);
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   F.sweep_ok = true;
+}
+
+// Subtrees whose part of the flux matrix is bitwise identical (same shape, same entries in template-local numbering:
+// every interior box of a uniform grid with constant K) get the same class: their factor blobs are identical too
+// (same deterministic kernels on the same numbers), so a pack of them streams ONE blob.  Only entries with an
+// interior variable matter: the others are assembled above the subtree.  Verified on the device after the numeric
+// factorisation (verify_shared_blobs).
+static std::vector<int32_t> subtree_classes(const NdTree &tr, const HostCsr &S, const std::vector<int32_t> &dof_of_canon) {
+  const int64_t nxe = int64_t(tr.nx + 1) * tr.ny;
+  std::vector<int32_t> cls(tr.instances.size(), -1);
+  std::map<std::pair<int32_t, uint64_t>, int32_t> seen;
+  std::vector<int32_t> local(size_t(tr.n_flux), -1);
+  auto mix = [](uint64_t x) {
+    x += 0x9e3779b97f4a7c15ull; x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull; x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+  };
+  for (size_t k = 0; k < tr.instances.size(); ++k) {
+    const SubtreeInstance &in = tr.instances[k];
+    const SubtreeTemplate &T = tr.templates[in.tmpl];
+    auto user = [&](int32_t code) {
+      const int type = code >> 30, dj = (code >> 15) & 0x7fff, di = code & 0x7fff;
+      const int64_t canon = type == 0 ? int64_t(in.J0 + dj) * (tr.nx + 1) + in.I0 + di : nxe + int64_t(in.J0 + dj) * tr.nx + in.I0 + di;
+      return dof_of_canon.empty() ? int32_t(canon) : dof_of_canon[canon];
+    };
+    for (int32_t l = 0; l < T.n_int; ++l) local[user(T.var_code[l])] = l;
+    for (int32_t q = 0; q < T.n_rootb; ++q) local[user(T.rootb_code[q])] = T.n_int + q;
+    uint64_t sig = 0;
+    for (int32_t l = 0; l < T.n_int; ++l) {
+      const int32_t row = user(T.var_code[l]);
+      for (int64_t e = S.rp[row]; e < S.rp[row + 1]; ++e) {
+        uint64_t bits;
+        std::memcpy(&bits, &S.val[e], sizeof bits);
+        sig += mix(mix(uint64_t(l) << 32 | uint32_t(local[S.col[e]])) ^ bits);
+      }
+    }
+    for (int32_t l = 0; l < T.n_int; ++l) local[user(T.var_code[l])] = -1;
+    for (int32_t q = 0; q < T.n_rootb; ++q) local[user(T.rootb_code[q])] = -1;
+    auto it = seen.find({in.tmpl, sig});
+    if (it == seen.end()) it = seen.insert({{in.tmpl, sig}, int32_t(seen.size())}).first;
+    cls[k] = it->second;
+  }
+  return cls;
 }
 
 static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax) {
@@ -509,7 +579,9 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax) 
     {
       std::vector<int32_t> iu(tr.idx.size());
       for (size_t i = 0; i < tr.idx.size(); ++i) iu[i] = dof_of_canon.empty() ? tr.idx[i] : dof_of_canon[tr.idx[i]];
-      if (build_sweep_layout(tr, iu, dof_of_canon, F->sweep_n_cta, c->sweep_chunk, F->sweep_ct / F->sweep_ng, F->lay, F->sweep_ng, c->sweep_mt, c->sweep_pack) != nullptr) { want_sweep = false; break; }
+      std::vector<int32_t> cls;
+      if (c->sweep_share_blobs) cls = subtree_classes(tr, S, dof_of_canon);
+      if (build_sweep_layout(tr, iu, dof_of_canon, F->sweep_n_cta, c->sweep_chunk, F->sweep_ct / F->sweep_ng, F->lay, F->sweep_ng, c->sweep_mt, c->sweep_pack, cls) != nullptr) { want_sweep = false; break; }
     }
     SweepSchedule probe;
     if (build_sweep_schedule(tr, F->lay, Mmax, F->sweep_ng, F->sweep_budget, c->sweep_min_fill, probe) == nullptr) { sweep_planned = true; break; }
@@ -1253,6 +1325,7 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   }
   else if (k == "sweep_min_fill") c->sweep_min_fill = value;
   else if (k == "sweep_micro_tile") c->sweep_mt = std::max(64, int(value));
+  else if (k == "sweep_share_blobs") c->sweep_share_blobs = value != 0;
   else if (k == "sweep_pack") {
     if (value != 1 && value != 2 && value != 4) { c->err = "sweep_pack must be 1, 2 or 4"; return MMMFE_E_INVALID; }
     c->sweep_pack = int(value);
@@ -1577,6 +1650,7 @@ int64_t mmmfe_stat(const mmmfe_ctx *c, const char *key) {
   if (k == "sweep_ctas") { for (auto &b : c->batches) if (b->sweep) v = std::max<int64_t>(v, b->factor->sweep_n_cta); return v; }
   if (k == "sweep_smem_bytes") { for (auto &b : c->batches) if (b->sweep) v = std::max<int64_t>(v, int64_t(b->sweep_smem)); return v; }
   if (k == "sweep_entries") { for (auto &b : c->batches) if (b->sweep) v += int64_t(b->s_entries.n); return v; }
+  if (k == "sweep_shared_blob_pairs") { for (auto &f : c->factors) if (f->sweep_ok) v += f->shared_blob_pairs; return v; }
   if (k == "sweep_factor_bytes") { for (auto &f : c->factors) if (f->sweep_ok) v += int64_t(f->lay.bytes_per_step); return v; }
   if (k == "rt0_factors") { for (auto &f : c->factors) v += f->rt0; return v; }
   if (k == "sweep_planned") { for (auto &b : c->batches) v += b->s_entries.n > 0; return v; }
@@ -1602,7 +1676,9 @@ int mmmfe_debug_sweep_trace(mmmfe_ctx *c, int32_t batch, int64_t cap, int64_t *n
       prof.alloc(size_t(n_cta) * 24); prof.zero(c->stream);
       trace.alloc(size_t(ne) * 3); trace.zero(c->stream);
       SweepArgs a = b.sargs;
-      a.prof = prof.p; a.trace = trace.p;
+      a.prof = std::getenv("MMMFE_TRACE_WITH_PROF") ? prof.p : nullptr;  // default: stamps only, undisturbed timing
+      a.trace = trace.p;
+      a.trace_step = std::min(std::max(1, b.nt / 2), b.nt - 1);
       CUDA_CHECK(cudaMemsetAsync(b.s_ptil.p, 0, b.s_ptil.n * sizeof(double), c->stream));
       CUDA_CHECK(cudaMemsetAsync(b.s_cnt.p, 0, b.s_cnt.n * sizeof(uint32_t), c->stream));
       const cudaError_t err = launch_sweep(b.M, b.factor->sweep_ct, a, n_cta, b.sweep_smem, c->stream);

@@ -52,6 +52,25 @@ void launch_repack_sub(const RepackSub *d_desc, int32_t n_desc, const int32_t *p
   }
 }
 
+// bitwise comparison of factor ranges (shared subtree blobs must really be identical)
+__global__ void __launch_bounds__(256) k_blob_compare(const BlobPair *__restrict__ pairs, const double *__restrict__ R,
+                                                      int *__restrict__ mismatch) {
+  const BlobPair p = pairs[blockIdx.x];
+  const unsigned long long *a = reinterpret_cast<const unsigned long long *>(R + p.a);
+  const unsigned long long *b = reinterpret_cast<const unsigned long long *>(R + p.b);
+  bool bad = false;
+  for (int64_t k = threadIdx.x; k < p.n; k += blockDim.x) bad |= a[k] != b[k];
+  if (bad) atomicAdd(mismatch, 1);
+}
+
+void launch_blob_compare(const BlobPair *d_pairs, int32_t n_pairs, const double *R, int *d_mismatch, cudaStream_t st) {
+  for (int32_t off = 0; off < n_pairs; off += 1 << 20) {
+    const int32_t cnt = n_pairs - off < (1 << 20) ? n_pairs - off : (1 << 20);
+    k_blob_compare<<<cnt, 256, 0, st>>>(d_pairs + off, R, d_mismatch);
+    launch_counter_add(1);
+  }
+}
+
 // =================================================================================================================
 // device helpers
 // =================================================================================================================
@@ -459,15 +478,12 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
       const int slot = int(G % NB);
       const uint32_t parity = uint32_t((G / NB) & 1);
       long long t_entry = 0, t_w = 0, g_entry = 0, g_w = 0;
-      if (a.prof && tid == 0) {
-        t_entry = clock64();
-        if (a.trace && step == 1) g_entry = global_ns();
-      }
+      const bool tracing = a.trace && tid == 0 && step == a.trace_step;  // stamps only: no read-modify-write, no stall
+      if (tracing) g_entry = global_ns();
+      if (a.prof && tid == 0) t_entry = clock64();
       bar_wait(dep_bar + slot, parity, a.abort_flag);
-      if (a.prof && tid == 0) {
-        t_w = clock64();
-        if (a.trace && step == 1) g_w = global_ns();
-      }
+      if (tracing) g_w = global_ns();
+      if (a.prof && tid == 0) t_w = clock64();
       const SweepEntry &e = edesc[slot];
       const int kind = e.kind, flags = e.flags;
       const double *reg = ring + e.ring_off;
@@ -728,7 +744,7 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
         const double *pc = reg + e.n[0] + e.n[1] + e.n[2] + sub * ncell_e * M;
         double *wsm = ws + sub * a.ws_sub_dbl;
         if (kind == SW_SUB_FWD) {
-          const double *blob = reg + sub * rf_size;
+          const double *blob = reg + ((flags & SWF_SHARED) ? 0 : sub * rf_size);
           double *va = wsm;                  // right-hand sides of the interior variables (+ children, level by level)
           double *zl = va + T.n_int * M;     // boundary contributions of every node
           if (act)
@@ -822,7 +838,7 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
           fence_async_global();  // xi is streamed back by TMA in the backward entry
           SWEEP_PROF(13)
         } else {
-          const double *blob = reg + sub * rb_size;
+          const double *blob = reg + ((flags & SWF_SHARED) ? 0 : sub * rb_size);
           const int xb_stride = (T.n_rootb + 3) & ~3;  // int32 entries per member
           const int *xb = reinterpret_cast<const int *>(reg + e.n[0]) + sub * xb_stride;
           const double *zs = reg + e.n[0] + e.n[1] + sub * nint_e * M;  // accumulated rhs of the interior variables
@@ -932,10 +948,10 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
         const long long t_end = clock64();
         a.prof[cta * 24 + kind] += t_end - t_entry;
         a.prof[cta * 24 + 6] += 1;
-        if (a.trace && step == 1) {
-          long long *tr = a.trace + (int64_t(e_first) + i) * 3;
-          tr[0] = g_entry; tr[1] = g_w; tr[2] = global_ns();  // nanoseconds of the global timer: comparable across SMs
-        }
+      }
+      if (tracing) {
+        long long *tr = a.trace + (int64_t(e_first) + i) * 3;
+        tr[0] = g_entry; tr[1] = g_w; tr[2] = global_ns();  // nanoseconds of the global timer: comparable across SMs
       }
       __syncwarp();
       if (lane == 0) done_signal(done_cnt + slot);

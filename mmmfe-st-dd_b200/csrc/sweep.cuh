@@ -34,7 +34,8 @@ constexpr int SWEEP_MAX_ENTRIES = 8 * SWEEP_GTAB_DBL - 8;  // entries per CTA an
 enum SweepKind : int32_t { SW_SUB_FWD = 0, SW_TOP_FWD = 1, SW_TOP_BWD = 2, SW_SUB_BWD = 3 };
 // SWF_ROWS_WS: the gathered rows of a wave live in the group's workspace (not in the ring scratch); SWF_REUSE: the
 // previous wave of this CTA gathered exactly these rows and left them there
-enum SweepFlag : int32_t { SWF_FIRST = 1, SWF_LAST = 2, SWF_ROWS_WS = 4, SWF_REUSE = 8 };
+// SWF_SHARED: the members of a subtree pack have bitwise identical factor blobs; segment 0 holds one copy
+enum SweepFlag : int32_t { SWF_FIRST = 1, SWF_LAST = 2, SWF_ROWS_WS = 4, SWF_REUSE = 8, SWF_SHARED = 16 };
 enum SweepSrc : int32_t { SRC_FACTOR = 0, SRC_INDEX = 1, SRC_XI = 2, SRC_PTIL = 3 };
 
 // One unit of work of one CTA (128 bytes).  The ring region of an entry holds its streamed segments back to back
@@ -112,7 +113,8 @@ struct SweepArgs {
   uint32_t *cnt;                // completion counters (2 per sweep node: forward, backward)
   volatile int *abort_flag;     // device memory: set when a spin-wait gave up
   long long *prof;              // optional [n_cta][24] cycle counters
-  long long *trace;             // optional [entries][3] clock stamps of step 1 (start, opened, end)
+  long long *trace;             // optional [entries][3] global-timer stamps of step trace_step (start, opened, end)
+  int32_t trace_step;
   const double *minv;           // 1 / (c0 |cell|), box-major cell order; nullptr: minv_const everywhere
   double minv_const;
   // boundary entries of the batch (interface dofs; in the bar problem also outer Dirichlet dofs)
@@ -157,6 +159,10 @@ struct RepackSub {
 };
 void launch_repack_sub(const RepackSub *d_desc, int32_t n_desc, const int32_t *perm, const double *R_old, double *Rs,
                        cudaStream_t st);
+
+struct BlobPair { int64_t a, b, n; };  // ranges [a, a + n) and [b, b + n) of the factor (doubles)
+// counts the pairs that differ in any bit into *d_mismatch
+void launch_blob_compare(const BlobPair *d_pairs, int32_t n_pairs, const double *R, int *d_mismatch, cudaStream_t st);
 
 size_t sweep_smem_optin();
 // resident CTAs per SM of the sweep kernel (ct compute threads) for this much dynamic shared memory

@@ -127,7 +127,7 @@ const char *pack_template(const SubtreeTemplate &T, int32_t ct, std::vector<uint
 
 const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx_user,
                                const std::vector<int32_t> &dof_of_canon, int32_t n_cta, int32_t chunk_dbl, int32_t ct,
-                               SweepLayout &L, int32_t ng, int32_t mt_dbl, int32_t pack) {
+                               SweepLayout &L, int32_t ng, int32_t mt_dbl, int32_t pack, const std::vector<int32_t> &inst_class) {
   L = SweepLayout();
   L.n_cta = n_cta;
   L.chunk_dbl = chunk_dbl;
@@ -171,9 +171,11 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
   // allocation order (CTA, template, instance): the members of a pack are neighbours in every array
   L.inst_at_pos.resize(n_inst);
   for (int32_t k = 0; k < n_inst; ++k) L.inst_at_pos[k] = k;
+  auto class_of = [&](int32_t k) { return inst_class.empty() ? -1 : inst_class[k]; };
   std::stable_sort(L.inst_at_pos.begin(), L.inst_at_pos.end(), [&](int32_t x, int32_t y) {
     if (L.cta_of_inst[x] != L.cta_of_inst[y]) return L.cta_of_inst[x] < L.cta_of_inst[y];
-    return tr.instances[x].tmpl < tr.instances[y].tmpl;
+    if (tr.instances[x].tmpl != tr.instances[y].tmpl) return tr.instances[x].tmpl < tr.instances[y].tmpl;
+    return class_of(x) < class_of(y);
   });
   L.cell_box.assign(size_t(tr.nx) * tr.ny, -1);
   L.inst.resize(tr.instances.size());
@@ -199,10 +201,15 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
       L.index.push_back(user(canon));
     }
     while (L.index.size() % 4) L.index.push_back(0);
+    // a pack never mixes classes: either all members share one blob, or (no class information) none does
     if (L.packs.empty() || L.packs.back().n >= L.pack || L.packs.back().tmpl != in.tmpl ||
-        L.packs.back().cta != L.cta_of_inst[k])
-      L.packs.push_back({pos, 0, in.tmpl, L.cta_of_inst[k], 0});
+        L.packs.back().cta != L.cta_of_inst[k] || L.packs.back().cls != class_of(k)) {
+      SweepPackH P;
+      P.pos0 = pos; P.tmpl = in.tmpl; P.cta = L.cta_of_inst[k]; P.cls = class_of(k);
+      L.packs.push_back(P);
+    }
     L.packs.back().n += 1;
+    L.packs.back().shared = (L.packs.back().cls >= 0 && L.packs.back().n > 1) ? 1 : 0;
   }
   for (int32_t cb : L.cell_box)
     if (cb < 0) return "a cell lies outside every subtree";
@@ -487,20 +494,32 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
     if (std::max(sn.n_fwd, sn.n_bwd) >= (1 << (31 - SWEEP_DEP_SHIFT))) return "too many waves per front";
   if (2 * L.nodes.size() >= (size_t(1) << SWEEP_DEP_SHIFT)) return "too many completion counters";
   L.prod_cta = prod_cta;
-  // ---- subtree blobs: per pack the forward blobs of the members, then their backward blobs ----
+  // ---- subtree blobs: per pack the forward blobs of the members, then their backward blobs; a shared pack stores
+  // one forward and one backward blob ----
+  double logical_extra = 0;
+  std::vector<uint8_t> writes_blob(tr.instances.size(), 1);
   for (SweepPackH &P : L.packs) {
     for (int pass = 0; pass < 2; ++pass)
       for (int32_t m = 0; m < P.n; ++m) {
         const int32_t k = L.inst_at_pos[P.pos0 + m];
-        const SubtreeTemplate &T = tr.templates[tr.instances[k].tmpl];
-        if (pass == 0) { L.inst[k].rf = rs; rs += T.rf_size; }
-        else { L.inst[k].rb = rs; rs += L.rb2_size[tr.instances[k].tmpl]; }
+        const int32_t tm = tr.instances[k].tmpl;
+        const int32_t sz = pass == 0 ? tr.templates[tm].rf_size : L.rb2_size[tm];
+        if (P.shared && m > 0) {
+          const int32_t k0 = L.inst_at_pos[P.pos0];
+          (pass == 0 ? L.inst[k].rf : L.inst[k].rb) = pass == 0 ? L.inst[k0].rf : L.inst[k0].rb;
+          writes_blob[k] = 0;
+          logical_extra += 8.0 * sz;
+          continue;
+        }
+        (pass == 0 ? L.inst[k].rf : L.inst[k].rb) = rs;
+        rs += sz;
       }
     P.sig_off = int64_t(L.index.size());
     for (int32_t m = 0; m < P.n; ++m) L.index.push_back(2 * (L.n_top + L.inst_at_pos[P.pos0 + m]));
     while (L.index.size() % 4) L.index.push_back(0);
   }
   for (size_t k = 0; k < tr.instances.size(); ++k) {
+    if (!writes_blob[k]) continue;
     const SubtreeInstance &in = tr.instances[k];
     const SubtreeTemplate &T = tr.templates[in.tmpl];
     RepackSub d;
@@ -510,6 +529,7 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
   }
   L.rs_total = rs;
   L.bytes_per_step = 8.0 * double(rs);
+  L.logical_bytes_per_step = L.bytes_per_step + logical_extra;
   for (int t = 0; t < 8; ++t) L.index.push_back(0);  // the padded tail of the last list may be read
   if (L.index.size() >= (size_t(1) << 31)) return "index lists beyond 32 bits";
   return nullptr;
@@ -549,7 +569,8 @@ const char *build_sweep_schedule(const NdTree &tr, const SweepLayout &L, int32_t
     e.flags = SWF_FIRST | SWF_LAST;
     e.a0 = in.tmpl; e.a1 = -1; e.a2 = P.n; e.a7 = P.pos0;
     e.o0 = L.nodes[L.n_top + k0].zc_off; e.o1 = ih.xi_off; e.o2 = ih.pb_off;
-    e.n[0] = P.n * (fwd ? T.rf_size : L.rb2_size[in.tmpl]);
+    e.n[0] = (P.shared ? 1 : P.n) * (fwd ? T.rf_size : L.rb2_size[in.tmpl]);
+    if (P.shared) e.flags |= SWF_SHARED;
     iss.off[0] = fwd ? ih.rf : ih.rb; iss.kind[0] = SRC_FACTOR;
     if (!fwd) {
       e.n[1] = P.n * even((T.n_rootb + 1) / 2);
@@ -808,7 +829,10 @@ extern "C" int mmmfe_sweep_plan_check(int32_t nx, int32_t ny, int32_t leaf_cells
   t.build(nx, ny, leaf_cells, subtree_cells);
   mmmfe::SweepLayout L;
   const int32_t pack = std::getenv("MMMFE_PLAN_PACK") ? std::atoi(std::getenv("MMMFE_PLAN_PACK")) : 1;
-  if (const char *e = mmmfe::build_sweep_layout(t, t.idx, std::vector<int32_t>(), n_cta, chunk_dbl, ct, L, 1, 512, pack)) { say(e); return -2; }
+  std::vector<int32_t> cls;  // MMMFE_PLAN_SHARE: plan as if all subtrees of one shape had identical factors (K = I grids)
+  if (std::getenv("MMMFE_PLAN_SHARE"))
+    for (const auto &in : t.instances) cls.push_back(in.tmpl);
+  if (const char *e = mmmfe::build_sweep_layout(t, t.idx, std::vector<int32_t>(), n_cta, chunk_dbl, ct, L, 1, 512, pack, cls)) { say(e); return -2; }
   if (std::getenv("MMMFE_PLAN_DEBUG")) {
     for (int pass = 0; pass < 2; ++pass)
       for (size_t h = 0; h < L.fwd.size(); ++h) {
@@ -823,7 +847,27 @@ extern "C" int mmmfe_sweep_plan_check(int32_t nx, int32_t ny, int32_t leaf_cells
       }
   }
   mmmfe::SweepSchedule S;
-  if (const char *e = mmmfe::build_sweep_schedule(t, L, M, 1, size_t(smem_bytes), 2.0, S)) { say(e); return -3; }
+  if (const char *e = mmmfe::build_sweep_schedule(t, L, M, 1, size_t(smem_bytes), std::getenv("MMMFE_PLAN_FILL") ? std::atof(std::getenv("MMMFE_PLAN_FILL")) : 2.0, S)) { say(e); return -3; }
+  if (const char *path = std::getenv("MMMFE_PLAN_DUMP")) {  // per entry, CTA-major: features for cost modelling
+    if (FILE *f = std::fopen(path, "w")) {
+      for (int32_t c = 0; c < n_cta; ++c)
+        for (int32_t i = S.cta_begin[c]; i < S.cta_begin[c + 1]; ++i) {
+          const mmmfe::SweepEntry &e = S.entries[size_t(i)];
+          const bool wave = e.kind == mmmfe::SW_TOP_FWD || e.kind == mmmfe::SW_TOP_BWD;
+          int32_t max_load = 0, n_w = 8;
+          if (wave) {  // largest per-warp micro-tile load (doubles), warps deal m = w, w + 8, ...
+            std::vector<int32_t> load(n_w, 0);
+            const int32_t *ix = L.index.data() + 2 * S.issue[size_t(i)].off[0];
+            const mmmfe::SweepMt *mts = reinterpret_cast<const mmmfe::SweepMt *>(ix + e.a5);
+            for (int32_t m = 0; m < e.a1; ++m) load[m % n_w] += mts[m].nrows * mts[m].ncols;
+            max_load = *std::max_element(load.begin(), load.end());
+          }
+          std::fprintf(f, "%d %d %d %d %d %d %d %d %d %d %d\n", c, e.kind, wave ? e.a7 : 0, e.flags, wave ? e.a0 : 0,
+                       wave ? e.a1 : 0, wave ? e.a2 : 0, wave ? e.a3 : 0, e.n[1], max_load, e.n_dep);
+        }
+      std::fclose(f);
+    }
+  }
   if (stats) {
     stats[0] = int64_t(L.nodes.size()); stats[1] = L.n_top; stats[2] = int64_t(S.entries.size()); stats[3] = L.rs_total;
     stats[4] = S.ring_dbl; stats[5] = S.ws_dbl; stats[6] = S.entry_max; stats[7] = int64_t(S.smem_bytes);

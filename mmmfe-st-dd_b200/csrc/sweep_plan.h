@@ -35,6 +35,7 @@ struct SweepWaveH {       // one wave: the work of ONE CTA at one tree level and
 
 struct SweepPackH {       // up to SweepLayout::pack subtrees of one template that one CTA walks in lockstep
   int32_t pos0 = 0, n = 0, tmpl = 0, cta = 0;
+  int32_t cls = -1, shared = 0;  // shared: all members have bitwise identical blobs, stored and streamed once
   int64_t sig_off = 0;    // forward completion counters of the members (index array, int32 units)
 };
 
@@ -73,6 +74,7 @@ struct SweepLayout {
   int32_t tmpl16_max = 0;                        // uint16 words of the largest template
   int32_t sub_ws_max = 0;                        // vector workspace entries (per right-hand side) of a subtree entry
   double bytes_per_step = 0;                     // factor bytes one step streams (with block padding)
+  double logical_bytes_per_step = 0;             // the same with every shared subtree blob counted per member
 };
 
 struct SweepSchedule {
@@ -90,7 +92,8 @@ struct SweepSchedule {
 // boxes wider than 127 cells, template fields beyond 16 bits.
 const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx_user,
                                const std::vector<int32_t> &dof_of_canon, int32_t n_cta, int32_t chunk_dbl, int32_t ct,
-                               SweepLayout &L, int32_t ng = 1, int32_t mt_dbl = 512, int32_t pack = 1);
+                               SweepLayout &L, int32_t ng = 1, int32_t mt_dbl = 512, int32_t pack = 1,
+                               const std::vector<int32_t> &inst_class = std::vector<int32_t>());
 
 // Shared-memory partition for M right-hand sides within smem_budget bytes per CTA, entry lists and ring schedule.
 // Returns nullptr on success; a message when the ring cannot hold max(2, min_fill) of the largest entries.

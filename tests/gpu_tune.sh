@@ -33,6 +33,11 @@ for cfg in "$@"; do
     p4) run p4 MMMFE_SWEEP_PACK=4 ;;
     p4s64) run p4s64 MMMFE_SWEEP_PACK=4 MMMFE_SUBTREE_CELLS=64 ;;
     p2s64) run p2s64 MMMFE_SWEEP_PACK=2 MMMFE_SUBTREE_CELLS=64 ;;
+    p4k6) run p4k6 MMMFE_SWEEP_PACK=4 MMMFE_SWEEP_CHUNK=6144 ;;
+    p2k6) run p2k6 MMMFE_SWEEP_PACK=2 MMMFE_SWEEP_CHUNK=6144 ;;
+    p4s256) run p4s256 MMMFE_SWEEP_PACK=4 MMMFE_SUBTREE_CELLS=256 ;;
+    p4s256k6) run p4s256k6 MMMFE_SWEEP_PACK=4 MMMFE_SUBTREE_CELLS=256 MMMFE_SWEEP_CHUNK=6144 ;;
+    p2ns) run p2ns MMMFE_SWEEP_PACK=2 MMMFE_SWEEP_SHARE_BLOBS=0 ;;
     s64) run s64 MMMFE_SUBTREE_CELLS=64 ;;
     s256) run s256 MMMFE_SUBTREE_CELLS=256 ;;
   esac

@@ -123,6 +123,24 @@ def test_sweep_kernel_subtree_packs_match_oracle(nxs, nts, mortar, k, cells, pac
     eng.close()
 
 
+def test_shared_subtree_blobs_change_nothing():
+    """Same-shape interior subtrees of a uniform K = I grid have bitwise identical factor blobs: a pack streams one
+    copy (verified on the device at set-up).  The operator must be bitwise the same with the sharing switched off."""
+    prob = _two_by_two((96, 48, 48, 96), (8, 4, 4, 8), [12, 12, 2], 1)
+    q = np.random.default_rng(28).standard_normal(prob.n_iface)
+    outs = {}
+    for share in (1, 0):
+        eng = engine_from_oracle(prob, options={"use_sweep": 1, "subtree_cells": 32, "sweep_autotune": 0, "sweep_pack": 4,
+                                                "sweep_share_blobs": share})
+        eng.setup()
+        assert eng.stat("sweep_batches") == eng.stat("batches")
+        assert (eng.stat("sweep_shared_blob_pairs") > 0) == bool(share)
+        outs[share] = eng.apply(q)
+        eng.close()
+    assert np.array_equal(outs[0], outs[1])
+    assert rel_l2(outs[1], prob.apply_S(q)) < TOL
+
+
 def test_persistent_sweep_kernel_with_permuted_dofs():
     prm = default_params(1, 2)
     prob = make_problem(prm, 1)
