@@ -105,6 +105,10 @@ struct Sub {
   Csr matrix, f2c[4], c2f[4];
   int mortar_len[4] = {0, 0, 0, 0};
   int local = -1;
+  // essential (Neumann) conditions of the outer boundary, constraint_bc of src/darcy_vtdd.cc:205-275
+  std::vector<int> con_dofs;
+  std::vector<double> con_vals, con_diag;
+  std::vector<std::pair<int, double>> rhs_bc;  // system_rhs_bar_bc (:479): row, value
   std::vector<double> solution;  // [nt][n] after the final sweep
   std::vector<double> levels_t;  // accumulated times t += dt
 };
@@ -191,6 +195,52 @@ void assemble_matrix(Sub &s, double c0) {
   }
 }
 
+int side_to_bc(int side);
+
+// constraint_bc (src/darcy_vtdd.cc:205-275) applied the way distribute_local_to_global does at :479.  Without a
+// manufactured solution the normal flux on every outer side marked 'N' is essential: u.n = bc_const_functs[left,
+// bottom, right, top] (:228-231 -- index 3 for the top, unlike the Dirichlet data of :673).  A flux dof is the flux
+// through its edge in the positive coordinate direction, so the constrained value is normal * g * |e|.  Constrained
+// rows and columns leave the matrix, the diagonal keeps |a_ii| (an outer edge belongs to one cell: local and global
+// diagonal agree), every other row j receives -a_ji g_i in system_rhs_bar_bc.
+void constrain_matrix(Sub &s, bool manufact, const std::vector<char> &bc_type, const std::vector<double> &bc_val) {
+  s.con_dofs.clear(); s.con_vals.clear(); s.con_diag.clear(); s.rhs_bc.clear();
+  if (manufact) return;  // :210, 271-273: all outer sides are Dirichlet
+  std::vector<double> g(s.n, 0.0);
+  std::vector<char> is_con(s.n, 0);
+  for (int side = 0; side < 4; ++side) {
+    if (s.nb[side] >= 0 || bc_type[side_to_bc(side)] != 'N') continue;
+    const double v = kNormal[side] * bc_val[side_to_bc(side)] * s.edge_len[side];
+    for (int m = 0; m < s.n_side[side]; ++m) {
+      const int d = s.side_edges[side][m];
+      s.con_dofs.push_back(d); s.con_vals.push_back(v);
+      g[d] = v; is_con[d] = 1;
+    }
+  }
+  if (s.con_dofs.empty()) return;
+  Csr &m = s.matrix, out;
+  out.n_rows = out.n_cols = m.n_rows;
+  out.rp.assign(size_t(s.n) + 1, 0);
+  out.col.reserve(m.col.size()); out.val.reserve(m.val.size());
+  std::vector<double> diag(s.n, 0.0);
+  for (int r = 0; r < s.n; ++r) {
+    double bc = 0.0;
+    bool touched = false;
+    for (long long k = m.rp[r]; k < m.rp[r + 1]; ++k) {
+      const int c = m.col[k];
+      if (c == r) diag[r] = m.val[k];
+      if (is_con[r]) continue;
+      if (is_con[c]) { bc -= m.val[k] * g[c]; touched = true; continue; }
+      out.col.push_back(c); out.val.push_back(m.val[k]);
+    }
+    if (is_con[r]) { out.col.push_back(r); out.val.push_back(std::fabs(diag[r])); }
+    else if (touched && bc != 0.0) s.rhs_bc.push_back({r, bc});
+    out.rp[r + 1] = (long long)out.col.size();
+  }
+  for (int d : s.con_dofs) s.con_diag.push_back(std::fabs(diag[d]));
+  m = std::move(out);
+}
+
 // cell index of a coordinate given in units of cells; ties go to the lower cell / earlier level (quirk Q5)
 int locate(double u, int n) {
   const double r = std::nearbyint(u);
@@ -268,7 +318,7 @@ void side_point(const Sub &s, int side, int m, double xi, double &x, double &y) 
   else { y = s.y0 + (m + xi) * s.hy; x = (side == LEFT) ? s.x0 : s.x0 + s.Lx; }
 }
 
-int side_to_bc(int side) { return side == LEFT ? 0 : side == BOTTOM ? 1 : side == RIGHT ? 2 : 3; }
+int side_to_bc(int side) { return side == LEFT ? 0 : side == BOTTOM ? 1 : side == RIGHT ? 2 : 3; }  // :215-217
 
 struct BarData {
   std::vector<double> p0, src, fr_vals;
@@ -319,16 +369,36 @@ void bar_data(const Sub &s, int qdegree, bool manufact, const std::vector<char> 
   std::vector<int> fr_side;
   for (int side = 0; side < 4; ++side) {
     if (s.nb[side] >= 0) continue;
-    if (!manufact && bc_type[side_to_bc(side)] != 'D') continue;  // Neumann sides: essential, see DESIGN.md
+    if (!manufact && bc_type[side_to_bc(side)] != 'D') continue;  // Neumann sides are essential: constrain_matrix
     for (int m = 0; m < s.n_side[side]; ++m) { out.fr_dofs.push_back(s.side_edges[side][m]); fr_side.push_back(side * (1 << 24) + m); }
+  }
+  // system_rhs_bar.sadd(1.0, system_rhs_bar_bc) (:863), every level.  Pressure rows go into the source, flux rows
+  // into the sparse flux data; the constrained rows themselves get |a_ii| g_i so that the solve returns g_i (the
+  // reference solves with 0 there and calls constraint_bc.distribute afterwards, :866 -- same solution).
+  const int n_dir = int(out.fr_dofs.size());
+  std::vector<std::pair<int, double>> extra;  // flux row -> constant right-hand-side value
+  for (const auto &rv : s.rhs_bc) {
+    if (rv.first >= s.nf) {
+      for (int lvl = 0; lvl < s.nt; ++lvl) out.src[size_t(lvl) * s.np + (rv.first - s.nf)] += rv.second;
+    } else extra.push_back(rv);
+  }
+  for (size_t k = 0; k < s.con_dofs.size(); ++k) extra.push_back({s.con_dofs[k], s.con_diag[k] * s.con_vals[k]});
+  std::vector<int> extra_slot(extra.size());
+  for (size_t k = 0; k < extra.size(); ++k) {  // the device adds fr entries without atomics: one entry per dof
+    int slot = -1;
+    for (int e = 0; e < int(out.fr_dofs.size()); ++e) if (out.fr_dofs[e] == extra[k].first) { slot = e; break; }
+    if (slot < 0) { slot = int(out.fr_dofs.size()); out.fr_dofs.push_back(extra[k].first); fr_side.push_back(-1); }
+    extra_slot[k] = slot;
   }
   const int nfr = int(out.fr_dofs.size());
   out.fr_vals.assign(size_t(s.nt) * nfr, 0.0);
+  for (int lvl = 0; lvl < s.nt; ++lvl)
+    for (size_t k = 0; k < extra.size(); ++k) out.fr_vals[size_t(lvl) * nfr + extra_slot[k]] += extra[k].second;
 #pragma omp parallel for schedule(static)
   for (int lvl = 0; lvl < s.nt; ++lvl) {
     PressureBoundaryValues<2> gfun;
     gfun.set_time(s.levels_t[lvl]);
-    for (int e = 0; e < nfr; ++e) {
+    for (int e = 0; e < n_dir; ++e) {
       const int side = fr_side[e] >> 24, m = fr_side[e] & ((1 << 24) - 1);
       double acc = 0;
       for (int q = 0; q < qdegree; ++q) {
@@ -339,7 +409,7 @@ void bar_data(const Sub &s, int qdegree, bool manufact, const std::vector<char> 
         else gv = (side == TOP) ? bc_val[1] : bc_val[side_to_bc(side)];  // the reference reads [1] for the top (:673)
         acc += wq[q] * gv;
       }
-      out.fr_vals[size_t(lvl) * nfr + e] = -kNormal[side] * acc;  // :748-751
+      out.fr_vals[size_t(lvl) * nfr + e] += -kNormal[side] * acc;  // :748-751
     }
   }
 }
@@ -575,6 +645,7 @@ void dump_subdomain(const std::vector<std::vector<int>> &reps, int r, double fin
   Sub s;
   init_sub(s, r, int(n0), int(n1), reps[r], final_time);
   assemble_matrix(s, c0);
+  constrain_matrix(s, manufact, bc_type, bc_val);
   auto wr = [&](const std::string &name, const void *p, size_t bytes) {
     std::ofstream f(dir + "/" + name, std::ios::binary);
     f.write(static_cast<const char *>(p), std::streamsize(bytes));
@@ -661,6 +732,7 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
     for (int li = 0; li < int(subs.size()); ++li) {
       Sub &s = *subs[li];
       assemble_matrix(s, prm.c_0);
+      constrain_matrix(s, is_manufact_solution, bc_condition_vect, bc_const_functs);
       for (int side = 0; side < 4; ++side)
         if (s.nb[side] >= 0) projector_tables(s, side, mortar, int(mortar_degree));
     }
@@ -798,6 +870,8 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
       for (auto &sp : subs) {
         sp->solution.resize(size_t(sp->nt) * sp->n);
         check(ctx, mmmfe_get_solution(ctx, sp->local, sp->solution.data()), "mmmfe_get_solution");
+        for (int lvl = 0; lvl < sp->nt; ++lvl)  // constraint_bc.distribute (:866): the essential values, exactly
+          for (size_t k = 0; k < sp->con_dofs.size(); ++k) sp->solution[size_t(lvl) * sp->n + sp->con_dofs[k]] = sp->con_vals[k];
       }
       rep.t_final = since(t0);
       if (say) std::cout << "finished local_gmres" << "\n";

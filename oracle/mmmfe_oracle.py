@@ -296,13 +296,58 @@ class Subdomain:
         mat.sum_duplicates()
         return mat
 
-    def factorize(self, ordering="colamd"):
+    def neumann_constraints(self, prm: "Params"):
+        """constraint_bc of make_grid_and_dofs, src/darcy_vtdd.cc:205-275: with is_manufact_soln = 0 the normal
+        flux on every outer side marked 'N' is an essential condition u.n = bc_const_functs[left, bottom, right,
+        top] (:228-231; the top side reads index 3 here, unlike the Dirichlet data of :673).  A flux dof is the
+        flux through its edge in the positive direction, so the constrained value is sign * g * |e|.
+        Returns (dofs, values)."""
+        dofs, vals = [], []
+        if prm.is_manufact:  # :210, all outer sides are Dirichlet (:271-273)
+            return np.zeros(0, dtype=np.int64), np.zeros(0)
+        for side in range(4):
+            if self.neighbors[side] >= 0 or prm.bc_type[_side_to_bc(side)] != "N":
+                continue
+            g = prm.bc_value[_side_to_bc(side)]
+            dofs.append(np.asarray(self.side_edges[side], dtype=np.int64))
+            vals.append(np.full(self.n_side[side], NORMAL_SIGN[side] * g * self.edge_len[side]))
+        if not dofs:
+            return np.zeros(0, dtype=np.int64), np.zeros(0)
+        return np.concatenate(dofs), np.concatenate(vals)
+
+    def constrain(self, mat, prm: "Params"):
+        """AffineConstraints::distribute_local_to_global as called at src/darcy_vtdd.cc:479: constrained rows and
+        columns are dropped, the diagonal keeps |a_ii| (an outer edge belongs to one cell, so the local and the
+        global diagonal agree), and the other rows receive -a_ji g_i in system_rhs_bar_bc.  The right-hand side of
+        a constrained row stays 0 (use_inhomogeneities_for_rhs defaults to false); constraint_bc.distribute sets
+        the value after the bar solve (:866).  Returns (constrained matrix, rhs_bc)."""
+        dofs, vals = self.neumann_constraints(prm)
+        self.con_dofs, self.con_vals = dofs, vals
+        if dofs.size == 0:
+            return mat, np.zeros(self.n)
+        g = np.zeros(self.n)
+        g[dofs] = vals
+        rhs_bc = -(mat @ g)
+        rhs_bc[dofs] = 0.0
+        keep = np.ones(self.n)
+        keep[dofs] = 0.0
+        diag = np.abs(mat.diagonal())
+        kd = sp.diags(keep)
+        out = (kd @ mat @ kd + sp.diags((1.0 - keep) * diag)).tocsc()
+        out.eliminate_zeros()
+        return out, rhs_bc
+
+    def factorize(self, ordering="colamd", prm: "Params" = None):
         """A_direct.initialize, src/darcy_vtdd.cc:483 (UMFPACK there, SuperLU here).
 
         ordering="nd": geometric nested-dissection column order (fill ~ n log n; what makes the large
         CPU-baseline cases fit) instead of SuperLU's COLAMD.
         """
         self.matrix = self.assemble_matrix()
+        self.rhs_bc = np.zeros(self.n)
+        self.con_dofs, self.con_vals = np.zeros(0, dtype=np.int64), np.zeros(0)
+        if prm is not None:
+            self.matrix, self.rhs_bc = self.constrain(self.matrix, prm)
         if ordering == "nd":
             perm = nested_dissection_order(self.nx, self.ny)
             self.lu = _PermutedLU(self.matrix, perm)
@@ -344,7 +389,8 @@ class Subdomain:
                     continue
                 gval = np.full_like(x, _dirichlet_constant(prm, side))
             rhs[self.side_edges[side]] += -NORMAL_SIGN[side] * (gval @ wg)  # :748-751
-        return rhs
+        rhs[getattr(self, "con_dofs", [])] = 0.0  # constrained rows drop their local right-hand side (:764)
+        return rhs + getattr(self, "rhs_bc", 0.0)  # system_rhs_bar.sadd(1.0, system_rhs_bar_bc), :863
 
     def rhs_star(self, lam_bar, p_old, first):
         """assemble_rhs_star, src/darcy_vtdd.cc:769-855.  lam_bar[side] = (2-D interface dof)/|e|."""
@@ -354,6 +400,7 @@ class Subdomain:
         for side in range(4):
             if self.neighbors[side] >= 0:
                 rhs[self.side_edges[side]] += -NORMAL_SIGN[side] * lam_bar[side]  # :840-844
+        rhs[getattr(self, "con_dofs", [])] = 0.0  # :853
         return rhs
 
 
@@ -550,7 +597,7 @@ class Problem:
 
     def setup(self):
         for sd in self.subs:
-            sd.factorize()
+            sd.factorize(prm=self.prm)
             sd.f2c, sd.c2f = {}, {}
             for side in range(4):
                 if sd.neighbors[side] >= 0:
@@ -567,6 +614,7 @@ class Problem:
             for lvl in range(sd.nt):
                 t += sd.dt
                 x = sd.lu.solve(sd.rhs_bar(t, p_old, self.qdegree, self.prm))
+                x[sd.con_dofs] = sd.con_vals  # constraint_bc.distribute(solution_bar), :866
                 sd.bar_solution[lvl] = x
                 p_old = x[sd.nf:]
                 for s in sd.bar_trace:

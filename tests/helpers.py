@@ -39,11 +39,20 @@ def bar_data(prob, sd):
     src = np.zeros((sd.nt, sd.np))
     outer = [s for s in range(4) if sd.neighbors[s] < 0]
     fr_dofs = np.concatenate([sd.side_edges[s] for s in outer]) if outer else np.zeros(0, dtype=np.int64)
+    con = np.asarray(getattr(sd, "con_dofs", []), dtype=np.int64)
+    if con.size:
+        # essential (Neumann) sides: also the rows that receive system_rhs_bar_bc, and the constrained rows
+        # themselves, which get |a_ii| g_i so that the solve returns g_i (constraint_bc.distribute, :866)
+        extra = np.nonzero(sd.rhs_bc[:sd.nf])[0]
+        fr_dofs = np.unique(np.concatenate([np.setdiff1d(fr_dofs, con), extra, con])).astype(np.int64)
     fr_vals = np.zeros((sd.nt, len(fr_dofs)))
+    diag = sd.matrix.diagonal()
     t = 0.0
     for lvl in range(sd.nt):
         t += sd.dt
         rhs = sd.rhs_bar(t, zero, prob.qdegree, prob.prm)
+        if con.size:
+            rhs[con] = diag[con] * sd.con_vals
         src[lvl] = rhs[sd.nf:]
         fr_vals[lvl] = rhs[fr_dofs]
     return sd.project_initial_condition(), src, fr_dofs, fr_vals

@@ -66,6 +66,19 @@ def test_medium_nonmatching_grids_match_oracle(tmp_path):
     assert r["factor_groups"] == 2
 
 
+def test_non_manufactured_run_with_neumann_sides_matches_oracle(tmp_path):
+    """parameter.txt with is_manufact_soln = 0, left/top essential (N), bottom/right Dirichlet constants."""
+    mesh, mortar = [[12, 12, 6], [8, 8, 4], [16, 16, 8], [12, 12, 6]], [4, 4, 2]
+    p = pkg().write_parameter_file(str(tmp_path / "parameter.txt"), mesh, mortar, is_manufact=0,
+                                   bc=("N 0.5", "D 1.0", "D 2.0", "N -0.25"))
+    reps, res, lam = pkg().host_run(p, verbose=0, write_output=0)
+    o = mo.run(mo.parse_parameter_file(p))[0]
+    assert reps[0]["gmres_iterations"] == o.gmres_iterations
+    assert reps[0]["r_norm"] == pytest.approx(o.r_norm, rel=1e-12)
+    np.testing.assert_allclose(res, o.residuals, rtol=1e-6, atol=1e-13)
+    assert rel_l2(lam, o.lam) < 1e-10
+
+
 def test_darcyvt_executable_is_a_drop_in(tmp_path):
     """Run from a directory holding parameter.txt and the two plot directories, like the reference (README:64)."""
     exe = os.path.join(ROOT, "DarcyVT")

@@ -195,6 +195,37 @@ def test_full_solve_matches_oracle(k, cycle, perm):
     eng.close()
 
 
+@pytest.mark.parametrize("bc_type,bc_value", [(["N", "D", "D", "N"], [0.5, 1.0, 2.0, -0.25]),
+                                              (["D", "N", "N", "D"], [1.0, 0.0, 1.5, 0.0])])
+def test_full_solve_with_essential_neumann_sides(bc_type, bc_value):
+    """is_manufact_soln = 0: outer sides marked N are essential flux conditions (src/darcy_vtdd.cc:205-275, 479,
+    863-866).  The constrained saddle matrix crosses the C ABI as assemble_system builds it; p, u and lambda
+    match the oracle, and the constrained fluxes are reproduced."""
+    prm = default_params(1, 2)
+    prm.is_manufact, prm.bc_type, prm.bc_value = False, bc_type, bc_value
+    prob = make_problem(prm, 1)
+    ref = prob.run_cycle(1)
+    eng = engine_from_oracle(prob)
+    eng.setup()
+    set_bar_data(eng, prob)
+    eng.bar_sweep()
+    out = eng.gmres(prm.tolerance, prm.max_iteration)
+    assert out["iterations"] == ref.gmres_iterations
+    assert out["r_norm"] == pytest.approx(ref.r_norm, rel=1e-12)
+    assert rel_l2(out["lam"], ref.lam) < TOL
+    eng.final_sweep()
+    n_con = 0
+    for li, sd in enumerate(prob.subs):
+        sol = eng.get_solution(li)
+        assert rel_l2(sol[:, sd.nf:], ref.solution_p[li]) < TOL
+        assert rel_l2(sol[:, :sd.nf], ref.solution_u[li]) < TOL
+        if len(sd.con_dofs):
+            np.testing.assert_allclose(sol[:, sd.con_dofs], np.tile(sd.con_vals, (sd.nt, 1)), rtol=1e-13, atol=1e-15)
+            n_con += len(sd.con_dofs)
+    assert n_con > 0
+    eng.close()
+
+
 def test_checkerboard_4x4_nonmatching_space_time():
     """4x4 subdomains, checkerboard fine/coarse in space and time (BASELINE config 3 scaled down)."""
     prm = default_params(1)
