@@ -1,0 +1,83 @@
+"""Multi-GPU parity check of the product path (one process per GPU, NCCL face exchange + allreduce).
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+      tests/gpu_multirank_check.py [out.json]
+
+Every rank runs the DarcyVT front-end on the same parameter files with (rank, world); rank 0 compares GMRES
+iteration counts, r_norm, the residual history and the mortar solution with the oracle (src/darcy_vtdd.cc:1139-1563
+run as `mpirun -n j DarcyVT`, one rank per subdomain; here the subdomains are sharded over N GPUs).
+"""
+import ctypes
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from helpers import ROOT, mo, pkg, rel_l2
+
+
+def unique_id(rank):
+    lib = pkg().load_engine()
+    n = lib.mmmfe_comm_unique_id_size()
+    buf = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        raw = ctypes.create_string_buffer(n)
+        assert lib.mmmfe_comm_unique_id(ctypes.cast(raw, ctypes.c_void_p)) == 0
+        buf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tmp = tempfile.mkdtemp(prefix="mmmfe_mr_")
+    cases = {
+        "default_2x2": dict(file=os.path.join(ROOT, "parameter.txt"), kw=dict(num_refinement=2)),
+        "checker_4x4": dict(mesh=[[12, 12, 6] if ((r % 4) + (r // 4)) % 2 == 0 else [6, 6, 3] for r in range(16)],
+                            mortar=[3, 3, 2], kw={}),
+        "nonmatching_2x2_sweep": dict(mesh=[[64, 64, 16], [32, 32, 8], [32, 32, 8], [64, 64, 16]], mortar=[16, 16, 4], kw={}),
+    }
+    results, ok = {}, True
+    for name, c in cases.items():
+        if "file" in c:
+            pfile = c["file"]
+        else:
+            pfile = os.path.join(tmp, f"{name}_{rank}.txt")
+            pkg().write_parameter_file(pfile, c["mesh"], c["mortar"])
+        nccl_id = unique_id(rank)
+        reps, res, lam = pkg().host_run(pfile, nccl_id=nccl_id, rank=rank, world=world, device=local, verbose=0,
+                                        write_output=0, **c["kw"])
+        dist.barrier()
+        if rank != 0:
+            continue
+        prm = mo.parse_parameter_file(pfile)
+        if "num_refinement" in c["kw"]:
+            prm.num_refinement = c["kw"]["num_refinement"]
+        ref = mo.run(prm)
+        r, o = reps[-1], ref[-1]
+        tol_lam = 1e-10 if o.gmres_iterations < 60 else 5 * prm.tolerance
+        entry = {"world": world, "iterations": r["gmres_iterations"], "oracle_iterations": o.gmres_iterations,
+                 "r_norm_rel": abs(r["r_norm"] - o.r_norm) / o.r_norm, "lambda_rel_l2": rel_l2(lam, o.lam),
+                 "errors_rel": max(abs(r[k] - o.errors[k]) / o.errors[k] for k in o.errors) if o.errors else None,
+                 "sweep_batches": r.get("sweep_batches")}
+        entry["ok"] = bool(abs(entry["iterations"] - entry["oracle_iterations"]) <= 1 and entry["r_norm_rel"] < 1e-11
+                           and entry["lambda_rel_l2"] < tol_lam)
+        ok = ok and entry["ok"]
+        results[name] = entry
+        print(name, json.dumps(entry), flush=True)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    if rank == 0 and len(sys.argv) > 1:
+        json.dump(results, open(sys.argv[1], "w"), indent=1)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag[0]) else 1)
+
+
+if __name__ == "__main__":
+    main()

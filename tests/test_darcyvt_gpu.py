@@ -111,3 +111,19 @@ def test_missing_parameter_file_is_an_error(tmp_path):
         pytest.skip("DarcyVT not built")
     out = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=60)
     assert out.returncode == 1 and "Exception on processing" in out.stderr
+
+
+def test_two_gpus_reproduce_the_oracle(tmp_path):
+    """Subdomains sharded over 2 GPUs (NCCL face exchange + allreduce): tests/gpu_multirank_check.py
+    under torchrun.  Needs a box with at least two GPUs."""
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = tmp_path / "multirank.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29531", os.path.join(ROOT, "tests", "gpu_multirank_check.py"), str(out)]
+    run = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=os.path.join(ROOT, "tests"))
+    assert run.returncode == 0, run.stdout[-2000:] + run.stderr[-2000:]
+    res = json.load(open(out))
+    assert all(v["ok"] for v in res.values()) and len(res) == 3

@@ -247,6 +247,24 @@ def test_checkerboard_4x4_nonmatching_space_time():
     eng.close()
 
 
+def test_checkerboard_8x8_quadratic_mortar():
+    """8x8 subdomains, checkerboard fine/coarse grids with twice as many time steps as cells per direction, mortar
+    degree 2 (BASELINE config 4 scaled down; every mortar-face centre Gauss point is a tie, quirk Q5)."""
+    prm = default_params(2)
+    mesh = []
+    for r in range(64):
+        fine = ((r % 8) + (r // 8)) % 2 == 0
+        mesh.append([8, 8, 16] if fine else [4, 4, 8])
+    prob = make_problem(prm, n_sub=64, mesh=mesh, mortar=[2, 2, 4])
+    eng = engine_from_oracle(prob)
+    eng.setup()
+    assert eng.stats()["factor_groups"] == 2
+    assert prob.n_iface == 2 * 112 * 2 * 4 * 9
+    q = np.random.default_rng(8).standard_normal(prob.n_iface)
+    assert rel_l2(eng.apply(q), prob.apply_S(q)) < TOL
+    eng.close()
+
+
 def test_errors_are_reported_not_swallowed():
     prm = default_params()
     prm.c0 = 0.0
