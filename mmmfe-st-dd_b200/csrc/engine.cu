@@ -117,6 +117,8 @@ struct Factor {
   bool p_identity = true;
   SweepLayout lay;
   int32_t sweep_n_cta = 0, sweep_ct = 128, sweep_ng = 1;
+  double sm_share = 1.0;              // fraction of the SMs the sweep kernels of this factor run on
+  cudaStream_t sweep_stream = nullptr;  // concurrent mode: all sweep launches of this factor, in order
   int64_t shared_blob_pairs = 0;
   size_t sweep_budget = 0;
   DevBuf<double> Rs, minv_c;
@@ -183,6 +185,9 @@ struct mmmfe_ctx {
   double sweep_min_fill = 1.75;
   int sweep_mt = 512, sweep_pack = 2;
   bool sweep_share_blobs = true;
+  // 1: the persistent kernels of different factors run CONCURRENTLY, each on its own share of the SMs (proportional
+  // to nt * factor bytes of its batches); 0: one after the other on all SMs
+  bool sweep_concurrent = false;
   int sweep_spin_ns = 100;
   bool is_setup = false, bar_done = false, final_done = false;
   int rank = 0, world = 1;
@@ -418,7 +423,7 @@ static bool detect_rt0(const Sub &sd, const HostCsr &kup, const HostCsr &kpu, co
 }
 
 // resident sweep CTAs per SM and the dynamic shared memory each may use
-static void sweep_geometry(int device, int M, int ct, int want_per_sm, int32_t &n_cta, size_t &budget) {
+static void sweep_geometry(int device, int M, int ct, int want_per_sm, double sm_share, int32_t &n_cta, size_t &budget) {
   int sms = 0, per_sm = 0, reserved = 0, optin = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
@@ -430,7 +435,7 @@ static void sweep_geometry(int device, int M, int ct, int want_per_sm, int32_t &
     if (sweep_ctas_per_sm(M, ct, budget) >= per) break;
   }
   per = std::max(per, 1);
-  n_cta = per * sms;
+  n_cta = per * std::max(1, std::min(sms, int(std::lround(sm_share * sms))));
 }
 
 // Factor in streaming order + the device copies of the layout tables (after the numeric factorisation).
@@ -537,9 +542,10 @@ static std::vector<int32_t> subtree_classes(const NdTree &tr, const HostCsr &S, 
   return cls;
 }
 
-static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax) {
+static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax, double sm_share) {
   const auto t0 = std::chrono::steady_clock::now();
   auto F = std::make_shared<Factor>();
+  F->sm_share = sm_share;
   F->nx = sd.nx; F->ny = sd.ny; F->nf = sd.nf; F->np = sd.np;
   HostCsr S, kup, kpu;
   std::vector<double> minv;
@@ -562,7 +568,7 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax) 
   bool want_sweep = c->use_sweep && F->rt0 && c->subtree_cells > 0;
   F->sweep_ct = c->sweep_ct;
   F->sweep_ng = (c->sweep_ct / c->sweep_groups >= 32) ? c->sweep_groups : 1;
-  if (want_sweep) sweep_geometry(c->device, Mmax, F->sweep_ct, c->sweep_ctas_per_sm, F->sweep_n_cta, F->sweep_budget);
+  if (want_sweep) sweep_geometry(c->device, Mmax, F->sweep_ct, c->sweep_ctas_per_sm, sm_share, F->sweep_n_cta, F->sweep_budget);
   bool sweep_planned = false;
   for (int cells = c->subtree_cells;; cells /= 2) {  // largest subtrees whose factor blob + vectors fit on chip twice per SM
     tr.build(sd.nx, sd.ny, c->leaf_cells, cells);
@@ -782,7 +788,7 @@ enum SweepMode { SWEEP_BAR, SWEEP_STAR, SWEEP_FINAL };
 static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> &iface_q,
                              const std::vector<int64_t> &tr_base, const std::vector<int32_t> &tr_stride,
                              const std::vector<double> &tr_sign);
-static void run_sweep_kernel(mmmfe_ctx *c, Batch &b);
+static void run_sweep_kernel(mmmfe_ctx *c, Batch &b, cudaStream_t st);
 
 static void enqueue_sweep(mmmfe_ctx *c, Batch &b, SweepMode mode) {
   const Factor &F = *b.factor;
@@ -808,8 +814,17 @@ static void run_star_sweeps(mmmfe_ctx *c, SweepMode mode) {
   CUDA_CHECK(cudaEventRecord(c->ev_start, c->stream));
   for (auto &bp : c->batches) {
     Batch &b = *bp;
-    if (mode == SWEEP_STAR && b.sweep) {  // persistent kernels own the whole GPU: one after the other
-      run_sweep_kernel(c, b);
+    if (mode == SWEEP_STAR && b.sweep) {
+      Factor &F = *b.factor;
+      if (F.sm_share >= 1.0) {  // the persistent kernel owns the whole GPU: batches one after the other
+        run_sweep_kernel(c, b, c->stream);
+      } else {                  // its factor's share of the SMs: the factors run side by side
+        if (!F.sweep_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&F.sweep_stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamWaitEvent(F.sweep_stream, c->ev_start, 0));
+        run_sweep_kernel(c, b, F.sweep_stream);
+        CUDA_CHECK(cudaEventRecord(b.done, F.sweep_stream));
+        CUDA_CHECK(cudaStreamWaitEvent(c->stream, b.done, 0));
+      }
       continue;
     }
     CUDA_CHECK(cudaStreamWaitEvent(b.stream, c->ev_start, 0));
@@ -896,10 +911,39 @@ static void setup(mmmfe_ctx *c) {
       if (same_matrix(*c->subs[reps[g]], *c->subs[i])) { group_of[i] = int(g); break; }
     if (group_of[i] < 0) { group_of[i] = int(reps.size()); reps.push_back(i); }
   }
+  // Concurrent mode: every factor group gets a share of the SMs proportional to the bytes its batches stream in one
+  // operator application (nt * factor values per batch; the factor size is known from the elimination tree alone).
+  std::vector<double> share(reps.size(), 1.0);
+  if (c->sweep_concurrent && c->use_sweep && reps.size() > 1) {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    std::vector<double> w(reps.size(), 0.0);
+    double tot = 0;
+    for (size_t g = 0; g < reps.size(); ++g) {
+      const Sub &sd = *c->subs[reps[g]];
+      NdTree probe;
+      probe.build(sd.nx, sd.ny, c->leaf_cells, 0);
+      double vals = 0;
+      for (const NdNode &n : probe.nodes) vals += double(n.s) * (double(n.s) + 2.0 * n.b);
+      int cnt = 0;
+      for (int i = 0; i < ns; ++i) cnt += group_of[i] == int(g);
+      w[g] = vals * sd.nt * ((cnt + 3) / 4);
+      tot += w[g];
+    }
+    // at least 1/16 of the machine each; the shares add up to all SMs
+    int left = sms;
+    std::vector<int> n_sm(reps.size(), 0);
+    for (size_t g = 0; g < reps.size(); ++g) { n_sm[g] = std::max(sms / 16, int(std::floor(w[g] / tot * sms))); left -= n_sm[g]; }
+    size_t big = 0;
+    for (size_t g = 1; g < reps.size(); ++g) if (w[g] > w[big]) big = g;
+    n_sm[big] += left;
+    if (n_sm[big] >= sms / 16)
+      for (size_t g = 0; g < reps.size(); ++g) share[g] = double(n_sm[g]) / sms;
+  }
   for (size_t g = 0; g < reps.size(); ++g) {
     int cnt = 0;
     for (int i = 0; i < ns; ++i) cnt += group_of[i] == int(g);
-    c->factors.push_back(factorize(c, *c->subs[reps[g]], cnt <= 1 ? 1 : (cnt == 2 ? 2 : 4)));
+    c->factors.push_back(factorize(c, *c->subs[reps[g]], cnt <= 1 ? 1 : (cnt == 2 ? 2 : 4), share[g]));
     c->factor_seconds += c->factors.back()->seconds;
   }
   // ---- interface and fine-trace layouts ----
@@ -1129,10 +1173,10 @@ static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> 
 }
 
 // all nt star steps of one batch in one cooperative launch on the interface stream
-static void run_sweep_kernel(mmmfe_ctx *c, Batch &b) {
-  CUDA_CHECK(cudaMemsetAsync(b.s_ptil.p, 0, b.s_ptil.n * sizeof(double), c->stream));
-  CUDA_CHECK(cudaMemsetAsync(b.s_cnt.p, 0, b.s_cnt.n * sizeof(uint32_t), c->stream));
-  const cudaError_t err = launch_sweep(b.M, b.factor->sweep_ct, b.sargs, b.factor->sweep_n_cta, b.sweep_smem, c->stream);
+static void run_sweep_kernel(mmmfe_ctx *c, Batch &b, cudaStream_t st) {
+  CUDA_CHECK(cudaMemsetAsync(b.s_ptil.p, 0, b.s_ptil.n * sizeof(double), st));
+  CUDA_CHECK(cudaMemsetAsync(b.s_cnt.p, 0, b.s_cnt.n * sizeof(uint32_t), st));
+  const cudaError_t err = launch_sweep(b.M, b.factor->sweep_ct, b.sargs, b.factor->sweep_n_cta, b.sweep_smem, st);
   if (err != cudaSuccess) fail(MMMFE_E_CUDA, "sweep kernel launch failed: %s", cudaGetErrorString(err));
 }
 
@@ -1288,6 +1332,8 @@ int mmmfe_destroy(mmmfe_ctx *c) {
     if (b->done) cudaEventDestroy(b->done);
     if (b->stream) cudaStreamDestroy(b->stream);
   }
+  for (auto &f : c->factors)
+    if (f->sweep_stream) { cudaStreamDestroy(f->sweep_stream); f->sweep_stream = nullptr; }
 #ifdef MMMFE_WITH_NCCL
   if (c->comm) nccl().CommDestroy(c->comm);
 #endif
@@ -1326,6 +1372,7 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   else if (k == "sweep_min_fill") c->sweep_min_fill = value;
   else if (k == "sweep_micro_tile") c->sweep_mt = std::max(64, int(value));
   else if (k == "sweep_share_blobs") c->sweep_share_blobs = value != 0;
+  else if (k == "sweep_concurrent") c->sweep_concurrent = value != 0;
   else if (k == "sweep_pack") {
     if (value != 1 && value != 2 && value != 4) { c->err = "sweep_pack must be 1, 2 or 4"; return MMMFE_E_INVALID; }
     c->sweep_pack = int(value);

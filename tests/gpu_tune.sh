@@ -38,6 +38,7 @@ for cfg in "$@"; do
     p4s256) run p4s256 MMMFE_SWEEP_PACK=4 MMMFE_SUBTREE_CELLS=256 ;;
     p4s256k6) run p4s256k6 MMMFE_SWEEP_PACK=4 MMMFE_SUBTREE_CELLS=256 MMMFE_SWEEP_CHUNK=6144 ;;
     p2ns) run p2ns MMMFE_SWEEP_PACK=2 MMMFE_SWEEP_SHARE_BLOBS=0 ;;
+    conc) run conc MMMFE_SWEEP_CONCURRENT=1 ;;
     s64) run s64 MMMFE_SUBTREE_CELLS=64 ;;
     s256) run s256 MMMFE_SUBTREE_CELLS=256 ;;
   esac

@@ -123,6 +123,21 @@ def test_sweep_kernel_subtree_packs_match_oracle(nxs, nts, mortar, k, cells, pac
     eng.close()
 
 
+def test_concurrent_sweep_kernels_on_sm_shares():
+    """sweep_concurrent = 1: the persistent kernels of the two factor groups run side by side, each on its share of the
+    SMs (different CTA counts, hence different plans) -- same operator."""
+    prob = _two_by_two((96, 48, 48, 96), (8, 4, 4, 8), [12, 12, 2], 1)
+    q = np.random.default_rng(28).standard_normal(prob.n_iface)
+    eng = engine_from_oracle(prob, options={"use_sweep": 1, "subtree_cells": 64, "sweep_autotune": 0, "sweep_concurrent": 1})
+    eng.setup()
+    assert eng.stat("sweep_batches") == eng.stat("batches") == 2
+    assert eng.stat("sweep_ctas") < 148
+    out = eng.apply(q)
+    assert np.array_equal(out, eng.apply(q))
+    assert rel_l2(out, prob.apply_S(q)) < TOL
+    eng.close()
+
+
 def test_shared_subtree_blobs_change_nothing():
     """Same-shape interior subtrees of a uniform K = I grid have bitwise identical factor blobs: a pack streams one
     copy (verified on the device at set-up).  The operator must be bitwise the same with the sharing switched off."""
