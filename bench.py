@@ -90,6 +90,21 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic(kernel_key, workload):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (bench.py cannot run
+    under a profiler): profiles/traffic.json maps kernel -> {workload, dram_bytes_per_launch, source}."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    try:
+        t = json.load(open(p)).get(kernel_key)
+    except (ValueError, OSError):
+        return None, None
+    if not t or t.get("workload") != workload:
+        return None, None
+    return t.get("dram_bytes_per_launch"), t.get("source")
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -260,12 +275,13 @@ def main():
         per_launch_ms = prof[dom]["ms"] / max(1, prof[dom]["launches"])
         achieved = prof[dom]["GBps"]
         bytes_per_launch = prof[dom]["MB"] * 1e6 / max(1, prof[dom]["launches"])
+    traffic, traffic_src = measured_traffic("k_sweep" if r["sweep_batches"] > 0 else dom, a.config)
     out = {"metric": "subdomain DOF*timesteps/s of the interface-GMRES loop", "value": value, "unit": "DOF*timesteps/s",
            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
            "gmres_iterations_per_s": 1e3 / ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": config,
            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                        "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                         "bytes_per_launch": bytes_per_launch, "ms_per_launch": per_launch_ms, "per_class": prof,
                         "star_sweep_autotune": tune},
            "e2e": {"value": dof_steps / (e2e_it * 1e-3) if e2e_it > 0 else None, "unit": "DOF*timesteps/s",

@@ -8,6 +8,10 @@ run() {  # name, env...
 }
 for cfg in "$@"; do
   case $cfg in
+    x:*)  # generic: x:<name>:VAR=VAL,VAR=VAL  (VAR without the MMMFE_ prefix)
+      name=$(echo "$cfg" | cut -d: -f2); envs=$(echo "$cfg" | cut -d: -f3 | tr ',' ' ')
+      args=(); for e in $envs; do args+=("MMMFE_$e"); done
+      run "$name" "${args[@]}" ;;
     base) run base ;;
     k6) run k6 MMMFE_SWEEP_CHUNK=6144 ;;
     k8) run k8 MMMFE_SWEEP_CHUNK=8192 ;;
