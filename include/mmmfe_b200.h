@@ -91,6 +91,8 @@ int mmmfe_set_option(mmmfe_ctx *ctx, const char *key, double value);
 /* ---- multi-GPU: one process per GPU, subdomains sharded over ranks ------------------------------------------ */
 /* Size in bytes of the NCCL unique id blob; mmmfe_comm_unique_id fills one (call on rank 0, broadcast it by any
  * out-of-band means, e.g. torch.distributed), mmmfe_comm_init joins.  Single-rank runs skip both.
+ * Communicators are cached per (id, rank, world, device) for the life of the process: the contexts of successive
+ * refinement cycles join with the same id and share one communicator.
  * Replaces MPI_COMM_WORLD of the reference (src/darcy_vtdd.cc:89).                                            */
 int mmmfe_comm_unique_id_size(void);
 int mmmfe_comm_unique_id(void *id_out);

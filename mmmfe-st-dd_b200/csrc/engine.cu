@@ -11,6 +11,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -61,6 +62,11 @@ static NcclApi &nccl() {
            api.GroupEnd && api.AllReduce;
   return api;
 }
+#endif
+
+#ifdef MMMFE_WITH_NCCL
+static std::mutex &comm_cache_mutex() { static std::mutex m; return m; }
+static std::map<std::string, ncclComm_t> &comm_cache() { static std::map<std::string, ncclComm_t> m; return m; }
 #endif
 
 static const double kNormalSign[4] = {-1.0, 1.0, 1.0, -1.0};  // inc/utilities.h:79-91
@@ -179,11 +185,11 @@ struct mmmfe_ctx {
   int device = 0;
   std::string err;
   bool keep_history = true, use_graphs = true, use_sweep = true, sweep_evict_first = true;
-  int leaf_cells = 4, subtree_cells = 256, sweep_chunk = 4096, sweep_ct = 256, sweep_ctas_per_sm = 1, sweep_groups = 1;
+  int leaf_cells = 4, subtree_cells = 256, sweep_chunk = 6144, sweep_ct = 256, sweep_ctas_per_sm = 1, sweep_groups = 1;
   bool sweep_autotune = true;
   double tune_ms_sweep = 0.0, tune_ms_levels = 0.0;
   double sweep_min_fill = 1.75;
-  int sweep_mt = 512, sweep_pack = 2;
+  int sweep_mt = 1024, sweep_pack = 4;
   bool sweep_share_blobs = true;
   // 1: the persistent kernels of different factors run CONCURRENTLY, each on its own share of the SMs (proportional
   // to nt * factor bytes of its batches); 0: one after the other on all SMs
@@ -1334,9 +1340,7 @@ int mmmfe_destroy(mmmfe_ctx *c) {
   }
   for (auto &f : c->factors)
     if (f->sweep_stream) { cudaStreamDestroy(f->sweep_stream); f->sweep_stream = nullptr; }
-#ifdef MMMFE_WITH_NCCL
-  if (c->comm) nccl().CommDestroy(c->comm);
-#endif
+  // the NCCL communicator belongs to the process-wide cache (mmmfe_comm_init), not to the context
   if (c->ev_start) cudaEventDestroy(c->ev_start);
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
@@ -1410,7 +1414,22 @@ int mmmfe_comm_init(mmmfe_ctx *c, int rank, int world, const void *id) {
   std::memcpy(&uid, id, sizeof uid);
   cudaSetDevice(c->device);
   if (!nccl().ok) { c->err = "libnccl.so.2 could not be loaded"; return MMMFE_E_COMM; }
-  if (nccl().CommInitRank(&c->comm, world, uid, rank) != ncclSuccess) { c->err = "ncclCommInitRank failed"; return MMMFE_E_COMM; }
+  // A unique id can initialise ONE communicator, but the front-end creates a context per refinement cycle
+  // (src/darcy_vtdd.cc:2079: everything is rebuilt per cycle) with the id it was launched with: communicators are
+  // cached per (id, rank, world, device) for the life of the process and shared by the contexts.
+  {
+    std::lock_guard<std::mutex> lock(comm_cache_mutex());
+    std::string key(reinterpret_cast<const char *>(&uid), sizeof uid);
+    key += "/" + std::to_string(rank) + "/" + std::to_string(world) + "/" + std::to_string(c->device);
+    auto &cache = comm_cache();
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+      ncclComm_t comm = nullptr;
+      if (nccl().CommInitRank(&comm, world, uid, rank) != ncclSuccess) { c->err = "ncclCommInitRank failed"; return MMMFE_E_COMM; }
+      it = cache.emplace(key, comm).first;
+    }
+    c->comm = it->second;
+  }
   return MMMFE_OK;
 #else
   (void)id;
