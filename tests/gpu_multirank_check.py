@@ -53,6 +53,17 @@ def main():
         nccl_id = unique_id(rank)
         reps, res, lam = pkg().host_run(pfile, nccl_id=nccl_id, rank=rank, world=world, device=local, verbose=0,
                                         write_output=0, **c["kw"])
+        # the front-end returns the interface vector of the LOCAL subdomains; ownership is in contiguous blocks of
+        # global ids (mmmfe_assign_owners), so the rank-ordered concatenation is the global vector of the oracle
+        n_loc = torch.tensor([len(lam)], dtype=torch.int64, device="cuda")
+        sizes = [torch.zeros_like(n_loc) for _ in range(world)]
+        dist.all_gather(sizes, n_loc)
+        n_max = int(max(int(x[0]) for x in sizes))
+        mine = torch.zeros(n_max, dtype=torch.float64, device="cuda")
+        mine[:len(lam)] = torch.from_numpy(np.ascontiguousarray(lam)).cuda()
+        parts = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        lam = np.concatenate([parts[r][:int(sizes[r][0])].cpu().numpy() for r in range(world)])
         dist.barrier()
         if rank != 0:
             continue
