@@ -185,7 +185,7 @@ struct mmmfe_ctx {
   int device = 0;
   std::string err;
   bool keep_history = true, use_graphs = true, use_sweep = true, sweep_evict_first = true;
-  int leaf_cells = 4, subtree_cells = 256, sweep_chunk = 6144, sweep_ct = 256, sweep_ctas_per_sm = 1, sweep_groups = 1;
+  int leaf_cells = 8, subtree_cells = 256, sweep_chunk = 7168, sweep_ct = 256, sweep_ctas_per_sm = 1, sweep_groups = 1;
   bool sweep_autotune = true;
   double tune_ms_sweep = 0.0, tune_ms_levels = 0.0;
   double sweep_min_fill = 1.75;
@@ -193,7 +193,7 @@ struct mmmfe_ctx {
   bool sweep_share_blobs = true;
   // 1: the persistent kernels of different factors run CONCURRENTLY, each on its own share of the SMs (proportional
   // to nt * factor bytes of its batches); 0: one after the other on all SMs
-  bool sweep_concurrent = false;
+  bool sweep_concurrent = true;
   int sweep_spin_ns = 100;
   bool is_setup = false, bar_done = false, final_done = false;
   int rank = 0, world = 1;
@@ -587,16 +587,28 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax, 
     if (cells == 0) break;
     if (F->smem_fwd[Mmax] > smem_limit / 2 || F->smem_bwd[Mmax] > smem_limit / 2) continue;
     if (!want_sweep) break;
-    // the persistent sweep kernel additionally wants a ring of several entries
+    // the persistent sweep kernel additionally wants a ring of several entries: the waves are as large as asked for
+    // (sweep_chunk) unless the ring then holds fewer than 2.6 of them -- the vectors of M right-hand sides take
+    // their share of the shared memory, and a ring of barely two waves stalls the TMA stream (measured at M = 2, ring
+    // of 19 478 doubles: 7168-double waves 221 ms, 8192-double waves 335 ms) -- in which case they shrink in steps
+    // of 1/8
     {
       std::vector<int32_t> iu(tr.idx.size());
       for (size_t i = 0; i < tr.idx.size(); ++i) iu[i] = dof_of_canon.empty() ? tr.idx[i] : dof_of_canon[tr.idx[i]];
       std::vector<int32_t> cls;
       if (c->sweep_share_blobs) cls = subtree_classes(tr, S, dof_of_canon);
-      if (build_sweep_layout(tr, iu, dof_of_canon, F->sweep_n_cta, c->sweep_chunk, F->sweep_ct / F->sweep_ng, F->lay, F->sweep_ng, c->sweep_mt, c->sweep_pack, cls) != nullptr) { want_sweep = false; break; }
+      bool layout_ok = true;
+      for (int chunk = c->sweep_chunk; chunk >= 1024; chunk = (chunk * 7 / 8) & ~1) {
+        if (build_sweep_layout(tr, iu, dof_of_canon, F->sweep_n_cta, chunk, F->sweep_ct / F->sweep_ng, F->lay, F->sweep_ng, std::min(c->sweep_mt, chunk), c->sweep_pack, cls) != nullptr) { layout_ok = false; break; }
+        SweepSchedule probe;
+        if (build_sweep_schedule(tr, F->lay, Mmax, F->sweep_ng, F->sweep_budget, c->sweep_min_fill, probe) != nullptr) continue;
+        if (10 * int64_t(probe.ring_dbl) < 26 * int64_t(chunk) && chunk * 7 / 8 >= 1024) continue;
+        sweep_planned = true;
+        break;
+      }
+      if (!layout_ok) { want_sweep = false; break; }
+      if (sweep_planned) break;
     }
-    SweepSchedule probe;
-    if (build_sweep_schedule(tr, F->lay, Mmax, F->sweep_ng, F->sweep_budget, c->sweep_min_fill, probe) == nullptr) { sweep_planned = true; break; }
     if (cells / 2 < std::max(1, c->leaf_cells)) {  // cannot shrink further: generic kernels with the widest subtrees
       want_sweep = false;
       cells = c->subtree_cells * 2;
@@ -1378,7 +1390,7 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   else if (k == "sweep_share_blobs") c->sweep_share_blobs = value != 0;
   else if (k == "sweep_concurrent") c->sweep_concurrent = value != 0;
   else if (k == "sweep_pack") {
-    if (value != 1 && value != 2 && value != 4) { c->err = "sweep_pack must be 1, 2 or 4"; return MMMFE_E_INVALID; }
+    if (value != 1 && value != 2 && value != 4 && value != 8) { c->err = "sweep_pack must be 1, 2, 4 or 8"; return MMMFE_E_INVALID; }
     c->sweep_pack = int(value);
   }
   else { c->err = "unknown option " + k; return MMMFE_E_INVALID; }
@@ -1718,6 +1730,8 @@ int64_t mmmfe_stat(const mmmfe_ctx *c, const char *key) {
   if (k == "sweep_entries") { for (auto &b : c->batches) if (b->sweep) v += int64_t(b->s_entries.n); return v; }
   if (k == "sweep_shared_blob_pairs") { for (auto &f : c->factors) if (f->sweep_ok) v += f->shared_blob_pairs; return v; }
   if (k == "sweep_factor_bytes") { for (auto &f : c->factors) if (f->sweep_ok) v += int64_t(f->lay.bytes_per_step); return v; }
+  if (k == "sweep_chunk_used") { for (auto &f : c->factors) if (f->sweep_ok) v = std::max<int64_t>(v, f->lay.chunk_dbl); return v; }
+  if (k == "sweep_ring_doubles") { for (auto &b : c->batches) if (b->sweep) v = std::max<int64_t>(v, b->sargs.ring_dbl); return v; }
   if (k == "rt0_factors") { for (auto &f : c->factors) v += f->rt0; return v; }
   if (k == "sweep_planned") { for (auto &b : c->batches) v += b->s_entries.n > 0; return v; }
   if (k == "tune_us_sweep") return int64_t(c->tune_ms_sweep * 1e3);

@@ -134,7 +134,7 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
   L.ct = ct;
   L.ng = std::max(1, ng);
   L.mt_dbl = std::max(64, mt_dbl);
-  L.pack = (pack == 2 || pack == 4) && ct / pack >= 32 ? pack : 1;
+  L.pack = (pack == 2 || pack == 4 || pack == 8) && ct / pack >= 32 ? pack : 1;
   if (const char *env = std::getenv("MMMFE_SWEEP_WS_ROWS")) L.ws_rows = std::atoi(env);
   const int32_t nn = int32_t(tr.nodes.size());
   if (tr.instances.empty()) return "no subtrees (subtree_cells = 0)";

@@ -50,7 +50,8 @@ if __name__ == "__main__":
     dofsteps = sum(sd.n * sd.nt for sd in prob.subs)
     print(f"DOF*steps/s {dofsteps / (ms_ * 1e-3):.3e}")
     print("sweep batches", eng.stat("sweep_batches"), "of", eng.stat("batches"), "ctas", eng.stat("sweep_ctas"),
-          "smem", eng.stat("sweep_smem_bytes"), "entries", eng.stat("sweep_entries"))
+          "smem", eng.stat("sweep_smem_bytes"), "entries", eng.stat("sweep_entries"), "chunk", eng.stat("sweep_chunk_used"),
+          "ring", eng.stat("sweep_ring_doubles"))
     for ms_sw, by, ns in eng.profile_sweeps():
         print(f"  sweep kernel: {ms_sw:9.3f} ms for {ns} steps = {ms_sw / ns * 1e3:8.1f} us/step, "
               f"{by / 1e6:8.1f} MB/step -> {by * ns / ms_sw / 1e6:7.0f} GB/s")

@@ -100,7 +100,7 @@ def test_persistent_sweep_kernel_matches_oracle_and_generic_kernels(nxs, nts, mo
     assert rel_l2(outs[1], outs[0]) < 1e-12
 
 
-@pytest.mark.parametrize("pack", [2, 4])
+@pytest.mark.parametrize("pack", [2, 4, 8])
 @pytest.mark.parametrize("nxs,nts,mortar,k,cells", [
     ((16, 8, 8, 16), (8, 4, 4, 8), [4, 4, 2], 1, 16),       # several packs of interior and boundary subtrees per CTA
     ((37, 23, 23, 37), (6, 3, 3, 6), [5, 5, 3], 2, 64),     # ragged boxes: many templates, short packs
