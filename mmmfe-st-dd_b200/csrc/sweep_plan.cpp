@@ -157,16 +157,33 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
     L.sub_ws_max = std::max(L.sub_ws_max, std::max(T.n_int + T.zl_size, T.n_int + T.n_rootb));
   }
   L.perm.push_back(0);
-  // ---- subtrees -> CTAs: interior and boundary subtrees are dealt out separately so that every CTA gets its share
-  // of both ----
+  // ---- subtrees -> CTAs, in units of PACKS: a pack costs the same whether it has one member or L.pack (lockstep), so
+  // the subtrees are first grouped by (template, class) -- what may share a pack -- cut into packs in instance order
+  // (neighbouring boxes stay together), and the packs are dealt out in contiguous runs: every CTA gets
+  // floor or ceil(n_packs / n_cta) of them.  (Dealing out subtrees instead left CTAs with up to 17 mostly
+  // half-empty packs against a mean of 14.9 on a 1024^2 grid.) ----
   const int32_t n_inst = int32_t(tr.instances.size());
   L.cta_of_inst.assign(n_inst, 0);
   {
-    std::vector<int32_t> interior, boundary;
-    for (int32_t k = 0; k < n_inst; ++k) (tr.templates[tr.instances[k].tmpl].flags == 0 ? interior : boundary).push_back(k);
-    for (size_t t = 0; t < interior.size(); ++t) L.cta_of_inst[interior[t]] = int32_t(int64_t(t) * n_cta / int64_t(interior.size()));
-    for (size_t t = 0; t < boundary.size(); ++t)
-      L.cta_of_inst[boundary[t]] = n_cta - 1 - int32_t(int64_t(t) * n_cta / int64_t(boundary.size()));
+    std::map<std::pair<int32_t, int32_t>, std::vector<int32_t>> groups;  // (interior first, template, class) -> instances
+    for (int32_t k = 0; k < n_inst; ++k) {
+      const int32_t t = tr.instances[k].tmpl;
+      const int32_t key0 = (tr.templates[t].flags == 0 ? 0 : 1 << 20) + t;
+      groups[{key0, inst_class.empty() ? -1 : inst_class[k]}].push_back(k);
+    }
+    std::vector<std::pair<int32_t, int32_t>> pack_of;  // (first index into order, members)
+    std::vector<int32_t> order;
+    for (const auto &g : groups)
+      for (size_t i = 0; i < g.second.size(); i += size_t(L.pack)) {
+        const size_t n = std::min(size_t(L.pack), g.second.size() - i);
+        pack_of.push_back({int32_t(order.size()), int32_t(n)});
+        order.insert(order.end(), g.second.begin() + i, g.second.begin() + i + n);
+      }
+    const int64_t n_packs = int64_t(pack_of.size());
+    for (int64_t j = 0; j < n_packs; ++j) {
+      const int32_t cta = int32_t(j * n_cta / n_packs);
+      for (int32_t m = 0; m < pack_of[j].second; ++m) L.cta_of_inst[order[pack_of[j].first + m]] = cta;
+    }
   }
   // allocation order (CTA, template, instance): the members of a pack are neighbours in every array
   L.inst_at_pos.resize(n_inst);
