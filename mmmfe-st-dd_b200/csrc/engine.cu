@@ -189,7 +189,7 @@ struct mmmfe_ctx {
   bool sweep_autotune = true;
   double tune_ms_sweep = 0.0, tune_ms_levels = 0.0;
   double sweep_min_fill = 1.75;
-  int sweep_mt = 1024, sweep_pack = 4;
+  int sweep_mt = 896, sweep_pack = 4;  // 7168 / 896 = one micro-tile per compute warp and wave
   bool sweep_share_blobs = true;
   // 1: the persistent kernels of different factors run CONCURRENTLY, each on its own share of the SMs (proportional
   // to nt * factor bytes of its batches); 0: one after the other on all SMs
