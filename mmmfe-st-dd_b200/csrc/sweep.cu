@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
             const int o = gt + u * GT;
 #pragma unroll
             for (int j = 0; j < M; ++j) pv[u][j] = 0.0;
-            if (o < n_cols) {
+            if (o < n_cols && (colA[o].y & 0xFFFF) != 0) {  // (columns of direct micro-tiles are loaded by their warp)
               const int c0 = colA[o].w, c1 = colB[o];
               double p0[M], p1[M];
               if (c0 >= 0) ld_vec<M>(a.z + int64_t(c0) * M, p0);
@@ -603,9 +603,54 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
           const int wig = gt >> 5, nw = GT >> 5;
           for (int m = wig; m < n_mt; m += nw) {
             const int4 md = *reinterpret_cast<const int4 *>(&mts[m]);  // tile_off, row0, nrows, ncols
-            const int part_off = mts[m].part_off;
+            const int4 me = *(reinterpret_cast<const int4 *>(&mts[m]) + 1);  // part_off, col0, direct
+            const int part_off = me.x;
+            const bool direct = me.z != 0;
             const int nrows = md.z, ncols = md.w;
             const double *vp = wsv + md.y * M;
+            // direct micro-tile: the lanes that end up with the column sums (row group 0) write the outputs; the
+            // pass-through of the children's contributions (forward) is loaded now, behind the multiply
+            const int cp_ = ncols >> 1;
+            const bool writer = direct && (ncols == 1 ? lane == 0 : lane < cp_);
+            int4 cw0 = make_int4(0, 0, 0, -1), cw1 = make_int4(0, 0, 0, -1);
+            double pq0[M], pq1[M];
+#pragma unroll
+            for (int j = 0; j < M; ++j) pq0[j] = pq1[j] = 0.0;
+            if (writer) {
+              const int o0 = me.y + (ncols == 1 ? 0 : 2 * lane);
+              cw0 = colA[o0];
+              if (ncols > 1) cw1 = colA[o0 + 1];
+              if (fwd) {
+                const int32_t *colB = ix + e.o3;
+                const int b0 = colB[o0], b1 = ncols > 1 ? colB[o0 + 1] : -1;
+                double t0[M], t1[M], t2[M], t3[M];
+                if (cw0.w >= 0) ld_vec<M>(a.z + int64_t(cw0.w) * M, t0);
+                if (b0 >= 0) ld_vec<M>(a.z + int64_t(b0) * M, t1);
+                if (ncols > 1 && cw1.w >= 0) ld_vec<M>(a.z + int64_t(cw1.w) * M, t2);
+                if (b1 >= 0) ld_vec<M>(a.z + int64_t(b1) * M, t3);
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                  pq0[j] = (cw0.w >= 0 ? t0[j] : 0.0) + (b0 >= 0 ? t1[j] : 0.0);
+                  pq1[j] = ((ncols > 1 && cw1.w >= 0) ? t2[j] : 0.0) + (b1 >= 0 ? t3[j] : 0.0);
+                }
+              }
+            }
+            auto put = [&](const int4 &cw, const double (&tot)[M], const double (&pq)[M]) {
+              if (fwd) {
+#pragma unroll
+                for (int j = 0; j < M; ++j) a.z[int64_t(cw.z) * M + j] = tot[j] + pq[j];
+              } else {
+#pragma unroll
+                for (int j = 0; j < M; ++j) a.x[int64_t(cw.z) * M + j] = tot[j];
+                if (a.hist)
+#pragma unroll
+                  for (int j = 0; j < M; ++j)
+                    if (a.hist[j]) {
+                      double *hp = a.hist[j] + int64_t(level) * a.hist_stride + cw.z;
+                      *hp = a.hist_add ? *hp + tot[j] : tot[j];
+                    }
+              }
+            };
             if (ncols == 1) {
               const double *tp = tiles + md.x;
               double acc[M];
@@ -620,7 +665,8 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
               for (int off = 16; off > 0; off >>= 1)
 #pragma unroll
                 for (int j = 0; j < M; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
-              if (lane == 0)
+              if (writer) put(cw0, acc, pq0);
+              else if (lane == 0)
 #pragma unroll
                 for (int j = 0; j < M; ++j) part[part_off * M + j] = acc[j];
             } else {
@@ -665,7 +711,10 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
                   a0[j] += __shfl_xor_sync(0xffffffffu, a0[j], off);
                   a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], off);
                 }
-              if (my_rg == 0)
+              if (writer) {  // lanes 0 .. cp - 1 are row group 0: my_cp == lane
+                put(cw0, a0, pq0);
+                put(cw1, a1, pq1);
+              } else if (my_rg == 0 && !direct)
 #pragma unroll
                 for (int j = 0; j < M; ++j) {
                   part[(part_off + 2 * my_cp) * M + j] = a0[j];
@@ -675,12 +724,13 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
           }
         }
         SWEEP_PROF(21)
-        gsync();
+        if (!(flags & SWF_DIRECT)) gsync();
         SWEEP_PROF(22)
         // outputs: the row parts of every column are added in a fixed order
-        for (int o = gt, u = 0; o < n_cols; o += GT, ++u) {
+        for (int o = gt, u = 0; o < n_cols && !(flags & SWF_DIRECT); o += GT, ++u) {
           const int4 ca = colA[o];
           const int np = ca.y & 0xFFFF, stride = ca.y >> 16;
+          if (np == 0) continue;  // column of a direct micro-tile
           double tot[M];
 #pragma unroll
           for (int j = 0; j < M; ++j) tot[j] = part[ca.x * M + j];

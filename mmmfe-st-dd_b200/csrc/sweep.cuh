@@ -35,7 +35,9 @@ enum SweepKind : int32_t { SW_SUB_FWD = 0, SW_TOP_FWD = 1, SW_TOP_BWD = 2, SW_SU
 // SWF_ROWS_WS: the gathered rows of a wave live in the group's workspace (not in the ring scratch); SWF_REUSE: the
 // previous wave of this CTA gathered exactly these rows and left them there
 // SWF_SHARED: the members of a subtree pack have bitwise identical factor blobs; segment 0 holds one copy
-enum SweepFlag : int32_t { SWF_FIRST = 1, SWF_LAST = 2, SWF_ROWS_WS = 4, SWF_REUSE = 8, SWF_SHARED = 16 };
+// SWF_DIRECT: every micro-tile of the wave holds ALL rows of its columns: the warps write the outputs themselves, the
+// wave has no partial sums, no second barrier and no output phase
+enum SweepFlag : int32_t { SWF_FIRST = 1, SWF_LAST = 2, SWF_ROWS_WS = 4, SWF_REUSE = 8, SWF_SHARED = 16, SWF_DIRECT = 32 };
 enum SweepSrc : int32_t { SRC_FACTOR = 0, SRC_INDEX = 1, SRC_XI = 2, SRC_PTIL = 3 };
 
 // One unit of work of one CTA (128 bytes).  The ring region of an entry holds its streamed segments back to back
@@ -83,7 +85,9 @@ struct alignas(16) SweepMt {  // micro-tile descriptor (32 bytes)
   int32_t row0, nrows;        // rows [row0, row0 + nrows) of the wave's gathered vector
   int32_t ncols;              // 2, 4, ..., 64
   int32_t part_off;           // first partial slot
-  int32_t pad[3];
+  int32_t col0;               // column record of the tile's first column
+  int32_t direct;             // 1: the tile holds all rows of its columns -> the warp writes their outputs itself
+  int32_t pad;
 };
 
 struct alignas(16) SweepIssue {  // what the TMA issuer needs of an entry

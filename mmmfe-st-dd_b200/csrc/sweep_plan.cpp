@@ -136,6 +136,7 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
   L.mt_dbl = std::max(64, mt_dbl);
   L.pack = (pack == 2 || pack == 4 || pack == 8) && ct / pack >= 32 ? pack : 1;
   if (const char *env = std::getenv("MMMFE_SWEEP_WS_ROWS")) L.ws_rows = std::atoi(env);
+  if (const char *env = std::getenv("MMMFE_SWEEP_DIRECT")) L.direct = std::atoi(env) != 0;
   const int32_t nn = int32_t(tr.nodes.size());
   if (tr.instances.empty()) return "no subtrees (subtree_cells = 0)";
   if (tr.idx.size() >= (size_t(1) << 30) || tr.src.size() >= (size_t(1) << 31)) return "index structure beyond 32 bits";
@@ -342,18 +343,23 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
     for (int32_t cta = 0; cta < n_cta; ++cta) {
       if (pieces[cta].empty()) continue;
       // strips of every piece: widths 64, then the binary digits of the rest; never more than chunk_dbl doubles
-      struct Strip { int32_t node, c0, w, parts; };
+      struct Strip { int32_t node, c0, w, parts, direct; };
       std::vector<Strip> strips;
       for (const Piece &pc : pieces[cta]) {
         const SweepNodeH &sn = L.nodes[pc.node];
         const int32_t rlen = pass == 0 ? sn.s : sn.s + sn.b;
-        if (pc.nc == 0) { strips.push_back({pc.node, 0, 0, 0}); continue; }
+        if (pc.nc == 0) { strips.push_back({pc.node, 0, 0, 0, 0}); continue; }
         const int32_t wmax = std::max(1, std::min(64, pow2_floor(std::max<int64_t>(1, L.chunk_dbl / std::max(1, rlen)))));
+        // DIRECT strips: as wide as ONE micro-tile (up to 1.5 mt_dbl doubles) can hold with all rows, so that the warp
+        // that multiplies it owns the complete column sums and writes the outputs itself (no partial sums in shared
+        // memory, no second barrier, no output phase).  Fronts with more rows than that keep the split tiles.
+        const int64_t cap = (3 * int64_t(L.mt_dbl)) / 2;
+        const int32_t wdir = (L.direct && rlen <= cap) ? std::min(wmax, pow2_floor(std::max<int64_t>(1, cap / rlen))) : 0;
         int32_t c = pc.c0, left = pc.nc;
         while (left > 0) {
-          const int32_t w = std::min(wmax, pow2_floor(left));
-          const int32_t parts = std::max(1, std::min(rlen, int32_t((int64_t(rlen) * w + L.mt_dbl / 2) / L.mt_dbl)));
-          strips.push_back({pc.node, c, w, parts});
+          const int32_t w = std::min(wdir > 0 ? wdir : wmax, pow2_floor(left));
+          const int32_t parts = wdir > 0 ? 1 : std::max(1, std::min(rlen, int32_t((int64_t(rlen) * w + L.mt_dbl / 2) / L.mt_dbl)));
+          strips.push_back({pc.node, c, w, parts, (L.direct && parts == 1) ? 1 : 0});
           c += w; left -= w;
         }
       }
@@ -367,6 +373,7 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
         std::vector<SweepMt> mts;
         std::vector<RepackDesc> reps;
         int64_t tile = 0;
+        bool all_direct = true;
         for (; i < strips.size(); ++i) {
           const Strip &sp = strips[i];
           const SweepNodeH &sn = L.nodes[sp.node];
@@ -435,13 +442,16 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
             fi = int32_t(it - W.fronts.begin());
           }
           if (sp.w == 0) continue;  // rows only
+          all_direct = all_direct && sp.direct != 0;
           const int32_t part0 = W.n_parts;
+          const int32_t rec0 = int32_t(colA.size() / 4);
           for (int32_t q = 0; q < sp.parts; ++q) {
             const int32_t r0 = int32_t(int64_t(rlen) * q / sp.parts), r1 = int32_t(int64_t(rlen) * (q + 1) / sp.parts);
             SweepMt m;
             std::memset(&m, 0, sizeof m);
             m.tile_off = int32_t(tile); m.row0 = row0_of[fi] + r0; m.nrows = r1 - r0; m.ncols = sp.w;
             m.part_off = W.n_parts;
+            m.col0 = rec0; m.direct = sp.direct;
             mts.push_back(m);
             RepackDesc d;
             d.dst = tile;  // relative to the wave; rebased below
@@ -454,7 +464,7 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
           }
           for (int32_t c = 0; c < sp.w; ++c) {
             const int32_t col = sp.c0 + c;  // < ncols: strips never pad
-            colA.push_back(part0 + c); colA.push_back(sp.parts | (sp.w << 16));
+            colA.push_back(part0 + c); colA.push_back((sp.direct ? 0 : sp.parts) | (sp.w << 16));
             if (pass == 0) {
               colA.push_back(sn.zc_off + col); colA.push_back(child_z(0, sn.s + col));
               colB.push_back(child_z(1, sn.s + col));
@@ -482,6 +492,7 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
         } else {
           prev_fronts.clear();
         }
+        if (all_direct && !mts.empty()) W.flags |= SWF_DIRECT;
         W.n_mt = int32_t(mts.size());
         W.n_cols = int32_t(colA.size() / 4);
         W.tile_src = rs; W.tile_dbl = int32_t(tile);

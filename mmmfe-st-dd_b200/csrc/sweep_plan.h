@@ -58,6 +58,7 @@ struct SweepLayout {
   int32_t pack = 1;                              // subtrees per pack (1, 2 or 4)
   std::vector<int32_t> prod_cta;                 // per completion counter: the CTA when a single one bumps it, else -2
   int32_t ng = 1, mt_dbl = 512;                  // compute groups per CTA; target doubles of a micro-tile
+  bool direct = true;                            // strips that fit one micro-tile are written out by their warp
   int32_t ws_rows = 4096;                        // waves with at most this many rows gather them into the workspace
   int32_t wave_ws_rows = 0;                      // most rows any wave keeps in the workspace
   std::vector<std::vector<SweepWaveH>> fwd, bwd;  // waves by height (ascending), CTA-major within a height
