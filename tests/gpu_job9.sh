@@ -2,14 +2,14 @@
 # final state of the round: tests, smoke, bench (N = 1), perf probe with trace, ncu launch list + full capture of k_sweep
 cd "$(dirname "$0")/.."; mkdir -p gpurun_out
 O=gpurun_out
-(time timeout 900 python -m pytest tests -m gpu -x -q) > $O/s11_pytest.log 2>&1; tail -4 $O/s11_pytest.log
+(time timeout 900 python -m pytest tests -m gpu -x -q) > $O/s16_pytest.log 2>&1; tail -4 $O/s16_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-(time timeout 500 python bench.py --steps 5 --warmup 3) > $O/s11_bench.log 2> $O/s11_bench.err; grep '^{"metric"' $O/s11_bench.log | cut -c1-400; tail -3 $O/s11_bench.err
-(time timeout 500 python bench.py --impl reference --steps 2 --warmup 1) > $O/s11_bench_ref.log 2> $O/s11_bench_ref.err; cut -c1-300 $O/s11_bench_ref.log | tail -2
+(time timeout 500 python bench.py --steps 5 --warmup 3) > $O/s16_bench.log 2> $O/s16_bench.err; grep '^{"metric"' $O/s16_bench.log | cut -c1-400; tail -3 $O/s16_bench.err
+(time timeout 500 python bench.py --impl reference --steps 2 --warmup 1) > $O/s16_bench_ref.log 2> $O/s16_bench_ref.err; cut -c1-300 $O/s16_bench_ref.log | tail -2
 cd tests
-MMMFE_SWEEP_AUTOTUNE=0 MMMFE_TRACE_ALL=../$O/s11_trace.npz timeout 300 python gpu_perf_probe.py 1024 256 512 128 256 64 3 > ../$O/s11_probe.log 2>&1
-grep -E "^apply|sweep kernel:|sweep batches|rror" ../$O/s11_probe.log | cut -c1-300
-python gpu_trace_report.py ../$O/s11_trace.npz > ../$O/s11_trace.txt 2>&1; tail -6 ../$O/s11_trace.txt
+MMMFE_SWEEP_AUTOTUNE=0 MMMFE_TRACE_ALL=../$O/s16_trace.npz timeout 300 python gpu_perf_probe.py 1024 256 512 128 256 64 3 > ../$O/s16_probe.log 2>&1
+grep -E "^apply|sweep kernel:|sweep batches|rror" ../$O/s16_probe.log | cut -c1-300
+python gpu_trace_report.py ../$O/s16_trace.npz > ../$O/s16_trace.txt 2>&1; tail -6 ../$O/s16_trace.txt
 cd ..
-timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 --csv --log-file $O/s11_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/s11_ncu_launch.log 2>&1; tail -1 $O/s11_ncu_launch.log | cut -c1-200
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sweep -c 2 -o $O/s11_ksweep -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/s11_ncu_full.log 2>&1; tail -2 $O/s11_ncu_full.log | cut -c1-200
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 --csv --log-file $O/s16_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/s16_ncu_launch.log 2>&1; tail -1 $O/s16_ncu_launch.log | cut -c1-200
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sweep -c 2 -o $O/s16_ksweep -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/s16_ncu_full.log 2>&1; tail -2 $O/s16_ncu_full.log | cut -c1-200
