@@ -194,6 +194,7 @@ struct mmmfe_ctx {
   // 1: the persistent kernels of different factors run CONCURRENTLY, each on its own share of the SMs (proportional
   // to nt * factor bytes of its batches); 0: one after the other on all SMs
   bool sweep_concurrent = true;
+  double sweep_share_exponent = 1.0;  // SM share of a factor group ~ (streamed bytes)^exponent
   int sweep_spin_ns = 100;
   bool is_setup = false, bar_done = false, final_done = false;
   int rank = 0, world = 1;
@@ -946,6 +947,7 @@ static void setup(mmmfe_ctx *c) {
       int cnt = 0;
       for (int i = 0; i < ns; ++i) cnt += group_of[i] == int(g);
       w[g] = vals * sd.nt * ((cnt + 3) / 4);
+      w[g] = std::pow(w[g], c->sweep_share_exponent);  // < 1 favours the small groups (they are latency-bound)
       tot += w[g];
     }
     // at least 1/16 of the machine each; the shares add up to all SMs
@@ -1389,6 +1391,7 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   else if (k == "sweep_micro_tile") c->sweep_mt = std::max(64, int(value));
   else if (k == "sweep_share_blobs") c->sweep_share_blobs = value != 0;
   else if (k == "sweep_concurrent") c->sweep_concurrent = value != 0;
+  else if (k == "sweep_share_exponent") c->sweep_share_exponent = std::min(2.0, std::max(0.1, value));
   else if (k == "sweep_pack") {
     if (value != 1 && value != 2 && value != 4 && value != 8) { c->err = "sweep_pack must be 1, 2, 4 or 8"; return MMMFE_E_INVALID; }
     c->sweep_pack = int(value);

@@ -28,7 +28,7 @@ if __name__ == "__main__":
     prob = build(nf, ntf, nc, ntc, [ms, ms, mt])
     eng = pkg().Engine()
     import os
-    for key in ("subtree_cells", "leaf_cells", "use_graphs", "use_sweep", "sweep_chunk", "sweep_min_fill", "sweep_evict_first", "sweep_compute_threads", "sweep_ctas_per_sm", "sweep_spin_ns", "sweep_groups", "sweep_autotune", "sweep_micro_tile", "sweep_pack", "sweep_share_blobs", "sweep_concurrent"):
+    for key in ("subtree_cells", "leaf_cells", "use_graphs", "use_sweep", "sweep_chunk", "sweep_min_fill", "sweep_evict_first", "sweep_compute_threads", "sweep_ctas_per_sm", "sweep_spin_ns", "sweep_groups", "sweep_autotune", "sweep_micro_tile", "sweep_pack", "sweep_share_blobs", "sweep_concurrent", "sweep_share_exponent"):
         if os.environ.get("MMMFE_" + key.upper()):
             eng.set_option(key, float(os.environ["MMMFE_" + key.upper()]))
     for sd in prob.subs:
