@@ -262,6 +262,23 @@ def test_checkerboard_4x4_nonmatching_space_time():
     eng.close()
 
 
+def test_checkerboard_4x4_persistent_kernel_with_four_right_hand_sides():
+    """4x4 checkerboard, 64^2 x 8 / 32^2 x 4: eight subdomains per colour = two batches of FOUR right-hand sides per
+    factor, forced through the persistent sweep kernel (top levels above the subtrees, concurrent factor groups)."""
+    prm = default_params(1)
+    mesh = [[64, 64, 8] if ((r % 4) + (r // 4)) % 2 == 0 else [32, 32, 4] for r in range(16)]
+    prob = make_problem(prm, n_sub=16, mesh=mesh, mortar=[8, 8, 2])
+    eng = engine_from_oracle(prob, options={"use_sweep": 1, "sweep_autotune": 0, "subtree_cells": 64})
+    eng.setup()
+    assert eng.stats()["factor_groups"] == 2 and eng.stat("batches") == 4
+    assert eng.stat("sweep_batches") == 4
+    q = np.random.default_rng(16).standard_normal(prob.n_iface)
+    out = eng.apply(q)
+    assert np.array_equal(out, eng.apply(q))
+    assert rel_l2(out, prob.apply_S(q)) < TOL
+    eng.close()
+
+
 def test_checkerboard_8x8_quadratic_mortar():
     """8x8 subdomains, checkerboard fine/coarse grids with twice as many time steps as cells per direction, mortar
     degree 2 (BASELINE config 4 scaled down; every mortar-face centre Gauss point is a tie, quirk Q5)."""
