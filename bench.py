@@ -8,7 +8,9 @@ A "step" is one interface-GMRES iteration: mortar->fine projection, nt backward-
 subdomain, fine->mortar projection, face exchange, classical Gram-Schmidt update.  The workload at N = 1 is
 BASELINE.json configs[1] (2x2 subdomains, non-matching space/time grids with ratio 2: 1024^2 x 256 steps on the
 fine colour, 512^2 x 128 on the coarse one, mortar 256 x 256 x 64, degree 1).  For N > 1 the subdomain grid grows
-to 4 N subdomains of the same sizes (checkerboard), 4 per GPU: weak scaling.
+to 4 N subdomains of the same sizes (checkerboard), 4 per GPU: weak scaling.  `--config cfg3` / `cfg4` run
+BASELINE.json configs[2] / configs[3] (8 subdomains per GPU: 4x4 at --gpus 2, 8x8 at --gpus 8) for DESIGN.md section 7;
+the driver's bench line is the default cfg2.
 `value` = subdomain DOF*timesteps per second over all GPUs (DOF*steps of one operator application x iterations/s).
 """
 import argparse
@@ -24,10 +26,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
-    # name: (fine pattern, coarse pattern, mortar pattern, mortar degree)
+    # name: (fine pattern, coarse pattern, mortar pattern, mortar degree[, subdomains per GPU (default 4)])
     "cfg2": ([1024, 1024, 256], [512, 512, 128], [256, 256, 64], 1),
     "cfg2_half": ([512, 512, 128], [256, 256, 64], [128, 128, 32], 1),
     "cfg2_small": ([128, 128, 32], [64, 64, 16], [32, 32, 8], 1),
+    # BASELINE.json configs[2] (4x4 checkerboard at --gpus 2) and configs[3] (8x8 = 64 subdomains, 2048^2 global x 512
+    # fine steps, quadratic mortar, at --gpus 8): not the bench line, measured for DESIGN.md section 7
+    "cfg3": ([512, 512, 128], [256, 256, 64], [128, 128, 32], 1, 8),
+    "cfg4": ([256, 256, 512], [128, 128, 256], [16, 16, 32], 2, 8),
 }
 
 
@@ -166,15 +172,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    fine, coarse, mortar, k = CONFIGS[a.config]
-    n_sub = 4 * max(1, a.gpus)
+    fine, coarse, mortar, k = CONFIGS[a.config][:4]
+    per_gpu = CONFIGS[a.config][4] if len(CONFIGS[a.config]) > 4 else 4
+    n_sub = per_gpu * max(1, a.gpus)
     mesh = checkerboard(n_sub, fine, coarse)
     dof = lambda p: 3 * p[0] * p[1] + p[0] + p[1]
     dof_steps = sum(dof(m) * m[2] for m in mesh)
     config = {"workload": f"{a.config}: {n_sub} subdomains ({find_divisors(n_sub)[0]}x{find_divisors(n_sub)[1]}) checkerboard "
                           f"{fine[0]}^2x{fine[2]} / {coarse[0]}^2x{coarse[2]}, mortar {mortar[0]}x{mortar[1]}x{mortar[2]} degree {k}, "
-                          f"RT0xDGQ0, c0=1, T=0.5, K=I (BASELINE.json configs[1])",
-              "subdomains": n_sub, "dof_steps_per_iteration": dof_steps, "parallelism": f"{max(1, a.gpus)} x 4 subdomains per GPU",
+                          f"RT0xDGQ0, c0=1, T=0.5, K=I (BASELINE.json configs[{dict(cfg3=2, cfg4=3).get(a.config, 1)}])",
+              "subdomains": n_sub, "dof_steps_per_iteration": dof_steps, "parallelism": f"{max(1, a.gpus)} x {per_gpu} subdomains per GPU",
               "l2": "factor stream per step (>= 0.7 GB) exceeds the 126 MB L2; no flush needed"}
 
     if a.impl == "reference":
