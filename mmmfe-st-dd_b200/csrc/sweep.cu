@@ -363,9 +363,7 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
       if (have && state == 0) {
         uint32_t v;
         asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];\n" : "=r"(v) : "r"(s_u32(done_cnt + (lane & (NB - 1)))) : "memory");
-        if (v >= uint32_t(G / NB + 1) * uint32_t(CT / 32 / a.ng)) {
-          if (sig >= 0) red_release(a.cnt + sig);
-          for (int t = 0; t < n_sig; ++t) red_release(a.cnt + a.index[sig_off + t]);
+        if (v >= uint32_t(G / NB + 1) * uint32_t(CT / 32 / a.ng)) {  // (the last compute warp published the completion)
           state = 1;
           progress = true;
         }
@@ -1003,8 +1001,26 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
         long long *tr = a.trace + (int64_t(e_first) + i) * 3;
         tr[0] = g_entry; tr[1] = g_w; tr[2] = global_ns();  // nanoseconds of the global timer: comparable across SMs
       }
+      // The LAST compute warp of the group to finish the entry publishes its completion counters itself (release at
+      // GPU scope; the other warps' writes are ordered before it through the acq_rel update of the shared counter):
+      // the consumers on other CTAs see the completion one polling hop earlier than through the retire warp, which
+      // only frees the ring space and issues the next TMA copies.  The descriptor is read BEFORE the update: once the
+      // count is complete the dependency warp may restage the slot.
       __syncwarp();
-      if (lane == 0) done_signal(done_cnt + slot);
+      if (lane == 0) {
+        const int p_sig = e.sig, p_n = e.n_sig, p_off = e.sig_off;
+        int32_t s0 = -1, s1 = -1;
+        if (p_n > 0) s0 = a.index[p_off];
+        if (p_n > 1) s1 = a.index[p_off + 1];
+        uint32_t old;
+        asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;\n" : "=r"(old) : "r"(s_u32(done_cnt + slot)) : "memory");
+        if (old + 1 == uint32_t(G / NB + 1) * uint32_t(CT / 32 / a.ng)) {
+          if (p_sig >= 0) red_release(a.cnt + p_sig);
+          if (p_n > 0) red_release(a.cnt + s0);
+          if (p_n > 1) red_release(a.cnt + s1);
+          for (int t = 2; t < p_n; ++t) red_release(a.cnt + a.index[p_off + t]);
+        }
+      }
     }
   }
 }
