@@ -64,14 +64,34 @@ const char *build_exchange_plan(const std::vector<ExchangeSide> &sides, int64_t 
   return nullptr;
 }
 
+// Contiguous blocks of subdomains in rank order (the reference launches rank r on subdomain r, README.md:64) that
+// minimise the largest block cost; every rank below min(world, n) owns at least one subdomain, owners are
+// non-decreasing.  Exact linear-partition dynamic programme (n <= a few thousand, world <= 8: microseconds).
 void assign_owners(const std::vector<double> &cost, int32_t world, std::vector<int32_t> &owner) {
+  const int n = int(cost.size());
   owner.assign(cost.size(), 0);
-  if (world <= 1) return;
-  double total = 0, acc = 0;
-  for (double c : cost) total += c;
-  for (size_t r = 0; r < cost.size(); ++r) {
-    owner[r] = std::min(world - 1, int32_t(acc / total * world));
-    acc += cost[r];
+  if (world <= 1 || n == 0) return;
+  const int w = std::min(world, n);
+  std::vector<double> pre(size_t(n) + 1, 0.0);
+  for (int i = 0; i < n; ++i) pre[i + 1] = pre[i] + std::max(cost[i], 0.0);
+  // best[k][i] = smallest possible largest-block cost when the first i subdomains go to k non-empty blocks
+  const double inf = 1e300;
+  std::vector<std::vector<double>> best(size_t(w) + 1, std::vector<double>(size_t(n) + 1, inf));
+  std::vector<std::vector<int>> cut(size_t(w) + 1, std::vector<int>(size_t(n) + 1, 0));
+  best[0][0] = 0.0;
+  for (int k = 1; k <= w; ++k)
+    for (int i = k; i <= n - (w - k); ++i)
+      for (int j = k - 1; j < i; ++j) {
+        if (best[k - 1][j] >= inf) continue;
+        const double v = std::max(best[k - 1][j], pre[i] - pre[j]);
+        // ties: the later cut (more even block sizes towards the end of the rank order)
+        if (v < best[k][i] || (v == best[k][i] && j > cut[k][i])) { best[k][i] = v; cut[k][i] = j; }
+      }
+  int i = n;
+  for (int k = w; k >= 1; --k) {
+    const int j = cut[k][i];
+    for (int r = j; r < i; ++r) owner[r] = k - 1;
+    i = j;
   }
 }
 

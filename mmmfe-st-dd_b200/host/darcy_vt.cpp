@@ -693,6 +693,8 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
   if (mortar_flag != 1) throw std::runtime_error("only the mortar path (mortar_flag = 1) exists, as in the reference driver");
   if (n_sub <= 1) throw std::runtime_error("Mortar MFEM is impossible with 1 subdomain");  // :2066
   if (degree != 0) throw std::runtime_error("space_degree >= 1 is not valid on the space-time mortar path (see DESIGN.md, quirk Q7)");
+  // every rank derives the same ownership table, so this fails on all ranks at once (no rank is left in a collective)
+  if (world > int(n_sub)) throw std::runtime_error("more ranks than subdomains: launch at most one process per subdomain");
   const int qdegree = int(quad_degree);
   unsigned n0, n1;
   find_divisors(n_sub, n0, n1);

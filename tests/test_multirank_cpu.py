@@ -151,6 +151,33 @@ def test_owner_rule_balances_cost_in_contiguous_blocks():
         assert max(loads) <= 1.15 * (sum(cost) / world)
 
 
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_owner_rule_leaves_no_rank_empty_on_the_shipped_parameter_file(world):
+    """Round-1 advisor finding: the default patterns 3^3, 2^3, 4^3, 3^3 at world = 4 left rank 2 without a subdomain
+    (owners [0, 0, 1, 3]), which hangs the reference's native one-rank-per-subdomain launch."""
+    pkg = mmmfe_import.load()
+    cost = [27.0, 8.0, 64.0, 27.0]
+    owner = list(pkg.assign_owners(cost, world))
+    assert owner == sorted(owner) and set(owner) == set(range(world))
+    loads = [sum(c for c, o in zip(cost, owner) if o == w) for w in range(world)]
+    assert max(loads) == {2: 91.0, 3: 64.0, 4: 64.0}[world]  # the optimum of a contiguous split
+
+
+def test_owner_rule_edge_cases():
+    pkg = mmmfe_import.load()
+    assert list(pkg.assign_owners([1, 8, 1, 8], 4)) == [0, 1, 2, 3]
+    assert list(pkg.assign_owners([1, 8, 1, 8], 2)) in ([0, 0, 1, 1], [0, 1, 1, 1])
+    # more ranks than subdomains: the first n ranks get one each (the front-end refuses such a launch up front)
+    assert list(pkg.assign_owners([3, 1], 4)) == [0, 1]
+    assert list(pkg.assign_owners([5.0], 1)) == [0]
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        n, world = int(rng.integers(1, 40)), int(rng.integers(1, 9))
+        cost = rng.uniform(0.5, 9.0, n)
+        owner = list(pkg.assign_owners(cost, world))
+        assert owner == sorted(owner) and set(owner) == set(range(min(n, world)))
+
+
 def test_exchange_plan_reports_missing_neighbours():
     pkg = mmmfe_import.load()
     with pytest.raises(Exception):
