@@ -32,6 +32,7 @@ typedef struct {
   int32_t e2e_iterations;    /* > 0: also time this many host-driven iterations (pinned host q -> device ->   */
                              /* host Ap, classical Gram-Schmidt on the host)                                   */
   int32_t profile;           /* != 0: fill prof_* with mmmfe_profile_step                                      */
+  const char *engine_options; /* NULL or "key=value,key=value" for mmmfe_set_option (before set-up)           */
 } mmmfe_host_options;
 
 typedef struct {
@@ -50,6 +51,11 @@ typedef struct {
   int32_t sweep_batches, sweep_steps[4];
   double sweep_ms[4], sweep_bytes_per_step[4];
   int64_t tune_us_sweep, tune_us_levels, sweep_planned;
+  int64_t tune_rel_diff_e18; /* set-up cross-check: relative l2 difference of the two sweep implementations * 1e18, -1 = not run */
+  /* multiscale-basis (time-Toeplitz) interface operator: 1 when GMRES ran on it, its precompute cost                */
+  int32_t basis_operator, basis_pad;
+  double t_basis, basis_gflop, basis_bytes;
+  int64_t basis_columns;
 } mmmfe_host_report;
 
 void mmmfe_host_default_options(mmmfe_host_options *opt);

@@ -393,7 +393,8 @@ class HostOptions(ctypes.Structure):
                 ("final_sweep", ctypes.c_int32), ("verbose", ctypes.c_int32), ("only_cycle", ctypes.c_int32),
                 ("fixed_iterations", ctypes.c_int32), ("apply_repeat", ctypes.c_int32),
                 ("num_refinement", ctypes.c_int32), ("mortar_degree", ctypes.c_int32), ("output_dir", ctypes.c_char_p),
-                ("warmup_iterations", ctypes.c_int32), ("e2e_iterations", ctypes.c_int32), ("profile", ctypes.c_int32)]
+                ("warmup_iterations", ctypes.c_int32), ("e2e_iterations", ctypes.c_int32), ("profile", ctypes.c_int32),
+                ("engine_options", ctypes.c_char_p)]
 
 
 class HostReport(ctypes.Structure):
@@ -412,7 +413,10 @@ class HostReport(ctypes.Structure):
                 ("prof_launches", ctypes.c_int64 * 6), ("sweep_batches", ctypes.c_int32),
                 ("sweep_steps", ctypes.c_int32 * 4), ("sweep_ms", ctypes.c_double * 4),
                 ("sweep_bytes_per_step", ctypes.c_double * 4), ("tune_us_sweep", ctypes.c_int64),
-                ("tune_us_levels", ctypes.c_int64), ("sweep_planned", ctypes.c_int64)]
+                ("tune_us_levels", ctypes.c_int64), ("sweep_planned", ctypes.c_int64),
+                ("tune_rel_diff_e18", ctypes.c_int64), ("basis_operator", ctypes.c_int32), ("basis_pad", ctypes.c_int32),
+                ("t_basis", ctypes.c_double), ("basis_gflop", ctypes.c_double), ("basis_bytes", ctypes.c_double),
+                ("basis_columns", ctypes.c_int64)]
 
 
 _host = None
@@ -456,7 +460,7 @@ def host_run(parameter_file, nccl_id=None, **options):
         keep = ctypes.create_string_buffer(nccl_id, len(nccl_id))
         opt.nccl_id = ctypes.cast(keep, ctypes.c_void_p)
     for k, v in options.items():
-        if k == "output_dir":
+        if k in ("output_dir", "engine_options"):
             v = v.encode()
         setattr(opt, k, v)
     reps = (HostReport * 16)()

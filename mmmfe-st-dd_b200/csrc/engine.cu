@@ -187,7 +187,8 @@ struct mmmfe_ctx {
   bool keep_history = true, use_graphs = true, use_sweep = true, sweep_evict_first = true;
   int leaf_cells = 8, subtree_cells = 256, sweep_chunk = 7168, sweep_ct = 256, sweep_ctas_per_sm = 1, sweep_groups = 1;
   bool sweep_autotune = true;
-  double tune_ms_sweep = 0.0, tune_ms_levels = 0.0;
+  bool sweep_crosscheck = false;  // with sweep_autotune = 0: still run both implementations once and compare their traces
+  double tune_ms_sweep = 0.0, tune_ms_levels = 0.0, tune_rel_diff = -1.0;
   double sweep_min_fill = 1.75;
   int sweep_mt = 896, sweep_pack = 4;  // 7168 / 896 = one micro-tile per compute warp and wave
   bool sweep_share_blobs = true;
@@ -1065,12 +1066,15 @@ static void setup(mmmfe_ctx *c) {
   }
   CUDA_CHECK(cudaDeviceSynchronize());
   c->is_setup = true;
-  // Both star-sweep implementations are exact; keep the one that is faster for THIS configuration (one timed star
-  // sweep each with the interface data at zero).  The persistent kernel runs the batches one after the other, the
-  // per-level kernels run them concurrently on their own streams, so the winner depends on the mix of subdomains.
+  // Both star-sweep implementations are exact; keep the one that is faster for THIS configuration.  One star sweep
+  // each on the SAME non-zero pseudo-random interface data: the traces of the two implementations must agree to
+  // 1e-11 (set-up fails otherwise -- the persistent kernel's plan depends on the grid, the SM share and M, so this is
+  // the check that the instantiation actually used on this problem is right), and the times decide.  The times are
+  // summed over the ranks, so every rank takes the same decision.  The persistent kernel runs the batches one after
+  // the other, the per-level kernels run them concurrently on their own streams, so the winner depends on the mix.
   bool any_sweep = false;
   for (auto &b : c->batches) any_sweep |= b->sweep;
-  if (any_sweep && c->sweep_autotune) {
+  if (any_sweep && (c->sweep_autotune || c->sweep_crosscheck)) {
     auto timed = [&](bool with_sweep) {
       std::vector<bool> keep;
       for (auto &b : c->batches) { keep.push_back(b->sweep); b->sweep = b->sweep && with_sweep; }
@@ -1085,11 +1089,33 @@ static void setup(mmmfe_ctx *c) {
       for (size_t i = 0; i < keep.size(); ++i) c->batches[i]->sweep = keep[i];
       return double(best);
     };
+    DevBuf<double> ref_trace, tune;
+    ref_trace.alloc(size_t(c->n_fine));
+    tune.alloc(4);
+    tune.zero(c->stream);
+    launch_fill_hash(c->n_fine, 0x5eedull, c->lam_bar.p, c->stream);
     c->tune_ms_sweep = timed(true);
     check_watchdog(c);
+    CUDA_CHECK(cudaMemcpyAsync(ref_trace.p, c->trace.p, size_t(c->n_fine) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     c->tune_ms_levels = timed(false);
-    if (c->tune_ms_levels < c->tune_ms_sweep)
+    launch_diff_norms(c->n_fine, ref_trace.p, c->trace.p, tune.p, c->stream);
+    double h[4] = {0, 0, 0, 0};
+    CUDA_CHECK(cudaMemcpyAsync(h, tune.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->tune_rel_diff = h[1] > 0 ? std::sqrt(h[0] / h[1]) : (h[0] > 0 ? 1.0 : 0.0);
+    if (!(c->tune_rel_diff <= 1e-11))
+      fail(MMMFE_E_NUMERIC, "set-up cross-check: persistent sweep kernel and per-level kernels disagree (relative l2 %.3e)", c->tune_rel_diff);
+    h[0] = c->tune_ms_sweep; h[1] = c->tune_ms_levels;
+    if (c->world > 1) {
+      CUDA_CHECK(cudaMemcpyAsync(tune.p, h, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      allreduce_sum(c, tune.p, 2);
+      CUDA_CHECK(cudaMemcpyAsync(h, tune.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    if (c->sweep_autotune && h[1] < h[0])
       for (auto &b : c->batches) b->sweep = false;
+    c->lam_bar.zero(c->stream); c->trace.zero(c->stream);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
   }
 }
 
@@ -1383,6 +1409,7 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   else if (k == "sweep_ctas_per_sm") c->sweep_ctas_per_sm = std::max(1, int(value));
   else if (k == "sweep_spin_ns") c->sweep_spin_ns = std::max(0, int(value));
   else if (k == "sweep_autotune") c->sweep_autotune = value != 0;
+  else if (k == "sweep_crosscheck") c->sweep_crosscheck = value != 0;
   else if (k == "sweep_groups") {
     if (value != 1 && value != 2 && value != 4 && value != 8) { c->err = "sweep_groups must be 1, 2, 4 or 8"; return MMMFE_E_INVALID; }
     c->sweep_groups = int(value);
@@ -1425,6 +1452,7 @@ int mmmfe_comm_init(mmmfe_ctx *c, int rank, int world, const void *id) {
   c->rank = rank; c->world = world;
   if (world == 1) return MMMFE_OK;
 #ifdef MMMFE_WITH_NCCL
+  if (!id) { c->err = "mmmfe_comm_init: the unique id is required when world > 1"; return MMMFE_E_INVALID; }
   ncclUniqueId uid;
   std::memcpy(&uid, id, sizeof uid);
   cudaSetDevice(c->device);
@@ -1739,6 +1767,8 @@ int64_t mmmfe_stat(const mmmfe_ctx *c, const char *key) {
   if (k == "sweep_planned") { for (auto &b : c->batches) v += b->s_entries.n > 0; return v; }
   if (k == "tune_us_sweep") return int64_t(c->tune_ms_sweep * 1e3);
   if (k == "tune_us_levels") return int64_t(c->tune_ms_levels * 1e3);
+  // relative l2 difference of the two star-sweep implementations at set-up, in units of 1e-18 (-1: not run)
+  if (k == "tune_rel_diff_e18") return c->tune_rel_diff < 0 ? -1 : int64_t(std::min(c->tune_rel_diff * 1e18, 9e18));
   return -1;
 }
 

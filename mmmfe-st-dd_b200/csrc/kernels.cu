@@ -7,6 +7,7 @@
 //  * time stepping, projector SpMV, exchange/combine and the classical Gram-Schmidt kernels.
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <atomic>
 
 namespace mmmfe {
@@ -906,6 +907,46 @@ void launch_axpy_rows(int64_t len, const double *Q, int64_t ldq, int32_t n_rows,
                       cudaStream_t st) {
   if (len <= 0) return;
   k_axpy_rows<<<unsigned((len + 255) / 256), 256, 0, st>>>(len, Q, ldq, n_rows, y, out);
+  launch_counter_add(1);
+}
+
+// =================================================================================================================
+// diagnostics of the set-up cross-check: reproducible pseudo-random data and ||a - b||^2, ||b||^2
+// =================================================================================================================
+__global__ void __launch_bounds__(256) k_fill_hash(int64_t n, uint64_t seed, double *__restrict__ out) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  uint64_t x = uint64_t(i) + seed * 0x9e3779b97f4a7c15ull;  // splitmix64
+  x += 0x9e3779b97f4a7c15ull; x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull; x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  out[i] = double(x >> 11) * (2.0 / 9007199254740992.0) - 1.0;  // uniform in [-1, 1)
+}
+
+void launch_fill_hash(int64_t n, uint64_t seed, double *out, cudaStream_t st) {
+  if (n <= 0) return;
+  k_fill_hash<<<unsigned((n + 255) / 256), 256, 0, st>>>(n, seed, out);
+  launch_counter_add(1);
+}
+
+__global__ void __launch_bounds__(512) k_diff_norms(int64_t n, const double *__restrict__ a, const double *__restrict__ b,
+                                                    double *__restrict__ out) {
+  __shared__ double sm[16];
+  double d2 = 0.0, b2 = 0.0;
+  for (int64_t j = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; j < n; j += int64_t(gridDim.x) * blockDim.x) {
+    const double d = a[j] - b[j];
+    d2 += d * d;
+    b2 += b[j] * b[j];
+  }
+  const double r0 = block_sum_512(d2, sm);
+  __syncthreads();
+  const double r1 = block_sum_512(b2, sm);
+  if (threadIdx.x == 0) { atomicAdd(out, r0); atomicAdd(out + 1, r1); }
+}
+
+// out[0] += ||a - b||^2, out[1] += ||b||^2 (out must be zeroed by the caller)
+void launch_diff_norms(int64_t n, const double *a, const double *b, double *out, cudaStream_t st) {
+  if (n <= 0) return;
+  k_diff_norms<<<unsigned(std::min<int64_t>(592, (n + 511) / 512)), 512, 0, st>>>(n, a, b, out);
   launch_counter_add(1);
 }
 

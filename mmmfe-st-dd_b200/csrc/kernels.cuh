@@ -151,4 +151,8 @@ void launch_scale_store(int64_t len, const double *w, double inv, double *dst, c
 void launch_axpy_rows(int64_t len, const double *Q, int64_t ldq, int32_t n_rows, const double *y, double *out,
                       cudaStream_t st);
 
+// ---- diagnostics -----------------------------------------------------------------------------------------------
+void launch_fill_hash(int64_t n, uint64_t seed, double *out, cudaStream_t st);
+void launch_diff_norms(int64_t n, const double *a, const double *b, double *out, cudaStream_t st);
+
 }  // namespace mmmfe

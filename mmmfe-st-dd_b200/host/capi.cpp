@@ -51,6 +51,7 @@ int mmmfe_host_run(const char *parameter_file, const mmmfe_host_options *opt, mm
     rc.apply_repeat = o.apply_repeat; rc.keep_lambda = true;
     rc.warmup_iterations = o.warmup_iterations; rc.e2e_iterations = o.e2e_iterations; rc.profile = o.profile != 0;
     if (o.output_dir) rc.output_dir = o.output_dir;
+    if (o.engine_options) rc.engine_options = o.engine_options;
     problem_2d.run(num_refinement, mesh_m3d, tolerence, max_iteration, mortar_degree + 1);
     const auto &reps = problem_2d.reports();
     int n = 0;
@@ -71,6 +72,9 @@ int mmmfe_host_run(const char *parameter_file, const mmmfe_host_options *opt, mm
         d.sweep_batches = r.sweep_batches;
         for (int k = 0; k < 4; ++k) { d.sweep_steps[k] = r.sweep_steps[k]; d.sweep_ms[k] = r.sweep_ms[k]; d.sweep_bytes_per_step[k] = r.sweep_bytes_per_step[k]; }
         d.tune_us_sweep = r.tune_us_sweep; d.tune_us_levels = r.tune_us_levels; d.sweep_planned = r.sweep_planned;
+        d.tune_rel_diff_e18 = r.tune_rel_diff_e18;
+        d.basis_operator = r.basis_operator; d.basis_pad = 0; d.t_basis = r.t_basis; d.basis_gflop = r.basis_gflop;
+        d.basis_bytes = r.basis_bytes; d.basis_columns = r.basis_columns;
       }
       ++n;
     }

@@ -2,7 +2,8 @@
 // parameter.txt, space-time-plots/ and time-step-plots/.  No arguments are needed; the number of subdomains is the
 // number of mesh_pattern_sub_d* lines (the reference takes it from `mpirun -n j`).  Under torchrun/mpirun-style
 // launchers RANK, WORLD_SIZE and LOCAL_RANK select one GPU per process; the NCCL id travels through the file named
-// by $MMMFE_NCCL_ID_FILE (default ./.mmmfe_nccl_id).
+// by $MMMFE_NCCL_ID_FILE (default ./.mmmfe_nccl_id.<MASTER_PORT>).  A file left behind by a crashed launch is never
+// consumed: rank 0 removes it before writing, the other ranks only accept a file written after they started.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -10,6 +11,8 @@
 #include <iostream>
 #include <thread>
 #include <vector>
+
+#include <sys/stat.h>
 
 #include "darcy_vt.h"
 #include "mmmfe_b200.h"
@@ -41,30 +44,38 @@ int main(int argc, char *argv[]) {
     problem_2d.control.rank = rank;
     problem_2d.control.world = world;
     problem_2d.control.device = env_int("LOCAL_RANK", -1);
+    std::string id_path;
     if (world > 1) {
       const char *p = std::getenv("MMMFE_NCCL_ID_FILE");
-      const std::string path = p ? p : ".mmmfe_nccl_id";
+      const char *port = std::getenv("MASTER_PORT");
+      id_path = p ? p : std::string(".mmmfe_nccl_id.") + (port ? port : "0");
+      const auto started = std::chrono::system_clock::to_time_t(std::chrono::system_clock::now());
       if (rank == 0) {
+        std::remove(id_path.c_str());
         if (mmmfe_comm_unique_id(id.data()) != 0) throw std::runtime_error("NCCL is not available");
-        std::ofstream tmp(path + ".tmp", std::ios::binary);
+        std::ofstream tmp(id_path + ".tmp", std::ios::binary);
         tmp.write(id.data(), mmmfe_comm_unique_id_size());
         tmp.close();
-        std::rename((path + ".tmp").c_str(), path.c_str());
+        std::rename((id_path + ".tmp").c_str(), id_path.c_str());
       } else {
         for (int tries = 0;; ++tries) {
-          std::ifstream in(path, std::ios::binary);
-          if (in && in.read(id.data(), mmmfe_comm_unique_id_size())) break;
-          if (tries > 600) throw std::runtime_error("timed out waiting for " + path);
+          struct stat sb;
+          // launchers start the ranks within seconds of each other: anything older than that is a stale file
+          if (::stat(id_path.c_str(), &sb) == 0 && sb.st_mtime + 20 >= started) {
+            std::ifstream in(id_path, std::ios::binary);
+            if (in && in.read(id.data(), mmmfe_comm_unique_id_size())) break;
+          }
+          if (tries > 600) throw std::runtime_error("timed out waiting for " + id_path);
           std::this_thread::sleep_for(std::chrono::milliseconds(100));
         }
       }
       problem_2d.control.nccl_id = id.data();
     }
+    struct IdFileGuard {  // rank 0 removes the id file however run() ends
+      std::string path; bool mine;
+      ~IdFileGuard() { if (mine && !path.empty()) std::remove(path.c_str()); }
+    } id_guard{id_path, rank == 0};
     problem_2d.run(num_refinement, mesh_m3d, tolerence, max_iteration, mortar_degree + 1);
-    if (world > 1 && rank == 0) {
-      const char *p = std::getenv("MMMFE_NCCL_ID_FILE");
-      std::remove(p ? p : ".mmmfe_nccl_id");
-    }
   } catch (std::exception &exc) {
     std::cerr << std::endl << std::endl << "----------------------------------------------------" << std::endl;
     std::cerr << "Exception on processing: " << std::endl << exc.what() << std::endl << "Aborting!" << std::endl

@@ -750,6 +750,19 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
       throw std::runtime_error("no usable CUDA device: the interface-GMRES path has no CPU fallback");
     struct Guard { mmmfe_ctx *c; ~Guard() { mmmfe_destroy(c); } } guard{ctx};
     mmmfe_set_option(ctx, "keep_history", control.final_sweep ? 1 : 0);
+    {
+      std::string all;
+      if (const char *env = std::getenv("MMMFE_ENGINE_OPTIONS")) all = env;
+      if (!control.engine_options.empty()) all += (all.empty() ? "" : ",") + control.engine_options;
+      std::stringstream ss(all);
+      std::string item;
+      while (std::getline(ss, item, ',')) {
+        const size_t eq = item.find('=');
+        if (item.empty()) continue;
+        if (eq == std::string::npos) throw std::runtime_error("engine option '" + item + "' is not key=value");
+        check(ctx, mmmfe_set_option(ctx, item.substr(0, eq).c_str(), std::atof(item.c_str() + eq + 1)), "mmmfe_set_option");
+      }
+    }
     if (world > 1) {
       check(ctx, mmmfe_comm_init(ctx, rank, world, control.nccl_id), "mmmfe_comm_init");
       check(ctx, mmmfe_set_owners(ctx, int(n_sub), owner.data()), "mmmfe_set_owners");
@@ -775,6 +788,8 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
     rep.factor_values = mmmfe_factor_values(ctx);
     rep.factor_flops = mmmfe_factor_flops(ctx);
     rep.factor_groups = mmmfe_num_factor_groups(ctx);
+    rep.sweep_batches = int(mmmfe_stat(ctx, "sweep_batches"));
+    rep.tune_rel_diff_e18 = mmmfe_stat(ctx, "tune_rel_diff_e18");
     for (auto &sp : subs) { rep.dof_steps += (long long)sp->n * sp->nt; sp->matrix = Csr(); }
     // ---- bar problems ----
     t0 = clk::now();

@@ -50,6 +50,11 @@ struct CycleReport {
   int sweep_batches = 0, sweep_steps[4] = {0, 0, 0, 0};
   double sweep_ms[4] = {0, 0, 0, 0}, sweep_bytes_per_step[4] = {0, 0, 0, 0};
   long long tune_us_sweep = 0, tune_us_levels = 0, sweep_planned = 0;
+  long long tune_rel_diff_e18 = -1;  // set-up cross-check of the two star-sweep implementations (relative l2 * 1e18)
+  // multiscale-basis (time-Toeplitz) operator, when the engine built it
+  int basis_operator = 0;
+  double t_basis = 0.0, basis_gflop = 0.0, basis_bytes = 0.0;
+  long long basis_columns = 0;
 };
 
 struct RunControl {
@@ -69,6 +74,9 @@ struct RunControl {
   int apply_repeat = 0;         // > 0: additionally time this many device-resident operator applications
   double apply_ms = 0.0;        // out
   std::string output_dir = ".";
+  // engine options "key=value,key=value" passed to mmmfe_set_option before set-up (after those of the environment
+  // variable MMMFE_ENGINE_OPTIONS, same format), e.g. "use_sweep=1,sweep_autotune=0"
+  std::string engine_options;
 };
 
 void parameter_pull_in(double &c_0, double &alpha, int &space_degree, int &mortar_degree, int &num_refinement,

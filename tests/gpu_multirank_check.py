@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from helpers import ROOT, mo, pkg, rel_l2
+from helpers import LAMBDA_TOL_CONVERGED, ROOT, mo, pkg, rel_l2
 
 
 def unique_id(rank):
@@ -32,6 +32,9 @@ def unique_id(rank):
     return bytes(buf.cpu().numpy().tobytes())
 
 
+SWEEP_ON = "use_sweep=1,sweep_autotune=0,sweep_crosscheck=1,subtree_cells=64"
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -41,7 +44,13 @@ def main():
         "default_2x2": dict(file=os.path.join(ROOT, "parameter.txt"), kw=dict(num_refinement=2)),
         "checker_4x4": dict(mesh=[[12, 12, 6] if ((r % 4) + (r // 4)) % 2 == 0 else [6, 6, 3] for r in range(16)],
                             mortar=[3, 3, 2], kw={}),
-        "nonmatching_2x2_sweep": dict(mesh=[[64, 64, 16], [32, 32, 8], [32, 32, 8], [64, 64, 16]], mortar=[16, 16, 4], kw={}),
+        # the persistent sweep kernel forced on (the set-up autotuner would pick the per-level kernels at these sizes),
+        # cross-checked against the per-level kernels at set-up
+        "nonmatching_2x2_sweep": dict(mesh=[[64, 64, 16], [32, 32, 8], [32, 32, 8], [64, 64, 16]], mortar=[16, 16, 4],
+                                      kw=dict(engine_options=SWEEP_ON), sweep=True),
+        # 4x4 checkerboard: 8 subdomains per rank = one batch of FOUR right-hand sides per colour and rank
+        "checker_4x4_sweep_m4": dict(mesh=[[64, 64, 8] if ((r % 4) + (r // 4)) % 2 == 0 else [32, 32, 4] for r in range(16)],
+                                     mortar=[8, 8, 2], kw=dict(engine_options=SWEEP_ON), sweep=True),
     }
     results, ok = {}, True
     for name, c in cases.items():
@@ -72,13 +81,14 @@ def main():
             prm.num_refinement = c["kw"]["num_refinement"]
         ref = mo.run(prm)
         r, o = reps[-1], ref[-1]
-        tol_lam = 1e-10 if o.gmres_iterations < 60 else 5 * prm.tolerance
+        tol_lam = 1e-10 if o.gmres_iterations < 40 else LAMBDA_TOL_CONVERGED  # tests/test_oracle_sensitivity.py
         entry = {"world": world, "iterations": r["gmres_iterations"], "oracle_iterations": o.gmres_iterations,
                  "r_norm_rel": abs(r["r_norm"] - o.r_norm) / o.r_norm, "lambda_rel_l2": rel_l2(lam, o.lam),
                  "errors_rel": max(abs(r[k] - o.errors[k]) / o.errors[k] for k in o.errors) if o.errors else None,
                  "sweep_batches": r.get("sweep_batches")}
+        entry["tune_rel_diff"] = r.get("tune_rel_diff_e18", -1) * 1e-18 if r.get("tune_rel_diff_e18", -1) >= 0 else None
         entry["ok"] = bool(abs(entry["iterations"] - entry["oracle_iterations"]) <= 1 and entry["r_norm_rel"] < 1e-11
-                           and entry["lambda_rel_l2"] < tol_lam)
+                           and entry["lambda_rel_l2"] < tol_lam and (not c.get("sweep") or entry["sweep_batches"] > 0))
         ok = ok and entry["ok"]
         results[name] = entry
         print(name, json.dumps(entry), flush=True)

@@ -106,3 +106,31 @@ def set_bar_data(eng, prob, local=None):
 
 def rel_l2(a, b):
     return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))
+
+
+# ---- tolerance of lambda after a converged GMRES run -------------------------------------------------------------
+# tests/test_oracle_sensitivity.py measures on the oracle alone that a relative perturbation eps of every operator
+# application moves the converged lambda by 75-150 eps (59 and 82 iterations; the iteration count does not move).
+# The CUDA operator agrees with the oracle's to OPERATOR_TOL (different direct solvers), so after a converged run
+# lambda can differ by up to LAMBDA_AMPLIFICATION * OPERATOR_TOL; runs of a few iterations stay at OPERATOR_TOL.
+OPERATOR_TOL = 1e-10
+LAMBDA_AMPLIFICATION = 200.0
+LAMBDA_TOL_CONVERGED = LAMBDA_AMPLIFICATION * OPERATOR_TOL
+
+
+def perturbed_gmres(prob, eps, seed):
+    """The oracle's local_gmres with every operator application multiplied entry-wise by (1 + eps * u), u uniform in
+    [-1, 1]: the experiment behind LAMBDA_AMPLIFICATION."""
+    rng = np.random.default_rng(seed)
+    orig = mo.Problem.apply_S
+
+    def noisy(self, q):
+        ap = orig(self, q)
+        return ap * (1.0 + eps * rng.uniform(-1, 1, ap.shape)) if eps > 0 else ap
+
+    mo.Problem.apply_S = noisy
+    try:
+        lam, its, _, res = prob.local_gmres()
+    finally:
+        mo.Problem.apply_S = orig
+    return lam, its, res

@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from helpers import ROOT, default_params, mo, pkg, rel_l2
+from helpers import LAMBDA_TOL_CONVERGED, ROOT, default_params, mo, pkg, rel_l2
 
 pytestmark = pytest.mark.gpu
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "report_tables.json")))
@@ -55,14 +55,13 @@ def test_medium_nonmatching_grids_match_oracle(tmp_path):
     r = reps[0]
     assert abs(r["gmres_iterations"] - o.gmres_iterations) <= 1
     assert r["r_norm"] == pytest.approx(o.r_norm, rel=1e-11)
-    # ~95 iterations of un-restarted classical Gram-Schmidt GMRES amplify 1-ulp differences of the operator to
-    # ~4e-7 in lambda (measured on the oracle against itself): the computed lambda is only
-    # defined to the stop tolerance (1e-6), the early residual history and the error columns are reproducible.
-    n = min(len(res), len(o.residuals), 20)
+    # ~95 iterations: the residual history is reproducible; lambda to the measured amplification of operator
+    # round-off (helpers.LAMBDA_TOL_CONVERGED = 200 x 1e-10, tests/test_oracle_sensitivity.py)
+    n = min(len(res), len(o.residuals))
     np.testing.assert_allclose(res[:n], o.residuals[:n], rtol=1e-5)
-    assert rel_l2(lam, o.lam) < 5 * prm.tolerance
+    assert rel_l2(lam, o.lam) < LAMBDA_TOL_CONVERGED
     for c in COLS:
-        assert r[c] == pytest.approx(o.errors[c], rel=1e-5), c
+        assert r[c] == pytest.approx(o.errors[c], rel=1e-7 if r["gmres_iterations"] == o.gmres_iterations else 1e-5), c
     assert r["factor_groups"] == 2
 
 
@@ -126,4 +125,5 @@ def test_two_gpus_reproduce_the_oracle(tmp_path):
     run = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=os.path.join(ROOT, "tests"))
     assert run.returncode == 0, run.stdout[-2000:] + run.stderr[-2000:]
     res = json.load(open(out))
-    assert all(v["ok"] for v in res.values()) and len(res) == 3
+    assert all(v["ok"] for v in res.values()) and len(res) == 4
+    assert res["nonmatching_2x2_sweep"]["sweep_batches"] > 0 and res["checker_4x4_sweep_m4"]["sweep_batches"] > 0

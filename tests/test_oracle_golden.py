@@ -41,24 +41,17 @@ def test_table2_linear_mortar_cycles_0_to_3():
 @pytest.mark.slow
 def test_table2_linear_mortar_cycle_4():
     res = mo.run(_params(1, 5), cycles=[4])
-    # errors match in every digit; the iteration count (82 vs 86 published) drifts with CGS round-off
+    # errors match in every digit; 82 iterations against 86 published.  Not a round-off effect (the count is stable
+    # under operator perturbations up to 1e-8, tests/test_oracle_sensitivity.py): the March-2020 report predates the
+    # current source, whose counts also differ by +1, +1, +1, 0 in cycles 0-3.  Parity of the COUNT is unpinned here.
     _check_row(res[0], GOLD["table2_linear_mortar"]["rows"][4], its_slack=4)
 
 
 def test_table4_quadratic_mortar_cycle_0():
-    """Quadratic mortar: reproduced only with the lower-cell / earlier-level tie rule (quirk Q5)."""
+    """Quadratic mortar: reproduced only with the lower-cell / earlier-level tie rule (quirk Q5); rows 3 and 5 are
+    bracketed, not reproduced -- see tests/test_oracle_ties.py for why."""
     res = mo.run(_params(2, 1))
     _check_row(res[0], GOLD["table4_quadratic_mortar"]["rows"][0], its_slack=1)
-
-
-def test_table4_row3_is_a_known_parity_hazard():
-    """Rows 3 and 5 of Table 4 depend on deal.II's search-order-dependent point location on ties with
-    fine/mortar ratios > 2; no uniform tie rule reproduces them.  Recorded, not hidden: errors agree to
-    ~3 % in velocity/pressure L2, not to the printed digits."""
-    res = mo.run(_params(2, 3), cycles=[2])[0]
-    row = GOLD["table4_quadratic_mortar"]["rows"][1]
-    assert res.errors["velocity_l2l2"] == pytest.approx(row["velocity_l2l2"], rel=0.05)
-    assert res.errors["pressure_l2l2"] == pytest.approx(row["pressure_l2l2"], rel=0.05)
 
 
 def test_survey_probe_values_cycle0():
