@@ -33,6 +33,8 @@ typedef struct {
                              /* host Ap, classical Gram-Schmidt on the host)                                   */
   int32_t profile;           /* != 0: fill prof_* with mmmfe_profile_step                                      */
   const char *engine_options; /* NULL or "key=value,key=value" for mmmfe_set_option (before set-up)           */
+  int32_t also_solve;        /* with fixed_iterations: then also the converged solve (file tolerance), timed      */
+  int32_t skip_fetch;        /* != 0: final sweep on the device only, solutions stay there (timing of big runs)   */
 } mmmfe_host_options;
 
 typedef struct {
@@ -56,6 +58,9 @@ typedef struct {
   int32_t basis_operator, basis_pad;
   double t_basis, basis_gflop, basis_bytes;
   int64_t basis_columns;
+  /* converged solve after the fixed-iteration timing (also_solve)                                                     */
+  int32_t solve_iterations, solve_converged;
+  double t_solve_gmres, solve_final_residual;
 } mmmfe_host_report;
 
 void mmmfe_host_default_options(mmmfe_host_options *opt);

@@ -394,7 +394,7 @@ class HostOptions(ctypes.Structure):
                 ("fixed_iterations", ctypes.c_int32), ("apply_repeat", ctypes.c_int32),
                 ("num_refinement", ctypes.c_int32), ("mortar_degree", ctypes.c_int32), ("output_dir", ctypes.c_char_p),
                 ("warmup_iterations", ctypes.c_int32), ("e2e_iterations", ctypes.c_int32), ("profile", ctypes.c_int32),
-                ("engine_options", ctypes.c_char_p)]
+                ("engine_options", ctypes.c_char_p), ("also_solve", ctypes.c_int32), ("skip_fetch", ctypes.c_int32)]
 
 
 class HostReport(ctypes.Structure):
@@ -416,7 +416,9 @@ class HostReport(ctypes.Structure):
                 ("tune_us_levels", ctypes.c_int64), ("sweep_planned", ctypes.c_int64),
                 ("tune_rel_diff_e18", ctypes.c_int64), ("basis_operator", ctypes.c_int32), ("basis_pad", ctypes.c_int32),
                 ("t_basis", ctypes.c_double), ("basis_gflop", ctypes.c_double), ("basis_bytes", ctypes.c_double),
-                ("basis_columns", ctypes.c_int64)]
+                ("basis_columns", ctypes.c_int64), ("solve_iterations", ctypes.c_int32),
+                ("solve_converged", ctypes.c_int32), ("t_solve_gmres", ctypes.c_double),
+                ("solve_final_residual", ctypes.c_double)]
 
 
 _host = None

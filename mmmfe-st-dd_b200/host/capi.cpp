@@ -52,6 +52,7 @@ int mmmfe_host_run(const char *parameter_file, const mmmfe_host_options *opt, mm
     rc.warmup_iterations = o.warmup_iterations; rc.e2e_iterations = o.e2e_iterations; rc.profile = o.profile != 0;
     if (o.output_dir) rc.output_dir = o.output_dir;
     if (o.engine_options) rc.engine_options = o.engine_options;
+    rc.also_solve = o.also_solve != 0; rc.fetch_solution = o.skip_fetch == 0;
     problem_2d.run(num_refinement, mesh_m3d, tolerence, max_iteration, mortar_degree + 1);
     const auto &reps = problem_2d.reports();
     int n = 0;
@@ -75,6 +76,8 @@ int mmmfe_host_run(const char *parameter_file, const mmmfe_host_options *opt, mm
         d.tune_rel_diff_e18 = r.tune_rel_diff_e18;
         d.basis_operator = r.basis_operator; d.basis_pad = 0; d.t_basis = r.t_basis; d.basis_gflop = r.basis_gflop;
         d.basis_bytes = r.basis_bytes; d.basis_columns = r.basis_columns;
+        d.solve_iterations = r.solve_iterations; d.solve_converged = r.solve_converged;
+        d.t_solve_gmres = r.t_solve_gmres; d.solve_final_residual = r.solve_final_residual;
       }
       ++n;
     }

@@ -50,6 +50,9 @@ struct CycleReport {
   int sweep_batches = 0, sweep_steps[4] = {0, 0, 0, 0};
   double sweep_ms[4] = {0, 0, 0, 0}, sweep_bytes_per_step[4] = {0, 0, 0, 0};
   long long tune_us_sweep = 0, tune_us_levels = 0, sweep_planned = 0;
+  // converged solve after a fixed-iteration timing run (RunControl::also_solve)
+  int solve_iterations = 0, solve_converged = 0;
+  double t_solve_gmres = 0.0, solve_final_residual = 0.0;
   long long tune_rel_diff_e18 = -1;  // set-up cross-check of the two star-sweep implementations (relative l2 * 1e18)
   // multiscale-basis (time-Toeplitz) operator, when the engine built it
   int basis_operator = 0;
@@ -77,6 +80,12 @@ struct RunControl {
   // engine options "key=value,key=value" passed to mmmfe_set_option before set-up (after those of the environment
   // variable MMMFE_ENGINE_OPTIONS, same format), e.g. "use_sweep=1,sweep_autotune=0"
   std::string engine_options;
+  // with fixed_iterations >= 0: afterwards also run the converged solve (tolerance and max_iteration of the parameter
+  // file) in the same context and report its iteration count and time (time-to-solution of the benchmarks)
+  bool also_solve = false;
+  // false: the final sweep runs on the device but the [nt][n] solutions are not copied to the host (no error norms, no
+  // output files): timing runs of problems whose full space-time solution is tens of GB
+  bool fetch_solution = true;
 };
 
 void parameter_pull_in(double &c_0, double &alpha, int &space_degree, int &mortar_degree, int &num_refinement,

@@ -1,0 +1,88 @@
+"""Parity at the sizes that are benchmarked (round-1 verdict, item 1): the k_sweep instantiations bench.py times --
+1024^2 / 512^2 fronts with non-direct micro-tiles, 13 top levels, the 134 + 14 SM split, M = 2 and M = 4 batches --
+against the oracle (spatial size of configs[1], few time steps so that the CPU side takes a minute) and against the
+per-level kernels at the FULL problem (all time steps, pseudo-random interface data, set-up cross-check)."""
+import os
+import time
+
+import numpy as np
+import pytest
+
+from helpers import default_params, mo, pkg, rel_l2
+
+pytestmark = pytest.mark.gpu
+SWEEP_ON = "use_sweep=1,sweep_autotune=0,sweep_crosscheck=1"
+
+
+def _problem_without_lu(mesh, mortar, k=1):
+    prm = default_params(k)
+    prob = mo.Problem(prm, len(mesh), mesh, mortar)
+    for sd in prob.subs:
+        sd.matrix = sd.assemble_matrix()
+        sd.rhs_bc = np.zeros(sd.n)
+        sd.con_dofs, sd.con_vals = np.zeros(0, dtype=np.int64), np.zeros(0)
+        sd.f2c, sd.c2f = {}, {}
+        for side in range(4):
+            if sd.neighbors[side] >= 0:
+                sd.f2c[side], sd.c2f[side] = mo.projector_tables(sd, side, prob.mortar, prob.k)
+    return prob
+
+
+def test_configs1_spatial_size_through_k_sweep_matches_oracle():
+    """2x2, 1024^2 x 8 / 512^2 x 4, mortar 256 x 256 x 2 (configs[1] with nt / 32): S q and the star traces of the
+    persistent sweep kernel against nested-dissection SuperLU solves of the saddle matrix, 1e-10."""
+    mesh = [[1024, 1024, 8], [512, 512, 4], [512, 512, 4], [1024, 1024, 8]]
+    prob = _problem_without_lu(mesh, [256, 256, 2])
+    t0 = time.time()
+    lus = {}
+    for sd in prob.subs:  # subdomains 0/3 and 1/2 have identical matrices: one LU each
+        key = (sd.nx, sd.ny, sd.nt)
+        if key not in lus:
+            lus[key] = mo._PermutedLU(sd.matrix, mo.nested_dissection_order(sd.nx, sd.ny))
+        sd.lu = lus[key]
+    print(f"oracle LU {time.time() - t0:.1f}s", flush=True)
+    q = np.random.default_rng(31).standard_normal(prob.n_iface)
+    t0 = time.time()
+    ref = prob.apply_S(q)
+    print(f"oracle S q {time.time() - t0:.1f}s", flush=True)
+    eng = pkg().Engine()
+    for key, val in dict(use_sweep=1, sweep_autotune=0, sweep_crosscheck=1).items():
+        eng.set_option(key, val)
+    for sd in prob.subs:
+        eng.add_subdomain(global_id=sd.r, nx=sd.nx, ny=sd.ny, nt=sd.nt, dt=sd.dt, matrix=sd.matrix.tocsr(), n_flux=sd.nf,
+                          n_pressure=sd.np, neighbor=sd.neighbors, side_dofs=[np.asarray(e) for e in sd.side_edges],
+                          f2c=sd.f2c, c2f=sd.c2f)
+    eng.setup()
+    assert eng.stat("sweep_batches") == eng.stat("batches") == 2
+    assert 0 <= eng.stat("tune_rel_diff_e18") <= 1e-12 * 1e18
+    out = eng.apply(q)
+    assert np.array_equal(out, eng.apply(q))
+    assert rel_l2(out, ref) < 1e-10
+    for li in (0, 1):
+        tr, _ = prob.star_sweep(prob.subs[li], prob.split(q, prob.subs[li]))
+        for side, t in tr.items():
+            assert rel_l2(eng.get_star_trace(li, side).ravel(), t) < 1e-10
+    eng.close()
+
+
+@pytest.mark.parametrize("name,mesh,mortar,k,batches", [
+    # BASELINE.json configs[1], the bench line: M = 2 batches, 1024^2 x 256 and 512^2 x 128
+    ("configs1_full", [[1024, 1024, 256], [512, 512, 128], [512, 512, 128], [1024, 1024, 256]], [256, 256, 64], 1, 2),
+    # one GPU's share of configs[2]: eight subdomains, M = 4 batches of 512^2 x 128 and 256^2 x 64
+    ("configs2_share", [[512, 512, 128] if ((r % 4) + (r // 4)) % 2 == 0 else [256, 256, 64] for r in range(8)],
+     [128, 128, 32], 1, 2),
+    # one GPU's share of configs[3] (the north-star problem): M = 4 batches of 256^2 x 512 and 128^2 x 256, quadratic mortar
+    ("configs3_share", [[256, 256, 512] if ((r % 4) + (r // 4)) % 2 == 0 else [128, 128, 256] for r in range(8)],
+     [16, 16, 32], 2, 2),
+])
+def test_full_problem_k_sweep_equals_per_level_kernels(tmp_path, name, mesh, mortar, k, batches):
+    """The FULL benched problems (all time steps): one star sweep of the persistent kernel and one of the per-level
+    kernels on the same pseudo-random interface data, traces compared on the device at set-up (engine option
+    sweep_crosscheck): relative l2 <= 1e-12.  Then two GMRES iterations run on the forced sweep path."""
+    p = pkg().write_parameter_file(str(tmp_path / "parameter.txt"), mesh, mortar, mortar_degree=k)
+    reps, res, _ = pkg().host_run(p, verbose=0, write_output=0, compute_errors=0, final_sweep=0, fixed_iterations=2,
+                                  engine_options=SWEEP_ON)
+    r = reps[0]
+    assert r["sweep_batches"] == batches
+    assert 0 <= r["tune_rel_diff_e18"] <= 1e-12 * 1e18, r["tune_rel_diff_e18"] * 1e-18
+    assert r["gmres_iterations"] == 2 and np.all(np.isfinite(res)) and 0 < res[-1] < 1.0
