@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from helpers import LAMBDA_TOL_CONVERGED, ROOT, mo, pkg, rel_l2
+from helpers import ROOT, lambda_tolerance, mo, pkg, rel_l2
 
 
 def unique_id(rank):
@@ -79,13 +79,18 @@ def main():
         prm = mo.parse_parameter_file(pfile)
         if "num_refinement" in c["kw"]:
             prm.num_refinement = c["kw"]["num_refinement"]
-        ref = mo.run(prm)
-        r, o = reps[-1], ref[-1]
-        tol_lam = 1e-10 if o.gmres_iterations < 40 else LAMBDA_TOL_CONVERGED  # tests/test_oracle_sensitivity.py
+        n_sub = len(prm.mesh) - 1
+        meshes = mo.refined_meshes(prm, n_sub)
+        for idx, msh in enumerate(meshes):  # the last cycle is compared
+            prob = mo.Problem(prm, n_sub, msh[:-1], msh[-1])
+            o = prob.run_cycle(idx) if idx == len(meshes) - 1 else None
+        r = reps[-1]
+        # lambda: 1e-10, or 10x what a 1e-11 perturbation of the operator does to the oracle itself when that is more
+        tol_lam, spread, _ = lambda_tolerance(prob, o.lam) if o.gmres_iterations >= 40 else (1e-10, None, None)
         entry = {"world": world, "iterations": r["gmres_iterations"], "oracle_iterations": o.gmres_iterations,
                  "r_norm_rel": abs(r["r_norm"] - o.r_norm) / o.r_norm, "lambda_rel_l2": rel_l2(lam, o.lam),
                  "errors_rel": max(abs(r[k] - o.errors[k]) / o.errors[k] for k in o.errors) if o.errors else None,
-                 "sweep_batches": r.get("sweep_batches")}
+                 "sweep_batches": r.get("sweep_batches"), "lambda_tol": tol_lam, "oracle_spread_at_1e-11": spread}
         entry["tune_rel_diff"] = r.get("tune_rel_diff_e18", -1) * 1e-18 if r.get("tune_rel_diff_e18", -1) >= 0 else None
         entry["ok"] = bool(abs(entry["iterations"] - entry["oracle_iterations"]) <= 1 and entry["r_norm_rel"] < 1e-11
                            and entry["lambda_rel_l2"] < tol_lam and (not c.get("sweep") or entry["sweep_batches"] > 0))

@@ -109,18 +109,20 @@ def rel_l2(a, b):
 
 
 # ---- tolerance of lambda after a converged GMRES run -------------------------------------------------------------
-# tests/test_oracle_sensitivity.py measures on the oracle alone that a relative perturbation eps of every operator
-# application moves the converged lambda by 75-150 eps (59 and 82 iterations; the iteration count does not move).
-# The CUDA operator agrees with the oracle's to OPERATOR_TOL (different direct solvers), so after a converged run
-# lambda can differ by up to LAMBDA_AMPLIFICATION * OPERATOR_TOL; runs of a few iterations stay at OPERATOR_TOL.
+# The reference's GMRES (classical Gram-Schmidt, no re-orthogonalisation, no restart) amplifies round-off of the
+# operator into lambda by a factor that depends strongly on the problem: measured on the oracle alone
+# (tests/test_oracle_sensitivity.py) 75-150 for the refinement cycles of the shipped parameter.txt (59 and 82
+# iterations), but ~4e7 for the 2x2 non-matching 96^2/48^2 case (95 iterations: a 1-ulp perturbation of every
+# operator application moves lambda by 5e-9 and the late residual history by 0.3 %).  The CUDA operator agrees with
+# the oracle's to ~1e-12 (different direct solvers; the tests assert OPERATOR_TOL), so a converged lambda can only be
+# compared to what the SAME perturbation does to the oracle itself: lambda_tolerance() measures that, per problem.
 OPERATOR_TOL = 1e-10
-LAMBDA_AMPLIFICATION = 200.0
-LAMBDA_TOL_CONVERGED = LAMBDA_AMPLIFICATION * OPERATOR_TOL
+LAMBDA_AMPLIFICATION = 200.0  # bound for the cycles of the shipped parameter.txt (asserted in test_oracle_sensitivity)
 
 
 def perturbed_gmres(prob, eps, seed):
     """The oracle's local_gmres with every operator application multiplied entry-wise by (1 + eps * u), u uniform in
-    [-1, 1]: the experiment behind LAMBDA_AMPLIFICATION."""
+    [-1, 1]: the experiment behind lambda_tolerance()."""
     rng = np.random.default_rng(seed)
     orig = mo.Problem.apply_S
 
@@ -134,3 +136,12 @@ def perturbed_gmres(prob, eps, seed):
     finally:
         mo.Problem.apply_S = orig
     return lam, its, res
+
+
+def lambda_tolerance(prob, lam_ref, eps=1e-11, factor=10.0, floor=1e-10):
+    """Relative l2 tolerance for a converged lambda of `prob` (bar sweep done): `factor` times what a relative
+    perturbation `eps` of every operator application does to the oracle's own lambda, never below `floor`.
+    Also returns the perturbed run's iteration count (it must not move)."""
+    lam, its, _ = perturbed_gmres(prob, eps, 12345)
+    spread = float(np.linalg.norm(lam - lam_ref) / np.linalg.norm(lam_ref))
+    return max(floor, factor * spread), spread, its

@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from helpers import LAMBDA_TOL_CONVERGED, ROOT, default_params, mo, pkg, rel_l2
+from helpers import ROOT, default_params, lambda_tolerance, mo, pkg, rel_l2
 
 pytestmark = pytest.mark.gpu
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "report_tables.json")))
@@ -51,17 +51,26 @@ def test_medium_nonmatching_grids_match_oracle(tmp_path):
     p = pkg().write_parameter_file(str(tmp_path / "parameter.txt"), mesh, mortar)
     reps, res, lam = pkg().host_run(p, verbose=0, write_output=0)
     prm = mo.parse_parameter_file(p)
-    o = mo.run(prm)[0]
+    prob = mo.Problem(prm, 4, mesh, mortar)
+    o = prob.run_cycle(0)
     r = reps[0]
     assert abs(r["gmres_iterations"] - o.gmres_iterations) <= 1
     assert r["r_norm"] == pytest.approx(o.r_norm, rel=1e-11)
-    # ~95 iterations: the residual history is reproducible; lambda to the measured amplification of operator
-    # round-off (helpers.LAMBDA_TOL_CONVERGED = 200 x 1e-10, tests/test_oracle_sensitivity.py)
-    n = min(len(res), len(o.residuals))
-    np.testing.assert_allclose(res[:n], o.residuals[:n], rtol=1e-5)
-    assert rel_l2(lam, o.lam) < LAMBDA_TOL_CONVERGED
+    # 95 iterations of classical Gram-Schmidt GMRES: on THIS problem a 1-ulp perturbation of the operator already
+    # moves the oracle's own lambda by 5e-9 and its late residual history by 0.3 % (tests/helpers.py), so: the early
+    # history to 1e-5, lambda to 10x what a 1e-11 operator perturbation does to the oracle (measured here), and --
+    # the well-conditioned statement -- the device's lambda solves the ORACLE's interface problem to the stop tolerance
+    np.testing.assert_allclose(res[:20], o.residuals[:20], rtol=1e-5)
+    tol_lam, spread, its_p = lambda_tolerance(prob, o.lam)
+    assert its_p == o.gmres_iterations
+    assert rel_l2(lam, o.lam) < tol_lam, (rel_l2(lam, o.lam), spread)
+    send = prob.flux_to_mortar({sd.r: sd.bar_trace for sd in prob.subs})
+    g = send + send[prob.partner]
+    true_res = np.linalg.norm(g - prob.apply_S(lam)) / np.linalg.norm(g)
+    true_res_oracle = np.linalg.norm(g - prob.apply_S(o.lam)) / np.linalg.norm(g)
+    assert true_res < 1.05 * true_res_oracle + 1e-9 and true_res < 3 * prm.tolerance
     for c in COLS:
-        assert r[c] == pytest.approx(o.errors[c], rel=1e-7 if r["gmres_iterations"] == o.gmres_iterations else 1e-5), c
+        assert r[c] == pytest.approx(o.errors[c], rel=1e-5), c
     assert r["factor_groups"] == 2
 
 
