@@ -85,7 +85,17 @@ const char *mmmfe_version(void);
  * "sweep_min_fill" (entries the shared-memory ring must hold), "sweep_evict_first" (L2 hint of the factor stream),
  * "sweep_compute_threads" (64, 128 or 256 compute threads per CTA), "sweep_ctas_per_sm" (resident CTAs per SM),
  * "sweep_groups" (independent compute groups per CTA), "sweep_autotune" (default 1: time one star sweep with the
- * persistent kernel and one with the per-level kernels at set-up and keep the faster).                         */
+ * persistent kernel and one with the per-level kernels at set-up, compare their traces (set-up fails above 1e-11) and
+ * keep the faster; the decision is summed over the ranks), "sweep_crosscheck" (with sweep_autotune = 0: still run and
+ * compare both once).
+ * Interface operator: "operator" 0 = nt star solves per subdomain in every GMRES iteration (the reference's loop,
+ * src/darcy_vtdd.cc:1316-1411), 1 = multiscale flux basis (the reference's dormant compute_multiscale_basis,
+ * src/darcy_vtdd.cc:959-1003): the response to every mortar basis function of the FIRST mortar time slab is computed
+ * once at set-up (multi-column multifrontal solves, fronts as FP64 DMMA GEMMs) and S q becomes one block
+ * lower-triangular Toeplitz product per subdomain -- the same operator to round-off; 2 (default) = 1 when the
+ * projector tables are slab structured and a factor group has at most "basis_auto_columns" (default 1024) basis
+ * columns, else 0.  "mortar_time_slabs" = time steps of the mortar mesh (mesh_pattern_mortar nt; required for 1/2),
+ * "basis_columns" = columns solved per pass (default 256).                                                       */
 int mmmfe_set_option(mmmfe_ctx *ctx, const char *key, double value);
 
 /* ---- multi-GPU: one process per GPU, subdomains sharded over ranks ------------------------------------------ */
@@ -211,7 +221,9 @@ int mmmfe_debug_sweep_trace(mmmfe_ctx *ctx, int32_t batch, int64_t cap, int64_t 
 /* Integer facts about the set-up context: "batches", "sweep_batches", "sweep_ctas", "sweep_smem_bytes",
  * "sweep_entries", "sweep_factor_bytes", "rt0_factors", "sweep_planned" (batches with a sweep plan, whether or
  * not the auto-tuner kept it), "tune_us_sweep" / "tune_us_levels" (microseconds of the timed star sweep of each
- * implementation); -1 for an unknown key.                                                                    */
+ * implementation), "tune_rel_diff_e18" (their relative l2 difference * 1e18), "basis_operator" (1: GMRES runs on the
+ * multiscale-basis operator), "basis_us", "basis_columns", "basis_mflop", "basis_passes", "basis_mw", "basis_values",
+ * "toeplitz_tiles", "toeplitz_mflop", "toeplitz_mbytes" (per operator application); -1 for an unknown key.        */
 int64_t mmmfe_stat(const mmmfe_ctx *ctx, const char *key);
 
 /* ---- diagnostics (host only, no device needed) ------------------------------------------------------------------- */
@@ -219,6 +231,10 @@ int64_t mmmfe_stat(const mmmfe_ctx *ctx, const char *key);
  * sizes = {n_nodes, idx_len, src_len, r_total, z_total, n_heights}.
  * node_table: n_nodes x 8 int32 = {s, b, child0, child1, height, nsplit, ldr, parent};
  * offsets:    n_nodes x 4 int64 = {idx_off, src_off, r_off, z_off}.                                            */
+/* The multiscale-basis operator of a local subdomain's factor group: info = {mortar time slabs m_t, rows = columns
+ * P_tot, leading dimension ldt, slots, slot of side 0..3 (-1: none), first row/column of side 0..3 (-1)}; t_out (may be
+ * NULL) receives T[d][row][ldt], d = 0..m_t-1: signed mortar response on `row` d slabs after the basis function `col`. */
+int mmmfe_debug_get_basis(mmmfe_ctx *ctx, int32_t local_index, int64_t info[12], double *t_out, int64_t capacity);
 /* Copies the stored factor (R blocks, layout given by the nd-tree offsets/ldr) of a local subdomain's group. */
 int mmmfe_debug_get_factor(mmmfe_ctx *ctx, int32_t local_index, double *r_out, int64_t capacity);
 int mmmfe_nd_tree_sizes(int32_t nx, int32_t ny, int32_t leaf_cells, int64_t sizes[6]);

@@ -86,6 +86,7 @@ def load_engine():
         "mmmfe_solve_saddle": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p, c_f64p]),
         "mmmfe_profile_step": (ctypes.c_int, [vp, c_f64p, c_f64p, c_i64p]),
         "mmmfe_debug_get_factor": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p, ctypes.c_int64]),
+        "mmmfe_debug_get_basis": (ctypes.c_int, [vp, ctypes.c_int32, c_i64p, c_f64p, ctypes.c_int64]),
         "mmmfe_profile_sweeps": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p, c_f64p, c_i32p, c_i32p]),
         "mmmfe_stat": (ctypes.c_int64, [vp, ctypes.c_char_p]),
         "mmmfe_profile_sweep_cycles": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p]),
@@ -309,6 +310,16 @@ class Engine:
         out = np.empty(r_total)
         self._check(self.lib.mmmfe_debug_get_factor(self.h, li, _ptr(out, c_f64p), r_total))
         return out
+
+    def get_basis(self, li):
+        """Multiscale-basis operator of the factor group of local subdomain li: (info dict, T[m_t][P_tot][P_tot])."""
+        info = np.zeros(12, dtype=np.int64)
+        self._check(self.lib.mmmfe_debug_get_basis(self.h, li, _ptr(info, c_i64p), None, 0))
+        m_t, p_tot, ldt = int(info[0]), int(info[1]), int(info[2])
+        t = np.empty(m_t * p_tot * ldt)
+        self._check(self.lib.mmmfe_debug_get_basis(self.h, li, _ptr(info, c_i64p), _ptr(t, c_f64p), t.size))
+        meta = dict(m_t=m_t, P_tot=p_tot, slot_of_side=[int(v) for v in info[4:8]], base_of_side=[int(v) for v in info[8:12]])
+        return meta, t.reshape(m_t, p_tot, ldt)[:, :, :p_tot].copy()
 
     def solve_saddle(self, li, rhs):
         rhs = _f64(rhs)

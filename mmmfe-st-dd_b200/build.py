@@ -37,8 +37,8 @@ def _run(cmd):
 
 
 def build_engine(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("kernels.cu", "sweep.cu", "engine.cu", "nd_tree.cpp", "sweep_plan.cpp", "exchange_plan.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("kernels.cuh", "nd_tree.h", "sweep.cuh", "sweep_plan.h", "exchange_plan.h", "common.h")] + \
+    srcs = [os.path.join(CSRC, f) for f in ("kernels.cu", "wide.cu", "sweep.cu", "engine.cu", "nd_tree.cpp", "sweep_plan.cpp", "exchange_plan.cpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("kernels.cuh", "wide.cuh", "dev_common.cuh", "nd_tree.h", "sweep.cuh", "sweep_plan.h", "exchange_plan.h", "common.h")] + \
         [os.path.join(ROOT, "include", "mmmfe_b200.h")]
     if not force and not _newer(LIB_ENGINE, deps):
         return LIB_ENGINE

@@ -22,6 +22,7 @@
 #include "nd_tree.h"
 #include "sweep.cuh"
 #include "sweep_plan.h"
+#include "wide.cuh"
 
 #ifdef MMMFE_WITH_NCCL
 #include <dlfcn.h>
@@ -91,6 +92,14 @@ struct Sub {
   bool has_bar_data = false;
 };
 
+// ---- multiscale flux basis of one factor group (src/darcy_vtdd.cc:959-1003, inc/darcy_vtdd.h:124, 264) ---------------
+// "slot" = one of the sides that is an interface on at least one member of the group.  Rows and columns of the operator
+// share one numbering: (slot, a) -> base[slot] + a, a = mortar dof within ONE time slab of that side.
+// T[d][row][col], d = delay in mortar time slabs: response on row's side, d slabs later, to the basis function col.
+struct Basis {
+  int32_t m_t = 0, lvl_per_slab = 0, nt = 0;
+  int32_t n_slots = 0, slot_of_side[4] = {-1, -1, -1, -1}, side_of_slot[4] = {0, 0, 0, 0};
+
 // ---- one factor: nested-dissection tree + block-inverse fronts on the device -------------------------------------
 struct LevelWork {  // one height level of the top of the tree
   DevBuf<WorkItem> fwd, bwd;
@@ -133,6 +142,16 @@ struct Factor {
   DevBuf<int32_t> sweep_index, p_of_cell, inst_ij;
   DevBuf<uint16_t> tmpl16;
   DevBuf<int64_t> tmpl_off;
+  std::unique_ptr<Basis> basis;  // multiscale flux basis of this factor group (time-Toeplitz operator)
+};
+
+  int32_t P[4] = {0, 0, 0, 0}, n_side[4] = {0, 0, 0, 0}, base[4] = {0, 0, 0, 0}, tr_base[4] = {0, 0, 0, 0};
+  int32_t rep[4] = {-1, -1, -1, -1};  // local subdomain whose tables represent the slot
+  int32_t P_tot = 0, n_tr = 0, MW = 0, n_pass = 0, MC = 8;
+  int64_t ldt = 0;
+  DevBuf<double> T;
+  double seconds = 0.0, flops = 0.0, bytes = 0.0;
+  long long graph_kernels = 0;
 };
 
 // ---- one batch: up to 4 subdomains solved as simultaneous right-hand sides of one factor ---------------------------
@@ -226,6 +245,17 @@ struct mmmfe_ctx {
   double factor_seconds = 0.0;
   long long launch_base = 0;
   int *abort_flag = nullptr;  // device memory: raised by the sweep kernel's watchdog
+  // interface operator: 0 = star sweeps every iteration (the reference's algorithm), 1 = multiscale flux basis /
+  // time-Toeplitz operator precomputed at set-up, 2 = basis when the structure allows it and it has at most
+  // basis_auto_columns columns per factor group, sweeps otherwise
+  int operator_mode = 2, mortar_slabs = 0, basis_cols_max = 256, basis_auto_columns = 1024;
+  bool use_basis = false;
+  std::string basis_note;  // why the basis operator is not in use
+  DevBuf<ToepProb> toep_probs;
+  DevBuf<ToepTile> toep_tiles;
+  int32_t n_toep_tiles = 0;
+  double basis_seconds = 0.0, basis_flops = 0.0, basis_bytes = 0.0, toep_flops = 0.0, toep_bytes = 0.0;
+  int64_t basis_columns = 0;
   // temporaries of the factorisation
   DevBuf<GemmProb> d_gemm;
   DevBuf<int32_t> d_tiles;
@@ -871,8 +901,9 @@ static void run_star_sweeps(mmmfe_ctx *c, SweepMode mode) {
 }
 
 // send = s * f2c(trace); exchange with the neighbours; out = sign * (send + recv)
-static void exchange_and_combine(mmmfe_ctx *c, double sign, double *out) {
-  launch_spmv(c->n_iface, c->f2c_all.rp.p, c->f2c_all.col.p, c->f2c_all.val.p, c->trace.p, c->send.p, c->stream);
+static void exchange_and_combine(mmmfe_ctx *c, double sign, double *out, bool send_ready = false) {
+  if (!send_ready)
+    launch_spmv(c->n_iface, c->f2c_all.rp.p, c->f2c_all.col.p, c->f2c_all.val.p, c->trace.p, c->send.p, c->stream);
 #ifdef MMMFE_WITH_NCCL
   if (!c->peers.empty()) {
     launch_gather(int64_t(c->send_index.n), c->send.p, c->send_index.p, c->send_buf.p, c->stream);
@@ -889,6 +920,11 @@ static void exchange_and_combine(mmmfe_ctx *c, double sign, double *out) {
 
 // Ap = S q for q resident in d_q (src/darcy_vtdd.cc:1316-1411)
 static void apply_operator(mmmfe_ctx *c, const double *d_q, double *d_ap) {
+  if (c->use_basis) {  // send = (signed f2c . star sweeps . c2f) q as one block-Toeplitz product per subdomain
+    launch_toeplitz_apply(c->toep_probs.p, c->toep_tiles.p, c->n_toep_tiles, d_q, c->send.p, c->stream);
+    exchange_and_combine(c, -1.0, d_ap, true);
+    return;
+  }
   launch_spmv(c->n_fine, c->c2f_all.rp.p, c->c2f_all.col.p, c->c2f_all.val.p, d_q, c->lam_bar.p, c->stream);
   run_star_sweeps(c, SWEEP_STAR);
   exchange_and_combine(c, -1.0, d_ap);
@@ -903,6 +939,343 @@ static void allreduce_sum(mmmfe_ctx *c, double *d, size_t n) {
 #else
   (void)c; (void)d; (void)n;
 #endif
+}
+
+
+// =================================================================================================================
+// multiscale flux basis / time-Toeplitz interface operator
+// =================================================================================================================
+// The tables of one interface side are slab-structured when (i) the mortar dofs are ordered slab-major (P per slab),
+// (ii) c2f and f2c couple a mortar slab only with the lvl_per_slab fine levels it covers and (iii) every slab's block
+// equals the first slab's (translation invariance in time).  project_mortar builds exactly such tables whenever the
+// mortar time mesh divides the subdomain's (inc/utilities.h:471-505; front-end: projector_tables).
+static bool slab_structured(const HostCsr &c2f, const HostCsr &f2c, int64_t ns, int64_t nt, int64_t m_t, int64_t P,
+                            std::string &why) {
+  const int64_t r = nt / m_t;
+  auto close = [](double a, double b) { return std::fabs(a - b) <= 1e-12 * std::max(std::fabs(a), std::fabs(b)); };
+  for (int64_t lvl = 0; lvl < nt; ++lvl) {
+    const int64_t J = lvl / r;
+    for (int64_t i = 0; i < ns; ++i) {
+      const int64_t row = lvl * ns + i, row0 = (lvl - J * r) * ns + i;
+      if (c2f.rp[row + 1] - c2f.rp[row] != c2f.rp[row0 + 1] - c2f.rp[row0]) { why = "c2f rows differ between time slabs"; return false; }
+      for (int64_t e = c2f.rp[row], e0 = c2f.rp[row0]; e < c2f.rp[row + 1]; ++e, ++e0) {
+        if (c2f.col[e] < J * P || c2f.col[e] >= (J + 1) * P) { why = "c2f couples a fine level with another mortar time slab"; return false; }
+        if (c2f.col[e] - J * P != c2f.col[e0] || !close(c2f.val[e], c2f.val[e0])) { why = "c2f is not translation invariant in time"; return false; }
+      }
+    }
+  }
+  for (int64_t J = 0; J < m_t; ++J)
+    for (int64_t a = 0; a < P; ++a) {
+      const int64_t row = J * P + a;
+      if (f2c.rp[row + 1] - f2c.rp[row] != f2c.rp[a + 1] - f2c.rp[a]) { why = "f2c rows differ between time slabs"; return false; }
+      for (int64_t e = f2c.rp[row], e0 = f2c.rp[a]; e < f2c.rp[row + 1]; ++e, ++e0) {
+        const int64_t lvl = f2c.col[e] / ns;
+        if (lvl < J * r || lvl >= (J + 1) * r) { why = "f2c couples a mortar time slab with fine levels outside it"; return false; }
+        if (f2c.col[e] - J * r * ns != f2c.col[e0] || !close(f2c.val[e], f2c.val[e0])) { why = "f2c is not translation invariant in time"; return false; }
+      }
+    }
+  return true;
+}
+
+static bool same_csr(const HostCsr &a, const HostCsr &b) {
+  return a.n_rows == b.n_rows && a.n_cols == b.n_cols && a.rp == b.rp && a.col == b.col && a.val == b.val;
+}
+
+// Slots, sizes and eligibility of the basis of one factor group; no device work.
+static std::unique_ptr<Basis> plan_basis(mmmfe_ctx *c, const std::vector<int32_t> &members, std::string &why) {
+  auto B = std::make_unique<Basis>();
+  const int m_t = c->mortar_slabs;
+  if (m_t < 1) { why = "option mortar_time_slabs is not set"; return nullptr; }
+  const Sub &first = *c->subs[members[0]];
+  if (first.nt % m_t != 0) { why = "the mortar time mesh does not divide the subdomain's time steps"; return nullptr; }
+  B->m_t = m_t; B->nt = first.nt; B->lvl_per_slab = first.nt / m_t;
+  for (int32_t li : members) {
+    const Sub &sd = *c->subs[li];
+    for (int sd_side = 0; sd_side < 4; ++sd_side) {
+      if (sd.neighbor[sd_side] < 0) continue;
+      if (sd.mortar_len[sd_side] % m_t != 0) { why = "mortar_len is not a multiple of the number of mortar time slabs"; return nullptr; }
+      int &slot = B->slot_of_side[sd_side];
+      if (slot < 0) {
+        slot = B->n_slots++;
+        B->side_of_slot[slot] = sd_side;
+        B->P[slot] = sd.mortar_len[sd_side] / m_t;
+        B->n_side[slot] = sd.n_side[sd_side];
+        B->rep[slot] = li;
+        if (!slab_structured(sd.c2f[sd_side], sd.f2c[sd_side], sd.n_side[sd_side], sd.nt, m_t, B->P[slot], why)) return nullptr;
+      } else {
+        const Sub &rp = *c->subs[B->rep[slot]];
+        if (!same_csr(rp.c2f[sd_side], sd.c2f[sd_side]) || !same_csr(rp.f2c[sd_side], sd.f2c[sd_side]) ||
+            rp.side_dofs[sd_side] != sd.side_dofs[sd_side]) {
+          why = "subdomains that share a factor have different projector tables on the same side";
+          return nullptr;
+        }
+      }
+    }
+  }
+  if (B->n_slots == 0) { why = "no interface side"; return nullptr; }
+  for (int k = 0; k < B->n_slots; ++k) {
+    B->base[k] = B->P_tot; B->P_tot += B->P[k];
+    B->tr_base[k] = B->n_tr; B->n_tr += B->n_side[k];
+  }
+  B->ldt = (int64_t(B->P_tot) + 7) & ~int64_t(7);
+  return B;
+}
+
+// Solves for the responses of all first-slab basis functions of the group (MW columns per pass, every time step one
+// replay of a static CUDA graph: rhs, multi-column multifrontal solve with the fronts as DMMA GEMMs, pressure update,
+// traces) and projects the traces to the mortar space: T[d][row][col].
+static void compute_basis(mmmfe_ctx *c, Factor &F, Basis &B) {
+  const auto t_begin = std::chrono::steady_clock::now();
+  cudaStream_t st = c->stream;
+  const NdTree &tr = F.tree;
+  const int nt = B.nt, r = B.lvl_per_slab;
+  // ---- columns per pass: as many as asked for, fewer when the work vectors would not fit ----
+  size_t free_b = 0, total_b = 0;
+  CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+  const double t_bytes = 8.0 * B.m_t * double(B.P_tot) * double(B.ldt);
+  const double per_col = 8.0 * (double(F.nf) + double(tr.z_total) + double(F.np) + double(nt) * B.n_tr);
+  int cap = std::max(8, c->basis_cols_max & ~7);
+  while (cap > 8 && per_col * cap > 0.6 * (double(free_b) - t_bytes)) cap -= 8;
+  if (per_col * cap + t_bytes > 0.9 * double(free_b)) fail(MMMFE_E_CUDA, "not enough device memory for the multiscale basis (%.1f GB needed)", (per_col * cap + t_bytes) / 1e9);
+  B.n_pass = (B.P_tot + cap - 1) / cap;
+  B.MW = (((B.P_tot + B.n_pass - 1) / B.n_pass) + 7) & ~7;
+  const int MW = B.MW;
+  // ---- subtree kernels: 8 columns per chunk when the vectors fit beside the factor blob, else 4 ----
+  const size_t smem_limit = subtree_smem_limit();
+  wide_set_smem_limit(smem_limit);
+  size_t smem_f = 0, smem_b = 0;
+  for (int MC : {8, 4}) {
+    smem_f = smem_b = 0;
+    for (const auto &T : tr.templates) {
+      smem_f = std::max(smem_f, 16 + 8 * (size_t(T.rf_size) + (size_t(T.zl_size) + size_t(T.n_int)) * MC));
+      smem_b = std::max(smem_b, 16 + 8 * (size_t(T.rb_size) + size_t(2 * T.n_int + T.n_rootb) * MC));
+    }
+    B.MC = MC;
+    if (smem_f <= smem_limit && smem_b <= smem_limit) break;
+  }
+  if (smem_f > smem_limit || smem_b > smem_limit) fail(MMMFE_E_UNSUPPORTED, "subtree factor blobs do not fit the multi-column kernels");
+  // ---- host tables ----
+  // interface data of the first slab: x[dof][column] += -sign * c2f(level, i; a), CSR by (pass, level)
+  std::vector<int64_t> add_rp(size_t(B.n_pass) * (r + 1) + 1, 0);
+  std::vector<int32_t> add_row, add_col;
+  std::vector<double> add_val;
+  int64_t add_max = 0;
+  for (int pass = 0; pass < B.n_pass; ++pass) {
+    for (int lvl = 0; lvl < r; ++lvl) {
+      add_rp[size_t(pass) * (r + 1) + lvl] = int64_t(add_row.size());
+      for (int k = 0; k < B.n_slots; ++k) {
+        const int side = B.side_of_slot[k];
+        const Sub &sd = *c->subs[B.rep[k]];
+        const HostCsr &t = sd.c2f[side];
+        const int64_t ns = B.n_side[k];
+        for (int64_t i = 0; i < ns; ++i) {
+          const int64_t row = int64_t(lvl) * ns + i;
+          for (int64_t e = t.rp[row]; e < t.rp[row + 1]; ++e) {
+            const int col = B.base[k] + t.col[e];  // first slab: t.col[e] < P (slab_structured)
+            if (col / MW != pass) continue;
+            add_row.push_back(sd.side_dofs[side][size_t(i)]);
+            add_col.push_back(col % MW);
+            add_val.push_back(-kNormalSign[side] * t.val[e]);  // rhs_i = -s * lam_bar, src/darcy_vtdd.cc:840-844
+          }
+        }
+      }
+      add_max = std::max(add_max, int64_t(add_row.size()) - add_rp[size_t(pass) * (r + 1) + lvl]);
+    }
+    add_rp[size_t(pass) * (r + 1) + r] = int64_t(add_row.size());
+  }
+  std::vector<int32_t> tr_dof(size_t(B.n_tr));
+  std::vector<int64_t> f_rp(1, 0), f_col, f_trow;
+  std::vector<double> f_val;
+  for (int k = 0; k < B.n_slots; ++k) {
+    const int side = B.side_of_slot[k];
+    const Sub &sd = *c->subs[B.rep[k]];
+    for (int i = 0; i < B.n_side[k]; ++i) tr_dof[size_t(B.tr_base[k] + i)] = sd.side_dofs[side][size_t(i)];
+    const HostCsr &t = sd.f2c[side];
+    const int64_t ns = B.n_side[k];
+    for (int64_t m = 0; m < t.n_rows; ++m) {
+      for (int64_t e = t.rp[m]; e < t.rp[m + 1]; ++e) {
+        const int64_t lvl = t.col[e] / ns, i = t.col[e] % ns;
+        f_col.push_back(lvl * B.n_tr + B.tr_base[k] + i);
+        f_val.push_back(kNormalSign[side] * t.val[e]);
+      }
+      f_rp.push_back(int64_t(f_col.size()));
+      f_trow.push_back((m / B.P[k]) * B.P_tot + B.base[k] + m % B.P[k]);
+    }
+  }
+  // per tree level: gather rows and GEMM problems
+  struct Lvl {
+    DevBuf<WideRow> fwd_rows, bwd_rows;
+    DevBuf<GemmProb> fwd_probs, bwd_probs;
+    DevBuf<int32_t> fwd_tiles, bwd_tiles;
+    int32_t n_fwd = 0, n_bwd = 0, t_fwd = 0, t_bwd = 0;
+  };
+  DevBuf<double> x, z, ptil, trace;
+  DevBuf<int32_t> state;
+  x.alloc(size_t(F.nf) * MW); z.alloc(size_t(tr.z_total) * MW + 8); ptil.alloc(size_t(F.np) * MW);
+  trace.alloc(size_t(nt) * B.n_tr * MW);
+  state.alloc(2);
+  z.zero(st);
+  B.T.alloc(size_t(B.m_t) * B.P_tot * B.ldt);
+  B.T.zero(st);
+  std::vector<std::unique_ptr<Lvl>> lvls;
+  const int tiles_n = (MW + 63) / 64;
+  for (const auto &level : tr.top_by_height) {
+    if (level.empty()) continue;
+    auto L = std::make_unique<Lvl>();
+    std::vector<WideRow> fr, br;
+    std::vector<GemmProb> fp, bp;
+    std::vector<int32_t> ft(1, 0), bt(1, 0);
+    for (int32_t id : level) {
+      const NdNode &n = tr.nodes[id];
+      const int32_t f = n.s + n.b;
+      for (int32_t p = 0; p < f; ++p) fr.push_back({id, p});
+      for (int32_t q = 0; q < n.b; ++q) br.push_back({id, q});
+      double *zs = z.p + n.z_off * MW;
+      if (n.b > 0) {  // contributions += (-G) v_s:  C(q, j) += sum_i rf[i][q] v[i][j]
+        fp.push_back({F.R.p + n.rf_off, zs, zs + int64_t(n.s) * MW, n.b, MW, n.s, MW, 1, n.ldf, MW, 1, 1.0, 1.0, nullptr});
+        ft.push_back(ft.back() + ((n.b + 63) / 64) * tiles_n);
+      }
+      // x_s = [F11^-1 | -G^T] [z_s ; x_b], written straight to the rows of x (row map = the front's dof indices)
+      bp.push_back({F.R.p + n.rb_off, zs, x.p, n.s, MW, f, MW, n.ldr, 1, MW, 1, 1.0, 0.0, F.idx_user.p + n.idx_off});
+      bt.push_back(bt.back() + ((n.s + 63) / 64) * tiles_n);
+    }
+    L->n_fwd = int32_t(fp.size()); L->n_bwd = int32_t(bp.size());
+    L->t_fwd = ft.back(); L->t_bwd = bt.back();
+    L->fwd_rows.upload(fr); L->bwd_rows.upload(br);
+    L->fwd_probs.upload(fp); L->bwd_probs.upload(bp);
+    L->fwd_tiles.upload(ft); L->bwd_tiles.upload(bt);
+    lvls.push_back(std::move(L));
+  }
+  DevBuf<int64_t> d_add_rp, d_frp, d_fcol, d_ftrow;
+  DevBuf<int32_t> d_add_row, d_add_col, d_tr_dof;
+  DevBuf<double> d_add_val, d_fval;
+  add_row.push_back(0); add_col.push_back(0); add_val.push_back(0.0);
+  d_add_rp.upload(add_rp); d_add_row.upload(add_row); d_add_col.upload(add_col); d_add_val.upload(add_val);
+  d_tr_dof.upload(tr_dof);
+  d_frp.upload(f_rp); d_fcol.upload(f_col); d_ftrow.upload(f_trow); d_fval.upload(f_val);
+
+  const WideStep ws{MW, F.nf, F.np, F.kup.rp.p, F.kup.col.p, F.kup.val.p, F.kpu.rp.p, F.kpu.col.p, F.kpu.val.p,
+                    F.minv.p, x.p, ptil.p, state.p};
+  const SolveArgs sa{F.fronts.p, F.R.p, F.idx_user.p, F.src.p, z.p, x.p};
+  const SubtreeArgs sub = subtree_args(F, x.p, z.p);
+  auto enqueue_step = [&]() {
+    launch_wide_rhs(ws, st);
+    launch_wide_add(ws, d_add_rp.p, d_add_row.p, d_add_col.p, d_add_val.p, r, add_max, st);
+    launch_wide_subtree_forward(B.MC, MW, sub, F.n_inst, smem_f, st);
+    for (auto &L : lvls) {
+      launch_wide_fwd_gather(sa, MW, L->fwd_rows.p, int64_t(L->fwd_rows.n), st);
+      launch_grouped_gemm(L->fwd_probs.p, L->fwd_tiles.p, L->n_fwd, L->t_fwd, st);
+    }
+    for (auto it = lvls.rbegin(); it != lvls.rend(); ++it) {
+      launch_wide_bwd_gather(sa, MW, (*it)->bwd_rows.p, int64_t((*it)->bwd_rows.n), st);
+      launch_grouped_gemm((*it)->bwd_probs.p, (*it)->bwd_tiles.p, (*it)->n_bwd, (*it)->t_bwd, st);
+    }
+    launch_wide_subtree_backward(B.MC, MW, sub, F.n_inst, smem_b, st);
+    launch_wide_update(ws, d_tr_dof.p, B.n_tr, trace.p, st);
+    launch_wide_next_level(state.p, st);
+  };
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  cudaGraph_t g = nullptr;
+  cudaGraphExec_t ge = nullptr;
+  if (c->use_graphs) {
+    const long long before = launch_counter();
+    CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    enqueue_step();
+    CUDA_CHECK(cudaStreamEndCapture(st, &g));
+    B.graph_kernels = launch_counter() - before;
+    launch_counter_add(-B.graph_kernels);
+    CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
+    CUDA_CHECK(cudaGraphDestroy(g));
+  }
+  for (int pass = 0; pass < B.n_pass; ++pass) {
+    const int32_t init[2] = {0, pass};
+    CUDA_CHECK(cudaMemcpyAsync(state.p, init, sizeof init, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));  // `init` is a stack variable
+    ptil.zero(st);
+    for (int lvl = 0; lvl < nt; ++lvl) {
+      if (ge) { CUDA_CHECK(cudaGraphLaunch(ge, st)); launch_counter_add(B.graph_kernels); }
+      else enqueue_step();
+    }
+    const int n_cols = std::min(MW, B.P_tot - pass * MW);
+    launch_wide_f2c(int64_t(f_trow.size()), d_frp.p, d_fcol.p, d_fval.p, trace.p, MW, n_cols, B.T.p, B.ldt, d_ftrow.p,
+                    int64_t(pass) * MW, st);
+  }
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  CUDA_CHECK(cudaGetLastError());
+  if (ge) cudaGraphExecDestroy(ge);
+  double vals = 0;
+  for (const NdNode &n : tr.nodes) vals += double(n.s) * (double(n.s) + 2.0 * n.b);
+  B.flops = 2.0 * vals * nt * double(B.n_pass) * MW;
+  B.bytes = double(B.n_pass) * nt * (8.0 * vals + 8.0 * MW * (4.0 * F.nf + 3.0 * F.np));
+  B.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+}
+
+// Decides whether the interface operator runs on the multiscale basis, computes the bases and the tile list of the
+// block-Toeplitz kernel.  Collective in the sense that every rank decides from its own subdomains; ranks may differ
+// (the operator is the same operator either way, to round-off).
+static void setup_basis_operator(mmmfe_ctx *c, const std::vector<int> &group_of) {
+  c->use_basis = false;
+  c->basis_note.clear();
+  if (c->operator_mode == 0) { c->basis_note = "operator = 0"; return; }
+  const int ns = int(c->subs.size());
+  std::vector<std::unique_ptr<Basis>> plans(c->factors.size());
+  for (size_t g = 0; g < c->factors.size(); ++g) {
+    std::vector<int32_t> members;
+    for (int i = 0; i < ns; ++i) if (group_of[i] == int(g)) members.push_back(i);
+    std::string why;
+    plans[g] = plan_basis(c, members, why);
+    if (!plans[g]) {
+      c->basis_note = why;
+      if (c->operator_mode == 1) fail(MMMFE_E_UNSUPPORTED, "operator = 1 (multiscale basis) is not possible here: %s", why.c_str());
+      return;
+    }
+    if (c->operator_mode == 2 && plans[g]->P_tot > c->basis_auto_columns) {
+      c->basis_note = "more basis columns per factor group than basis_auto_columns";
+      return;
+    }
+  }
+  for (size_t g = 0; g < c->factors.size(); ++g) {
+    Factor &F = *c->factors[g];
+    F.basis = std::move(plans[g]);
+    compute_basis(c, F, *F.basis);
+    c->basis_seconds += F.basis->seconds;
+    c->basis_flops += F.basis->flops;
+    c->basis_bytes += F.basis->bytes;
+    c->basis_columns += F.basis->P_tot;
+  }
+  std::vector<ToepProb> probs;
+  std::vector<ToepTile> tiles;
+  c->toep_flops = c->toep_bytes = 0;
+  for (int i = 0; i < ns; ++i) {
+    const Sub &sd = *c->subs[i];
+    const Basis &B = *c->factors[group_of[i]]->basis;
+    for (int so = 0; so < 4; ++so) {
+      if (sd.neighbor[so] < 0) continue;
+      ToepProb pr{};
+      const int ko = B.slot_of_side[so];
+      pr.T = B.T.p; pr.ldt = B.ldt; pr.d_stride = int64_t(B.P_tot) * B.ldt; pr.m_t = B.m_t;
+      pr.P_out = B.P[ko]; pr.row_base = B.base[ko]; pr.out_off = sd.iface_off[so];
+      double k_len = 0;
+      for (int si = 0; si < 4; ++si) {
+        if (sd.neighbor[si] < 0) continue;
+        const int ki = B.slot_of_side[si];
+        pr.P_in[pr.n_in] = B.P[ki]; pr.col_base[pr.n_in] = B.base[ki]; pr.in_off[pr.n_in] = sd.iface_off[si];
+        ++pr.n_in;
+        k_len += B.P[ki];
+      }
+      c->toep_flops += 2.0 * pr.P_out * k_len * 0.5 * B.m_t * (B.m_t + 1.0);
+      c->toep_bytes += 8.0 * pr.P_out * k_len * B.m_t;
+      for (int row0 = 0; row0 < pr.P_out; row0 += TOEP_BM)
+        for (int slab0 = 0; slab0 < B.m_t; slab0 += TOEP_BN) tiles.push_back({int32_t(probs.size()), row0, slab0});
+      probs.push_back(pr);
+    }
+  }
+  // heavy tiles (late slabs: long delay sums) first
+  std::stable_sort(tiles.begin(), tiles.end(), [](const ToepTile &a, const ToepTile &b) { return a.slab0 > b.slab0; });
+  c->toep_probs.upload(probs);
+  c->toep_tiles.upload(tiles);
+  c->n_toep_tiles = int32_t(tiles.size());
+  c->use_basis = true;
 }
 
 // =================================================================================================================
@@ -1117,6 +1490,7 @@ static void setup(mmmfe_ctx *c) {
     c->lam_bar.zero(c->stream); c->trace.zero(c->stream);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   }
+  setup_basis_operator(c, group_of);
 }
 
 // Entry lists, ring schedule and boundary-entry tables of one batch for the persistent sweep kernel.
@@ -1410,6 +1784,13 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   else if (k == "sweep_spin_ns") c->sweep_spin_ns = std::max(0, int(value));
   else if (k == "sweep_autotune") c->sweep_autotune = value != 0;
   else if (k == "sweep_crosscheck") c->sweep_crosscheck = value != 0;
+  else if (k == "operator") {
+    if (value != 0 && value != 1 && value != 2) { c->err = "operator must be 0 (sweeps), 1 (multiscale basis) or 2 (auto)"; return MMMFE_E_INVALID; }
+    c->operator_mode = int(value);
+  }
+  else if (k == "mortar_time_slabs") c->mortar_slabs = std::max(0, int(value));
+  else if (k == "basis_columns") c->basis_cols_max = std::max(8, int(value));
+  else if (k == "basis_auto_columns") c->basis_auto_columns = std::max(0, int(value));
   else if (k == "sweep_groups") {
     if (value != 1 && value != 2 && value != 4 && value != 8) { c->err = "sweep_groups must be 1, 2, 4 or 8"; return MMMFE_E_INVALID; }
     c->sweep_groups = int(value);
@@ -1765,6 +2146,17 @@ int64_t mmmfe_stat(const mmmfe_ctx *c, const char *key) {
   if (k == "sweep_ring_doubles") { for (auto &b : c->batches) if (b->sweep) v = std::max<int64_t>(v, b->sargs.ring_dbl); return v; }
   if (k == "rt0_factors") { for (auto &f : c->factors) v += f->rt0; return v; }
   if (k == "sweep_planned") { for (auto &b : c->batches) v += b->s_entries.n > 0; return v; }
+  if (k == "basis_operator") return c->use_basis ? 1 : 0;
+  if (k == "basis_us") return int64_t(c->basis_seconds * 1e6);
+  if (k == "basis_columns") return c->basis_columns;
+  if (k == "basis_mflop") return int64_t(c->basis_flops / 1e6);
+  if (k == "basis_mbytes") return int64_t(c->basis_bytes / 1e6);
+  if (k == "basis_passes") { for (auto &f : c->factors) if (f->basis) v += f->basis->n_pass; return v; }
+  if (k == "basis_mw") { for (auto &f : c->factors) if (f->basis) v = std::max<int64_t>(v, f->basis->MW); return v; }
+  if (k == "basis_values") { for (auto &f : c->factors) if (f->basis) v += int64_t(f->basis->T.n); return v; }
+  if (k == "toeplitz_tiles") return c->n_toep_tiles;
+  if (k == "toeplitz_mflop") return int64_t(c->toep_flops / 1e6);
+  if (k == "toeplitz_mbytes") return int64_t(c->toep_bytes / 1e6);
   if (k == "tune_us_sweep") return int64_t(c->tune_ms_sweep * 1e3);
   if (k == "tune_us_levels") return int64_t(c->tune_ms_levels * 1e3);
   // relative l2 difference of the two star-sweep implementations at set-up, in units of 1e-18 (-1: not run)
@@ -1882,6 +2274,25 @@ int mmmfe_profile_sweeps(mmmfe_ctx *c, int32_t cap, double *ms, double *bytes_pe
       ++k;
     }
     *n_out = k;
+  });
+}
+
+int mmmfe_debug_get_basis(mmmfe_ctx *c, int32_t li, int64_t info[12], double *t_out, int64_t capacity) {
+  if (!c || li < 0 || li >= int32_t(c->subs.size()) || !info) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, {
+    if (!c->is_setup) fail(MMMFE_E_INVALID, "mmmfe_setup first");
+    const Factor &F = *c->batches[c->subs[li]->batch]->factor;
+    if (!c->use_basis || !F.basis) fail(MMMFE_E_INVALID, "the multiscale-basis operator is not in use (%s)", c->basis_note.c_str());
+    const Basis &B = *F.basis;
+    info[0] = B.m_t; info[1] = B.P_tot; info[2] = B.ldt; info[3] = B.n_slots;
+    for (int sd = 0; sd < 4; ++sd) {
+      info[4 + sd] = B.slot_of_side[sd];
+      info[8 + sd] = B.slot_of_side[sd] >= 0 ? B.base[B.slot_of_side[sd]] : -1;
+    }
+    if (t_out) {
+      if (capacity < int64_t(B.T.n)) fail(MMMFE_E_INVALID, "buffer too small (%lld needed)", (long long)B.T.n);
+      CUDA_CHECK(cudaMemcpy(t_out, B.T.p, B.T.n * sizeof(double), cudaMemcpyDeviceToHost));
+    }
   });
 }
 

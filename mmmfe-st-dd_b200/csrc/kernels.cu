@@ -6,6 +6,7 @@
 //    solves), batched over the M subdomains that share a factor; HBM-bound, coalesced row streaming;
 //  * time stepping, projector SpMV, exchange/combine and the classical Gram-Schmidt kernels.
 #include "kernels.cuh"
+#include "dev_common.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -19,19 +20,19 @@ void launch_counter_add(long long n) { g_launches.fetch_add(n); }
 // =================================================================================================================
 // grouped GEMM  C = alpha * A * B + beta * C   (FP64, DMMA)
 // =================================================================================================================
-__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(d0), "+d"(d1)
-               : "d"(a), "d"(b));
-}
+constexpr int GT = 64;         // C tile
+constexpr int GK = 16;         // k step
+constexpr int AS_LD = GK + 4;  // row strides of the staged tiles: fragment loads of a half-warp hit 16 distinct banks
+constexpr int BS_LD = GT + 4;
 
-constexpr int GT = 64;  // C tile
-constexpr int GK = 16;  // k step
-
+// One 64 x 64 tile of one problem per CTA, 8 warps (4 x 2, 16 x 32 each).  The next k-slab of A and B is fetched into
+// registers while the current one is multiplied from shared memory (two staging buffers, one barrier per k step);
+// the global-load mapping follows the unit stride of each operand so that every layout the factorisation, the
+// multi-column solve and the operator application use is read in full 128-byte lines.
 __global__ void __launch_bounds__(256) k_grouped_gemm(const GemmProb *__restrict__ probs,
                                                       const int32_t *__restrict__ tile_start, int32_t n_probs) {
-  __shared__ double As[GT][GK + 1];
-  __shared__ double Bs[GK][GT + 1];
+  __shared__ double As[2][GT * AS_LD];
+  __shared__ double Bs[2][GK * BS_LD];
   // locate the problem of this tile
   int lo = 0, hi = n_probs - 1;
   const int tile = blockIdx.x;
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(256) k_grouped_gemm(const GemmProb *__restrict
   const int tm = local / tiles_n, tn = local % tiles_n;
   const int row0 = tm * GT, col0 = tn * GT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 1, wn = warp & 1;  // 4 x 2 warps, each 16 rows x 32 cols
+  const int wm = warp >> 1, wn = warp & 1;
   double acc[2][4][2];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -54,34 +55,54 @@ __global__ void __launch_bounds__(256) k_grouped_gemm(const GemmProb *__restrict
 
   const bool a_rowmajor = (pr.acs == 1);
   const bool b_rowmajor = (pr.bcs == 1);
-  for (int k0 = 0; k0 < pr.k; k0 += GK) {
+  // this thread's four elements of each staged tile
+  int ai[4], ak[4], bk[4], bj[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int e = tid + 256 * r;
+    if (a_rowmajor) { ai[r] = e / GK; ak[r] = e % GK; } else { ai[r] = e % GT; ak[r] = e / GT; }
+    if (b_rowmajor) { bk[r] = e / GT; bj[r] = e % GT; } else { bk[r] = e % GK; bj[r] = e / GK; }
+  }
+  double ra[4], rb[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const int e = tid + 256 * r;
-      int i, kk;
-      if (a_rowmajor) { i = e / GK; kk = e % GK; } else { i = e % GT; kk = e / GT; }
-      const int gi = row0 + i, gk = k0 + kk;
-      As[i][kk] = (gi < pr.m && gk < pr.k) ? pr.A[gi * pr.ars + gk * pr.acs] : 0.0;
-      int j;
-      if (b_rowmajor) { kk = e / GT; j = e % GT; } else { kk = e % GK; j = e / GK; }
-      const int gj = col0 + j;
-      const int gk2 = k0 + kk;
-      Bs[kk][j] = (gj < pr.n && gk2 < pr.k) ? pr.B[gk2 * pr.brs + gj * pr.bcs] : 0.0;
+      const int gi = row0 + ai[r], gk = k0 + ak[r];
+      ra[r] = (gi < pr.m && gk < pr.k) ? __ldg(pr.A + gi * pr.ars + gk * pr.acs) : 0.0;
+      const int gj = col0 + bj[r], gk2 = k0 + bk[r];
+      rb[r] = (gj < pr.n && gk2 < pr.k) ? __ldg(pr.B + gk2 * pr.brs + gj * pr.bcs) : 0.0;
     }
-    __syncthreads();
+  };
+  auto stage = [&](int buf) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      As[buf][ai[r] * AS_LD + ak[r]] = ra[r];
+      Bs[buf][bk[r] * BS_LD + bj[r]] = rb[r];
+    }
+  };
+  fetch(0);
+  stage(0);
+  __syncthreads();
+  int cur = 0;
+  for (int k0 = 0; k0 < pr.k; k0 += GK) {
+    const bool more = k0 + GK < pr.k;
+    if (more) fetch(k0 + GK);
+    const double *as = As[cur], *bs = Bs[cur];
 #pragma unroll
     for (int kk = 0; kk < GK; kk += 4) {
       double a[2], b[4];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) a[i] = As[wm * 16 + i * 8 + (lane >> 2)][kk + (lane & 3)];
+      for (int i = 0; i < 2; ++i) a[i] = as[(wm * 16 + i * 8 + (lane >> 2)) * AS_LD + kk + (lane & 3)];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk + (lane & 3)][wn * 32 + j * 8 + (lane >> 2)];
+      for (int j = 0; j < 4; ++j) b[j] = bs[(kk + (lane & 3)) * BS_LD + wn * 32 + j * 8 + (lane >> 2)];
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
+    if (more) stage(cur ^ 1);
     __syncthreads();
+    cur ^= 1;
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -90,10 +111,11 @@ __global__ void __launch_bounds__(256) k_grouped_gemm(const GemmProb *__restrict
       const int gi = row0 + wm * 16 + i * 8 + (lane >> 2);
       const int gj = col0 + wn * 32 + j * 8 + (lane & 3) * 2;
       if (gi < pr.m) {
+        double *crow = pr.C + int64_t(pr.crow ? pr.crow[gi] : gi) * pr.ldc;
 #pragma unroll
         for (int t = 0; t < 2; ++t)
           if (gj + t < pr.n) {
-            double *c = pr.C + int64_t(gi) * pr.ldc + gj + t;
+            double *c = crow + gj + t;
             const double old = (pr.beta == 0.0) ? 0.0 : pr.beta * (*c);
             *c = pr.alpha * acc[i][j][t] + old;
           }
@@ -444,49 +466,6 @@ __global__ void __launch_bounds__(256) k_backward_large(SolveArgs a, const WorkI
 // is staged into shared memory by one TMA bulk copy (cp.async.bulk + mbarrier); all index structure comes from
 // the shared template, so HBM traffic is the factor, the right-hand side and the solution.
 // =================================================================================================================
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void bulk_load_start(double *dst, const double *src, uint32_t bytes, uint64_t *bar) {
-  // one thread: arm the barrier with the byte count, then issue the bulk copies (<= 64 KB each)
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-  uint32_t done = 0;
-  while (done < bytes) {
-    const uint32_t n = min(bytes - done, 65536u);
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-            smem_u32(reinterpret_cast<char *>(dst) + done)),
-        "l"(reinterpret_cast<const char *>(src) + done), "r"(n), "r"(smem_u32(bar))
-        : "memory");
-    done += n;
-  }
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(bar)) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-
-__device__ __forceinline__ int64_t subtree_dof(const SubtreeArgs &a, const InstanceDev &in, int32_t code) {
-  const int type = code >> 30, dj = (code >> 15) & 0x7fff, di = code & 0x7fff;
-  const int64_t canon = type == 0 ? int64_t(in.J0 + dj) * (a.nx + 1) + in.I0 + di
-                                  : a.nxe + int64_t(in.J0 + dj) * a.nx + in.I0 + di;
-  return a.dof_of_canon ? int64_t(a.dof_of_canon[canon]) : canon;
-}
-
 template <int M>
 __global__ void __launch_bounds__(256) k_subtree_forward(SubtreeArgs a) {
   extern __shared__ __align__(16) double sm[];

@@ -61,6 +61,7 @@ struct GemmProb {
   int32_t m, n, k, ldc;
   int64_t ars, acs, brs, bcs;  // element (i,k) of A at A[i*ars + k*acs]; (k,j) of B at B[k*brs + j*bcs]
   double alpha, beta;
+  const int32_t *crow;  // optional row map of C: row i is written at C + crow[i] * ldc (nullptr: i)
 };
 
 struct InvProb {

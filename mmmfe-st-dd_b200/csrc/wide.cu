@@ -1,0 +1,416 @@
+// Multi-column solve / time-stepping kernels and the block-Toeplitz operator kernel (sm_100a).  See wide.cuh.
+#include "wide.cuh"
+
+#include <algorithm>
+
+#include "dev_common.cuh"
+
+namespace mmmfe {
+
+// =================================================================================================================
+// time stepping, MW columns: thread = (row, column), columns fastest (coalesced rows of MW doubles)
+// =================================================================================================================
+__global__ void __launch_bounds__(256) k_wide_rhs(WideStep a) {
+  const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  const int64_t e = idx / a.MW;
+  if (e >= a.n_flux) return;
+  const int j = int(idx - e * a.MW);
+  double acc = 0.0;
+  for (int64_t k = a.kup_rp[e]; k < a.kup_rp[e + 1]; ++k) acc -= a.kup_val[k] * a.ptil[int64_t(a.kup_col[k]) * a.MW + j];
+  a.x[idx] = acc;
+}
+
+void launch_wide_rhs(const WideStep &a, cudaStream_t st) {
+  const int64_t n = a.n_flux * a.MW;
+  k_wide_rhs<<<unsigned((n + 255) / 256), 256, 0, st>>>(a);
+  launch_counter_add(1);
+}
+
+__global__ void __launch_bounds__(256) k_wide_add(WideStep a, const int64_t *__restrict__ lvl_rp,
+                                                  const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                                                  const double *__restrict__ val, int32_t n_lvl) {
+  const int32_t level = a.state[0], pass = a.state[1];
+  if (level >= n_lvl) return;
+  const int64_t *rp = lvl_rp + int64_t(pass) * (n_lvl + 1) + level;
+  const int64_t e = rp[0] + blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (e >= rp[1]) return;
+  a.x[int64_t(row[e]) * a.MW + col[e]] += val[e];  // (row, column) pairs are unique within a level
+}
+
+void launch_wide_add(const WideStep &a, const int64_t *lvl_rp, const int32_t *row, const int32_t *col, const double *val,
+                     int32_t n_lvl, int64_t max_entries, cudaStream_t st) {
+  if (max_entries <= 0) return;
+  k_wide_add<<<unsigned((max_entries + 255) / 256), 256, 0, st>>>(a, lvl_rp, row, col, val, n_lvl);
+  launch_counter_add(1);
+}
+
+__global__ void __launch_bounds__(256) k_wide_update(WideStep a, const int32_t *__restrict__ tr_dof, int32_t n_tr,
+                                                     double *__restrict__ trace) {
+  const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  const int64_t r = idx / a.MW;
+  const int j = int(idx - r * a.MW);
+  if (r < a.n_pressure) {
+    double acc = 0.0;
+    for (int64_t k = a.kpu_rp[r]; k < a.kpu_rp[r + 1]; ++k) acc += a.kpu_val[k] * a.x[int64_t(a.kpu_col[k]) * a.MW + j];
+    a.ptil[idx] -= a.minv[r] * acc;
+    return;
+  }
+  const int64_t t = r - a.n_pressure;
+  if (t < n_tr) trace[(int64_t(a.state[0]) * n_tr + t) * a.MW + j] = a.x[int64_t(tr_dof[t]) * a.MW + j];
+}
+
+void launch_wide_update(const WideStep &a, const int32_t *tr_dof, int32_t n_tr, double *trace, cudaStream_t st) {
+  const int64_t n = (a.n_pressure + n_tr) * a.MW;
+  k_wide_update<<<unsigned((n + 255) / 256), 256, 0, st>>>(a, tr_dof, n_tr, trace);
+  launch_counter_add(1);
+}
+
+__global__ void k_wide_next_level(int32_t *state) { state[0] += 1; }
+
+void launch_wide_next_level(int32_t *state, cudaStream_t st) {
+  k_wide_next_level<<<1, 1, 0, st>>>(state);
+  launch_counter_add(1);
+}
+
+// =================================================================================================================
+// top of the tree: gathers around the per-level grouped GEMMs
+// =================================================================================================================
+__global__ void __launch_bounds__(256) k_wide_fwd_gather(SolveArgs a, int32_t MW, const WideRow *__restrict__ rows,
+                                                         int64_t n_rows) {
+  const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  const int64_t w = idx / MW;
+  if (w >= n_rows) return;
+  const int j = int(idx - w * MW);
+  const WideRow rw = rows[w];
+  const FrontDesc fd = a.fronts[rw.node];
+  const int32_t f = fd.s + fd.b, p = rw.p;
+  double v = p < fd.s ? a.x[int64_t(a.idx[fd.idx_off + p]) * MW + j] : 0.0;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int32_t ch = c ? fd.child1 : fd.child0;
+    if (ch < 0) continue;
+    const int32_t q = a.src[fd.src_off + int64_t(c) * f + p];
+    if (q < 0) continue;
+    const FrontDesc cd = a.fronts[ch];
+    v += a.z[(cd.z_off + cd.s + q) * MW + j];
+  }
+  a.z[(fd.z_off + p) * MW + j] = v;
+}
+
+void launch_wide_fwd_gather(const SolveArgs &a, int32_t MW, const WideRow *rows, int64_t n_rows, cudaStream_t st) {
+  if (n_rows <= 0) return;
+  k_wide_fwd_gather<<<unsigned((n_rows * MW + 255) / 256), 256, 0, st>>>(a, MW, rows, n_rows);
+  launch_counter_add(1);
+}
+
+__global__ void __launch_bounds__(256) k_wide_bwd_gather(SolveArgs a, int32_t MW, const WideRow *__restrict__ rows,
+                                                         int64_t n_rows) {
+  const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  const int64_t w = idx / MW;
+  if (w >= n_rows) return;
+  const int j = int(idx - w * MW);
+  const WideRow rw = rows[w];
+  const FrontDesc fd = a.fronts[rw.node];
+  const int32_t p = fd.s + rw.p;
+  a.z[(fd.z_off + p) * MW + j] = a.x[int64_t(a.idx[fd.idx_off + p]) * MW + j];
+}
+
+void launch_wide_bwd_gather(const SolveArgs &a, int32_t MW, const WideRow *rows, int64_t n_rows, cudaStream_t st) {
+  if (n_rows <= 0) return;
+  k_wide_bwd_gather<<<unsigned((n_rows * MW + 255) / 256), 256, 0, st>>>(a, MW, rows, n_rows);
+  launch_counter_add(1);
+}
+
+// =================================================================================================================
+// bottom of the tree: one CTA per subtree, factor blob staged once (TMA bulk copy), column chunks of MC
+// =================================================================================================================
+template <int MC>
+__global__ void __launch_bounds__(256) k_wide_subtree_forward(SubtreeArgs a, int32_t MW) {
+  extern __shared__ __align__(16) double sm[];
+  const InstanceDev in = a.inst[blockIdx.x];
+  const TemplateDev T = a.tmpl[in.tmpl];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(sm);
+  double *blob = sm + 2;
+  double *zl = blob + T.rf_size;
+  double *vs = zl + int64_t(T.zl_size) * MC;
+  const int tid = threadIdx.x;
+  if (tid == 0) mbar_init(bar);
+  __syncthreads();
+  if (tid == 0 && T.rf_size > 0) bulk_load_start(blob, a.R + in.rf_base, uint32_t(T.rf_size) * 8u, bar);
+  bool waited = T.rf_size <= 0;
+  const int32_t zr = T.node_zl[T.n_nodes - 1];
+  for (int32_t c0 = 0; c0 < MW; c0 += MC) {
+    for (int l = tid; l < T.n_int; l += 256) {
+      const int64_t d = subtree_dof(a, in, T.var_code[l]);
+#pragma unroll
+      for (int j = 0; j < MC; ++j) vs[l * MC + j] = (c0 + j < MW) ? a.x[d * MW + c0 + j] : 0.0;
+    }
+    __syncthreads();
+    if (!waited) { mbar_wait(bar, 0); waited = true; }
+    for (int lv = 0; lv < T.n_levels; ++lv) {
+      if (lv > 0) {
+        for (int e = T.lvl_sep[lv] + tid; e < T.lvl_sep[lv + 1]; e += 256) {
+          const int32_t s0 = T.sep_c0[e], s1 = T.sep_c1[e];
+#pragma unroll
+          for (int j = 0; j < MC; ++j) {
+            double v = vs[e * MC + j];
+            if (s0 >= 0) v += zl[s0 * MC + j];
+            if (s1 >= 0) v += zl[s1 * MC + j];
+            vs[e * MC + j] = v;
+          }
+        }
+        __syncthreads();
+      }
+      for (int e = T.lvl_out[lv] + tid; e < T.lvl_out[lv + 1]; e += 256) {
+        const int32_t n = T.out_node[e];
+        const int32_t s = T.node_s[n], b = T.node_b[n];
+        const double *rf = blob + T.node_rf[n] + (e - T.node_zl[n]);
+        const double *v = vs + int64_t(T.node_sep[n]) * MC;
+        double acc[MC];
+        const int32_t o0 = T.out_c0[e], o1 = T.out_c1[e];
+#pragma unroll
+        for (int j = 0; j < MC; ++j) {
+          acc[j] = 0.0;
+          if (o0 >= 0) acc[j] += zl[o0 * MC + j];
+          if (o1 >= 0) acc[j] += zl[o1 * MC + j];
+        }
+        for (int i = 0; i < s; ++i) {
+          const double r = rf[i * b];
+#pragma unroll
+          for (int j = 0; j < MC; ++j) acc[j] += r * v[i * MC + j];
+        }
+#pragma unroll
+        for (int j = 0; j < MC; ++j) zl[e * MC + j] = acc[j];
+      }
+      __syncthreads();
+    }
+    for (int l = tid; l < T.n_int; l += 256) {
+      const int64_t d = subtree_dof(a, in, T.var_code[l]);
+#pragma unroll
+      for (int j = 0; j < MC; ++j)
+        if (c0 + j < MW) a.x[d * MW + c0 + j] = vs[l * MC + j];
+    }
+    for (int q = tid; q < T.n_rootb; q += 256)
+#pragma unroll
+      for (int j = 0; j < MC; ++j)
+        if (c0 + j < MW) a.z[(in.z_root + q) * MW + c0 + j] = zl[(zr + q) * MC + j];
+    __syncthreads();  // vs / zl are reused by the next column chunk
+  }
+}
+
+template <int MC>
+__global__ void __launch_bounds__(256) k_wide_subtree_backward(SubtreeArgs a, int32_t MW) {
+  extern __shared__ __align__(16) double sm[];
+  const InstanceDev in = a.inst[blockIdx.x];
+  const TemplateDev T = a.tmpl[in.tmpl];
+  uint64_t *bar = reinterpret_cast<uint64_t *>(sm);
+  double *blob = sm + 2;
+  double *zs = blob + T.rb_size;            // accumulated right-hand sides of the interior variables
+  double *xs = zs + int64_t(T.n_int) * MC;  // solution: [interior | root boundary]
+  const int tid = threadIdx.x;
+  if (tid == 0) mbar_init(bar);
+  __syncthreads();
+  if (tid == 0) bulk_load_start(blob, a.R + in.rb_base, uint32_t(T.rb_size) * 8u, bar);
+  bool waited = false;
+  for (int32_t c0 = 0; c0 < MW; c0 += MC) {
+    for (int l = tid; l < T.n_int; l += 256) {
+      const int64_t d = subtree_dof(a, in, T.var_code[l]);
+#pragma unroll
+      for (int j = 0; j < MC; ++j) zs[l * MC + j] = (c0 + j < MW) ? a.x[d * MW + c0 + j] : 0.0;
+    }
+    for (int q = tid; q < T.n_rootb; q += 256) {
+      const int64_t d = subtree_dof(a, in, T.rootb_code[q]);
+#pragma unroll
+      for (int j = 0; j < MC; ++j) xs[(T.n_int + q) * MC + j] = (c0 + j < MW) ? a.x[d * MW + c0 + j] : 0.0;
+    }
+    __syncthreads();
+    if (!waited) { mbar_wait(bar, 0); waited = true; }
+    for (int lv = T.n_levels - 1; lv >= 0; --lv) {
+      for (int e = T.lvl_sep[lv] + tid; e < T.lvl_sep[lv + 1]; e += 256) {
+        const int32_t n = T.sep_node[e];
+        const int32_t s = T.node_s[n], b = T.node_b[n], sep0 = T.node_sep[n];
+        const double *rb = blob + T.node_rb[n] + (e - sep0);  // R^T[p][i] at p * s + i
+        const int32_t *bv = T.bnd_var + T.node_bnd[n];
+        double acc[MC];
+#pragma unroll
+        for (int j = 0; j < MC; ++j) acc[j] = 0.0;
+        for (int p = 0; p < s; ++p) {
+          const double r = rb[p * s];
+#pragma unroll
+          for (int j = 0; j < MC; ++j) acc[j] += r * zs[(sep0 + p) * MC + j];
+        }
+        rb += s * s;
+        for (int q = 0; q < b; ++q) {
+          const double r = rb[q * s];
+          const int32_t l = bv[q];
+#pragma unroll
+          for (int j = 0; j < MC; ++j) acc[j] += r * xs[l * MC + j];
+        }
+#pragma unroll
+        for (int j = 0; j < MC; ++j) xs[e * MC + j] = acc[j];
+      }
+      __syncthreads();
+    }
+    for (int l = tid; l < T.n_int; l += 256) {
+      const int64_t d = subtree_dof(a, in, T.var_code[l]);
+#pragma unroll
+      for (int j = 0; j < MC; ++j)
+        if (c0 + j < MW) a.x[d * MW + c0 + j] = xs[l * MC + j];
+    }
+    __syncthreads();
+  }
+}
+
+void wide_set_smem_limit(size_t bytes) {
+  cudaFuncSetAttribute(k_wide_subtree_forward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+  cudaFuncSetAttribute(k_wide_subtree_forward<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+  cudaFuncSetAttribute(k_wide_subtree_backward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+  cudaFuncSetAttribute(k_wide_subtree_backward<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+}
+
+void launch_wide_subtree_forward(int MC, int32_t MW, const SubtreeArgs &a, int32_t n_inst, size_t smem_bytes, cudaStream_t st) {
+  if (n_inst <= 0) return;
+  if (MC == 8) k_wide_subtree_forward<8><<<n_inst, 256, smem_bytes, st>>>(a, MW);
+  else k_wide_subtree_forward<4><<<n_inst, 256, smem_bytes, st>>>(a, MW);
+  launch_counter_add(1);
+}
+
+void launch_wide_subtree_backward(int MC, int32_t MW, const SubtreeArgs &a, int32_t n_inst, size_t smem_bytes, cudaStream_t st) {
+  if (n_inst <= 0) return;
+  if (MC == 8) k_wide_subtree_backward<8><<<n_inst, 256, smem_bytes, st>>>(a, MW);
+  else k_wide_subtree_backward<4><<<n_inst, 256, smem_bytes, st>>>(a, MW);
+  launch_counter_add(1);
+}
+
+// =================================================================================================================
+// fine -> mortar projection of the stored traces of all columns: one sparse row per operator row
+// =================================================================================================================
+__global__ void __launch_bounds__(256) k_wide_f2c(int64_t n_rows, const int64_t *__restrict__ rp,
+                                                  const int64_t *__restrict__ col, const double *__restrict__ val,
+                                                  const double *__restrict__ trace, int32_t MW, int32_t n_cols,
+                                                  double *__restrict__ T, int64_t ldt, const int64_t *__restrict__ t_row,
+                                                  int64_t col0) {
+  const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  const int64_t r = idx / n_cols;
+  if (r >= n_rows) return;
+  const int j = int(idx - r * n_cols);
+  double acc = 0.0;
+  for (int64_t e = rp[r]; e < rp[r + 1]; ++e) acc += val[e] * trace[col[e] * MW + j];
+  T[t_row[r] * ldt + col0 + j] = acc;
+}
+
+void launch_wide_f2c(int64_t n_rows, const int64_t *rp, const int64_t *col, const double *val, const double *trace,
+                     int32_t MW, int32_t n_cols, double *T, int64_t ldt, const int64_t *t_row, int64_t col0,
+                     cudaStream_t st) {
+  if (n_rows <= 0 || n_cols <= 0) return;
+  k_wide_f2c<<<unsigned((n_rows * n_cols + 255) / 256), 256, 0, st>>>(n_rows, rp, col, val, trace, MW, n_cols, T, ldt,
+                                                                     t_row, col0);
+  launch_counter_add(1);
+}
+
+// =================================================================================================================
+// block lower-triangular Toeplitz operator application (FP64 DMMA)
+//   tile = 64 operator rows (a') x 32 mortar time slabs (I) of one (subdomain, output side);
+//   k runs over (d, input side, a): A = T_d rows, B[k][I] = q[(side, I - d, a)] (zero for I < d)
+// Every output entry is written by exactly one thread: deterministic, no atomics.
+// =================================================================================================================
+constexpr int TA_LD = 16 + 4;
+constexpr int TB_LD = TOEP_BN + 4;
+
+__global__ void __launch_bounds__(256) k_toeplitz_apply(const ToepProb *__restrict__ probs,
+                                                        const ToepTile *__restrict__ tiles,
+                                                        const double *__restrict__ q, double *__restrict__ out) {
+  __shared__ double As[2][TOEP_BM * TA_LD];
+  __shared__ double Bs[2][16 * TB_LD];
+  const ToepTile tl = tiles[blockIdx.x];
+  const ToepProb pr = probs[tl.prob];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;  // 4 x 2 warps: 16 rows x 16 slabs each
+  double acc[2][2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const int slab_hi = min(pr.m_t, tl.slab0 + TOEP_BN) - 1;  // last slab of this tile: delays d = 0 .. slab_hi
+  // position in the k space
+  int d = 0, s = 0, a0 = 0;
+  double ra[4], rb[2];
+  auto fetch = [&]() {
+    const int P = pr.P_in[s];
+    const double *Td = pr.T + int64_t(d) * pr.d_stride + int64_t(pr.row_base + tl.row0) * pr.ldt + pr.col_base[s] + a0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = tid + 256 * r, i = e >> 4, kk = e & 15;
+      ra[r] = (tl.row0 + i < pr.P_out && a0 + kk < P) ? __ldg(Td + int64_t(i) * pr.ldt + kk) : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int e = tid + 256 * r, n = e >> 4, kk = e & 15;
+      const int I = tl.slab0 + n, J = I - d;
+      rb[r] = (I < pr.m_t && J >= 0 && a0 + kk < P) ? __ldg(q + pr.in_off[s] + int64_t(J) * P + a0 + kk) : 0.0;
+    }
+  };
+  auto stage = [&](int buf) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = tid + 256 * r;
+      As[buf][(e >> 4) * TA_LD + (e & 15)] = ra[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int e = tid + 256 * r;
+      Bs[buf][(e & 15) * TB_LD + (e >> 4)] = rb[r];
+    }
+  };
+  auto advance = [&]() {  // next k slab; false when the k space is exhausted
+    a0 += 16;
+    if (a0 >= pr.P_in[s]) { a0 = 0; ++s; }
+    if (s >= pr.n_in) { s = 0; ++d; }
+    return d <= slab_hi;
+  };
+  fetch();
+  stage(0);
+  __syncthreads();
+  int cur = 0;
+  bool more = true;
+  while (more) {
+    more = advance();
+    if (more) fetch();
+    const double *as = As[cur], *bs = Bs[cur];
+#pragma unroll
+    for (int kk = 0; kk < 16; kk += 4) {
+      double av[2], bv[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) av[i] = as[(wm * 16 + i * 8 + (lane >> 2)) * TA_LD + kk + (lane & 3)];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) bv[j] = bs[(kk + (lane & 3)) * TB_LD + wn * 16 + j * 8 + (lane >> 2)];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+    }
+    if (more) stage(cur ^ 1);
+    __syncthreads();
+    cur ^= 1;
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int row = tl.row0 + wm * 16 + i * 8 + (lane >> 2);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int I = tl.slab0 + wn * 16 + j * 8 + (lane & 3) * 2 + t;
+        if (row < pr.P_out && I < pr.m_t) out[pr.out_off + int64_t(I) * pr.P_out + row] = acc[i][j][t];
+      }
+    }
+}
+
+void launch_toeplitz_apply(const ToepProb *probs, const ToepTile *tiles, int32_t n_tiles, const double *q, double *out,
+                           cudaStream_t st) {
+  if (n_tiles <= 0) return;
+  k_toeplitz_apply<<<n_tiles, 256, 0, st>>>(probs, tiles, q, out);
+  launch_counter_add(1);
+}
+
+}  // namespace mmmfe

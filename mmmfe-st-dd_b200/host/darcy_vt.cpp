@@ -750,6 +750,7 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
       throw std::runtime_error("no usable CUDA device: the interface-GMRES path has no CPU fallback");
     struct Guard { mmmfe_ctx *c; ~Guard() { mmmfe_destroy(c); } } guard{ctx};
     mmmfe_set_option(ctx, "keep_history", control.final_sweep ? 1 : 0);
+    mmmfe_set_option(ctx, "mortar_time_slabs", mortar[2]);  // lets the engine build the multiscale-basis operator
     {
       std::string all;
       if (const char *env = std::getenv("MMMFE_ENGINE_OPTIONS")) all = env;
@@ -790,6 +791,11 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
     rep.factor_groups = mmmfe_num_factor_groups(ctx);
     rep.sweep_batches = int(mmmfe_stat(ctx, "sweep_batches"));
     rep.tune_rel_diff_e18 = mmmfe_stat(ctx, "tune_rel_diff_e18");
+    rep.basis_operator = int(mmmfe_stat(ctx, "basis_operator"));
+    rep.t_basis = double(mmmfe_stat(ctx, "basis_us")) * 1e-6;
+    rep.basis_gflop = double(mmmfe_stat(ctx, "basis_mflop")) * 1e-3;
+    rep.basis_bytes = double(mmmfe_stat(ctx, "basis_mbytes")) * 1e6;
+    rep.basis_columns = mmmfe_stat(ctx, "basis_columns");
     for (auto &sp : subs) { rep.dof_steps += (long long)sp->n * sp->nt; sp->matrix = Csr(); }
     // ---- bar problems ----
     t0 = clk::now();

@@ -32,7 +32,7 @@ def unique_id(rank):
     return bytes(buf.cpu().numpy().tobytes())
 
 
-SWEEP_ON = "use_sweep=1,sweep_autotune=0,sweep_crosscheck=1,subtree_cells=64"
+SWEEP_ON = "operator=0,use_sweep=1,sweep_autotune=0,sweep_crosscheck=1,subtree_cells=64"
 
 
 def main():

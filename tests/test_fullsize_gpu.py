@@ -11,7 +11,7 @@ import pytest
 from helpers import default_params, mo, pkg, rel_l2
 
 pytestmark = pytest.mark.gpu
-SWEEP_ON = "use_sweep=1,sweep_autotune=0,sweep_crosscheck=1"
+SWEEP_ON = "operator=0,use_sweep=1,sweep_autotune=0,sweep_crosscheck=1"
 
 
 def _problem_without_lu(mesh, mortar, k=1):
