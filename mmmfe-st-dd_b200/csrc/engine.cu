@@ -99,6 +99,14 @@ struct Sub {
 struct Basis {
   int32_t m_t = 0, lvl_per_slab = 0, nt = 0;
   int32_t n_slots = 0, slot_of_side[4] = {-1, -1, -1, -1}, side_of_slot[4] = {0, 0, 0, 0};
+  int32_t P[4] = {0, 0, 0, 0}, n_side[4] = {0, 0, 0, 0}, base[4] = {0, 0, 0, 0}, tr_base[4] = {0, 0, 0, 0};
+  int32_t rep[4] = {-1, -1, -1, -1};  // local subdomain whose tables represent the slot
+  int32_t P_tot = 0, n_tr = 0, MW = 0, n_pass = 0, MC = 8;
+  int64_t ldt = 0;
+  DevBuf<double> T;
+  double seconds = 0.0, flops = 0.0, bytes = 0.0;
+  long long graph_kernels = 0;
+};
 
 // ---- one factor: nested-dissection tree + block-inverse fronts on the device -------------------------------------
 struct LevelWork {  // one height level of the top of the tree
@@ -145,14 +153,6 @@ struct Factor {
   std::unique_ptr<Basis> basis;  // multiscale flux basis of this factor group (time-Toeplitz operator)
 };
 
-  int32_t P[4] = {0, 0, 0, 0}, n_side[4] = {0, 0, 0, 0}, base[4] = {0, 0, 0, 0}, tr_base[4] = {0, 0, 0, 0};
-  int32_t rep[4] = {-1, -1, -1, -1};  // local subdomain whose tables represent the slot
-  int32_t P_tot = 0, n_tr = 0, MW = 0, n_pass = 0, MC = 8;
-  int64_t ldt = 0;
-  DevBuf<double> T;
-  double seconds = 0.0, flops = 0.0, bytes = 0.0;
-  long long graph_kernels = 0;
-};
 
 // ---- one batch: up to 4 subdomains solved as simultaneous right-hand sides of one factor ---------------------------
 struct Batch {
