@@ -16,6 +16,19 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
+// Asynchronous 8-byte copy global -> shared (LDGSTS); pred == false writes a zero without touching global memory.
+// Element-wise so that every operand layout and alignment the callers have works; the copies of one stage are
+// committed as a group and waited for STAGES - 2 groups later (multi-stage software pipeline).
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, bool pred) {
+  const int n = pred ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
 __device__ __forceinline__ void bulk_load_start(double *dst, const double *src, uint32_t bytes, uint64_t *bar) {
   // one thread: arm the barrier with the byte count, then issue the bulk copies (<= 64 KB each)
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");

@@ -253,7 +253,7 @@ struct mmmfe_ctx {
   std::string basis_note;  // why the basis operator is not in use
   DevBuf<ToepProb> toep_probs;
   DevBuf<ToepTile> toep_tiles;
-  int32_t n_toep_tiles = 0;
+  int32_t n_toep_tiles = 0, toep_bm = 64;
   double basis_seconds = 0.0, basis_flops = 0.0, basis_bytes = 0.0, toep_flops = 0.0, toep_bytes = 0.0;
   int64_t basis_columns = 0;
   // temporaries of the factorisation
@@ -921,7 +921,7 @@ static void exchange_and_combine(mmmfe_ctx *c, double sign, double *out, bool se
 // Ap = S q for q resident in d_q (src/darcy_vtdd.cc:1316-1411)
 static void apply_operator(mmmfe_ctx *c, const double *d_q, double *d_ap) {
   if (c->use_basis) {  // send = (signed f2c . star sweeps . c2f) q as one block-Toeplitz product per subdomain
-    launch_toeplitz_apply(c->toep_probs.p, c->toep_tiles.p, c->n_toep_tiles, d_q, c->send.p, c->stream);
+    launch_toeplitz_apply(c->toep_bm, c->toep_probs.p, c->toep_tiles.p, c->n_toep_tiles, d_q, c->send.p, c->stream);
     exchange_and_combine(c, -1.0, d_ap, true);
     return;
   }
@@ -952,7 +952,13 @@ static void allreduce_sum(mmmfe_ctx *c, double *d, size_t n) {
 static bool slab_structured(const HostCsr &c2f, const HostCsr &f2c, int64_t ns, int64_t nt, int64_t m_t, int64_t P,
                             std::string &why) {
   const int64_t r = nt / m_t;
-  auto close = [](double a, double b) { return std::fabs(a - b) <= 1e-12 * std::max(std::fabs(a), std::fabs(b)); };
+  // entries that are zero in exact arithmetic (odd Legendre modes at a midpoint) come out as round-off of either
+  // sign: compare against the size of the table, not of the entry
+  double c2f_max = 0, f2c_max = 0;
+  for (double v : c2f.val) c2f_max = std::max(c2f_max, std::fabs(v));
+  for (double v : f2c.val) f2c_max = std::max(f2c_max, std::fabs(v));
+  double scale = c2f_max;
+  auto close = [&](double a, double b) { return std::fabs(a - b) <= 1e-12 * scale; };
   for (int64_t lvl = 0; lvl < nt; ++lvl) {
     const int64_t J = lvl / r;
     for (int64_t i = 0; i < ns; ++i) {
@@ -964,6 +970,7 @@ static bool slab_structured(const HostCsr &c2f, const HostCsr &f2c, int64_t ns, 
       }
     }
   }
+  scale = f2c_max;
   for (int64_t J = 0; J < m_t; ++J)
     for (int64_t a = 0; a < P; ++a) {
       const int64_t row = J * P + a;
@@ -1175,6 +1182,47 @@ static void compute_basis(mmmfe_ctx *c, Factor &F, Basis &B) {
     launch_wide_next_level(state.p, st);
   };
   CUDA_CHECK(cudaStreamSynchronize(st));
+  if (std::getenv("MMMFE_BASIS_PROFILE")) {  // one instrumented step (level 0 of pass 0), microseconds per kernel class
+    const int32_t init[2] = {0, 0};
+    CUDA_CHECK(cudaMemcpy(state.p, init, sizeof init, cudaMemcpyHostToDevice));
+    ptil.zero(st);
+    std::vector<cudaEvent_t> ev;
+    std::vector<const char *> name;
+    auto mark = [&](const char *nm) {
+      cudaEvent_t e;
+      CUDA_CHECK(cudaEventCreate(&e));
+      CUDA_CHECK(cudaEventRecord(e, st));
+      ev.push_back(e); name.push_back(nm);
+    };
+    for (int rep = 0; rep < 2; ++rep) {  // second repetition is reported (warm caches, attributes set)
+      ev.clear(); name.clear();
+      mark("start");
+      launch_wide_rhs(ws, st);
+      launch_wide_add(ws, d_add_rp.p, d_add_row.p, d_add_col.p, d_add_val.p, r, add_max, st); mark("rhs");
+      launch_wide_subtree_forward(B.MC, MW, sub, F.n_inst, smem_f, st); mark("subtree_fwd");
+      for (auto &L : lvls) launch_wide_fwd_gather(sa, MW, L->fwd_rows.p, int64_t(L->fwd_rows.n), st);
+      mark("fwd_gathers(all levels, without their gemms)");
+      for (auto &L : lvls) launch_grouped_gemm(L->fwd_probs.p, L->fwd_tiles.p, L->n_fwd, L->t_fwd, st);
+      mark("fwd_gemms");
+      for (auto it = lvls.rbegin(); it != lvls.rend(); ++it) launch_wide_bwd_gather(sa, MW, (*it)->bwd_rows.p, int64_t((*it)->bwd_rows.n), st);
+      mark("bwd_gathers");
+      for (auto it = lvls.rbegin(); it != lvls.rend(); ++it) launch_grouped_gemm((*it)->bwd_probs.p, (*it)->bwd_tiles.p, (*it)->n_bwd, (*it)->t_bwd, st);
+      mark("bwd_gemms");
+      launch_wide_subtree_backward(B.MC, MW, sub, F.n_inst, smem_b, st); mark("subtree_bwd");
+      launch_wide_update(ws, d_tr_dof.p, B.n_tr, trace.p, st); mark("update");
+      CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    std::fprintf(stderr, "[basis profile] grid %dx%d nt %d columns %d MW %d passes %d MC %d levels %zu subtrees %d smem %zu/%zu:",
+                 F.nx, F.ny, nt, B.P_tot, MW, B.n_pass, B.MC, lvls.size(), F.n_inst, smem_f, smem_b);
+    for (size_t i = 1; i < ev.size(); ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      std::fprintf(stderr, " %s %.1f us;", name[i], ms * 1e3);
+    }
+    std::fprintf(stderr, "\n");
+    for (auto e : ev) cudaEventDestroy(e);
+    if (std::atoi(std::getenv("MMMFE_BASIS_PROFILE")) == 2) fail(MMMFE_E_INVALID, "MMMFE_BASIS_PROFILE=2: profile only");
+  }
   cudaGraph_t g = nullptr;
   cudaGraphExec_t ge = nullptr;
   if (c->use_graphs) {
@@ -1265,10 +1313,19 @@ static void setup_basis_operator(mmmfe_ctx *c, const std::vector<int> &group_of)
       }
       c->toep_flops += 2.0 * pr.P_out * k_len * 0.5 * B.m_t * (B.m_t + 1.0);
       c->toep_bytes += 8.0 * pr.P_out * k_len * B.m_t;
-      for (int row0 = 0; row0 < pr.P_out; row0 += TOEP_BM)
-        for (int slab0 = 0; slab0 < B.m_t; slab0 += TOEP_BN) tiles.push_back({int32_t(probs.size()), row0, slab0});
       probs.push_back(pr);
     }
+  }
+  // rows per tile: the largest of 128 / 64 / 32 that still yields two tiles per SM
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  for (int bm : {128, 64, 32}) {
+    tiles.clear();
+    for (size_t p = 0; p < probs.size(); ++p)
+      for (int row0 = 0; row0 < probs[p].P_out; row0 += bm)
+        for (int slab0 = 0; slab0 < probs[p].m_t; slab0 += TOEP_BN) tiles.push_back({int32_t(p), row0, slab0});
+    c->toep_bm = bm;
+    if (int(tiles.size()) >= 2 * sms) break;
   }
   // heavy tiles (late slabs: long delay sums) first
   std::stable_sort(tiles.begin(), tiles.end(), [](const ToepTile &a, const ToepTile &b) { return a.slab0 > b.slab0; });

@@ -24,15 +24,17 @@ constexpr int GT = 64;         // C tile
 constexpr int GK = 16;         // k step
 constexpr int AS_LD = GK + 4;  // row strides of the staged tiles: fragment loads of a half-warp hit 16 distinct banks
 constexpr int BS_LD = GT + 4;
+constexpr int G_STAGES = 4;    // k slabs in flight (cp.async groups)
+constexpr int G_STAGE_DBL = GT * AS_LD + GK * BS_LD;
+constexpr size_t G_SMEM = size_t(G_STAGES) * G_STAGE_DBL * sizeof(double);
 
-// One 64 x 64 tile of one problem per CTA, 8 warps (4 x 2, 16 x 32 each).  The next k-slab of A and B is fetched into
-// registers while the current one is multiplied from shared memory (two staging buffers, one barrier per k step);
-// the global-load mapping follows the unit stride of each operand so that every layout the factorisation, the
-// multi-column solve and the operator application use is read in full 128-byte lines.
+// One 64 x 64 tile of one problem per CTA, 8 warps (4 x 2, 16 x 32 each).  A and B are staged through a four-deep
+// cp.async pipeline (three k slabs in flight while one is multiplied, one barrier per k step), so the many short
+// problems of the factorisation and of the multi-column solve are not bound by the global-load latency of a k step;
+// the copy mapping follows the unit stride of each operand so that every layout is read in full 128-byte lines.
 __global__ void __launch_bounds__(256) k_grouped_gemm(const GemmProb *__restrict__ probs,
                                                       const int32_t *__restrict__ tile_start, int32_t n_probs) {
-  __shared__ double As[2][GT * AS_LD];
-  __shared__ double Bs[2][GK * BS_LD];
+  extern __shared__ __align__(16) double gsm[];
   // locate the problem of this tile
   int lo = 0, hi = n_probs - 1;
   const int tile = blockIdx.x;
@@ -63,31 +65,30 @@ __global__ void __launch_bounds__(256) k_grouped_gemm(const GemmProb *__restrict
     if (a_rowmajor) { ai[r] = e / GK; ak[r] = e % GK; } else { ai[r] = e % GT; ak[r] = e / GT; }
     if (b_rowmajor) { bk[r] = e / GT; bj[r] = e % GT; } else { bk[r] = e % GK; bj[r] = e / GK; }
   }
-  double ra[4], rb[4];
-  auto fetch = [&](int k0) {
+  auto issue = [&](int stage, int k0) {
+    double *as = gsm + stage * G_STAGE_DBL, *bs = as + GT * AS_LD;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int gi = row0 + ai[r], gk = k0 + ak[r];
-      ra[r] = (gi < pr.m && gk < pr.k) ? __ldg(pr.A + gi * pr.ars + gk * pr.acs) : 0.0;
+      const bool pa = gi < pr.m && gk < pr.k;
+      cp_async8(as + ai[r] * AS_LD + ak[r], pa ? pr.A + gi * pr.ars + gk * pr.acs : pr.A, pa);
       const int gj = col0 + bj[r], gk2 = k0 + bk[r];
-      rb[r] = (gj < pr.n && gk2 < pr.k) ? __ldg(pr.B + gk2 * pr.brs + gj * pr.bcs) : 0.0;
+      const bool pb = gj < pr.n && gk2 < pr.k;
+      cp_async8(bs + bk[r] * BS_LD + bj[r], pb ? pr.B + gk2 * pr.brs + gj * pr.bcs : pr.B, pb);
     }
   };
-  auto stage = [&](int buf) {
+  const int nk = (pr.k + GK - 1) / GK;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      As[buf][ai[r] * AS_LD + ak[r]] = ra[r];
-      Bs[buf][bk[r] * BS_LD + bj[r]] = rb[r];
-    }
-  };
-  fetch(0);
-  stage(0);
-  __syncthreads();
-  int cur = 0;
-  for (int k0 = 0; k0 < pr.k; k0 += GK) {
-    const bool more = k0 + GK < pr.k;
-    if (more) fetch(k0 + GK);
-    const double *as = As[cur], *bs = Bs[cur];
+  for (int st = 0; st < G_STAGES - 1; ++st) {
+    if (st < nk) issue(st, st * GK);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<G_STAGES - 2>();
+    __syncthreads();  // slab kt has landed for every thread; everyone is done with the buffer refilled next
+    if (kt + G_STAGES - 1 < nk) issue((kt + G_STAGES - 1) % G_STAGES, (kt + G_STAGES - 1) * GK);
+    cp_async_commit();
+    const double *as = gsm + (kt % G_STAGES) * G_STAGE_DBL, *bs = as + GT * AS_LD;
 #pragma unroll
     for (int kk = 0; kk < GK; kk += 4) {
       double a[2], b[4];
@@ -100,9 +101,6 @@ __global__ void __launch_bounds__(256) k_grouped_gemm(const GemmProb *__restrict
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
-    if (more) stage(cur ^ 1);
-    __syncthreads();
-    cur ^= 1;
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -126,7 +124,12 @@ __global__ void __launch_bounds__(256) k_grouped_gemm(const GemmProb *__restrict
 void launch_grouped_gemm(const GemmProb *d_probs, const int32_t *d_tile_start, int32_t n_probs, int32_t n_tiles,
                          cudaStream_t st) {
   if (n_tiles <= 0) return;
-  k_grouped_gemm<<<n_tiles, 256, 0, st>>>(d_probs, d_tile_start, n_probs);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_grouped_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, int(G_SMEM));
+    attr_set = true;
+  }
+  k_grouped_gemm<<<n_tiles, 256, G_SMEM, st>>>(d_probs, d_tile_start, n_probs);
   launch_counter_add(1);
 }
 

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) k_wide_subtree_forward(SubtreeArgs a, int
   if (tid == 0 && T.rf_size > 0) bulk_load_start(blob, a.R + in.rf_base, uint32_t(T.rf_size) * 8u, bar);
   bool waited = T.rf_size <= 0;
   const int32_t zr = T.node_zl[T.n_nodes - 1];
-  for (int32_t c0 = 0; c0 < MW; c0 += MC) {
+  for (int32_t c0 = blockIdx.y * MC; c0 < MW; c0 += gridDim.y * MC) {  // this CTA's column chunks
     for (int l = tid; l < T.n_int; l += 256) {
       const int64_t d = subtree_dof(a, in, T.var_code[l]);
 #pragma unroll
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) k_wide_subtree_backward(SubtreeArgs a, in
   __syncthreads();
   if (tid == 0) bulk_load_start(blob, a.R + in.rb_base, uint32_t(T.rb_size) * 8u, bar);
   bool waited = false;
-  for (int32_t c0 = 0; c0 < MW; c0 += MC) {
+  for (int32_t c0 = blockIdx.y * MC; c0 < MW; c0 += gridDim.y * MC) {
     for (int l = tid; l < T.n_int; l += 256) {
       const int64_t d = subtree_dof(a, in, T.var_code[l]);
 #pragma unroll
@@ -268,17 +268,30 @@ void wide_set_smem_limit(size_t bytes) {
   cudaFuncSetAttribute(k_wide_subtree_backward<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
 }
 
+// Column chunks are dealt to gridDim.y CTAs per subtree: enough CTAs for ~4 waves of the machine (the chunk loop of one
+// CTA is serial), few enough that the factor blob a CTA stages is reused for several chunks when subtrees are many.
+static unsigned subtree_column_groups(int MC, int32_t MW, int32_t n_inst) {
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int chunks = (MW + MC - 1) / MC;
+  const int want = (4 * sms + n_inst - 1) / n_inst;
+  return unsigned(std::max(1, std::min(chunks, want)));
+}
+
 void launch_wide_subtree_forward(int MC, int32_t MW, const SubtreeArgs &a, int32_t n_inst, size_t smem_bytes, cudaStream_t st) {
   if (n_inst <= 0) return;
-  if (MC == 8) k_wide_subtree_forward<8><<<n_inst, 256, smem_bytes, st>>>(a, MW);
-  else k_wide_subtree_forward<4><<<n_inst, 256, smem_bytes, st>>>(a, MW);
+  const dim3 grid(unsigned(n_inst), subtree_column_groups(MC, MW, n_inst));
+  if (MC == 8) k_wide_subtree_forward<8><<<grid, 256, smem_bytes, st>>>(a, MW);
+  else k_wide_subtree_forward<4><<<grid, 256, smem_bytes, st>>>(a, MW);
   launch_counter_add(1);
 }
 
 void launch_wide_subtree_backward(int MC, int32_t MW, const SubtreeArgs &a, int32_t n_inst, size_t smem_bytes, cudaStream_t st) {
   if (n_inst <= 0) return;
-  if (MC == 8) k_wide_subtree_backward<8><<<n_inst, 256, smem_bytes, st>>>(a, MW);
-  else k_wide_subtree_backward<4><<<n_inst, 256, smem_bytes, st>>>(a, MW);
+  const dim3 grid(unsigned(n_inst), subtree_column_groups(MC, MW, n_inst));
+  if (MC == 8) k_wide_subtree_backward<8><<<grid, 256, smem_bytes, st>>>(a, MW);
+  else k_wide_subtree_backward<4><<<grid, 256, smem_bytes, st>>>(a, MW);
   launch_counter_add(1);
 }
 
@@ -316,100 +329,112 @@ void launch_wide_f2c(int64_t n_rows, const int64_t *rp, const int64_t *col, cons
 // =================================================================================================================
 constexpr int TA_LD = 16 + 4;
 constexpr int TB_LD = TOEP_BN + 4;
+constexpr int T_STAGES = 4;
 
+template <int BM>
+struct ToepCfg {
+  static constexpr int WM = BM / 16;            // warps along the rows, 16 rows each
+  static constexpr int WN = 8 / WM;             // warps along the slabs
+  static constexpr int NJ = TOEP_BN / WN / 8;   // 8-slab blocks per warp
+  static constexpr int A_PER = BM * 16 / 256;   // staged A elements per thread and k slab
+  static constexpr int STAGE_DBL = BM * TA_LD + 16 * TB_LD;
+  static constexpr size_t SMEM = size_t(T_STAGES) * STAGE_DBL * sizeof(double);
+};
+
+// BM = 128, 64 or 32 operator rows per tile: large tiles re-read q less often (the large problems are bound by the
+// HBM stream of T), small tiles give the small problems enough CTAs to fill the machine.
+template <int BM>
 __global__ void __launch_bounds__(256) k_toeplitz_apply(const ToepProb *__restrict__ probs,
                                                         const ToepTile *__restrict__ tiles,
                                                         const double *__restrict__ q, double *__restrict__ out) {
-  __shared__ double As[2][TOEP_BM * TA_LD];
-  __shared__ double Bs[2][16 * TB_LD];
+  using C = ToepCfg<BM>;
+  extern __shared__ __align__(16) double tsm[];
   const ToepTile tl = tiles[blockIdx.x];
   const ToepProb pr = probs[tl.prob];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 1, wn = warp & 1;  // 4 x 2 warps: 16 rows x 16 slabs each
-  double acc[2][2][2];
+  const int wm = warp / C::WN, wn = warp % C::WN;
+  double acc[2][C::NJ][2];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < C::NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   const int slab_hi = min(pr.m_t, tl.slab0 + TOEP_BN) - 1;  // last slab of this tile: delays d = 0 .. slab_hi
-  // position in the k space
+  int per_d = 0;
+  for (int s = 0; s < pr.n_in; ++s) per_d += (pr.P_in[s] + 15) >> 4;
+  const int nk = (slab_hi + 1) * per_d;
+  // position of the NEXT k slab to be issued
   int d = 0, s = 0, a0 = 0;
-  double ra[4], rb[2];
-  auto fetch = [&]() {
+  auto issue = [&](int stage) {
+    double *as = tsm + stage * C::STAGE_DBL, *bs = as + BM * TA_LD;
     const int P = pr.P_in[s];
     const double *Td = pr.T + int64_t(d) * pr.d_stride + int64_t(pr.row_base + tl.row0) * pr.ldt + pr.col_base[s] + a0;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < C::A_PER; ++r) {
       const int e = tid + 256 * r, i = e >> 4, kk = e & 15;
-      ra[r] = (tl.row0 + i < pr.P_out && a0 + kk < P) ? __ldg(Td + int64_t(i) * pr.ldt + kk) : 0.0;
+      const bool ok = tl.row0 + i < pr.P_out && a0 + kk < P;
+      cp_async8(as + i * TA_LD + kk, ok ? Td + int64_t(i) * pr.ldt + kk : pr.T, ok);
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int e = tid + 256 * r, n = e >> 4, kk = e & 15;
       const int I = tl.slab0 + n, J = I - d;
-      rb[r] = (I < pr.m_t && J >= 0 && a0 + kk < P) ? __ldg(q + pr.in_off[s] + int64_t(J) * P + a0 + kk) : 0.0;
+      const bool ok = I < pr.m_t && J >= 0 && a0 + kk < P;
+      cp_async8(bs + kk * TB_LD + n, ok ? q + pr.in_off[s] + int64_t(J) * P + a0 + kk : q, ok);
     }
-  };
-  auto stage = [&](int buf) {
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int e = tid + 256 * r;
-      As[buf][(e >> 4) * TA_LD + (e & 15)] = ra[r];
-    }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int e = tid + 256 * r;
-      Bs[buf][(e & 15) * TB_LD + (e >> 4)] = rb[r];
-    }
-  };
-  auto advance = [&]() {  // next k slab; false when the k space is exhausted
     a0 += 16;
-    if (a0 >= pr.P_in[s]) { a0 = 0; ++s; }
+    if (a0 >= P) { a0 = 0; ++s; }
     if (s >= pr.n_in) { s = 0; ++d; }
-    return d <= slab_hi;
   };
-  fetch();
-  stage(0);
-  __syncthreads();
-  int cur = 0;
-  bool more = true;
-  while (more) {
-    more = advance();
-    if (more) fetch();
-    const double *as = As[cur], *bs = Bs[cur];
+#pragma unroll
+  for (int st = 0; st < T_STAGES - 1; ++st) {
+    if (st < nk) issue(st);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<T_STAGES - 2>();
+    __syncthreads();
+    if (kt + T_STAGES - 1 < nk) issue((kt + T_STAGES - 1) % T_STAGES);
+    cp_async_commit();
+    const double *as = tsm + (kt % T_STAGES) * C::STAGE_DBL, *bs = as + BM * TA_LD;
 #pragma unroll
     for (int kk = 0; kk < 16; kk += 4) {
-      double av[2], bv[2];
+      double av[2], bv[C::NJ];
 #pragma unroll
       for (int i = 0; i < 2; ++i) av[i] = as[(wm * 16 + i * 8 + (lane >> 2)) * TA_LD + kk + (lane & 3)];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) bv[j] = bs[(kk + (lane & 3)) * TB_LD + wn * 16 + j * 8 + (lane >> 2)];
+      for (int j = 0; j < C::NJ; ++j) bv[j] = bs[(kk + (lane & 3)) * TB_LD + (wn * C::NJ + j) * 8 + (lane >> 2)];
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 2; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+        for (int j = 0; j < C::NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
     }
-    if (more) stage(cur ^ 1);
-    __syncthreads();
-    cur ^= 1;
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < C::NJ; ++j) {
       const int row = tl.row0 + wm * 16 + i * 8 + (lane >> 2);
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const int I = tl.slab0 + wn * 16 + j * 8 + (lane & 3) * 2 + t;
+        const int I = tl.slab0 + (wn * C::NJ + j) * 8 + (lane & 3) * 2 + t;
         if (row < pr.P_out && I < pr.m_t) out[pr.out_off + int64_t(I) * pr.P_out + row] = acc[i][j][t];
       }
     }
 }
 
-void launch_toeplitz_apply(const ToepProb *probs, const ToepTile *tiles, int32_t n_tiles, const double *q, double *out,
-                           cudaStream_t st) {
+void launch_toeplitz_apply(int bm, const ToepProb *probs, const ToepTile *tiles, int32_t n_tiles, const double *q,
+                           double *out, cudaStream_t st) {
   if (n_tiles <= 0) return;
-  k_toeplitz_apply<<<n_tiles, 256, 0, st>>>(probs, tiles, q, out);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_toeplitz_apply<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ToepCfg<128>::SMEM));
+    cudaFuncSetAttribute(k_toeplitz_apply<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ToepCfg<64>::SMEM));
+    cudaFuncSetAttribute(k_toeplitz_apply<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ToepCfg<32>::SMEM));
+    attr_set = true;
+  }
+  if (bm == 128) k_toeplitz_apply<128><<<n_tiles, 256, ToepCfg<128>::SMEM, st>>>(probs, tiles, q, out);
+  else if (bm == 64) k_toeplitz_apply<64><<<n_tiles, 256, ToepCfg<64>::SMEM, st>>>(probs, tiles, q, out);
+  else k_toeplitz_apply<32><<<n_tiles, 256, ToepCfg<32>::SMEM, st>>>(probs, tiles, q, out);
   launch_counter_add(1);
 }
 

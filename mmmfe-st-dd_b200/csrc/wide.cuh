@@ -67,9 +67,8 @@ struct ToepProb {
 struct ToepTile {
   int32_t prob, row0, slab0;
 };
-constexpr int TOEP_BM = 64;  // rows (a') per tile
-constexpr int TOEP_BN = 32;  // mortar time slabs per tile
-void launch_toeplitz_apply(const ToepProb *probs, const ToepTile *tiles, int32_t n_tiles, const double *q, double *out,
-                           cudaStream_t st);
+constexpr int TOEP_BN = 32;  // mortar time slabs per tile; rows per tile: 128, 64 or 32 (chosen by the caller)
+void launch_toeplitz_apply(int rows_per_tile, const ToepProb *probs, const ToepTile *tiles, int32_t n_tiles,
+                           const double *q, double *out, cudaStream_t st);
 
 }  // namespace mmmfe

