@@ -158,6 +158,27 @@ def cpu_iteration_seconds(fine, coarse, n_sub, n_solves):
                                fine_dofs=nf_, coarse_dofs=nc_)
 
 
+def init_distributed(pkg, rank, world, local_rank):
+    """torch.distributed (NCCL) for the barriers/reductions of the harness, and the NCCL unique id of the engine's own
+    communicator (rank 0 creates it, broadcast through torch).  Returns the id bytes, None on one rank."""
+    if world <= 1:
+        return None
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng_lib = pkg.load_engine()
+    n = eng_lib.mmmfe_comm_unique_id_size()
+    buf = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        raw = ctypes.create_string_buffer(n)
+        assert eng_lib.mmmfe_comm_unique_id(ctypes.cast(raw, ctypes.c_void_p)) == 0
+        buf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -213,20 +234,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
-    nccl_id = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        eng_lib = pkg.load_engine()
-        n = eng_lib.mmmfe_comm_unique_id_size()
-        buf = torch.zeros(n, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            import ctypes
-            raw = ctypes.create_string_buffer(n)
-            assert eng_lib.mmmfe_comm_unique_id(ctypes.cast(raw, ctypes.c_void_p)) == 0
-            buf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
-        dist.broadcast(buf, 0)
-        nccl_id = bytes(buf.cpu().numpy().tobytes())
+    nccl_id = init_distributed(pkg, rank, world, local_rank)
 
     tmp = tempfile.mkdtemp(prefix="mmmfe_bench_")
     pfile = pkg.write_parameter_file(os.path.join(tmp, "parameter.txt"), mesh, mortar, mortar_degree=k, num_refinement=1)

@@ -64,7 +64,9 @@ typedef struct {
    * sampling operators:
    *   f2c[s] : (mortar_len[s]) x (n_side[s]*nt)  fine 2-D flux trace U[level*n_side+i] -> mortar coefficients
    *   c2f[s] : (n_side[s]*nt) x (mortar_len[s])  mortar coefficients -> lam_bar = (2-D interface dof)/|e|
-   * mortar_len[s] = interface_dofs[s].size() (src/darcy_vtdd.cc:524-541).                                 */
+   * mortar_len[s] = interface_dofs[s].size() (src/darcy_vtdd.cc:524-541).
+   * Sides WITHOUT a neighbour may also carry n_side, side_dofs, mortar_len and both tables (else leave them zero):
+   * they are never applied to this subdomain, they let ranks share the multiscale-basis work of a factor group.  */
   int32_t mortar_len[4];
   mmmfe_csr f2c[4];
   mmmfe_csr c2f[4];
@@ -95,7 +97,9 @@ const char *mmmfe_version(void);
  * lower-triangular Toeplitz product per subdomain -- the same operator to round-off; 2 (default) = 1 when the
  * projector tables are slab structured and a factor group has at most "basis_auto_columns" (default 1024) basis
  * columns, else 0.  "mortar_time_slabs" = time steps of the mortar mesh (mesh_pattern_mortar nt; required for 1/2),
- * "basis_columns" = columns solved per pass (default 256).                                                       */
+ * "basis_columns" = columns solved per pass (default 256), "basis_share" (default 1: with several ranks, a factor
+ * group that every rank holds is solved for once, each rank taking a block of its columns; needs the projector tables
+ * of all four sides, see mmmfe_subdomain).                                                                        */
 int mmmfe_set_option(mmmfe_ctx *ctx, const char *key, double value);
 
 /* ---- multi-GPU: one process per GPU, subdomains sharded over ranks ------------------------------------------ */

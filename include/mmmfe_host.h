@@ -55,7 +55,7 @@ typedef struct {
   int64_t tune_us_sweep, tune_us_levels, sweep_planned;
   int64_t tune_rel_diff_e18; /* set-up cross-check: relative l2 difference of the two sweep implementations * 1e18, -1 = not run */
   /* multiscale-basis (time-Toeplitz) interface operator: 1 when GMRES ran on it, its precompute cost                */
-  int32_t basis_operator, basis_pad;
+  int32_t basis_operator, basis_shared_by; /* ranks that split the basis columns of a group among themselves */
   double t_basis, basis_gflop, basis_bytes;
   int64_t basis_columns;
   /* converged solve after the fixed-iteration timing (also_solve)                                                     */

@@ -425,7 +425,7 @@ class HostReport(ctypes.Structure):
                 ("sweep_steps", ctypes.c_int32 * 4), ("sweep_ms", ctypes.c_double * 4),
                 ("sweep_bytes_per_step", ctypes.c_double * 4), ("tune_us_sweep", ctypes.c_int64),
                 ("tune_us_levels", ctypes.c_int64), ("sweep_planned", ctypes.c_int64),
-                ("tune_rel_diff_e18", ctypes.c_int64), ("basis_operator", ctypes.c_int32), ("basis_pad", ctypes.c_int32),
+                ("tune_rel_diff_e18", ctypes.c_int64), ("basis_operator", ctypes.c_int32), ("basis_shared_by", ctypes.c_int32),
                 ("t_basis", ctypes.c_double), ("basis_gflop", ctypes.c_double), ("basis_bytes", ctypes.c_double),
                 ("basis_columns", ctypes.c_int64), ("solve_iterations", ctypes.c_int32),
                 ("solve_converged", ctypes.c_int32), ("t_solve_gmres", ctypes.c_double),

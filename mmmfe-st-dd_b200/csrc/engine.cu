@@ -102,6 +102,8 @@ struct Basis {
   int32_t P[4] = {0, 0, 0, 0}, n_side[4] = {0, 0, 0, 0}, base[4] = {0, 0, 0, 0}, tr_base[4] = {0, 0, 0, 0};
   int32_t rep[4] = {-1, -1, -1, -1};  // local subdomain whose tables represent the slot
   int32_t P_tot = 0, n_tr = 0, MW = 0, n_pass = 0, MC = 8;
+  int32_t col_lo = 0, col_hi = 0;  // the columns THIS rank solves for (all of them unless the ranks share the group)
+  int32_t shared_by = 1;           // ranks that share the work of this group
   int64_t ldt = 0;
   DevBuf<double> T;
   double seconds = 0.0, flops = 0.0, bytes = 0.0;
@@ -249,11 +251,13 @@ struct mmmfe_ctx {
   // time-Toeplitz operator precomputed at set-up, 2 = basis when the structure allows it and it has at most
   // basis_auto_columns columns per factor group, sweeps otherwise
   int operator_mode = 2, mortar_slabs = 0, basis_cols_max = 256, basis_auto_columns = 1024;
+  bool basis_share = true;  // several ranks: split the columns of a group every rank holds among the ranks
   bool use_basis = false;
   std::string basis_note;  // why the basis operator is not in use
   DevBuf<ToepProb> toep_probs;
   DevBuf<ToepTile> toep_tiles;
-  int32_t n_toep_tiles = 0, toep_bm = 64;
+  int32_t n_toep_tiles = 0, toep_bm = 64, toep_parts = 1;
+  DevBuf<double> toep_part_buf;
   double basis_seconds = 0.0, basis_flops = 0.0, basis_bytes = 0.0, toep_flops = 0.0, toep_bytes = 0.0;
   int64_t basis_columns = 0;
   // temporaries of the factorisation
@@ -921,7 +925,12 @@ static void exchange_and_combine(mmmfe_ctx *c, double sign, double *out, bool se
 // Ap = S q for q resident in d_q (src/darcy_vtdd.cc:1316-1411)
 static void apply_operator(mmmfe_ctx *c, const double *d_q, double *d_ap) {
   if (c->use_basis) {  // send = (signed f2c . star sweeps . c2f) q as one block-Toeplitz product per subdomain
-    launch_toeplitz_apply(c->toep_bm, c->toep_probs.p, c->toep_tiles.p, c->n_toep_tiles, d_q, c->send.p, c->stream);
+    if (c->toep_parts <= 1) {
+      launch_toeplitz_apply(c->toep_bm, c->toep_probs.p, c->toep_tiles.p, c->n_toep_tiles, d_q, c->send.p, 0, c->stream);
+    } else {  // split over the delays: partial sums, added in fixed order
+      launch_toeplitz_apply(c->toep_bm, c->toep_probs.p, c->toep_tiles.p, c->n_toep_tiles, d_q, c->toep_part_buf.p, c->n_iface, c->stream);
+      launch_sum_parts(c->n_iface, c->toep_part_buf.p, c->n_iface, c->toep_parts, c->send.p, c->stream);
+    }
     exchange_and_combine(c, -1.0, d_ap, true);
     return;
   }
@@ -989,35 +998,42 @@ static bool same_csr(const HostCsr &a, const HostCsr &b) {
 }
 
 // Slots, sizes and eligibility of the basis of one factor group; no device work.
-static std::unique_ptr<Basis> plan_basis(mmmfe_ctx *c, const std::vector<int32_t> &members, std::string &why) {
+static bool has_tables(const Sub &sd, int side) { return !sd.f2c[side].rp.empty() && !sd.c2f[side].rp.empty(); }
+
+// Slots, sizes and eligibility of the basis of one factor group for the sides in `mask`; no device work.  The tables of
+// a side are taken from any member that carries them (the front-end passes the tables of all four sides, so that ranks
+// can share the work of a group whose members have different interface sides on different ranks).
+static std::unique_ptr<Basis> plan_basis(mmmfe_ctx *c, const std::vector<int32_t> &members, int mask, std::string &why) {
   auto B = std::make_unique<Basis>();
   const int m_t = c->mortar_slabs;
   if (m_t < 1) { why = "option mortar_time_slabs is not set"; return nullptr; }
   const Sub &first = *c->subs[members[0]];
   if (first.nt % m_t != 0) { why = "the mortar time mesh does not divide the subdomain's time steps"; return nullptr; }
   B->m_t = m_t; B->nt = first.nt; B->lvl_per_slab = first.nt / m_t;
-  for (int32_t li : members) {
-    const Sub &sd = *c->subs[li];
-    for (int sd_side = 0; sd_side < 4; ++sd_side) {
-      if (sd.neighbor[sd_side] < 0) continue;
-      if (sd.mortar_len[sd_side] % m_t != 0) { why = "mortar_len is not a multiple of the number of mortar time slabs"; return nullptr; }
-      int &slot = B->slot_of_side[sd_side];
+  for (int side = 0; side < 4; ++side) {
+    if (!(mask & (1 << side))) continue;
+    int slot = -1;
+    for (int32_t li : members) {
+      const Sub &sd = *c->subs[li];
+      if (!has_tables(sd, side)) continue;
+      if (sd.mortar_len[side] % m_t != 0) { why = "mortar_len is not a multiple of the number of mortar time slabs"; return nullptr; }
       if (slot < 0) {
         slot = B->n_slots++;
-        B->side_of_slot[slot] = sd_side;
-        B->P[slot] = sd.mortar_len[sd_side] / m_t;
-        B->n_side[slot] = sd.n_side[sd_side];
+        B->slot_of_side[side] = slot;
+        B->side_of_slot[slot] = side;
+        B->P[slot] = sd.mortar_len[side] / m_t;
+        B->n_side[slot] = sd.n_side[side];
         B->rep[slot] = li;
-        if (!slab_structured(sd.c2f[sd_side], sd.f2c[sd_side], sd.n_side[sd_side], sd.nt, m_t, B->P[slot], why)) return nullptr;
+        if (!slab_structured(sd.c2f[side], sd.f2c[side], sd.n_side[side], sd.nt, m_t, B->P[slot], why)) return nullptr;
       } else {
         const Sub &rp = *c->subs[B->rep[slot]];
-        if (!same_csr(rp.c2f[sd_side], sd.c2f[sd_side]) || !same_csr(rp.f2c[sd_side], sd.f2c[sd_side]) ||
-            rp.side_dofs[sd_side] != sd.side_dofs[sd_side]) {
+        if (!same_csr(rp.c2f[side], sd.c2f[side]) || !same_csr(rp.f2c[side], sd.f2c[side]) || rp.side_dofs[side] != sd.side_dofs[side]) {
           why = "subdomains that share a factor have different projector tables on the same side";
           return nullptr;
         }
       }
     }
+    if (slot < 0) { why = "no projector tables for a side the multiscale basis needs"; return nullptr; }
   }
   if (B->n_slots == 0) { why = "no interface side"; return nullptr; }
   for (int k = 0; k < B->n_slots; ++k) {
@@ -1025,6 +1041,7 @@ static std::unique_ptr<Basis> plan_basis(mmmfe_ctx *c, const std::vector<int32_t
     B->tr_base[k] = B->n_tr; B->n_tr += B->n_side[k];
   }
   B->ldt = (int64_t(B->P_tot) + 7) & ~int64_t(7);
+  B->col_lo = 0; B->col_hi = B->P_tot;
   return B;
 }
 
@@ -1044,23 +1061,34 @@ static void compute_basis(mmmfe_ctx *c, Factor &F, Basis &B) {
   int cap = std::max(8, c->basis_cols_max & ~7);
   while (cap > 8 && per_col * cap > 0.6 * (double(free_b) - t_bytes)) cap -= 8;
   if (per_col * cap + t_bytes > 0.9 * double(free_b)) fail(MMMFE_E_CUDA, "not enough device memory for the multiscale basis (%.1f GB needed)", (per_col * cap + t_bytes) / 1e9);
-  B.n_pass = (B.P_tot + cap - 1) / cap;
-  B.MW = (((B.P_tot + B.n_pass - 1) / B.n_pass) + 7) & ~7;
+  const int n_local = B.col_hi - B.col_lo;  // this rank's share of the columns
+  B.T.alloc(size_t(B.m_t) * B.P_tot * B.ldt);
+  B.T.zero(st);
+  if (n_local <= 0) { B.n_pass = 0; B.MW = 8; CUDA_CHECK(cudaStreamSynchronize(st)); return; }
+  B.n_pass = (n_local + cap - 1) / cap;
+  B.MW = (((n_local + B.n_pass - 1) / B.n_pass) + 7) & ~7;
   const int MW = B.MW;
-  // ---- subtree kernels: 8 columns per chunk when the vectors fit beside the factor blob, else 4 ----
+  // ---- subtree kernels: column chunks as wide as the shared memory allows next to the factor blob, preferring two
+  // resident CTAs per SM (the level walk is latency-bound: a wider chunk costs almost the same as a narrow one) ----
   const size_t smem_limit = subtree_smem_limit();
   wide_set_smem_limit(smem_limit);
   size_t smem_f = 0, smem_b = 0;
-  for (int MC : {8, 4}) {
+  auto smem_for = [&](int MC) {
     smem_f = smem_b = 0;
     for (const auto &T : tr.templates) {
       smem_f = std::max(smem_f, 16 + 8 * (size_t(T.rf_size) + (size_t(T.zl_size) + size_t(T.n_int)) * MC));
       smem_b = std::max(smem_b, 16 + 8 * (size_t(T.rb_size) + size_t(2 * T.n_int + T.n_rootb) * MC));
     }
+    return std::max(smem_f, smem_b);
+  };
+  B.MC = 8;
+  for (int MC : {32, 16, 8}) {
+    const size_t need = smem_for(MC);
+    if (MC > 8 && need > (smem_limit - 2048) / 2) continue;  // two CTAs per SM (1 KB reserved per block)
     B.MC = MC;
-    if (smem_f <= smem_limit && smem_b <= smem_limit) break;
+    break;
   }
-  if (smem_f > smem_limit || smem_b > smem_limit) fail(MMMFE_E_UNSUPPORTED, "subtree factor blobs do not fit the multi-column kernels");
+  if (smem_for(B.MC) > smem_limit) fail(MMMFE_E_UNSUPPORTED, "subtree factor blobs do not fit the multi-column kernels");
   // ---- host tables ----
   // interface data of the first slab: x[dof][column] += -sign * c2f(level, i; a), CSR by (pass, level)
   std::vector<int64_t> add_rp(size_t(B.n_pass) * (r + 1) + 1, 0);
@@ -1078,8 +1106,8 @@ static void compute_basis(mmmfe_ctx *c, Factor &F, Basis &B) {
         for (int64_t i = 0; i < ns; ++i) {
           const int64_t row = int64_t(lvl) * ns + i;
           for (int64_t e = t.rp[row]; e < t.rp[row + 1]; ++e) {
-            const int col = B.base[k] + t.col[e];  // first slab: t.col[e] < P (slab_structured)
-            if (col / MW != pass) continue;
+            const int col = B.base[k] + t.col[e] - B.col_lo;  // first slab: t.col[e] < P (slab_structured)
+            if (col < 0 || col >= n_local || col / MW != pass) continue;
             add_row.push_back(sd.side_dofs[side][size_t(i)]);
             add_col.push_back(col % MW);
             add_val.push_back(-kNormalSign[side] * t.val[e]);  // rhs_i = -s * lam_bar, src/darcy_vtdd.cc:840-844
@@ -1122,8 +1150,6 @@ static void compute_basis(mmmfe_ctx *c, Factor &F, Basis &B) {
   trace.alloc(size_t(nt) * B.n_tr * MW);
   state.alloc(2);
   z.zero(st);
-  B.T.alloc(size_t(B.m_t) * B.P_tot * B.ldt);
-  B.T.zero(st);
   std::vector<std::unique_ptr<Lvl>> lvls;
   const int tiles_n = (MW + 63) / 64;
   for (const auto &level : tr.top_by_height) {
@@ -1244,9 +1270,9 @@ static void compute_basis(mmmfe_ctx *c, Factor &F, Basis &B) {
       if (ge) { CUDA_CHECK(cudaGraphLaunch(ge, st)); launch_counter_add(B.graph_kernels); }
       else enqueue_step();
     }
-    const int n_cols = std::min(MW, B.P_tot - pass * MW);
+    const int n_cols = std::min(MW, n_local - pass * MW);
     launch_wide_f2c(int64_t(f_trow.size()), d_frp.p, d_fcol.p, d_fval.p, trace.p, MW, n_cols, B.T.p, B.ldt, d_ftrow.p,
-                    int64_t(pass) * MW, st);
+                    int64_t(B.col_lo) + int64_t(pass) * MW, st);
   }
   CUDA_CHECK(cudaStreamSynchronize(st));
   CUDA_CHECK(cudaGetLastError());
@@ -1258,38 +1284,167 @@ static void compute_basis(mmmfe_ctx *c, Factor &F, Basis &B) {
   B.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
 }
 
+static uint64_t mix64(uint64_t h, uint64_t x) {
+  h ^= x + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+  h = (h ^ (h >> 30)) * 0xbf58476d1ce4e5b9ull;
+  return h ^ (h >> 27);
+}
+template <class T>
+static uint64_t hash_vec(uint64_t h, const std::vector<T> &v) {
+  h = mix64(h, v.size());
+  for (const T &e : v) {
+    uint64_t bits = 0;
+    std::memcpy(&bits, &e, sizeof(T) < 8 ? sizeof(T) : 8);
+    h = mix64(h, bits);
+  }
+  return h;
+}
+// identifies a factor group across ranks: same matrix, numbering, time steps and projector tables of every side
+static uint64_t group_signature(const mmmfe_ctx *c, const std::vector<int32_t> &members) {
+  const Sub &sd = *c->subs[members[0]];
+  uint64_t h = 0x1234567ull;
+  for (int v : {sd.nx, sd.ny, sd.nt, sd.nf, sd.np, c->mortar_slabs}) h = mix64(h, uint64_t(v));
+  uint64_t bits;
+  std::memcpy(&bits, &sd.dt, 8);
+  h = mix64(h, bits);
+  h = hash_vec(h, sd.matrix.rp); h = hash_vec(h, sd.matrix.col); h = hash_vec(h, sd.matrix.val); h = hash_vec(h, sd.canon);
+  for (int side = 0; side < 4; ++side)
+    for (int32_t li : members) {
+      const Sub &m = *c->subs[li];
+      if (!has_tables(m, side)) continue;
+      h = mix64(h, uint64_t(side));
+      h = hash_vec(h, m.c2f[side].col); h = hash_vec(h, m.c2f[side].val);
+      h = hash_vec(h, m.f2c[side].col); h = hash_vec(h, m.f2c[side].val); h = hash_vec(h, m.side_dofs[side]);
+      break;
+    }
+  return h;
+}
+
 // Decides whether the interface operator runs on the multiscale basis, computes the bases and the tile list of the
-// block-Toeplitz kernel.  Collective in the sense that every rank decides from its own subdomains; ranks may differ
-// (the operator is the same operator either way, to round-off).
+// block-Toeplitz kernel.  With several ranks the groups are matched by signature: when EVERY rank holds a group of a
+// signature and has the tables of all the sides any of them needs, the ranks split that group's columns among
+// themselves and sum the (disjoint) results with one all-reduce -- a checkerboard over 8 GPUs solves for an eighth of
+// the columns per GPU.  All ranks take the same decisions from the same exchanged data.
 static void setup_basis_operator(mmmfe_ctx *c, const std::vector<int> &group_of) {
   c->use_basis = false;
   c->basis_note.clear();
   if (c->operator_mode == 0) { c->basis_note = "operator = 0"; return; }
   const int ns = int(c->subs.size());
-  std::vector<std::unique_ptr<Basis>> plans(c->factors.size());
-  for (size_t g = 0; g < c->factors.size(); ++g) {
-    std::vector<int32_t> members;
-    for (int i = 0; i < ns; ++i) if (group_of[i] == int(g)) members.push_back(i);
-    std::string why;
-    plans[g] = plan_basis(c, members, why);
-    if (!plans[g]) {
-      c->basis_note = why;
-      if (c->operator_mode == 1) fail(MMMFE_E_UNSUPPORTED, "operator = 1 (multiscale basis) is not possible here: %s", why.c_str());
-      return;
+  const int ng = int(c->factors.size());
+  std::vector<std::vector<int32_t>> members(ng);
+  for (int i = 0; i < ns; ++i) members[group_of[i]].push_back(i);
+  std::vector<int> mask(ng, 0);
+  for (int g = 0; g < ng; ++g)
+    for (int32_t li : members[g])
+      for (int side = 0; side < 4; ++side)
+        if (c->subs[li]->neighbor[side] >= 0) mask[g] |= 1 << side;
+  std::vector<int> share_ranks(ng, 1), share_index(ng, 0);
+  // ---- match groups across ranks ----
+  constexpr int MAXG = 8, REC = 6;
+  const bool try_share = c->world > 1 && c->basis_share && ng <= MAXG;
+  std::vector<double> info;
+  if (c->world > 1) {
+    // every rank takes part in this exchange whatever its options are (the record says whether it can share)
+    info.assign(size_t(c->world) * MAXG * REC, 0.0);
+    for (int g = 0; g < ng && g < MAXG; ++g) {
+      std::string why;
+      const bool own_ok = plan_basis(c, members[g], mask[g], why) != nullptr;
+      bool all_tables = true;
+      for (int side = 0; side < 4; ++side) {
+        bool any = false;
+        for (int32_t li : members[g]) any |= has_tables(*c->subs[li], side);
+        all_tables &= any;
+      }
+      const uint64_t sig = group_signature(c, members[g]);
+      double *rec = &info[(size_t(c->rank) * MAXG + g) * REC];
+      rec[0] = 1.0; rec[1] = double(sig & 0xffffffffull); rec[2] = double(sig >> 32); rec[3] = double(mask[g]);
+      rec[4] = (try_share && own_ok && all_tables) ? 1.0 : 0.0;
     }
-    if (c->operator_mode == 2 && plans[g]->P_tot > c->basis_auto_columns) {
-      c->basis_note = "more basis columns per factor group than basis_auto_columns";
-      return;
+    DevBuf<double> d;
+    d.upload(info);
+    allreduce_sum(c, d.p, info.size());
+    CUDA_CHECK(cudaMemcpyAsync(info.data(), d.p, info.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (int g = 0; g < ng && g < MAXG; ++g) {
+      const double *mine = &info[(size_t(c->rank) * MAXG + g) * REC];
+      int holders = 0, can = 0, uni = 0, before = 0;
+      for (int rk = 0; rk < c->world; ++rk)
+        for (int k = 0; k < MAXG; ++k) {
+          const double *rec = &info[(size_t(rk) * MAXG + k) * REC];
+          if (rec[0] != 1.0 || rec[1] != mine[1] || rec[2] != mine[2]) continue;
+          ++holders; can += rec[4] == 1.0; uni |= int(rec[3]);
+          if (rk < c->rank) ++before;
+          break;  // one group per signature and rank
+        }
+      if (holders == c->world && can == c->world) {  // every rank holds it and can share
+        share_ranks[g] = c->world; share_index[g] = before; mask[g] = uni;
+      }
     }
   }
-  for (size_t g = 0; g < c->factors.size(); ++g) {
+  // ---- plans (identical on the ranks that share a group) ----
+  std::vector<std::unique_ptr<Basis>> plans(ng);
+  for (int g = 0; g < ng; ++g) {
+    std::string why;
+    plans[g] = plan_basis(c, members[g], mask[g], why);
+    if (!plans[g]) { c->basis_note = why; break; }
+    if (c->operator_mode == 2 && plans[g]->P_tot > c->basis_auto_columns) {
+      c->basis_note = "more basis columns per factor group than basis_auto_columns";
+      plans[g].reset();
+      break;
+    }
+    Basis &B = *plans[g];
+    B.shared_by = share_ranks[g];
+    if (B.shared_by > 1) {  // contiguous column blocks, multiples of 8 columns
+      const int64_t blocks = (B.P_tot + 7) / 8;
+      B.col_lo = int32_t(std::min<int64_t>(B.P_tot, 8 * (blocks * share_index[g] / B.shared_by)));
+      B.col_hi = int32_t(std::min<int64_t>(B.P_tot, 8 * (blocks * (share_index[g] + 1) / B.shared_by)));
+    }
+  }
+  bool all = true;
+  for (int g = 0; g < ng; ++g) all &= plans[g] != nullptr;
+  // One operator for the whole run: the basis is used only when EVERY rank can use it (also keeps the collectives of
+  // the shared groups matched).
+  if (c->world > 1) {
+    DevBuf<double> flag;
+    const double mine = all ? 1.0 : 0.0;
+    flag.upload(&mine, 1);
+    allreduce_sum(c, flag.p, 1);
+    double sum = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&sum, flag.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (all && sum != double(c->world)) { all = false; c->basis_note = "another rank cannot use the multiscale basis"; }
+  }
+  if (!all) {
+    if (c->operator_mode == 1) fail(MMMFE_E_UNSUPPORTED, "operator = 1 (multiscale basis) is not possible here: %s", c->basis_note.c_str());
+    return;
+  }
+  for (int g = 0; g < ng; ++g) {
     Factor &F = *c->factors[g];
     F.basis = std::move(plans[g]);
     compute_basis(c, F, *F.basis);
     c->basis_seconds += F.basis->seconds;
     c->basis_flops += F.basis->flops;
     c->basis_bytes += F.basis->bytes;
-    c->basis_columns += F.basis->P_tot;
+    c->basis_columns += F.basis->col_hi - F.basis->col_lo;
+  }
+  // shared groups: the ranks hold disjoint column blocks (zeros elsewhere); groups in the order of their signature
+  {
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::pair<std::pair<double, double>, int>> order;
+    for (int g = 0; g < ng && g < MAXG; ++g)
+      if (share_ranks[g] > 1) {
+        const double *mine = &info[(size_t(c->rank) * MAXG + g) * REC];
+        order.push_back({{mine[2], mine[1]}, g});
+      }
+    std::sort(order.begin(), order.end());
+    for (const auto &o : order) {
+      Basis &B = *c->factors[o.second]->basis;
+      allreduce_sum(c, B.T.p, B.T.n);
+    }
+    if (!order.empty()) {
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      c->basis_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
   }
   std::vector<ToepProb> probs;
   std::vector<ToepTile> tiles;
@@ -1316,19 +1471,33 @@ static void setup_basis_operator(mmmfe_ctx *c, const std::vector<int> &group_of)
       probs.push_back(pr);
     }
   }
-  // rows per tile: the largest of 128 / 64 / 32 that still yields two tiles per SM
+  // rows per tile: large tiles re-read q less often, small problems need small tiles to yield enough CTAs; the delay
+  // range of every slab tile is then cut into parts (split-k) until the machine is filled about four times
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-  for (int bm : {128, 64, 32}) {
-    tiles.clear();
-    for (size_t p = 0; p < probs.size(); ++p)
-      for (int row0 = 0; row0 < probs[p].P_out; row0 += bm)
-        for (int slab0 = 0; slab0 < probs[p].m_t; slab0 += TOEP_BN) tiles.push_back({int32_t(p), row0, slab0});
-    c->toep_bm = bm;
-    if (int(tiles.size()) >= 2 * sms) break;
-  }
-  // heavy tiles (late slabs: long delay sums) first
-  std::stable_sort(tiles.begin(), tiles.end(), [](const ToepTile &a, const ToepTile &b) { return a.slab0 > b.slab0; });
+  auto base_tiles = [&](int bm) {
+    int64_t n = 0;
+    for (const ToepProb &pr : probs) n += int64_t((pr.P_out + bm - 1) / bm) * ((pr.m_t + TOEP_BN - 1) / TOEP_BN);
+    return n;
+  };
+  c->toep_bm = base_tiles(128) >= 96 ? 128 : (base_tiles(64) >= 48 ? 64 : 32);
+  const int64_t n_base = std::max<int64_t>(1, base_tiles(c->toep_bm));
+  c->toep_parts = int(std::min<int64_t>(16, std::max<int64_t>(1, (4 * sms + n_base - 1) / n_base)));
+  int max_part = 0;
+  for (size_t p = 0; p < probs.size(); ++p)
+    for (int row0 = 0; row0 < probs[p].P_out; row0 += c->toep_bm)
+      for (int slab0 = 0; slab0 < probs[p].m_t; slab0 += TOEP_BN) {
+        const int nd = std::min(probs[p].m_t, slab0 + TOEP_BN);  // delays 0 .. nd-1 reach this tile's slabs
+        const int parts = std::min(c->toep_parts, nd);
+        for (int k = 0; k < parts; ++k) {
+          tiles.push_back({int32_t(p), row0, slab0, int32_t(int64_t(k) * nd / parts), int32_t(int64_t(k + 1) * nd / parts), k});
+          max_part = std::max(max_part, k);
+        }
+      }
+  c->toep_parts = max_part + 1;
+  if (c->toep_parts > 1) { c->toep_part_buf.alloc(size_t(c->toep_parts) * size_t(c->n_iface)); c->toep_part_buf.zero(c->stream); }
+  // long tiles first
+  std::stable_sort(tiles.begin(), tiles.end(), [](const ToepTile &a, const ToepTile &b) { return a.d1 - a.d0 > b.d1 - b.d0; });
   c->toep_probs.upload(probs);
   c->toep_tiles.upload(tiles);
   c->n_toep_tiles = int32_t(tiles.size());
@@ -1848,6 +2017,7 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   else if (k == "mortar_time_slabs") c->mortar_slabs = std::max(0, int(value));
   else if (k == "basis_columns") c->basis_cols_max = std::max(8, int(value));
   else if (k == "basis_auto_columns") c->basis_auto_columns = std::max(0, int(value));
+  else if (k == "basis_share") c->basis_share = value != 0;
   else if (k == "sweep_groups") {
     if (value != 1 && value != 2 && value != 4 && value != 8) { c->err = "sweep_groups must be 1, 2, 4 or 8"; return MMMFE_E_INVALID; }
     c->sweep_groups = int(value);
@@ -1955,6 +2125,11 @@ int mmmfe_add_subdomain(mmmfe_ctx *c, const mmmfe_subdomain *d, int32_t *local_i
       s->neighbor[k] = d->neighbor[k]; s->n_side[k] = d->n_side[k]; s->mortar_len[k] = d->mortar_len[k];
       if (d->neighbor[k] >= 0) {
         if (!d->side_dofs[k]) fail(MMMFE_E_INVALID, "side_dofs missing for side %d", k);
+        s->side_dofs[k].assign(d->side_dofs[k], d->side_dofs[k] + d->n_side[k]);
+        s->f2c[k].from(d->f2c[k]);
+        s->c2f[k].from(d->c2f[k]);
+      } else if (d->side_dofs[k] && d->f2c[k].row_ptr && d->c2f[k].row_ptr && d->n_side[k] > 0 && d->mortar_len[k] > 0) {
+        // tables of an outer side: never applied to this subdomain, only used to solve basis columns for other ranks
         s->side_dofs[k].assign(d->side_dofs[k], d->side_dofs[k] + d->n_side[k]);
         s->f2c[k].from(d->f2c[k]);
         s->c2f[k].from(d->c2f[k]);
@@ -2208,6 +2383,7 @@ int64_t mmmfe_stat(const mmmfe_ctx *c, const char *key) {
   if (k == "basis_columns") return c->basis_columns;
   if (k == "basis_mflop") return int64_t(c->basis_flops / 1e6);
   if (k == "basis_mbytes") return int64_t(c->basis_bytes / 1e6);
+  if (k == "basis_shared_by") { for (auto &f : c->factors) if (f->basis) v = std::max<int64_t>(v, f->basis->shared_by); return v; }
   if (k == "basis_passes") { for (auto &f : c->factors) if (f->basis) v += f->basis->n_pass; return v; }
   if (k == "basis_mw") { for (auto &f : c->factors) if (f->basis) v = std::max<int64_t>(v, f->basis->MW); return v; }
   if (k == "basis_values") { for (auto &f : c->factors) if (f->basis) v += int64_t(f->basis->T.n); return v; }

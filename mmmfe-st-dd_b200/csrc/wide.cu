@@ -122,10 +122,15 @@ void launch_wide_bwd_gather(const SolveArgs &a, int32_t MW, const WideRow *rows,
 }
 
 // =================================================================================================================
-// bottom of the tree: one CTA per subtree, factor blob staged once (TMA bulk copy), column chunks of MC
+// bottom of the tree: one CTA per (subtree, column group).  The subtree's factor blob is staged once by a TMA bulk copy
+// and reused for every column chunk of the CTA; a chunk is MC = 8, 16 or 32 columns wide (as wide as the shared memory
+// allows: the walk is bound by the latency of its levels, not by arithmetic, so wider chunks are almost free).
+// Thread = (row slot, group of 8 columns): rows of a level are dealt to the row slots, every thread keeps 8 column
+// sums in registers; vectors are stored [row][MC] in shared memory, global rows are moved as 64-byte segments.
 // =================================================================================================================
 template <int MC>
 __global__ void __launch_bounds__(256) k_wide_subtree_forward(SubtreeArgs a, int32_t MW) {
+  constexpr int CG = MC / 8, RT = 256 / CG;
   extern __shared__ __align__(16) double sm[];
   const InstanceDev in = a.inst[blockIdx.x];
   const TemplateDev T = a.tmpl[in.tmpl];
@@ -133,73 +138,82 @@ __global__ void __launch_bounds__(256) k_wide_subtree_forward(SubtreeArgs a, int
   double *blob = sm + 2;
   double *zl = blob + T.rf_size;
   double *vs = zl + int64_t(T.zl_size) * MC;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, cg = tid % CG, rt = tid / CG, cj = cg * 8;
   if (tid == 0) mbar_init(bar);
   __syncthreads();
   if (tid == 0 && T.rf_size > 0) bulk_load_start(blob, a.R + in.rf_base, uint32_t(T.rf_size) * 8u, bar);
   bool waited = T.rf_size <= 0;
   const int32_t zr = T.node_zl[T.n_nodes - 1];
   for (int32_t c0 = blockIdx.y * MC; c0 < MW; c0 += gridDim.y * MC) {  // this CTA's column chunks
-    for (int l = tid; l < T.n_int; l += 256) {
+    const bool live = c0 + cj < MW;  // MW is a multiple of 8: a group of 8 columns is inside or outside as a whole
+    for (int l = rt; l < T.n_int; l += RT) {
       const int64_t d = subtree_dof(a, in, T.var_code[l]);
+      const double2 *src = reinterpret_cast<const double2 *>(a.x + d * MW + c0 + cj);
+      double2 *dst = reinterpret_cast<double2 *>(vs + l * MC + cj);
 #pragma unroll
-      for (int j = 0; j < MC; ++j) vs[l * MC + j] = (c0 + j < MW) ? a.x[d * MW + c0 + j] : 0.0;
+      for (int h = 0; h < 4; ++h) dst[h] = live ? src[h] : make_double2(0.0, 0.0);
     }
     __syncthreads();
     if (!waited) { mbar_wait(bar, 0); waited = true; }
     for (int lv = 0; lv < T.n_levels; ++lv) {
       if (lv > 0) {
-        for (int e = T.lvl_sep[lv] + tid; e < T.lvl_sep[lv + 1]; e += 256) {
+        for (int e = T.lvl_sep[lv] + rt; e < T.lvl_sep[lv + 1]; e += RT) {
           const int32_t s0 = T.sep_c0[e], s1 = T.sep_c1[e];
 #pragma unroll
-          for (int j = 0; j < MC; ++j) {
-            double v = vs[e * MC + j];
-            if (s0 >= 0) v += zl[s0 * MC + j];
-            if (s1 >= 0) v += zl[s1 * MC + j];
-            vs[e * MC + j] = v;
+          for (int j = 0; j < 8; ++j) {
+            double v = vs[e * MC + cj + j];
+            if (s0 >= 0) v += zl[s0 * MC + cj + j];
+            if (s1 >= 0) v += zl[s1 * MC + cj + j];
+            vs[e * MC + cj + j] = v;
           }
         }
         __syncthreads();
       }
-      for (int e = T.lvl_out[lv] + tid; e < T.lvl_out[lv + 1]; e += 256) {
+      for (int e = T.lvl_out[lv] + rt; e < T.lvl_out[lv + 1]; e += RT) {
         const int32_t n = T.out_node[e];
         const int32_t s = T.node_s[n], b = T.node_b[n];
         const double *rf = blob + T.node_rf[n] + (e - T.node_zl[n]);
-        const double *v = vs + int64_t(T.node_sep[n]) * MC;
-        double acc[MC];
+        const double *v = vs + int64_t(T.node_sep[n]) * MC + cj;
+        double acc[8];
         const int32_t o0 = T.out_c0[e], o1 = T.out_c1[e];
 #pragma unroll
-        for (int j = 0; j < MC; ++j) {
+        for (int j = 0; j < 8; ++j) {
           acc[j] = 0.0;
-          if (o0 >= 0) acc[j] += zl[o0 * MC + j];
-          if (o1 >= 0) acc[j] += zl[o1 * MC + j];
+          if (o0 >= 0) acc[j] += zl[o0 * MC + cj + j];
+          if (o1 >= 0) acc[j] += zl[o1 * MC + cj + j];
         }
         for (int i = 0; i < s; ++i) {
           const double r = rf[i * b];
 #pragma unroll
-          for (int j = 0; j < MC; ++j) acc[j] += r * v[i * MC + j];
+          for (int j = 0; j < 8; ++j) acc[j] += r * v[i * MC + j];
         }
 #pragma unroll
-        for (int j = 0; j < MC; ++j) zl[e * MC + j] = acc[j];
+        for (int j = 0; j < 8; ++j) zl[e * MC + cj + j] = acc[j];
       }
       __syncthreads();
     }
-    for (int l = tid; l < T.n_int; l += 256) {
-      const int64_t d = subtree_dof(a, in, T.var_code[l]);
+    if (live) {
+      for (int l = rt; l < T.n_int; l += RT) {
+        const int64_t d = subtree_dof(a, in, T.var_code[l]);
+        double2 *dst = reinterpret_cast<double2 *>(a.x + d * MW + c0 + cj);
+        const double2 *src = reinterpret_cast<const double2 *>(vs + l * MC + cj);
 #pragma unroll
-      for (int j = 0; j < MC; ++j)
-        if (c0 + j < MW) a.x[d * MW + c0 + j] = vs[l * MC + j];
+        for (int h = 0; h < 4; ++h) dst[h] = src[h];
+      }
+      for (int q = rt; q < T.n_rootb; q += RT) {
+        double2 *dst = reinterpret_cast<double2 *>(a.z + (in.z_root + q) * MW + c0 + cj);
+        const double2 *src = reinterpret_cast<const double2 *>(zl + (zr + q) * MC + cj);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) dst[h] = src[h];
+      }
     }
-    for (int q = tid; q < T.n_rootb; q += 256)
-#pragma unroll
-      for (int j = 0; j < MC; ++j)
-        if (c0 + j < MW) a.z[(in.z_root + q) * MW + c0 + j] = zl[(zr + q) * MC + j];
     __syncthreads();  // vs / zl are reused by the next column chunk
   }
 }
 
 template <int MC>
 __global__ void __launch_bounds__(256) k_wide_subtree_backward(SubtreeArgs a, int32_t MW) {
+  constexpr int CG = MC / 8, RT = 256 / CG;
   extern __shared__ __align__(16) double sm[];
   const InstanceDev in = a.inst[blockIdx.x];
   const TemplateDev T = a.tmpl[in.tmpl];
@@ -207,65 +221,67 @@ __global__ void __launch_bounds__(256) k_wide_subtree_backward(SubtreeArgs a, in
   double *blob = sm + 2;
   double *zs = blob + T.rb_size;            // accumulated right-hand sides of the interior variables
   double *xs = zs + int64_t(T.n_int) * MC;  // solution: [interior | root boundary]
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, cg = tid % CG, rt = tid / CG, cj = cg * 8;
   if (tid == 0) mbar_init(bar);
   __syncthreads();
   if (tid == 0) bulk_load_start(blob, a.R + in.rb_base, uint32_t(T.rb_size) * 8u, bar);
   bool waited = false;
   for (int32_t c0 = blockIdx.y * MC; c0 < MW; c0 += gridDim.y * MC) {
-    for (int l = tid; l < T.n_int; l += 256) {
-      const int64_t d = subtree_dof(a, in, T.var_code[l]);
+    const bool live = c0 + cj < MW;
+    for (int l = rt; l < T.n_int + T.n_rootb; l += RT) {
+      const int64_t d = subtree_dof(a, in, l < T.n_int ? T.var_code[l] : T.rootb_code[l - T.n_int]);
+      const double2 *src = reinterpret_cast<const double2 *>(a.x + d * MW + c0 + cj);
+      double2 *dst = reinterpret_cast<double2 *>((l < T.n_int ? zs + l * MC : xs + l * MC) + cj);
 #pragma unroll
-      for (int j = 0; j < MC; ++j) zs[l * MC + j] = (c0 + j < MW) ? a.x[d * MW + c0 + j] : 0.0;
-    }
-    for (int q = tid; q < T.n_rootb; q += 256) {
-      const int64_t d = subtree_dof(a, in, T.rootb_code[q]);
-#pragma unroll
-      for (int j = 0; j < MC; ++j) xs[(T.n_int + q) * MC + j] = (c0 + j < MW) ? a.x[d * MW + c0 + j] : 0.0;
+      for (int h = 0; h < 4; ++h) dst[h] = live ? src[h] : make_double2(0.0, 0.0);
     }
     __syncthreads();
     if (!waited) { mbar_wait(bar, 0); waited = true; }
     for (int lv = T.n_levels - 1; lv >= 0; --lv) {
-      for (int e = T.lvl_sep[lv] + tid; e < T.lvl_sep[lv + 1]; e += 256) {
+      for (int e = T.lvl_sep[lv] + rt; e < T.lvl_sep[lv + 1]; e += RT) {
         const int32_t n = T.sep_node[e];
         const int32_t s = T.node_s[n], b = T.node_b[n], sep0 = T.node_sep[n];
         const double *rb = blob + T.node_rb[n] + (e - sep0);  // R^T[p][i] at p * s + i
         const int32_t *bv = T.bnd_var + T.node_bnd[n];
-        double acc[MC];
+        double acc[8];
 #pragma unroll
-        for (int j = 0; j < MC; ++j) acc[j] = 0.0;
+        for (int j = 0; j < 8; ++j) acc[j] = 0.0;
         for (int p = 0; p < s; ++p) {
           const double r = rb[p * s];
 #pragma unroll
-          for (int j = 0; j < MC; ++j) acc[j] += r * zs[(sep0 + p) * MC + j];
+          for (int j = 0; j < 8; ++j) acc[j] += r * zs[(sep0 + p) * MC + cj + j];
         }
         rb += s * s;
         for (int q = 0; q < b; ++q) {
           const double r = rb[q * s];
           const int32_t l = bv[q];
 #pragma unroll
-          for (int j = 0; j < MC; ++j) acc[j] += r * xs[l * MC + j];
+          for (int j = 0; j < 8; ++j) acc[j] += r * xs[l * MC + cj + j];
         }
 #pragma unroll
-        for (int j = 0; j < MC; ++j) xs[e * MC + j] = acc[j];
+        for (int j = 0; j < 8; ++j) xs[e * MC + cj + j] = acc[j];
       }
       __syncthreads();
     }
-    for (int l = tid; l < T.n_int; l += 256) {
-      const int64_t d = subtree_dof(a, in, T.var_code[l]);
+    if (live)
+      for (int l = rt; l < T.n_int; l += RT) {
+        const int64_t d = subtree_dof(a, in, T.var_code[l]);
+        double2 *dst = reinterpret_cast<double2 *>(a.x + d * MW + c0 + cj);
+        const double2 *src = reinterpret_cast<const double2 *>(xs + l * MC + cj);
 #pragma unroll
-      for (int j = 0; j < MC; ++j)
-        if (c0 + j < MW) a.x[d * MW + c0 + j] = xs[l * MC + j];
-    }
+        for (int h = 0; h < 4; ++h) dst[h] = src[h];
+      }
     __syncthreads();
   }
 }
 
 void wide_set_smem_limit(size_t bytes) {
-  cudaFuncSetAttribute(k_wide_subtree_forward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
   cudaFuncSetAttribute(k_wide_subtree_forward<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
-  cudaFuncSetAttribute(k_wide_subtree_backward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+  cudaFuncSetAttribute(k_wide_subtree_forward<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+  cudaFuncSetAttribute(k_wide_subtree_forward<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
   cudaFuncSetAttribute(k_wide_subtree_backward<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+  cudaFuncSetAttribute(k_wide_subtree_backward<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+  cudaFuncSetAttribute(k_wide_subtree_backward<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
 }
 
 // Column chunks are dealt to gridDim.y CTAs per subtree: enough CTAs for ~4 waves of the machine (the chunk loop of one
@@ -282,16 +298,18 @@ static unsigned subtree_column_groups(int MC, int32_t MW, int32_t n_inst) {
 void launch_wide_subtree_forward(int MC, int32_t MW, const SubtreeArgs &a, int32_t n_inst, size_t smem_bytes, cudaStream_t st) {
   if (n_inst <= 0) return;
   const dim3 grid(unsigned(n_inst), subtree_column_groups(MC, MW, n_inst));
-  if (MC == 8) k_wide_subtree_forward<8><<<grid, 256, smem_bytes, st>>>(a, MW);
-  else k_wide_subtree_forward<4><<<grid, 256, smem_bytes, st>>>(a, MW);
+  if (MC == 32) k_wide_subtree_forward<32><<<grid, 256, smem_bytes, st>>>(a, MW);
+  else if (MC == 16) k_wide_subtree_forward<16><<<grid, 256, smem_bytes, st>>>(a, MW);
+  else k_wide_subtree_forward<8><<<grid, 256, smem_bytes, st>>>(a, MW);
   launch_counter_add(1);
 }
 
 void launch_wide_subtree_backward(int MC, int32_t MW, const SubtreeArgs &a, int32_t n_inst, size_t smem_bytes, cudaStream_t st) {
   if (n_inst <= 0) return;
   const dim3 grid(unsigned(n_inst), subtree_column_groups(MC, MW, n_inst));
-  if (MC == 8) k_wide_subtree_backward<8><<<grid, 256, smem_bytes, st>>>(a, MW);
-  else k_wide_subtree_backward<4><<<grid, 256, smem_bytes, st>>>(a, MW);
+  if (MC == 32) k_wide_subtree_backward<32><<<grid, 256, smem_bytes, st>>>(a, MW);
+  else if (MC == 16) k_wide_subtree_backward<16><<<grid, 256, smem_bytes, st>>>(a, MW);
+  else k_wide_subtree_backward<8><<<grid, 256, smem_bytes, st>>>(a, MW);
   launch_counter_add(1);
 }
 
@@ -346,7 +364,8 @@ struct ToepCfg {
 template <int BM>
 __global__ void __launch_bounds__(256) k_toeplitz_apply(const ToepProb *__restrict__ probs,
                                                         const ToepTile *__restrict__ tiles,
-                                                        const double *__restrict__ q, double *__restrict__ out) {
+                                                        const double *__restrict__ q, double *__restrict__ out_parts,
+                                                        int64_t part_stride) {
   using C = ToepCfg<BM>;
   extern __shared__ __align__(16) double tsm[];
   const ToepTile tl = tiles[blockIdx.x];
@@ -358,12 +377,12 @@ __global__ void __launch_bounds__(256) k_toeplitz_apply(const ToepProb *__restri
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < C::NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  const int slab_hi = min(pr.m_t, tl.slab0 + TOEP_BN) - 1;  // last slab of this tile: delays d = 0 .. slab_hi
+  double *out = out_parts + int64_t(tl.part) * part_stride;
   int per_d = 0;
   for (int s = 0; s < pr.n_in; ++s) per_d += (pr.P_in[s] + 15) >> 4;
-  const int nk = (slab_hi + 1) * per_d;
+  const int nk = (tl.d1 - tl.d0) * per_d;  // the host clips [d0, d1) to the delays the tile's slabs can see
   // position of the NEXT k slab to be issued
-  int d = 0, s = 0, a0 = 0;
+  int d = tl.d0, s = 0, a0 = 0;
   auto issue = [&](int stage) {
     double *as = tsm + stage * C::STAGE_DBL, *bs = as + BM * TA_LD;
     const int P = pr.P_in[s];
@@ -423,7 +442,7 @@ __global__ void __launch_bounds__(256) k_toeplitz_apply(const ToepProb *__restri
 }
 
 void launch_toeplitz_apply(int bm, const ToepProb *probs, const ToepTile *tiles, int32_t n_tiles, const double *q,
-                           double *out, cudaStream_t st) {
+                           double *out_parts, int64_t part_stride, cudaStream_t st) {
   if (n_tiles <= 0) return;
   static bool attr_set = false;
   if (!attr_set) {
@@ -432,9 +451,24 @@ void launch_toeplitz_apply(int bm, const ToepProb *probs, const ToepTile *tiles,
     cudaFuncSetAttribute(k_toeplitz_apply<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ToepCfg<32>::SMEM));
     attr_set = true;
   }
-  if (bm == 128) k_toeplitz_apply<128><<<n_tiles, 256, ToepCfg<128>::SMEM, st>>>(probs, tiles, q, out);
-  else if (bm == 64) k_toeplitz_apply<64><<<n_tiles, 256, ToepCfg<64>::SMEM, st>>>(probs, tiles, q, out);
-  else k_toeplitz_apply<32><<<n_tiles, 256, ToepCfg<32>::SMEM, st>>>(probs, tiles, q, out);
+  if (bm == 128) k_toeplitz_apply<128><<<n_tiles, 256, ToepCfg<128>::SMEM, st>>>(probs, tiles, q, out_parts, part_stride);
+  else if (bm == 64) k_toeplitz_apply<64><<<n_tiles, 256, ToepCfg<64>::SMEM, st>>>(probs, tiles, q, out_parts, part_stride);
+  else k_toeplitz_apply<32><<<n_tiles, 256, ToepCfg<32>::SMEM, st>>>(probs, tiles, q, out_parts, part_stride);
+  launch_counter_add(1);
+}
+
+__global__ void __launch_bounds__(256) k_sum_parts(int64_t n, const double *__restrict__ parts, int64_t part_stride,
+                                                   int32_t n_parts, double *__restrict__ out) {
+  const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  double acc = parts[i];
+  for (int p = 1; p < n_parts; ++p) acc += parts[p * part_stride + i];
+  out[i] = acc;
+}
+
+void launch_sum_parts(int64_t n, const double *parts, int64_t part_stride, int32_t n_parts, double *out, cudaStream_t st) {
+  if (n <= 0) return;
+  k_sum_parts<<<unsigned((n + 255) / 256), 256, 0, st>>>(n, parts, part_stride, n_parts, out);
   launch_counter_add(1);
 }
 

@@ -66,9 +66,14 @@ struct ToepProb {
 };
 struct ToepTile {
   int32_t prob, row0, slab0;
+  int32_t d0, d1;  // delays [d0, d1) of this tile (split-k: the delay range of a slab tile is cut into parts)
+  int32_t part;    // partial-sum buffer this tile writes (0 .. n_parts-1)
 };
 constexpr int TOEP_BN = 32;  // mortar time slabs per tile; rows per tile: 128, 64 or 32 (chosen by the caller)
+// Tiles write out_parts[part * part_stride + ...]; entries no tile of a part covers must be zero (static structure:
+// zero the buffer once).  launch_sum_parts adds the parts in fixed order: deterministic.
 void launch_toeplitz_apply(int rows_per_tile, const ToepProb *probs, const ToepTile *tiles, int32_t n_tiles,
-                           const double *q, double *out, cudaStream_t st);
+                           const double *q, double *out_parts, int64_t part_stride, cudaStream_t st);
+void launch_sum_parts(int64_t n, const double *parts, int64_t part_stride, int32_t n_parts, double *out, cudaStream_t st);
 
 }  // namespace mmmfe

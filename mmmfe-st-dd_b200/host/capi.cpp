@@ -74,7 +74,7 @@ int mmmfe_host_run(const char *parameter_file, const mmmfe_host_options *opt, mm
         for (int k = 0; k < 4; ++k) { d.sweep_steps[k] = r.sweep_steps[k]; d.sweep_ms[k] = r.sweep_ms[k]; d.sweep_bytes_per_step[k] = r.sweep_bytes_per_step[k]; }
         d.tune_us_sweep = r.tune_us_sweep; d.tune_us_levels = r.tune_us_levels; d.sweep_planned = r.sweep_planned;
         d.tune_rel_diff_e18 = r.tune_rel_diff_e18;
-        d.basis_operator = r.basis_operator; d.basis_pad = 0; d.t_basis = r.t_basis; d.basis_gflop = r.basis_gflop;
+        d.basis_operator = r.basis_operator; d.basis_shared_by = r.basis_shared_by; d.t_basis = r.t_basis; d.basis_gflop = r.basis_gflop;
         d.basis_bytes = r.basis_bytes; d.basis_columns = r.basis_columns;
         d.solve_iterations = r.solve_iterations; d.solve_converged = r.solve_converged;
         d.t_solve_gmres = r.t_solve_gmres; d.solve_final_residual = r.solve_final_residual;

@@ -735,8 +735,9 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
       Sub &s = *subs[li];
       assemble_matrix(s, prm.c_0);
       constrain_matrix(s, is_manufact_solution, bc_condition_vect, bc_const_functs);
+      // outer sides too when several ranks run: lets the ranks share the multiscale-basis work of a factor group
       for (int side = 0; side < 4; ++side)
-        if (s.nb[side] >= 0) projector_tables(s, side, mortar, int(mortar_degree));
+        if (s.nb[side] >= 0 || world > 1) projector_tables(s, side, mortar, int(mortar_degree));
     }
     rep.t_assemble = since(t0);
     if (say && !subs.empty()) {
@@ -776,7 +777,7 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
       for (int k = 0; k < 4; ++k) {
         d.neighbor[k] = s.nb[k]; d.n_side[k] = s.n_side[k]; d.side_dofs[k] = s.side_edges[k].data();
         d.mortar_len[k] = s.mortar_len[k];
-        if (s.nb[k] >= 0) { d.f2c[k] = s.f2c[k].view(); d.c2f[k] = s.c2f[k].view(); }
+        if (s.nb[k] >= 0 || (world > 1 && !s.f2c[k].rp.empty())) { d.f2c[k] = s.f2c[k].view(); d.c2f[k] = s.c2f[k].view(); }
       }
       check(ctx, mmmfe_add_subdomain(ctx, &d, &s.local), "mmmfe_add_subdomain");
     }
@@ -796,6 +797,7 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
     rep.basis_gflop = double(mmmfe_stat(ctx, "basis_mflop")) * 1e-3;
     rep.basis_bytes = double(mmmfe_stat(ctx, "basis_mbytes")) * 1e6;
     rep.basis_columns = mmmfe_stat(ctx, "basis_columns");
+    rep.basis_shared_by = int(std::max<long long>(1, mmmfe_stat(ctx, "basis_shared_by")));
     for (auto &sp : subs) { rep.dof_steps += (long long)sp->n * sp->nt; sp->matrix = Csr(); }
     // ---- bar problems ----
     t0 = clk::now();

@@ -55,7 +55,7 @@ struct CycleReport {
   double t_solve_gmres = 0.0, solve_final_residual = 0.0;
   long long tune_rel_diff_e18 = -1;  // set-up cross-check of the two star-sweep implementations (relative l2 * 1e18)
   // multiscale-basis (time-Toeplitz) operator, when the engine built it
-  int basis_operator = 0;
+  int basis_operator = 0, basis_shared_by = 1;
   double t_basis = 0.0, basis_gflop = 0.0, basis_bytes = 0.0;
   long long basis_columns = 0;
 };

@@ -90,7 +90,8 @@ def main():
         entry = {"world": world, "iterations": r["gmres_iterations"], "oracle_iterations": o.gmres_iterations,
                  "r_norm_rel": abs(r["r_norm"] - o.r_norm) / o.r_norm, "lambda_rel_l2": rel_l2(lam, o.lam),
                  "errors_rel": max(abs(r[k] - o.errors[k]) / o.errors[k] for k in o.errors) if o.errors else None,
-                 "sweep_batches": r.get("sweep_batches"), "lambda_tol": tol_lam, "oracle_spread_at_1e-11": spread}
+                 "sweep_batches": r.get("sweep_batches"), "lambda_tol": tol_lam, "oracle_spread_at_1e-11": spread,
+                 "basis_operator": r.get("basis_operator"), "basis_shared_by": r.get("basis_shared_by")}
         entry["tune_rel_diff"] = r.get("tune_rel_diff_e18", -1) * 1e-18 if r.get("tune_rel_diff_e18", -1) >= 0 else None
         entry["ok"] = bool(abs(entry["iterations"] - entry["oracle_iterations"]) <= 1 and entry["r_norm_rel"] < 1e-11
                            and entry["lambda_rel_l2"] < tol_lam and (not c.get("sweep") or entry["sweep_batches"] > 0))
