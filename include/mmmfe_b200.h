@@ -99,7 +99,9 @@ const char *mmmfe_version(void);
  * columns, else 0.  "mortar_time_slabs" = time steps of the mortar mesh (mesh_pattern_mortar nt; required for 1/2),
  * "basis_columns" = columns solved per pass (default 256), "basis_share" (default 1: with several ranks, a factor
  * group that every rank holds is solved for once, each rank taking a block of its columns; needs the projector tables
- * of all four sides, see mmmfe_subdomain).                                                                        */
+ * of all four sides, see mmmfe_subdomain), "basis_drop_tol" (default 1e-18; 0 = off): a pass of the basis solve stops
+ * at the end of a mortar slab once the pressures -- the only state carried between steps -- are below this fraction of
+ * their peak (no data after the first slab, backward Euler contracts), the later delays of the operator are zero.  */
 int mmmfe_set_option(mmmfe_ctx *ctx, const char *key, double value);
 
 /* ---- multi-GPU: one process per GPU, subdomains sharded over ranks ------------------------------------------ */
@@ -226,9 +228,14 @@ int mmmfe_debug_sweep_trace(mmmfe_ctx *ctx, int32_t batch, int64_t cap, int64_t 
  * "sweep_entries", "sweep_factor_bytes", "rt0_factors", "sweep_planned" (batches with a sweep plan, whether or
  * not the auto-tuner kept it), "tune_us_sweep" / "tune_us_levels" (microseconds of the timed star sweep of each
  * implementation), "tune_rel_diff_e18" (their relative l2 difference * 1e18), "basis_operator" (1: GMRES runs on the
- * multiscale-basis operator), "basis_us", "basis_columns", "basis_mflop", "basis_passes", "basis_mw", "basis_values",
+ * multiscale-basis operator), "basis_us", "basis_columns", "basis_mflop", "basis_passes", "basis_mw", "basis_values", "basis_steps" (time steps
+ * solved, summed over passes), "basis_delays" (mortar slabs after which the response is zero), "basis_shared_by",
  * "toeplitz_tiles", "toeplitz_mflop", "toeplitz_mbytes" (per operator application); -1 for an unknown key.        */
 int64_t mmmfe_stat(const mmmfe_ctx *ctx, const char *key);
+
+/* Measured peak of the FP64 tensor cores (register-resident mma.sync.m8n8k4.f64 on all SMs), TFLOP/s: the roofline
+ * denominator of the factorisation and of the multiscale-basis kernels (MEASURED_PEAKS.json has no FP64 figure).   */
+int mmmfe_measure_fp64_tensor_tflops(int device, double *tflops);
 
 /* ---- diagnostics (host only, no device needed) ------------------------------------------------------------------- */
 /* The nested-dissection tree the engine builds for an nx x ny RT0 grid, in canonical flux numbering.

@@ -62,6 +62,7 @@ def load_engine():
         "mmmfe_set_owners": (ctypes.c_int, [vp, ctypes.c_int32, c_i32p]),
         "mmmfe_comm_allreduce_sum": (ctypes.c_int, [vp, c_f64p, ctypes.c_int32]),
         "mmmfe_kernel_launches": (ctypes.c_int64, [vp]),
+        "mmmfe_measure_fp64_tensor_tflops": (ctypes.c_int, [ctypes.c_int, c_f64p]),
         "mmmfe_add_subdomain": (ctypes.c_int, [vp, ctypes.POINTER(SubdomainDesc), c_i32p]),
         "mmmfe_setup": (ctypes.c_int, [vp]),
         "mmmfe_interface_length": (ctypes.c_int64, [vp]),
@@ -326,6 +327,15 @@ class Engine:
         out = np.empty_like(rhs)
         self._check(self.lib.mmmfe_solve_saddle(self.h, li, _ptr(rhs, c_f64p), _ptr(out, c_f64p)))
         return out
+
+
+def fp64_tensor_peak_tflops(device=-1):
+    """Measured DMMA peak of the device (TFLOP/s)."""
+    lib = load_engine()
+    v = ctypes.c_double(0.0)
+    if lib.mmmfe_measure_fp64_tensor_tflops(device, ctypes.byref(v)) != 0:
+        raise MmmfeError("DMMA peak measurement failed")
+    return v.value
 
 
 def sweep_plan_check(nx, ny, leaf_cells=4, subtree_cells=128, M=1, n_cta=296, smem_bytes=115000, n_steps=3,

@@ -104,6 +104,8 @@ struct Basis {
   int32_t P_tot = 0, n_tr = 0, MW = 0, n_pass = 0, MC = 8;
   int32_t col_lo = 0, col_hi = 0;  // the columns THIS rank solves for (all of them unless the ranks share the group)
   int32_t shared_by = 1;           // ranks that share the work of this group
+  int32_t d_used = 0;              // delays d >= d_used are identically zero (the response has died out)
+  int64_t steps = 0;               // time steps actually solved, summed over the passes
   int64_t ldt = 0;
   DevBuf<double> T;
   double seconds = 0.0, flops = 0.0, bytes = 0.0;
@@ -252,6 +254,7 @@ struct mmmfe_ctx {
   // basis_auto_columns columns per factor group, sweeps otherwise
   int operator_mode = 2, mortar_slabs = 0, basis_cols_max = 256, basis_auto_columns = 1024;
   bool basis_share = true;  // several ranks: split the columns of a group every rank holds among the ranks
+  double basis_drop_tol = 1e-18;  // a pass of the basis solve stops once the pressures fell below this fraction of their peak
   bool use_basis = false;
   std::string basis_note;  // why the basis operator is not in use
   DevBuf<ToepProb> toep_probs;
@@ -1076,8 +1079,8 @@ static void compute_basis(mmmfe_ctx *c, Factor &F, Basis &B) {
   auto smem_for = [&](int MC) {
     smem_f = smem_b = 0;
     for (const auto &T : tr.templates) {
-      smem_f = std::max(smem_f, 16 + 8 * (size_t(T.rf_size) + (size_t(T.zl_size) + size_t(T.n_int)) * MC));
-      smem_b = std::max(smem_b, 16 + 8 * (size_t(T.rb_size) + size_t(2 * T.n_int + T.n_rootb) * MC));
+      smem_f = std::max(smem_f, 16 + 8 * (size_t(T.rf_size) + (size_t(T.zl_size) + size_t(T.n_int)) * (MC + 2)));
+      smem_b = std::max(smem_b, 16 + 8 * (size_t(T.rb_size) + size_t(2 * T.n_int + T.n_rootb) * (MC + 2)));
     }
     return std::max(smem_f, smem_b);
   };
@@ -1261,15 +1264,39 @@ static void compute_basis(mmmfe_ctx *c, Factor &F, Basis &B) {
     CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
     CUDA_CHECK(cudaGraphDestroy(g));
   }
+  // The star problem has zero data after the first mortar slab and backward Euler contracts: once the pressures
+  // (the only state carried from step to step) have decayed below basis_drop_tol (default 1e-18) of their peak, every
+  // later trace is below that fraction of the peak response too -- far under the rounding of the sums it would enter
+  // -- and the remaining steps of the pass are skipped (their traces stay zero).  Checked at the end of every slab.
+  DevBuf<unsigned long long> d_peak;
+  d_peak.alloc(1);
+  int64_t steps_done = 0;
+  B.d_used = 0;
   for (int pass = 0; pass < B.n_pass; ++pass) {
     const int32_t init[2] = {0, pass};
     CUDA_CHECK(cudaMemcpyAsync(state.p, init, sizeof init, cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaStreamSynchronize(st));  // `init` is a stack variable
     ptil.zero(st);
+    trace.zero(st);
+    double peak = 0.0;
+    int done = nt;
     for (int lvl = 0; lvl < nt; ++lvl) {
       if (ge) { CUDA_CHECK(cudaGraphLaunch(ge, st)); launch_counter_add(B.graph_kernels); }
       else enqueue_step();
+      if (c->basis_drop_tol > 0 && (lvl + 1) % r == 0 && lvl + 1 < nt) {
+        d_peak.zero(st);
+        launch_absmax(int64_t(ptil.n), ptil.p, d_peak.p, st);
+        unsigned long long bits = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&bits, d_peak.p, sizeof bits, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        double v;
+        std::memcpy(&v, &bits, sizeof v);
+        peak = std::max(peak, v);
+        if (v <= c->basis_drop_tol * peak) { done = lvl + 1; break; }
+      }
     }
+    steps_done += done;
+    B.d_used = std::max(B.d_used, (done + r - 1) / r);
     const int n_cols = std::min(MW, n_local - pass * MW);
     launch_wide_f2c(int64_t(f_trow.size()), d_frp.p, d_fcol.p, d_fval.p, trace.p, MW, n_cols, B.T.p, B.ldt, d_ftrow.p,
                     int64_t(B.col_lo) + int64_t(pass) * MW, st);
@@ -1279,8 +1306,9 @@ static void compute_basis(mmmfe_ctx *c, Factor &F, Basis &B) {
   if (ge) cudaGraphExecDestroy(ge);
   double vals = 0;
   for (const NdNode &n : tr.nodes) vals += double(n.s) * (double(n.s) + 2.0 * n.b);
-  B.flops = 2.0 * vals * nt * double(B.n_pass) * MW;
-  B.bytes = double(B.n_pass) * nt * (8.0 * vals + 8.0 * MW * (4.0 * F.nf + 3.0 * F.np));
+  B.flops = 2.0 * vals * double(steps_done) * MW;
+  B.bytes = double(steps_done) * (8.0 * vals + 8.0 * MW * (4.0 * F.nf + 3.0 * F.np));
+  B.steps = steps_done;
   B.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
 }
 
@@ -1437,17 +1465,28 @@ static void setup_basis_operator(mmmfe_ctx *c, const std::vector<int> &group_of)
         order.push_back({{mine[2], mine[1]}, g});
       }
     std::sort(order.begin(), order.end());
-    for (const auto &o : order) {
-      Basis &B = *c->factors[o.second]->basis;
+    std::vector<double> used(order.size() * size_t(c->world), 0.0);
+    for (size_t k = 0; k < order.size(); ++k) {
+      Basis &B = *c->factors[order[k].second]->basis;
       allreduce_sum(c, B.T.p, B.T.n);
+      used[k * c->world + c->rank] = B.d_used;
     }
-    if (!order.empty()) {
+    if (!order.empty()) {  // the delays any rank's columns reach
+      DevBuf<double> d;
+      d.upload(used);
+      allreduce_sum(c, d.p, used.size());
+      CUDA_CHECK(cudaMemcpyAsync(used.data(), d.p, used.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
       CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      for (size_t k = 0; k < order.size(); ++k) {
+        Basis &B = *c->factors[order[k].second]->basis;
+        for (int rk = 0; rk < c->world; ++rk) B.d_used = std::max(B.d_used, int32_t(used[k * c->world + rk]));
+      }
       c->basis_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
   }
   std::vector<ToepProb> probs;
   std::vector<ToepTile> tiles;
+  std::vector<int> prob_dmax;
   c->toep_flops = c->toep_bytes = 0;
   for (int i = 0; i < ns; ++i) {
     const Sub &sd = *c->subs[i];
@@ -1466,9 +1505,11 @@ static void setup_basis_operator(mmmfe_ctx *c, const std::vector<int> &group_of)
         ++pr.n_in;
         k_len += B.P[ki];
       }
-      c->toep_flops += 2.0 * pr.P_out * k_len * 0.5 * B.m_t * (B.m_t + 1.0);
-      c->toep_bytes += 8.0 * pr.P_out * k_len * B.m_t;
+      const double du = std::max(1, B.d_used);
+      c->toep_flops += 2.0 * pr.P_out * k_len * (du * B.m_t - 0.5 * du * (du - 1.0));  // slab I sees delays 0 .. min(I, du-1)
+      c->toep_bytes += 8.0 * pr.P_out * k_len * du;
       probs.push_back(pr);
+      prob_dmax.push_back(std::max(1, B.d_used));
     }
   }
   // rows per tile: large tiles re-read q less often, small problems need small tiles to yield enough CTAs; the delay
@@ -1487,7 +1528,7 @@ static void setup_basis_operator(mmmfe_ctx *c, const std::vector<int> &group_of)
   for (size_t p = 0; p < probs.size(); ++p)
     for (int row0 = 0; row0 < probs[p].P_out; row0 += c->toep_bm)
       for (int slab0 = 0; slab0 < probs[p].m_t; slab0 += TOEP_BN) {
-        const int nd = std::min(probs[p].m_t, slab0 + TOEP_BN);  // delays 0 .. nd-1 reach this tile's slabs
+        const int nd = std::min(std::min(probs[p].m_t, slab0 + TOEP_BN), prob_dmax[p]);  // delays 0 .. nd-1 reach this tile's slabs and carry data
         const int parts = std::min(c->toep_parts, nd);
         for (int k = 0; k < parts; ++k) {
           tiles.push_back({int32_t(p), row0, slab0, int32_t(int64_t(k) * nd / parts), int32_t(int64_t(k + 1) * nd / parts), k});
@@ -2018,6 +2059,7 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   else if (k == "basis_columns") c->basis_cols_max = std::max(8, int(value));
   else if (k == "basis_auto_columns") c->basis_auto_columns = std::max(0, int(value));
   else if (k == "basis_share") c->basis_share = value != 0;
+  else if (k == "basis_drop_tol") c->basis_drop_tol = std::max(0.0, value);
   else if (k == "sweep_groups") {
     if (value != 1 && value != 2 && value != 4 && value != 8) { c->err = "sweep_groups must be 1, 2, 4 or 8"; return MMMFE_E_INVALID; }
     c->sweep_groups = int(value);
@@ -2106,6 +2148,13 @@ int mmmfe_comm_allreduce_sum(mmmfe_ctx *c, double *inout, int32_t n) {
     CUDA_CHECK(cudaMemcpyAsync(inout, d.p, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   });
+}
+
+int mmmfe_measure_fp64_tensor_tflops(int device, double *tflops) {
+  if (!tflops) return MMMFE_E_INVALID;
+  if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return MMMFE_E_CUDA;
+  *tflops = measure_dmma_tflops(nullptr);
+  return *tflops > 0 ? MMMFE_OK : MMMFE_E_CUDA;
 }
 
 int64_t mmmfe_kernel_launches(const mmmfe_ctx *c) { return c ? launch_counter() - c->launch_base : 0; }
@@ -2384,6 +2433,8 @@ int64_t mmmfe_stat(const mmmfe_ctx *c, const char *key) {
   if (k == "basis_mflop") return int64_t(c->basis_flops / 1e6);
   if (k == "basis_mbytes") return int64_t(c->basis_bytes / 1e6);
   if (k == "basis_shared_by") { for (auto &f : c->factors) if (f->basis) v = std::max<int64_t>(v, f->basis->shared_by); return v; }
+  if (k == "basis_steps") { for (auto &f : c->factors) if (f->basis) v += f->basis->steps; return v; }
+  if (k == "basis_delays") { for (auto &f : c->factors) if (f->basis) v = std::max<int64_t>(v, f->basis->d_used); return v; }
   if (k == "basis_passes") { for (auto &f : c->factors) if (f->basis) v += f->basis->n_pass; return v; }
   if (k == "basis_mw") { for (auto &f : c->factors) if (f->basis) v = std::max<int64_t>(v, f->basis->MW); return v; }
   if (k == "basis_values") { for (auto &f : c->factors) if (f->basis) v += int64_t(f->basis->T.n); return v; }

@@ -932,4 +932,48 @@ void launch_diff_norms(int64_t n, const double *a, const double *b, double *out,
   launch_counter_add(1);
 }
 
+// =================================================================================================================
+// measured FP64 tensor-core (DMMA) peak: the denominator of the factorisation / multiscale-basis rooflines
+// =================================================================================================================
+__global__ void __launch_bounds__(256) k_dmma_peak(double *out, int iters) {
+  double acc[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+  for (int i = 0; i < iters; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dmma_m8n8k4(acc[j][0], acc[j][1], a, b);  // 8 independent accumulators per warp
+  double sum = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sum += acc[j][0] + acc[j][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
+
+// TFLOP/s of register-resident mma.sync.m8n8k4.f64 on all SMs (8 warps x 4 CTAs per SM), best of 3
+double measure_dmma_tflops(cudaStream_t st) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = sms * 4, iters = 20000;
+  double *out = nullptr;
+  if (cudaMalloc(&out, size_t(blocks) * 256 * sizeof(double)) != cudaSuccess) return 0.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, st);
+    k_dmma_peak<<<blocks, 256, 0, st>>>(out, iters);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = double(blocks) * 8.0 * iters * 8.0 * 512.0;  // m8n8k4: 256 FMA = 512 flop
+    if (rep > 0 && ms > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  launch_counter_add(4);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  return best;
+}
+
 }  // namespace mmmfe

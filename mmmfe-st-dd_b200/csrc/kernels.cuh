@@ -155,5 +155,6 @@ void launch_axpy_rows(int64_t len, const double *Q, int64_t ldq, int32_t n_rows,
 // ---- diagnostics -----------------------------------------------------------------------------------------------
 void launch_fill_hash(int64_t n, uint64_t seed, double *out, cudaStream_t st);
 void launch_diff_norms(int64_t n, const double *a, const double *b, double *out, cudaStream_t st);
+double measure_dmma_tflops(cudaStream_t st);
 
 }  // namespace mmmfe

@@ -10,19 +10,21 @@ namespace mmmfe {
 // =================================================================================================================
 // time stepping, MW columns: thread = (row, column), columns fastest (coalesced rows of MW doubles)
 // =================================================================================================================
+// one warp per row, lanes over the columns: the sparse row is read once per warp, the vector rows in full lines
 __global__ void __launch_bounds__(256) k_wide_rhs(WideStep a) {
-  const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  const int64_t e = idx / a.MW;
+  const int64_t e = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (e >= a.n_flux) return;
-  const int j = int(idx - e * a.MW);
-  double acc = 0.0;
-  for (int64_t k = a.kup_rp[e]; k < a.kup_rp[e + 1]; ++k) acc -= a.kup_val[k] * a.ptil[int64_t(a.kup_col[k]) * a.MW + j];
-  a.x[idx] = acc;
+  const int lane = threadIdx.x & 31;
+  const int64_t k0 = a.kup_rp[e], k1 = a.kup_rp[e + 1];
+  for (int j = lane; j < a.MW; j += 32) {
+    double acc = 0.0;
+    for (int64_t k = k0; k < k1; ++k) acc -= a.kup_val[k] * a.ptil[int64_t(a.kup_col[k]) * a.MW + j];
+    a.x[e * a.MW + j] = acc;
+  }
 }
 
 void launch_wide_rhs(const WideStep &a, cudaStream_t st) {
-  const int64_t n = a.n_flux * a.MW;
-  k_wide_rhs<<<unsigned((n + 255) / 256), 256, 0, st>>>(a);
+  k_wide_rhs<<<unsigned((a.n_flux + 7) / 8), 256, 0, st>>>(a);
   launch_counter_add(1);
 }
 
@@ -46,22 +48,44 @@ void launch_wide_add(const WideStep &a, const int64_t *lvl_rp, const int32_t *ro
 
 __global__ void __launch_bounds__(256) k_wide_update(WideStep a, const int32_t *__restrict__ tr_dof, int32_t n_tr,
                                                      double *__restrict__ trace) {
-  const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  const int64_t r = idx / a.MW;
-  const int j = int(idx - r * a.MW);
+  const int64_t r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (r < a.n_pressure) {
-    double acc = 0.0;
-    for (int64_t k = a.kpu_rp[r]; k < a.kpu_rp[r + 1]; ++k) acc += a.kpu_val[k] * a.x[int64_t(a.kpu_col[k]) * a.MW + j];
-    a.ptil[idx] -= a.minv[r] * acc;
+    const int64_t k0 = a.kpu_rp[r], k1 = a.kpu_rp[r + 1];
+    const double mi = a.minv[r];
+    for (int j = lane; j < a.MW; j += 32) {
+      double acc = 0.0;
+      for (int64_t k = k0; k < k1; ++k) acc += a.kpu_val[k] * a.x[int64_t(a.kpu_col[k]) * a.MW + j];
+      a.ptil[r * a.MW + j] -= mi * acc;
+    }
     return;
   }
   const int64_t t = r - a.n_pressure;
-  if (t < n_tr) trace[(int64_t(a.state[0]) * n_tr + t) * a.MW + j] = a.x[int64_t(tr_dof[t]) * a.MW + j];
+  if (t < n_tr) {
+    const double *src = a.x + int64_t(tr_dof[t]) * a.MW;
+    double *dst = trace + (int64_t(a.state[0]) * n_tr + t) * a.MW;
+    for (int j = lane; j < a.MW; j += 32) dst[j] = src[j];
+  }
 }
 
 void launch_wide_update(const WideStep &a, const int32_t *tr_dof, int32_t n_tr, double *trace, cudaStream_t st) {
-  const int64_t n = (a.n_pressure + n_tr) * a.MW;
-  k_wide_update<<<unsigned((n + 255) / 256), 256, 0, st>>>(a, tr_dof, n_tr, trace);
+  const int64_t rows = a.n_pressure + n_tr;
+  k_wide_update<<<unsigned((rows + 7) / 8), 256, 0, st>>>(a, tr_dof, n_tr, trace);
+  launch_counter_add(1);
+}
+
+// max |v| over a vector as the bit pattern of a non-negative double (monotone): out must be zeroed by the caller
+__global__ void __launch_bounds__(256) k_absmax(int64_t n, const double *__restrict__ v, unsigned long long *out) {
+  double m = 0.0;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) m = fmax(m, fabs(v[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+void launch_absmax(int64_t n, const double *v, unsigned long long *out, cudaStream_t st) {
+  if (n <= 0) return;
+  k_absmax<<<unsigned(std::min<int64_t>(1184, (n + 255) / 256)), 256, 0, st>>>(n, v, out);
   launch_counter_add(1);
 }
 
@@ -77,47 +101,53 @@ void launch_wide_next_level(int32_t *state, cudaStream_t st) {
 // =================================================================================================================
 __global__ void __launch_bounds__(256) k_wide_fwd_gather(SolveArgs a, int32_t MW, const WideRow *__restrict__ rows,
                                                          int64_t n_rows) {
-  const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  const int64_t w = idx / MW;
+  const int64_t w = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (w >= n_rows) return;
-  const int j = int(idx - w * MW);
+  const int lane = threadIdx.x & 31;
   const WideRow rw = rows[w];
   const FrontDesc fd = a.fronts[rw.node];
   const int32_t f = fd.s + fd.b, p = rw.p;
-  double v = p < fd.s ? a.x[int64_t(a.idx[fd.idx_off + p]) * MW + j] : 0.0;
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    const int32_t ch = c ? fd.child1 : fd.child0;
-    if (ch < 0) continue;
-    const int32_t q = a.src[fd.src_off + int64_t(c) * f + p];
-    if (q < 0) continue;
-    const FrontDesc cd = a.fronts[ch];
-    v += a.z[(cd.z_off + cd.s + q) * MW + j];
+  const double *xr = p < fd.s ? a.x + int64_t(a.idx[fd.idx_off + p]) * MW : nullptr;
+  const double *c0 = nullptr, *c1 = nullptr;
+  if (fd.child0 >= 0) {
+    const int32_t q = a.src[fd.src_off + p];
+    if (q >= 0) { const FrontDesc cd = a.fronts[fd.child0]; c0 = a.z + (cd.z_off + cd.s + q) * MW; }
   }
-  a.z[(fd.z_off + p) * MW + j] = v;
+  if (fd.child1 >= 0) {
+    const int32_t q = a.src[fd.src_off + f + p];
+    if (q >= 0) { const FrontDesc cd = a.fronts[fd.child1]; c1 = a.z + (cd.z_off + cd.s + q) * MW; }
+  }
+  double *dst = a.z + (fd.z_off + p) * MW;
+  for (int j = lane; j < MW; j += 32) {
+    double v = xr ? xr[j] : 0.0;
+    if (c0) v += c0[j];
+    if (c1) v += c1[j];
+    dst[j] = v;
+  }
 }
 
 void launch_wide_fwd_gather(const SolveArgs &a, int32_t MW, const WideRow *rows, int64_t n_rows, cudaStream_t st) {
   if (n_rows <= 0) return;
-  k_wide_fwd_gather<<<unsigned((n_rows * MW + 255) / 256), 256, 0, st>>>(a, MW, rows, n_rows);
+  k_wide_fwd_gather<<<unsigned((n_rows + 7) / 8), 256, 0, st>>>(a, MW, rows, n_rows);
   launch_counter_add(1);
 }
 
 __global__ void __launch_bounds__(256) k_wide_bwd_gather(SolveArgs a, int32_t MW, const WideRow *__restrict__ rows,
                                                          int64_t n_rows) {
-  const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-  const int64_t w = idx / MW;
+  const int64_t w = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (w >= n_rows) return;
-  const int j = int(idx - w * MW);
+  const int lane = threadIdx.x & 31;
   const WideRow rw = rows[w];
   const FrontDesc fd = a.fronts[rw.node];
   const int32_t p = fd.s + rw.p;
-  a.z[(fd.z_off + p) * MW + j] = a.x[int64_t(a.idx[fd.idx_off + p]) * MW + j];
+  const double *src = a.x + int64_t(a.idx[fd.idx_off + p]) * MW;
+  double *dst = a.z + (fd.z_off + p) * MW;
+  for (int j = lane; j < MW; j += 32) dst[j] = src[j];
 }
 
 void launch_wide_bwd_gather(const SolveArgs &a, int32_t MW, const WideRow *rows, int64_t n_rows, cudaStream_t st) {
   if (n_rows <= 0) return;
-  k_wide_bwd_gather<<<unsigned((n_rows * MW + 255) / 256), 256, 0, st>>>(a, MW, rows, n_rows);
+  k_wide_bwd_gather<<<unsigned((n_rows + 7) / 8), 256, 0, st>>>(a, MW, rows, n_rows);
   launch_counter_add(1);
 }
 
@@ -125,20 +155,21 @@ void launch_wide_bwd_gather(const SolveArgs &a, int32_t MW, const WideRow *rows,
 // bottom of the tree: one CTA per (subtree, column group).  The subtree's factor blob is staged once by a TMA bulk copy
 // and reused for every column chunk of the CTA; a chunk is MC = 8, 16 or 32 columns wide (as wide as the shared memory
 // allows: the walk is bound by the latency of its levels, not by arithmetic, so wider chunks are almost free).
-// Thread = (row slot, group of 8 columns): rows of a level are dealt to the row slots, every thread keeps 8 column
-// sums in registers; vectors are stored [row][MC] in shared memory, global rows are moved as 64-byte segments.
+// Thread = (row slot, group of 8 columns), row slots fastest: rows of a level are dealt to the row slots, every thread
+// keeps 8 column sums in registers; vectors are stored [row][MC + 2] in shared memory (the padding spreads the 16-byte
+// accesses of 8 consecutive rows over all banks), global rows are moved as 64-byte segments.
 // =================================================================================================================
 template <int MC>
 __global__ void __launch_bounds__(256) k_wide_subtree_forward(SubtreeArgs a, int32_t MW) {
-  constexpr int CG = MC / 8, RT = 256 / CG;
+  constexpr int CG = MC / 8, RT = 256 / CG, LD = MC + 2;
   extern __shared__ __align__(16) double sm[];
   const InstanceDev in = a.inst[blockIdx.x];
   const TemplateDev T = a.tmpl[in.tmpl];
   uint64_t *bar = reinterpret_cast<uint64_t *>(sm);
   double *blob = sm + 2;
   double *zl = blob + T.rf_size;
-  double *vs = zl + int64_t(T.zl_size) * MC;
-  const int tid = threadIdx.x, cg = tid % CG, rt = tid / CG, cj = cg * 8;
+  double *vs = zl + int64_t(T.zl_size) * LD;
+  const int tid = threadIdx.x, rt = tid % RT, cg = tid / RT, cj = cg * 8;
   if (tid == 0) mbar_init(bar);
   __syncthreads();
   if (tid == 0 && T.rf_size > 0) bulk_load_start(blob, a.R + in.rf_base, uint32_t(T.rf_size) * 8u, bar);
@@ -149,7 +180,7 @@ __global__ void __launch_bounds__(256) k_wide_subtree_forward(SubtreeArgs a, int
     for (int l = rt; l < T.n_int; l += RT) {
       const int64_t d = subtree_dof(a, in, T.var_code[l]);
       const double2 *src = reinterpret_cast<const double2 *>(a.x + d * MW + c0 + cj);
-      double2 *dst = reinterpret_cast<double2 *>(vs + l * MC + cj);
+      double2 *dst = reinterpret_cast<double2 *>(vs + l * LD + cj);
 #pragma unroll
       for (int h = 0; h < 4; ++h) dst[h] = live ? src[h] : make_double2(0.0, 0.0);
     }
@@ -161,10 +192,10 @@ __global__ void __launch_bounds__(256) k_wide_subtree_forward(SubtreeArgs a, int
           const int32_t s0 = T.sep_c0[e], s1 = T.sep_c1[e];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            double v = vs[e * MC + cj + j];
-            if (s0 >= 0) v += zl[s0 * MC + cj + j];
-            if (s1 >= 0) v += zl[s1 * MC + cj + j];
-            vs[e * MC + cj + j] = v;
+            double v = vs[e * LD + cj + j];
+            if (s0 >= 0) v += zl[s0 * LD + cj + j];
+            if (s1 >= 0) v += zl[s1 * LD + cj + j];
+            vs[e * LD + cj + j] = v;
           }
         }
         __syncthreads();
@@ -173,22 +204,22 @@ __global__ void __launch_bounds__(256) k_wide_subtree_forward(SubtreeArgs a, int
         const int32_t n = T.out_node[e];
         const int32_t s = T.node_s[n], b = T.node_b[n];
         const double *rf = blob + T.node_rf[n] + (e - T.node_zl[n]);
-        const double *v = vs + int64_t(T.node_sep[n]) * MC + cj;
+        const double *v = vs + int64_t(T.node_sep[n]) * LD + cj;
         double acc[8];
         const int32_t o0 = T.out_c0[e], o1 = T.out_c1[e];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           acc[j] = 0.0;
-          if (o0 >= 0) acc[j] += zl[o0 * MC + cj + j];
-          if (o1 >= 0) acc[j] += zl[o1 * MC + cj + j];
+          if (o0 >= 0) acc[j] += zl[o0 * LD + cj + j];
+          if (o1 >= 0) acc[j] += zl[o1 * LD + cj + j];
         }
         for (int i = 0; i < s; ++i) {
           const double r = rf[i * b];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += r * v[i * MC + j];
+          for (int j = 0; j < 8; ++j) acc[j] += r * v[i * LD + j];
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) zl[e * MC + cj + j] = acc[j];
+        for (int j = 0; j < 8; ++j) zl[e * LD + cj + j] = acc[j];
       }
       __syncthreads();
     }
@@ -196,13 +227,13 @@ __global__ void __launch_bounds__(256) k_wide_subtree_forward(SubtreeArgs a, int
       for (int l = rt; l < T.n_int; l += RT) {
         const int64_t d = subtree_dof(a, in, T.var_code[l]);
         double2 *dst = reinterpret_cast<double2 *>(a.x + d * MW + c0 + cj);
-        const double2 *src = reinterpret_cast<const double2 *>(vs + l * MC + cj);
+        const double2 *src = reinterpret_cast<const double2 *>(vs + l * LD + cj);
 #pragma unroll
         for (int h = 0; h < 4; ++h) dst[h] = src[h];
       }
       for (int q = rt; q < T.n_rootb; q += RT) {
         double2 *dst = reinterpret_cast<double2 *>(a.z + (in.z_root + q) * MW + c0 + cj);
-        const double2 *src = reinterpret_cast<const double2 *>(zl + (zr + q) * MC + cj);
+        const double2 *src = reinterpret_cast<const double2 *>(zl + (zr + q) * LD + cj);
 #pragma unroll
         for (int h = 0; h < 4; ++h) dst[h] = src[h];
       }
@@ -213,15 +244,15 @@ __global__ void __launch_bounds__(256) k_wide_subtree_forward(SubtreeArgs a, int
 
 template <int MC>
 __global__ void __launch_bounds__(256) k_wide_subtree_backward(SubtreeArgs a, int32_t MW) {
-  constexpr int CG = MC / 8, RT = 256 / CG;
+  constexpr int CG = MC / 8, RT = 256 / CG, LD = MC + 2;
   extern __shared__ __align__(16) double sm[];
   const InstanceDev in = a.inst[blockIdx.x];
   const TemplateDev T = a.tmpl[in.tmpl];
   uint64_t *bar = reinterpret_cast<uint64_t *>(sm);
   double *blob = sm + 2;
   double *zs = blob + T.rb_size;            // accumulated right-hand sides of the interior variables
-  double *xs = zs + int64_t(T.n_int) * MC;  // solution: [interior | root boundary]
-  const int tid = threadIdx.x, cg = tid % CG, rt = tid / CG, cj = cg * 8;
+  double *xs = zs + int64_t(T.n_int) * LD;  // solution: [interior | root boundary]
+  const int tid = threadIdx.x, rt = tid % RT, cg = tid / RT, cj = cg * 8;
   if (tid == 0) mbar_init(bar);
   __syncthreads();
   if (tid == 0) bulk_load_start(blob, a.R + in.rb_base, uint32_t(T.rb_size) * 8u, bar);
@@ -231,7 +262,7 @@ __global__ void __launch_bounds__(256) k_wide_subtree_backward(SubtreeArgs a, in
     for (int l = rt; l < T.n_int + T.n_rootb; l += RT) {
       const int64_t d = subtree_dof(a, in, l < T.n_int ? T.var_code[l] : T.rootb_code[l - T.n_int]);
       const double2 *src = reinterpret_cast<const double2 *>(a.x + d * MW + c0 + cj);
-      double2 *dst = reinterpret_cast<double2 *>((l < T.n_int ? zs + l * MC : xs + l * MC) + cj);
+      double2 *dst = reinterpret_cast<double2 *>((l < T.n_int ? zs + l * LD : xs + l * LD) + cj);
 #pragma unroll
       for (int h = 0; h < 4; ++h) dst[h] = live ? src[h] : make_double2(0.0, 0.0);
     }
@@ -249,17 +280,17 @@ __global__ void __launch_bounds__(256) k_wide_subtree_backward(SubtreeArgs a, in
         for (int p = 0; p < s; ++p) {
           const double r = rb[p * s];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += r * zs[(sep0 + p) * MC + cj + j];
+          for (int j = 0; j < 8; ++j) acc[j] += r * zs[(sep0 + p) * LD + cj + j];
         }
         rb += s * s;
         for (int q = 0; q < b; ++q) {
           const double r = rb[q * s];
           const int32_t l = bv[q];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += r * xs[l * MC + cj + j];
+          for (int j = 0; j < 8; ++j) acc[j] += r * xs[l * LD + cj + j];
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) xs[e * MC + cj + j] = acc[j];
+        for (int j = 0; j < 8; ++j) xs[e * LD + cj + j] = acc[j];
       }
       __syncthreads();
     }
@@ -267,7 +298,7 @@ __global__ void __launch_bounds__(256) k_wide_subtree_backward(SubtreeArgs a, in
       for (int l = rt; l < T.n_int; l += RT) {
         const int64_t d = subtree_dof(a, in, T.var_code[l]);
         double2 *dst = reinterpret_cast<double2 *>(a.x + d * MW + c0 + cj);
-        const double2 *src = reinterpret_cast<const double2 *>(xs + l * MC + cj);
+        const double2 *src = reinterpret_cast<const double2 *>(xs + l * LD + cj);
 #pragma unroll
         for (int h = 0; h < 4; ++h) dst[h] = src[h];
       }

@@ -34,6 +34,8 @@ void launch_wide_add(const WideStep &a, const int64_t *lvl_rp, const int32_t *ro
 // ptil -= M^-1 K_pu x ; trace[level][t][:] = x[tr_dof[t]][:]
 void launch_wide_update(const WideStep &a, const int32_t *tr_dof, int32_t n_tr, double *trace, cudaStream_t st);
 void launch_wide_next_level(int32_t *state, cudaStream_t st);
+// *out = max(*out, bits of max |v|): zero *out first; the bit pattern of a non-negative double orders like the value
+void launch_absmax(int64_t n, const double *v, unsigned long long *out, cudaStream_t st);
 
 struct WideRow {
   int32_t node, p;

@@ -107,6 +107,26 @@ def test_basis_operator_checkerboards():
     eng.close()
 
 
+def test_basis_passes_stop_when_the_response_has_died_out():
+    """8x8 subdomains of size 1/8: the slowest mode of a star problem decays by 1/(1 + 2 pi^2 dt / L^2) per step, so the
+    response to first-slab data falls below 1e-18 of its peak long before the final time; the remaining steps are
+    skipped and the Toeplitz sums stop at the last delay that carries data -- same operator to round-off."""
+    prm = default_params(1)
+    mesh = [[8, 8, 32] if ((r % 8) + (r // 8)) % 2 == 0 else [4, 4, 16] for r in range(64)]
+    prob = make_problem(prm, n_sub=64, mesh=mesh, mortar=[2, 2, 8])
+    q = np.random.default_rng(12).standard_normal(prob.n_iface)
+    ref = prob.apply_S(q)
+    eng = _basis_engine(prob)
+    assert 1 <= eng.stat("basis_delays") < 8
+    assert eng.stat("basis_steps") < eng.stat("basis_passes") // 2 * (32 + 16)
+    assert rel_l2(eng.apply(q), ref) < TOL
+    eng.close()
+    eng = _basis_engine(prob, {"basis_drop_tol": 0})  # switched off: all delays, all steps
+    assert eng.stat("basis_delays") == 8
+    assert rel_l2(eng.apply(q), ref) < TOL
+    eng.close()
+
+
 def test_basis_operator_with_permuted_dofs_and_neumann_sides():
     prm = default_params(1, 2)
     prob = make_problem(prm, 1)
