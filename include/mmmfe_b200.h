@@ -242,6 +242,9 @@ int mmmfe_measure_fp64_tensor_tflops(int device, double *tflops);
  * sizes = {n_nodes, idx_len, src_len, r_total, z_total, n_heights}.
  * node_table: n_nodes x 8 int32 = {s, b, child0, child1, height, nsplit, ldr, parent};
  * offsets:    n_nodes x 4 int64 = {idx_off, src_off, r_off, z_off}.                                            */
+/* Device milliseconds of ONE block-Toeplitz product of all local subdomains (the kernel of an operator application on
+ * the multiscale basis; exchange and Arnoldi excluded), averaged over `repeat` back-to-back launches.               */
+int mmmfe_profile_basis_apply(mmmfe_ctx *ctx, int32_t repeat, double *ms_per_launch);
 /* The multiscale-basis operator of a local subdomain's factor group: info = {mortar time slabs m_t, rows = columns
  * P_tot, leading dimension ldt, slots, slot of side 0..3 (-1: none), first row/column of side 0..3 (-1)}; t_out (may be
  * NULL) receives T[d][row][ldt], d = 0..m_t-1: signed mortar response on `row` d slabs after the basis function `col`. */

@@ -61,6 +61,9 @@ typedef struct {
   /* converged solve after the fixed-iteration timing (also_solve)                                                     */
   int32_t solve_iterations, solve_converged;
   double t_solve_gmres, solve_final_residual;
+  /* operator on the multiscale basis (profile != 0): one block-Toeplitz product of all local subdomains              */
+  double toeplitz_ms, toeplitz_gflop, toeplitz_mbytes;
+  int64_t basis_steps, basis_delays, basis_mw, toeplitz_tiles;
 } mmmfe_host_report;
 
 void mmmfe_host_default_options(mmmfe_host_options *opt);

@@ -88,6 +88,7 @@ def load_engine():
         "mmmfe_profile_step": (ctypes.c_int, [vp, c_f64p, c_f64p, c_i64p]),
         "mmmfe_debug_get_factor": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p, ctypes.c_int64]),
         "mmmfe_debug_get_basis": (ctypes.c_int, [vp, ctypes.c_int32, c_i64p, c_f64p, ctypes.c_int64]),
+        "mmmfe_profile_basis_apply": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p]),
         "mmmfe_profile_sweeps": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p, c_f64p, c_i32p, c_i32p]),
         "mmmfe_stat": (ctypes.c_int64, [vp, ctypes.c_char_p]),
         "mmmfe_profile_sweep_cycles": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p]),
@@ -439,7 +440,10 @@ class HostReport(ctypes.Structure):
                 ("t_basis", ctypes.c_double), ("basis_gflop", ctypes.c_double), ("basis_bytes", ctypes.c_double),
                 ("basis_columns", ctypes.c_int64), ("solve_iterations", ctypes.c_int32),
                 ("solve_converged", ctypes.c_int32), ("t_solve_gmres", ctypes.c_double),
-                ("solve_final_residual", ctypes.c_double)]
+                ("solve_final_residual", ctypes.c_double), ("toeplitz_ms", ctypes.c_double),
+                ("toeplitz_gflop", ctypes.c_double), ("toeplitz_mbytes", ctypes.c_double),
+                ("basis_steps", ctypes.c_int64), ("basis_delays", ctypes.c_int64), ("basis_mw", ctypes.c_int64),
+                ("toeplitz_tiles", ctypes.c_int64)]
 
 
 _host = None

@@ -2561,6 +2561,30 @@ int mmmfe_profile_sweeps(mmmfe_ctx *c, int32_t cap, double *ms, double *bytes_pe
   });
 }
 
+int mmmfe_profile_basis_apply(mmmfe_ctx *c, int32_t repeat, double *ms_per_launch) {
+  if (!c || repeat < 1 || !ms_per_launch) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, {
+    if (!c->use_basis) fail(MMMFE_E_INVALID, "the multiscale-basis operator is not in use (%s)", c->basis_note.c_str());
+    cudaStream_t st = c->stream;
+    auto once = [&]() {
+      if (c->toep_parts <= 1) {
+        launch_toeplitz_apply(c->toep_bm, c->toep_probs.p, c->toep_tiles.p, c->n_toep_tiles, c->qin.p, c->send.p, 0, st);
+      } else {
+        launch_toeplitz_apply(c->toep_bm, c->toep_probs.p, c->toep_tiles.p, c->n_toep_tiles, c->qin.p, c->toep_part_buf.p, c->n_iface, st);
+        launch_sum_parts(c->n_iface, c->toep_part_buf.p, c->n_iface, c->toep_parts, c->send.p, st);
+      }
+    };
+    once();  // warm-up
+    CUDA_CHECK(cudaEventRecord(c->ev_t0, st));
+    for (int i = 0; i < repeat; ++i) once();
+    CUDA_CHECK(cudaEventRecord(c->ev_t1, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    float t = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&t, c->ev_t0, c->ev_t1));
+    *ms_per_launch = double(t) / repeat;
+  });
+}
+
 int mmmfe_debug_get_basis(mmmfe_ctx *c, int32_t li, int64_t info[12], double *t_out, int64_t capacity) {
   if (!c || li < 0 || li >= int32_t(c->subs.size()) || !info) return MMMFE_E_INVALID;
   MMMFE_TRY(c, {

@@ -78,6 +78,8 @@ int mmmfe_host_run(const char *parameter_file, const mmmfe_host_options *opt, mm
         d.basis_bytes = r.basis_bytes; d.basis_columns = r.basis_columns;
         d.solve_iterations = r.solve_iterations; d.solve_converged = r.solve_converged;
         d.t_solve_gmres = r.t_solve_gmres; d.solve_final_residual = r.solve_final_residual;
+        d.toeplitz_ms = r.toeplitz_ms; d.toeplitz_gflop = r.toeplitz_gflop; d.toeplitz_mbytes = r.toeplitz_mbytes;
+        d.basis_steps = r.basis_steps; d.basis_delays = r.basis_delays; d.basis_mw = r.basis_mw; d.toeplitz_tiles = r.toeplitz_tiles;
       }
       ++n;
     }

@@ -798,6 +798,10 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
     rep.basis_bytes = double(mmmfe_stat(ctx, "basis_mbytes")) * 1e6;
     rep.basis_columns = mmmfe_stat(ctx, "basis_columns");
     rep.basis_shared_by = int(std::max<long long>(1, mmmfe_stat(ctx, "basis_shared_by")));
+    rep.basis_steps = mmmfe_stat(ctx, "basis_steps"); rep.basis_delays = mmmfe_stat(ctx, "basis_delays");
+    rep.basis_mw = mmmfe_stat(ctx, "basis_mw"); rep.toeplitz_tiles = mmmfe_stat(ctx, "toeplitz_tiles");
+    rep.toeplitz_gflop = double(mmmfe_stat(ctx, "toeplitz_mflop")) * 1e-3;
+    rep.toeplitz_mbytes = double(mmmfe_stat(ctx, "toeplitz_mbytes"));
     for (auto &sp : subs) { rep.dof_steps += (long long)sp->n * sp->nt; sp->matrix = Csr(); }
     // ---- bar problems ----
     t0 = clk::now();
@@ -843,6 +847,8 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
     }
     if (control.apply_repeat > 0)
       check(ctx, mmmfe_apply_interface_operator_device(ctx, control.apply_repeat, &control.apply_ms), "apply");
+    if (control.profile && rep.basis_operator)
+      check(ctx, mmmfe_profile_basis_apply(ctx, 20, &rep.toeplitz_ms), "profile basis apply");
     if (control.profile) {
       check(ctx, mmmfe_profile_step(ctx, rep.prof_ms, rep.prof_bytes, (int64_t *)rep.prof_launches), "profile");
       int32_t nsw = 0;

@@ -53,6 +53,8 @@ struct CycleReport {
   // converged solve after a fixed-iteration timing run (RunControl::also_solve)
   int solve_iterations = 0, solve_converged = 0;
   double t_solve_gmres = 0.0, solve_final_residual = 0.0;
+  double toeplitz_ms = 0.0, toeplitz_gflop = 0.0, toeplitz_mbytes = 0.0;
+  long long basis_steps = 0, basis_delays = 0, basis_mw = 0, toeplitz_tiles = 0;
   long long tune_rel_diff_e18 = -1;  // set-up cross-check of the two star-sweep implementations (relative l2 * 1e18)
   // multiscale-basis (time-Toeplitz) operator, when the engine built it
   int basis_operator = 0, basis_shared_by = 1;
