@@ -174,6 +174,8 @@ struct Batch {
   cudaEvent_t done = nullptr;
   cudaGraphExec_t graph_star = nullptr;
   long long graph_kernels = 0;
+  DevBuf<int32_t> level_dev;  // time level of the step graphs of the bar and final sweeps
+  cudaGraphExec_t graph_step = nullptr;
   StepArgs step{};
   // persistent sweep path
   bool sweep = false;
@@ -847,24 +849,59 @@ static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> 
                              const std::vector<double> &tr_sign);
 static void run_sweep_kernel(mmmfe_ctx *c, Batch &b, cudaStream_t st);
 
-static void enqueue_sweep(mmmfe_ctx *c, Batch &b, SweepMode mode) {
+// one time step of a batch on the per-level kernels; lvl < 0: the kernels read the level from b.level_dev (step graph)
+static void enqueue_step(mmmfe_ctx *c, Batch &b, SweepMode mode, int lvl) {
   const Factor &F = *b.factor;
   cudaStream_t st = b.stream;
   const bool bar = mode == SWEEP_BAR;
   const bool with_hist = (bar && c->keep_history) || (mode == SWEEP_FINAL && c->keep_history);
-  launch_init_ptil(b.step, bar ? b.p0_ptr.p : nullptr, bar ? b.src_ptr.p : nullptr, st);
-  for (int lvl = 0; lvl < b.nt; ++lvl) {
-    launch_build_rhs(b.step, bar ? nullptr : c->lam_bar.p, lvl, st);
-    if (bar)
-      for (int j = 0; j < int(b.members.size()); ++j) {
-        const Sub &sd = *c->subs[b.members[j]];
-        launch_add_sparse(b.x.p, b.M, j, sd.fr_dofs.p, sd.fr_vals.p + int64_t(lvl) * sd.n_fr, sd.n_fr, st);
-      }
-    run_solve(F, b.M, b.x.p, b.z.p, st);
-    const bool has_next = bar && lvl + 1 < b.nt;
-    launch_update(b.step, c->trace.p, lvl, has_next ? b.src_ptr.p : nullptr, F.np, with_hist ? b.hist_ptr.p : nullptr,
-                  int64_t(F.nf) + F.np, mode == SWEEP_FINAL ? 1 : 0, st);
+  StepArgs sa = b.step;
+  const bool from_dev = lvl < 0;
+  if (from_dev) { sa.level_dev = b.level_dev.p; lvl = 0; }
+  launch_build_rhs(sa, bar ? nullptr : c->lam_bar.p, lvl, st);
+  if (bar)
+    for (int j = 0; j < int(b.members.size()); ++j) {
+      const Sub &sd = *c->subs[b.members[j]];
+      launch_add_sparse(b.x.p, b.M, j, sd.fr_dofs.p, from_dev ? sd.fr_vals.p : sd.fr_vals.p + int64_t(lvl) * sd.n_fr, sd.n_fr, st,
+                        from_dev ? b.level_dev.p : nullptr);
+    }
+  run_solve(F, b.M, b.x.p, b.z.p, st);
+  const bool has_next = bar && (from_dev || lvl + 1 < b.nt);
+  launch_update(sa, c->trace.p, lvl, has_next ? b.src_ptr.p : nullptr, F.np, with_hist ? b.hist_ptr.p : nullptr,
+                int64_t(F.nf) + F.np, mode == SWEEP_FINAL ? 1 : 0, st, from_dev ? b.nt : 0);
+}
+
+static void enqueue_sweep(mmmfe_ctx *c, Batch &b, SweepMode mode) {
+  const bool bar = mode == SWEEP_BAR;
+  launch_init_ptil(b.step, bar ? b.p0_ptr.p : nullptr, bar ? b.src_ptr.p : nullptr, b.stream);
+  for (int lvl = 0; lvl < b.nt; ++lvl) enqueue_step(c, b, mode, lvl);
+}
+
+// bar and final sweeps: ONE step captured as a CUDA graph (the level comes from a device scalar) and replayed nt times
+// -- a sweep of 512 steps is ~15 000 kernel launches otherwise, bound by the launch rate of the host thread
+static void enqueue_sweep_by_step_graph(mmmfe_ctx *c, Batch &b, SweepMode mode) {
+  const bool bar = mode == SWEEP_BAR;
+  cudaStream_t st = b.stream;
+  if (!b.level_dev.p) b.level_dev.alloc(2);
+  if (b.graph_step) {  // of an earlier sweep (its pointers may be stale): that sweep has long finished
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaGraphExecDestroy(b.graph_step);
+    b.graph_step = nullptr;
   }
+  cudaGraph_t g = nullptr;
+  const long long before = launch_counter();
+  CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  enqueue_step(c, b, mode, -1);
+  launch_wide_next_level(b.level_dev.p, st);
+  CUDA_CHECK(cudaStreamEndCapture(st, &g));
+  const long long per_step = launch_counter() - before;
+  launch_counter_add(-per_step);
+  CUDA_CHECK(cudaGraphInstantiate(&b.graph_step, g, 0));
+  CUDA_CHECK(cudaGraphDestroy(g));
+  CUDA_CHECK(cudaMemsetAsync(b.level_dev.p, 0, 2 * sizeof(int32_t), st));
+  launch_init_ptil(b.step, bar ? b.p0_ptr.p : nullptr, bar ? b.src_ptr.p : nullptr, st);
+  for (int lvl = 0; lvl < b.nt; ++lvl) CUDA_CHECK(cudaGraphLaunch(b.graph_step, st));
+  launch_counter_add(per_step * b.nt);
 }
 
 static void run_star_sweeps(mmmfe_ctx *c, SweepMode mode) {
@@ -899,6 +936,8 @@ static void run_star_sweeps(mmmfe_ctx *c, SweepMode mode) {
       }
       CUDA_CHECK(cudaGraphLaunch(b.graph_star, b.stream));
       launch_counter_add(b.graph_kernels);
+    } else if (c->use_graphs && mode != SWEEP_STAR && b.nt >= 8) {
+      enqueue_sweep_by_step_graph(c, b, mode);
     } else {
       enqueue_sweep(c, b, mode);
     }
@@ -1699,7 +1738,7 @@ static void setup(mmmfe_ctx *c) {
       CUDA_CHECK(cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming));
       b->step = StepArgs{b->M, F.nf, F.np, F.kup.rp.p, F.kup.col.p, F.kup.val.p, F.kpu.rp.p, F.kpu.col.p,
                          F.kpu.val.p, F.minv.p, b->x.p, b->ptil.p, b->n_tr, b->tr_dof.p, b->tr_mem.p,
-                         b->tr_stride.p, b->tr_base.p, b->tr_sign.p, b->iface_q.p};
+                         b->tr_stride.p, b->tr_base.p, b->tr_sign.p, b->iface_q.p, nullptr};
       if (c->use_sweep) plan_batch_sweep(c, *b, iface_q, tr_base, tr_stride, tr_sign);
       c->batches.push_back(std::move(b));
     }
@@ -2016,6 +2055,7 @@ int mmmfe_destroy(mmmfe_ctx *c) {
   cudaDeviceSynchronize();
   for (auto &b : c->batches) {
     if (b->graph_star) cudaGraphExecDestroy(b->graph_star);
+    if (b->graph_step) cudaGraphExecDestroy(b->graph_step);
     if (b->done) cudaEventDestroy(b->done);
     if (b->stream) cudaStreamDestroy(b->stream);
   }
@@ -2354,7 +2394,7 @@ int mmmfe_solve_saddle(mmmfe_ctx *c, int32_t li, const double *rhs, double *x) {
     DevBuf<double *> d_histp;
     d_srcp.upload(srcp); d_histp.upload(histp);
     StepArgs a{1, F.nf, F.np, F.kup.rp.p, F.kup.col.p, F.kup.val.p, F.kpu.rp.p, F.kpu.col.p, F.kpu.val.p,
-               F.minv.p, xv.p, pt.p, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+               F.minv.p, xv.p, pt.p, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     launch_init_ptil(a, nullptr, d_srcp.p, st);
     launch_build_rhs(a, nullptr, 0, st);
     launch_add_sparse(xv.p, 1, 0, dofs.p, d_rhs.p, F.nf, st);

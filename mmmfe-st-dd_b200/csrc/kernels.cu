@@ -650,6 +650,7 @@ void launch_subtree_backward(int M, const SubtreeArgs &a, int32_t n_inst, size_t
 __global__ void __launch_bounds__(256) k_build_rhs(StepArgs a, const double *__restrict__ lam_bar, int32_t level) {
   const int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
   if (e >= a.n_flux) return;
+  if (a.level_dev) level = *a.level_dev;
   const int64_t k0 = a.kup_rp[e], k1 = a.kup_rp[e + 1];
   for (int j = 0; j < a.M; ++j) {
     double acc = 0.0;
@@ -669,22 +670,27 @@ void launch_build_rhs(const StepArgs &a, const double *lam_bar, int32_t level, c
 
 __global__ void __launch_bounds__(256) k_add_sparse(double *x, int32_t M, int32_t member,
                                                     const int32_t *__restrict__ dofs,
-                                                    const double *__restrict__ vals, int32_t n) {
+                                                    const double *__restrict__ vals, int32_t n,
+                                                    const int32_t *__restrict__ level_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) x[int64_t(dofs[i]) * M + member] += vals[i];
+  if (i >= n) return;
+  if (level_dev) vals += int64_t(*level_dev) * n;
+  x[int64_t(dofs[i]) * M + member] += vals[i];
 }
 
 void launch_add_sparse(double *x, int32_t M, int32_t member, const int32_t *dofs, const double *vals, int32_t n,
-                       cudaStream_t st) {
+                       cudaStream_t st, const int32_t *level_dev) {
   if (n <= 0) return;
-  k_add_sparse<<<(n + 255) / 256, 256, 0, st>>>(x, M, member, dofs, vals, n);
+  k_add_sparse<<<(n + 255) / 256, 256, 0, st>>>(x, M, member, dofs, vals, n, level_dev);
   launch_counter_add(1);
 }
 
 __global__ void __launch_bounds__(256)
 k_update(StepArgs a, double *__restrict__ trace, int32_t level, const double *const *__restrict__ src_next,
-         int64_t src_stride, double *const *__restrict__ hist, int64_t hist_level_stride, int add_hist) {
+         int64_t src_stride, double *const *__restrict__ hist, int64_t hist_level_stride, int add_hist, int32_t n_levels) {
   int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (a.level_dev) level = *a.level_dev;
+  if (n_levels > 0 && level + 1 >= n_levels) src_next = nullptr;
   if (t < a.n_pressure) {
     const int64_t c = t;
     const int64_t k0 = a.kpu_rp[c], k1 = a.kpu_rp[c + 1];
@@ -721,10 +727,10 @@ k_update(StepArgs a, double *__restrict__ trace, int32_t level, const double *co
 
 void launch_update(const StepArgs &a, double *trace, int32_t level, const double *const *src_next,
                    int64_t src_stride, double *const *hist, int64_t hist_level_stride, int add_hist,
-                   cudaStream_t st) {
+                   cudaStream_t st, int32_t n_levels) {
   const int64_t n = a.n_pressure + a.n_tr + (hist ? a.n_flux : 0);
   k_update<<<unsigned((n + 255) / 256), 256, 0, st>>>(a, trace, level, src_next, src_stride, hist,
-                                                      hist_level_stride, add_hist);
+                                                      hist_level_stride, add_hist, n_levels);
   launch_counter_add(1);
 }
 

@@ -123,16 +123,20 @@ struct StepArgs {
   const int64_t *tr_base;
   const double *tr_sign;
   const int32_t *iface_q;  // [n_flux][M] -> q or -1
+  // when set, the kernels take the time level from this device scalar instead of their `level` argument: one time
+  // step can then be captured as a static CUDA graph and replayed for every level (bar and final sweeps)
+  const int32_t *level_dev;
 };
 // x = - K_up ptil - sign * lam_bar(level)      (assemble_rhs_star/bar after pressure elimination)
 void launch_build_rhs(const StepArgs &a, const double *lam_bar, int32_t level, cudaStream_t st);
 // x[dofs[i]][member] += vals[i]
 void launch_add_sparse(double *x, int32_t M, int32_t member, const int32_t *dofs, const double *vals, int32_t n,
-                       cudaStream_t st);
+                       cudaStream_t st, const int32_t *level_dev = nullptr);  // level_dev: vals += *level_dev * n
 // p = ptil - M^-1 K_pu x ; ptil_next = p + M^-1 src_next ; trace(level) = x[interface dofs] ; optional history
+// n_levels > 0: src_next is only read while level + 1 < n_levels (graph replays pass it for every level)
 void launch_update(const StepArgs &a, double *trace, int32_t level, const double *const *src_next,
                    int64_t src_stride, double *const *hist, int64_t hist_level_stride, int add_hist,
-                   cudaStream_t st);
+                   cudaStream_t st, int32_t n_levels = 0);
 void launch_init_ptil(const StepArgs &a, const double *const *p0, const double *const *src0, cudaStream_t st);
 
 // ---- interface vector ------------------------------------------------------------------------------------------
