@@ -591,12 +591,22 @@ static std::vector<int32_t> subtree_classes(const NdTree &tr, const HostCsr &S, 
 
 static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax, double sm_share) {
   const auto t0 = std::chrono::steady_clock::now();
+  const bool prof = std::getenv("MMMFE_SETUP_PROFILE") != nullptr;
+  auto t_last = t0;
+  auto lap = [&](const char *what) {
+    if (!prof) return;
+    cudaDeviceSynchronize();
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[setup profile] %dx%d %-28s %8.1f ms\n", sd.nx, sd.ny, what, std::chrono::duration<double>(now - t_last).count() * 1e3);
+    t_last = now;
+  };
   auto F = std::make_shared<Factor>();
   F->sm_share = sm_share;
   F->nx = sd.nx; F->ny = sd.ny; F->nf = sd.nf; F->np = sd.np;
   HostCsr S, kup, kpu;
   std::vector<double> minv;
   build_schur(sd, S, kup, kpu, minv);
+  lap("schur complement (host)");
   F->kup.upload(kup); F->kpu.upload(kpu); F->minv.upload(minv);
   NdTree &tr = F->tree;
   const size_t smem_limit = subtree_smem_limit();
@@ -655,6 +665,7 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax, 
       cells = c->subtree_cells * 2;
     }
   }
+  lap("tree + sweep plan (host)");
   const int32_t nn = int32_t(tr.nodes.size());
   // user numbering of the front variables
   std::vector<int32_t> idx_user(tr.idx.size());
@@ -711,6 +722,7 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax, 
     F->inst_dev.upload(id);
   }
 
+  lap("descriptor uploads");
   // ---- numeric phase ----
   DevCsr dS;
   dS.upload(S);
@@ -776,6 +788,7 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax, 
     run_gemm_batch(c, gG);
     run_gemm_batch(c, gF);
   }
+  lap("numeric factorisation");
   int32_t failed = 0;
   CUDA_CHECK(cudaMemcpy(&failed, c->d_fail.p, sizeof(int32_t), cudaMemcpyDeviceToHost));
   if (failed) fail(MMMFE_E_NUMERIC, "non-positive pivot in a front: the flux Schur complement is not SPD");
@@ -810,7 +823,9 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax, 
   }
   F->solve_bytes = bytes;
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  lap("solve work lists");
   if (sweep_planned) build_sweep_factor(c, *F, minv);
+  lap("sweep factor repack");
   F->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return F;
 }

@@ -15,6 +15,8 @@
 #include <stdexcept>
 #include <thread>
 
+#include <omp.h>
+
 #include "mmmfe_b200.h"
 
 #ifndef MMMFE_DATA_HEADER
@@ -696,6 +698,17 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
   // every rank derives the same ownership table, so this fails on all ranks at once (no rank is left in a collective)
   if (world > int(n_sub)) throw std::runtime_error("more ranks than subdomains: launch at most one process per subdomain");
   const int qdegree = int(quad_degree);
+  // The ranks of one node share its cores: every rank takes its share of them for the host-side loops (matrix and
+  // projector tables, right-hand-side data, error norms).  torchrun exports OMP_NUM_THREADS=1 to its workers, which
+  // made the bar data of two ranks 6x slower than that of one (30 s against 5 s): with several ranks the share is set
+  // explicitly; $MMMFE_HOST_THREADS overrides.
+  if (const char *ht = std::getenv("MMMFE_HOST_THREADS")) {
+    omp_set_num_threads(std::max(1, std::atoi(ht)));
+  } else if (world > 1) {
+    int local_world = world;
+    if (const char *lw = std::getenv("LOCAL_WORLD_SIZE")) local_world = std::max(1, std::atoi(lw));
+    omp_set_num_threads(std::max(1, omp_get_num_procs() / local_world));
+  }
   unsigned n0, n1;
   find_divisors(n_sub, n0, n1);
   std::vector<std::vector<int>> reps = reps_st;
