@@ -52,13 +52,19 @@ def main():
         "checker_4x4_sweep_m4": dict(mesh=[[64, 64, 8] if ((r % 4) + (r // 4)) % 2 == 0 else [32, 32, 4] for r in range(16)],
                                      mortar=[8, 8, 2], kw=dict(engine_options=SWEEP_ON), sweep=True),
     }
+    # BASELINE configs[3] scaled down: 8x8 checkerboard, quadratic mortar (every centre Gauss point a tie), multiscale
+    # basis shared by all ranks when every rank holds both colours
+    cases["checker_8x8_quadratic"] = dict(mesh=[[8, 8, 16] if ((r % 8) + (r // 8)) % 2 == 0 else [4, 4, 8] for r in range(64)],
+                                          mortar=[2, 2, 4], kw=dict(mortar_degree=2), k=2)
+    if world > 4:  # the 2x2 cases have fewer subdomains than ranks
+        cases = {n: c for n, c in cases.items() if "mesh" in c and len(c["mesh"]) >= world}
     results, ok = {}, True
     for name, c in cases.items():
         if "file" in c:
             pfile = c["file"]
         else:
             pfile = os.path.join(tmp, f"{name}_{rank}.txt")
-            pkg().write_parameter_file(pfile, c["mesh"], c["mortar"])
+            pkg().write_parameter_file(pfile, c["mesh"], c["mortar"], mortar_degree=c.get("k", 1))
         nccl_id = unique_id(rank)
         reps, res, lam = pkg().host_run(pfile, nccl_id=nccl_id, rank=rank, world=world, device=local, verbose=0,
                                         write_output=0, **c["kw"])
@@ -79,6 +85,8 @@ def main():
         prm = mo.parse_parameter_file(pfile)
         if "num_refinement" in c["kw"]:
             prm.num_refinement = c["kw"]["num_refinement"]
+        if "mortar_degree" in c["kw"]:
+            prm.mortar_degree = c["kw"]["mortar_degree"]
         n_sub = len(prm.mesh) - 1
         meshes = mo.refined_meshes(prm, n_sub)
         for idx, msh in enumerate(meshes):  # the last cycle is compared

@@ -134,5 +134,5 @@ def test_two_gpus_reproduce_the_oracle(tmp_path):
     run = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=os.path.join(ROOT, "tests"))
     assert run.returncode == 0, run.stdout[-2000:] + run.stderr[-2000:]
     res = json.load(open(out))
-    assert all(v["ok"] for v in res.values()) and len(res) == 4
+    assert all(v["ok"] for v in res.values()) and len(res) == 5
     assert res["nonmatching_2x2_sweep"]["sweep_batches"] > 0 and res["checker_4x4_sweep_m4"]["sweep_batches"] > 0
