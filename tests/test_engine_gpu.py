@@ -305,3 +305,37 @@ def test_errors_are_reported_not_swallowed():
     with pytest.raises(Exception, match="c0"):
         eng.setup()
     eng.close()
+
+
+class _VariableK(mo.DataDefault):
+    """A genuinely variable, full, SPD K^-1(x, y): the KInverse::value_list API of inc/data.h:29-62 that no shipped data
+    file exercises (all ten have K = I, quirk Q8)."""
+
+    def k_inverse(self, x, y):
+        k00 = 1.0 + 0.5 * np.sin(3 * x) * np.cos(2 * y)
+        k11 = 2.0 + np.cos(x + y)
+        k01 = 0.3 * np.sin(5 * x * y)
+        return k00, k01, k01, k11
+
+
+@pytest.mark.parametrize("options", [{"use_sweep": 1, "sweep_autotune": 0, "sweep_crosscheck": 1, "subtree_cells": 64},
+                                     {"use_sweep": 0},
+                                     {"operator": 1, "mortar_time_slabs": 2}])
+def test_variable_full_k_tensor(options):
+    """Non-identity, non-diagonal, space-dependent K^-1: x- and y-edges of a cell couple, no two subtree factor blobs
+    are equal (nothing to share), the flux Schur complement is still SPD.  Operator and a saddle solve vs the oracle."""
+    prm = default_params(1)
+    mesh = [[48, 48, 8], [24, 24, 4], [24, 24, 4], [48, 48, 8]]
+    prob = mo.Problem(prm, 4, mesh, [6, 6, 2], data=_VariableK(), keep_solution=True)
+    prob.setup()
+    eng = engine_from_oracle(prob, options=options)
+    eng.setup()
+    q = np.random.default_rng(77).standard_normal(prob.n_iface)
+    assert rel_l2(eng.apply(q), prob.apply_S(q)) < TOL
+    sd = prob.subs[0]
+    rhs = np.random.default_rng(78).standard_normal(sd.n)
+    rhs[sd.nf:] *= prm.c0 * sd.hx * sd.hy
+    ref = sd.lu.solve(rhs)
+    x = eng.solve_saddle(0, rhs)
+    assert rel_l2(x[:sd.nf], ref[:sd.nf]) < 1e-11 and rel_l2(x[sd.nf:], ref[sd.nf:]) < 1e-10
+    eng.close()
