@@ -25,7 +25,7 @@ if __name__ == "__main__":
     p = pkg.write_parameter_file(os.path.join(tmp, "parameter.txt"), mesh, mortar, mortar_degree=k, num_refinement=1)
     reps, res, _ = pkg.host_run(p, nccl_id=nccl_id, rank=rank, world=world, device=local, verbose=0, write_output=0,
                                 compute_errors=0, final_sweep=1, skip_fetch=1, fixed_iterations=3, warmup_iterations=1,
-                                also_solve=1, engine_options=opts, apply_repeat=10)
+                                also_solve=0 if os.environ.get("MMMFE_PROBE_NOSOLVE") else 1, engine_options=opts, apply_repeat=10)
     r = reps[0]
     keys = ["t_assemble", "t_factor", "t_bar_data", "t_bar", "t_gmres", "t_solve_gmres", "t_final", "solve_iterations",
             "solve_converged", "solve_final_residual", "gmres_device_ms", "sweep_batches", "interface_length",
