@@ -156,6 +156,12 @@ int64_t mmmfe_kernel_launches(const mmmfe_ctx *ctx);
  * (src/darcy_vtdd.cc:1203-1256).                                                                              */
 int mmmfe_bar_set_data(mmmfe_ctx *ctx, int32_t local_index, const double *p0, const double *src, int32_t n_fr,
                        const int32_t *fr_dofs, const double *fr_vals);
+/* The same, for callers that evaluate the data ON THE DEVICE (the host front-end compiles the inc/data.h function
+ * classes for the GPU, host/data_device.cu): the library allocates the three arrays (zero-filled), copies fr_dofs
+ * (HOST) and returns DEVICE pointers into its own buffers, laid out as above, for the caller's kernels to fill on
+ * the legacy default stream (or any stream it synchronises) before mmmfe_bar_sweep.  The library keeps ownership. */
+int mmmfe_bar_data_buffers(mmmfe_ctx *ctx, int32_t local_index, int32_t n_fr, const int32_t *fr_dofs,
+                           double **d_p0, double **d_src, double **d_fr_vals);
 int mmmfe_bar_sweep(mmmfe_ctx *ctx);
 
 /* ---- interface operator and GMRES ------------------------------------------------------------------------------ */
@@ -192,6 +198,9 @@ int mmmfe_gmres_solve(mmmfe_ctx *ctx, double tol, int32_t max_iter, mmmfe_gmres_
  * given local subdomain (user dof numbering) is written to HOST memory.                                        */
 int mmmfe_final_sweep(mmmfe_ctx *ctx);
 int mmmfe_get_solution(mmmfe_ctx *ctx, int32_t local_index, double *solution);
+/* DEVICE pointer to the same array (valid until the context is destroyed or the next bar sweep): error norms and
+ * the space-time output are computed from it without copying the solution to the host.                          */
+int mmmfe_solution_device(mmmfe_ctx *ctx, int32_t local_index, double **d_solution);
 /* Interface flux traces of the last star (or final) sweep of one side: [nt][n_side]. */
 int mmmfe_get_star_trace(mmmfe_ctx *ctx, int32_t local_index, int32_t side, double *trace);
 

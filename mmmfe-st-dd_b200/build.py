@@ -56,6 +56,50 @@ def build_engine(force=False, verbose=False):
     return LIB_ENGINE
 
 
+DATA_OBJ = os.path.join(HERE, "data_device.o")
+DATA_DIAG = ["-diag-suppress", "20012,20014,940,20011,20015,177"]
+
+
+def build_data_device(data_header, force=False):
+    """host/data_device.cu: the problem-data header (inc/data.h interface) compiled for the GPU.  A header that does
+    not compile for the device (helpers that are not members, exotic includes) is not an error: the object is then
+    built with MMMFE_NO_DEVICE_DATA and the front-end keeps its host loops.  Returns True when the device path is in."""
+    src = os.path.join(HOST, "data_device.cu")
+    deps = [src, os.path.join(HOST, "data_device.h"), data_header]
+    for d, _, fs in os.walk(os.path.join(HOST, "shim")):
+        deps += [os.path.join(d, f) for f in fs]
+    marker = DATA_OBJ + ".mode"
+    key = f"{data_header}"
+    if not force and not _newer(DATA_OBJ, deps) and os.path.exists(marker):
+        mode, old_key = (open(marker).read().split("\n") + [""])[:2]
+        if old_key == key:
+            return mode == "device"
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    base = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+            "-Xcompiler", "-fPIC", "-I", os.path.join(HOST, "shim"), "-I", HOST, "-I", os.path.join(ROOT, "include"),
+            f'-DMMMFE_DATA_HEADER="{data_header}"'] + DATA_DIAG + ["-c", src, "-o", DATA_OBJ + ".tmp"]
+    res = subprocess.run(base, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    mode = "device"
+    if res.returncode != 0:
+        sys.stderr.write("[build] the data header does not compile for the device; keeping the host loops:\n" +
+                         "\n".join(res.stdout.splitlines()[:12]) + "\n")
+        _run(base[:-4] + ["-DMMMFE_NO_DEVICE_DATA", "-c", src, "-o", DATA_OBJ + ".tmp"])
+        mode = "host"
+    os.replace(DATA_OBJ + ".tmp", DATA_OBJ)
+    with open(marker, "w") as f:
+        f.write(mode + "\n" + key)
+    return mode == "device"
+
+
+def _cuda_lib_dir():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    root = os.path.dirname(os.path.dirname(os.path.realpath(nvcc)))
+    for d in ("lib64", "targets/x86_64-linux/lib"):
+        if os.path.exists(os.path.join(root, d, "libcudart_static.a")):
+            return os.path.join(root, d)
+    return os.path.join(root, "lib64")
+
+
 def build_host(force=False):
     srcs = [os.path.join(HOST, f) for f in sorted(os.listdir(HOST)) if f.endswith(".cpp") and f != "darcy_main.cpp"] \
         if os.path.isdir(HOST) else []
@@ -68,10 +112,12 @@ def build_host(force=False):
     data_header = os.environ.get("MMMFE_DATA_HEADER", os.path.join(HOST, "data_default.h"))
     common = ["g++", "-O2", "-std=c++17", "-fPIC", "-fopenmp", "-I", os.path.join(ROOT, "include"),
               "-I", os.path.join(HOST, "shim"), "-I", HOST, f'-DMMMFE_DATA_HEADER="{data_header}"']
-    if force or _newer(LIB_HOST, deps + [LIB_ENGINE]):
+    build_data_device(data_header, force=force)
+    if force or _newer(LIB_HOST, deps + [LIB_ENGINE, DATA_OBJ]):
         build_engine()
-        _run(common + ["-shared", "-o", LIB_HOST] + srcs +
-             ["-L", HERE, "-lmmmfe_b200", f"-Wl,-rpath,{HERE}", "-Wl,-rpath,$ORIGIN"])
+        _run(common + ["-shared", "-o", LIB_HOST] + srcs + [DATA_OBJ] +
+             ["-L", HERE, "-lmmmfe_b200", "-L", _cuda_lib_dir(), "-lcudart_static", "-lrt", "-lpthread", "-ldl", "-lz",
+              f"-Wl,-rpath,{HERE}", "-Wl,-rpath,$ORIGIN"])
     main = os.path.join(HOST, "darcy_main.cpp")
     if os.path.exists(main) and (force or _newer(EXE, [main, LIB_HOST])):
         _run(common + ["-o", EXE, main, "-L", HERE, "-lmmmfe_host", "-lmmmfe_b200",

@@ -212,6 +212,7 @@ struct mmmfe_ctx {
   bool keep_history = true, use_graphs = true, use_sweep = true, sweep_evict_first = true;
   int leaf_cells = 8, subtree_cells = 256, sweep_chunk = 7168, sweep_ct = 256, sweep_ctas_per_sm = 1, sweep_groups = 1;
   bool sweep_autotune = true;
+  int tune_steps = 32;             // time levels of the set-up comparison of the two sweep implementations (0: all)
   bool sweep_crosscheck = false;  // with sweep_autotune = 0: still run both implementations once and compare their traces
   double tune_ms_sweep = 0.0, tune_ms_levels = 0.0, tune_rel_diff = -1.0;
   double sweep_min_fill = 1.75;
@@ -1769,18 +1770,36 @@ static void setup(mmmfe_ctx *c) {
   bool any_sweep = false;
   for (auto &b : c->batches) any_sweep |= b->sweep;
   if (any_sweep && (c->sweep_autotune || c->sweep_crosscheck)) {
+    // The comparison runs on the first tune_steps time levels only (every level walks the same entry lists and the
+    // same kernels, so both the check and the time ratio carry over): a full sweep of each implementation, twice,
+    // was 1.1 s of the set-up on configs[1].
     auto timed = [&](bool with_sweep) {
       std::vector<bool> keep;
-      for (auto &b : c->batches) { keep.push_back(b->sweep); b->sweep = b->sweep && with_sweep; }
+      std::vector<int> keep_nt;
+      for (auto &b : c->batches) {
+        keep.push_back(b->sweep); b->sweep = b->sweep && with_sweep;
+        keep_nt.push_back(b->nt);
+        if (c->tune_steps > 0) b->nt = std::min(b->nt, c->tune_steps);
+        b->sargs.n_steps = b->nt;
+      }
       float best = 0;
-      for (int rep = 0; rep < 2; ++rep) {  // the first pass of the per-level path captures its graphs
+      for (int rep = 0; rep < (with_sweep ? 1 : 2); ++rep) {  // the first pass of the per-level path captures its graphs
         CUDA_CHECK(cudaEventRecord(c->ev_t0, c->stream));
         run_star_sweeps(c, SWEEP_STAR);
         CUDA_CHECK(cudaEventRecord(c->ev_t1, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         CUDA_CHECK(cudaEventElapsedTime(&best, c->ev_t0, c->ev_t1));
       }
-      for (size_t i = 0; i < keep.size(); ++i) c->batches[i]->sweep = keep[i];
+      for (size_t i = 0; i < keep.size(); ++i) {
+        Batch &b = *c->batches[i];
+        b.sweep = keep[i];
+        if (b.nt != keep_nt[i] && b.graph_star) {  // captured for the shortened sweep
+          cudaGraphExecDestroy(b.graph_star);
+          b.graph_star = nullptr;
+        }
+        b.nt = keep_nt[i];
+        b.sargs.n_steps = b.nt;
+      }
       return double(best);
     };
     DevBuf<double> ref_trace, tune;
@@ -2111,6 +2130,7 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   else if (k == "sweep_ctas_per_sm") c->sweep_ctas_per_sm = std::max(1, int(value));
   else if (k == "sweep_spin_ns") c->sweep_spin_ns = std::max(0, int(value));
   else if (k == "sweep_autotune") c->sweep_autotune = value != 0;
+  else if (k == "tune_steps") c->tune_steps = int(value);
   else if (k == "sweep_crosscheck") c->sweep_crosscheck = value != 0;
   else if (k == "operator") {
     if (value != 0 && value != 1 && value != 2) { c->err = "operator must be 0 (sweeps), 1 (multiscale basis) or 2 (auto)"; return MMMFE_E_INVALID; }
@@ -2306,6 +2326,24 @@ int mmmfe_bar_set_data(mmmfe_ctx *c, int32_t li, const double *p0, const double 
   });
 }
 
+int mmmfe_bar_data_buffers(mmmfe_ctx *c, int32_t li, int32_t n_fr, const int32_t *fr_dofs, double **d_p0, double **d_src,
+                           double **d_fr_vals) {
+  if (!c || li < 0 || li >= int32_t(c->subs.size()) || n_fr < 0 || (n_fr > 0 && !fr_dofs) || !d_p0 || !d_src || !d_fr_vals)
+    return MMMFE_E_INVALID;
+  MMMFE_TRY(c, {
+    Sub &sd = *c->subs[li];
+    CUDA_CHECK(cudaSetDevice(c->device));
+    sd.p0.alloc(size_t(sd.np)); sd.p0.zero();
+    sd.src.alloc(size_t(sd.nt) * sd.np); sd.src.zero();
+    sd.n_fr = n_fr;
+    sd.fr_dofs.upload(fr_dofs, size_t(n_fr));
+    sd.fr_vals.alloc(size_t(n_fr) * sd.nt); sd.fr_vals.zero();
+    CUDA_CHECK(cudaDeviceSynchronize());
+    sd.has_bar_data = true;
+    *d_p0 = sd.p0.p; *d_src = sd.src.p; *d_fr_vals = sd.fr_vals.p;
+  });
+}
+
 int mmmfe_bar_sweep(mmmfe_ctx *c) {
   if (!c) return MMMFE_E_INVALID;
   MMMFE_TRY(c, bar_sweep(c));
@@ -2382,6 +2420,16 @@ int mmmfe_get_solution(mmmfe_ctx *c, int32_t li, double *solution) {
     Sub &sd = *c->subs[li];
     if (!sd.hist.p) fail(MMMFE_E_INVALID, "no stored solution (keep_history = 0 or no sweep yet)");
     CUDA_CHECK(cudaMemcpy(solution, sd.hist.p, sd.hist.n * sizeof(double), cudaMemcpyDeviceToHost));
+  });
+}
+
+int mmmfe_solution_device(mmmfe_ctx *c, int32_t li, double **d_solution) {
+  if (!c || li < 0 || li >= int32_t(c->subs.size()) || !d_solution) return MMMFE_E_INVALID;
+  MMMFE_TRY(c, {
+    Sub &sd = *c->subs[li];
+    if (!sd.hist.p) fail(MMMFE_E_INVALID, "no stored solution (keep_history = 0 or no sweep yet)");
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    *d_solution = sd.hist.p;
   });
 }
 

@@ -10,14 +10,17 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <map>
 #include <memory>
 #include <sstream>
 #include <stdexcept>
 #include <thread>
 
 #include <omp.h>
+#include <zlib.h>
 
 #include "mmmfe_b200.h"
+#include "data_device.h"
 
 #ifndef MMMFE_DATA_HEADER
 #define MMMFE_DATA_HEADER "data_default.h"
@@ -327,8 +330,51 @@ struct BarData {
   std::vector<int> fr_dofs;
 };
 
+// Which flux rows carry outer-boundary data and which constant rows system_rhs_bar_bc adds (both bar-data paths).
+struct BarLayout {
+  std::vector<int> fr_dofs, fr_side;  // fr_side[e] = side << 24 | position for the first n_dir entries, -1 after
+  int n_dir = 0;
+  std::vector<int> cell_rows, fr_slots;        // pressure rows (cell index) / flux slots that receive a constant
+  std::vector<double> cell_vals, fr_slot_vals;
+};
+
+void bar_layout(const Sub &s, bool manufact, const std::vector<char> &bc_type, BarLayout &L) {
+  for (int side = 0; side < 4; ++side) {
+    if (s.nb[side] >= 0) continue;
+    if (!manufact && bc_type[side_to_bc(side)] != 'D') continue;  // Neumann sides are essential: constrain_matrix
+    for (int m = 0; m < s.n_side[side]; ++m) { L.fr_dofs.push_back(s.side_edges[side][m]); L.fr_side.push_back(side * (1 << 24) + m); }
+  }
+  L.n_dir = int(L.fr_dofs.size());
+  // system_rhs_bar.sadd(1.0, system_rhs_bar_bc) (:863), every level.  Pressure rows go into the source, flux rows
+  // into the sparse flux data; the constrained rows themselves get |a_ii| g_i so that the solve returns g_i (the
+  // reference solves with 0 there and calls constraint_bc.distribute afterwards, :866 -- same solution).
+  std::vector<std::pair<int, double>> extra;  // flux row -> constant right-hand-side value
+  for (const auto &rv : s.rhs_bc) {
+    if (rv.first >= s.nf) { L.cell_rows.push_back(rv.first - s.nf); L.cell_vals.push_back(rv.second); }
+    else extra.push_back(rv);
+  }
+  for (size_t k = 0; k < s.con_dofs.size(); ++k) extra.push_back({s.con_dofs[k], s.con_diag[k] * s.con_vals[k]});
+  std::map<int, int> slot_of;
+  for (int e = 0; e < int(L.fr_dofs.size()); ++e) slot_of.insert({L.fr_dofs[e], e});
+  for (size_t k = 0; k < extra.size(); ++k) {  // the device adds fr entries without atomics: one entry per dof
+    auto it = slot_of.find(extra[k].first);
+    int slot;
+    if (it != slot_of.end()) slot = it->second;
+    else { slot = int(L.fr_dofs.size()); L.fr_dofs.push_back(extra[k].first); L.fr_side.push_back(-1); slot_of.insert({extra[k].first, slot}); }
+    // several constants of one slot are summed here, in order, so that both paths add ONE value per slot
+    bool merged = false;
+    for (size_t q = 0; q < L.fr_slots.size(); ++q) if (L.fr_slots[q] == slot) { L.fr_slot_vals[q] += extra[k].second; merged = true; break; }
+    if (!merged) { L.fr_slots.push_back(slot); L.fr_slot_vals.push_back(extra[k].second); }
+  }
+}
+
+double dirichlet_constant(int side, const std::vector<double> &bc_val) {
+  return (side == TOP) ? bc_val[1] : bc_val[side_to_bc(side)];  // the reference reads [1] for the top (:673)
+}
+
 // The data-dependent part of assemble_rhs_bar (src/darcy_vtdd.cc:632-766): dt (f, w) per cell and the outer
-// Dirichlet rows -s * int g; the c0 (p_old, w) term is added on the device.
+// Dirichlet rows -s * int g; the c0 (p_old, w) term is added on the device.  HOST evaluation of the data classes
+// (builds without the device data path, or MMMFE_HOST_DATA=1).
 void bar_data(const Sub &s, int qdegree, bool manufact, const std::vector<char> &bc_type,
               const std::vector<double> &bc_val, double c0, double alpha, BarData &out) {
   std::vector<double> g2, w2, g5, w5, gq, wq;
@@ -339,8 +385,9 @@ void bar_data(const Sub &s, int qdegree, bool manufact, const std::vector<char> 
   out.p0.assign(s.np, 0.0);
   {
     const InitialCondition<2> ic;
-    dealii::Vector<double> v(3);
-    for (int j = 0; j < s.ny; ++j)
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < s.ny; ++j) {
+      dealii::Vector<double> v(3);
       for (int i = 0; i < s.nx; ++i) {
         double acc = 0;
         for (int a = 0; a < 5; ++a)
@@ -350,6 +397,7 @@ void bar_data(const Sub &s, int qdegree, bool manufact, const std::vector<char> 
           }
         out.p0[j * s.nx + i] = acc;
       }
+    }
   }
   out.src.assign(size_t(s.nt) * s.np, 0.0);
   const double area = s.hx * s.hy;
@@ -367,53 +415,54 @@ void bar_data(const Sub &s, int qdegree, bool manufact, const std::vector<char> 
         dst[j * s.nx + i] = s.dt * acc * area;  // :718
       }
   }
-  out.fr_dofs.clear();
-  std::vector<int> fr_side;
-  for (int side = 0; side < 4; ++side) {
-    if (s.nb[side] >= 0) continue;
-    if (!manufact && bc_type[side_to_bc(side)] != 'D') continue;  // Neumann sides are essential: constrain_matrix
-    for (int m = 0; m < s.n_side[side]; ++m) { out.fr_dofs.push_back(s.side_edges[side][m]); fr_side.push_back(side * (1 << 24) + m); }
-  }
-  // system_rhs_bar.sadd(1.0, system_rhs_bar_bc) (:863), every level.  Pressure rows go into the source, flux rows
-  // into the sparse flux data; the constrained rows themselves get |a_ii| g_i so that the solve returns g_i (the
-  // reference solves with 0 there and calls constraint_bc.distribute afterwards, :866 -- same solution).
-  const int n_dir = int(out.fr_dofs.size());
-  std::vector<std::pair<int, double>> extra;  // flux row -> constant right-hand-side value
-  for (const auto &rv : s.rhs_bc) {
-    if (rv.first >= s.nf) {
-      for (int lvl = 0; lvl < s.nt; ++lvl) out.src[size_t(lvl) * s.np + (rv.first - s.nf)] += rv.second;
-    } else extra.push_back(rv);
-  }
-  for (size_t k = 0; k < s.con_dofs.size(); ++k) extra.push_back({s.con_dofs[k], s.con_diag[k] * s.con_vals[k]});
-  std::vector<int> extra_slot(extra.size());
-  for (size_t k = 0; k < extra.size(); ++k) {  // the device adds fr entries without atomics: one entry per dof
-    int slot = -1;
-    for (int e = 0; e < int(out.fr_dofs.size()); ++e) if (out.fr_dofs[e] == extra[k].first) { slot = e; break; }
-    if (slot < 0) { slot = int(out.fr_dofs.size()); out.fr_dofs.push_back(extra[k].first); fr_side.push_back(-1); }
-    extra_slot[k] = slot;
-  }
-  const int nfr = int(out.fr_dofs.size());
+  BarLayout L;
+  bar_layout(s, manufact, bc_type, L);
+  out.fr_dofs = L.fr_dofs;
+  for (int lvl = 0; lvl < s.nt; ++lvl)
+    for (size_t k = 0; k < L.cell_rows.size(); ++k) out.src[size_t(lvl) * s.np + L.cell_rows[k]] += L.cell_vals[k];
+  const int nfr = int(out.fr_dofs.size()), n_dir = L.n_dir;
   out.fr_vals.assign(size_t(s.nt) * nfr, 0.0);
   for (int lvl = 0; lvl < s.nt; ++lvl)
-    for (size_t k = 0; k < extra.size(); ++k) out.fr_vals[size_t(lvl) * nfr + extra_slot[k]] += extra[k].second;
+    for (size_t k = 0; k < L.fr_slots.size(); ++k) out.fr_vals[size_t(lvl) * nfr + L.fr_slots[k]] += L.fr_slot_vals[k];
 #pragma omp parallel for schedule(static)
   for (int lvl = 0; lvl < s.nt; ++lvl) {
     PressureBoundaryValues<2> gfun;
     gfun.set_time(s.levels_t[lvl]);
     for (int e = 0; e < n_dir; ++e) {
-      const int side = fr_side[e] >> 24, m = fr_side[e] & ((1 << 24) - 1);
+      const int side = L.fr_side[e] >> 24, m = L.fr_side[e] & ((1 << 24) - 1);
       double acc = 0;
       for (int q = 0; q < qdegree; ++q) {
         double x, y;
         side_point(s, side, m, gq[q], x, y);
         double gv;
         if (manufact) gv = gfun.value(dealii::Point<2>(x, y));
-        else gv = (side == TOP) ? bc_val[1] : bc_val[side_to_bc(side)];  // the reference reads [1] for the top (:673)
+        else gv = dirichlet_constant(side, bc_val);
         acc += wq[q] * gv;
       }
       out.fr_vals[size_t(lvl) * nfr + e] += -kNormal[side] * acc;  // :748-751
     }
   }
+}
+
+devdata::Grid dev_grid(const Sub &s) { return devdata::Grid{s.nx, s.ny, s.nt, s.x0, s.y0, s.hx, s.hy, s.dt, s.levels_t.data()}; }
+
+// The same data evaluated by CUDA kernels straight into the engine's buffers (host/data_device.cu).
+void bar_data_device(mmmfe_ctx *ctx, const Sub &s, int qdegree, bool manufact, const std::vector<char> &bc_type,
+                     const std::vector<double> &bc_val, double c0, double alpha) {
+  BarLayout L;
+  bar_layout(s, manufact, bc_type, L);
+  const int nfr = int(L.fr_dofs.size());
+  double *d_p0 = nullptr, *d_src = nullptr, *d_fr = nullptr;
+  if (mmmfe_bar_data_buffers(ctx, s.local, nfr, L.fr_dofs.data(), &d_p0, &d_src, &d_fr) != 0)
+    throw std::runtime_error(std::string("mmmfe_bar_data_buffers: ") + mmmfe_last_error(ctx));
+  const devdata::Grid g = dev_grid(s);
+  devdata::initial_pressure(g, d_p0);
+  devdata::bar_source(g, c0, alpha, d_src);
+  devdata::add_constant_rows(s.nt, s.np, int(L.cell_rows.size()), L.cell_rows.data(), L.cell_vals.data(), d_src);
+  devdata::add_constant_rows(s.nt, nfr, int(L.fr_slots.size()), L.fr_slots.data(), L.fr_slot_vals.data(), d_fr);
+  double bc_side[4];
+  for (int side = 0; side < 4; ++side) bc_side[side] = dirichlet_constant(side, bc_val);
+  devdata::boundary_values(g, s.Lx, s.Ly, L.n_dir, L.fr_side.data(), nfr, qdegree, manufact ? 1 : 0, bc_side, d_fr);
 }
 
 // compute_errors per subdomain, src/darcy_vtdd.cc:1657-1775; numerators/denominators {velocity, pressure L2, DG}
@@ -501,43 +550,193 @@ std::string pad4(int v) {
   return b;
 }
 
-// output_results, src/darcy_vtdd.cc:1906-1948: one patch per space-time cell, values at its 8 vertices; u3 = 0
-void write_st_vtu(const Sub &s, const std::string &dir) {
+// compute_errors from the device-resident solution: the per-level sums are reduced by CUDA kernels
+// (host/data_device.cu error_sums), the combination over the levels is the host code of subdomain_errors.
+void subdomain_errors_device(const Sub &s, const double *d_solution, double num[3], double den[3]) {
+  std::vector<double> sums(size_t(s.nt) * 5);
+  devdata::error_sums(dev_grid(s), d_solution, sums.data());
+  for (int k = 0; k < 3; ++k) num[k] = den[k] = 0;
+  const double final_time = s.dt * s.nt;
+  for (int lvl = 0; lvl < s.nt; ++lvl) {
+    const double n0 = sums[lvl * 5 + 0], d0 = sums[lvl * 5 + 1], n1 = sums[lvl * 5 + 2], d1 = sums[lvl * 5 + 3], jump = sums[lvl * 5 + 4];
+    num[0] += n0; den[0] += d0;                // :1774-1775, no dt weight
+    num[1] += s.dt * n1; den[1] += s.dt * d1;  // :1714-1715
+    num[2] += jump;
+    if (std::fabs(s.levels_t[lvl] - final_time) < 1e-12) { num[2] += n1; den[2] += d1; }  // :1744-1749
+  }
+}
+
+// ---- VTK XML "binary" data arrays: base64(header) base64(zlib blocks), header = {blocks, block size, size of the
+// partial last block, compressed sizes}, UInt64 -- what deal.II's DataOut writes when built with zlib (compressor
+// vtkZLibDataCompressor), cut into 1 MiB blocks that are compressed in parallel ----
+std::string base64(const unsigned char *d, size_t n) {
+  static const char T[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+  std::string o;
+  o.resize((n + 2) / 3 * 4);
+  size_t k = 0, i = 0;
+  for (; i + 3 <= n; i += 3) {
+    const unsigned v = (unsigned(d[i]) << 16) | (unsigned(d[i + 1]) << 8) | d[i + 2];
+    o[k++] = T[v >> 18]; o[k++] = T[(v >> 12) & 63]; o[k++] = T[(v >> 6) & 63]; o[k++] = T[v & 63];
+  }
+  if (i < n) {
+    const unsigned v = (unsigned(d[i]) << 16) | (i + 1 < n ? unsigned(d[i + 1]) << 8 : 0u);
+    o[k++] = T[v >> 18]; o[k++] = T[(v >> 12) & 63]; o[k++] = (i + 1 < n) ? T[(v >> 6) & 63] : '='; o[k++] = '=';
+  }
+  return o;
+}
+
+constexpr size_t kVtuBlock = size_t(1) << 20;
+
+// One data array of a .vtu file, fed in pieces (the space-time file is produced a few time levels at a time).
+class VtuArray {
+ public:
+  void append(const void *data, size_t bytes) {
+    const unsigned char *p = static_cast<const unsigned char *>(data);
+    total_ += bytes;
+    if (!pending_.empty()) {
+      const size_t take = std::min(bytes, kVtuBlock - pending_.size());
+      pending_.insert(pending_.end(), p, p + take);
+      p += take; bytes -= take;
+      if (pending_.size() == kVtuBlock) { compress_blocks(pending_.data(), 1); pending_.clear(); }
+    }
+    const size_t full = bytes / kVtuBlock;
+    if (full) compress_blocks(p, full);
+    pending_.insert(pending_.end(), p + full * kVtuBlock, p + bytes);
+  }
+  // <DataArray ...> body
+  void write(std::ostream &o) {
+    size_t partial = 0;
+    if (!pending_.empty()) { partial = pending_.size(); compress_one(pending_.data(), pending_.size(), blocks_.emplace_back()); pending_.clear(); }
+    std::vector<uint64_t> head{uint64_t(blocks_.size()), uint64_t(kVtuBlock), uint64_t(partial)};
+    size_t csum = 0;
+    for (const auto &b : blocks_) { head.push_back(b.size()); csum += b.size(); }
+    o << base64(reinterpret_cast<const unsigned char *>(head.data()), head.size() * 8);
+    std::vector<unsigned char> all;
+    all.reserve(csum);
+    for (const auto &b : blocks_) all.insert(all.end(), b.begin(), b.end());
+    o << base64(all.data(), all.size()) << "\n";
+    blocks_.clear();
+  }
+
+ private:
+  static void compress_one(const unsigned char *src, size_t n, std::vector<unsigned char> &dst) {
+    uLongf cap = compressBound(uLong(n));
+    dst.resize(cap);
+    if (compress2(dst.data(), &cap, src, uLong(n), Z_BEST_SPEED) != Z_OK) throw std::runtime_error("zlib compress2 failed");
+    dst.resize(cap);
+  }
+  void compress_blocks(const unsigned char *src, size_t n_blocks) {
+    const size_t first = blocks_.size();
+    blocks_.resize(first + n_blocks);
+#pragma omp parallel for schedule(dynamic)
+    for (long long b = 0; b < (long long)n_blocks; ++b) compress_one(src + size_t(b) * kVtuBlock, kVtuBlock, blocks_[first + size_t(b)]);
+  }
+  std::vector<std::vector<unsigned char>> blocks_;
+  std::vector<unsigned char> pending_;
+  size_t total_ = 0;
+};
+
+const char *kVtuHead = "<?xml version=\"1.0\" ?>\n<VTKFile type=\"UnstructuredGrid\" version=\"1.0\" byte_order=\"LittleEndian\" "
+                       "header_type=\"UInt64\" compressor=\"vtkZLibDataCompressor\">\n<UnstructuredGrid>\n";
+
+bool vtu_ascii() {
+  const char *e = std::getenv("MMMFE_VTU_ASCII");
+  return e && e[0] == '1';
+}
+
+// patches of levels [l0, l1) expanded on the host (the builds / runs without the device data path)
+void expand_space_time_host(const Sub &s, int l0, int l1, double *pts, double *u, double *p) {
+#pragma omp parallel for schedule(static)
+  for (int l = l0; l < l1; ++l) {
+    const double *x = &s.solution[size_t(l) * s.n];
+    size_t idx = size_t(l - l0) * s.np * 8;
+    for (int j = 0; j < s.ny; ++j)
+      for (int i = 0; i < s.nx; ++i)
+        for (int v = 0; v < 8; ++v, ++idx) {
+          pts[idx * 3] = s.x0 + (i + (v & 1)) * s.hx; pts[idx * 3 + 1] = s.y0 + (j + ((v >> 1) & 1)) * s.hy;
+          pts[idx * 3 + 2] = (l + ((v >> 2) & 1)) * s.dt;
+          u[idx * 3] = x[j * (s.nx + 1) + i + (v & 1)] / s.hy; u[idx * 3 + 1] = x[s.nxe + (j + ((v >> 1) & 1)) * s.nx + i] / s.hx;
+          u[idx * 3 + 2] = 0.0;
+          p[idx] = x[s.nf + j * s.nx + i];
+        }
+  }
+}
+
+// output_results, src/darcy_vtdd.cc:1906-1948: one patch per space-time cell, values at its 8 vertices; u3 = 0.
+// d_solution != nullptr: the patches are expanded on the device from the solution that lives there, a few time
+// levels at a time (host memory stays bounded); else from s.solution.  Binary + zlib like deal.II's DataOut.
+void write_st_vtu(const Sub &s, const double *d_solution, const std::string &dir) {
   std::ofstream o(dir + "/space-time-plots/st_solution_d3_p" + pad4(s.r) + ".vtu");
   if (!o) return;
   const long long nc = (long long)s.nx * s.ny * s.nt;
-  o << std::setprecision(12);
-  o << "<?xml version=\"1.0\" ?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n<UnstructuredGrid>\n";
-  o << "<Piece NumberOfPoints=\"" << nc * 8 << "\" NumberOfCells=\"" << nc << "\">\n<Points>\n<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n";
-  for (int l = 0; l < s.nt; ++l)
-    for (int j = 0; j < s.ny; ++j)
-      for (int i = 0; i < s.nx; ++i)
-        for (int v = 0; v < 8; ++v)
-          o << s.x0 + (i + (v & 1)) * s.hx << ' ' << s.y0 + (j + ((v >> 1) & 1)) * s.hy << ' ' << (l + ((v >> 2) & 1)) * s.dt << '\n';
-  o << "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int64\" Name=\"connectivity\" format=\"ascii\">\n";
+  const bool ascii = vtu_ascii();
+  const char *fmt = ascii ? "ascii" : "binary";
+  VtuArray a_pts, a_u, a_p, a_conn, a_off, a_types;
+  std::ostringstream t_pts, t_u, t_p;
+  t_pts << std::setprecision(12); t_u << std::setprecision(12); t_p << std::setprecision(12);
+  const int chunk = int(std::max<long long>(1, (long long)(size_t(32) << 20) / (8LL * 8 * s.np)));  // ~32 MiB of p per piece
+  std::vector<double> pts, u, p;
+  for (int l0 = 0; l0 < s.nt; l0 += chunk) {
+    const int l1 = std::min(s.nt, l0 + chunk);
+    const size_t cells = size_t(l1 - l0) * s.np;
+    pts.resize(cells * 24); u.resize(cells * 24); p.resize(cells * 8);
+    if (d_solution) devdata::expand_space_time(dev_grid(s), d_solution, l0, l1, pts.data(), u.data(), p.data());
+    else expand_space_time_host(s, l0, l1, pts.data(), u.data(), p.data());
+    if (ascii) {
+      for (size_t k = 0; k < cells * 8; ++k) {
+        t_pts << pts[3 * k] << ' ' << pts[3 * k + 1] << ' ' << pts[3 * k + 2] << '\n';
+        t_u << u[3 * k] << ' ' << u[3 * k + 1] << " 0\n";
+        t_p << p[k] << '\n';
+      }
+    } else {
+      a_pts.append(pts.data(), pts.size() * 8); a_u.append(u.data(), u.size() * 8); a_p.append(p.data(), p.size() * 8);
+    }
+  }
   const int perm[8] = {0, 1, 3, 2, 4, 5, 7, 6};  // lexicographic -> VTK_HEXAHEDRON
-  for (long long c = 0; c < nc; ++c) { for (int v = 0; v < 8; ++v) o << c * 8 + perm[v] << ' '; o << '\n'; }
-  o << "</DataArray>\n<DataArray type=\"Int64\" Name=\"offsets\" format=\"ascii\">\n";
-  for (long long c = 1; c <= nc; ++c) o << c * 8 << '\n';
-  o << "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n";
-  for (long long c = 0; c < nc; ++c) o << "12\n";
-  o << "</DataArray>\n</Cells>\n<PointData Scalars=\"scalars\">\n<DataArray type=\"Float64\" Name=\"u\" NumberOfComponents=\"3\" format=\"ascii\">\n";
-  for (int l = 0; l < s.nt; ++l) {
-    const double *x = &s.solution[size_t(l) * s.n];
-    for (int j = 0; j < s.ny; ++j)
-      for (int i = 0; i < s.nx; ++i)
-        for (int v = 0; v < 8; ++v) {
-          const double u1 = x[j * (s.nx + 1) + i + (v & 1)] / s.hy, u2 = x[s.nxe + (j + ((v >> 1) & 1)) * s.nx + i] / s.hx;
-          o << u1 << ' ' << u2 << " 0\n";
-        }
+  if (ascii) o << "<?xml version=\"1.0\" ?>\n<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n<UnstructuredGrid>\n";
+  else o << kVtuHead;
+  o << "<Piece NumberOfPoints=\"" << nc * 8 << "\" NumberOfCells=\"" << nc << "\">\n<Points>\n<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"" << fmt << "\">\n";
+  if (ascii) o << t_pts.str(); else a_pts.write(o);
+  o << "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int64\" Name=\"connectivity\" format=\"" << fmt << "\">\n";
+  if (ascii) {
+    for (long long c = 0; c < nc; ++c) { for (int v = 0; v < 8; ++v) o << c * 8 + perm[v] << ' '; o << '\n'; }
+  } else {
+    std::vector<int64_t> buf;
+    const long long step = 1 << 17;
+    for (long long c0 = 0; c0 < nc; c0 += step) {
+      const long long c1 = std::min(nc, c0 + step);
+      buf.resize(size_t(c1 - c0) * 8);
+      for (long long c = c0; c < c1; ++c) for (int v = 0; v < 8; ++v) buf[size_t(c - c0) * 8 + v] = c * 8 + perm[v];
+      a_conn.append(buf.data(), buf.size() * 8);
+    }
+    a_conn.write(o);
   }
-  o << "</DataArray>\n<DataArray type=\"Float64\" Name=\"p\" format=\"ascii\">\n";
-  for (int l = 0; l < s.nt; ++l) {
-    const double *x = &s.solution[size_t(l) * s.n];
-    for (int j = 0; j < s.ny; ++j)
-      for (int i = 0; i < s.nx; ++i)
-        for (int v = 0; v < 8; ++v) o << x[s.nf + j * s.nx + i] << '\n';
+  o << "</DataArray>\n<DataArray type=\"Int64\" Name=\"offsets\" format=\"" << fmt << "\">\n";
+  if (ascii) {
+    for (long long c = 1; c <= nc; ++c) o << c * 8 << '\n';
+  } else {
+    std::vector<int64_t> buf;
+    const long long step = 1 << 20;
+    for (long long c0 = 0; c0 < nc; c0 += step) {
+      const long long c1 = std::min(nc, c0 + step);
+      buf.resize(size_t(c1 - c0));
+      for (long long c = c0; c < c1; ++c) buf[size_t(c - c0)] = (c + 1) * 8;
+      a_off.append(buf.data(), buf.size() * 8);
+    }
+    a_off.write(o);
   }
+  o << "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"" << fmt << "\">\n";
+  if (ascii) {
+    for (long long c = 0; c < nc; ++c) o << "12\n";
+  } else {
+    std::vector<unsigned char> buf(size_t(std::min<long long>(nc, 1 << 22)), 12);
+    for (long long c0 = 0; c0 < nc; c0 += (long long)buf.size()) a_types.append(buf.data(), size_t(std::min<long long>((long long)buf.size(), nc - c0)));
+    a_types.write(o);
+  }
+  o << "</DataArray>\n</Cells>\n<PointData Scalars=\"scalars\">\n<DataArray type=\"Float64\" Name=\"u\" NumberOfComponents=\"3\" format=\"" << fmt << "\">\n";
+  if (ascii) o << t_u.str(); else a_u.write(o);
+  o << "</DataArray>\n<DataArray type=\"Float64\" Name=\"p\" format=\"" << fmt << "\">\n";
+  if (ascii) o << t_p.str(); else a_p.write(o);
   o << "</DataArray>\n</PointData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n";
 }
 
@@ -818,7 +1017,12 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
     for (auto &sp : subs) { rep.dof_steps += (long long)sp->n * sp->nt; sp->matrix = Csr(); }
     // ---- bar problems ----
     t0 = clk::now();
+    const bool dev_data = devdata::enabled();  // the data classes are evaluated by CUDA kernels (host/data_device.cu)
     for (auto &sp : subs) {
+      if (dev_data) {
+        bar_data_device(ctx, *sp, qdegree, is_manufact_solution, bc_condition_vect, bc_const_functs, prm.c_0, prm.alpha);
+        continue;
+      }
       BarData bd;
       bar_data(*sp, qdegree, is_manufact_solution, bc_condition_vect, bc_const_functs, prm.c_0, prm.alpha, bd);
       check(ctx, mmmfe_bar_set_data(ctx, sp->local, bd.p0.data(), bd.src.data(), int(bd.fr_dofs.size()),
@@ -923,7 +1127,19 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
     if (control.final_sweep) {
       t0 = clk::now();
       check(ctx, mmmfe_final_sweep(ctx), "mmmfe_final_sweep");
-      if (control.fetch_solution)
+      // With the device data path the solution stays on the GPU: the essential values are set there, the error sums
+      // are reduced there and the output patches are expanded there.  The host copy is only made for the host
+      // paths (no device data, or the per-level 2-D plots).
+      std::vector<double *> d_sol(subs.size(), nullptr);
+      if (dev_data)
+        for (size_t li = 0; li < subs.size(); ++li) {
+          Sub &sd = *subs[li];
+          check(ctx, mmmfe_solution_device(ctx, sd.local, &d_sol[li]), "mmmfe_solution_device");
+          devdata::set_constant_rows(sd.nt, sd.n, int(sd.con_dofs.size()), sd.con_dofs.data(), sd.con_vals.data(), d_sol[li]);
+        }
+      const bool want_files = control.write_output && cycle + 1 == refine;  // :1847
+      const bool host_copy = control.fetch_solution && (!dev_data || (want_files && need_each_time_step_plot));
+      if (host_copy)
       for (auto &sp : subs) {
         sp->solution.resize(size_t(sp->nt) * sp->n);
         check(ctx, mmmfe_get_solution(ctx, sp->local, sp->solution.data()), "mmmfe_get_solution");
@@ -932,12 +1148,14 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
       }
       rep.t_final = since(t0);
       if (say) std::cout << "finished local_gmres" << "\n";
-      if (is_manufact_solution && control.compute_errors && control.fetch_solution) {
+      if (is_manufact_solution && control.compute_errors && (dev_data || control.fetch_solution)) {
         t0 = clk::now();
         double buf[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // num{vel, pL2, DG, lambda}, den{...}
-        for (auto &sp : subs) {
+        for (size_t li = 0; li < subs.size(); ++li) {
+          Sub *sp = subs[li].get();
           double num[3], den[3];
-          subdomain_errors(*sp, num, den);
+          if (dev_data) subdomain_errors_device(*sp, d_sol[li], num, den);
+          else subdomain_errors(*sp, num, den);
           for (int k = 0; k < 3; ++k) { buf[k] += num[k]; buf[4 + k] += den[k]; }
           for (int side = 0; side < 4; ++side)
             if (sp->nb[side] >= 0) {
@@ -952,10 +1170,11 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
         rep.lambda_l2 = std::sqrt(buf[3]) / std::sqrt(buf[7]);
         rep.t_errors = since(t0);
       }
-      if (control.write_output && control.fetch_solution && cycle + 1 == refine) {  // :1847
+      if (want_files && (dev_data || control.fetch_solution)) {
         t0 = clk::now();
-        for (auto &sp : subs) {
-          write_st_vtu(*sp, control.output_dir);
+        for (size_t li = 0; li < subs.size(); ++li) {
+          Sub *sp = subs[li].get();
+          write_st_vtu(*sp, dev_data ? d_sol[li] : nullptr, control.output_dir);
           if (need_each_time_step_plot)
             for (int l = 0; l < sp->nt; ++l) write_level_vtu(*sp, l, control.output_dir, int(n_sub), root && sp->local == 0);
         }

@@ -13,19 +13,20 @@
 namespace vt_darcy {
 using namespace dealii;
 
+// (MMMFE_HD: usable in device code too -- the data classes are also evaluated by CUDA kernels, host/data_device.cu)
 namespace manufactured {
 constexpr double kQuarterPi = 3.1415 / 4;
-inline double sx(double x) { return std::sin(11 * x); }
-inline double cx(double x) { return std::cos(11 * x); }
-inline double cy(double y) { return std::cos(11 * y - kQuarterPi); }
-inline double sy(double y) { return std::sin(11 * y - kQuarterPi); }
-inline double pressure(double x, double y, double t) { return std::sin(8 * t) * sx(x) * cy(y); }
+MMMFE_HD inline double sx(double x) { return std::sin(11 * x); }
+MMMFE_HD inline double cx(double x) { return std::cos(11 * x); }
+MMMFE_HD inline double cy(double y) { return std::cos(11 * y - kQuarterPi); }
+MMMFE_HD inline double sy(double y) { return std::sin(11 * y - kQuarterPi); }
+MMMFE_HD inline double pressure(double x, double y, double t) { return std::sin(8 * t) * sx(x) * cy(y); }
 }  // namespace manufactured
 
 template <int dim>
 class KInverse : public TensorFunction<2, dim> {
  public:
-  void value_list(const std::vector<Point<dim>> &points, std::vector<Tensor<2, dim>> &values) const override {
+  virtual void value_list(const std::vector<Point<dim>> &points, std::vector<Tensor<2, dim>> &values) const override {
     for (std::size_t q = 0; q < points.size(); ++q) {
       values[q].clear();
       for (int d = 0; d < dim; ++d) values[q][d][d] = 1.0;
@@ -37,7 +38,7 @@ template <int dim>
 class RightHandSidePressure : public Function<dim> {
  public:
   RightHandSidePressure(const double c0 = 1.0, const double alpha = 1.0) : Function<dim>(1), c0_(c0), alpha_(alpha) {}
-  double value(const Point<dim> &p, const unsigned int = 0) const override {
+  virtual double value(const Point<dim> &p, const unsigned int = 0) const override {
     // c0 p_t - laplace p with c0 = 1 hard-wired, as in the reference data file
     const double t = this->get_time();
     const double shape = manufactured::sx(p[0]) * manufactured::cy(p[1]);
@@ -52,7 +53,7 @@ template <int dim>
 class PressureBoundaryValues : public Function<dim> {
  public:
   PressureBoundaryValues() : Function<dim>(1) {}
-  double value(const Point<dim> &p, const unsigned int = 0) const override {
+  virtual double value(const Point<dim> &p, const unsigned int = 0) const override {
     // in 3-d (space-time mortar faces) the third coordinate is the time
     const double t = (dim == 3) ? p[dim - 1] : this->get_time();
     return manufactured::pressure(p[0], p[1], t);
@@ -63,7 +64,7 @@ template <int dim>
 class ExactSolution : public Function<dim> {
  public:
   ExactSolution() : Function<dim>(dim + 1) {}
-  void vector_value(const Point<dim> &p, Vector<double> &values) const override {
+  virtual void vector_value(const Point<dim> &p, Vector<double> &values) const override {
     using namespace manufactured;
     const double st = std::sin(8 * this->get_time());
     values(0) = -st * 11 * cx(p[0]) * cy(p[1]);
@@ -76,7 +77,7 @@ template <int dim>
 class InitialCondition : public Function<dim> {
  public:
   InitialCondition() : Function<dim>(dim + 1) {}
-  void vector_value(const Point<dim> &p, Vector<double> &values) const override {
+  virtual void vector_value(const Point<dim> &p, Vector<double> &values) const override {
     values(0) = 0;
     values(1) = 0;
     values(2) = manufactured::pressure(p[0], p[1], 0.0);

@@ -11,18 +11,27 @@
 #include <string>
 #include <vector>
 
+// Under nvcc every class below is usable in device code as well (host/data_device.cu compiles an unmodified
+// inc/data.h-style header for the GPU: the right-hand-side, boundary and exact-solution tables are then evaluated
+// by CUDA kernels instead of host loops).  g++ sees plain host classes.
+#if defined(__CUDACC__)
+#define MMMFE_HD __host__ __device__
+#else
+#define MMMFE_HD
+#endif
+
 namespace dealii {
 
 template <int dim, typename Number = double>
 class Point {
  public:
-  Point() { for (int d = 0; d < dim; ++d) v_[d] = Number(); }
-  Point(Number x, Number y) { static_assert(dim == 2, "2-d constructor"); v_[0] = x; v_[1] = y; }
-  Point(Number x, Number y, Number z) { static_assert(dim == 3, "3-d constructor"); v_[0] = x; v_[1] = y; v_[2] = z; }
-  Number &operator[](unsigned i) { return v_[i]; }
-  const Number &operator[](unsigned i) const { return v_[i]; }
-  Number &operator()(unsigned i) { return v_[i]; }
-  const Number &operator()(unsigned i) const { return v_[i]; }
+  MMMFE_HD Point() { for (int d = 0; d < dim; ++d) v_[d] = Number(); }
+  MMMFE_HD Point(Number x, Number y) { static_assert(dim == 2, "2-d constructor"); v_[0] = x; v_[1] = y; }
+  MMMFE_HD Point(Number x, Number y, Number z) { static_assert(dim == 3, "3-d constructor"); v_[0] = x; v_[1] = y; v_[2] = z; }
+  MMMFE_HD Number &operator[](unsigned i) { return v_[i]; }
+  MMMFE_HD const Number &operator[](unsigned i) const { return v_[i]; }
+  MMMFE_HD Number &operator()(unsigned i) { return v_[i]; }
+  MMMFE_HD const Number &operator()(unsigned i) const { return v_[i]; }
 
  private:
   Number v_[dim];
@@ -34,10 +43,10 @@ class Tensor;
 template <int dim, typename Number>
 class Tensor<1, dim, Number> {
  public:
-  Tensor() { clear(); }
-  void clear() { for (int d = 0; d < dim; ++d) v_[d] = Number(); }
-  Number &operator[](unsigned i) { return v_[i]; }
-  const Number &operator[](unsigned i) const { return v_[i]; }
+  MMMFE_HD Tensor() { clear(); }
+  MMMFE_HD void clear() { for (int d = 0; d < dim; ++d) v_[d] = Number(); }
+  MMMFE_HD Number &operator[](unsigned i) { return v_[i]; }
+  MMMFE_HD const Number &operator[](unsigned i) const { return v_[i]; }
 
  private:
   Number v_[dim];
@@ -46,37 +55,44 @@ class Tensor<1, dim, Number> {
 template <int dim, typename Number>
 class Tensor<2, dim, Number> {
  public:
-  void clear() { for (int d = 0; d < dim; ++d) v_[d].clear(); }
-  Tensor<1, dim, Number> &operator[](unsigned i) { return v_[i]; }
-  const Tensor<1, dim, Number> &operator[](unsigned i) const { return v_[i]; }
+  MMMFE_HD void clear() { for (int d = 0; d < dim; ++d) v_[d].clear(); }
+  MMMFE_HD Tensor<1, dim, Number> &operator[](unsigned i) { return v_[i]; }
+  MMMFE_HD const Tensor<1, dim, Number> &operator[](unsigned i) const { return v_[i]; }
 
  private:
   Tensor<1, dim, Number> v_[dim];
 };
 
+// The data headers only ever hold the components of one function value in a Vector (dim + 1 at most): inline
+// storage, so that the class works in device code too.
 template <typename Number = double>
 class Vector {
  public:
-  Vector() = default;
-  explicit Vector(std::size_t n) : v_(n, Number()) {}
-  std::size_t size() const { return v_.size(); }
-  Number &operator()(std::size_t i) { return v_[i]; }
-  const Number &operator()(std::size_t i) const { return v_[i]; }
-  Number &operator[](std::size_t i) { return v_[i]; }
-  const Number &operator[](std::size_t i) const { return v_[i]; }
+  static constexpr std::size_t capacity = 8;
+  MMMFE_HD Vector() : n_(0) { for (std::size_t i = 0; i < capacity; ++i) v_[i] = Number(); }
+  MMMFE_HD explicit Vector(std::size_t n) : n_(n) {
+    assert(n <= capacity);
+    for (std::size_t i = 0; i < capacity; ++i) v_[i] = Number();
+  }
+  MMMFE_HD std::size_t size() const { return n_; }
+  MMMFE_HD Number &operator()(std::size_t i) { return v_[i]; }
+  MMMFE_HD const Number &operator()(std::size_t i) const { return v_[i]; }
+  MMMFE_HD Number &operator[](std::size_t i) { return v_[i]; }
+  MMMFE_HD const Number &operator[](std::size_t i) const { return v_[i]; }
 
  private:
-  std::vector<Number> v_;
+  std::size_t n_;
+  Number v_[capacity];
 };
 
 template <typename Number = double>
 class FunctionTime {
  public:
-  explicit FunctionTime(Number t0 = Number()) : time_(t0) {}
-  virtual ~FunctionTime() = default;
-  Number get_time() const { return time_; }
-  virtual void set_time(const Number t) { time_ = t; }
-  virtual void advance_time(const Number dt) { set_time(time_ + dt); }
+  MMMFE_HD explicit FunctionTime(Number t0 = Number()) : time_(t0) {}
+  MMMFE_HD virtual ~FunctionTime() {}
+  MMMFE_HD Number get_time() const { return time_; }
+  MMMFE_HD virtual void set_time(const Number t) { time_ = t; }
+  MMMFE_HD virtual void advance_time(const Number dt) { set_time(time_ + dt); }
 
  private:
   Number time_;
@@ -86,10 +102,10 @@ template <int dim, typename Number = double>
 class Function : public FunctionTime<Number> {
  public:
   const unsigned int n_components;
-  explicit Function(unsigned int n_comp = 1, Number t0 = Number()) : FunctionTime<Number>(t0), n_components(n_comp) {}
-  virtual ~Function() = default;
-  virtual Number value(const Point<dim> &, const unsigned int = 0) const { return Number(); }
-  virtual void vector_value(const Point<dim> &p, Vector<Number> &values) const {
+  MMMFE_HD explicit Function(unsigned int n_comp = 1, Number t0 = Number()) : FunctionTime<Number>(t0), n_components(n_comp) {}
+  MMMFE_HD virtual ~Function() {}
+  MMMFE_HD virtual Number value(const Point<dim> &, const unsigned int = 0) const { return Number(); }
+  MMMFE_HD virtual void vector_value(const Point<dim> &p, Vector<Number> &values) const {
     for (unsigned c = 0; c < n_components; ++c) values(c) = value(p, c);
   }
   virtual void value_list(const std::vector<Point<dim>> &pts, std::vector<Number> &vals, const unsigned int c = 0) const {

@@ -136,3 +136,71 @@ def test_two_gpus_reproduce_the_oracle(tmp_path):
     res = json.load(open(out))
     assert all(v["ok"] for v in res.values()) and len(res) == 5
     assert res["nonmatching_2x2_sweep"]["sweep_batches"] > 0 and res["checker_4x4_sweep_m4"]["sweep_batches"] > 0
+
+
+def _decode_vtu_array(text, name):
+    """One binary DataArray of a .vtu written by the front-end: base64(header) base64(zlib blocks), UInt64 header."""
+    import base64
+    import re
+    import zlib
+    m = re.search(r'<DataArray[^>]*' + name + r'[^>]*format="binary">\n([^\n<]*)\n', text)
+    assert m, name
+    body = m.group(1)
+    n_blocks = int(np.frombuffer(base64.b64decode(body[:12]), dtype="<u8", count=1)[0])
+    head_len = (3 + n_blocks) * 8
+    head_chars = (head_len + 2) // 3 * 4
+    head = np.frombuffer(base64.b64decode(body[:head_chars])[:head_len], dtype="<u8")
+    block, partial, csizes = int(head[1]), int(head[2]), head[3:]
+    data = base64.b64decode(body[head_chars:])
+    out, pos = [], 0
+    for k, cs in enumerate(csizes):
+        raw = zlib.decompress(data[pos:pos + int(cs)])
+        assert len(raw) == (partial if (k == n_blocks - 1 and partial) else block)
+        out.append(raw)
+        pos += int(cs)
+    return b"".join(out)
+
+
+def test_device_data_path_matches_host_evaluation_and_binary_vtu_decodes(tmp_path, monkeypatch):
+    """(f)2/(f)3: bar data, error sums and output patches evaluated on the GPU from the unmodified data header give
+    the numbers of the host loops; the zlib/base64 .vtu holds exactly the values of the ASCII writer."""
+    p = pkg()
+    param = os.path.join(ROOT, "parameter.txt")
+    runs = {}
+    for mode in ("device", "host"):
+        out = tmp_path / mode
+        os.makedirs(out / "space-time-plots")
+        os.makedirs(out / "time-step-plots")
+        monkeypatch.setenv("MMMFE_HOST_DATA", "1" if mode == "host" else "0")
+        monkeypatch.setenv("MMMFE_VTU_ASCII", "1" if mode == "host" else "0")
+        reps, res, lam = p.host_run(param, verbose=0, write_output=1, num_refinement=2, output_dir=str(out))
+        runs[mode] = (reps, res, lam)
+    for rd, rh in zip(runs["device"][0], runs["host"][0]):
+        assert rd["gmres_iterations"] == rh["gmres_iterations"]
+        assert rd["r_norm"] == pytest.approx(rh["r_norm"], rel=1e-13)
+        for key in ("velocity_l2l2", "pressure_dg", "pressure_l2l2", "lambda_l2"):
+            assert rd[key] == pytest.approx(rh[key], rel=1e-11), key
+    assert rel_l2(runs["device"][2], runs["host"][2]) < 1e-11
+    # space-time output of subdomain 2 (cycle 1: 8 x 8 x 8 cells): binary arrays against the ASCII file
+    tb = (tmp_path / "device" / "space-time-plots" / "st_solution_d3_p0002.vtu").read_text()
+    ta = (tmp_path / "host" / "space-time-plots" / "st_solution_d3_p0002.vtu").read_text()
+    assert 'compressor="vtkZLibDataCompressor"' in tb and 'NumberOfCells="512"' in tb and 'Name="u"' in tb
+    import re
+
+    def ascii_array(name, dtype=float):
+        m = re.search(r'<DataArray[^>]*' + name + r'[^>]*format="ascii">\n(.*?)</DataArray>', ta, flags=re.S)
+        return np.array(m.group(1).split(), dtype=dtype)
+
+    pts_b = np.frombuffer(_decode_vtu_array(tb, 'NumberOfComponents="3" format'), dtype="<f8")
+    m = re.search(r'<Points>\n<DataArray[^>]*format="ascii">\n(.*?)</DataArray>', ta, flags=re.S)
+    pts_a = np.array(m.group(1).split(), dtype=float)
+    np.testing.assert_allclose(pts_b, pts_a, rtol=0, atol=1e-11)
+    np.testing.assert_allclose(np.frombuffer(_decode_vtu_array(tb, 'Name="u"'), dtype="<f8"), ascii_array('Name="u"'),
+                               rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(np.frombuffer(_decode_vtu_array(tb, 'Name="p"'), dtype="<f8"), ascii_array('Name="p"'),
+                               rtol=1e-9, atol=1e-9)
+    assert np.array_equal(np.frombuffer(_decode_vtu_array(tb, 'Name="connectivity"'), dtype="<i8"),
+                          ascii_array('Name="connectivity"', dtype=np.int64))
+    assert np.array_equal(np.frombuffer(_decode_vtu_array(tb, 'Name="offsets"'), dtype="<i8"),
+                          ascii_array('Name="offsets"', dtype=np.int64))
+    assert set(np.frombuffer(_decode_vtu_array(tb, 'Name="types"'), dtype="u1")) == {12}

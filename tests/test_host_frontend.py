@@ -100,3 +100,28 @@ def test_reference_data_headers_compile_against_the_shim():
         r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", shim, "-x", "c++", "-"], input=src, text=True,
                            capture_output=True)
         assert r.returncode == 0, (f, r.stderr[:500])
+
+
+def test_reference_data_headers_compile_for_the_device():
+    """The same unmodified headers must also build for sm_100a through host/data_device.cu (bar data, error sums and
+    output patches are then evaluated by CUDA kernels).  Three of the ten here to keep the CPU suite short; all ten
+    were compiled when the path was written."""
+    import shutil
+    import subprocess
+    import tempfile
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    files = [f"/root/reference/inc/{n}" for n in ("data.h", "data_sinx_siny.h", "data_const.h")]
+    if not all(os.path.exists(f) for f in files):
+        pytest.skip("/root/reference is not present on this machine")
+    host = os.path.join(ROOT, "mmmfe-st-dd_b200", "host")
+    with tempfile.TemporaryDirectory() as tmp:
+        procs = [subprocess.Popen([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-fmad=false",
+                                   "-diag-suppress", "20012,20014,940,20011,20015,177", "-I", os.path.join(host, "shim"),
+                                   "-I", host, "-I", os.path.join(ROOT, "include"), f'-DMMMFE_DATA_HEADER="{f}"', "-c",
+                                   os.path.join(host, "data_device.cu"), "-o", os.path.join(tmp, f"d{i}.o")],
+                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for i, f in enumerate(files)]
+        for f, p in zip(files, procs):
+            out = p.communicate()[0]
+            assert p.returncode == 0, (f, out[:800])
