@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -247,7 +248,13 @@ struct mmmfe_ctx {
   DevBuf<int64_t> send_index;
   DevBuf<double> send_buf, recv_buf;
   // GMRES workspace
-  DevBuf<double> Q, h_dev, norm_dev;
+  DevBuf<double> Q, h_dev, norm_dev, arn_scratch;
+  DevBuf<unsigned int> arn_ticket;
+  int gmres_lookahead = -1;        // iterations enqueued ahead of the host's stop test; -1: 3 on the basis operator, else 0
+  int gmres_surplus = 0;           // iterations of the last solve that ran beyond the converged one
+  double *gmres_ring = nullptr;    // pinned
+  size_t gmres_ring_dbl = 0;
+  std::vector<cudaEvent_t> gmres_events;
   int64_t q_rows = 0;
   double factor_seconds = 0.0;
   long long launch_base = 0;
@@ -360,43 +367,79 @@ static void build_schur(const Sub &sd, HostCsr &S, HostCsr &kup, HostCsr &kpu, s
   const HostCsr &K = sd.matrix;
   if (K.n_rows != nf + np || K.n_cols != nf + np) fail(MMMFE_E_INVALID, "matrix must be (n_flux+n_pressure)^2");
   minv.assign(np, 0.0);
-  kpu.n_rows = np; kpu.n_cols = nf; kpu.rp.assign(1, 0);
+  // Two passes per block (count, prefix sum, fill), rows in parallel; the entries of a row keep the order of the
+  // serial construction (first appearance), so the matrices are the same bit for bit.
+  int bad = 0;
+  kpu.n_rows = np; kpu.n_cols = nf; kpu.rp.assign(size_t(np) + 1, 0);
+#pragma omp parallel for schedule(static) reduction(max : bad)
   for (int32_t c = 0; c < np; ++c) {
     double d = 0.0;
+    int64_t cnt = 0;
     for (int64_t e = K.rp[nf + c]; e < K.rp[nf + c + 1]; ++e) {
       const int32_t col = K.col[e];
-      if (col < nf) {
-        if (K.val[e] != 0.0) { kpu.col.push_back(col); kpu.val.push_back(K.val[e]); }
-      } else if (col == nf + c) d += K.val[e];
-      else if (K.val[e] != 0.0) fail(MMMFE_E_UNSUPPORTED, "pressure block is not diagonal (only DGQ0 is on the path)");
+      if (col < nf) cnt += K.val[e] != 0.0;
+      else if (col == nf + c) d += K.val[e];
+      else if (K.val[e] != 0.0) bad = std::max(bad, 1);
     }
-    if (!(d > 0.0)) fail(MMMFE_E_UNSUPPORTED, "c0 * |cell| must be positive (c0 = 0 is not on the accelerated path)");
+    if (!(d > 0.0)) bad = std::max(bad, 2);
     minv[c] = 1.0 / d;
-    kpu.rp.push_back(int64_t(kpu.col.size()));
+    kpu.rp[c + 1] = cnt;
   }
-  kup.n_rows = nf; kup.n_cols = np; kup.rp.assign(1, 0);
-  S.n_rows = S.n_cols = nf; S.rp.assign(1, 0);
-  std::vector<int32_t> rc;
-  std::vector<double> rv;
-  for (int32_t e = 0; e < nf; ++e) {
-    rc.clear(); rv.clear();
+  if (bad == 1) fail(MMMFE_E_UNSUPPORTED, "pressure block is not diagonal (only DGQ0 is on the path)");
+  if (bad == 2) fail(MMMFE_E_UNSUPPORTED, "c0 * |cell| must be positive (c0 = 0 is not on the accelerated path)");
+  for (int32_t c = 0; c < np; ++c) kpu.rp[c + 1] += kpu.rp[c];
+  kpu.col.resize(size_t(kpu.rp[np])); kpu.val.resize(size_t(kpu.rp[np]));
+#pragma omp parallel for schedule(static)
+  for (int32_t c = 0; c < np; ++c) {
+    int64_t o = kpu.rp[c];
+    for (int64_t e = K.rp[nf + c]; e < K.rp[nf + c + 1]; ++e)
+      if (K.col[e] < nf && K.val[e] != 0.0) { kpu.col[o] = K.col[e]; kpu.val[o] = K.val[e]; ++o; }
+  }
+  kup.n_rows = nf; kup.n_cols = np; kup.rp.assign(size_t(nf) + 1, 0);
+  S.n_rows = S.n_cols = nf; S.rp.assign(size_t(nf) + 1, 0);
+  // one row of S = A + (dt / c0) B^T M^-1 B and of K_up, into small fixed buffers
+  constexpr int RW = 64;
+  auto row_of = [&](int32_t e, int32_t *rc, double *rv, int &n_s, int32_t *uc, double *uv, int &n_u) {
+    n_s = n_u = 0;
     auto add = [&](int32_t col, double v) {
-      for (size_t t = 0; t < rc.size(); ++t) if (rc[t] == col) { rv[t] += v; return; }
-      rc.push_back(col); rv.push_back(v);
+      for (int t = 0; t < n_s; ++t) if (rc[t] == col) { rv[t] += v; return; }
+      if (n_s < RW) { rc[n_s] = col; rv[n_s] = v; }
+      ++n_s;
     };
     for (int64_t k = K.rp[e]; k < K.rp[e + 1]; ++k) {
       const int32_t col = K.col[k];
       if (col < nf) add(col, K.val[k]);
       else if (K.val[k] != 0.0) {
         const int32_t cell = col - nf;
-        kup.col.push_back(cell); kup.val.push_back(K.val[k]);
+        if (n_u < RW) { uc[n_u] = cell; uv[n_u] = K.val[k]; }
+        ++n_u;
         const double f = -K.val[k] * minv[cell];
         for (int64_t t = kpu.rp[cell]; t < kpu.rp[cell + 1]; ++t) add(kpu.col[t], f * kpu.val[t]);
       }
     }
-    kup.rp.push_back(int64_t(kup.col.size()));
-    for (size_t t = 0; t < rc.size(); ++t) { S.col.push_back(rc[t]); S.val.push_back(rv[t]); }
-    S.rp.push_back(int64_t(S.col.size()));
+  };
+  int wide = 0;
+#pragma omp parallel for schedule(static) reduction(max : wide)
+  for (int32_t e = 0; e < nf; ++e) {
+    int32_t rc[RW], uc[RW];
+    double rv[RW], uv[RW];
+    int n_s, n_u;
+    row_of(e, rc, rv, n_s, uc, uv, n_u);
+    if (n_s > RW || n_u > RW) wide = 1;
+    S.rp[e + 1] = n_s; kup.rp[e + 1] = n_u;
+  }
+  if (wide) fail(MMMFE_E_UNSUPPORTED, "a flux row of the saddle matrix couples more than 64 dofs");
+  for (int32_t e = 0; e < nf; ++e) { S.rp[e + 1] += S.rp[e]; kup.rp[e + 1] += kup.rp[e]; }
+  S.col.resize(size_t(S.rp[nf])); S.val.resize(size_t(S.rp[nf]));
+  kup.col.resize(size_t(kup.rp[nf])); kup.val.resize(size_t(kup.rp[nf]));
+#pragma omp parallel for schedule(static)
+  for (int32_t e = 0; e < nf; ++e) {
+    int32_t rc[RW], uc[RW];
+    double rv[RW], uv[RW];
+    int n_s, n_u;
+    row_of(e, rc, rv, n_s, uc, uv, n_u);
+    for (int t = 0; t < n_s; ++t) { S.col[S.rp[e] + t] = rc[t]; S.val[S.rp[e] + t] = rv[t]; }
+    for (int t = 0; t < n_u; ++t) { kup.col[kup.rp[e] + t] = uc[t]; kup.val[kup.rp[e] + t] = uv[t]; }
   }
 }
 
@@ -590,6 +633,8 @@ static std::vector<int32_t> subtree_classes(const NdTree &tr, const HostCsr &S, 
   return cls;
 }
 
+static double nd_factor_values(int nx, int ny, int leaf_cells);
+
 static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax, double sm_share) {
   const auto t0 = std::chrono::steady_clock::now();
   const bool prof = std::getenv("MMMFE_SETUP_PROFILE") != nullptr;
@@ -667,6 +712,12 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax, 
     }
   }
   lap("tree + sweep plan (host)");
+  if (prof) {  // the size-only recursion that sizes the SM shares must agree with the tree
+    double vals = 0;
+    for (const NdNode &n : tr.nodes) vals += double(n.s) * (double(n.s) + 2.0 * n.b);
+    const double est = nd_factor_values(sd.nx, sd.ny, c->leaf_cells);
+    if (vals != est) fail(MMMFE_E_INVALID, "nd_factor_values %.0f != tree %.0f", est, vals);
+  }
   const int32_t nn = int32_t(tr.nodes.size());
   // user numbering of the front variables
   std::vector<int32_t> idx_user(tr.idx.size());
@@ -1603,6 +1654,30 @@ static void setup_basis_operator(mmmfe_ctx *c, const std::vector<int> &group_of)
 // =================================================================================================================
 // setup
 // =================================================================================================================
+// sum over the fronts of s (s + 2 b) for the nested dissection NdTree::build would produce (same bisection rule,
+// sizes only): the factor values one solve multiplies with, without building the tree
+static double nd_factor_values(int nx, int ny, int leaf_cells) {
+  std::function<double(int, int, int, int)> rec = [&](int i0, int i1, int j0, int j1) -> double {
+    const int w = i1 - i0, h = j1 - j0;
+    double below = 0.0, s;
+    if (int64_t(w) * h <= leaf_cells || (w == 1 && h == 1)) {
+      s = double(h) * ((w - 1) + (i0 == 0) + (i1 == nx)) + double(w) * ((h - 1) + (j0 == 0) + (j1 == ny));
+      if (s == 0.0) return 0.0;
+    } else if (w >= h) {
+      const int is = i0 + w / 2;
+      below = rec(i0, is, j0, j1) + rec(is, i1, j0, j1);
+      s = h;
+    } else {
+      const int js = j0 + h / 2;
+      below = rec(i0, i1, j0, js) + rec(i0, i1, js, j1);
+      s = w;
+    }
+    const double b = double(h) * ((i0 > 0) + (i1 < nx)) + double(w) * ((j0 > 0) + (j1 < ny));
+    return below + s * (s + 2.0 * b);
+  };
+  return rec(0, nx, 0, ny);
+}
+
 static bool same_matrix(const Sub &a, const Sub &b) {
   return a.nx == b.nx && a.ny == b.ny && a.nt == b.nt && a.nf == b.nf && a.np == b.np && a.dt == b.dt &&
          a.canon == b.canon && a.matrix.rp == b.matrix.rp && a.matrix.col == b.matrix.col &&
@@ -1618,6 +1693,15 @@ static void setup(mmmfe_ctx *c) {
   CUDA_CHECK(cudaEventCreate(&c->ev_t0));
   CUDA_CHECK(cudaEventCreate(&c->ev_t1));
   const int ns = int(c->subs.size());
+  const bool prof = std::getenv("MMMFE_SETUP_PROFILE") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!prof) return;
+    cudaDeviceSynchronize();
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[setup profile] set-up: %-36s %8.1f ms\n", what, std::chrono::duration<double>(now - t_last).count() * 1e3);
+    t_last = now;
+  };
   // ---- group identical matrices, factorise one representative each ----
   std::vector<int> group_of(ns, -1);
   std::vector<int> reps;
@@ -1636,10 +1720,7 @@ static void setup(mmmfe_ctx *c) {
     double tot = 0;
     for (size_t g = 0; g < reps.size(); ++g) {
       const Sub &sd = *c->subs[reps[g]];
-      NdTree probe;
-      probe.build(sd.nx, sd.ny, c->leaf_cells, 0);
-      double vals = 0;
-      for (const NdNode &n : probe.nodes) vals += double(n.s) * (double(n.s) + 2.0 * n.b);
+      const double vals = nd_factor_values(sd.nx, sd.ny, c->leaf_cells);
       int cnt = 0;
       for (int i = 0; i < ns; ++i) cnt += group_of[i] == int(g);
       w[g] = vals * sd.nt * ((cnt + 3) / 4);
@@ -1656,12 +1737,14 @@ static void setup(mmmfe_ctx *c) {
     if (n_sm[big] >= sms / 16)
       for (size_t g = 0; g < reps.size(); ++g) share[g] = double(n_sm[g]) / sms;
   }
+  lap("matrix groups + SM shares");
   for (size_t g = 0; g < reps.size(); ++g) {
     int cnt = 0;
     for (int i = 0; i < ns; ++i) cnt += group_of[i] == int(g);
     c->factors.push_back(factorize(c, *c->subs[reps[g]], cnt <= 1 ? 1 : (cnt == 2 ? 2 : 4), share[g]));
     c->factor_seconds += c->factors.back()->seconds;
   }
+  lap("factorize (all groups)");
   // ---- interface and fine-trace layouts ----
   int64_t io = 0, fo = 0;
   std::map<std::pair<int, int>, int64_t> local_off;  // (gid, side) -> offset
@@ -1716,6 +1799,7 @@ static void setup(mmmfe_ctx *c) {
   c->send.alloc(size_t(io)); c->ap.alloc(size_t(io)); c->qin.alloc(size_t(io)); c->lam.alloc(size_t(io));
   c->r0.alloc(size_t(io));
   c->lam_bar.zero(); c->trace.zero(); c->qin.zero(); c->lam.zero();
+  lap("projector + exchange tables");
   // ---- batches ----
   for (size_t g = 0; g < reps.size(); ++g) {
     std::vector<int32_t> mem;
@@ -1761,6 +1845,7 @@ static void setup(mmmfe_ctx *c) {
   }
   CUDA_CHECK(cudaDeviceSynchronize());
   c->is_setup = true;
+  lap("batches + sweep schedules");
   // Both star-sweep implementations are exact; keep the one that is faster for THIS configuration.  One star sweep
   // each on the SAME non-zero pseudo-random interface data: the traces of the two implementations must agree to
   // 1e-11 (set-up fails otherwise -- the persistent kernel's plan depends on the grid, the SM share and M, so this is
@@ -1770,20 +1855,24 @@ static void setup(mmmfe_ctx *c) {
   bool any_sweep = false;
   for (auto &b : c->batches) any_sweep |= b->sweep;
   if (any_sweep && (c->sweep_autotune || c->sweep_crosscheck)) {
-    // The comparison runs on the first tune_steps time levels only (every level walks the same entry lists and the
+    // The comparison runs on the first tune_steps of the longest sweep's time levels (every level walks the same entry lists and the
     // same kernels, so both the check and the time ratio carry over): a full sweep of each implementation, twice,
     // was 1.1 s of the set-up on configs[1].
     auto timed = [&](bool with_sweep) {
       std::vector<bool> keep;
       std::vector<int> keep_nt;
+      int nt_max = 1;
+      for (auto &b : c->batches) nt_max = std::max(nt_max, b->nt);
       for (auto &b : c->batches) {
         keep.push_back(b->sweep); b->sweep = b->sweep && with_sweep;
         keep_nt.push_back(b->nt);
-        if (c->tune_steps > 0) b->nt = std::min(b->nt, c->tune_steps);
+        // every batch keeps its share of the sweep (the SM shares of concurrent kernels are sized for whole sweeps)
+        if (c->tune_steps > 0 && nt_max > c->tune_steps)
+          b->nt = std::max(1, int((int64_t(b->nt) * c->tune_steps + nt_max - 1) / nt_max));
         b->sargs.n_steps = b->nt;
       }
       float best = 0;
-      for (int rep = 0; rep < (with_sweep ? 1 : 2); ++rep) {  // the first pass of the per-level path captures its graphs
+      for (int rep = 0; rep < 2; ++rep) {  // first pass: graph capture (per-level path), first-launch costs (persistent kernel)
         CUDA_CHECK(cudaEventRecord(c->ev_t0, c->stream));
         run_star_sweeps(c, SWEEP_STAR);
         CUDA_CHECK(cudaEventRecord(c->ev_t1, c->stream));
@@ -1830,7 +1919,11 @@ static void setup(mmmfe_ctx *c) {
     c->lam_bar.zero(c->stream); c->trace.zero(c->stream);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   }
+  if (prof) std::fprintf(stderr, "[setup profile] set-up: cross-check on %d levels: persistent %.3f ms, per-level %.3f ms, rel diff %.2e\n",
+                         c->tune_steps, c->tune_ms_sweep, c->tune_ms_levels, c->tune_rel_diff);
+  lap("sweep cross-check / selection");
   setup_basis_operator(c, group_of);
+  lap("multiscale basis");
   // NCCL opens its point-to-point channels on first use (measured: 1.5 s on 8 ranks, charged to the bar sweep): do one
   // exchange of zeros now, where set-up time belongs
   if (!c->peers.empty()) {
@@ -1971,7 +2064,16 @@ static void bar_sweep(mmmfe_ctx *c) {
   c->final_done = false;
 }
 
-// local_gmres, src/darcy_vtdd.cc:1139-1521
+// local_gmres, src/darcy_vtdd.cc:1139-1521.
+//
+// The reference decides after every iteration (Givens rotation + stop test on the host).  Here the GPU never waits
+// for that decision: the norm h[k+1] stays on the device (the next Krylov vector is scaled by a kernel that reads
+// it), the Hessenberg column travels to a pinned ring slot behind an event, and the host enqueues up to
+// `gmres_lookahead` iterations AHEAD of the one whose column it is rotating.  When the stop test fires at iteration
+// j, the iterations enqueued beyond j are surplus Krylov vectors that are simply not used (lambda is built from the
+// first k_counter columns, as in the reference), so iteration counts, residual history and lambda are those of the
+// in-order algorithm.  Lookahead 0 is the in-order loop; it is the default whenever one operator application is long
+// against a launch (star sweeps), where running ahead would only waste sweeps after convergence.
 static void gmres(mmmfe_ctx *c, double tol, int max_iter, mmmfe_gmres_info *info, double *hist, int hist_cap,
                   double *lambda_out) {
   if (!c->bar_done) fail(MMMFE_E_INVALID, "mmmfe_bar_sweep must precede mmmfe_gmres_solve");
@@ -1980,11 +2082,27 @@ static void gmres(mmmfe_ctx *c, double tol, int max_iter, mmmfe_gmres_info *info
   const int64_t rows = int64_t(max_iter) + 2;
   if (c->q_rows < rows) { c->Q.alloc(size_t(rows) * len); c->q_rows = rows; }
   c->h_dev.alloc(size_t(max_iter) + 4);
-  c->norm_dev.alloc(1024);
+  c->norm_dev.alloc(8);
+  c->arn_scratch.alloc(arnoldi_scratch_doubles(len, max_iter + 2));
+  if (!c->arn_ticket.p) { c->arn_ticket.alloc(4); c->arn_ticket.zero(c->stream); }
   cudaStream_t st = c->stream;
   double *Q = c->Q.p;
+  const int lag = c->gmres_lookahead >= 0 ? c->gmres_lookahead : (c->use_basis ? 3 : 0);
+  const int L = lag + 1;
+  // pinned ring: per slot the Hessenberg column (max_iter + 1), ||w||^2 and the sweep kernel's watchdog flag
+  const size_t slot_dbl = size_t(max_iter) + 4;
+  if (c->gmres_ring_dbl < slot_dbl * L) {
+    if (c->gmres_ring) cudaFreeHost(c->gmres_ring);
+    CUDA_CHECK(cudaMallocHost(&c->gmres_ring, slot_dbl * L * sizeof(double)));
+    c->gmres_ring_dbl = slot_dbl * L;
+  }
+  while (int(c->gmres_events.size()) < L) {
+    cudaEvent_t e;
+    CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->gmres_events.push_back(e);
+  }
   // initial residual r was formed at the end of the bar sweep
-  launch_multi_dot(len, c->r0.p, c->r0.p, len, 1, c->h_dev.p, st);
+  launch_multi_dot(len, c->r0.p, c->r0.p, len, 1, c->h_dev.p, c->arn_scratch.p, c->arn_ticket.p, st);
   allreduce_sum(c, c->h_dev.p, 1);
   double rr = 0.0;
   CUDA_CHECK(cudaMemcpyAsync(&rr, c->h_dev.p, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1994,24 +2112,39 @@ static void gmres(mmmfe_ctx *c, double tol, int max_iter, mmmfe_gmres_info *info
   std::vector<double> cs, sn, beta{r_norm};
   std::vector<std::vector<double>> H;
   std::vector<double> res{1.0};
-  std::vector<double> hh(size_t(max_iter) + 4);
   int k = 0, its = 0, converged = 0;
   CUDA_CHECK(cudaEventRecord(c->ev_t0, st));
+  // one Arnoldi step on the device, everything stream-ordered, nothing waits for the host
+  auto enqueue = [&](int kk) {
+    double *slot = c->gmres_ring + size_t(kk % L) * slot_dbl;
+    apply_operator(c, Q + int64_t(kk) * len, c->ap.p);
+    launch_multi_dot(len, c->ap.p, Q, len, kk + 1, c->h_dev.p, c->arn_scratch.p, c->arn_ticket.p, st);  // :1416-1422
+    allreduce_sum(c, c->h_dev.p, size_t(kk) + 1);                                                        // :1427-1432
+    launch_cgs_update(len, c->ap.p, Q, len, kk + 1, c->h_dev.p, c->norm_dev.p, c->arn_scratch.p, c->arn_ticket.p, st);  // :1436-1441
+    allreduce_sum(c, c->norm_dev.p, 1);                                                                  // :1449-1454
+    CUDA_CHECK(cudaMemcpyAsync(slot, c->h_dev.p, (size_t(kk) + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(slot + kk + 1, c->norm_dev.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (c->abort_flag)
+      CUDA_CHECK(cudaMemcpyAsync(slot + kk + 2, const_cast<int *>(c->abort_flag), sizeof(int), cudaMemcpyDeviceToHost, st));
+    else
+      std::memset(slot + kk + 2, 0, sizeof(double));
+    CUDA_CHECK(cudaEventRecord(c->gmres_events[kk % L], st));
+    launch_scale_store(len, c->ap.p, 0.0, Q + int64_t(kk + 1) * len, st, c->norm_dev.p);  // :1458-1463
+  };
+  int enq = 0;  // iterations enqueued so far
   while (k < max_iter) {
-    apply_operator(c, Q + int64_t(k) * len, c->ap.p);
+    while (enq < max_iter && enq - k <= lag) enqueue(enq++);
+    CUDA_CHECK(cudaEventSynchronize(c->gmres_events[k % L]));
+    const double *slot = c->gmres_ring + size_t(k % L) * slot_dbl;
+    int flag = 0;
+    std::memcpy(&flag, slot + k + 2, sizeof(int));
+    if (flag) {
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      check_watchdog(c);
+    }
     ++its;  // cg_iteration++, :1363
-    launch_multi_dot(len, c->ap.p, Q, len, k + 1, c->h_dev.p, st);  // :1416-1422
-    allreduce_sum(c, c->h_dev.p, size_t(k) + 1);                      // :1427-1432
-    launch_cgs_update(len, c->ap.p, Q, len, k + 1, c->h_dev.p, c->norm_dev.p, st);  // :1436-1441
-    allreduce_sum(c, c->norm_dev.p, 1);                                               // :1449-1454
-    CUDA_CHECK(cudaMemcpyAsync(hh.data(), c->h_dev.p, (size_t(k) + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
-    double n2 = 0.0;
-    CUDA_CHECK(cudaMemcpyAsync(&n2, c->norm_dev.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    check_watchdog(c);
-    std::vector<double> h(hh.begin(), hh.begin() + k + 1);
-    h.push_back(std::sqrt(n2));  // :1455
-    launch_scale_store(len, c->ap.p, h[k + 1], Q + int64_t(k + 1) * len, st);  // :1458-1463
+    std::vector<double> h(slot, slot + k + 1);
+    h.push_back(std::sqrt(slot[k + 1]));  // :1455
     // apply_givens_rotation, :1092-1118
     for (int i = 0; i < k; ++i) {
       const double temp = cs[i] * h[i] + sn[i] * h[i + 1];
@@ -2034,6 +2167,7 @@ static void gmres(mmmfe_ctx *c, double tol, int max_iter, mmmfe_gmres_info *info
     ++k;
   }
   CUDA_CHECK(cudaEventRecord(c->ev_t1, st));
+  c->gmres_surplus = enq - its;
   // back_solve over k columns, :1121-1135; y[k] stays 0
   std::vector<double> y(size_t(k) + 1, 0.0);
   for (int i = k - 1; i >= 0; --i) {
@@ -2044,6 +2178,7 @@ static void gmres(mmmfe_ctx *c, double tol, int max_iter, mmmfe_gmres_info *info
   launch_axpy_rows(len, Q, len, k + 1, c->h_dev.p, c->lam.p, st);  // :1517-1521
   if (lambda_out) CUDA_CHECK(cudaMemcpyAsync(lambda_out, c->lam.p, size_t(len) * sizeof(double), cudaMemcpyDeviceToHost, st));
   CUDA_CHECK(cudaStreamSynchronize(st));
+  check_watchdog(c);
   if (info) {
     info->iterations = its; info->converged = converged; info->r_norm = r_norm; info->final_residual = res.back();
     info->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
@@ -2107,6 +2242,8 @@ int mmmfe_destroy(mmmfe_ctx *c) {
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->abort_flag) cudaFree(c->abort_flag);
+  if (c->gmres_ring) cudaFreeHost(c->gmres_ring);
+  for (cudaEvent_t e : c->gmres_events) cudaEventDestroy(e);
   delete c;
   return MMMFE_OK;
 }
@@ -2131,6 +2268,7 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   else if (k == "sweep_spin_ns") c->sweep_spin_ns = std::max(0, int(value));
   else if (k == "sweep_autotune") c->sweep_autotune = value != 0;
   else if (k == "tune_steps") c->tune_steps = int(value);
+  else if (k == "gmres_lookahead") c->gmres_lookahead = int(value);
   else if (k == "sweep_crosscheck") c->sweep_crosscheck = value != 0;
   else if (k == "operator") {
     if (value != 0 && value != 1 && value != 2) { c->err = "operator must be 0 (sweeps), 1 (multiscale basis) or 2 (auto)"; return MMMFE_E_INVALID; }
@@ -2550,6 +2688,7 @@ int64_t mmmfe_stat(const mmmfe_ctx *c, const char *key) {
   if (k == "toeplitz_tiles") return c->n_toep_tiles;
   if (k == "toeplitz_mflop") return int64_t(c->toep_flops / 1e6);
   if (k == "toeplitz_mbytes") return int64_t(c->toep_bytes / 1e6);
+  if (k == "gmres_surplus") return c->gmres_surplus;
   if (k == "tune_us_sweep") return int64_t(c->tune_ms_sweep * 1e3);
   if (k == "tune_us_levels") return int64_t(c->tune_ms_levels * 1e3);
   // relative l2 difference of the two star-sweep implementations at set-up, in units of 1e-18 (-1: not run)

@@ -816,67 +816,159 @@ __device__ __forceinline__ double block_sum_512(double v, double *sm) {
   return r;  // valid in thread 0
 }
 
-__global__ void __launch_bounds__(512) k_multi_dot(int64_t len, const double *__restrict__ w,
-                                                   const double *__restrict__ Q, int64_t ldq,
-                                                   double *__restrict__ h) {
-  __shared__ double sm[16];
-  const double *q = Q + int64_t(blockIdx.x) * ldq;
-  double acc = 0.0;
-  for (int64_t j = threadIdx.x; j < len; j += blockDim.x) acc += w[j] * q[j];
-  const double r = block_sum_512(acc, sm);
-  if (threadIdx.x == 0) h[blockIdx.x] = r;
-}
+// ---- Arnoldi / classical Gram-Schmidt on the interface vector (src/darcy_vtdd.cc:1413-1463) ------------------------
+// The interface vector is cut into segments of ARN_SEG entries; a block keeps its segment of w in registers and
+// walks a chunk of the Krylov vectors, so w is read once per block and the grid has (segments x vector chunks)
+// blocks however few vectors there are.  Partial sums go to scratch[vector][segment]; the LAST block to finish
+// (ticket counter) adds them in segment order: one launch, no atomics on the data, bitwise reproducible.
+constexpr int ARN_THREADS = 256;
+constexpr int ARN_PER = 4;                       // entries per thread
+constexpr int ARN_SEG = ARN_THREADS * ARN_PER;   // 1024
 
-void launch_multi_dot(int64_t len, const double *w, const double *Q, int64_t ldq, int32_t k_plus_1, double *h,
-                      cudaStream_t st) {
-  k_multi_dot<<<k_plus_1, 512, 0, st>>>(len, w, Q, ldq, h);
-  launch_counter_add(1);
-}
-
-constexpr int CGS_BLOCKS = 592;  // 4 per SM
-
-__global__ void __launch_bounds__(512) k_cgs_update(int64_t len, double *__restrict__ w,
-                                                    const double *__restrict__ Q, int64_t ldq, int32_t k_plus_1,
-                                                    const double *__restrict__ h, double *__restrict__ partial) {
-  __shared__ double sm[16];
-  double acc2 = 0.0;
-  for (int64_t j = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; j < len; j += int64_t(gridDim.x) * blockDim.x) {
-    double v = w[j];
-    for (int i = 0; i < k_plus_1; ++i) v -= h[i] * Q[int64_t(i) * ldq + j];
-    w[j] = v;
-    acc2 += v * v;
+__device__ __forceinline__ double block_sum_256(double v, double *sm) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();  // sm may still be read by the previous call
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (warp == 0) {
+    r = (lane < (ARN_THREADS >> 5)) ? sm[lane] : 0.0;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
   }
-  const double r = block_sum_512(acc2, sm);
-  if (threadIdx.x == 0) partial[blockIdx.x] = r;
+  return r;  // valid in thread 0
 }
 
-__global__ void __launch_bounds__(512) k_final_sum(const double *__restrict__ partial, int n, double *out) {
-  __shared__ double sm[16];
-  double acc = 0.0;
-  for (int j = threadIdx.x; j < n; j += blockDim.x) acc += partial[j];
-  const double r = block_sum_512(acc, sm);
-  if (threadIdx.x == 0) out[0] = r;
+// true in every thread of the last block of the grid to get here (all other blocks' global writes are visible)
+__device__ __forceinline__ bool last_block(unsigned int *ticket) {
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int total = gridDim.x * gridDim.y;
+    const unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == total - 1) ? 1u : 0u;
+    if (s_last) *ticket = 0u;  // ready for the next launch (stream-ordered)
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0u;
 }
 
-// norm2 must have room for 1 + CGS_BLOCKS doubles; result in norm2[0]
-void launch_cgs_update(int64_t len, double *w, const double *Q, int64_t ldq, int32_t k_plus_1, const double *h,
-                       double *norm2, cudaStream_t st) {
-  k_cgs_update<<<CGS_BLOCKS, 512, 0, st>>>(len, w, Q, ldq, k_plus_1, h, norm2 + 1);
+__global__ void __launch_bounds__(ARN_THREADS) k_multi_dot(int64_t len, const double *__restrict__ w,
+                                                           const double *__restrict__ Q, int64_t ldq, int32_t n_vec,
+                                                           int32_t vec_per_block, double *__restrict__ scratch,
+                                                           unsigned int *ticket, double *__restrict__ h) {
+  __shared__ double sm[8];
+  const int n_seg = gridDim.x;
+  const int64_t j0 = int64_t(blockIdx.x) * ARN_SEG + threadIdx.x;
+  double wv[ARN_PER];
+#pragma unroll
+  for (int u = 0; u < ARN_PER; ++u) {
+    const int64_t j = j0 + u * ARN_THREADS;
+    wv[u] = j < len ? w[j] : 0.0;
+  }
+  const int v0 = blockIdx.y * vec_per_block, v1 = min(n_vec, v0 + vec_per_block);
+  for (int i = v0; i < v1; ++i) {
+    const double *q = Q + int64_t(i) * ldq;
+    double acc = 0.0;
+#pragma unroll
+    for (int u = 0; u < ARN_PER; ++u) {
+      const int64_t j = j0 + u * ARN_THREADS;
+      if (j < len) acc += wv[u] * q[j];
+    }
+    const double r = block_sum_256(acc, sm);
+    if (threadIdx.x == 0) scratch[int64_t(i) * n_seg + blockIdx.x] = r;
+  }
+  if (!last_block(ticket)) return;
+  // one warp per vector: lane l adds the segments l, l + 32, ... in order, then the lanes are combined by a fixed
+  // shuffle tree -- the same order on every launch
+  for (int i = threadIdx.x >> 5; i < n_vec; i += ARN_THREADS / 32) {
+    const double *p = scratch + int64_t(i) * n_seg;
+    double t = 0.0;
+    for (int sg = threadIdx.x & 31; sg < n_seg; sg += 32) t += __ldcg(p + sg);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) h[i] = t;
+  }
+}
+
+static int arnoldi_segments(int64_t len) { return int((len + ARN_SEG - 1) / ARN_SEG); }
+
+size_t arnoldi_scratch_doubles(int64_t len, int32_t max_vectors) {
+  return size_t(arnoldi_segments(len)) * size_t(max_vectors) + 16;
+}
+
+// h[i] = <w, Q_i>, i < k_plus_1.  scratch: arnoldi_scratch_doubles(len, k_plus_1); ticket: one zeroed counter.
+void launch_multi_dot(int64_t len, const double *w, const double *Q, int64_t ldq, int32_t k_plus_1, double *h,
+                      double *scratch, unsigned int *ticket, cudaStream_t st) {
+  const int n_seg = arnoldi_segments(len);
+  // enough blocks for four per SM when the vectors allow it
+  int chunks = std::max(1, std::min(k_plus_1, (592 + n_seg - 1) / n_seg));
+  const int per = (k_plus_1 + chunks - 1) / chunks;
+  chunks = (k_plus_1 + per - 1) / per;
+  k_multi_dot<<<dim3(n_seg, chunks), ARN_THREADS, 0, st>>>(len, w, Q, ldq, k_plus_1, per, scratch, ticket, h);
   launch_counter_add(1);
-  k_final_sum<<<1, 512, 0, st>>>(norm2 + 1, CGS_BLOCKS, norm2);
+}
+
+// w -= sum_i h[i] Q_i; norm2[0] = ||w||^2 (partials per segment, added in segment order by the last block)
+__global__ void __launch_bounds__(ARN_THREADS) k_cgs_update(int64_t len, double *__restrict__ w,
+                                                            const double *__restrict__ Q, int64_t ldq, int32_t k_plus_1,
+                                                            const double *__restrict__ h, double *__restrict__ scratch,
+                                                            unsigned int *ticket, double *__restrict__ norm2) {
+  __shared__ double sm[8];
+  const int64_t j0 = int64_t(blockIdx.x) * ARN_SEG + threadIdx.x;
+  double v[ARN_PER];
+#pragma unroll
+  for (int u = 0; u < ARN_PER; ++u) {
+    const int64_t j = j0 + u * ARN_THREADS;
+    v[u] = j < len ? w[j] : 0.0;
+  }
+#pragma unroll 2
+  for (int i = 0; i < k_plus_1; ++i) {
+    const double hi = h[i];
+    const double *q = Q + int64_t(i) * ldq;
+#pragma unroll
+    for (int u = 0; u < ARN_PER; ++u) {
+      const int64_t j = j0 + u * ARN_THREADS;
+      if (j < len) v[u] -= hi * q[j];
+    }
+  }
+  double acc2 = 0.0;
+#pragma unroll
+  for (int u = 0; u < ARN_PER; ++u) {
+    const int64_t j = j0 + u * ARN_THREADS;
+    if (j < len) { w[j] = v[u]; acc2 += v[u] * v[u]; }
+  }
+  const double r = block_sum_256(acc2, sm);
+  if (threadIdx.x == 0) scratch[blockIdx.x] = r;
+  if (!last_block(ticket)) return;
+  double t = 0.0;
+  for (int sg = threadIdx.x; sg < int(gridDim.x); sg += ARN_THREADS) t += __ldcg(scratch + sg);
+  const double tot = block_sum_256(t, sm);  // fixed tree
+  if (threadIdx.x == 0) norm2[0] = tot;
+}
+
+void launch_cgs_update(int64_t len, double *w, const double *Q, int64_t ldq, int32_t k_plus_1, const double *h,
+                       double *norm2, double *scratch, unsigned int *ticket, cudaStream_t st) {
+  k_cgs_update<<<arnoldi_segments(len), ARN_THREADS, 0, st>>>(len, w, Q, ldq, k_plus_1, h, scratch, ticket, norm2);
   launch_counter_add(1);
 }
 
 __global__ void __launch_bounds__(256) k_scale_store(int64_t len, const double *__restrict__ w, double inv,
-                                                     double *__restrict__ dst) {
+                                                     const double *__restrict__ norm2_dev, double *__restrict__ dst) {
   const int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (norm2_dev) inv = sqrt(norm2_dev[0]);  // IEEE square root: the value the host computes from the same number
   if (i < len) dst[i] = w[i] / inv;
 }
 
-// dst = w / inv  (the reference divides: q[i] /= h[k+1], src/darcy_vtdd.cc:1461)
-void launch_scale_store(int64_t len, const double *w, double inv, double *dst, cudaStream_t st) {
+// dst = w / inv  (the reference divides: q[i] /= h[k+1], src/darcy_vtdd.cc:1461); norm2_dev != nullptr: inv =
+// sqrt(*norm2_dev), read on the device (no host round trip between the norm and the next Krylov vector)
+void launch_scale_store(int64_t len, const double *w, double inv, double *dst, cudaStream_t st, const double *norm2_dev) {
   if (len <= 0) return;
-  k_scale_store<<<unsigned((len + 255) / 256), 256, 0, st>>>(len, w, inv, dst);
+  k_scale_store<<<unsigned((len + 255) / 256), 256, 0, st>>>(len, w, inv, norm2_dev, dst);
   launch_counter_add(1);
 }
 

@@ -146,13 +146,18 @@ void launch_spmv(int64_t n_rows, const int64_t *rp, const int32_t *col, const do
 void launch_exchange_combine(int64_t n, const double *send, const int64_t *partner, const double *recv, double sign,
                              double *out, cudaStream_t st);
 void launch_gather(int64_t n, const double *srcv, const int64_t *index, double *dst, cudaStream_t st);
-// h[i] = <w, Q_i>, i = 0..k  (classical Gram-Schmidt: all against the unmodified w)
+// h[i] = <w, Q_i>, i = 0..k  (classical Gram-Schmidt: all against the unmodified w).  scratch holds
+// arnoldi_scratch_doubles(len, k + 1) doubles, ticket is one zeroed counter (left zeroed); both are shared with
+// launch_cgs_update (stream-ordered).  Grid-wide, one launch, fixed summation order.
+size_t arnoldi_scratch_doubles(int64_t len, int32_t max_vectors);
 void launch_multi_dot(int64_t len, const double *w, const double *Q, int64_t ldq, int32_t k_plus_1, double *h,
-                      cudaStream_t st);
-// w -= sum_i h[i] Q_i ; partial[block] = sum w^2
+                      double *scratch, unsigned int *ticket, cudaStream_t st);
+// w -= sum_i h[i] Q_i ; norm2[0] = sum w^2
 void launch_cgs_update(int64_t len, double *w, const double *Q, int64_t ldq, int32_t k_plus_1, const double *h,
-                       double *norm2, cudaStream_t st);
-void launch_scale_store(int64_t len, const double *w, double inv, double *dst, cudaStream_t st);
+                       double *norm2, double *scratch, unsigned int *ticket, cudaStream_t st);
+// dst = w / inv, or w / sqrt(*norm2_dev) when norm2_dev is given
+void launch_scale_store(int64_t len, const double *w, double inv, double *dst, cudaStream_t st,
+                        const double *norm2_dev = nullptr);
 void launch_axpy_rows(int64_t len, const double *Q, int64_t ldq, int32_t n_rows, const double *y, double *out,
                       cudaStream_t st);
 

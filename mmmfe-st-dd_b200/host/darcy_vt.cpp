@@ -139,32 +139,32 @@ void init_sub(Sub &s, int r, int n0, int n1, const std::vector<int> &pat, double
   for (int l = 0; l < s.nt; ++l) { t += s.dt; s.levels_t[l] = t; }  // prm.time += prm.time_step, :887
 }
 
-// assemble_system, src/darcy_vtdd.cc:401-484: [[A, -B^T], [dt B, c0 M]], QGauss<2>(degree+2) = 2x2 points
+// assemble_system, src/darcy_vtdd.cc:401-484: [[A, -B^T], [dt B, c0 M]], QGauss<2>(degree+2) = 2x2 points.
+// Row-parallel: every row gathers the contributions of its (at most two) cells in cell order, which is the order
+// the reference's cell loop adds them in; explicit zeros of the local matrices are kept (same sparsity pattern).
 void assemble_matrix(Sub &s, double c0) {
   const int n = s.n, W = 12;
-  std::vector<int> cnt(n, 0), cols(size_t(n) * W);
-  std::vector<double> vals(size_t(n) * W);
-  auto add = [&](int r, int c, double v) {
-    int *rc = &cols[size_t(r) * W];
-    double *rv = &vals[size_t(r) * W];
-    for (int t = 0; t < cnt[r]; ++t) if (rc[t] == c) { rv[t] += v; return; }
-    if (cnt[r] >= W) throw std::runtime_error("matrix row overflow");
-    rc[cnt[r]] = c; rv[cnt[r]] = v; ++cnt[r];
-  };
+  std::unique_ptr<int[]> cnt(new int[n]), cols(new int[size_t(n) * W]);  // (written before they are read: no zero fill)
+  std::unique_ptr<double[]> vals(new double[size_t(n) * W]);
   std::vector<double> g, w;
   gauss01(2, g, w);
   const KInverse<2> k_inverse;
-  std::vector<dealii::Point<2>> pts(4);
-  std::vector<dealii::Tensor<2, 2>> kin(4);
   const double div[4] = {-1.0, 1.0, -1.0, 1.0};
-  for (int j = 0; j < s.ny; ++j)
-    for (int i = 0; i < s.nx; ++i) {
-      const int loc[4] = {j * (s.nx + 1) + i, j * (s.nx + 1) + i + 1, s.nxe + j * s.nx + i, s.nxe + (j + 1) * s.nx + i};
-      const int cell = s.nf + j * s.nx + i;
+  const int nx = s.nx, ny = s.ny;
+  // local mass matrices of all cells, 16 doubles each: aloc[e][f], e, f = x-left, x-right, y-bottom, y-top
+  std::unique_ptr<double[]> A(new double[size_t(s.np) * 16]);
+#pragma omp parallel
+  {
+    std::vector<dealii::Point<2>> pts(4);
+    std::vector<dealii::Tensor<2, 2>> kin(4);
+#pragma omp for schedule(static)
+    for (int c = 0; c < s.np; ++c) {
+      const int j = c / nx, i = c % nx;
+      double *aloc = &A[size_t(c) * 16];
       for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 2; ++b) pts[a * 2 + b] = dealii::Point<2>(s.x0 + (i + g[a]) * s.hx, s.y0 + (j + g[b]) * s.hy);
       k_inverse.value_list(pts, kin);
-      double aloc[4][4] = {{0}};
+      for (int t = 0; t < 16; ++t) aloc[t] = 0;
       for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 2; ++b) {
           const int q = a * 2 + b;
@@ -176,26 +176,64 @@ void assemble_matrix(Sub &s, double c0) {
               double v = 0;
               for (int d = 0; d < 2; ++d)
                 for (int d2 = 0; d2 < 2; ++d2) v += phi[e][d] * kin[q][d][d2] * phi[f][d2];
-              aloc[e][f] += jxw * v;
+              aloc[e * 4 + f] += jxw * v;
             }
         }
-      for (int e = 0; e < 4; ++e) {
-        for (int f = 0; f < 4; ++f) add(loc[e], loc[f], aloc[e][f]);
-        add(loc[e], cell, -div[e]);         // -phi_p div phi_u
-        add(cell, loc[e], s.dt * div[e]);   // dt div phi_u phi_p
-      }
-      add(cell, cell, c0 * s.hx * s.hy);
     }
+  }
+  bool overflow = false;
+#pragma omp parallel
+  {
+    auto add = [&](int r, int c, double v) {
+      int *rc = &cols[size_t(r) * W];
+      double *rv = &vals[size_t(r) * W];
+      for (int t = 0; t < cnt[r]; ++t) if (rc[t] == c) { rv[t] += v; return; }
+      if (cnt[r] >= W) { overflow = true; return; }
+      rc[cnt[r]] = c; rv[cnt[r]] = v; ++cnt[r];
+    };
+    // the contributions of local edge e of cell (i, j) to row r
+    auto edge_row = [&](int r, int i, int j, int e) {
+      const int loc[4] = {j * (nx + 1) + i, j * (nx + 1) + i + 1, s.nxe + j * nx + i, s.nxe + (j + 1) * nx + i};
+      const double *aloc = &A[size_t(j * nx + i) * 16];
+      for (int f = 0; f < 4; ++f) add(r, loc[f], aloc[e * 4 + f]);
+      add(r, s.nf + j * nx + i, -div[e]);  // -phi_p div phi_u
+    };
+#pragma omp for schedule(static)
+    for (int r = 0; r < s.nxe; ++r) {  // x-edges: left cell, then right cell
+      const int j = r / (nx + 1), i = r % (nx + 1);
+      cnt[r] = 0;
+      if (i > 0) edge_row(r, i - 1, j, 1);
+      if (i < nx) edge_row(r, i, j, 0);
+    }
+#pragma omp for schedule(static)
+    for (int k = 0; k < s.nye; ++k) {  // y-edges: lower cell, then upper cell
+      const int j = k / nx, i = k % nx, r = s.nxe + k;
+      cnt[r] = 0;
+      if (j > 0) edge_row(r, i, j - 1, 3);
+      if (j < ny) edge_row(r, i, j, 2);
+    }
+#pragma omp for schedule(static)
+    for (int c = 0; c < s.np; ++c) {
+      const int j = c / nx, i = c % nx, r = s.nf + c;
+      const int loc[4] = {j * (nx + 1) + i, j * (nx + 1) + i + 1, s.nxe + j * nx + i, s.nxe + (j + 1) * nx + i};
+      cnt[r] = 0;
+      for (int e = 0; e < 4; ++e) add(r, loc[e], s.dt * div[e]);  // dt div phi_u phi_p
+      add(r, r, c0 * s.hx * s.hy);
+    }
+  }
+  if (overflow) throw std::runtime_error("matrix row overflow");
+  A.reset();
   Csr &m = s.matrix;
   m.n_rows = m.n_cols = n;
   m.rp.assign(n + 1, 0);
   for (int r = 0; r < n; ++r) m.rp[r + 1] = m.rp[r] + cnt[r];
   m.col.resize(m.rp[n]);
   m.val.resize(m.rp[n]);
+#pragma omp parallel for schedule(static)
   for (int r = 0; r < n; ++r) {
-    std::vector<std::pair<int, double>> row(cnt[r]);
+    std::pair<int, double> row[12];
     for (int t = 0; t < cnt[r]; ++t) row[t] = {cols[size_t(r) * W + t], vals[size_t(r) * W + t]};
-    std::sort(row.begin(), row.end());
+    std::sort(row, row + cnt[r]);
     for (int t = 0; t < cnt[r]; ++t) { m.col[m.rp[r] + t] = row[t].first; m.val[m.rp[r] + t] = row[t].second; }
   }
 }
@@ -942,14 +980,22 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
       init_sub(*s, int(r), int(n0), int(n1), reps[r], prm.final_time);
       subs.push_back(std::move(s));
     }
-#pragma omp parallel for schedule(dynamic)
-    for (int li = 0; li < int(subs.size()); ++li) {
-      Sub &s = *subs[li];
-      assemble_matrix(s, prm.c_0);
-      constrain_matrix(s, is_manufact_solution, bc_condition_vect, bc_const_functs);
+    const bool host_prof = std::getenv("MMMFE_SETUP_PROFILE") != nullptr;
+    for (auto &sp : subs) {  // row-parallel inside
+      assemble_matrix(*sp, prm.c_0);
+      constrain_matrix(*sp, is_manufact_solution, bc_condition_vect, bc_const_functs);
+    }
+    if (host_prof) std::fprintf(stderr, "[setup profile] host: saddle matrices %8.1f ms\n", since(t0) * 1e3);
+    {
       // outer sides too when several ranks run: lets the ranks share the multiscale-basis work of a factor group
-      for (int side = 0; side < 4; ++side)
-        if (s.nb[side] >= 0 || world > 1) projector_tables(s, side, mortar, int(mortar_degree));
+      std::vector<std::pair<int, int>> jobs;
+      for (int li = 0; li < int(subs.size()); ++li)
+        for (int side = 0; side < 4; ++side)
+          if (subs[li]->nb[side] >= 0 || world > 1) jobs.push_back({li, side});
+      const auto t1 = clk::now();
+#pragma omp parallel for schedule(dynamic)
+      for (int q = 0; q < int(jobs.size()); ++q) projector_tables(*subs[jobs[q].first], jobs[q].second, mortar, int(mortar_degree));
+      if (host_prof) std::fprintf(stderr, "[setup profile] host: projector tables %8.1f ms\n", since(t1) * 1e3);
     }
     rep.t_assemble = since(t0);
     if (say && !subs.empty()) {

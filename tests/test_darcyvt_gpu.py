@@ -191,7 +191,7 @@ def test_device_data_path_matches_host_evaluation_and_binary_vtu_decodes(tmp_pat
         m = re.search(r'<DataArray[^>]*' + name + r'[^>]*format="ascii">\n(.*?)</DataArray>', ta, flags=re.S)
         return np.array(m.group(1).split(), dtype=dtype)
 
-    pts_b = np.frombuffer(_decode_vtu_array(tb, 'NumberOfComponents="3" format'), dtype="<f8")
+    pts_b = np.frombuffer(_decode_vtu_array(tb, 'NumberOfComponents="3"'), dtype="<f8")
     m = re.search(r'<Points>\n<DataArray[^>]*format="ascii">\n(.*?)</DataArray>', ta, flags=re.S)
     pts_a = np.array(m.group(1).split(), dtype=float)
     np.testing.assert_allclose(pts_b, pts_a, rtol=0, atol=1e-11)
