@@ -33,6 +33,14 @@ struct Error {
                                 __FILE__, __LINE__);                                               \
   } while (0)
 
+// keeps freed blocks in the device's default memory pool (see DevBuf::release)
+inline void dev_pool_retain(int device) {
+  cudaMemPool_t pool = nullptr;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess || !pool) { cudaGetLastError(); return; }
+  unsigned long long threshold = ~0ull;
+  if (cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold) != cudaSuccess) cudaGetLastError();
+}
+
 template <class T>
 struct DevBuf {
   T *p = nullptr;
@@ -46,15 +54,30 @@ struct DevBuf {
     return *this;
   }
   ~DevBuf() { release(); }
+  // Device memory comes from the device's stream-ordered pool with an unlimited release threshold
+  // (dev_pool_retain, called once per context): a release hands the block back to the pool instead of unmapping it.
+  // cudaFree of the multi-GB factorisation workspaces cost 0.5-1.3 s per factor group on the B200 boxes (measured,
+  // DESIGN.md section 12), and the next group / refinement cycle allocates the same sizes again.  Like cudaFree, a
+  // release first waits for the device: the engine's streams are non-blocking, a block must not be handed out again
+  // while one of them still uses it.
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      cudaDeviceSynchronize();
+      if (cudaFreeAsync(p, cudaStreamLegacy) != cudaSuccess) cudaFree(p);
+    }
     p = nullptr;
     n = 0;
   }
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+    if (!count) return;
+    if (cudaMallocAsync(reinterpret_cast<void **>(&p), count * sizeof(T), cudaStreamLegacy) != cudaSuccess) {
+      cudaGetLastError();
+      CUDA_CHECK(cudaMalloc(&p, count * sizeof(T)));
+      return;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));  // usable on every stream from here on
   }
   void zero(cudaStream_t st = 0) {
     if (n) CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), st));

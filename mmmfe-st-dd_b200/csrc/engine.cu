@@ -89,6 +89,7 @@ struct Sub {
   // bar data on the device
   DevBuf<double> p0, src, fr_vals, hist;
   DevBuf<int32_t> fr_dofs;
+  std::vector<int32_t> fr_dofs_h;
   int32_t n_fr = 0;
   bool has_bar_data = false;
 };
@@ -152,7 +153,7 @@ struct Factor {
   DevBuf<double> Rs, minv_c;
   double minv_const = 0.0;
   bool minv_uniform = false;
-  DevBuf<int32_t> sweep_index, p_of_cell, inst_ij;
+  DevBuf<int32_t> sweep_index, p_of_cell, inst_ij, cell_box;
   DevBuf<uint16_t> tmpl16;
   DevBuf<int64_t> tmpl_off;
   std::unique_ptr<Basis> basis;  // multiscale flux basis of this factor group (time-Toeplitz operator)
@@ -190,6 +191,14 @@ struct Batch {
   DevBuf<const double *> s_bq_data;
   DevBuf<double *> s_bq_trace;
   SweepArgs sargs{};
+  // bar sweep through the persistent kernel: boundary-entry tables that also carry the outer Dirichlet rows
+  std::vector<int32_t> h_iface_q, h_bq_stride;
+  std::vector<double *> h_bq_trace;
+  bool bar_planned = false, bar_sweep = false;
+  DevBuf<int32_t> sb_sub_q, sb_bq_stride, sb_inst_bq;
+  DevBuf<double> sb_bq_coef;
+  DevBuf<const double *> sb_bq_data;
+  DevBuf<double *> sb_bq_trace;
 };
 
 struct Arena {
@@ -213,6 +222,8 @@ struct mmmfe_ctx {
   bool keep_history = true, use_graphs = true, use_sweep = true, sweep_evict_first = true;
   int leaf_cells = 8, subtree_cells = 256, sweep_chunk = 7168, sweep_ct = 256, sweep_ctas_per_sm = 1, sweep_groups = 1;
   bool sweep_autotune = true;
+  bool sweep_bar = true;           // bar sweep through the persistent kernel where the star sweeps use it
+  bool sweep_final = true;         // final sweep through the persistent kernel where the star sweeps use it
   int tune_steps = 32;             // time levels of the set-up comparison of the two sweep implementations (0: all)
   bool sweep_crosscheck = false;  // with sweep_autotune = 0: still run both implementations once and compare their traces
   double tune_ms_sweep = 0.0, tune_ms_levels = 0.0, tune_rel_diff = -1.0;
@@ -586,6 +597,7 @@ static void build_sweep_factor(mmmfe_ctx *c, Factor &F, const std::vector<double
   }
   F.minv_const = minv[F.p_of_cell_h[0]];
   F.minv_c.upload(mc);
+  F.cell_box.upload(L.cell_box);
   if (!F.p_identity) F.p_of_cell.upload(F.p_of_cell_h);
   CUDA_CHECK(cudaStreamSynchronize(c->stream));
   F.sweep_ok = true;
@@ -914,7 +926,7 @@ enum SweepMode { SWEEP_BAR, SWEEP_STAR, SWEEP_FINAL };
 static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> &iface_q,
                              const std::vector<int64_t> &tr_base, const std::vector<int32_t> &tr_stride,
                              const std::vector<double> &tr_sign);
-static void run_sweep_kernel(mmmfe_ctx *c, Batch &b, cudaStream_t st);
+static void run_sweep_kernel(mmmfe_ctx *c, Batch &b, cudaStream_t st, int mode = 0);
 
 // one time step of a batch on the per-level kernels; lvl < 0: the kernels read the level from b.level_dev (step graph)
 static void enqueue_step(mmmfe_ctx *c, Batch &b, SweepMode mode, int lvl) {
@@ -975,14 +987,19 @@ static void run_star_sweeps(mmmfe_ctx *c, SweepMode mode) {
   CUDA_CHECK(cudaEventRecord(c->ev_start, c->stream));
   for (auto &bp : c->batches) {
     Batch &b = *bp;
-    if (mode == SWEEP_STAR && b.sweep) {
+    // the final sweep is a star sweep that adds its solution to the stored bar levels: the persistent kernel does that
+    // through its history pointers (hist_add)
+    const bool final_by_sweep = mode == SWEEP_FINAL && c->keep_history && c->sweep_final && b.hist_ptr.p;
+    const bool bar_by_sweep = mode == SWEEP_BAR && b.bar_sweep;
+    const int sk_mode = final_by_sweep ? 1 : (bar_by_sweep ? 2 : 0);  // SweepKernelMode
+    if ((mode == SWEEP_STAR || final_by_sweep || bar_by_sweep) && b.sweep) {
       Factor &F = *b.factor;
       if (F.sm_share >= 1.0) {  // the persistent kernel owns the whole GPU: batches one after the other
-        run_sweep_kernel(c, b, c->stream);
+        run_sweep_kernel(c, b, c->stream, sk_mode);
       } else {                  // its factor's share of the SMs: the factors run side by side
         if (!F.sweep_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&F.sweep_stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamWaitEvent(F.sweep_stream, c->ev_start, 0));
-        run_sweep_kernel(c, b, F.sweep_stream);
+        run_sweep_kernel(c, b, F.sweep_stream, sk_mode);
         CUDA_CHECK(cudaEventRecord(b.done, F.sweep_stream));
         CUDA_CHECK(cudaStreamWaitEvent(c->stream, b.done, 0));
       }
@@ -1741,8 +1758,12 @@ static void setup(mmmfe_ctx *c) {
   for (size_t g = 0; g < reps.size(); ++g) {
     int cnt = 0;
     for (int i = 0; i < ns; ++i) cnt += group_of[i] == int(g);
+    const auto tf0 = std::chrono::steady_clock::now();
     c->factors.push_back(factorize(c, *c->subs[reps[g]], cnt <= 1 ? 1 : (cnt == 2 ? 2 : 4), share[g]));
     c->factor_seconds += c->factors.back()->seconds;
+    if (prof)
+      std::fprintf(stderr, "[setup profile] set-up: factorize() body %.1f ms, with the release of its work buffers %.1f ms\n",
+                   c->factors.back()->seconds * 1e3, std::chrono::duration<double>(std::chrono::steady_clock::now() - tf0).count() * 1e3);
   }
   lap("factorize (all groups)");
   // ---- interface and fine-trace layouts ----
@@ -1932,6 +1953,41 @@ static void setup(mmmfe_ctx *c) {
   }
 }
 
+// Boundary-entry tables of the persistent kernel: per boundary subtree a table [interior variable][member] -> entry
+// (q_of[dof * M + member], -1 = none), and per subtree position the offset of its table (-1 = no entries).
+// referenced (optional): set to 1 for every entry some subtree variable refers to.
+static void build_sub_q(const Factor &F, int M, const std::vector<int32_t> &q_of, const std::vector<int32_t> &dof_of_canon,
+                        std::vector<int32_t> &sub_q, std::vector<int32_t> &bq_pos, std::vector<uint8_t> *referenced) {
+  const NdTree &tr = F.tree;
+  const int64_t nxe = int64_t(F.nx + 1) * F.ny;
+  std::vector<int32_t> bq_off(tr.instances.size(), -1);
+  sub_q.clear();
+  for (size_t k = 0; k < tr.instances.size(); ++k) {
+    const SubtreeInstance &in = tr.instances[k];
+    const SubtreeTemplate &T = tr.templates[in.tmpl];
+    if (T.flags == 0) continue;
+    const size_t base = sub_q.size();
+    bool any = false;
+    for (int32_t l = 0; l < T.n_int; ++l) {
+      const int32_t code = T.var_code[l];
+      const int type = code >> 30, dj = (code >> 15) & 0x7fff, di = code & 0x7fff;
+      const int64_t canon = type == 0 ? int64_t(in.J0 + dj) * (F.nx + 1) + in.I0 + di : nxe + int64_t(in.J0 + dj) * F.nx + in.I0 + di;
+      const int64_t d = dof_of_canon.empty() ? canon : dof_of_canon[canon];
+      for (int j = 0; j < M; ++j) {
+        const int32_t q = q_of[size_t(d) * M + j];
+        sub_q.push_back(q);
+        any |= q >= 0;
+        if (q >= 0 && referenced) (*referenced)[q] = 1;
+      }
+    }
+    if (any) bq_off[k] = int32_t(base);
+    else sub_q.resize(base);
+  }
+  bq_pos.assign(bq_off.size() + 1, -1);
+  for (size_t pos = 0; pos < bq_off.size(); ++pos) bq_pos[pos] = bq_off[F.lay.inst_at_pos[pos]];
+  sub_q.push_back(-1);
+}
+
 // Entry lists, ring schedule and boundary-entry tables of one batch for the persistent sweep kernel.
 static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> &iface_q,
                              const std::vector<int64_t> &tr_base, const std::vector<int32_t> &tr_stride,
@@ -1953,33 +2009,9 @@ static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> 
     dof_of_canon.resize(F.dof_of_canon.n);
     CUDA_CHECK(cudaMemcpy(dof_of_canon.data(), F.dof_of_canon.p, F.dof_of_canon.n * sizeof(int32_t), cudaMemcpyDeviceToHost));
   }
-  std::vector<int32_t> sub_q, bq_off(tr.instances.size(), -1);
-  for (size_t k = 0; k < tr.instances.size(); ++k) {
-    const SubtreeInstance &in = tr.instances[k];
-    const SubtreeTemplate &T = tr.templates[in.tmpl];
-    if (T.flags == 0) continue;
-    const size_t base = sub_q.size();
-    bool any = false;
-    for (int32_t l = 0; l < T.n_int; ++l) {
-      const int32_t code = T.var_code[l];
-      const int type = code >> 30, dj = (code >> 15) & 0x7fff, di = code & 0x7fff;
-      const int64_t canon = type == 0 ? int64_t(in.J0 + dj) * (F.nx + 1) + in.I0 + di : nxe + int64_t(in.J0 + dj) * F.nx + in.I0 + di;
-      const int64_t d = dof_of_canon.empty() ? canon : dof_of_canon[canon];
-      for (int j = 0; j < M; ++j) {
-        const int32_t q = iface_q[size_t(d) * M + j];
-        sub_q.push_back(q);
-        any |= q >= 0;
-      }
-    }
-    if (any) bq_off[k] = int32_t(base);
-    else sub_q.resize(base);
-  }
-  {
-    std::vector<int32_t> bq_pos(bq_off.size() + 1, -1);
-    for (size_t pos = 0; pos < bq_off.size(); ++pos) bq_pos[pos] = bq_off[F.lay.inst_at_pos[pos]];
-    b.s_inst_bq.upload(bq_pos);
-  }
-  sub_q.push_back(-1);
+  std::vector<int32_t> sub_q, bq_pos;
+  build_sub_q(F, M, iface_q, dof_of_canon, sub_q, bq_pos, nullptr);
+  b.s_inst_bq.upload(bq_pos);
   const size_t nq = tr_base.size();
   std::vector<const double *> data(nq + 1, nullptr);
   std::vector<double *> trace(nq + 1, nullptr);
@@ -1997,6 +2029,7 @@ static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> 
   b.s_grp.upload(S.grp);
   b.s_sub_q.upload(sub_q); b.s_bq_stride.upload(stride); b.s_bq_coef.upload(coef);
   b.s_bq_data.upload(data); b.s_bq_trace.upload(trace);
+  b.h_iface_q = iface_q; b.h_bq_stride = stride; b.h_bq_trace = trace;
   b.s_z.alloc(size_t(F.lay.z_total + 1) * M); b.s_z.zero();
   b.s_xi.alloc(size_t(F.lay.xi_total + 2) * M); b.s_xi.zero();
   b.s_ptil.alloc(size_t(F.lay.pb_total + 2) * M); b.s_ptil.zero();
@@ -2032,10 +2065,65 @@ static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> 
 }
 
 // all nt star steps of one batch in one cooperative launch on the interface stream
-static void run_sweep_kernel(mmmfe_ctx *c, Batch &b, cudaStream_t st) {
-  CUDA_CHECK(cudaMemsetAsync(b.s_ptil.p, 0, b.s_ptil.n * sizeof(double), st));
+// The bar problem on the persistent kernel: the boundary-entry tables additionally carry the outer Dirichlet rows of
+// every member (data = its fr_vals column, no trace); the interface entries keep their trace slots and have no data
+// (lambda = 0).  False when a data row is not an interior variable of a boundary subtree (rows that constrain_matrix
+// adds on separators): the per-level kernels run the bar sweep then.
+static bool plan_batch_bar(mmmfe_ctx *c, Batch &b) {
+  const Factor &F = *b.factor;
+  const int M = b.M;
+  std::vector<int32_t> q_of = b.h_iface_q;
+  const size_t nq = b.h_bq_trace.size() - 1;  // interface entries
+  std::vector<const double *> data(nq, nullptr);
+  std::vector<double *> trace(b.h_bq_trace.begin(), b.h_bq_trace.begin() + nq);
+  std::vector<int32_t> stride(b.h_bq_stride.begin(), b.h_bq_stride.begin() + nq);
+  std::vector<double> coef(nq, 0.0);
+  for (size_t j = 0; j < b.members.size(); ++j) {
+    const Sub &sd = *c->subs[b.members[j]];
+    for (int32_t e = 0; e < sd.n_fr; ++e) {
+      const int32_t d = sd.fr_dofs_h[e];
+      if (d < 0 || d >= F.nf || q_of[size_t(d) * M + j] >= 0) return false;
+      q_of[size_t(d) * M + j] = int32_t(data.size());
+      data.push_back(sd.fr_vals.p + e); trace.push_back(nullptr); stride.push_back(sd.n_fr); coef.push_back(1.0);
+    }
+  }
+  std::vector<int32_t> dof_of_canon;
+  if (F.dof_of_canon.n) {
+    dof_of_canon.resize(F.dof_of_canon.n);
+    CUDA_CHECK(cudaMemcpy(dof_of_canon.data(), F.dof_of_canon.p, F.dof_of_canon.n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  }
+  std::vector<uint8_t> referenced(data.size() + 1, 0);
+  std::vector<int32_t> sub_q, bq_pos;
+  build_sub_q(F, M, q_of, dof_of_canon, sub_q, bq_pos, &referenced);
+  for (size_t q = nq; q < data.size(); ++q) if (!referenced[q]) return false;
+  data.push_back(nullptr); trace.push_back(nullptr); stride.push_back(0); coef.push_back(0.0);
+  b.sb_sub_q.upload(sub_q); b.sb_inst_bq.upload(bq_pos);
+  b.sb_bq_data.upload(data); b.sb_bq_trace.upload(trace); b.sb_bq_stride.upload(stride); b.sb_bq_coef.upload(coef);
+  return true;
+}
+
+enum SweepKernelMode { SK_STAR, SK_FINAL, SK_BAR };
+
+static void run_sweep_kernel(mmmfe_ctx *c, Batch &b, cudaStream_t st, int mode) {
+  const Factor &F = *b.factor;
+  SweepArgs a = b.sargs;
+  if (mode == SK_BAR) {  // solve_timestep(0, .), src/darcy_vtdd.cc:902-920
+    launch_init_ptil_box(F.np, b.M, F.cell_box.p, F.p_of_cell.p, F.minv_uniform ? nullptr : F.minv_c.p, F.minv_const,
+                         b.p0_ptr.p, b.src_ptr.p, b.s_ptil.p, st);
+    a.sub_q = b.sb_sub_q.p; a.inst_bq = b.sb_inst_bq.p;
+    a.bq_data = b.sb_bq_data.p; a.bq_trace = b.sb_bq_trace.p; a.bq_stride = b.sb_bq_stride.p; a.bq_coef = b.sb_bq_coef.p;
+    a.has_src = 1; a.src_next = b.src_ptr.p;
+    if (c->keep_history) { a.hist = b.hist_ptr.p; a.hist_add = 0; a.hist_stride = int64_t(F.nf) + F.np; }
+  } else {
+    CUDA_CHECK(cudaMemsetAsync(b.s_ptil.p, 0, b.s_ptil.n * sizeof(double), st));
+  }
   CUDA_CHECK(cudaMemsetAsync(b.s_cnt.p, 0, b.s_cnt.n * sizeof(uint32_t), st));
-  const cudaError_t err = launch_sweep(b.M, b.factor->sweep_ct, b.sargs, b.factor->sweep_n_cta, b.sweep_smem, st);
+  if (mode == SK_FINAL) {  // solution = star + bar_collection[level], src/darcy_vtdd.cc:944-950
+    a.hist = b.hist_ptr.p;
+    a.hist_add = 1;
+    a.hist_stride = int64_t(F.nf) + F.np;
+  }
+  const cudaError_t err = launch_sweep(b.M, b.factor->sweep_ct, a, b.factor->sweep_n_cta, b.sweep_smem, st);
   if (err != cudaSuccess) fail(MMMFE_E_CUDA, "sweep kernel launch failed: %s", cudaGetErrorString(err));
 }
 
@@ -2055,6 +2143,11 @@ static void bar_sweep(mmmfe_ctx *c) {
       }
     }
     b.p0_ptr.upload(p0); b.src_ptr.upload(src); b.hist_ptr.upload(hist);
+    if (b.sweep && c->sweep_bar && !b.bar_planned) {
+      b.bar_sweep = plan_batch_bar(c, b);
+      b.bar_planned = true;
+    }
+    if (!b.sweep || !c->sweep_bar) b.bar_sweep = false;
   }
   run_star_sweeps(c, SWEEP_BAR);
   // initial residual r = send + recv of the signed bar traces in mortar space (src/darcy_vtdd.cc:1203-1256)
@@ -2220,6 +2313,7 @@ int mmmfe_create(mmmfe_ctx **out, int device) {
   c->device = device;
   c->launch_base = launch_counter();
   if (cudaSetDevice(device) != cudaSuccess) { delete c; return MMMFE_E_CUDA; }
+  dev_pool_retain(device);
   *out = c;
   return MMMFE_OK;
 }
@@ -2268,6 +2362,8 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   else if (k == "sweep_spin_ns") c->sweep_spin_ns = std::max(0, int(value));
   else if (k == "sweep_autotune") c->sweep_autotune = value != 0;
   else if (k == "tune_steps") c->tune_steps = int(value);
+  else if (k == "sweep_final") c->sweep_final = value != 0;
+  else if (k == "sweep_bar") c->sweep_bar = value != 0;
   else if (k == "gmres_lookahead") c->gmres_lookahead = int(value);
   else if (k == "sweep_crosscheck") c->sweep_crosscheck = value != 0;
   else if (k == "operator") {
@@ -2459,8 +2555,10 @@ int mmmfe_bar_set_data(mmmfe_ctx *c, int32_t li, const double *p0, const double 
     sd.src.upload(src, size_t(sd.nt) * sd.np);
     sd.n_fr = n_fr;
     sd.fr_dofs.upload(fr_dofs, size_t(n_fr));
+    sd.fr_dofs_h.assign(fr_dofs, fr_dofs + n_fr);
     sd.fr_vals.upload(fr_vals, size_t(n_fr) * sd.nt);
     sd.has_bar_data = true;
+    if (sd.batch >= 0) c->batches[sd.batch]->bar_planned = false;
   });
 }
 
@@ -2475,6 +2573,8 @@ int mmmfe_bar_data_buffers(mmmfe_ctx *c, int32_t li, int32_t n_fr, const int32_t
     sd.src.alloc(size_t(sd.nt) * sd.np); sd.src.zero();
     sd.n_fr = n_fr;
     sd.fr_dofs.upload(fr_dofs, size_t(n_fr));
+    sd.fr_dofs_h.assign(fr_dofs, fr_dofs + n_fr);
+    if (sd.batch >= 0) c->batches[sd.batch]->bar_planned = false;
     sd.fr_vals.alloc(size_t(n_fr) * sd.nt); sd.fr_vals.zero();
     CUDA_CHECK(cudaDeviceSynchronize());
     sd.has_bar_data = true;
@@ -2689,6 +2789,7 @@ int64_t mmmfe_stat(const mmmfe_ctx *c, const char *key) {
   if (k == "toeplitz_mflop") return int64_t(c->toep_flops / 1e6);
   if (k == "toeplitz_mbytes") return int64_t(c->toep_bytes / 1e6);
   if (k == "gmres_surplus") return c->gmres_surplus;
+  if (k == "bar_sweep_batches") { int64_t n = 0; for (auto &b : c->batches) n += b->sweep && b->bar_sweep; return n; }
   if (k == "tune_us_sweep") return int64_t(c->tune_ms_sweep * 1e3);
   if (k == "tune_us_levels") return int64_t(c->tune_ms_levels * 1e3);
   // relative l2 difference of the two star-sweep implementations at set-up, in units of 1e-18 (-1: not run)

@@ -746,6 +746,29 @@ __global__ void __launch_bounds__(256) k_init_ptil(StepArgs a, const double *con
   }
 }
 
+// the same for the persistent kernel's pressures: [box-major cell][M]
+__global__ void __launch_bounds__(256) k_init_ptil_box(int64_t n_cells, int32_t M, const int32_t *__restrict__ cell_box,
+                                                       const int32_t *__restrict__ p_of_cell, const double *__restrict__ minv_box,
+                                                       double minv_const, const double *const *__restrict__ p0,
+                                                       const double *const *__restrict__ src0, double *__restrict__ ptil) {
+  const int64_t c = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;  // canonical cell
+  if (c >= n_cells) return;
+  const int64_t pos = cell_box[c], p = p_of_cell ? int64_t(p_of_cell[c]) : c;
+  const double mi = minv_box ? minv_box[pos] : minv_const;
+  for (int j = 0; j < M; ++j) {
+    double v = 0.0;
+    if (p0 && p0[j]) v = p0[j][p];
+    if (src0 && src0[j]) v += mi * src0[j][p];
+    ptil[pos * M + j] = v;
+  }
+}
+
+void launch_init_ptil_box(int64_t n_cells, int32_t M, const int32_t *cell_box, const int32_t *p_of_cell, const double *minv_box,
+                          double minv_const, const double *const *p0, const double *const *src0, double *ptil, cudaStream_t st) {
+  k_init_ptil_box<<<unsigned((n_cells + 255) / 256), 256, 0, st>>>(n_cells, M, cell_box, p_of_cell, minv_box, minv_const, p0, src0, ptil);
+  launch_counter_add(1);
+}
+
 void launch_init_ptil(const StepArgs &a, const double *const *p0, const double *const *src0, cudaStream_t st) {
   k_init_ptil<<<unsigned((a.n_pressure + 255) / 256), 256, 0, st>>>(a, p0, src0);
   launch_counter_add(1);

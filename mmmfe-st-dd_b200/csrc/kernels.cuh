@@ -138,6 +138,10 @@ void launch_update(const StepArgs &a, double *trace, int32_t level, const double
                    int64_t src_stride, double *const *hist, int64_t hist_level_stride, int add_hist,
                    cudaStream_t st, int32_t n_levels = 0);
 void launch_init_ptil(const StepArgs &a, const double *const *p0, const double *const *src0, cudaStream_t st);
+// ptil[cell_box[c]][j] = p0[j][p] + minv * src0[j][p], p = p_of_cell[c] (nullptr: c): the pressures of the persistent
+// sweep kernel (box-major cell order) at the start of a bar sweep
+void launch_init_ptil_box(int64_t n_cells, int32_t M, const int32_t *cell_box, const int32_t *p_of_cell, const double *minv_box,
+                          double minv_const, const double *const *p0, const double *const *src0, double *ptil, cudaStream_t st);
 
 // ---- interface vector ------------------------------------------------------------------------------------------
 void launch_spmv(int64_t n_rows, const int64_t *rp, const int32_t *col, const double *val, const double *x,

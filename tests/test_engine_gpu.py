@@ -210,6 +210,41 @@ def test_full_solve_matches_oracle(k, cycle, perm):
     eng.close()
 
 
+@pytest.mark.parametrize("k,cycle,perm", [(1, 2, None), (2, 1, None), (1, 1, 11)])
+def test_bar_and_final_sweeps_through_the_persistent_kernel(k, cycle, perm):
+    """solve_timestep(0, .) and solve_timestep(2, .) (src/darcy_vtdd.cc:902-920, 937-953) with the persistent kernel
+    forced on: the bar sweep feeds source terms, outer Dirichlet rows and the stored levels through k_sweep's boundary
+    tables and history pointers, the final sweep adds the star solution to the stored bar levels.  r_norm, iteration
+    count, p and u against the oracle, and against the per-level sweeps of a second engine."""
+    prm = default_params(k, cycle + 1)
+    prob = make_problem(prm, cycle)
+    ref = prob.run_cycle(cycle)
+    sols = {}
+    for final in (1, 0):
+        eng = engine_from_oracle(prob, perm_seed=perm, options={"use_sweep": 1, "sweep_autotune": 0, "sweep_final": final,
+                                                                "sweep_bar": final})
+        eng.setup()
+        assert eng.stat("sweep_batches") > 0
+        set_bar_data(eng, prob)
+        eng.bar_sweep()
+        assert eng.stat("bar_sweep_batches") == (eng.stat("sweep_batches") if final else 0)
+        out = eng.gmres(prm.tolerance, prm.max_iteration)
+        assert out["iterations"] == ref.gmres_iterations
+        assert out["r_norm"] == pytest.approx(ref.r_norm, rel=1e-12)
+        eng.final_sweep()
+        sols[final] = [eng.get_solution(li) for li in range(len(prob.subs))]
+        for li, sd in enumerate(prob.subs):
+            sol = sols[final][li]
+            if perm is not None:
+                full, inv = eng.perms[sd.r]
+                sol = sol[:, inv]
+            assert rel_l2(sol[:, sd.nf:], ref.solution_p[li]) < TOL
+            assert rel_l2(sol[:, :sd.nf], ref.solution_u[li]) < TOL
+        eng.close()
+    for a, b in zip(sols[1], sols[0]):
+        assert rel_l2(a, b) < 1e-13
+
+
 @pytest.mark.parametrize("bc_type,bc_value", [(["N", "D", "D", "N"], [0.5, 1.0, 2.0, -0.25]),
                                               (["D", "N", "N", "D"], [1.0, 0.0, 1.5, 0.0])])
 def test_full_solve_with_essential_neumann_sides(bc_type, bc_value):
