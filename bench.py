@@ -363,6 +363,7 @@ def main():
                     "GBps": (r["prof_bytes"][i] / 1e9) / (r["prof_ms"][i] * 1e-3) if r["prof_ms"][i] > 0 else 0.0}
                 for i, n in enumerate(names)}
         tune = {"persistent_kernel_ms": r["tune_us_sweep"] / 1e3, "per_level_kernels_ms": r["tune_us_levels"] / 1e3,
+                "compared_on": "the first 32 time levels of the longest sweep, every batch its share (engine option tune_steps)",
                 "batches_with_sweep_plan": r["sweep_planned"],
                 "relative_l2_difference_of_their_traces": r["tune_rel_diff_e18"] * 1e-18 if r["tune_rel_diff_e18"] >= 0 else None,
                 "selected": "persistent sweep kernel" if r["sweep_batches"] > 0 else "per-level kernels"}

@@ -222,6 +222,7 @@ struct mmmfe_ctx {
   bool keep_history = true, use_graphs = true, use_sweep = true, sweep_evict_first = true;
   int leaf_cells = 8, subtree_cells = 256, sweep_chunk = 7168, sweep_ct = 256, sweep_ctas_per_sm = 1, sweep_groups = 1;
   bool sweep_autotune = true;
+  bool sweep_debug_stall = false;  // test hook, see plan_batch_sweep
   bool sweep_bar = true;           // bar sweep through the persistent kernel where the star sweeps use it
   bool sweep_final = true;         // final sweep through the persistent kernel where the star sweeps use it
   int tune_steps = 32;             // time levels of the set-up comparison of the two sweep implementations (0: all)
@@ -2023,6 +2024,12 @@ static void plan_batch_sweep(mmmfe_ctx *c, Batch &b, const std::vector<int32_t> 
     coef[q] = -tr_sign[q];  // rhs_i = -s * lam_bar, src/darcy_vtdd.cc:840-844
     stride[q] = tr_stride[q];
   }
+  if (c->sweep_debug_stall) {
+    // test hook: the first cross-CTA dependency of the batch can never be satisfied -> the kernel's bounded spin-waits
+    // must give up (watchdog flag) and the host must report it instead of hanging or returning garbage
+    for (SweepEntry &e : S.entries)
+      if (e.n_dep > 0) { e.dep[0] |= ((1 << (31 - SWEEP_DEP_SHIFT)) - 1) << SWEEP_DEP_SHIFT; break; }
+  }
   b.s_entries.upload(S.entries); b.s_issue.upload(S.issue);
   b.s_cta_begin.upload(S.cta_begin); b.s_cta_pro.upload(S.cta_prologue);
   S.grp.push_back(0);
@@ -2364,6 +2371,7 @@ int mmmfe_set_option(mmmfe_ctx *c, const char *key, double value) {
   else if (k == "tune_steps") c->tune_steps = int(value);
   else if (k == "sweep_final") c->sweep_final = value != 0;
   else if (k == "sweep_bar") c->sweep_bar = value != 0;
+  else if (k == "sweep_debug_stall") c->sweep_debug_stall = value != 0;
   else if (k == "gmres_lookahead") c->gmres_lookahead = int(value);
   else if (k == "sweep_crosscheck") c->sweep_crosscheck = value != 0;
   else if (k == "operator") {

@@ -485,6 +485,13 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
       const SweepEntry &e = edesc[slot];
       const int kind = e.kind, flags = e.flags;
       const double *reg = ring + e.ring_off;
+      // the first two completion counters of the entry, loaded now (an L2 round trip that would otherwise sit between
+      // the end of the arithmetic and the publication of the completion)
+      int32_t sig0 = -1, sig1 = -1;
+      if (lane == 0) {
+        if (e.n_sig > 0) sig0 = __ldg(a.index + e.sig_off);
+        if (e.n_sig > 1) sig1 = __ldg(a.index + e.sig_off + 1);
+      }
       bar_wait(full_bar + slot, parity, a.abort_flag);
       if (a.prof && tid == 0) {
         const long long t = clock64();
@@ -1009,16 +1016,13 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
       __syncwarp();
       if (lane == 0) {
         const int p_sig = e.sig, p_n = e.n_sig, p_off = e.sig_off;
-        int32_t s0 = -1, s1 = -1;
-        if (p_n > 0) s0 = a.index[p_off];
-        if (p_n > 1) s1 = a.index[p_off + 1];
         uint32_t old;
         asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;\n" : "=r"(old) : "r"(s_u32(done_cnt + slot)) : "memory");
         if (old + 1 == uint32_t(G / NB + 1) * uint32_t(CT / 32 / a.ng)) {
           if (p_sig >= 0) red_release(a.cnt + p_sig);
-          if (p_n > 0) red_release(a.cnt + s0);
-          if (p_n > 1) red_release(a.cnt + s1);
-          for (int t = 2; t < p_n; ++t) red_release(a.cnt + a.index[p_off + t]);
+          if (p_n > 0) red_release(a.cnt + sig0);
+          if (p_n > 1) red_release(a.cnt + sig1);
+          for (int t = 2; t < p_n; ++t) red_release(a.cnt + __ldg(a.index + p_off + t));
         }
       }
     }

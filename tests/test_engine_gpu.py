@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import scipy.sparse.linalg as spla
 
-from helpers import default_params, engine_from_oracle, make_problem, mo, rel_l2, set_bar_data
+from helpers import default_params, engine_from_oracle, make_problem, mo, pkg, rel_l2, set_bar_data
 
 pytestmark = pytest.mark.gpu
 
@@ -373,4 +373,27 @@ def test_variable_full_k_tensor(options):
     ref = sd.lu.solve(rhs)
     x = eng.solve_saddle(0, rhs)
     assert rel_l2(x[:sd.nf], ref[:sd.nf]) < 1e-11 and rel_l2(x[sd.nf:], ref[sd.nf:]) < 1e-10
+    eng.close()
+
+
+def test_sweep_kernel_watchdog_reports_a_dependency_that_never_completes():
+    """Every spin-wait of k_sweep is bounded (csrc/sweep.cu spin_expired): with one cross-CTA dependency made
+    unsatisfiable (test hook sweep_debug_stall) the kernel gives up after ~4 s, raises its flag, and the host reports
+    the failure -- no hang, no silently wrong result.  The engine stays usable afterwards."""
+    import time
+    prm = default_params(1, 3)
+    prob = make_problem(prm, 2)
+    eng = engine_from_oracle(prob, options={"use_sweep": 1, "sweep_autotune": 0, "sweep_debug_stall": 1})
+    eng.setup()
+    assert eng.stat("sweep_batches") > 0
+    q = np.random.default_rng(5).standard_normal(eng.interface_length)
+    t0 = time.time()
+    with pytest.raises(pkg().MmmfeError, match="watchdog"):
+        eng.apply(q)
+    assert time.time() - t0 < 60
+    eng.close()
+    # a fresh engine on the same GPU works
+    eng = engine_from_oracle(prob, options={"use_sweep": 1, "sweep_autotune": 0})
+    eng.setup()
+    assert rel_l2(eng.apply(q), prob.apply_S(q)) < 1e-10
     eng.close()
