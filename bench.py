@@ -402,7 +402,7 @@ def main():
                             "used": "multiscale basis (time-Toeplitz, precomputed at set-up)" if on_basis else
                                     "star sweeps (nt backward-Euler solves per subdomain and iteration)",
                             "rule": "auto = basis when the mortar time mesh divides the subdomain's and a factor group has at "
-                                    "most 1024 basis columns (engine option basis_auto_columns)"},
+                                    "most 2048 basis columns (engine option basis_auto_columns)"},
                "roofline": roof,
                "e2e": {"value": dof_steps / (e2e_it * 1e-3) if e2e_it > 0 else None, "unit": "DOF*timesteps/s",
                        "ms_per_step": e2e_it, "iterations_timed": a.steps, "h2d_bytes_per_step": r["e2e_h2d_bytes"],

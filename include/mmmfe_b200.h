@@ -95,7 +95,7 @@ const char *mmmfe_version(void);
  * src/darcy_vtdd.cc:959-1003): the response to every mortar basis function of the FIRST mortar time slab is computed
  * once at set-up (multi-column multifrontal solves, fronts as FP64 DMMA GEMMs) and S q becomes one block
  * lower-triangular Toeplitz product per subdomain -- the same operator to round-off; 2 (default) = 1 when the
- * projector tables are slab structured and a factor group has at most "basis_auto_columns" (default 1024) basis
+ * projector tables are slab structured and a factor group has at most "basis_auto_columns" (default 2048) basis
  * columns, else 0.  "mortar_time_slabs" = time steps of the mortar mesh (mesh_pattern_mortar nt; required for 1/2),
  * "basis_columns" = columns solved per pass (default 256), "basis_share" (default 1: with several ranks, a factor
  * group that every rank holds is solved for once, each rank taking a block of its columns; needs the projector tables

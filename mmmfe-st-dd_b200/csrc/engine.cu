@@ -274,7 +274,7 @@ struct mmmfe_ctx {
   // interface operator: 0 = star sweeps every iteration (the reference's algorithm), 1 = multiscale flux basis /
   // time-Toeplitz operator precomputed at set-up, 2 = basis when the structure allows it and it has at most
   // basis_auto_columns columns per factor group, sweeps otherwise
-  int operator_mode = 2, mortar_slabs = 0, basis_cols_max = 256, basis_auto_columns = 1024;
+  int operator_mode = 2, mortar_slabs = 0, basis_cols_max = 256, basis_auto_columns = 2048;
   bool basis_share = true;  // several ranks: split the columns of a group every rank holds among the ranks
   double basis_drop_tol = 1e-18;  // a pass of the basis solve stops once the pressures fell below this fraction of their peak
   bool use_basis = false;

@@ -1133,8 +1133,23 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
       std::vector<std::vector<double>> Q;
       std::vector<double> r(size_t(len) + 1);
       check(ctx, mmmfe_get_initial_residual(ctx, r.data()), "initial residual");
-      double nn[1] = {0};
-      for (long long i = 0; i < len; ++i) nn[0] += r[i] * r[i];
+      // (the host loops below run on all threads of the rank, in fixed chunks: reproducible run to run)
+      auto dot = [&](const double *x, const double *y) {
+        const int nchunk = 64;
+        double part[nchunk];
+#pragma omp parallel for schedule(static)
+        for (int cidx = 0; cidx < nchunk; ++cidx) {
+          const long long j0 = len * cidx / nchunk, j1 = len * (cidx + 1) / nchunk;
+          double a = 0;
+#pragma omp simd reduction(+ : a)
+          for (long long j = j0; j < j1; ++j) a += x[j] * y[j];
+          part[cidx] = a;
+        }
+        double a = 0;
+        for (int cidx = 0; cidx < nchunk; ++cidx) a += part[cidx];
+        return a;
+      };
+      double nn[1] = {dot(r.data(), r.data())};
       check(ctx, mmmfe_comm_allreduce_sum(ctx, nn, 1), "allreduce");
       Q.emplace_back(r.begin(), r.begin() + len);
       for (auto &v : Q[0]) v /= std::sqrt(nn[0]);
@@ -1144,15 +1159,23 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
         std::copy(Q[k].begin(), Q[k].end(), q);
         check(ctx, mmmfe_apply_interface_operator(ctx, q, ap), "apply (host buffers)");
         std::vector<double> h(size_t(k) + 2, 0.0);
-        for (int i = 0; i <= k; ++i) { double a = 0; for (long long j = 0; j < len; ++j) a += ap[j] * Q[i][j]; h[i] = a; }
+        for (int i = 0; i <= k; ++i) h[i] = dot(ap, Q[i].data());
         check(ctx, mmmfe_comm_allreduce_sum(ctx, h.data(), k + 1), "allreduce");
-        for (int i = 0; i <= k; ++i) for (long long j = 0; j < len; ++j) ap[j] -= h[i] * Q[i][j];
-        double n2[1] = {0};
-        for (long long j = 0; j < len; ++j) n2[0] += ap[j] * ap[j];
+#pragma omp parallel for schedule(static)
+        for (long long j = 0; j < len; ++j) {
+          double v = ap[j];
+          for (int i = 0; i <= k; ++i) v -= h[i] * Q[i][j];
+          ap[j] = v;
+        }
+        double n2[1] = {dot(ap, ap)};
         check(ctx, mmmfe_comm_allreduce_sum(ctx, n2, 1), "allreduce");
         const double hk = std::sqrt(n2[0]);
-        Q.emplace_back(ap, ap + len);
-        for (auto &v : Q.back()) v /= hk;
+        Q.emplace_back(size_t(len));
+        {
+          double *qn = Q.back().data();
+#pragma omp parallel for schedule(static)
+          for (long long j = 0; j < len; ++j) qn[j] = ap[j] / hk;
+        }
         if (k > 0) total += since(ti);
       }
       rep.e2e_ms_per_iteration = 1e3 * total / ne;
