@@ -116,6 +116,12 @@ int mmmfe_comm_init(mmmfe_ctx *ctx, int rank, int world, const void *id);
 /* owner_rank[g] = rank that holds global subdomain g (length n_global); required before mmmfe_setup when
  * world > 1, optional (all zero) otherwise.                                                                   */
 int mmmfe_set_owners(mmmfe_ctx *ctx, int32_t n_global, const int32_t *owner_rank);
+/* Opens the NCCL paths this rank will use -- the point-to-point channels to `peers` (the ranks that own a
+ * neighbour of one of its subdomains; the relation is symmetric, every peer must list this rank too) and the
+ * all-reduce path -- by exchanging one double.  NCCL opens them on first use (measured: 1.5 s on 8 ranks); a
+ * front-end calls this right after mmmfe_comm_init from a helper thread while it assembles its matrices, so that
+ * the cost is hidden.  Collective over the communicator; no other call on the context may run concurrently.      */
+int mmmfe_comm_warmup(mmmfe_ctx *ctx, int32_t n_peers, const int32_t *peers);
 /* In-place sum over ranks of n host doubles (error numerators/denominators: MPI_Reduce, src/darcy_vtdd.cc:1812-1813).
  * A no-op on one rank.                                                                                        */
 int mmmfe_comm_allreduce_sum(mmmfe_ctx *ctx, double *inout, int32_t n);

@@ -83,6 +83,7 @@ def load_engine():
                                              ctypes.c_int32, c_f64p]),
         "mmmfe_final_sweep": (ctypes.c_int, [vp]),
         "mmmfe_get_solution": (ctypes.c_int, [vp, ctypes.c_int32, c_f64p]),
+        "mmmfe_comm_warmup": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
         "mmmfe_solution_device": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
         "mmmfe_bar_data_buffers": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
                                                   ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),

@@ -2460,6 +2460,33 @@ int mmmfe_set_owners(mmmfe_ctx *c, int32_t n_global, const int32_t *owner_rank) 
   return MMMFE_OK;
 }
 
+int mmmfe_comm_warmup(mmmfe_ctx *c, int32_t n_peers, const int32_t *peers) {
+  if (!c || n_peers < 0 || (n_peers > 0 && !peers)) return MMMFE_E_INVALID;
+  if (c->world <= 1) return MMMFE_OK;
+#ifdef MMMFE_WITH_NCCL
+  MMMFE_TRY(c, {
+    if (!c->comm) fail(MMMFE_E_INVALID, "mmmfe_comm_init first");
+    CUDA_CHECK(cudaSetDevice(c->device));
+    if (!c->stream) CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    DevBuf<double> buf;
+    buf.alloc(size_t(2 * n_peers) + 2);
+    buf.zero(c->stream);
+    nccl().GroupStart();
+    for (int32_t k = 0; k < n_peers; ++k) {
+      if (peers[k] < 0 || peers[k] >= c->world || peers[k] == c->rank) continue;
+      nccl().Send(buf.p + 2 * k, 1, ncclDouble, peers[k], c->comm, c->stream);
+      nccl().Recv(buf.p + 2 * k + 1, 1, ncclDouble, peers[k], c->comm, c->stream);
+    }
+    if (nccl().GroupEnd() != ncclSuccess) fail(MMMFE_E_COMM, "NCCL warm-up exchange failed");
+    allreduce_sum(c, buf.p + 2 * n_peers, 1);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  });
+#else
+  (void)peers;
+  return MMMFE_E_UNSUPPORTED;
+#endif
+}
+
 int mmmfe_comm_allreduce_sum(mmmfe_ctx *c, double *inout, int32_t n) {
   if (!c || !inout || n < 0) return MMMFE_E_INVALID;
   if (c->world <= 1 || n == 0) return MMMFE_OK;

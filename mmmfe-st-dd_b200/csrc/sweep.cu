@@ -1019,10 +1019,14 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
         uint32_t old;
         asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;\n" : "=r"(old) : "r"(s_u32(done_cnt + slot)) : "memory");
         if (old + 1 == uint32_t(G / NB + 1) * uint32_t(CT / 32 / a.ng)) {
+          // (-1: nobody on another CTA waits for that completion, sweep_plan.cpp)
           if (p_sig >= 0) red_release(a.cnt + p_sig);
-          if (p_n > 0) red_release(a.cnt + sig0);
-          if (p_n > 1) red_release(a.cnt + sig1);
-          for (int t = 2; t < p_n; ++t) red_release(a.cnt + __ldg(a.index + p_off + t));
+          if (p_n > 0 && sig0 >= 0) red_release(a.cnt + sig0);
+          if (p_n > 1 && sig1 >= 0) red_release(a.cnt + sig1);
+          for (int t = 2; t < p_n; ++t) {
+            const int32_t id = __ldg(a.index + p_off + t);
+            if (id >= 0) red_release(a.cnt + id);
+          }
         }
       }
     }

@@ -363,6 +363,11 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
           c += w; left -= w;
         }
       }
+      // A front that several consecutive waves of this CTA work on is signalled ONCE, by the last of them: the warps
+      // run a CTA's entries in order (one compute group), so that wave's completion implies the earlier ones', and
+      // the consumers cannot start before it anyway.  Fewer release operations (each one drains the SM's stores).
+      std::map<int32_t, size_t> last_strip;
+      for (size_t q = 0; q < strips.size(); ++q) last_strip[strips[q].node] = q;
       size_t i = 0;
       std::vector<int32_t> prev_fronts;
       while (i < strips.size()) {
@@ -514,10 +519,12 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
         }
         W.idx_len = here();
         W.sig_off = int64_t(L.index.size());
-        W.n_sig = int32_t(W.fronts.size());
+        W.n_sig = 0;
         for (int32_t fnode : W.fronts) {
+          if (L.ng == 1 && last_strip[fnode] >= i) continue;  // a later wave of this CTA finishes the front
           L.index.push_back(2 * fnode + pass);
           (pass == 0 ? L.nodes[fnode].n_fwd : L.nodes[fnode].n_bwd) += 1;
+          ++W.n_sig;
         }
         pad4();
         waves.push_back(std::move(W));
@@ -559,6 +566,56 @@ const char *build_sweep_layout(const NdTree &tr, const std::vector<int32_t> &idx
     P.sig_off = int64_t(L.index.size());
     for (int32_t m = 0; m < P.n; ++m) L.index.push_back(2 * (L.n_top + L.inst_at_pos[P.pos0 + m]));
     while (L.index.size() % 4) L.index.push_back(0);
+  }
+  // ---- completions nobody on another CTA waits for are not published: a counter is needed only when some entry
+  // lists it as a dependency (same-CTA consumers rely on program order, their dependencies were elided above).  On a
+  // uniform grid the shares of consecutive levels line up, so most fronts of the lower top levels are produced and
+  // consumed by one CTA: their release operations (a store drain each) disappear.  Entries -1 are skipped. ----
+  {
+    std::vector<uint8_t> used(2 * L.nodes.size(), 0);
+    const int32_t mask = (1 << SWEEP_DEP_SHIFT) - 1;
+    for (const auto *lv : {&L.fwd, &L.bwd})
+      for (const auto &waves : *lv)
+        for (const SweepWaveH &W : waves)
+          for (int32_t d : W.deps) used[d & mask] = 1;
+    for (int32_t k = 0; k < n_inst; ++k) {  // subtree backward entries (build_sweep_schedule adds the dependency)
+      const SweepNodeH &sn = L.nodes[L.n_top + k];
+      if (sn.parent >= 0 && !(L.ng == 1 && prod_cta[2 * sn.parent + 1] == L.cta_of_inst[k])) used[2 * sn.parent + 1] = 1;
+    }
+    auto prune = [&](int64_t off, int32_t n) {
+      for (int32_t t = 0; t < n; ++t) {
+        int32_t &id = L.index[size_t(off) + t];
+        if (id >= 0 && !used[id]) {
+          SweepNodeH &sn = L.nodes[id >> 1];
+          ((id & 1) ? sn.n_bwd : sn.n_fwd) -= 1;
+          id = -1;
+        }
+      }
+    };
+    const bool stats = std::getenv("MMMFE_PLAN_STATS") != nullptr;
+    int pass_id = 0;
+    for (auto *lv : {&L.fwd, &L.bwd}) {
+      for (size_t h = 0; h < lv->size(); ++h) {
+        int64_t before = 0, after = 0, nd = 0;
+        for (SweepWaveH &W : (*lv)[h]) {
+          before += W.n_sig;
+          prune(W.sig_off, W.n_sig);
+          for (int32_t t = 0; t < W.n_sig; ++t) after += L.index[size_t(W.sig_off) + t] >= 0;
+          nd += int64_t(W.deps.size());
+        }
+        if (stats && !(*lv)[h].empty())
+          std::fprintf(stderr, "[plan] %s level %2zu: %5zu waves, %5lld cross-CTA dependencies, signals %5lld -> %5lld\n",
+                       pass_id == 0 ? "fwd" : "bwd", h, (*lv)[h].size(), (long long)nd, (long long)before, (long long)after);
+      }
+      ++pass_id;
+    }
+    int64_t pb = 0, pa = 0;
+    for (SweepPackH &P : L.packs) {
+      pb += P.n;
+      prune(P.sig_off, P.n);
+      for (int32_t t = 0; t < P.n; ++t) pa += L.index[size_t(P.sig_off) + t] >= 0;
+    }
+    if (stats) std::fprintf(stderr, "[plan] subtree packs: signals %lld -> %lld\n", (long long)pb, (long long)pa);
   }
   for (size_t k = 0; k < tr.instances.size(); ++k) {
     if (!writes_blob[k]) continue;
@@ -839,7 +896,8 @@ const char *check_sweep_schedule(const SweepLayout &L, const SweepSchedule &S, i
         }
         if (blocked) break;
         if (e.sig >= 0) ++cnt[e.sig];
-        for (int32_t t = 0; t < e.n_sig; ++t) ++cnt[L.index[size_t(e.sig_off) + t]];
+        for (int32_t t = 0; t < e.n_sig; ++t)
+          if (L.index[size_t(e.sig_off) + t] >= 0) ++cnt[L.index[size_t(e.sig_off) + t]];
         ++s.G;
         --remaining;
         progress = true;

@@ -972,6 +972,33 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
       for (unsigned r = 0; r < n_sub; ++r) cost[r] = double(reps[r][0]) * reps[r][1] * reps[r][2];
       if (mmmfe_assign_owners(int(n_sub), cost.data(), world, owner.data()) != 0) throw std::runtime_error("mmmfe_assign_owners failed");
     }
+    // ---- engine context first: with several ranks NCCL is initialised and its paths are opened by a helper thread
+    // WHILE this thread assembles the matrices (communicator set-up + first-use channel opening cost 2-3 s on 8 ranks
+    // and would otherwise sit in front of / inside mmmfe_setup)
+    mmmfe_ctx *ctx = nullptr;
+    if (mmmfe_create(&ctx, control.device) != 0)
+      throw std::runtime_error("no usable CUDA device: the interface-GMRES path has no CPU fallback");
+    struct Guard { mmmfe_ctx *c; ~Guard() { mmmfe_destroy(c); } } guard{ctx};
+    std::thread comm_thread;
+    int comm_rc = 0;
+    std::string comm_what;
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{comm_thread};  // (before guard runs)
+    if (world > 1) {
+      std::vector<int32_t> peers;
+      for (unsigned r = 0; r < n_sub; ++r) {
+        if (owner[r] != rank) continue;
+        int nb[4];
+        find_neighbors(int(r), int(n0), int(n1), nb);
+        for (int k = 0; k < 4; ++k)
+          if (nb[k] >= 0 && owner[nb[k]] != rank && std::find(peers.begin(), peers.end(), owner[nb[k]]) == peers.end())
+            peers.push_back(owner[nb[k]]);
+      }
+      comm_thread = std::thread([this, ctx, rank, world, peers, &comm_rc, &comm_what] {
+        comm_rc = mmmfe_comm_init(ctx, rank, world, control.nccl_id);
+        comm_what = "mmmfe_comm_init";
+        if (comm_rc == 0) { comm_rc = mmmfe_comm_warmup(ctx, int32_t(peers.size()), peers.data()); comm_what = "mmmfe_comm_warmup"; }
+      });
+    }
     auto t0 = clk::now();
     std::vector<std::unique_ptr<Sub>> subs;
     for (unsigned r = 0; r < n_sub; ++r) {
@@ -1004,10 +1031,6 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
       std::cout << "Assembling system...\n";
     }
     // ---- engine ----
-    mmmfe_ctx *ctx = nullptr;
-    if (mmmfe_create(&ctx, control.device) != 0)
-      throw std::runtime_error("no usable CUDA device: the interface-GMRES path has no CPU fallback");
-    struct Guard { mmmfe_ctx *c; ~Guard() { mmmfe_destroy(c); } } guard{ctx};
     mmmfe_set_option(ctx, "keep_history", control.final_sweep ? 1 : 0);
     mmmfe_set_option(ctx, "mortar_time_slabs", mortar[2]);  // lets the engine build the multiscale-basis operator
     {
@@ -1024,7 +1047,8 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
       }
     }
     if (world > 1) {
-      check(ctx, mmmfe_comm_init(ctx, rank, world, control.nccl_id), "mmmfe_comm_init");
+      comm_thread.join();
+      check(ctx, comm_rc, comm_what.c_str());
       check(ctx, mmmfe_set_owners(ctx, int(n_sub), owner.data()), "mmmfe_set_owners");
     }
     for (auto &sp : subs) {
