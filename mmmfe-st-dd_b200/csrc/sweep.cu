@@ -777,6 +777,9 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
         // ---------------------------------------------------------------------------------------------------------
         // subtree: factor blob, index lists and this CTA's own vectors are in the ring; walk the levels on chip
         // ---------------------------------------------------------------------------------------------------------
+        // (the boundary-table offset of this thread's pack member: an L2 round trip, started before the barrier)
+        const int sub_early = gt / (GT / a.pack);
+        const int bq_early = sub_early < e.a2 ? __ldg(a.inst_bq + e.a7 + sub_early) : -1;
         gsync();  // every warp is done with the workspace (and the template) of the previous entry
         if (e.a0 != cur_tmpl) {
           const int64_t off = a.tmpl_off[e.a0];
@@ -792,7 +795,7 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
         const int TPS = GT / a.pack, sub = gt / TPS, lt = gt - sub * TPS;
         const bool act = sub < e.a2;
         const int pos = e.a7 + (act ? sub : 0);
-        const int bq = act ? a.inst_bq[pos] : -1;
+        const int bq = bq_early;
         const int ncell = T.w * T.h, ncell_e = (ncell + 1) & ~1, nint_e = (T.n_int + 1) & ~1;
         const int rf_size = reinterpret_cast<const int *>(tb)[6], rb_size = reinterpret_cast<const int *>(tb)[7];
         // pressures of the box (this CTA wrote them last step)
