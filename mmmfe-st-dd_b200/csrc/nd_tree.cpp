@@ -22,83 +22,129 @@ void NdTree::build(int32_t nx_, int32_t ny_, int32_t leaf_cells, int32_t subtree
   auto xe = [&](int i, int j) { return int32_t(int64_t(j) * (nx + 1) + i); };
   auto ye = [&](int i, int j) { return int32_t(nxe + int64_t(j) * nx + i); };
 
-  std::vector<int32_t> pos(n_flux, -1);  // scratch: position of a variable in the front being built
   std::vector<int32_t> first_desc;       // first node id of every node's subtree (post-order)
 
+  // Pass 1 (serial, sizes only): the recursion fixes the post-order numbering, boxes, children, heights and the sizes
+  // s / b of every front, so that all offsets are known.  Pass 2 fills the index lists of all fronts in parallel:
+  // the separator and boundary lists of a front are a function of its box alone (ascending canonical index), and the
+  // gather maps from a child's boundary entries are found by binary search in those sorted lists -- no state is
+  // shared between fronts.  (The serial one-pass version took 0.45 s for a 1024^2 grid.)
+  nodes.reserve(size_t(4) * size_t(nx) * ny / size_t(std::max(1, leaf_cells)) + 64);
+  first_desc.reserve(nodes.capacity());
   std::function<int32_t(int, int, int, int)> rec = [&](int i0, int i1, int j0, int j1) -> int32_t {
     const int w = i1 - i0, h = j1 - j0;
-    std::vector<int32_t> sep;
-    int32_t c0 = -1, c1 = -1;
+    int32_t c0 = -1, c1 = -1, s = 0;
     const int32_t first = int32_t(nodes.size());
     if (int64_t(w) * h <= leaf_cells || (w == 1 && h == 1)) {
-      for (int j = j0; j < j1; ++j)
-        for (int i = i0; i <= i1; ++i) {
-          const bool inner = i > i0 && i < i1;
-          if (inner || (i == i0 && i0 == 0) || (i == i1 && i1 == nx)) sep.push_back(xe(i, j));
-        }
-      for (int j = j0; j <= j1; ++j) {
-        const bool inner = j > j0 && j < j1;
-        if (inner || (j == j0 && j0 == 0) || (j == j1 && j1 == ny))
-          for (int i = i0; i < i1; ++i) sep.push_back(ye(i, j));
-      }
-      if (sep.empty()) return -1;
+      s = h * ((w - 1) + (i0 == 0) + (i1 == nx)) + w * ((h - 1) + (j0 == 0) + (j1 == ny));
+      if (s == 0) return -1;
     } else if (w >= h) {
       const int is = i0 + w / 2;
       c0 = rec(i0, is, j0, j1);
       c1 = rec(is, i1, j0, j1);
-      for (int j = j0; j < j1; ++j) sep.push_back(xe(is, j));
+      s = h;
     } else {
       const int js = j0 + h / 2;
       c0 = rec(i0, i1, j0, js);
       c1 = rec(i0, i1, js, j1);
-      for (int i = i0; i < i1; ++i) sep.push_back(ye(i, js));
+      s = w;
     }
-    std::vector<int32_t> bnd;
-    if (i0 > 0) for (int j = j0; j < j1; ++j) bnd.push_back(xe(i0, j));
-    if (i1 < nx) for (int j = j0; j < j1; ++j) bnd.push_back(xe(i1, j));
-    if (j0 > 0) for (int i = i0; i < i1; ++i) bnd.push_back(ye(i, j0));
-    if (j1 < ny) for (int i = i0; i < i1; ++i) bnd.push_back(ye(i, j1));
-    std::sort(sep.begin(), sep.end());
-    std::sort(bnd.begin(), bnd.end());
-
     NdNode nd;
-    nd.s = int32_t(sep.size());
-    nd.b = int32_t(bnd.size());
+    nd.s = s;
+    nd.b = h * ((i0 > 0) + (i1 < nx)) + w * ((j0 > 0) + (j1 < ny));
     nd.child[0] = c0;
     nd.child[1] = c1;
     nd.i0 = i0; nd.i1 = i1; nd.j0 = j0; nd.j1 = j1;
-    nd.idx_off = int64_t(idx.size());
     const int32_t id = int32_t(nodes.size());
-    for (int32_t p = 0; p < nd.s; ++p) {
-      idx.push_back(sep[p]);
-      node_of[sep[p]] = id;
-      pos_of[sep[p]] = p;
-      pos[sep[p]] = p;
-    }
-    for (int32_t q = 0; q < nd.b; ++q) {
-      idx.push_back(bnd[q]);
-      pos[bnd[q]] = nd.s + q;
-    }
-    const int32_t f = nd.s + nd.b;
-    nd.src_off = int64_t(src.size());
-    src.resize(src.size() + 2 * size_t(f), -1);
-    for (int c = 0; c < 2; ++c) {
-      const int32_t ch = nd.child[c];
-      if (ch < 0) continue;
-      nodes[ch].parent = id;
-      nd.height = std::max(nd.height, nodes[ch].height + 1);
-      const NdNode &cn = nodes[ch];
-      for (int32_t q = 0; q < cn.b; ++q) {
-        const int32_t v = idx[cn.idx_off + cn.s + q];
-        src[nd.src_off + int64_t(c) * f + pos[v]] = q;  // pos[v] is valid: child boundary is in this front
+    for (int c = 0; c < 2; ++c)
+      if (nd.child[c] >= 0) {
+        nodes[nd.child[c]].parent = id;
+        nd.height = std::max(nd.height, nodes[nd.child[c]].height + 1);
       }
-    }
-    for (int32_t p = 0; p < f; ++p) pos[idx[nd.idx_off + p]] = -1;
     nodes.push_back(nd);
     first_desc.push_back(first);
     return id;
   };
   rec(0, nx, 0, ny);
+  {
+    int64_t io = 0, so = 0;
+    for (NdNode &nd : nodes) {
+      nd.idx_off = io; io += nd.s + nd.b;
+      nd.src_off = so; so += 2 * int64_t(nd.s + nd.b);
+    }
+    idx.assign(size_t(io), -1);
+    src.assign(size_t(so), -1);
+  }
+  // separator / leaf-interior list of a box, ascending (x-edges before y-edges, each row-major = ascending index)
+  auto fill_sep = [&](const NdNode &nd, int32_t *out) {
+    const int i0 = nd.i0, i1 = nd.i1, j0 = nd.j0, j1 = nd.j1, w = i1 - i0, h = j1 - j0;
+    int32_t n = 0;
+    if (nd.child[0] < 0 && nd.child[1] < 0) {
+      for (int j = j0; j < j1; ++j)
+        for (int i = i0; i <= i1; ++i) {
+          const bool inner = i > i0 && i < i1;
+          if (inner || (i == i0 && i0 == 0) || (i == i1 && i1 == nx)) out[n++] = xe(i, j);
+        }
+      for (int j = j0; j <= j1; ++j) {
+        const bool inner = j > j0 && j < j1;
+        if (inner || (j == j0 && j0 == 0) || (j == j1 && j1 == ny))
+          for (int i = i0; i < i1; ++i) out[n++] = ye(i, j);
+      }
+    } else if (w >= h) {
+      const int is = i0 + w / 2;
+      for (int j = j0; j < j1; ++j) out[n++] = xe(is, j);
+    } else {
+      const int js = j0 + h / 2;
+      for (int i = i0; i < i1; ++i) out[n++] = ye(i, js);
+    }
+    return n;
+  };
+  // boundary list of a box, ascending: x-edges of the two vertical sides interleave row by row, then the y-edges of
+  // the bottom row, then those of the top row
+  auto fill_bnd = [&](const NdNode &nd, int32_t *out) {
+    const int i0 = nd.i0, i1 = nd.i1, j0 = nd.j0, j1 = nd.j1;
+    int32_t n = 0;
+    for (int j = j0; j < j1; ++j) {
+      if (i0 > 0) out[n++] = xe(i0, j);
+      if (i1 < nx) out[n++] = xe(i1, j);
+    }
+    if (j0 > 0) for (int i = i0; i < i1; ++i) out[n++] = ye(i, j0);
+    if (j1 < ny) for (int i = i0; i < i1; ++i) out[n++] = ye(i, j1);
+    return n;
+  };
+  bool bad = false;
+#pragma omp parallel
+  {
+    std::vector<int32_t> cb;  // a child's boundary list
+#pragma omp for schedule(dynamic, 256)
+    for (int32_t id = 0; id < int32_t(nodes.size()); ++id) {
+      const NdNode &nd = nodes[id];
+      int32_t *sep = idx.data() + nd.idx_off, *bnd = sep + nd.s;
+      if (fill_sep(nd, sep) != nd.s || fill_bnd(nd, bnd) != nd.b) { bad = true; continue; }
+      for (int32_t p = 0; p < nd.s; ++p) { node_of[sep[p]] = id; pos_of[sep[p]] = p; }
+      const int32_t f = nd.s + nd.b;
+      for (int c = 0; c < 2; ++c) {
+        const int32_t ch = nd.child[c];
+        if (ch < 0) continue;
+        const NdNode &cn = nodes[ch];
+        cb.resize(size_t(cn.b));
+        fill_bnd(cn, cb.data());
+        for (int32_t q = 0; q < cn.b; ++q) {  // the child's boundary is part of this front
+          const int32_t v = cb[q];
+          const int32_t *ps = std::lower_bound(sep, sep + nd.s, v);
+          int32_t pos;
+          if (ps != sep + nd.s && *ps == v) pos = int32_t(ps - sep);
+          else {
+            const int32_t *pb = std::lower_bound(bnd, bnd + nd.b, v);
+            if (pb == bnd + nd.b || *pb != v) { bad = true; continue; }
+            pos = nd.s + int32_t(pb - bnd);
+          }
+          src[nd.src_off + int64_t(c) * f + pos] = q;
+        }
+      }
+    }
+  }
+  if (bad) { nodes.clear(); return; }  // (cannot happen: the lists are a function of the boxes)
   const int32_t nn = int32_t(nodes.size());
 
   // ---- cut the tree: maximal boxes of at most subtree_cells cells become subtrees --------------------------------
