@@ -286,10 +286,8 @@ struct mmmfe_ctx {
   double basis_seconds = 0.0, basis_flops = 0.0, basis_bytes = 0.0, toep_flops = 0.0, toep_bytes = 0.0;
   int64_t basis_columns = 0;
   // temporaries of the factorisation
-  DevBuf<GemmProb> d_gemm;
-  DevBuf<int32_t> d_tiles;
-  DevBuf<InvProb> d_inv;
-  DevBuf<TransProb> d_trans;
+  DevBuf<char> desc_arena;  // problem descriptors of the factorisation batches (desc_upload)
+  size_t desc_top = 0;
   DevBuf<int32_t> d_fail;
 };
 
@@ -298,6 +296,24 @@ namespace mmmfe {
 // =================================================================================================================
 // numeric factorisation
 // =================================================================================================================
+// Problem descriptors of the batched factorisation kernels go into a device bump arena: every batch gets its own
+// range, so the host never waits for a kernel to finish before it uploads the next batch (the stream orders the
+// work; cudaMemcpyAsync from pageable memory returns once the source has been staged).  The arena is rewound -- after
+// a stream synchronisation -- only when it is full.
+template <class T>
+static T *desc_upload(mmmfe_ctx *c, const T *h, size_t count) {
+  const size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+  if (c->desc_top + bytes > c->desc_arena.n) {
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->desc_top = 0;
+    if (bytes > c->desc_arena.n) c->desc_arena.alloc(std::max(bytes * 2, size_t(64) << 20));
+  }
+  T *p = reinterpret_cast<T *>(c->desc_arena.p + c->desc_top);
+  c->desc_top += bytes;
+  CUDA_CHECK(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  return p;
+}
+
 static void run_gemm_batch(mmmfe_ctx *c, const std::vector<GemmProb> &pr) {
   if (pr.empty()) return;
   std::vector<int32_t> ts(pr.size() + 1);
@@ -308,20 +324,14 @@ static void run_gemm_batch(mmmfe_ctx *c, const std::vector<GemmProb> &pr) {
   }
   ts[pr.size()] = int32_t(tiles);
   if (tiles > 2000000000LL) fail(MMMFE_E_INVALID, "too many GEMM tiles");
-  if (c->d_gemm.n < pr.size()) c->d_gemm.alloc(pr.size() * 2);
-  if (c->d_tiles.n < ts.size()) c->d_tiles.alloc(ts.size() * 2);
-  CUDA_CHECK(cudaMemcpyAsync(c->d_gemm.p, pr.data(), pr.size() * sizeof(GemmProb), cudaMemcpyHostToDevice, c->stream));
-  CUDA_CHECK(cudaMemcpyAsync(c->d_tiles.p, ts.data(), ts.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-  launch_grouped_gemm(c->d_gemm.p, c->d_tiles.p, int32_t(pr.size()), int32_t(tiles), c->stream);
-  CUDA_CHECK(cudaStreamSynchronize(c->stream));  // descriptor buffers are reused by the next batch
+  const GemmProb *d_pr = desc_upload(c, pr.data(), pr.size());
+  const int32_t *d_ts = desc_upload(c, ts.data(), ts.size());
+  launch_grouped_gemm(d_pr, d_ts, int32_t(pr.size()), int32_t(tiles), c->stream);
 }
 
 static void run_trans_batch(mmmfe_ctx *c, const std::vector<TransProb> &pr) {
   if (pr.empty()) return;
-  if (c->d_trans.n < pr.size()) c->d_trans.alloc(pr.size() * 2);
-  CUDA_CHECK(cudaMemcpyAsync(c->d_trans.p, pr.data(), pr.size() * sizeof(TransProb), cudaMemcpyHostToDevice, c->stream));
-  launch_transpose(c->d_trans.p, int32_t(pr.size()), c->stream);
-  CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  launch_transpose(desc_upload(c, pr.data(), pr.size()), int32_t(pr.size()), c->stream);
 }
 
 // In place: SPD block A (full storage) -> L^-1, the inverse of its Cholesky factor (lower triangle, exact zeros
@@ -331,12 +341,8 @@ static void run_trans_batch(mmmfe_ctx *c, const std::vector<TransProb> &pr) {
 static void chol_inv_batch(mmmfe_ctx *c, const std::vector<InvProb> &probs, Arena &arena) {
   std::vector<InvProb> small, big;
   for (const auto &p : probs) (p.n <= 32 ? small : big).push_back(p);
-  if (!small.empty()) {
-    if (c->d_inv.n < small.size()) c->d_inv.alloc(small.size() * 2);
-    CUDA_CHECK(cudaMemcpyAsync(c->d_inv.p, small.data(), small.size() * sizeof(InvProb), cudaMemcpyHostToDevice, c->stream));
-    launch_small_inverse(c->d_inv.p, int32_t(small.size()), c->d_fail.p, c->stream);
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
-  }
+  if (!small.empty())
+    launch_small_inverse(desc_upload(c, small.data(), small.size()), int32_t(small.size()), c->d_fail.p, c->stream);
   if (big.empty()) return;
   const size_t mark = arena.top;
   std::vector<InvProb> a11, a22;
@@ -612,35 +618,44 @@ static void build_sweep_factor(mmmfe_ctx *c, Factor &F, const std::vector<double
 static std::vector<int32_t> subtree_classes(const NdTree &tr, const HostCsr &S, const std::vector<int32_t> &dof_of_canon) {
   const int64_t nxe = int64_t(tr.nx + 1) * tr.ny;
   std::vector<int32_t> cls(tr.instances.size(), -1);
-  std::map<std::pair<int32_t, uint64_t>, int32_t> seen;
-  std::vector<int32_t> local(size_t(tr.n_flux), -1);
+  std::vector<uint64_t> sigs(tr.instances.size(), 0);
   auto mix = [](uint64_t x) {
     x += 0x9e3779b97f4a7c15ull; x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull; x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
     return x ^ (x >> 31);
   };
-  for (size_t k = 0; k < tr.instances.size(); ++k) {
-    const SubtreeInstance &in = tr.instances[k];
-    const SubtreeTemplate &T = tr.templates[in.tmpl];
-    auto user = [&](int32_t code) {
-      const int type = code >> 30, dj = (code >> 15) & 0x7fff, di = code & 0x7fff;
-      const int64_t canon = type == 0 ? int64_t(in.J0 + dj) * (tr.nx + 1) + in.I0 + di : nxe + int64_t(in.J0 + dj) * tr.nx + in.I0 + di;
-      return dof_of_canon.empty() ? int32_t(canon) : dof_of_canon[canon];
-    };
-    for (int32_t l = 0; l < T.n_int; ++l) local[user(T.var_code[l])] = l;
-    for (int32_t q = 0; q < T.n_rootb; ++q) local[user(T.rootb_code[q])] = T.n_int + q;
-    uint64_t sig = 0;
-    for (int32_t l = 0; l < T.n_int; ++l) {
-      const int32_t row = user(T.var_code[l]);
-      for (int64_t e = S.rp[row]; e < S.rp[row + 1]; ++e) {
-        uint64_t bits;
-        std::memcpy(&bits, &S.val[e], sizeof bits);
-        sig += mix(mix(uint64_t(l) << 32 | uint32_t(local[S.col[e]])) ^ bits);
+#pragma omp parallel
+  {
+    std::vector<int32_t> local(size_t(tr.n_flux), -1);  // per thread: neighbouring subtrees share boundary variables
+#pragma omp for schedule(dynamic, 16)
+    for (int64_t k = 0; k < int64_t(tr.instances.size()); ++k) {
+      const SubtreeInstance &in = tr.instances[size_t(k)];
+      const SubtreeTemplate &T = tr.templates[in.tmpl];
+      auto user = [&](int32_t code) {
+        const int type = code >> 30, dj = (code >> 15) & 0x7fff, di = code & 0x7fff;
+        const int64_t canon = type == 0 ? int64_t(in.J0 + dj) * (tr.nx + 1) + in.I0 + di : nxe + int64_t(in.J0 + dj) * tr.nx + in.I0 + di;
+        return dof_of_canon.empty() ? int32_t(canon) : dof_of_canon[canon];
+      };
+      for (int32_t l = 0; l < T.n_int; ++l) local[user(T.var_code[l])] = l;
+      for (int32_t q = 0; q < T.n_rootb; ++q) local[user(T.rootb_code[q])] = T.n_int + q;
+      uint64_t sig = 0;
+      for (int32_t l = 0; l < T.n_int; ++l) {
+        const int32_t row = user(T.var_code[l]);
+        for (int64_t e = S.rp[row]; e < S.rp[row + 1]; ++e) {
+          uint64_t bits;
+          std::memcpy(&bits, &S.val[e], sizeof bits);
+          sig += mix(mix(uint64_t(l) << 32 | uint32_t(local[S.col[e]])) ^ bits);
+        }
       }
+      for (int32_t l = 0; l < T.n_int; ++l) local[user(T.var_code[l])] = -1;
+      for (int32_t q = 0; q < T.n_rootb; ++q) local[user(T.rootb_code[q])] = -1;
+      sigs[size_t(k)] = sig;
     }
-    for (int32_t l = 0; l < T.n_int; ++l) local[user(T.var_code[l])] = -1;
-    for (int32_t q = 0; q < T.n_rootb; ++q) local[user(T.rootb_code[q])] = -1;
-    auto it = seen.find({in.tmpl, sig});
-    if (it == seen.end()) it = seen.insert({{in.tmpl, sig}, int32_t(seen.size())}).first;
+  }
+  std::map<std::pair<int32_t, uint64_t>, int32_t> seen;
+  for (size_t k = 0; k < tr.instances.size(); ++k) {  // class numbers in instance order, as before
+    const int32_t tm = tr.instances[k].tmpl;
+    auto it = seen.find({tm, sigs[k]});
+    if (it == seen.end()) it = seen.insert({{tm, sigs[k]}, int32_t(seen.size())}).first;
     cls[k] = it->second;
   }
   return cls;
@@ -813,39 +828,56 @@ static std::shared_ptr<Factor> factorize(mmmfe_ctx *c, const Sub &sd, int Mmax, 
     arena_need = std::max(arena_need, need);
   }
   arena.buf.alloc(arena_need + 16);
-  DevBuf<int32_t> d_lvl;
+  {  // room for the descriptors of the whole factorisation (~0.6 KB per front), at most 512 MB
+    const size_t want = std::min(size_t(512) << 20, tr.nodes.size() * 700 + (size_t(16) << 20));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (c->desc_arena.n < want) c->desc_arena.alloc(want);
+    c->desc_top = 0;
+  }
   for (size_t h = 0; h < tr.by_height.size(); ++h) {
     const auto &lvl = tr.by_height[h];
-    if (h > 0) {
-      d_lvl.upload(lvl);
-      launch_extend_add(d_lvl.p, int32_t(lvl.size()), F->fronts.p, d_foff.p, F->src.p, W.p, c->stream);
-      CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    }
+    const int64_t nl = int64_t(lvl.size());
+    if (h > 0)
+      launch_extend_add(desc_upload(c, lvl.data(), lvl.size()), int32_t(nl), F->fronts.p, d_foff.p, F->src.p, W.p, c->stream);
     arena.top = 0;
-    std::vector<InvProb> inv;
-    for (int32_t id : lvl) {
-      const NdNode &n = tr.nodes[id];
-      inv.push_back({W.p + n.f_off, n.s, n.s + n.b});
+    // the descriptor arrays of a level are filled in parallel (the leaf levels of a 1024^2 grid have 131 072 fronts)
+    const size_t nls = size_t(nl);
+    std::vector<InvProb> inv(nls);
+#pragma omp parallel for schedule(static) if (nl > 4096)
+    for (int64_t k = 0; k < nl; ++k) {
+      const NdNode &n = tr.nodes[lvl[size_t(k)]];
+      inv[size_t(k)] = {W.p + n.f_off, n.s, n.s + n.b};
     }
     chol_inv_batch(c, inv, arena);  // F11 block now holds Li = L^-1
-    std::vector<GemmProb> gW, gU, gX, gG, gF;
-    for (int32_t id : lvl) {
-      const NdNode &n = tr.nodes[id];
+    // positions of the fronts with a boundary part (all but the root) and of their b x s work blocks in the arena
+    std::vector<int64_t> slot(size_t(nl) + 1, 0), wt_off(size_t(nl) + 1, 0);
+    for (int64_t k = 0; k < nl; ++k) {
+      const NdNode &n = tr.nodes[lvl[size_t(k)]];
+      slot[size_t(k) + 1] = slot[size_t(k)] + (n.b > 0 ? 1 : 0);
+      wt_off[size_t(k) + 1] = wt_off[size_t(k)] + int64_t(n.b) * n.s;
+    }
+    double *wt_base = arena.take(size_t(wt_off[size_t(nl)]));
+    const size_t nb = size_t(slot[size_t(nl)]);
+    std::vector<GemmProb> gW(nb), gU(nb), gX(nls), gG(nb), gF(nb);
+#pragma omp parallel for schedule(static) if (nl > 4096)
+    for (int64_t k = 0; k < nl; ++k) {
+      const NdNode &n = tr.nodes[lvl[size_t(k)]];
       const int s = n.s, b = n.b, f = s + b;
       double *Fp = W.p + n.f_off;
       double *Rb = F->R.p + n.rb_off, *Rf = F->R.p + n.rf_off;
       const bool sub = n.subtree >= 0;
       // F11^-1 = Li^T Li: rows of R (top node, stride ldr) or the first s rows of R^T (subtree node, stride s)
-      gX.push_back({Fp, Fp, Rb, s, s, s, sub ? s : n.ldr, 1, f, f, 1, 1.0, 0.0});
+      gX[size_t(k)] = {Fp, Fp, Rb, s, s, s, sub ? s : n.ldr, 1, f, f, 1, 1.0, 0.0};
       if (b == 0) continue;
-      double *Wt = arena.take(size_t(b) * s);
+      const size_t q = size_t(slot[size_t(k)]);
+      double *Wt = wt_base + wt_off[size_t(k)];
       double *F21 = Fp + int64_t(s) * f, *F22 = F21 + s;
-      gW.push_back({F21, Fp, Wt, b, s, s, s, f, 1, 1, f, 1.0, 0.0});          // Wt = F21 Li^T        (b x s)
-      gU.push_back({Wt, Wt, F22, b, b, s, f, s, 1, 1, s, -1.0, 1.0});         // U  = F22 - Wt Wt^T
+      gW[q] = {F21, Fp, Wt, b, s, s, s, f, 1, 1, f, 1.0, 0.0};          // Wt = F21 Li^T        (b x s)
+      gU[q] = {Wt, Wt, F22, b, b, s, f, s, 1, 1, s, -1.0, 1.0};         // U  = F22 - Wt Wt^T
       // -G^T = -Li^T Wt^T (s x b): forward copy, and the right part of R for top nodes
-      gF.push_back({Fp, Wt, Rf, s, b, s, n.ldf, 1, f, 1, s, -1.0, 0.0});
-      if (sub) gG.push_back({Wt, Fp, Rb + int64_t(s) * s, b, s, s, s, s, 1, f, 1, -1.0, 0.0});  // rows s.. of R^T = -G = -Wt Li
-      else gG.push_back({Fp, Wt, Rb + s, s, b, s, n.ldr, 1, f, 1, s, -1.0, 0.0});
+      gF[q] = {Fp, Wt, Rf, s, b, s, n.ldf, 1, f, 1, s, -1.0, 0.0};
+      if (sub) gG[q] = {Wt, Fp, Rb + int64_t(s) * s, b, s, s, s, s, 1, f, 1, -1.0, 0.0};  // rows s.. of R^T = -G = -Wt Li
+      else gG[q] = {Fp, Wt, Rb + s, s, b, s, n.ldr, 1, f, 1, s, -1.0, 0.0};
     }
     run_gemm_batch(c, gW);
     run_gemm_batch(c, gU);
