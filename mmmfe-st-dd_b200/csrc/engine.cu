@@ -260,7 +260,7 @@ struct mmmfe_ctx {
   DevBuf<int64_t> send_index;
   DevBuf<double> send_buf, recv_buf;
   // GMRES workspace
-  DevBuf<double> Q, h_dev, norm_dev, arn_scratch;
+  DevBuf<double> Q, h_dev, norm_dev, arn_scratch, ar_buf;
   DevBuf<unsigned int> arn_ticket;
   int gmres_lookahead = -1;        // iterations enqueued ahead of the host's stop test; -1: 3 on the basis operator, else 0
   int gmres_surplus = 0;           // iterations of the last solve that ran beyond the converged one
@@ -2523,11 +2523,11 @@ int mmmfe_comm_allreduce_sum(mmmfe_ctx *c, double *inout, int32_t n) {
   if (!c || !inout || n < 0) return MMMFE_E_INVALID;
   if (c->world <= 1 || n == 0) return MMMFE_OK;
   MMMFE_TRY(c, {
-    DevBuf<double> d;
-    d.upload(inout, size_t(n));
     if (!c->stream) CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    allreduce_sum(c, d.p, size_t(n));
-    CUDA_CHECK(cudaMemcpyAsync(inout, d.p, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (c->ar_buf.n < size_t(n)) c->ar_buf.alloc(std::max(size_t(n) * 2, size_t(1024)));  // kept: no allocation per call
+    CUDA_CHECK(cudaMemcpyAsync(c->ar_buf.p, inout, size_t(n) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    allreduce_sum(c, c->ar_buf.p, size_t(n));
+    CUDA_CHECK(cudaMemcpyAsync(inout, c->ar_buf.p, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
   });
 }
