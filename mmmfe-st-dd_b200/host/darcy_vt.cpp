@@ -143,9 +143,8 @@ void init_sub(Sub &s, int r, int n0, int n1, const std::vector<int> &pat, double
 // Row-parallel: every row gathers the contributions of its (at most two) cells in cell order, which is the order
 // the reference's cell loop adds them in; explicit zeros of the local matrices are kept (same sparsity pattern).
 void assemble_matrix(Sub &s, double c0) {
-  const int n = s.n, W = 12;
-  std::unique_ptr<int[]> cnt(new int[n]), cols(new int[size_t(n) * W]);  // (written before they are read: no zero fill)
-  std::unique_ptr<double[]> vals(new double[size_t(n) * W]);
+  const int n = s.n;
+  constexpr int W = 12;
   std::vector<double> g, w;
   gauss01(2, g, w);
   const KInverse<2> k_inverse;
@@ -181,61 +180,69 @@ void assemble_matrix(Sub &s, double c0) {
         }
     }
   }
+  // Rows straight into CSR: a flux row holds the 4 edges + the cell of each adjacent cell with the shared edge (the
+  // row's own) merged, a pressure row its 4 edges + itself, so the row lengths are known up front.
+  Csr &m = s.matrix;
+  m.n_rows = m.n_cols = n;
+  m.rp.assign(size_t(n) + 1, 0);
+#pragma omp parallel for schedule(static)
+  for (int r = 0; r < n; ++r) {
+    int cells;
+    if (r < s.nxe) { const int i = r % (nx + 1); cells = (i > 0) + (i < nx); }
+    else if (r < s.nf) { const int j = (r - s.nxe) / nx; cells = (j > 0) + (j < ny); }
+    else cells = 0;
+    m.rp[size_t(r) + 1] = r < s.nf ? 5 * cells - (cells == 2 ? 1 : 0) : 5;
+  }
+  for (int r = 0; r < n; ++r) m.rp[size_t(r) + 1] += m.rp[size_t(r)];
+  m.col.resize(size_t(m.rp[n]));
+  m.val.resize(size_t(m.rp[n]));
   bool overflow = false;
 #pragma omp parallel
   {
-    auto add = [&](int r, int c, double v) {
-      int *rc = &cols[size_t(r) * W];
-      double *rv = &vals[size_t(r) * W];
-      for (int t = 0; t < cnt[r]; ++t) if (rc[t] == c) { rv[t] += v; return; }
-      if (cnt[r] >= W) { overflow = true; return; }
-      rc[cnt[r]] = c; rv[cnt[r]] = v; ++cnt[r];
+    std::pair<int, double> row[W];
+    int cnt = 0;
+    auto add = [&](int c, double v) {
+      for (int t = 0; t < cnt; ++t) if (row[t].first == c) { row[t].second += v; return; }
+      if (cnt >= W) { overflow = true; return; }
+      row[cnt++] = {c, v};
     };
-    // the contributions of local edge e of cell (i, j) to row r
-    auto edge_row = [&](int r, int i, int j, int e) {
+    // the contributions of local edge e of cell (i, j)
+    auto edge_row = [&](int i, int j, int e) {
       const int loc[4] = {j * (nx + 1) + i, j * (nx + 1) + i + 1, s.nxe + j * nx + i, s.nxe + (j + 1) * nx + i};
       const double *aloc = &A[size_t(j * nx + i) * 16];
-      for (int f = 0; f < 4; ++f) add(r, loc[f], aloc[e * 4 + f]);
-      add(r, s.nf + j * nx + i, -div[e]);  // -phi_p div phi_u
+      for (int f = 0; f < 4; ++f) add(loc[f], aloc[e * 4 + f]);
+      add(s.nf + j * nx + i, -div[e]);  // -phi_p div phi_u
+    };
+    auto flush = [&](int r) {
+      if (cnt != int(m.rp[size_t(r) + 1] - m.rp[size_t(r)])) { overflow = true; cnt = 0; return; }
+      std::sort(row, row + cnt);
+      for (int t = 0; t < cnt; ++t) { m.col[size_t(m.rp[r]) + t] = row[t].first; m.val[size_t(m.rp[r]) + t] = row[t].second; }
+      cnt = 0;
     };
 #pragma omp for schedule(static)
     for (int r = 0; r < s.nxe; ++r) {  // x-edges: left cell, then right cell
       const int j = r / (nx + 1), i = r % (nx + 1);
-      cnt[r] = 0;
-      if (i > 0) edge_row(r, i - 1, j, 1);
-      if (i < nx) edge_row(r, i, j, 0);
+      if (i > 0) edge_row(i - 1, j, 1);
+      if (i < nx) edge_row(i, j, 0);
+      flush(r);
     }
 #pragma omp for schedule(static)
     for (int k = 0; k < s.nye; ++k) {  // y-edges: lower cell, then upper cell
-      const int j = k / nx, i = k % nx, r = s.nxe + k;
-      cnt[r] = 0;
-      if (j > 0) edge_row(r, i, j - 1, 3);
-      if (j < ny) edge_row(r, i, j, 2);
+      const int j = k / nx, i = k % nx;
+      if (j > 0) edge_row(i, j - 1, 3);
+      if (j < ny) edge_row(i, j, 2);
+      flush(s.nxe + k);
     }
 #pragma omp for schedule(static)
     for (int c = 0; c < s.np; ++c) {
       const int j = c / nx, i = c % nx, r = s.nf + c;
       const int loc[4] = {j * (nx + 1) + i, j * (nx + 1) + i + 1, s.nxe + j * nx + i, s.nxe + (j + 1) * nx + i};
-      cnt[r] = 0;
-      for (int e = 0; e < 4; ++e) add(r, loc[e], s.dt * div[e]);  // dt div phi_u phi_p
-      add(r, r, c0 * s.hx * s.hy);
+      for (int e = 0; e < 4; ++e) add(loc[e], s.dt * div[e]);  // dt div phi_u phi_p
+      add(r, c0 * s.hx * s.hy);
+      flush(r);
     }
   }
   if (overflow) throw std::runtime_error("matrix row overflow");
-  A.reset();
-  Csr &m = s.matrix;
-  m.n_rows = m.n_cols = n;
-  m.rp.assign(n + 1, 0);
-  for (int r = 0; r < n; ++r) m.rp[r + 1] = m.rp[r] + cnt[r];
-  m.col.resize(m.rp[n]);
-  m.val.resize(m.rp[n]);
-#pragma omp parallel for schedule(static)
-  for (int r = 0; r < n; ++r) {
-    std::pair<int, double> row[12];
-    for (int t = 0; t < cnt[r]; ++t) row[t] = {cols[size_t(r) * W + t], vals[size_t(r) * W + t]};
-    std::sort(row, row + cnt[r]);
-    for (int t = 0; t < cnt[r]; ++t) { m.col[m.rp[r] + t] = row[t].first; m.val[m.rp[r] + t] = row[t].second; }
-  }
 }
 
 int side_to_bc(int side);
