@@ -397,3 +397,38 @@ def test_sweep_kernel_watchdog_reports_a_dependency_that_never_completes():
     eng.setup()
     assert rel_l2(eng.apply(q), prob.apply_S(q)) < 1e-10
     eng.close()
+
+
+@pytest.mark.parametrize("mesh,mortar,k", [
+    ([[24, 40, 6], [40, 24, 3], [17, 33, 3], [33, 17, 6]], [4, 4, 3], 1),   # anisotropic cells, every subdomain its own factor
+    ([[48, 20, 4], [20, 48, 4], [20, 48, 4], [48, 20, 4]], [5, 5, 2], 2),   # two factor groups of two, quadratic mortar
+])
+def test_rectangular_grids_through_the_persistent_kernel(mesh, mortar, k):
+    """nx != ny (hx != hy: different K_up / K_pu constants per direction, non-square subtree boxes): operator, bar
+    sweep, GMRES and final sweep with the persistent kernel forced on, against the oracle and the per-level kernels."""
+    prm = default_params(k)
+    prob = make_problem(prm, n_sub=4, mesh=mesh, mortar=mortar)
+    ref = prob.run_cycle(0)
+    q = np.random.default_rng(21).standard_normal(prob.n_iface)
+    ap_ref = prob.apply_S(q)
+    outs = {}
+    for sweep in (1, 0):
+        eng = engine_from_oracle(prob, options={"use_sweep": sweep, "subtree_cells": 64, "sweep_autotune": 0, "operator": 0})
+        eng.setup()
+        assert eng.stat("sweep_batches") == (eng.stat("batches") if sweep else 0)
+        outs[sweep] = eng.apply(q)
+        assert rel_l2(outs[sweep], ap_ref) < TOL
+        if sweep:
+            set_bar_data(eng, prob)
+            eng.bar_sweep()
+            assert eng.stat("bar_sweep_batches") == eng.stat("sweep_batches")
+            out = eng.gmres(prm.tolerance, prm.max_iteration)
+            assert out["iterations"] == ref.gmres_iterations
+            assert out["r_norm"] == pytest.approx(ref.r_norm, rel=1e-12)
+            eng.final_sweep()
+            for li, sd in enumerate(prob.subs):
+                sol = eng.get_solution(li)
+                assert rel_l2(sol[:, sd.nf:], ref.solution_p[li]) < 1e-9
+                assert rel_l2(sol[:, :sd.nf], ref.solution_u[li]) < 1e-9
+        eng.close()
+    assert rel_l2(outs[1], outs[0]) < 1e-12
