@@ -141,6 +141,10 @@ __device__ __forceinline__ void red_release(uint32_t *p) {
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" ::"l"(p) : "memory");
 }
 
+__device__ __forceinline__ void red_relaxed(uint32_t *p) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;\n" ::"l"(p) : "memory");
+}
+
 __device__ __forceinline__ void wait_counter(const uint32_t *p, uint32_t target, volatile int *abort_flag) {
   if (ld_acquire(p) >= target) return;
   const long long t0 = clock64();
@@ -1023,13 +1027,19 @@ __global__ void __launch_bounds__(CT + 64, (CT >= 256 ? 1 : (CT >= 128 ? 3 : 6))
         asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;\n" : "=r"(old) : "r"(s_u32(done_cnt + slot)) : "memory");
         if (old + 1 == uint32_t(G / NB + 1) * uint32_t(CT / 32 / a.ng)) {
           // (-1: nobody on another CTA waits for that completion, sweep_plan.cpp)
-          if (p_sig >= 0) red_release(a.cnt + p_sig);
-          if (p_n > 0 && sig0 >= 0) red_release(a.cnt + sig0);
-          if (p_n > 1 && sig1 >= 0) red_release(a.cnt + sig1);
-          for (int t = 2; t < p_n; ++t) {
-            const int32_t id = __ldg(a.index + p_off + t);
-            if (id >= 0) red_release(a.cnt + id);
-          }
+          // one counter: release increment; several (option pub_fence): ONE release fence, then relaxed increments
+          const int n_pub = (p_sig >= 0) + (p_n > 0 && sig0 >= 0) + (p_n > 1 && sig1 >= 0) + (p_n > 2 ? p_n - 2 : 0);
+          const bool fence = a.pub_fence && n_pub > 1;
+          if (fence) asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+          auto pub = [&](int32_t id) {
+            if (id < 0) return;
+            if (fence) red_relaxed(a.cnt + id);
+            else red_release(a.cnt + id);
+          };
+          pub(p_sig);
+          if (p_n > 0) pub(sig0);
+          if (p_n > 1) pub(sig1);
+          for (int t = 2; t < p_n; ++t) pub(__ldg(a.index + p_off + t));
         }
       }
     }

@@ -143,6 +143,7 @@ struct SweepArgs {
   const int32_t *inst_bq;              // per subtree (allocation order): boundary-entry table offset or -1
   const int32_t *inst_ij;              // per subtree (allocation order): I0, J0
   int32_t evict_first;
+  int32_t pub_fence;            // entries with several completion counters: one release fence + relaxed increments
   uint32_t spin_ns;             // back-off of the service warps' polling loops
   int32_t poll_window;          // entries ahead of the oldest unopened one that poll the completion counters
 };
