@@ -125,3 +125,29 @@ def test_reference_data_headers_compile_for_the_device():
         for f, p in zip(files, procs):
             out = p.communicate()[0]
             assert p.returncode == 0, (f, out[:800])
+
+
+def test_a_data_header_that_cannot_run_on_the_device_keeps_the_host_loops(tmp_path):
+    """build.py's fallback: a header whose overriders call a plain host helper does not compile for sm_100a; the same
+    translation unit with MMMFE_NO_DEVICE_DATA (stubs, `enabled()` = false) does, and the front-end then evaluates the
+    data classes on the host as before."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    host = os.path.join(ROOT, "mmmfe-st-dd_b200", "host")
+    default = open(os.path.join(host, "data_default.h")).read()
+    # a host-only helper (no MMMFE_HD) inside the right-hand side
+    bad = default.replace("MMMFE_HD inline double pressure(", "inline double host_only_scale() { return 1.0; }\nMMMFE_HD inline double pressure(")
+    bad = bad.replace("return 8 * std::cos(8 * t) * shape", "return host_only_scale() * 8 * std::cos(8 * t) * shape")
+    assert bad != default
+    hdr = tmp_path / "data_host_only.h"
+    hdr.write_text(bad.replace("MMMFE_DATA_DEFAULT_H", "MMMFE_DATA_HOST_ONLY_H"))
+    base = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-fmad=false", "-diag-suppress",
+            "20012,20014,940,20011,20015,177", "-I", os.path.join(host, "shim"), "-I", host, "-I", os.path.join(ROOT, "include"),
+            f'-DMMMFE_DATA_HEADER="{hdr}"', "-c", os.path.join(host, "data_device.cu")]
+    dev = subprocess.run(base + ["-o", str(tmp_path / "dev.o")], capture_output=True, text=True)
+    assert dev.returncode != 0 and "host_only_scale" in (dev.stdout + dev.stderr)
+    stub = subprocess.run(base + ["-DMMMFE_NO_DEVICE_DATA", "-o", str(tmp_path / "stub.o")], capture_output=True, text=True)
+    assert stub.returncode == 0, stub.stderr[:500]
