@@ -89,7 +89,11 @@ const char *mmmfe_version(void);
  * "sweep_groups" (independent compute groups per CTA), "sweep_autotune" (default 1: time one star sweep with the
  * persistent kernel and one with the per-level kernels at set-up, compare their traces (set-up fails above 1e-11) and
  * keep the faster; the decision is summed over the ranks), "sweep_crosscheck" (with sweep_autotune = 0: still run and
- * compare both once).
+ * compare both once; "tune_steps", default 32: time levels of the longest sweep that comparison runs on, 0 = all),
+ * "sweep_bar" / "sweep_final" (default 1: the bar and final sweeps run through the persistent kernel where the star
+ * sweeps do), "sweep_pub_fence" (-1 = by the number of right-hand sides: entries with several completion counters
+ * publish with one release fence), "gmres_lookahead" (iterations enqueued ahead of the host's stop test; -1 = 3 on
+ * the multiscale-basis operator, 0 on the star sweeps; iteration counts, residuals and lambda do not depend on it).
  * Interface operator: "operator" 0 = nt star solves per subdomain in every GMRES iteration (the reference's loop,
  * src/darcy_vtdd.cc:1316-1411), 1 = multiscale flux basis (the reference's dormant compute_multiscale_basis,
  * src/darcy_vtdd.cc:959-1003): the response to every mortar basis function of the FIRST mortar time slab is computed
