@@ -44,6 +44,25 @@ def test_report_tables_through_the_product_path():
     assert abs(reps[0]["gmres_iterations"] - row["gmres"]) <= 1
 
 
+@pytest.mark.parametrize("mortar_degree,cycle,published", [(1, 0, 11), (1, 1, 23), (1, 2, 39), (1, 3, 59), (2, 0, 18)])
+def test_published_gmres_counts_from_the_product_residual_history(tmp_path, mortar_degree, cycle, published):
+    """report.pdf prints the first k with residual_k / r_norm < tol (the relative residual of
+    src/darcy_vtdd.cc:1478 divided once more by r_norm; tests/test_oracle_golden.py), the current source stops at
+    residual_k < tol.  Both counts are read off the residual history the CUDA path returns (run to tol / 10)."""
+    prm = default_params(mortar_degree, cycle + 1)
+    p = pkg().write_parameter_file(str(tmp_path / "parameter.txt"), prm.mesh[:-1], prm.mesh[-1],
+                                   mortar_degree=mortar_degree, num_refinement=cycle + 1, tol=1e-7,
+                                   bc=("D 0.0", "N 0.0", "D 0.0", "N 1.0"))  # the shipped parameter.txt
+    reps, res, _ = pkg().host_run(p, verbose=0, write_output=0, only_cycle=cycle, compute_errors=0)
+    r_norm = reps[-1]["r_norm"]
+    first = lambda thr: next(k for k in range(1, len(res)) if res[k] < thr)  # noqa: E731
+    assert first(1e-6 * r_norm) == published
+    prm.tolerance = 1e-7
+    o = mo.run(prm, cycles=[cycle])[0]
+    assert first(1e-6) == next(k for k in range(1, len(o.residuals)) if o.residuals[k] < 1e-6)
+    assert reps[-1]["gmres_iterations"] == o.gmres_iterations and r_norm == pytest.approx(o.r_norm, rel=1e-12)
+
+
 def test_medium_nonmatching_grids_match_oracle(tmp_path):
     """2x2, ratio-2 non-matching space and time grids (BASELINE configs[1] scaled down): 96^2x24 / 48^2x12."""
     mesh = [[96, 96, 24], [48, 48, 12], [48, 48, 12], [96, 96, 24]]

@@ -30,8 +30,8 @@ def _check_row(res, row, its_slack):
 def test_table2_linear_mortar_cycles_0_to_3():
     """Every printed digit of all four error columns; GMRES count within the +-1 the contract allows.
 
-    The current source counts the operator application before the stop test
-    (src/darcy_vtdd.cc:1363 vs 1488), one more than the March-2020 table in cycles 0-2.
+    The current source stops at residual_k < tol, the March-2020 table at residual_k / r_norm < tol
+    (test_published_gmres_counts_follow_from_the_residual_history): one fewer in cycles 0-2 where r_norm > 1.
     """
     res = mo.run(_params(1, 4))
     for r, row in zip(res, GOLD["table2_linear_mortar"]["rows"]):
@@ -41,9 +41,8 @@ def test_table2_linear_mortar_cycles_0_to_3():
 @pytest.mark.slow
 def test_table2_linear_mortar_cycle_4():
     res = mo.run(_params(1, 5), cycles=[4])
-    # errors match in every digit; 82 iterations against 86 published.  Not a round-off effect (the count is stable
-    # under operator perturbations up to 1e-8, tests/test_oracle_sensitivity.py): the March-2020 report predates the
-    # current source, whose counts also differ by +1, +1, +1, 0 in cycles 0-3.  Parity of the COUNT is unpinned here.
+    # errors match in every digit; 82 iterations against 86 published: the report-era stop test was scaled by
+    # r_norm once more (test_published_count_of_table2_row5_follows_from_the_residual_history reproduces the 86).
     _check_row(res[0], GOLD["table2_linear_mortar"]["rows"][4], its_slack=4)
 
 
