@@ -141,6 +141,35 @@ def test_two_rank_exchange_equals_single_rank(n0, n1, fine_first):
         assert np.array_equal(np.asarray(vals), ref[key]), key  # bitwise: a + b is commutative, order is fixed
 
 
+@pytest.mark.parametrize("n0,n1,world", [(4, 4, 3), (4, 4, 4), (8, 8, 8), (8, 4, 5), (3, 5, 7)])
+def test_plans_of_all_ranks_fit_together(n0, n1, world):
+    """The plans of 3 ... 8 ranks (what SCALE runs at N = 4 and 8), delivered in-process: rank a's slice for peer b is
+    as long as b's slice for a, faces arrive in the order the receiver indexes them, and exchange + combine equals
+    the single-rank result bit for bit."""
+    pkg = mmmfe_import.load()
+    nb = _topology(n0, n1)
+    rng = np.random.default_rng(n0 * 100 + n1 * 10 + world)
+    owner = pkg.assign_owners(list(rng.uniform(1.0, 8.0, n0 * n1)), world)
+    ref, _ = _reference(n0, n1)
+    state = {}
+    for rank in range(world):
+        mine = [r for r in range(n0 * n1) if owner[r] == rank]
+        sides, n_iface = _local_sides(mine, nb, n0)
+        partner, send_index, peers = pkg.exchange_plan(sides, n_iface, owner, rank, world)
+        send = _values(sides, n_iface)
+        assert [p[0] for p in peers] == sorted({owner[o] for r, _, o, _, _ in sides if owner[o] != rank})
+        state[rank] = (sides, partner, send, send[send_index], peers)
+    for rank, (sides, partner, send, _, peers) in state.items():
+        recv = np.zeros(int(sum(p[3] for p in peers)))
+        for prank, _, roff, cnt in peers:
+            back = [q for q in state[prank][4] if q[0] == rank]
+            assert len(back) == 1 and back[0][3] == cnt  # the peer sends exactly what this rank expects
+            recv[roff:roff + cnt] = state[prank][3][back[0][1]:back[0][1] + cnt]
+        out = _combine(send, partner, recv)
+        for g, s, _, off, ln in sides:
+            assert np.array_equal(out[off:off + ln], ref[(g, s)]), (rank, g, s)
+
+
 def test_owner_rule_balances_cost_in_contiguous_blocks():
     pkg = mmmfe_import.load()
     cost = [8.0 if ((r % 8) + (r // 8)) % 2 == 0 else 1.0 for r in range(64)]  # configs[3]: 8x8 checkerboard
