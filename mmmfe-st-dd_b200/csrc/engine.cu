@@ -1909,6 +1909,15 @@ static void setup(mmmfe_ctx *c) {
   // the other, the per-level kernels run them concurrently on their own streams, so the winner depends on the mix.
   bool any_sweep = false;
   for (auto &b : c->batches) any_sweep |= b->sweep;
+  // A rank without a sweep plan (only constrained or very small subdomains) still takes part in the all-reduce of the
+  // times below: the condition of a collective must not depend on what a rank happens to own.
+  if (!any_sweep && c->world > 1 && (c->sweep_autotune || c->sweep_crosscheck)) {
+    DevBuf<double> tune;
+    tune.alloc(4);
+    tune.zero(c->stream);
+    allreduce_sum(c, tune.p, 2);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  }
   if (any_sweep && (c->sweep_autotune || c->sweep_crosscheck)) {
     // The comparison runs on the first tune_steps of the longest sweep's time levels (every level walks the same entry lists and the
     // same kernels, so both the check and the time ratio carry over): a full sweep of each implementation, twice,
