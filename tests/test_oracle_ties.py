@@ -1,16 +1,24 @@
 """The point-location hazard of the quadratic mortar (quirk Q5): which fine cell a mortar-face Gauss point samples
 when it lies exactly on a fine cell boundary (FEFieldFunction, inc/utilities.h:484).
 
-deal.II tries the candidate cells in the order of GridTools' compare_point_association (scalar product of
-cell-centre direction and point direction, equal products keep ascending cell index).  With dyadic coordinates the
-two products are bitwise equal and the lower cell / earlier level wins; with non-dyadic coordinates the last bit of
-the mapped quadrature point decides, point by point.  Consequences pinned here:
-  * report.pdf Table 4 row 1 (ties only on the dyadic 2- and 4-cell subdomains) is reproduced digit for digit by the
-    lower/earlier rule and by no other uniform rule;
-  * row 3 (ties with ratio 6 on the non-dyadic 12-cell subdomains 0 and 3) lies strictly between the uniform choices
-    on those two subdomains -- it cannot be reproduced without deal.II's round-off, and is bracketed instead;
-  * on BASELINE.json configs[3] (8x8 subdomains, 256^2 x 512 / 128^2 x 256, mortar 16 x 16 x 32: every coordinate
-    dyadic) the rule is deterministic, and the scaled-down case shows how much is at stake if it were not.
+deal.II (9.1 series, restated in oracle/dealii_point_location.py) tries the cells around the closest vertex in the
+order of the scalar product of cell-centre direction and point direction; equal products keep ascending cell index.
+In exact arithmetic the two candidates of a tie have equal products and the lower cell / earlier level wins -- the rule
+the oracle and the product implement.  In floating point the mapped Gauss point is a sum of eight rounded products
+(its OTHER two abscissae are irrational) and the centre directions are normalised sums, so the last bits decide,
+point by point, unless every coordinate has a single significant bit.  Consequences pinned here:
+  * report.pdf Table 4 row 1 (ties only on the 2- and 4-cell subdomains, coordinates 0, 1/2, 1: everything exact) is
+    reproduced digit for digit by the lower/earlier rule and by no other uniform rule -- and the restated candidate
+    order predicts exactly that rule there;
+  * row 3 and row 5 (ties with ratio 6 and 12 on the 12- and 48-cell subdomains 0 and 3) lie strictly between the
+    uniform choices; the restated candidate order (no fitted parameter) brings the four error columns from 3-30 %
+    off (uniform lower rule) to 0.2-1.4 % (row 3) and 0.1-2.7 % (row 5) and the report-era GMRES count to +-1; the
+    remaining gap is the strict inside-unit-cell test on deal.II's inverse map, which is not restated;
+  * on BASELINE.json configs[3] (8x8 subdomains, 256^2 x 512 / 128^2 x 256, mortar 16 x 16 x 32) the tie COORDINATES
+    are exact, but the mapped Gauss points are not: under the restated order about a tenth of the tie points leave
+    the lower cell on the scaled-down case and the operator moves by ~17 %.  What the reference returns there depends
+    on the deal.II version and its round-off (README.md:42 names 9.5.2, whose point location is a different
+    algorithm again); the product implements the exact-arithmetic limit and says so.
 """
 import itertools
 import json
@@ -62,10 +70,11 @@ def test_row3_is_bracketed_by_the_choices_on_the_non_dyadic_subdomains():
     assert vals["pressure_l2l2"][0] == pytest.approx(row["pressure_l2l2"], rel=0.05)
 
 
-def test_configs3_coordinates_are_exact_so_ties_are_deterministic():
-    """Every fine vertex coordinate and every mortar Gauss-point tie coordinate of configs[3] is a dyadic rational
-    with few bits: x0 + i*h and the mapped face centre are computed without rounding, the candidates' scalar
-    products are bitwise equal, deal.II keeps ascending cell order = lower cell / earlier level."""
+def test_configs3_tie_coordinates_are_exact():
+    """Every fine vertex coordinate and every mortar-face centre of configs[3] is a dyadic rational with few bits:
+    the TIE ITSELF is exact (x0 + i*h and the face centre are computed without rounding), so the exact-arithmetic
+    rule -- lower cell / earlier level -- is well defined there.  (What deal.II's floating-point point location
+    makes of it is a different matter: test_restated_candidate_order_on_a_scaled_configs3.)"""
     from fractions import Fraction
     n0 = 8
     for nx, nt, ms, mt in ((256, 512, 16, 32), (128, 256, 16, 32)):
@@ -94,3 +103,69 @@ def test_what_the_tie_rule_is_worth_on_a_scaled_configs3():
         outs.append(prob.apply_S(q))
     rel = np.linalg.norm(outs[0] - outs[1]) / np.linalg.norm(outs[0])
     assert 0.05 < rel < 2.0
+
+
+# ---- the restated deal.II 9.1 candidate order (oracle/dealii_point_location.py) -----------------------------------
+def _restated(idx, subs=(0, 3), tol=1e-7):
+    from dealii_point_location import tie_points
+    prm = default_params(2, idx + 1)
+    prm.tolerance = tol
+    mesh = mo.refined_meshes(prm, 4)[idx]
+    rules = {r: {"points": tie_points(r, mesh[r][0], mesh[-1][0])} for r in subs}
+    res = mo.Problem(prm, 4, mesh[:-1], mesh[-1], tie_rules=rules).run_cycle(idx)
+    report_era = next(k for k in range(1, len(res.residuals)) if res.residuals[k] < 1e-6 * res.r_norm)
+    return res, report_era, rules
+
+
+def test_restated_candidate_order_predicts_the_lower_rule_where_row1_pins_it():
+    """Cycle 0: the only ties are on the 2- and 4-cell subdomains 1 and 2 (coordinates with one significant bit).
+    The restated order keeps every one of them in the lower cell / earlier level -- the rule that alone reproduces
+    Table 4 row 1 (test_row1_only_the_lower_rule_on_the_dyadic_subdomains) -- and the row follows digit for digit."""
+    res, report_era, rules = _restated(0, subs=(0, 1, 2, 3))
+    picks = [v for r in (1, 2) for side in rules[r]["points"].values() for v in side.values()]
+    assert len(picks) == 20 and not any(a or b for a, b in picks)
+    assert not any(rules[r]["points"][side] for r in (0, 3) for side in rules[r]["points"])  # 3 cells: no ties
+    row = GOLD["table4_quadratic_mortar"]["rows"][0]
+    assert all(float(f"{res.errors[c]:.3e}") == pytest.approx(row[c], rel=1.01e-3) for c in COLS)
+    assert report_era == row["gmres"]
+
+
+def test_row3_is_approached_by_the_restated_candidate_order():
+    row = GOLD["table4_quadratic_mortar"]["rows"][1]
+    res, report_era, _ = _restated(2)
+    default = _cycle(2, 2, None)
+    for c in COLS:
+        assert res.errors[c] == pytest.approx(row[c], rel=0.015), (c, res.errors[c], row[c])
+        assert abs(default.errors[c] / row[c] - 1) > 0.025  # the uniform lower rule is 2.6 ... 30 % off
+    assert abs(report_era - row["gmres"]) <= 1  # 35 against 34 (uniform lower rule: 36)
+
+
+@pytest.mark.slow
+def test_row5_is_approached_by_the_restated_candidate_order():
+    row = GOLD["table4_quadratic_mortar"]["rows"][2]
+    res, report_era, _ = _restated(4)
+    for c in COLS:
+        assert res.errors[c] == pytest.approx(row[c], rel=0.03), (c, res.errors[c], row[c])
+    assert abs(report_era - row["gmres"]) <= 1  # 58 against 57 (uniform lower rule: 54)
+
+
+def test_restated_candidate_order_on_a_scaled_configs3():
+    """8x8 checkerboard 8^2 x 16 / 4^2 x 8, mortar 2 x 2 x 4, degree 2: dyadic coordinates, yet under the restated
+    floating-point order a tenth of the tie points leave the lower cell (the mapped Gauss point is off the vertex by
+    an ulp) and the operator moves by ~17 %.  The reference's answer on such meshes is a property of the deal.II build;
+    the product's is the exact-arithmetic limit."""
+    from dealii_point_location import tie_points
+    prm = default_params(2)
+    mesh = [[8, 8, 16] if ((r % 8) + (r // 8)) % 2 == 0 else [4, 4, 8] for r in range(64)]
+    rules = {r: {"points": tie_points(r, mesh[r], [2, 2, 4], n0=8, n1=8)} for r in range(64)}
+    picks = [v for r in range(64) for side in rules[r]["points"].values() for v in side.values()]
+    moved = sum(1 for a, b in picks if a or b)
+    assert len(picks) == 8960 and 0.05 < moved / len(picks) < 0.2
+    q = np.random.default_rng(0).standard_normal(2 * 112 * 2 * 4 * 9)
+    outs = []
+    for tr in (None, rules):
+        prob = mo.Problem(prm, 64, mesh, [2, 2, 4], tie_rules=tr)
+        prob.setup()
+        outs.append(prob.apply_S(q))
+    rel = np.linalg.norm(outs[0] - outs[1]) / np.linalg.norm(outs[0])
+    assert 0.05 < rel < 0.5
