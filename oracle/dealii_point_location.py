@@ -4,7 +4,7 @@ TEST INFRASTRUCTURE ONLY (see mmmfe_oracle.py).  The reference samples the fine 
 through ``Functions::FEFieldFunction`` (inc/utilities.h:484), i.e. through deal.II's point location.  deal.II is a
 third-party dependency that is absent from /root/reference and unpinned (CMakeLists.txt:23 asks for >= 8.4,
 README.md:42 names 9.5.2, report.pdf of March 2020 was produced with 9.1 or older); what follows restates the published
-algorithm of the 9.1 series from memory, in IEEE double arithmetic without fused multiply-adds:
+algorithm of the 9.0/9.1 series, in IEEE double arithmetic without fused multiply-adds:
 
   * ``GridGenerator::subdivided_hyper_rectangle``: vertex i of a direction = fl(p1 + fl(i * fl((p2 - p1) / reps)));
   * ``QGauss``/``QProjector::project_to_face`` + ``MappingQGeneric`` (degree 1, hard-coded trilinear shape functions
@@ -15,14 +15,20 @@ algorithm of the 9.1 series from memory, in IEEE double arithmetic without fused
     (``cell->center()`` = sum of the 8 vertices / 8) with the normalised direction V -> point; the first cell of that
     order that contains the point is taken.
 
-On dyadic meshes every quantity above is exact, the candidates' scalar products are bitwise equal and the lower cell
-(earlier level) wins: quirk Q5, what the oracle and the product implement.  On the non-dyadic 12- and 48-cell
-subdomains 0 and 3 of report.pdf Table 4 rows 3 and 5 the products differ in the last bits and decide point by point.
-What is NOT restated (and is why the rows are approached, not reproduced): the strict ``is_inside_unit_cell`` test on
-the Newton/affine inverse map of the first candidate, whose round-off can reject it and promote the second.
+In exact arithmetic the two candidates of a tie have equal products and the lower cell (earlier level) wins: quirk
+Q5, the default of the oracle and of the product.  In floating point the mapped Gauss point (its other two abscissae
+are irrational) and the normalised centre directions carry round-off, and the last bits decide point by point --
+also on the dyadic subdomains once a coordinate has more than one significant bit.
 
-``tie_points(sub, n_fine, n_mortar)`` returns {side: {(fs, ft, q, r): (space upper?, time upper?)}} for the 2 x 2
-layout of the shipped parameter.txt, in the form ``mmmfe_oracle.Problem(..., tie_rules={sub: {"points": ...}})`` takes.
+Pinned by every golden number the reference holds for the quadratic mortar (tests/test_oracle_ties.py): with this
+rule on all four subdomains the oracle reproduces report.pdf Table 4 rows 1, 3 AND 5 in every printed digit of the
+four error columns, and their GMRES counts 18 / 34 / 57 under the report-era stop test (tests/test_oracle_golden.py).
+Not restated: the strict ``is_inside_unit_cell`` test on deal.II's inverse map (whether it is emulated with per
+direction quotients or left out changes none of the picks on these meshes); fused multiply-adds (none assumed).
+
+``tie_points(sub, n_fine, n_mortar, ...)`` returns {side: {(fs, ft, q, r): (space upper?, time upper?)}} in the form
+``mmmfe_oracle.Problem(..., tie_rules={sub: {"points": ...}})`` takes; ``Problem(..., tie_rules="dealii91")`` calls it
+for every subdomain.  3-point Gauss rule (mortar degree 2) only.
 """
 from decimal import Decimal, getcontext
 

@@ -601,7 +601,10 @@ class Problem:
     """DarcyVTProblem<2> for one refinement cycle (inc/darcy_vtdd.h:90-276; run() src/darcy_vtdd.cc:2029-2204)."""
 
     def __init__(self, prm: Params, n_sub: int, mesh, mortar, data=None, keep_solution=False, tie_rules=None):
-        """tie_rules: optional {subdomain id: {"space": ..., "time": ...}} (tests of the point-location hazard)."""
+        """tie_rules: optional {subdomain id: {"space": ..., "time": ...}} (tests of the point-location hazard), or the
+        string "dealii91": every tie decided point by point by the restated deal.II 9.1 point location
+        (dealii_point_location.py) -- the rule report.pdf Table 4 was produced with; the default is its
+        exact-arithmetic limit (lower cell, earlier level)."""
         self.prm = prm
         self.data = data or DataDefault()
         self.n0, self.n1 = find_divisors(n_sub)
@@ -611,6 +614,12 @@ class Problem:
         self.keep_solution = keep_solution
         self.subs = [Subdomain(r, self.n0, self.n1, mesh[r][0], mesh[r][1], mesh[r][2], prm, self.data)
                      for r in range(n_sub)]
+        if tie_rules == "dealii91":
+            from dealii_point_location import tie_points
+            tie_rules = {}
+            if self.k == 2:  # the 2-point rule of the linear mortar never hits a cell boundary
+                tie_rules = {r: {"points": tie_points(r, mesh[r], mortar, final_time=prm.final_time, n0=self.n0, n1=self.n1)}
+                             for r in range(n_sub)}
         for r, rule in (tie_rules or {}).items():
             if "points" in rule:  # {"points": {side: {(fs, ft, q, r): (space upper?, time upper?)}}}
                 self.subs[r].tie_points = rule["points"]
@@ -891,7 +900,7 @@ def refined_meshes(prm: Params, n_sub: int):
 
 
 def run(prm: Params, n_sub: Optional[int] = None, data=None, cycles: Optional[Sequence[int]] = None,
-        keep_solution=False, log: Optional[Callable[[str], None]] = None) -> List[CycleResult]:
+        keep_solution=False, log: Optional[Callable[[str], None]] = None, tie_rules=None) -> List[CycleResult]:
     """DarcyVTProblem::run, src/darcy_vtdd.cc:2029-2204."""
     n_sub = n_sub if n_sub is not None else len(prm.mesh) - 1
     if n_sub <= 1:
@@ -902,7 +911,7 @@ def run(prm: Params, n_sub: Optional[int] = None, data=None, cycles: Optional[Se
     for idx, mesh in enumerate(refined_meshes(prm, n_sub)):
         if cycles is not None and idx not in cycles:
             continue
-        prob = Problem(prm, n_sub, mesh[:-1], mesh[-1], data=data, keep_solution=keep_solution)
+        prob = Problem(prm, n_sub, mesh[:-1], mesh[-1], data=data, keep_solution=keep_solution, tie_rules=tie_rules)
         res = prob.run_cycle(idx)
         if log:
             log(f"cycle {idx}: gmres {res.gmres_iterations} r_norm {res.r_norm:.16g} errors {res.errors}")
