@@ -110,7 +110,7 @@ def build_host(force=False):
         hdrs += [os.path.join(d, f) for f in fs]
     deps = srcs + hdrs + [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
     data_header = os.environ.get("MMMFE_DATA_HEADER", os.path.join(HOST, "data_default.h"))
-    common = ["g++", "-O2", "-std=c++17", "-fPIC", "-fopenmp", "-I", os.path.join(ROOT, "include"),
+    common = ["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-fopenmp", "-I", os.path.join(ROOT, "include"),
               "-I", os.path.join(HOST, "shim"), "-I", HOST, f'-DMMMFE_DATA_HEADER="{data_header}"']
     build_data_device(data_header, force=force)
     if force or _newer(LIB_HOST, deps + [LIB_ENGINE, DATA_OBJ]):

@@ -101,8 +101,8 @@ struct Csr {
 
 // One subdomain: canonical dof order x-edges (i=0..nx, j) at j*(nx+1)+i, y-edges at nxe + j*nx + i, cells after.
 struct Sub {
-  int r, ix, iy, nx, ny, nt;
-  double x0, y0, Lx, Ly, hx, hy, dt;
+  int r, ix, iy, nx, ny, nt, n0 = 1, n1 = 1;
+  double x0, y0, Lx, Ly, hx, hy, dt, final_time = 0.0;
   int nxe, nye, nf, np, n;
   int nb[4], n_side[4];
   double edge_len[4];
@@ -119,7 +119,7 @@ struct Sub {
 };
 
 void init_sub(Sub &s, int r, int n0, int n1, const std::vector<int> &pat, double final_time) {
-  s.r = r; s.ix = r % n0; s.iy = r / n0;
+  s.r = r; s.ix = r % n0; s.iy = r / n0; s.n0 = n0; s.n1 = n1; s.final_time = final_time;
   s.Lx = 1.0 / n0; s.Ly = 1.0 / n1;
   s.x0 = s.ix * s.Lx;                                   // get_subdomain_coordinates, inc/utilities.h:152-157
   s.y0 = s.Ly * std::floor(double(r) / double(n0));
@@ -312,6 +312,131 @@ void finish_row(Csr &m, std::vector<int> &rc, std::vector<double> &rv) {
   rc.clear(); rv.clear();
 }
 
+// ---- MMMFE_TIE_RULE=dealii91 ---------------------------------------------------------------------------------------
+// Which fine cell a mortar Gauss point gets that lies on a fine cell boundary, decided the way deal.II's point
+// location (FEFieldFunction, inc/utilities.h:484; 9.0/9.1 series) decides it in IEEE doubles -- the rule report.pdf
+// Table 4 was produced with (all three rows, every printed digit: tests/test_oracle_ties.py pins the Python
+// restatement oracle/dealii_point_location.py, tests/test_host_frontend.py pins this one against it).  Restated:
+// subdivided_hyper_rectangle vertices fl(p1 + fl(i * fl((p2 - p1) / reps))); the mapped quadrature point as the sum
+// of the eight hard-coded trilinear shape values times the mortar cell's vertices; find_active_cell_around_point:
+// closest fine vertex, its cells in ascending index order, stably sorted by descending scalar product of the
+// normalised vertex->centre direction (centre = sum of the 8 vertices / 8) with the normalised vertex->point
+// direction; the first cell of that order that holds the point.  No fused multiply-adds (the file is built with
+// -ffp-contract=off).  Default (variable unset): the exact-arithmetic limit of this rule, lower cell / earlier level.
+bool tie_rule_dealii91() {
+  const char *v = std::getenv("MMMFE_TIE_RULE");
+  if (!v || !*v || std::string(v) == "lower" || std::string(v) == "exact") return false;
+  if (std::string(v) == "dealii91") return true;
+  throw std::runtime_error(std::string("MMMFE_TIE_RULE must be 'lower' or 'dealii91', not '") + v + "'");
+}
+
+struct Vec3 { double v[3]; };
+
+static Vec3 normalised(Vec3 t) {
+  double s = t.v[0] * t.v[0];
+  s = s + t.v[1] * t.v[1];
+  s = s + t.v[2] * t.v[2];
+  const double n = std::sqrt(s);
+  if (n > 0) for (double &x : t.v) x = x / n;
+  return t;
+}
+
+// picks[((ft * ms + fs) * 3 + r) * 3 + q]: bit 0 = space tie goes to the upper cell, bit 1 = time tie to the later level
+std::vector<unsigned char> dealii91_tie_picks(const Sub &s, int side, const std::vector<int> &mortar) {
+  static const double g[3] = {0.11270166537925831148, 0.5, 0.88729833462074168852};  // QGauss<1>(3) on [0, 1]
+  const int n_fine[3] = {s.nx, s.ny, s.nt}, n_mortar[3] = {mortar[0], mortar[1], mortar[2]};
+  // get_subdomain_coordinates, inc/utilities.h:152-157; p1_st, p2_st of src/darcy_vtdd.cc:2097
+  const double dims[2] = {1.0 / double(s.n0), 1.0 / double(s.n1)};
+  const double p1[3] = {double(s.r % s.n0) * dims[0], dims[1] * std::floor(double(s.r) / double(s.n0)), 0.0};
+  const double p2[3] = {p1[0] + dims[0], p1[1] + dims[1], s.final_time};
+  std::vector<double> fine[3], mort[3];
+  for (int a = 0; a < 3; ++a) {
+    const double df = (p2[a] - p1[a]) / double(n_fine[a]), dm = (p2[a] - p1[a]) / double(n_mortar[a]);
+    for (int i = 0; i <= n_fine[a]; ++i) fine[a].push_back(p1[a] + double(i) * df);
+    for (int i = 0; i <= n_mortar[a]; ++i) mort[a].push_back(p1[a] + double(i) * dm);
+  }
+  const int face = side == LEFT ? 0 : side == RIGHT ? 1 : side == BOTTOM ? 2 : 3;  // deal.II face of the 3-D cell
+  const int normal = face < 2 ? 0 : 1, tangent = 1 - normal;
+  const int ms = n_mortar[tangent], mnt = n_mortar[2];
+  std::vector<unsigned char> picks(size_t(ms) * mnt * 9, 0);
+  auto centre_dir = [&](const int c[3], const Vec3 &vc) {
+    Vec3 p{{0.0, 0.0, 0.0}};
+    for (int v = 0; v < 8; ++v) {
+      const int o[3] = {v & 1, (v >> 1) & 1, (v >> 2) & 1};
+      for (int a = 0; a < 3; ++a) p.v[a] = p.v[a] + fine[a][c[a] + o[a]];
+    }
+    Vec3 t;
+    for (int a = 0; a < 3; ++a) t.v[a] = p.v[a] / 8.0 - vc.v[a];
+    return normalised(t);
+  };
+  for (int cs = 0; cs < ms; ++cs)
+    for (int ct = 0; ct < mnt; ++ct)
+      for (int r = 0; r < 3; ++r)
+        for (int q = 0; q < 3; ++q) {
+          const bool tie_s = q == 1 && ((2LL * cs + 1) * n_fine[tangent]) % (2LL * n_mortar[tangent]) == 0;
+          const bool tie_t = r == 1 && ((2LL * ct + 1) * n_fine[2]) % (2LL * n_mortar[2]) == 0;
+          if (!tie_s && !tie_t) continue;
+          // QProjector::project_to_face: (face, q0, q1) on x-faces, (q1, face, q0) on y-faces; q = space, r = time
+          double unit[3];
+          int cell[3];
+          if (face < 2) { unit[0] = double(face); unit[1] = g[q]; unit[2] = g[r]; cell[0] = face == 0 ? 0 : n_mortar[0] - 1; cell[1] = cs; }
+          else { unit[0] = g[q]; unit[1] = double(face - 2); unit[2] = g[r]; cell[0] = cs; cell[1] = face == 2 ? 0 : n_mortar[1] - 1; }
+          cell[2] = ct;
+          const double x = unit[0], y = unit[1], z = unit[2];
+          const double shape[8] = {(1. - x) * (1. - y) * (1. - z), x * (1. - y) * (1. - z), (1. - x) * y * (1. - z),
+                                   x * y * (1. - z), (1. - x) * (1. - y) * z, x * (1. - y) * z, (1. - x) * y * z, x * y * z};
+          Vec3 p;
+          for (int a = 0; a < 3; ++a) p.v[a] = shape[0] * mort[a][cell[a]];
+          for (int v = 1; v < 8; ++v) {
+            const int o[3] = {v & 1, (v >> 1) & 1, (v >> 2) & 1};
+            for (int a = 0; a < 3; ++a) p.v[a] = p.v[a] + shape[v] * mort[a][cell[a] + o[a]];
+          }
+          int idx[3];
+          Vec3 vc;
+          for (int a = 0; a < 3; ++a) {
+            int best = 0;
+            for (int i = 1; i <= n_fine[a]; ++i)
+              if (std::fabs(p.v[a] - fine[a][i]) < std::fabs(p.v[a] - fine[a][best])) best = i;
+            idx[a] = best; vc.v[a] = fine[a][best];
+          }
+          Vec3 to_point;
+          for (int a = 0; a < 3; ++a) to_point.v[a] = p.v[a] - vc.v[a];
+          to_point = normalised(to_point);
+          struct Cand { int c[3]; double prod; };
+          std::vector<Cand> cand;
+          for (int dk = -1; dk <= 0; ++dk)      // ascending cell index: time slowest, x fastest
+            for (int dj = -1; dj <= 0; ++dj)
+              for (int di = -1; di <= 0; ++di) {
+                Cand cd{{idx[0] + di, idx[1] + dj, idx[2] + dk}, 0.0};
+                bool in = true;
+                for (int a = 0; a < 3; ++a) in = in && cd.c[a] >= 0 && cd.c[a] < n_fine[a];
+                if (!in) continue;
+                const Vec3 d = centre_dir(cd.c, vc);
+                double sp = d.v[0] * to_point.v[0];
+                sp = sp + d.v[1] * to_point.v[1];
+                sp = sp + d.v[2] * to_point.v[2];
+                cd.prod = sp;
+                cand.push_back(cd);
+              }
+          std::stable_sort(cand.begin(), cand.end(), [](const Cand &a, const Cand &b) { return a.prod > b.prod; });
+          const Cand *chosen = nullptr;
+          for (const Cand &cd : cand) {
+            bool holds = true;
+            for (int a = 0; a < 3; ++a)
+              if (a != normal) holds = holds && fine[a][cd.c[a]] <= p.v[a] && p.v[a] <= fine[a][cd.c[a] + 1];
+            if (holds) { chosen = &cd; break; }
+          }
+          if (!chosen) throw std::runtime_error("dealii91 tie rule: no cell holds a mortar Gauss point");
+          const long long s_vertex = (2LL * cs + 1) * n_fine[tangent] / (2LL * n_mortar[tangent]);
+          const long long t_vertex = (2LL * ct + 1) * n_fine[2] / (2LL * n_mortar[2]);
+          unsigned char bits = 0;
+          if (tie_s && chosen->c[tangent] == s_vertex) bits |= 1;
+          if (tie_t && chosen->c[2] == t_vertex) bits |= 2;
+          picks[((size_t(ct) * ms + cs) * 3 + r) * 3 + q] = bits;
+        }
+  return picks;
+}
+
 // project_mortar as two explicit sampling operators (inc/utilities.h:471-505, inc/projector.h:150-207, 445-524;
 // SURVEY.md appendix A.4).  Mortar layout ((ft*ms + fs)*(k+1) + b)*(k+1) + a; fine layout level*n_side + m.
 void projector_tables(Sub &s, int side, const std::vector<int> &mortar, int k) {
@@ -330,15 +455,22 @@ void projector_tables(Sub &s, int side, const std::vector<int> &mortar, int k) {
   std::vector<int> rc;
   std::vector<double> rv;
   // f2c: Gauss points of each mortar face sample the piecewise-constant fine normal flux U/|e|
+  std::vector<unsigned char> picks;  // MMMFE_TIE_RULE=dealii91: per-point tie choices (3-point rule only)
+  if (k == 2 && tie_rule_dealii91()) picks = dealii91_tie_picks(s, side, mortar);
   const double coef = H * T / e_len;
   for (int ft = 0; ft < mnt; ++ft)
     for (int fs = 0; fs < ms; ++fs)
       for (int b = 0; b < nq; ++b)
         for (int a = 0; a < nq; ++a) {
           for (int r = 0; r < nq; ++r) {
-            const int lvl = locate((ft + xi[r]) / mnt * nt, nt);
+            const int lvl0 = locate((ft + xi[r]) / mnt * nt, nt);
             for (int q = 0; q < nq; ++q) {
-              const int m = locate((fs + xi[q]) / ms * ns, ns);
+              int m = locate((fs + xi[q]) / ms * ns, ns), lvl = lvl0;
+              if (!picks.empty()) {
+                const unsigned char bits = picks[((size_t(ft) * ms + fs) * 3 + r) * 3 + q];
+                if (bits & 1) m = std::min(m + 1, ns - 1);
+                if (bits & 2) lvl = std::min(lvl + 1, nt - 1);
+              }
               push_merged(rc, rv, lvl * ns + m, coef * w[q] * w[r] * leg[a * nq + q] * leg[b * nq + r]);
             }
           }

@@ -55,6 +55,49 @@ def test_front_end_setup_matches_oracle(k, cycle):
     _check_setup_against_oracle(os.path.join(ROOT, "parameter.txt"), make_problem(prm, cycle), k, cycle)
 
 
+@pytest.mark.parametrize("cycle", [0, 1, 2, 3])
+def test_front_end_dealii91_tie_rule_matches_oracle(monkeypatch, cycle):
+    """MMMFE_TIE_RULE=dealii91: the C++ restatement of deal.II's point location picks the same cell as the oracle's
+    (oracle/dealii_point_location.py, pinned to report.pdf Table 4 rows 1, 3, 5) at every tie point -- the tables
+    are compared entry for entry -- and differs from the default rule from cycle 1 on."""
+    monkeypatch.setenv("MMMFE_TIE_RULE", "dealii91")
+    prm = default_params(2, cycle + 1)
+    mesh = mo.refined_meshes(prm, 4)[cycle]
+    prob = mo.Problem(prm, 4, mesh[:-1], mesh[-1], keep_solution=True, tie_rules="dealii91")
+    prob.setup()
+    _check_setup_against_oracle(os.path.join(ROOT, "parameter.txt"), prob, 2, cycle)
+    ref = make_problem(prm, cycle)
+    moved = sum(_maxdiff(a.f2c[s], b.f2c[s]) > 0 for a, b in zip(prob.subs, ref.subs) for s in a.f2c)
+    assert (moved > 0) == (cycle >= 1)
+
+
+def test_front_end_dealii91_tie_rule_on_an_8x8_layout(monkeypatch, tmp_path):
+    """The same on the scaled-down configs[3] (8 x 8 checkerboard, non-cubic meshes, every side type)."""
+    monkeypatch.setenv("MMMFE_TIE_RULE", "dealii91")
+    mesh = [[8, 8, 16] if ((r % 8) + (r // 8)) % 2 == 0 else [4, 4, 8] for r in range(64)]
+    p = pkg().write_parameter_file(str(tmp_path / "parameter.txt"), mesh, [2, 2, 4], mortar_degree=2)
+    prm = mo.parse_parameter_file(p)
+    prob = mo.Problem(prm, 64, mesh, [2, 2, 4], tie_rules="dealii91")
+    lib = pkg().load_host()
+    for r in (0, 7, 9, 27, 36, 63):
+        sd = prob.subs[r]
+        with tempfile.TemporaryDirectory() as d:
+            assert lib.mmmfe_host_dump_subdomain(p.encode(), 0, r, 2, d.encode()) == 0, lib.mmmfe_host_last_error()
+            for side in range(4):
+                if sd.neighbors[side] < 0:
+                    continue
+                f2c, _ = mo.projector_tables(sd, side, [2, 2, 4], 2)
+                assert _maxdiff(_load_csr(d, f"f2c{side}"), f2c) < 1e-13 * abs(f2c).max(), (r, side)
+
+
+def test_front_end_rejects_an_unknown_tie_rule(monkeypatch):
+    monkeypatch.setenv("MMMFE_TIE_RULE", "nearest")
+    lib = pkg().load_host()
+    with tempfile.TemporaryDirectory() as d:
+        assert lib.mmmfe_host_dump_subdomain(os.path.join(ROOT, "parameter.txt").encode(), 0, 0, 2, d.encode()) != 0
+        assert b"MMMFE_TIE_RULE" in lib.mmmfe_host_last_error()
+
+
 @pytest.mark.parametrize("bc", [("N 0.5", "D 1.0", "D 2.0", "N -0.25"), ("D 1.0", "N 0.0", "N 1.5", "D 0.0")])
 def test_front_end_neumann_sides_match_oracle(tmp_path, bc):
     """is_manufact_soln = 0 with essential (Neumann) outer sides: constrained matrix, system_rhs_bar_bc and the
