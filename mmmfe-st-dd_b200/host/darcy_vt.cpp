@@ -1159,6 +1159,7 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
         for (int side = 0; side < 4; ++side)
           if (subs[li]->nb[side] >= 0 || world > 1) jobs.push_back({li, side});
       const auto t1 = clk::now();
+      (void)tie_rule_dealii91();  // an invalid MMMFE_TIE_RULE is reported here, not from inside the parallel loop
 #pragma omp parallel for schedule(dynamic)
       for (int q = 0; q < int(jobs.size()); ++q) projector_tables(*subs[jobs[q].first], jobs[q].second, mortar, int(mortar_degree));
       if (host_prof) std::fprintf(stderr, "[setup profile] host: projector tables %8.1f ms\n", since(t1) * 1e3);
