@@ -67,8 +67,9 @@ def test_published_gmres_counts_follow_from_the_residual_history(cycle):
     is ONE scaling in the stop test and nothing else: the first k with residual_k / r_norm < tol (i.e. the scaled
     residual of :1478 divided once more by r_norm; r_norm = 4.13, 2.30, 1.50, 0.92, 0.60 over the cycles, which is
     why the published count is smaller in cycles 0-2, equal in cycle 3 and larger in cycle 4) is the published
-    count in every row whose errors the oracle reproduces -- 5 of Table 2 and row 1 of Table 4.  The residual
-    HISTORY of the oracle is therefore pinned to the report by six integers, two of them with a margin of a few
+    count in every published row -- 5 of Table 2 here, 3 of Table 4 (rows 3 and 5 with the deal.II tie rule) in
+    tests/test_oracle_ties.py.  The residual HISTORY of the oracle is therefore pinned to the report by eight
+    integers, two of them with a margin of a few
     per cent (cycle 3: 8.72e-7 < 9.22e-7 <= 1.011e-6, cycle 4: 5.81e-7 < 5.95e-7 <= 6.56e-7); what is left open
     is only which scaling the March-2020 binary used (:1289 still carries `// r_norm; scaled residual`)."""
     now, then, res = _both_counts(1, cycle)
@@ -90,7 +91,7 @@ def test_published_count_of_table2_row5_follows_from_the_residual_history():
 
 def test_table4_quadratic_mortar_cycle_0():
     """Quadratic mortar: reproduced only with the lower-cell / earlier-level tie rule (quirk Q5); rows 3 and 5 are
-    bracketed, not reproduced -- see tests/test_oracle_ties.py for why."""
+    reproduced with the restated deal.II tie rule -- tests/test_oracle_ties.py."""
     res = mo.run(_params(2, 1))
     _check_row(res[0], GOLD["table4_quadratic_mortar"]["rows"][0], its_slack=1)
 

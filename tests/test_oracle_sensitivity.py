@@ -42,7 +42,7 @@ def test_iteration_count_of_table2_row5_is_not_a_roundoff_effect():
     """Cycle 4: 82 iterations here against 86 in report.pdf Table 2.  Perturbing every operator application by up
     to 1e-8 relative leaves the count at 82 (1e-7: 83) and moves lambda by ~150 eps, so the published 86 is not
     explained by solver round-off (UMFPACK vs SuperLU).  It is explained by the scaling of the stop test the
-    March-2020 report was produced with (residual_k / r_norm < tol: tests/test_oracle_golden.py reproduces all six
+    March-2020 report was produced with (residual_k / r_norm < tol: tests/test_oracle_golden.py and tests/test_oracle_ties.py reproduce all eight
     published counts from the oracle's residual history).  The error columns agree in every printed digit."""
     its0, rows = _spread(4, [1e-12, 1e-8], seeds=(1,))
     assert its0 == 82
