@@ -456,7 +456,10 @@ void projector_tables(Sub &s, int side, const std::vector<int> &mortar, int k) {
   std::vector<double> rv;
   // f2c: Gauss points of each mortar face sample the piecewise-constant fine normal flux U/|e|
   std::vector<unsigned char> picks;  // MMMFE_TIE_RULE=dealii91: per-point tie choices (3-point rule only)
-  if (k == 2 && tie_rule_dealii91()) picks = dealii91_tie_picks(s, side, mortar);
+  if (k % 2 == 0 && tie_rule_dealii91()) {  // odd-point Gauss rules have a centre abscissa that can hit a cell boundary
+    if (k != 2) throw std::runtime_error("MMMFE_TIE_RULE=dealii91 is restated for mortar_degree 2 only");
+    picks = dealii91_tie_picks(s, side, mortar);
+  }
   const double coef = H * T / e_len;
   for (int ft = 0; ft < mnt; ++ft)
     for (int fs = 0; fs < ms; ++fs)
@@ -1159,7 +1162,9 @@ void DarcyVTProblem<dim>::run(const unsigned int refine, const std::vector<std::
         for (int side = 0; side < 4; ++side)
           if (subs[li]->nb[side] >= 0 || world > 1) jobs.push_back({li, side});
       const auto t1 = clk::now();
-      (void)tie_rule_dealii91();  // an invalid MMMFE_TIE_RULE is reported here, not from inside the parallel loop
+      // an invalid MMMFE_TIE_RULE is reported here, not from inside the parallel loop
+      if (tie_rule_dealii91() && mortar_degree % 2 == 0 && mortar_degree != 2)
+        throw std::runtime_error("MMMFE_TIE_RULE=dealii91 is restated for mortar_degree 2 only");
 #pragma omp parallel for schedule(dynamic)
       for (int q = 0; q < int(jobs.size()); ++q) projector_tables(*subs[jobs[q].first], jobs[q].second, mortar, int(mortar_degree));
       if (host_prof) std::fprintf(stderr, "[setup profile] host: projector tables %8.1f ms\n", since(t1) * 1e3);

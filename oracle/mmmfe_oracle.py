@@ -617,7 +617,9 @@ class Problem:
         if tie_rules == "dealii91":
             from dealii_point_location import tie_points
             tie_rules = {}
-            if self.k == 2:  # the 2-point rule of the linear mortar never hits a cell boundary
+            if self.k % 2 == 0 and self.k != 2:
+                raise ValueError("the dealii91 tie rule is restated for mortar degree 2 only")
+            if self.k == 2:  # even-point Gauss rules (odd degrees) never hit a cell boundary
                 tie_rules = {r: {"points": tie_points(r, mesh[r], mortar, final_time=prm.final_time, n0=self.n0, n1=self.n1)}
                              for r in range(n_sub)}
         for r, rule in (tie_rules or {}).items():
