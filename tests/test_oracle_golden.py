@@ -38,7 +38,6 @@ def test_table2_linear_mortar_cycles_0_to_3():
         _check_row(r, row, its_slack=1)
 
 
-@pytest.mark.slow
 def test_table2_linear_mortar_cycle_4():
     res = mo.run(_params(1, 5), cycles=[4])
     # errors match in every digit; 82 iterations against 86 published: the report-era stop test was scaled by
@@ -82,7 +81,6 @@ def test_published_count_of_table4_row1_follows_from_the_residual_history():
     assert (now, then) == (19, GOLD["table4_quadratic_mortar"]["rows"][0]["gmres"])
 
 
-@pytest.mark.slow
 def test_published_count_of_table2_row5_follows_from_the_residual_history():
     now, then, res = _both_counts(1, 4)
     assert (now, then) == (82, 86) and GOLD["table2_linear_mortar"]["rows"][4]["gmres"] == 86

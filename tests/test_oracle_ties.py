@@ -146,7 +146,6 @@ def test_row3_is_reproduced_by_the_restated_candidate_order():
     assert not _digits(default, row) and all(abs(default.errors[c] / row[c] - 1) > 0.025 for c in COLS)
 
 
-@pytest.mark.slow
 def test_row5_is_reproduced_by_the_restated_candidate_order():
     """Table 4 row 5 (cycle 4, 48- and 64-cell subdomains): every printed digit and the published count 57 -- the
     out-of-sample row (the restatement was written against row 3)."""
