@@ -44,20 +44,6 @@ def test_report_tables_through_the_product_path():
     assert abs(reps[0]["gmres_iterations"] - row["gmres"]) <= 1
 
 
-def test_report_table4_all_rows_with_the_dealii91_tie_rule(monkeypatch):
-    """report.pdf Table 4 rows 1, 3 AND 5 (cycles 0, 2, 4), every printed digit, from the CUDA path: with
-    MMMFE_TIE_RULE=dealii91 the front-end assigns the quadratic mortar's tie points the way deal.II's point location
-    does.  GMRES counts of the current stop rule as the oracle gives them under the same rule
-    (19 / 38 / 60; the published 18 / 34 / 57 are the report-era rule, tests/test_oracle_ties.py)."""
-    monkeypatch.setenv("MMMFE_TIE_RULE", "dealii91")
-    reps, _, _ = pkg().host_run(os.path.join(ROOT, "parameter.txt"), verbose=0, write_output=0, num_refinement=5,
-                                mortar_degree=2)
-    assert [r["gmres_iterations"] for r in reps] == [19, 24, 38, 38, 60]
-    for cycle, row in zip((0, 2, 4), GOLD["table4_quadratic_mortar"]["rows"]):
-        for c in COLS:
-            assert float(f"{reps[cycle][c]:.3e}") == pytest.approx(row[c], rel=1.01e-3), (cycle, c, reps[cycle][c])
-
-
 @pytest.mark.parametrize("mortar_degree,cycle,published", [(1, 0, 11), (1, 1, 23), (1, 2, 39), (1, 3, 59), (2, 0, 18)])
 def test_published_gmres_counts_from_the_product_residual_history(tmp_path, mortar_degree, cycle, published):
     """report.pdf prints the first k with residual_k / r_norm < tol (the relative residual of
