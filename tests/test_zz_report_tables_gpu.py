@@ -24,3 +24,28 @@ def test_report_table4_all_rows_with_the_dealii91_tie_rule(monkeypatch):
     for cycle, row in zip((0, 2, 4), GOLD["table4_quadratic_mortar"]["rows"]):
         for c in COLS:
             assert float(f"{reps[cycle][c]:.3e}") == pytest.approx(row[c], rel=1.01e-3), (cycle, c, reps[cycle][c])
+
+
+@pytest.mark.parametrize("name,degree,rule", [("linear", 1, None), ("quadratic_lower", 2, None),
+                                              ("quadratic_dealii91", 2, "dealii91")])
+def test_product_against_the_committed_oracle_vectors(monkeypatch, name, degree, rule):
+    """The CUDA path against tests/golden/oracle_vectors.json (full-precision oracle outputs of the shipped
+    parameter.txt, three cycles, both tie rules) -- no oracle code runs here: counts equal, r_norm 1e-12, error columns
+    1e-9, residual history 1e-6, lambda of the last cycle 1e-8 relative l2."""
+    import numpy as np
+    vec = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_vectors.json")))[name]
+    if rule:
+        monkeypatch.setenv("MMMFE_TIE_RULE", rule)
+    else:
+        monkeypatch.delenv("MMMFE_TIE_RULE", raising=False)
+    reps, res, lam = pkg().host_run(os.path.join(ROOT, "parameter.txt"), verbose=0, write_output=0, num_refinement=3,
+                                    mortar_degree=degree)
+    assert len(reps) == 3
+    for r, g in zip(reps, vec):
+        assert r["gmres_iterations"] == g["gmres_iterations"]
+        assert r["r_norm"] == pytest.approx(g["r_norm"], rel=1e-12)
+        for c in COLS:
+            assert r[c] == pytest.approx(g["errors"][c], rel=1e-9), c
+    np.testing.assert_allclose(res, vec[-1]["residuals"], rtol=1e-6, atol=1e-13)
+    ref = np.asarray(vec[-1]["lambda"])
+    assert np.linalg.norm(np.asarray(lam) - ref) <= 1e-8 * np.linalg.norm(ref)
