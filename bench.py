@@ -439,6 +439,11 @@ def main():
                 r4[key] = v
             rec = solve_record(r4, ds4)
             rec["workload"] = text4 + (" -- ONE GPU's share of the 64-subdomain problem" if a.gpus == 1 else "")
+            rec["tie_rule"] = (os.environ.get("MMMFE_TIE_RULE") or "lower") + (
+                " (quadratic mortar: centre Gauss points on fine cell boundaries sample the lower cell / earlier level, "
+                "the exact-arithmetic limit of deal.II's point location; MMMFE_TIE_RULE=dealii91 = its floating-point "
+                "choice, under which the operator is not time-Toeplitz and the engine falls back to the star sweeps; "
+                "DESIGN.md section 6)")
             rec["ms_per_iteration_device_timed_20_fixed"] = r4["gmres_device_ms"] / 20
             rec["gmres_solves_per_s"] = 1.0 / max(r4["t_solve_gmres"], 1e-12)
             rec["solve_darcy_vt_per_s"] = 1.0 / max(rec["time_to_solution_s"], 1e-12)
