@@ -90,6 +90,34 @@ def test_front_end_dealii91_tie_rule_on_an_8x8_layout(monkeypatch, tmp_path):
                 assert _maxdiff(_load_csr(d, f"f2c{side}"), f2c) < 1e-13 * abs(f2c).max(), (r, side)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_front_end_dealii91_tie_rule_on_random_layouts(monkeypatch, tmp_path, seed):
+    """Random decompositions (also 3 x 2 and 1 x 3: subdomain widths of 1/3), non-cubic meshes, mortar meshes with
+    ties in space and time, final times 0.3 / 0.5 / 1: every f2c table of the C++ restatement equals the oracle's."""
+    monkeypatch.setenv("MMMFE_TIE_RULE", "dealii91")
+    rng = np.random.default_rng(seed)
+    n0, n1 = [(3, 2), (2, 3), (1, 3), (4, 2)][seed]
+    mort = [int(rng.integers(1, 4)) for _ in range(3)]
+    mesh = [[mort[0] * 2 * int(rng.integers(1, 4)), mort[1] * 2 * int(rng.integers(1, 4)), mort[2] * 2 * int(rng.integers(1, 3))]
+            for _ in range(n0 * n1)]
+    p = pkg().write_parameter_file(str(tmp_path / "parameter.txt"), mesh, mort, mortar_degree=2,
+                                   final_time=float(rng.choice([0.5, 1.0, 0.3])))
+    prob = mo.Problem(mo.parse_parameter_file(p), n0 * n1, mesh, mort, tie_rules="dealii91")
+    lib = pkg().load_host()
+    sides = moved = 0
+    for sd in prob.subs:
+        with tempfile.TemporaryDirectory() as d:
+            assert lib.mmmfe_host_dump_subdomain(p.encode(), 0, sd.r, 2, d.encode()) == 0, lib.mmmfe_host_last_error()
+            for side in range(4):
+                if sd.neighbors[side] < 0:
+                    continue
+                f2c, _ = mo.projector_tables(sd, side, mort, 2)
+                assert _maxdiff(_load_csr(d, f"f2c{side}"), f2c) < 1e-13 * abs(f2c).max(), (sd.r, side)
+                sides += 1
+                moved += sum(1 for v in sd.tie_points.get(side, {}).values() if any(v))
+    assert sides >= 4 and moved > 0
+
+
 def test_front_end_rejects_an_unknown_tie_rule(monkeypatch):
     monkeypatch.setenv("MMMFE_TIE_RULE", "nearest")
     lib = pkg().load_host()
